@@ -1,0 +1,137 @@
+/*
+ * krasis_b200 — C ABI of the B200-native MoE prefill path (drop-in boundary).
+ *
+ * Every entry point replaces one reference interface on the prefill hot path; the citation after
+ * each declaration is the reference call site / PyO3 method it stands in for (paths relative to the
+ * reference tree).  Conventions:
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - `*_dev` pointers are device memory owned by the caller, `*_host` pointers are host memory;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*) and performs no hidden
+ *     device synchronisation, except the `_host` convenience calls which synchronise before returning;
+ *   - return value 0 = ok; non-zero = error, text via kb2_last_error() (thread-local).
+ *     KB2_ERR_STATE mirrors the reference's PyRuntimeError ("Model not loaded", "GPU weights not
+ *     available"), KB2_ERR_VALUE mirrors PyValueError for size/shape mismatch
+ *     (src/moe.rs:1543-1550,1790-1803,2285-2300), KB2_ERR_CUDA wraps a CUDA runtime error.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with KB2_ERR_CUDA.
+ */
+#ifndef KRASIS_B200_H
+#define KRASIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KB2_API __attribute__((visibility("default")))
+#else
+#define KB2_API
+#endif
+
+#define KB2_OK 0
+#define KB2_ERR_STATE 1
+#define KB2_ERR_VALUE 2
+#define KB2_ERR_CUDA 3
+
+#define KB2_SCORE_SOFTMAX 0 /* softmax over all experts, then top-k   (python/krasis/layer.py:548-558) */
+#define KB2_SCORE_SIGMOID 1 /* sigmoid (+ selection-only bias)         (python/krasis/layer.py:540-547) */
+#define KB2_SCORE_TOPK_SOFTMAX 2 /* GPT-OSS: top-k on logits, softmax of the k (layer.py:536-539) */
+
+#define KB2_FMT_INT4_G128 0 /* Krasis symmetric INT4, group 128 (src/weights/marlin.rs:145-207) */
+#define KB2_FMT_INT8_G128 1 /* Krasis symmetric INT8, group 128 (src/weights/marlin.rs:65-114)  */
+
+typedef struct kb2_engine kb2_engine;
+
+/* Mirrors the constructor arguments of GpuPrefillManager (python/krasis/gpu_prefill.py:326-346) plus
+ * the routing configuration KrasisEngine.set_routing_config takes (src/moe.rs:2959). */
+typedef struct kb2_config {
+  int32_t hidden_size;            /* H */
+  int32_t moe_intermediate_size;  /* I */
+  int32_t n_routed_experts;       /* E (global) */
+  int32_t num_experts_per_tok;    /* top-k */
+  int32_t num_moe_layers;
+  int32_t weight_format;          /* KB2_FMT_* */
+  int32_t rank;                   /* EP: this engine owns experts [rank*(E/R), (rank+1)*(E/R)), last rank takes */
+  int32_t num_ranks;              /*     the remainder — python/krasis/gpu_prefill.py:353-359                   */
+  int32_t scoring_func;           /* KB2_SCORE_* */
+  int32_t norm_topk_prob;         /* 0/1 */
+  float routed_scaling_factor;
+  int32_t max_tokens;             /* largest M a forward call may pass (sizes the scratch buffers) */
+  int32_t device;                 /* CUDA device ordinal; forward calls cudaSetDevice(device) like gpu_prefill.py:4401 */
+} kb2_config;
+
+/* lifecycle — KrasisEngine(...) + GpuPrefillManager(...) (src/moe.rs:1482, gpu_prefill.py:326) */
+KB2_API int kb2_create(const kb2_config* cfg, kb2_engine** out);
+KB2_API void kb2_destroy(kb2_engine* e);
+KB2_API const char* kb2_last_error(void);
+KB2_API const char* kb2_version(void);
+
+/* introspection — KrasisEngine.num_moe_layers/hidden_size/num_experts/top_k/group_size/intermediate_size/
+ * gpu_num_bits (src/moe.rs:1874-1965) and GpuPrefillManager.expert_start/expert_end */
+KB2_API int kb2_get_config(const kb2_engine* e, kb2_config* out);
+KB2_API int kb2_expert_range(const kb2_engine* e, int32_t* expert_start, int32_t* expert_end);
+
+/* Bytes of one layer's LOCAL experts in the B200 tile layout: which = 0 w13 packed, 1 w13 scales,
+ * 2 w2 packed, 3 w2 scales.  (Counterpart of the per-expert sizes in src/weights/mod.rs:955-970.) */
+KB2_API size_t kb2_tiled_bytes(const kb2_engine* e, int which);
+
+/* Weight hand-off, host side — replaces KrasisEngine.get_expert_{w13_packed,w13_scales,w2_packed,
+ * w2_scales} / write_experts_range_into_pinned (src/moe.rs:1972-2097,2431) followed by the H2D copy in
+ * GpuPrefillManager (gpu_prefill.py:1059-1062).  Inputs are the reference QUANTISER's outputs for the
+ * local experts (src/weights/marlin.rs:145-207, 65-114), row-major [E_local][N][K/8] u32 (INT4) or
+ * [E_local][N][K] i8 (INT8) with scales [E_local][N][K/128] bf16; w13 = [gate rows ; up rows]
+ * (src/weights/mod.rs:346-349).  The engine re-tiles them on the device and owns the result. */
+KB2_API int kb2_load_experts_host(kb2_engine* e, int moe_layer_idx, const void* w13_q_host, const void* w13_s_host,
+                          const void* w2_q_host, const void* w2_s_host);
+
+/* Same, but the caller already holds device buffers in the B200 tile layout (sizes = kb2_tiled_bytes);
+ * the engine only records the pointers (caller keeps ownership).  Used to build synthetic full-size
+ * models without a host copy — the analogue of the persistent-expert buffers gpu_prefill.py:4128-4137. */
+KB2_API int kb2_attach_experts_tiled_dev(kb2_engine* e, int moe_layer_idx, const void* w13_q_dev, const void* w13_s_dev,
+                                 const void* w2_q_dev, const void* w2_s_dev);
+
+/* Re-tile on the device without attaching (exposed so tests can check the layout transform). */
+KB2_API int kb2_retile_dev(kb2_engine* e, int weight_format, const void* src_q_dev, const void* src_s_dev, void* dst_q_dev,
+                   void* dst_s_dev, int n_experts, int n_rows, int k_cols, void* stream);
+
+/* Router weights — KrasisEngine.set_routing_weights(layer, gate_bf16, bias_f32) (src/moe.rs:2989) and the
+ * layer attributes gate_weight / gate_bias / e_score_correction_bias (python/krasis/layer.py:526-560).
+ * gate: [E][H] bf16; gate_bias, e_score_correction_bias: [E] f32 or NULL. */
+KB2_API int kb2_set_router_host(kb2_engine* e, int moe_layer_idx, const void* gate_bf16_host, const float* gate_bias_host,
+                        const float* e_score_correction_bias_host);
+
+/* TransformerLayer.compute_routing (python/krasis/layer.py:526-560): hidden [M][H] bf16 ->
+ * topk_ids [M][k] int32 (descending score, ties -> lower expert index), topk_weights [M][k] f32. */
+KB2_API int kb2_route(kb2_engine* e, int moe_layer_idx, const void* hidden_dev, int32_t num_tokens, int32_t* topk_ids_dev,
+              float* topk_weights_dev, void* stream);
+
+/* GpuPrefillManager.forward(moe_layer_idx, hidden_states, topk_ids, topk_weights, routed_only)
+ * (python/krasis/gpu_prefill.py:4374-4484): x [M][H] bf16, ids [M][k] int32 (GLOBAL expert ids; ids outside
+ * this engine's expert range, or negative, contribute zero — gpu_prefill.py:4140-4149, src/moe.rs:2722),
+ * weights [M][k] f32 -> out [M][H] bf16.  routed_only=1 returns the raw routed sum (EP partial sums);
+ * otherwise out = bf16(rsf * routed) (+ shared_dev [M][H] bf16 if not NULL), gpu_prefill.py:4467-4482. */
+KB2_API int kb2_moe_forward(kb2_engine* e, int moe_layer_idx, const void* x_dev, const int32_t* topk_ids_dev,
+                    const float* topk_weights_dev, void* out_dev, int32_t num_tokens, int32_t routed_only,
+                    const void* shared_dev, void* stream);
+
+/* Host-buffer variant of route + forward for callers that hold activations in (pinned) host memory —
+ * the shape of KrasisEngine.submit_forward/sync_forward (src/moe.rs:2722,2809: bytes in, bytes out).
+ * If topk_ids_host is NULL the engine routes with its own router weights.  Copies H2D, computes,
+ * copies D2H and synchronises `stream` before returning. */
+KB2_API int kb2_moe_forward_host(kb2_engine* e, int moe_layer_idx, const void* x_host, const int32_t* topk_ids_host,
+                         const float* topk_weights_host, void* out_host, int32_t num_tokens, int32_t routed_only,
+                         void* stream);
+
+/* Introspection for tests / profiling: after a forward, copies the per-local-expert token counts
+ * (int32 [E_local]) of the last call to host. */
+KB2_API int kb2_last_expert_counts(kb2_engine* e, int32_t* counts_host, void* stream);
+
+/* Number of kernels this library has launched since creation (bench.py reports it as gpu_launches). */
+KB2_API int64_t kb2_launch_count(const kb2_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRASIS_B200_H */

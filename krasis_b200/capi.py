@@ -1,0 +1,78 @@
+"""ctypes binding of include/krasis_b200.h — the same stub a maintainer of the reference would add
+(INTEGRATION.md).  No fallback: if the CUDA library is missing or fails to load, importing the compute
+entry points raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libkrasis_b200.so")
+
+KB2_OK, KB2_ERR_STATE, KB2_ERR_VALUE, KB2_ERR_CUDA = 0, 1, 2, 3
+SCORE_SOFTMAX, SCORE_SIGMOID, SCORE_TOPK_SOFTMAX = 0, 1, 2
+FMT_INT4_G128, FMT_INT8_G128 = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("hidden_size", C.c_int32), ("moe_intermediate_size", C.c_int32), ("n_routed_experts", C.c_int32),
+        ("num_experts_per_tok", C.c_int32), ("num_moe_layers", C.c_int32), ("weight_format", C.c_int32),
+        ("rank", C.c_int32), ("num_ranks", C.c_int32), ("scoring_func", C.c_int32),
+        ("norm_topk_prob", C.c_int32), ("routed_scaling_factor", C.c_float), ("max_tokens", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/krasis_b200.h declares
+SIGNATURES = {
+    "kb2_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "kb2_destroy": (None, [C.c_void_p]),
+    "kb2_last_error": (C.c_char_p, []),
+    "kb2_version": (C.c_char_p, []),
+    "kb2_get_config": (C.c_int, [C.c_void_p, C.POINTER(Config)]),
+    "kb2_expert_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "kb2_tiled_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "kb2_load_experts_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
+    "kb2_attach_experts_tiled_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
+    "kb2_retile_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
+    "kb2_set_router_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kb2_route": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kb2_moe_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "kb2_moe_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "kb2_last_expert_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kb2_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library (works without a GPU; compute calls then fail with KB2_ERR_CUDA)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m krasis_b200.build` "
+                "(krasis_b200 has no CPU or PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the header and the library disagree
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class Kb2Error(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    """Map C error codes onto the exception types the reference's PyO3 layer raises
+    (PyRuntimeError for state, PyValueError for shape — src/moe.rs:1543-1550,2285-2300)."""
+    if rc == KB2_OK:
+        return
+    msg = load().kb2_last_error().decode()
+    if rc == KB2_ERR_VALUE:
+        raise ValueError(msg)
+    raise Kb2Error(msg)

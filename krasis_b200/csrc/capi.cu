@@ -1,0 +1,359 @@
+// C-ABI implementation (include/krasis_b200.h).  Host-side engine state + kernel orchestration.
+// The reference keeps this state in Rust (`KrasisEngine`, src/moe.rs:1377-3296) and Python
+// (`GpuPrefillManager`, python/krasis/gpu_prefill.py:326-4484); here it is C++ behind a C boundary.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/krasis_b200.h"
+#include "moe_common.cuh"
+
+namespace kb2 {
+cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_router_logits(const void* h, const void* gate, const float* bias, float* logits, int M, int E,
+                                 int H, cudaStream_t s);
+cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int M, int E, int top_k, int scoring,
+                               int renorm, int* ids, float* wts, cudaStream_t s);
+cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
+                           int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, int* sorted_token,
+                           float* sorted_w, int* slot_of, cudaStream_t s);
+cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
+                           const void* shared, void* out, cudaStream_t s);
+cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,
+                          cudaStream_t s);
+}  // namespace kb2
+
+using namespace kb2;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return fail(KB2_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+struct LayerWeights {
+  const uint8_t* w13_q = nullptr;
+  const uint8_t* w13_s = nullptr;
+  const uint8_t* w2_q = nullptr;
+  const uint8_t* w2_s = nullptr;
+  bool owned = false;
+  void* gate = nullptr;        // [E][H] bf16
+  float* gate_bias = nullptr;  // [E]
+  float* corr_bias = nullptr;  // [E]
+};
+
+struct kb2_engine {
+  kb2_config cfg{};
+  int e_start = 0, e_end = 0, e_local = 0;
+  int num_sms = 0;
+  std::vector<LayerWeights> layers;
+  // scratch (sized for cfg.max_tokens)
+  int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *n_chunks = nullptr;
+  ChunkDesc* chunks = nullptr;
+  int *sorted_token = nullptr, *slot_of = nullptr;
+  float* sorted_w = nullptr;
+  void *act = nullptr, *c3 = nullptr;
+  float* logits = nullptr;
+  int* ids_tmp = nullptr;
+  float* w_tmp = nullptr;
+  void *x_tmp = nullptr, *out_tmp = nullptr;
+  int64_t launches = 0;
+};
+
+static size_t tile_bytes_per_weight(int fmt) { return fmt == KB2_FMT_INT4_G128 ? 1 : 2; }  // half-bytes x2
+
+static size_t tiled_bytes(const kb2_engine* e, int which) {
+  const size_t H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, E = e->e_local;
+  const size_t hb = tile_bytes_per_weight(e->cfg.weight_format);  // in half-bytes
+  switch (which) {
+    case 0: return E * 2 * I * H * hb / 2;
+    case 1: return E * 2 * I * (H / kGroup) * 2;
+    case 2: return E * H * I * hb / 2;
+    case 3: return E * H * (I / kGroup) * 2;
+  }
+  return 0;
+}
+
+extern "C" {
+
+KB2_API const char* kb2_last_error(void) { return g_err.c_str(); }
+KB2_API const char* kb2_version(void) { return "krasis_b200 0.1 (sm_100a)"; }
+
+KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
+  if (!c || !out) return fail(KB2_ERR_VALUE, "null argument");
+  if (c->hidden_size <= 0 || c->hidden_size % 256)
+    return fail(KB2_ERR_VALUE, "hidden_size (%d) must be a positive multiple of 256", c->hidden_size);
+  if (c->moe_intermediate_size <= 0 || c->moe_intermediate_size % 128)
+    return fail(KB2_ERR_VALUE, "moe_intermediate_size (%d) must be a positive multiple of 128", c->moe_intermediate_size);
+  if (c->num_ranks < 1 || c->rank < 0 || c->rank >= c->num_ranks) return fail(KB2_ERR_VALUE, "bad rank %d/%d", c->rank, c->num_ranks);
+  if (c->n_routed_experts < c->num_ranks) return fail(KB2_ERR_VALUE, "fewer experts than ranks");
+  if (c->num_experts_per_tok < 1 || c->num_experts_per_tok > 32) return fail(KB2_ERR_VALUE, "top-k must be in [1,32]");
+  if (c->weight_format != KB2_FMT_INT4_G128 && c->weight_format != KB2_FMT_INT8_G128)
+    return fail(KB2_ERR_VALUE, "unknown weight_format %d", c->weight_format);
+  if (c->max_tokens < 1 || c->num_moe_layers < 1) return fail(KB2_ERR_VALUE, "max_tokens and num_moe_layers must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KB2_ERR_CUDA, "no CUDA device: krasis_b200 has no CPU fallback");
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major != 10) return fail(KB2_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", c->device, prop.major, prop.minor);
+
+  kb2_engine* e = new kb2_engine();
+  e->cfg = *c;
+  const int per = c->n_routed_experts / c->num_ranks;            // gpu_prefill.py:353-359
+  e->e_start = c->rank * per;
+  e->e_end = (c->rank == c->num_ranks - 1) ? c->n_routed_experts : (c->rank + 1) * per;
+  e->e_local = e->e_end - e->e_start;
+  if (e->e_local > 1024) { delete e; return fail(KB2_ERR_VALUE, "more than 1024 local experts"); }
+  if (c->n_routed_experts > 1024) { delete e; return fail(KB2_ERR_VALUE, "more than 1024 experts"); }
+  e->num_sms = prop.multiProcessorCount;
+  e->layers.resize(c->num_moe_layers);
+  const size_t MK = (size_t)c->max_tokens * c->num_experts_per_tok;
+  const size_t max_chunks = e->e_local + MK / kMaxChunkTokens + 1;
+#define ALLOC(ptr, bytes) CUDA_TRY(cudaMalloc((void**)&(ptr), (bytes)))
+  ALLOC(e->counts, sizeof(int) * e->e_local);
+  ALLOC(e->offsets, sizeof(int) * (e->e_local + 1));
+  ALLOC(e->cursor, sizeof(int) * e->e_local);
+  ALLOC(e->n_chunks, sizeof(int));
+  ALLOC(e->chunks, sizeof(ChunkDesc) * max_chunks);
+  ALLOC(e->sorted_token, sizeof(int) * MK);
+  ALLOC(e->slot_of, sizeof(int) * MK);
+  ALLOC(e->sorted_w, sizeof(float) * MK);
+  ALLOC(e->act, MK * c->moe_intermediate_size * 2);
+  ALLOC(e->c3, MK * c->hidden_size * 2);
+  ALLOC(e->logits, sizeof(float) * (size_t)c->max_tokens * c->n_routed_experts);
+  ALLOC(e->ids_tmp, sizeof(int) * MK);
+  ALLOC(e->w_tmp, sizeof(float) * MK);
+  ALLOC(e->x_tmp, (size_t)c->max_tokens * c->hidden_size * 2);
+  ALLOC(e->out_tmp, (size_t)c->max_tokens * c->hidden_size * 2);
+#undef ALLOC
+  *out = e;
+  return KB2_OK;
+}
+
+static void free_layer(LayerWeights& L) {
+  if (L.owned) {
+    cudaFree((void*)L.w13_q); cudaFree((void*)L.w13_s); cudaFree((void*)L.w2_q); cudaFree((void*)L.w2_s);
+  }
+  L.w13_q = L.w13_s = L.w2_q = L.w2_s = nullptr;
+  L.owned = false;
+}
+
+KB2_API void kb2_destroy(kb2_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  for (auto& L : e->layers) {
+    free_layer(L);
+    cudaFree(L.gate); cudaFree(L.gate_bias); cudaFree(L.corr_bias);
+  }
+  cudaFree(e->counts); cudaFree(e->offsets); cudaFree(e->cursor); cudaFree(e->n_chunks); cudaFree(e->chunks);
+  cudaFree(e->sorted_token); cudaFree(e->slot_of); cudaFree(e->sorted_w); cudaFree(e->act); cudaFree(e->c3);
+  cudaFree(e->logits); cudaFree(e->ids_tmp); cudaFree(e->w_tmp); cudaFree(e->x_tmp); cudaFree(e->out_tmp);
+  delete e;
+}
+
+KB2_API int kb2_get_config(const kb2_engine* e, kb2_config* out) {
+  if (!e || !out) return fail(KB2_ERR_VALUE, "null argument");
+  *out = e->cfg;
+  return KB2_OK;
+}
+
+KB2_API int kb2_expert_range(const kb2_engine* e, int32_t* s, int32_t* t) {
+  if (!e || !s || !t) return fail(KB2_ERR_VALUE, "null argument");
+  *s = e->e_start; *t = e->e_end;
+  return KB2_OK;
+}
+
+KB2_API size_t kb2_tiled_bytes(const kb2_engine* e, int which) { return e ? tiled_bytes(e, which) : 0; }
+KB2_API int64_t kb2_launch_count(const kb2_engine* e) { return e ? e->launches : 0; }
+
+static int check_layer(kb2_engine* e, int layer) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  if (layer < 0 || layer >= (int)e->layers.size())
+    return fail(KB2_ERR_VALUE, "moe_layer_idx %d out of range [0, %d)", layer, (int)e->layers.size());
+  return KB2_OK;
+}
+
+KB2_API int kb2_retile_dev(kb2_engine* e, int fmt, const void* sq, const void* ss, void* dq, void* ds, int n_experts,
+                   int n_rows, int k_cols, void* stream) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaError_t r = launch_repack(fmt, sq, ss, dq, ds, n_experts, n_rows, k_cols, (cudaStream_t)stream);
+  if (r != cudaSuccess) return fail(r == cudaErrorInvalidValue ? KB2_ERR_VALUE : KB2_ERR_CUDA, "retile: %s", cudaGetErrorString(r));
+  e->launches += 2;
+  return KB2_OK;
+}
+
+KB2_API int kb2_load_experts_host(kb2_engine* e, int layer, const void* w13_q, const void* w13_s, const void* w2_q,
+                          const void* w2_s) {
+  if (int r = check_layer(e, layer)) return r;
+  if (!w13_q || !w13_s || !w2_q || !w2_s) return fail(KB2_ERR_VALUE, "null weight pointer");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  LayerWeights& L = e->layers[layer];
+  free_layer(L);
+  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, fmt = e->cfg.weight_format;
+  void* dst[4];
+  const void* src[4] = {w13_q, w13_s, w2_q, w2_s};
+  void* tmp[4];
+  for (int i = 0; i < 4; ++i) {
+    const size_t b = tiled_bytes(e, i);   // the re-tiling is a permutation: same byte counts
+    CUDA_TRY(cudaMalloc(&dst[i], b));
+    CUDA_TRY(cudaMalloc(&tmp[i], b));
+    CUDA_TRY(cudaMemcpy(tmp[i], src[i], b, cudaMemcpyHostToDevice));
+  }
+  cudaError_t r1 = launch_repack(fmt, tmp[0], tmp[1], dst[0], dst[1], e->e_local, 2 * I, H, 0);
+  cudaError_t r2 = launch_repack(fmt, tmp[2], tmp[3], dst[2], dst[3], e->e_local, H, I, 0);
+  e->launches += 4;
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < 4; ++i) cudaFree(tmp[i]);
+  if (r1 != cudaSuccess || r2 != cudaSuccess) return fail(KB2_ERR_CUDA, "retile failed");
+  L.w13_q = (const uint8_t*)dst[0]; L.w13_s = (const uint8_t*)dst[1];
+  L.w2_q = (const uint8_t*)dst[2]; L.w2_s = (const uint8_t*)dst[3];
+  L.owned = true;
+  return KB2_OK;
+}
+
+KB2_API int kb2_attach_experts_tiled_dev(kb2_engine* e, int layer, const void* w13_q, const void* w13_s, const void* w2_q,
+                                 const void* w2_s) {
+  if (int r = check_layer(e, layer)) return r;
+  if (!w13_q || !w13_s || !w2_q || !w2_s) return fail(KB2_ERR_VALUE, "null weight pointer");
+  LayerWeights& L = e->layers[layer];
+  free_layer(L);
+  L.w13_q = (const uint8_t*)w13_q; L.w13_s = (const uint8_t*)w13_s;
+  L.w2_q = (const uint8_t*)w2_q; L.w2_s = (const uint8_t*)w2_s;
+  L.owned = false;
+  return KB2_OK;
+}
+
+KB2_API int kb2_set_router_host(kb2_engine* e, int layer, const void* gate, const float* bias, const float* corr) {
+  if (int r = check_layer(e, layer)) return r;
+  if (!gate) return fail(KB2_ERR_VALUE, "null gate weight");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  LayerWeights& L = e->layers[layer];
+  const size_t E = e->cfg.n_routed_experts, H = e->cfg.hidden_size;
+  cudaFree(L.gate); cudaFree(L.gate_bias); cudaFree(L.corr_bias);
+  L.gate = nullptr; L.gate_bias = nullptr; L.corr_bias = nullptr;
+  CUDA_TRY(cudaMalloc(&L.gate, E * H * 2));
+  CUDA_TRY(cudaMemcpy(L.gate, gate, E * H * 2, cudaMemcpyHostToDevice));
+  if (bias) {
+    CUDA_TRY(cudaMalloc((void**)&L.gate_bias, E * 4));
+    CUDA_TRY(cudaMemcpy(L.gate_bias, bias, E * 4, cudaMemcpyHostToDevice));
+  }
+  if (corr) {
+    CUDA_TRY(cudaMalloc((void**)&L.corr_bias, E * 4));
+    CUDA_TRY(cudaMemcpy(L.corr_bias, corr, E * 4, cudaMemcpyHostToDevice));
+  }
+  return KB2_OK;
+}
+
+KB2_API int kb2_route(kb2_engine* e, int layer, const void* hidden, int32_t M, int32_t* ids, float* wts, void* stream) {
+  if (int r = check_layer(e, layer)) return r;
+  LayerWeights& L = e->layers[layer];
+  if (!L.gate) return fail(KB2_ERR_STATE, "router weights not set for layer %d", layer);
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (M == 0) return KB2_OK;
+  if (!hidden || !ids || !wts) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(launch_router_logits(hidden, L.gate, L.gate_bias, e->logits, M, e->cfg.n_routed_experts, e->cfg.hidden_size, s));
+  CUDA_TRY(launch_router_topk(e->logits, L.corr_bias, M, e->cfg.n_routed_experts, e->cfg.num_experts_per_tok,
+                              e->cfg.scoring_func, e->cfg.norm_topk_prob, ids, wts, s));
+  e->launches += 2;
+  return KB2_OK;
+}
+
+KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32_t* ids, const float* wts, void* out,
+                    int32_t M, int32_t routed_only, const void* shared, void* stream) {
+  if (int r = check_layer(e, layer)) return r;
+  LayerWeights& L = e->layers[layer];
+  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (M == 0) return KB2_OK;
+  if (!x || !ids || !wts || !out) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, K = e->cfg.num_experts_per_tok;
+  const int fmt = e->cfg.weight_format;
+
+  CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
+                          e->n_chunks, e->sorted_token, e->sorted_w, e->slot_of, s));
+  e->launches += 3;
+
+  GemmParams g1{};
+  g1.wq = L.w13_q; g1.ws = L.w13_s;
+  g1.wq_expert_stride = (long long)(tiled_bytes(e, 0) / e->e_local);
+  g1.ws_expert_stride = (long long)(tiled_bytes(e, 1) / e->e_local);
+  g1.n_kblocks = H / kBlockK;
+  g1.items_per_chunk = I / kTileRows; g1.tile1_offset = I / kTileRows; g1.tile0_mul = 1;
+  g1.b_src = (const __nv_bfloat16*)x; g1.b_ld = H; g1.b_row_index = e->sorted_token;
+  g1.chunks = e->chunks; g1.n_chunks = e->n_chunks;
+  g1.out = (__nv_bfloat16*)e->act; g1.out_ld = I; g1.slot_weight = nullptr;
+  CUDA_TRY(launch_grouped_gemm(fmt, true, g1, e->num_sms, s));
+
+  GemmParams g2{};
+  g2.wq = L.w2_q; g2.ws = L.w2_s;
+  g2.wq_expert_stride = (long long)(tiled_bytes(e, 2) / e->e_local);
+  g2.ws_expert_stride = (long long)(tiled_bytes(e, 3) / e->e_local);
+  g2.n_kblocks = I / kBlockK;
+  g2.items_per_chunk = H / (2 * kTileRows); g2.tile1_offset = 1; g2.tile0_mul = 2;
+  g2.b_src = (const __nv_bfloat16*)e->act; g2.b_ld = I; g2.b_row_index = nullptr;
+  g2.chunks = e->chunks; g2.n_chunks = e->n_chunks;
+  g2.out = (__nv_bfloat16*)e->c3; g2.out_ld = H; g2.slot_weight = e->sorted_w;
+  CUDA_TRY(launch_grouped_gemm(fmt, false, g2, e->num_sms, s));
+
+  const int apply = routed_only ? 0 : 1;
+  CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply,
+                          routed_only ? nullptr : shared, out, s));
+  e->launches += 3;
+  return KB2_OK;
+}
+
+KB2_API int kb2_moe_forward_host(kb2_engine* e, int layer, const void* x_host, const int32_t* ids_host, const float* w_host,
+                         void* out_host, int32_t M, int32_t routed_only, void* stream) {
+  if (int r = check_layer(e, layer)) return r;
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (M == 0) return KB2_OK;
+  if (!x_host || !out_host) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t H = e->cfg.hidden_size, K = e->cfg.num_experts_per_tok;
+  CUDA_TRY(cudaMemcpyAsync(e->x_tmp, x_host, (size_t)M * H * 2, cudaMemcpyHostToDevice, s));
+  if (ids_host) {
+    if (!w_host) return fail(KB2_ERR_VALUE, "topk_weights_host is NULL but topk_ids_host is not");
+    CUDA_TRY(cudaMemcpyAsync(e->ids_tmp, ids_host, (size_t)M * K * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->w_tmp, w_host, (size_t)M * K * 4, cudaMemcpyHostToDevice, s));
+  } else {
+    if (int r = kb2_route(e, layer, e->x_tmp, M, e->ids_tmp, e->w_tmp, stream)) return r;
+  }
+  if (int r = kb2_moe_forward(e, layer, e->x_tmp, e->ids_tmp, e->w_tmp, e->out_tmp, M, routed_only, nullptr, stream)) return r;
+  CUDA_TRY(cudaMemcpyAsync(out_host, e->out_tmp, (size_t)M * H * 2, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return KB2_OK;
+}
+
+KB2_API int kb2_last_expert_counts(kb2_engine* e, int32_t* counts_host, void* stream) {
+  if (!e || !counts_host) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(counts_host, e->counts, sizeof(int) * e->e_local, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return KB2_OK;
+}
+
+}  // extern "C"

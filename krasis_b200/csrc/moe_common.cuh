@@ -1,0 +1,65 @@
+// Shared definitions for the MoE prefill kernels (layouts, work descriptors).
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace kb2 {
+
+// ---------------------------------------------------------------------------------------------
+// B200 expert-weight layout ("KB2 tiles").  The reference's quantiser emits, per expert and matrix,
+// packed[N][K/8] u32 (nibble i of word w = column 8w+i, value q+8) and scales[N][K/128] bf16
+// (src/weights/marlin.rs:145-207); its GPU form is a Marlin permutation of those values
+// (marlin.rs:323-491) designed for mma.sync.  For tcgen05 we keep the same VALUES and re-tile:
+//
+//   packed tile (nt, kb) = 128 rows x 64 K-columns = 4096 B at ((nt * K/64) + kb) * 4096
+//       [half h in {0,1}] [row r in 0..127] [16 B]   16 B = 4 words, word j covers columns
+//       kb*64 + h*32 + j*8 + {0,2,4,6,1,3,5,7}  (nibble p holds column offset kNibOrder[p]) so that
+//       (w >> 4i) & 0x000F000F yields the BF16 pair (col 2i, col 2i+1) directly.
+//   scale  tile (nt, g)  = 128 x bf16 = 256 B at ((nt * K/128) + g) * 256,  [row r]
+//
+// One tile is one contiguous blob => a single 1-D bulk-TMA copy per (tile, k-block), fully coalesced,
+// and bank-conflict-free 16 B reads per thread-row in the dequant warps.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileRows = 128;
+constexpr int kBlockK = 64;
+constexpr int kGroup = 128;
+constexpr int kInt4TileBytes = kTileRows * kBlockK / 2;   // 4096
+constexpr int kInt8TileBytes = kTileRows * kBlockK;       // 8192
+constexpr int kScaleTileBytes = kTileRows * 2;            // 256
+
+enum WeightFormat : int {
+  kFmtInt4G128 = 0,   // Krasis symmetric INT4, group 128
+  kFmtInt8G128 = 1,   // Krasis symmetric INT8, group 128
+};
+
+// One unit of grouped-GEMM work along the token axis: a run of <= 256 sorted slots of one expert.
+struct ChunkDesc {
+  int expert;      // local expert index
+  int slot_begin;  // first sorted slot
+  int n_tok;       // real token slots in this chunk (1..256)
+  int pad_;
+};
+
+constexpr int kMaxChunkTokens = 256;
+
+struct GemmParams {
+  const uint8_t* wq;          // packed tiles, all local experts
+  const uint8_t* ws;          // scale tiles
+  long long wq_expert_stride; // bytes
+  long long ws_expert_stride; // bytes
+  int n_kblocks;              // K / 64
+  int items_per_chunk;        // GEMM1: I/128 (gate tile + up tile)   GEMM2: H/256 (two consecutive tiles)
+  int tile1_offset;           // GEMM1: I/128   GEMM2: 1
+  int tile0_mul;              // GEMM1: 1       GEMM2: 2          tile0 = rt * tile0_mul, tile1 = tile0 + tile1_offset
+  const __nv_bfloat16* b_src; // token rows
+  long long b_ld;             // elements between rows
+  const int* b_row_index;     // slot -> source row, or nullptr for identity
+  const ChunkDesc* chunks;
+  const int* n_chunks;        // device scalar
+  __nv_bfloat16* out;         // GEMM1: act[slot][I]   GEMM2: c3[slot][H]
+  long long out_ld;
+  const float* slot_weight;   // GEMM2: routing weight per sorted slot
+};
+
+}  // namespace kb2

@@ -1,0 +1,417 @@
+// Router, token binning and combine kernels for MoE prefill (HBM-bound integer / elementwise work),
+// plus the load-time re-tiling of the reference's quantised expert weights.
+//
+//   router_logits_kernel   layer.py:532-534   logits = hidden.float() @ gate.float().T (+bias), fp32 FMA
+//   router_topk_kernel     layer.py:536-560   softmax|sigmoid|gpt-oss scoring, top-k (ties -> lower index,
+//                                              src/moe.rs:3116-3128), optional renorm
+//   count / scan / scatter                     replaces sglang moe_align_block_size (gpu_prefill.py:118):
+//                                              bins (token, k) slots into per-expert contiguous runs
+//   combine_kernel                             moe_sum_reduce (gpu_prefill.py:238) + rsf*out + shared
+//                                              (gpu_prefill.py:4471-4482)
+#include "moe_common.cuh"
+
+namespace kb2 {
+
+// ------------------------------------------------------------------------------------------------
+// Router logits: C[M,E] = A[M,H] (bf16) * B[E,H]^T (bf16), fp32 FMA, k ascending per output.
+// 64x64 tile, 256 threads, 4x4 micro-tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int RT = 64, RK = 32;
+
+__global__ void __launch_bounds__(256) router_logits_kernel(const __nv_bfloat16* __restrict__ h,
+                                                            const __nv_bfloat16* __restrict__ gate,
+                                                            const float* __restrict__ gate_bias,
+                                                            float* __restrict__ logits, int M, int E, int H) {
+  __shared__ float hs[RK][RT + 4];
+  __shared__ float gs[RK][RT + 4];
+  const int m0 = blockIdx.y * RT, e0 = blockIdx.x * RT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < H; k0 += RK) {
+    // 64 rows x 32 k of each operand: 2048 elements / 256 threads = 8 each (one 16 B load)
+    {
+      const int r = threadIdx.x >> 2, kc = (threadIdx.x & 3) * 8;
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (m0 + r < M) va = *reinterpret_cast<const uint4*>(h + (long long)(m0 + r) * H + k0 + kc);
+      if (e0 + r < E) vb = *reinterpret_cast<const uint4*>(gate + (long long)(e0 + r) * H + k0 + kc);
+      const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&va);
+      const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&vb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        hs[kc + i][r] = __bfloat162float(pa[i]);
+        gs[kc + i][r] = __bfloat162float(pb[i]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&hs[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&gs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = e0 + tx * 4 + j;
+      if (e < E) logits[(long long)m * E + e] = acc[i][j] + (gate_bias ? gate_bias[e] : 0.0f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scoring + top-k: one warp per token; E <= 1024, E % 32 == 0 not required.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPerLane = 32;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int PER_LANE>
+__global__ void __launch_bounds__(128) router_topk_kernel(const float* __restrict__ logits,
+                                                          const float* __restrict__ corr_bias, int M, int E,
+                                                          int top_k, int scoring, int renorm,
+                                                          int* __restrict__ ids, float* __restrict__ wts) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float* lg = logits + (long long)m * E;
+  float score[PER_LANE], key[PER_LANE];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int e = i * 32 + lane;
+    score[i] = e < E ? lg[e] : -INFINITY;
+    mx = fmaxf(mx, score[i]);
+  }
+  if (scoring == 0) {           // softmax over all experts
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int e = i * 32 + lane;
+      score[i] = e < E ? expf(score[i] - mx) : 0.f;
+      s += score[i];
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) score[i] = score[i] / s;
+  } else if (scoring == 1) {    // sigmoid
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) score[i] = 1.0f / (1.0f + expf(-score[i]));
+  }                              // scoring == 2: raw logits (GPT-OSS), softmax over the selected k below
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int e = i * 32 + lane;
+    key[i] = e < E ? score[i] + ((corr_bias && scoring != 2) ? corr_bias[e] : 0.f) : -INFINITY;
+  }
+  float wsum = 0.f, my_w = 0.f;
+  int my_id = 0;
+  float first_val = 0.f;
+  for (int j = 0; j < top_k; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    float bs = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {       // ascending expert index within the lane: strict '>' keeps the lower index
+      if (key[i] > bv) {
+        bv = key[i];
+        bi = i * 32 + lane;
+        bs = score[i];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+        bs = os;
+      }
+    }
+    if ((bi & 31) == lane) {
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i)
+        if (i == (bi >> 5)) key[i] = -INFINITY;
+    }
+    float wj = bs;
+    if (scoring == 2) {
+      if (j == 0) first_val = bs;
+      wj = expf(bs - first_val);
+    }
+    wsum += wj;
+    if (lane == j) {
+      my_w = wj;
+      my_id = bi;
+    }
+  }
+  if (lane < top_k) {
+    if (renorm || scoring == 2) my_w = my_w / wsum;
+    ids[(long long)m * top_k + lane] = my_id;
+    wts[(long long)m * top_k + lane] = my_w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Binning: count -> scan (+ chunk descriptors) -> scatter
+// ------------------------------------------------------------------------------------------------
+__global__ void count_kernel(const int* __restrict__ ids, int n, int e_start, int e_end, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = ids[i];
+  if (e >= e_start && e < e_end) atomicAdd(&counts[e - e_start], 1);
+}
+
+// single block of 1024 threads; E_local <= 1024
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ counts, int E, int* __restrict__ offsets,
+                                                    int* __restrict__ cursor, ChunkDesc* __restrict__ chunks,
+                                                    int* __restrict__ n_chunks) {
+  __shared__ int s_cnt[1024], s_chk[1024];
+  const int t = threadIdx.x;
+  const int c = t < E ? counts[t] : 0;
+  const int nch = (c + kMaxChunkTokens - 1) / kMaxChunkTokens;
+  s_cnt[t] = c;
+  s_chk[t] = nch;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan (tiny)
+    int a = 0, b = 0;
+    if (t >= o) {
+      a = s_cnt[t - o];
+      b = s_chk[t - o];
+    }
+    __syncthreads();
+    s_cnt[t] += a;
+    s_chk[t] += b;
+    __syncthreads();
+  }
+  const int off = s_cnt[t] - c, choff = s_chk[t] - nch;
+  if (t < E) {
+    offsets[t] = off;
+    cursor[t] = 0;
+    if (nch > 0) {
+      int per = (c + nch - 1) / nch;
+      per = (per + 15) & ~15;
+      for (int i = 0; i < nch; ++i) {
+        ChunkDesc d;
+        d.expert = t;
+        d.slot_begin = off + i * per;
+        d.n_tok = min(per, c - i * per);
+        d.pad_ = 0;
+        chunks[choff + i] = d;
+      }
+    }
+  }
+  if (t == 1023) {
+    offsets[E] = s_cnt[1023];
+    *n_chunks = s_chk[1023];
+  }
+}
+
+__global__ void scatter_kernel(const int* __restrict__ ids, const float* __restrict__ wts, int n, int top_k,
+                               int e_start, int e_end, const int* __restrict__ offsets, int* __restrict__ cursor,
+                               int* __restrict__ sorted_token, float* __restrict__ sorted_w,
+                               int* __restrict__ slot_of) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = ids[i];
+  int slot = -1;
+  if (e >= e_start && e < e_end) {
+    const int le = e - e_start;
+    slot = offsets[le] + atomicAdd(&cursor[le], 1);
+    sorted_token[slot] = i / top_k;
+    sorted_w[slot] = wts[i];
+  }
+  slot_of[i] = slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Combine: out[m] = bf16( sum_j f32(c3[slot_of[m][j]]) ) in j order; then bf16(rsf*out) (+ shared)
+// one thread = 8 consecutive h (16 B)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) combine_kernel(const __nv_bfloat16* __restrict__ c3,
+                                                      const int* __restrict__ slot_of, int M, int H, int top_k,
+                                                      float rsf, int apply_rsf,
+                                                      const __nv_bfloat16* __restrict__ shared,
+                                                      __nv_bfloat16* __restrict__ out) {
+  const int vec_per_row = H >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * vec_per_row) return;
+  const int m = (int)(idx / vec_per_row), v = (int)(idx % vec_per_row);
+  float acc[8] = {};
+  for (int j = 0; j < top_k; ++j) {
+    const int slot = slot_of[(long long)m * top_k + j];
+    if (slot < 0) continue;
+    const uint4 x = *reinterpret_cast<const uint4*>(c3 + (long long)slot * H + v * 8);
+    const __nv_bfloat16* px = reinterpret_cast<const __nv_bfloat16*>(&x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += __bfloat162float(px[i]);
+  }
+  uint4 sh = make_uint4(0, 0, 0, 0);
+  if (shared) sh = *reinterpret_cast<const uint4*>(shared + (long long)m * H + v * 8);
+  const __nv_bfloat16* ps = reinterpret_cast<const __nv_bfloat16*>(&sh);
+  uint4 o;
+  __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16 r = __float2bfloat16_rn(acc[i]);
+    if (apply_rsf) r = __float2bfloat16_rn(rsf * __bfloat162float(r));
+    if (shared) r = __float2bfloat16_rn(__bfloat162float(r) + __bfloat162float(ps[i]));
+    po[i] = r;
+  }
+  *reinterpret_cast<uint4*>(out + (long long)m * H + v * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Load-time re-tiling of the reference quantiser's output into KB2 tiles (see moe_common.cuh)
+// ------------------------------------------------------------------------------------------------
+// INT4: src packed[E][N][K/8] u32 -> dst tiles; one thread per destination word
+__global__ void repack_int4_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int E, int N, int K) {
+  const long long total = (long long)E * N * (K / 8);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int words_per_expert_row = K / 8;
+  const long long per_expert = (long long)N * words_per_expert_row;
+  const int e = (int)(i / per_expert);
+  long long r = i % per_expert;          // destination word index within the expert
+  const int nkb = K / kBlockK;
+  const int tile = (int)(r / (nkb * 1024));          // 1024 words per (tile, kb)
+  r %= (long long)nkb * 1024;
+  const int kb = (int)(r / 1024);
+  const int w = (int)(r % 1024);
+  const int h = w / 512, row = (w % 512) / 4, j = w % 4;
+  const int n = tile * kTileRows + row;
+  const int kw = kb * 8 + h * 4 + j;
+  const uint32_t s = src[((long long)e * N + n) * words_per_expert_row + kw];
+  // destination nibble p holds source nibble {0,2,4,6,1,3,5,7}[p]
+  uint32_t d = 0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int sp = (p < 4) ? 2 * p : 2 * (p - 4) + 1;
+    d |= ((s >> (4 * sp)) & 0xFu) << (4 * p);
+  }
+  dst[i] = d;
+}
+
+// INT8: src data[E][N][K] i8 -> dst tiles [tile][kb][quarter][row][16 B]; one thread per 16 B
+__global__ void repack_int8_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int E, int N, int K) {
+  const long long total = (long long)E * N * (K / 16);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long per_expert = (long long)N * (K / 16);
+  const int e = (int)(i / per_expert);
+  long long r = i % per_expert;
+  const int nkb = K / kBlockK;
+  const int tile = (int)(r / (nkb * 512));           // 512 x 16 B per (tile, kb)
+  r %= (long long)nkb * 512;
+  const int kb = (int)(r / 512);
+  const int w = (int)(r % 512);
+  const int q = w / 128, row = w % 128;
+  const int n = tile * kTileRows + row;
+  dst[i] = src[((long long)e * N + n) * (K / 16) + kb * 4 + q];
+}
+
+// scales: src[E][N][K/128] bf16 -> dst[E][N/128][K/128][128]
+__global__ void repack_scales_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int E, int N,
+                                     int G) {
+  const long long total = (long long)E * N * G;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long per_expert = (long long)N * G;
+  const int e = (int)(i / per_expert);
+  long long r = i % per_expert;
+  const int tile = (int)(r / (G * kTileRows));
+  r %= (long long)G * kTileRows;
+  const int g = (int)(r / kTileRows), row = (int)(r % kTileRows);
+  dst[i] = src[((long long)e * N + tile * kTileRows + row) * G + g];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_router_logits(const void* h, const void* gate, const float* bias, float* logits, int M, int E,
+                                 int H, cudaStream_t s) {
+  dim3 grid((E + RT - 1) / RT, (M + RT - 1) / RT);
+  router_logits_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)gate, bias, logits, M, E, H);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int M, int E, int top_k, int scoring,
+                               int renorm, int* ids, float* wts, cudaStream_t s) {
+  const int warps = 4;
+  dim3 grid((M + warps - 1) / warps);
+  if (top_k > 32 || E > 1024) return cudaErrorInvalidValue;
+  if (E <= 64)
+    router_topk_kernel<2><<<grid, warps * 32, 0, s>>>(logits, corr_bias, M, E, top_k, scoring, renorm, ids, wts);
+  else if (E <= 128)
+    router_topk_kernel<4><<<grid, warps * 32, 0, s>>>(logits, corr_bias, M, E, top_k, scoring, renorm, ids, wts);
+  else if (E <= 256)
+    router_topk_kernel<8><<<grid, warps * 32, 0, s>>>(logits, corr_bias, M, E, top_k, scoring, renorm, ids, wts);
+  else if (E <= 512)
+    router_topk_kernel<16><<<grid, warps * 32, 0, s>>>(logits, corr_bias, M, E, top_k, scoring, renorm, ids, wts);
+  else
+    router_topk_kernel<32><<<grid, warps * 32, 0, s>>>(logits, corr_bias, M, E, top_k, scoring, renorm, ids, wts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
+                           int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, int* sorted_token,
+                           float* sorted_w, int* slot_of, cudaStream_t s) {
+  const int n = M * top_k, E = e_end - e_start;
+  if (E > 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * E, s);
+  if (e != cudaSuccess) return e;
+  if (n > 0) count_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, n, e_start, e_end, counts);
+  scan_kernel<<<1, 1024, 0, s>>>(counts, E, offsets, cursor, chunks, n_chunks);
+  if (n > 0)
+    scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, wts, n, top_k, e_start, e_end, offsets, cursor, sorted_token,
+                                                   sorted_w, slot_of);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
+                           const void* shared, void* out, cudaStream_t s) {
+  const long long total = (long long)M * (H / 8);
+  if (total == 0) return cudaSuccess;
+  combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)c3, slot_of, M, H, top_k, rsf,
+                                                                apply_rsf, (const __nv_bfloat16*)shared,
+                                                                (__nv_bfloat16*)out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,
+                          cudaStream_t s) {
+  if (N % kTileRows || K % kGroup) return cudaErrorInvalidValue;
+  if (fmt == kFmtInt4G128) {
+    const long long total = (long long)E * N * (K / 8);
+    repack_int4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint32_t*)src_q, (uint32_t*)dst_q, E, N, K);
+  } else if (fmt == kFmtInt8G128) {
+    const long long total = (long long)E * N * (K / 16);
+    repack_int8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint4*)src_q, (uint4*)dst_q, E, N, K);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  const long long ts = (long long)E * N * (K / kGroup);
+  repack_scales_kernel<<<(unsigned)((ts + 255) / 256), 256, 0, s>>>((const uint16_t*)src_s, (uint16_t*)dst_s, E, N,
+                                                                   K / kGroup);
+  return cudaGetLastError();
+}
+
+}  // namespace kb2

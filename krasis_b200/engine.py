@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's engine surface for the prefill path.
+
+Reference interfaces mirrored (names, argument meaning and error behaviour kept):
+  KrasisEngine                      src/moe.rs:1377-3296 (#[pyclass]); introspection methods :1874-1965,
+                                    set_routing_config/weights :2959,2989
+  GpuPrefillManager.__init__        python/krasis/gpu_prefill.py:326-346 (rank/num_ranks expert slicing :353-359)
+  GpuPrefillManager.forward         python/krasis/gpu_prefill.py:4374-4484
+  TransformerLayer.compute_routing  python/krasis/layer.py:526-560
+torch is used only for device memory, streams and dtype plumbing; all arithmetic happens inside
+libkrasis_b200.so (hand-written sm_100a kernels).  No fallback path exists.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import capi
+
+_SCORING = {"softmax": capi.SCORE_SOFTMAX, "sigmoid": capi.SCORE_SIGMOID, "topk_softmax": capi.SCORE_TOPK_SOFTMAX}
+
+
+@dataclass
+class QuantizedExperts:
+    """One MoE layer's LOCAL experts in the reference quantiser's output format
+    (src/weights/marlin.rs:145-207 / 65-114), numpy host arrays:
+      w13_q [E, 2I, H/8] uint32 (INT4) or [E, 2I, H] int8 (INT8);  w13_s [E, 2I, H/128] uint16 (raw BF16)
+      w2_q  [E, H, I/8]  uint32          or [E, H, I]  int8;        w2_s  [E, H, I/128]  uint16
+    w13 = [gate rows ; up rows] (src/weights/mod.rs:346-349)."""
+    w13_q: np.ndarray
+    w13_s: np.ndarray
+    w2_q: np.ndarray
+    w2_s: np.ndarray
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class KrasisEngine:
+    """Weight store + routing config behind the C ABI (the B200 counterpart of `#[pyclass] KrasisEngine`).
+
+    The reference constructor is KrasisEngine(parallel, num_threads, skip_shared_experts) followed by
+    load(model_dir, ...) (src/moe.rs:1482,1538).  Here the geometry is explicit (the C ABI takes it in
+    kb2_config) and weights arrive either as the quantiser's arrays (`load_quantized_layer`) or as
+    device-resident tiles (`attach_tiled_layer`)."""
+
+    def __init__(self, *, hidden_size: int, moe_intermediate_size: int, n_routed_experts: int,
+                 num_experts_per_tok: int, num_moe_layers: int, num_bits: int = 4, group_size: int = 128,
+                 rank: int = 0, num_ranks: int = 1, scoring_func: str = "softmax", norm_topk_prob: bool = False,
+                 routed_scaling_factor: float = 1.0, max_tokens: int = 8192, device: int = 0):
+        if num_bits not in (4, 8):
+            raise ValueError(f"num_bits must be 4 or 8, got {num_bits}")           # gpu_prefill.py:259
+        if group_size != 128:
+            raise ValueError("only group_size=128 is supported (src/weights/marlin.rs:12)")
+        if scoring_func not in _SCORING:
+            raise ValueError(f"unknown scoring_func {scoring_func!r}")
+        self._lib = capi.load()
+        self._cfg = capi.Config(hidden_size, moe_intermediate_size, n_routed_experts, num_experts_per_tok,
+                                num_moe_layers, capi.FMT_INT4_G128 if num_bits == 4 else capi.FMT_INT8_G128,
+                                rank, num_ranks, _SCORING[scoring_func], int(bool(norm_topk_prob)),
+                                float(routed_scaling_factor), max_tokens, device)
+        self._h = C.c_void_p()
+        capi.check(self._lib.kb2_create(C.byref(self._cfg), C.byref(self._h)))
+        self._num_bits, self._group_size = num_bits, group_size
+        self._keep = {}          # device tensors attached by the caller (kept alive)
+        self.device = torch.device("cuda", device)
+        s, t = C.c_int32(), C.c_int32()
+        capi.check(self._lib.kb2_expert_range(self._h, C.byref(s), C.byref(t)))
+        self.expert_start, self.expert_end = s.value, t.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.kb2_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- introspection: all METHODS, as in the reference (src/moe.rs:1874-1965)
+    def num_moe_layers(self): return self._cfg.num_moe_layers
+    def hidden_size(self): return self._cfg.hidden_size
+    def intermediate_size(self): return self._cfg.moe_intermediate_size
+    def num_experts(self): return self._cfg.n_routed_experts
+    def top_k(self): return self._cfg.num_experts_per_tok
+    def group_size(self): return self._group_size
+    def gpu_num_bits(self): return self._num_bits
+    def cpu_num_bits(self): return self._num_bits
+    def is_parallel(self): return True
+    def is_marlin_format(self): return True       # gpu_prefill.py:851 reads this without calling it: keep truthy
+    def marlin_w2_padded_n(self): return self._cfg.hidden_size
+    def launch_count(self): return int(self._lib.kb2_launch_count(self._h))
+
+    def tiled_bytes(self, which: int) -> int:
+        return int(self._lib.kb2_tiled_bytes(self._h, which))
+
+    # ---- weights
+    def load_quantized_layer(self, moe_layer_idx: int, q: QuantizedExperts):
+        E = self.expert_end - self.expert_start
+        H, I = self._cfg.hidden_size, self._cfg.moe_intermediate_size
+        shapes = ({4: (E, 2 * I, H // 8), 8: (E, 2 * I, H)}[self._num_bits], (E, 2 * I, H // 128),
+                  {4: (E, H, I // 8), 8: (E, H, I)}[self._num_bits], (E, H, I // 128))
+        arrs = []
+        for name, a, shp in zip(("w13_q", "w13_s", "w2_q", "w2_s"), (q.w13_q, q.w13_s, q.w2_q, q.w2_s), shapes):
+            a = np.ascontiguousarray(a)
+            if tuple(a.shape) != shp:
+                raise ValueError(f"{name}: expected shape {shp}, got {tuple(a.shape)}")   # moe.rs:2285-2300
+            arrs.append(a)
+        capi.check(self._lib.kb2_load_experts_host(self._h, moe_layer_idx, *[a.ctypes.data for a in arrs]))
+
+    def attach_tiled_layer(self, moe_layer_idx: int, w13_q: torch.Tensor, w13_s: torch.Tensor,
+                           w2_q: torch.Tensor, w2_s: torch.Tensor):
+        ts = (w13_q, w13_s, w2_q, w2_s)
+        for i, t in enumerate(ts):
+            if not t.is_cuda or not t.is_contiguous():
+                raise ValueError("tiled weights must be contiguous CUDA tensors")
+            if t.numel() * t.element_size() != self.tiled_bytes(i):
+                raise ValueError(f"tiled buffer {i}: expected {self.tiled_bytes(i)} bytes, got {t.numel() * t.element_size()}")
+        capi.check(self._lib.kb2_attach_experts_tiled_dev(self._h, moe_layer_idx, *[t.data_ptr() for t in ts]))
+        self._keep[moe_layer_idx] = ts
+
+    # ---- routing (src/moe.rs:2959-3050 set_routing_config / set_routing_weights)
+    def set_routing_weights(self, moe_layer_idx: int, gate_bf16, bias_f32=None, e_score_correction_bias=None):
+        g = gate_bf16
+        if isinstance(g, torch.Tensor):
+            g = g.detach().to(torch.bfloat16).cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+        g = np.ascontiguousarray(g, dtype=np.uint16)
+        if g.shape != (self._cfg.n_routed_experts, self._cfg.hidden_size):
+            raise ValueError(f"gate weight: expected {(self._cfg.n_routed_experts, self._cfg.hidden_size)}, got {g.shape}")
+
+        def f32(a):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                a = a.detach().float().cpu().numpy()
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            if a.shape != (self._cfg.n_routed_experts,):
+                raise ValueError("bias must have shape [n_routed_experts]")
+            return a
+        b, cb = f32(bias_f32), f32(e_score_correction_bias)
+        capi.check(self._lib.kb2_set_router_host(self._h, moe_layer_idx, g.ctypes.data,
+                                                 b.ctypes.data if b is not None else None,
+                                                 cb.ctypes.data if cb is not None else None))
+
+    def compute_routing(self, moe_layer_idx: int, hidden: torch.Tensor):
+        """TransformerLayer.compute_routing (layer.py:526-560): -> (topk_ids int32 [M,k], topk_weights f32 [M,k])."""
+        self._check_act(hidden, "hidden")
+        M, k = hidden.shape[0], self._cfg.num_experts_per_tok
+        ids = torch.empty((M, k), dtype=torch.int32, device=hidden.device)
+        w = torch.empty((M, k), dtype=torch.float32, device=hidden.device)
+        capi.check(self._lib.kb2_route(self._h, moe_layer_idx, hidden.data_ptr(), M, ids.data_ptr(), w.data_ptr(),
+                                       _stream_ptr(hidden.device)))
+        return ids, w
+
+    def _check_act(self, x: torch.Tensor, name: str):
+        if not x.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor: krasis_b200 has no CPU path")
+        if x.dtype != torch.bfloat16 or x.dim() != 2 or x.shape[1] != self._cfg.hidden_size or not x.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous bf16 [M, {self._cfg.hidden_size}], got {x.dtype} {tuple(x.shape)}")
+        if x.device.index != self._cfg.device:
+            raise ValueError(f"{name} is on {x.device}, engine is on cuda:{self._cfg.device}")
+
+    def moe_forward(self, moe_layer_idx, hidden_states, topk_ids, topk_weights, routed_only=False, shared=None):
+        self._check_act(hidden_states, "hidden_states")
+        M, k = hidden_states.shape[0], self._cfg.num_experts_per_tok
+        if tuple(topk_ids.shape) != (M, k) or topk_ids.dtype != torch.int32 or not topk_ids.is_contiguous():
+            raise ValueError(f"topk_ids: expected contiguous int32 [{M}, {k}]")
+        if tuple(topk_weights.shape) != (M, k) or topk_weights.dtype != torch.float32 or not topk_weights.is_contiguous():
+            raise ValueError(f"topk_weights: expected contiguous float32 [{M}, {k}]")
+        if shared is not None:
+            self._check_act(shared, "shared")
+        out = torch.empty_like(hidden_states)
+        capi.check(self._lib.kb2_moe_forward(self._h, moe_layer_idx, hidden_states.data_ptr(), topk_ids.data_ptr(),
+                                             topk_weights.data_ptr(), out.data_ptr(), M, int(bool(routed_only)),
+                                             shared.data_ptr() if shared is not None else None,
+                                             _stream_ptr(hidden_states.device)))
+        return out
+
+    def moe_forward_host(self, moe_layer_idx, x_host: torch.Tensor, topk_ids=None, topk_weights=None,
+                         routed_only=False, out_host: Optional[torch.Tensor] = None):
+        """Host-buffer entry (bytes in / bytes out like submit_forward+sync_forward, src/moe.rs:2722,2809)."""
+        if x_host.is_cuda or x_host.dtype != torch.bfloat16 or not x_host.is_contiguous():
+            raise ValueError("x_host must be a contiguous CPU bf16 tensor")
+        M = x_host.shape[0]
+        if out_host is None:
+            out_host = torch.empty_like(x_host)
+        ids_p = topk_ids.data_ptr() if topk_ids is not None else None
+        w_p = topk_weights.data_ptr() if topk_weights is not None else None
+        capi.check(self._lib.kb2_moe_forward_host(self._h, moe_layer_idx, x_host.data_ptr(), ids_p, w_p,
+                                                  out_host.data_ptr(), M, int(bool(routed_only)),
+                                                  _stream_ptr(self.device)))
+        return out_host
+
+    def last_expert_counts(self) -> np.ndarray:
+        out = np.zeros(self.expert_end - self.expert_start, np.int32)
+        capi.check(self._lib.kb2_last_expert_counts(self._h, out.ctypes.data, _stream_ptr(self.device)))
+        return out
+
+
+class GpuPrefillManager:
+    """Drop-in for python/krasis/gpu_prefill.py:GpuPrefillManager on the prefill path.
+
+    Constructor keeps the reference's argument names (gpu_prefill.py:326-346); arguments that only
+    steer expert streaming on 16 GB GPUs (chunk_size, layer_group_size, model_path) are accepted and
+    ignored — on a 180 GB B200 every expert is resident."""
+
+    def __init__(self, model_path: str = "", device=None, num_experts: int = 0, hidden_size: int = 0,
+                 intermediate_size: int = 0, params_dtype=torch.bfloat16, n_shared_experts: int = 0,
+                 routed_scaling_factor: float = 1.0, first_k_dense: int = 0, chunk_size=None, num_bits: int = 4,
+                 krasis_engine: Optional[KrasisEngine] = None, num_moe_layers: int = 0, layer_group_size: int = 1,
+                 skip_shared_experts: bool = False, swiglu_limit: float = 0.0, rank: int = 0, num_ranks: int = 1,
+                 top_k: int = 0, max_tokens: int = 8192, scoring_func: str = "softmax", norm_topk_prob: bool = False):
+        if params_dtype != torch.bfloat16:
+            raise ValueError("only bfloat16 activations are supported")
+        if swiglu_limit > 0:
+            raise NotImplementedError("GPT-OSS activation (swiglu_limit > 0) is out of scope (SURVEY.md §8a)")
+        device = torch.device(device if device is not None else "cuda:0")
+        if krasis_engine is None:
+            krasis_engine = KrasisEngine(hidden_size=hidden_size, moe_intermediate_size=intermediate_size,
+                                         n_routed_experts=num_experts, num_experts_per_tok=top_k,
+                                         num_moe_layers=num_moe_layers, num_bits=num_bits, rank=rank,
+                                         num_ranks=num_ranks, scoring_func=scoring_func,
+                                         norm_topk_prob=norm_topk_prob,
+                                         routed_scaling_factor=routed_scaling_factor, max_tokens=max_tokens,
+                                         device=device.index or 0)
+        self._engine = krasis_engine
+        self.device = krasis_engine.device
+        self.num_experts = krasis_engine.num_experts()
+        self.rank, self.num_ranks = rank, num_ranks
+        self.expert_start, self.expert_end = krasis_engine.expert_start, krasis_engine.expert_end
+        self.num_local_experts = self.expert_end - self.expert_start
+        self.hidden_size, self.intermediate_size = krasis_engine.hidden_size(), krasis_engine.intermediate_size()
+        self.n_shared_experts = 0 if skip_shared_experts else n_shared_experts
+        self.routed_scaling_factor = routed_scaling_factor
+        self.num_bits = num_bits
+
+    def forward(self, moe_layer_idx: int, hidden_states: torch.Tensor, topk_ids: torch.Tensor,
+                topk_weights: torch.Tensor, routed_only: bool = False, shared_output: Optional[torch.Tensor] = None):
+        """gpu_prefill.py:4374-4484.  `shared_output` (optional, [M,H] bf16) is added after the rsf scaling,
+        which is what the reference does with its own shared-expert result (gpu_prefill.py:4471-4480)."""
+        torch.cuda.set_device(self.device)                     # gpu_prefill.py:4401
+        return self._engine.moe_forward(moe_layer_idx, hidden_states, topk_ids, topk_weights,
+                                        routed_only=routed_only, shared=shared_output)
