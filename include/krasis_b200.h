@@ -124,12 +124,33 @@ KB2_API int kb2_moe_forward_host(kb2_engine* e, int moe_layer_idx, const void* x
                          const float* topk_weights_host, void* out_host, int32_t num_tokens, int32_t routed_only,
                          void* stream);
 
+/* Prefill through a stack of MoE layers with HOST buffers: H2D of x [M][H] bf16, then for every layer in
+ * [first_layer, first_layer + n_layers): on-device routing (kb2_route) + kb2_moe_forward of the SAME x, then
+ * D2H of the last layer's output and a stream synchronise.  This is the shape of the reference's per-layer
+ * prefill loop (python/krasis/model.py:2944-2955 -> layer.py:562-723) restricted to the MoE blocks; it exists
+ * so end-to-end throughput can be measured through the C ABI with host<->device copies inside the call. */
+KB2_API int kb2_prefill_moe_stack_host(kb2_engine* e, const void* x_host, void* out_host, int32_t num_tokens,
+                                       int32_t first_layer, int32_t n_layers, void* stream);
+
 /* Introspection for tests / profiling: after a forward, copies the per-local-expert token counts
  * (int32 [E_local]) of the last call to host. */
 KB2_API int kb2_last_expert_counts(kb2_engine* e, int32_t* counts_host, void* stream);
 
 /* Number of kernels this library has launched since creation (bench.py reports it as gpu_launches). */
 KB2_API int64_t kb2_launch_count(const kb2_engine* e);
+
+/* Per-kernel device timing with CUDA events recorded on the launching stream (the reference's
+ * KRASIS_LAYER_TIMING / EP breakdown, python/krasis/model.py:2839-2860).  kb2_profile_collect synchronises the
+ * device and returns, per kernel class, the summed milliseconds and the number of launches since enable. */
+#define KB2_PROF_ROUTER_LOGITS 0
+#define KB2_PROF_ROUTER_TOPK 1
+#define KB2_PROF_BINNING 2
+#define KB2_PROF_GEMM1 3
+#define KB2_PROF_GEMM2 4
+#define KB2_PROF_COMBINE 5
+#define KB2_PROF_NUM 6
+KB2_API int kb2_profile_enable(kb2_engine* e, int on);
+KB2_API int kb2_profile_collect(kb2_engine* e, double* total_ms, int64_t* n_spans);
 
 #ifdef __cplusplus
 }

@@ -40,9 +40,14 @@ SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "kb2_moe_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_void_p]),
+    "kb2_prefill_moe_stack_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_void_p]),
     "kb2_last_expert_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "kb2_launch_count": (C.c_int64, [C.c_void_p]),
+    "kb2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "kb2_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
+PROF_NAMES = ["router_logits", "router_topk", "binning", "gemm1_gate_up_silu", "gemm2_down", "combine"]
 
 _lib = None
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/krasis_b200.h"
@@ -72,6 +73,28 @@ struct kb2_engine {
   float* w_tmp = nullptr;
   void *x_tmp = nullptr, *out_tmp = nullptr;
   int64_t launches = 0;
+  // optional per-kernel timing (CUDA events on the launching stream)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_spans[KB2_PROF_NUM];   // (begin, end) indices into ev_pool
+  size_t ev_used = 0;
+};
+
+struct ProfSpan {
+  kb2_engine* e; int which; cudaStream_t s; int b = -1;
+  ProfSpan(kb2_engine* e_, int w, cudaStream_t s_) : e(e_), which(w), s(s_) {
+    if (!e->profiling) return;
+    if (e->ev_used + 2 > e->ev_pool.size()) {
+      for (int i = 0; i < 256; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev_pool.push_back(ev); }
+    }
+    b = (int)e->ev_used; e->ev_used += 2;
+    cudaEventRecord(e->ev_pool[b], s);
+  }
+  ~ProfSpan() {
+    if (b < 0) return;
+    cudaEventRecord(e->ev_pool[b + 1], s);
+    e->ev_spans[which].push_back({b, b + 1});
+  }
 };
 
 static size_t tile_bytes_per_weight(int fmt) { return fmt == KB2_FMT_INT4_G128 ? 1 : 2; }  // half-bytes x2
@@ -165,6 +188,7 @@ KB2_API void kb2_destroy(kb2_engine* e) {
   }
   cudaFree(e->counts); cudaFree(e->offsets); cudaFree(e->cursor); cudaFree(e->n_chunks); cudaFree(e->chunks);
   cudaFree(e->sorted_token); cudaFree(e->slot_of); cudaFree(e->sorted_w); cudaFree(e->act); cudaFree(e->c3);
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   cudaFree(e->logits); cudaFree(e->ids_tmp); cudaFree(e->w_tmp); cudaFree(e->x_tmp); cudaFree(e->out_tmp);
   delete e;
 }
@@ -272,7 +296,9 @@ KB2_API int kb2_route(kb2_engine* e, int layer, const void* hidden, int32_t M, i
   if (!hidden || !ids || !wts) return fail(KB2_ERR_VALUE, "null argument");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(launch_router_logits(hidden, L.gate, L.gate_bias, e->logits, M, e->cfg.n_routed_experts, e->cfg.hidden_size, s));
+  { ProfSpan ps(e, KB2_PROF_ROUTER_LOGITS, s);
+    CUDA_TRY(launch_router_logits(hidden, L.gate, L.gate_bias, e->logits, M, e->cfg.n_routed_experts, e->cfg.hidden_size, s)); }
+  ProfSpan ps2(e, KB2_PROF_ROUTER_TOPK, s);
   CUDA_TRY(launch_router_topk(e->logits, L.corr_bias, M, e->cfg.n_routed_experts, e->cfg.num_experts_per_tok,
                               e->cfg.scoring_func, e->cfg.norm_topk_prob, ids, wts, s));
   e->launches += 2;
@@ -292,8 +318,9 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
   const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, K = e->cfg.num_experts_per_tok;
   const int fmt = e->cfg.weight_format;
 
-  CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
-                          e->n_chunks, e->sorted_token, e->sorted_w, e->slot_of, s));
+  { ProfSpan ps(e, KB2_PROF_BINNING, s);
+    CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
+                            e->n_chunks, e->sorted_token, e->sorted_w, e->slot_of, s)); }
   e->launches += 3;
 
   GemmParams g1{};
@@ -305,7 +332,8 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
   g1.b_src = (const __nv_bfloat16*)x; g1.b_ld = H; g1.b_row_index = e->sorted_token;
   g1.chunks = e->chunks; g1.n_chunks = e->n_chunks;
   g1.out = (__nv_bfloat16*)e->act; g1.out_ld = I; g1.slot_weight = nullptr;
-  CUDA_TRY(launch_grouped_gemm(fmt, true, g1, e->num_sms, s));
+  { ProfSpan ps(e, KB2_PROF_GEMM1, s);
+    CUDA_TRY(launch_grouped_gemm(fmt, true, g1, e->num_sms, s)); }
 
   GemmParams g2{};
   g2.wq = L.w2_q; g2.ws = L.w2_s;
@@ -316,11 +344,13 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
   g2.b_src = (const __nv_bfloat16*)e->act; g2.b_ld = I; g2.b_row_index = nullptr;
   g2.chunks = e->chunks; g2.n_chunks = e->n_chunks;
   g2.out = (__nv_bfloat16*)e->c3; g2.out_ld = H; g2.slot_weight = e->sorted_w;
-  CUDA_TRY(launch_grouped_gemm(fmt, false, g2, e->num_sms, s));
+  { ProfSpan ps(e, KB2_PROF_GEMM2, s);
+    CUDA_TRY(launch_grouped_gemm(fmt, false, g2, e->num_sms, s)); }
 
   const int apply = routed_only ? 0 : 1;
-  CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply,
-                          routed_only ? nullptr : shared, out, s));
+  { ProfSpan ps(e, KB2_PROF_COMBINE, s);
+    CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply,
+                            routed_only ? nullptr : shared, out, s)); }
   e->launches += 3;
   return KB2_OK;
 }
@@ -348,11 +378,58 @@ KB2_API int kb2_moe_forward_host(kb2_engine* e, int layer, const void* x_host, c
   return KB2_OK;
 }
 
+KB2_API int kb2_prefill_moe_stack_host(kb2_engine* e, const void* x_host, void* out_host, int32_t M, int32_t first_layer,
+                                       int32_t n_layers, void* stream) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  if (first_layer < 0 || n_layers < 1 || first_layer + n_layers > (int)e->layers.size())
+    return fail(KB2_ERR_VALUE, "layer range [%d, %d) outside [0, %d)", first_layer, first_layer + n_layers, (int)e->layers.size());
+  if (M < 1 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [1, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (!x_host || !out_host) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t H = e->cfg.hidden_size;
+  CUDA_TRY(cudaMemcpyAsync(e->x_tmp, x_host, (size_t)M * H * 2, cudaMemcpyHostToDevice, s));
+  for (int l = first_layer; l < first_layer + n_layers; ++l) {
+    if (int r = kb2_route(e, l, e->x_tmp, M, e->ids_tmp, e->w_tmp, stream)) return r;
+    if (int r = kb2_moe_forward(e, l, e->x_tmp, e->ids_tmp, e->w_tmp, e->out_tmp, M, 0, nullptr, stream)) return r;
+  }
+  CUDA_TRY(cudaMemcpyAsync(out_host, e->out_tmp, (size_t)M * H * 2, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return KB2_OK;
+}
+
 KB2_API int kb2_last_expert_counts(kb2_engine* e, int32_t* counts_host, void* stream) {
   if (!e || !counts_host) return fail(KB2_ERR_VALUE, "null argument");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   CUDA_TRY(cudaMemcpyAsync(counts_host, e->counts, sizeof(int) * e->e_local, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_profile_enable(kb2_engine* e, int on) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  e->profiling = on != 0;
+  e->ev_used = 0;
+  for (auto& v : e->ev_spans) v.clear();
+  return KB2_OK;
+}
+
+KB2_API int kb2_profile_collect(kb2_engine* e, double* total_ms, int64_t* n_spans) {
+  if (!e || !total_ms || !n_spans) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int k = 0; k < KB2_PROF_NUM; ++k) {
+    double t = 0;
+    for (auto& sp : e->ev_spans[k]) {
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, e->ev_pool[sp.first], e->ev_pool[sp.second]));
+      t += ms;
+    }
+    total_ms[k] = t;
+    n_spans[k] = (int64_t)e->ev_spans[k].size();
+    e->ev_spans[k].clear();
+  }
+  e->ev_used = 0;
   return KB2_OK;
 }
 

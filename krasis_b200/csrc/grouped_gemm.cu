@@ -25,7 +25,6 @@
 namespace kb2 {
 
 constexpr int kNumThreads = 384;
-constexpr int kStagesW = 4;   // packed-weight ring
 constexpr int kStagesA = 2;   // dequantised A ring
 constexpr int kStagesB = 3;   // token (B operand) ring
 constexpr int kATileBytes = kTileRows * kBlockK * 2;            // 16 KB (bf16)
@@ -42,14 +41,17 @@ struct Fmt;
 template <>
 struct Fmt<kFmtInt4G128> {
   static constexpr int kTileBytes = kInt4TileBytes;
+  static constexpr int kStagesW = 4;   // packed-weight ring depth
 };
 template <>
 struct Fmt<kFmtInt8G128> {
   static constexpr int kTileBytes = kInt8TileBytes;
+  static constexpr int kStagesW = 2;   // 16.5 KB per stage: keep the CTA under 227 KB
 };
 
 template <int FMT>
 struct SmemLayout {
+  static constexpr int kStagesW = Fmt<FMT>::kStagesW;
   static constexpr int kWStageBytes = 2 * Fmt<FMT>::kTileBytes + 2 * kScaleTileBytes;
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kOffA + kStagesA * kAStageBytes;
@@ -59,6 +61,7 @@ struct SmemLayout {
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
+  static_assert(kDynamic <= 227 * 1024, "CTA shared memory exceeds the 227 KB sm_100 limit");
 };
 
 struct Ring {
@@ -89,6 +92,7 @@ __device__ __forceinline__ uint32_t deq_pair_int4(uint32_t w_shifted, __nv_bfloa
 template <int FMT, bool kGemm1>
 __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const GemmParams p) {
   using L = SmemLayout<FMT>;
+  constexpr int kStagesW = L::kStagesW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);

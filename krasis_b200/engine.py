@@ -195,6 +195,26 @@ class KrasisEngine:
                                                   _stream_ptr(self.device)))
         return out_host
 
+    def prefill_moe_stack_host(self, x_host: torch.Tensor, out_host: torch.Tensor, first_layer=0, n_layers=None):
+        """H2D x, route + MoE forward through layers [first_layer, first_layer+n_layers), D2H last output."""
+        if x_host.is_cuda or out_host.is_cuda or x_host.dtype != torch.bfloat16 or out_host.dtype != torch.bfloat16:
+            raise ValueError("x_host/out_host must be CPU bf16 tensors")
+        n_layers = self._cfg.num_moe_layers - first_layer if n_layers is None else n_layers
+        capi.check(self._lib.kb2_prefill_moe_stack_host(self._h, x_host.data_ptr(), out_host.data_ptr(),
+                                                        x_host.shape[0], first_layer, n_layers,
+                                                        _stream_ptr(self.device)))
+        return out_host
+
+    def profile(self, on: bool):
+        capi.check(self._lib.kb2_profile_enable(self._h, int(bool(on))))
+
+    def profile_collect(self):
+        """-> {kernel class: (total_ms, launches)} since profile(True); synchronises the device."""
+        ms = (C.c_double * len(capi.PROF_NAMES))()
+        n = (C.c_int64 * len(capi.PROF_NAMES))()
+        capi.check(self._lib.kb2_profile_collect(self._h, ms, n))
+        return {name: (ms[i], n[i]) for i, name in enumerate(capi.PROF_NAMES)}
+
     def last_expert_counts(self) -> np.ndarray:
         out = np.zeros(self.expert_end - self.expert_start, np.int32)
         capi.check(self._lib.kb2_last_expert_counts(self._h, out.ctypes.data, _stream_ptr(self.device)))
