@@ -45,6 +45,18 @@ def peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def host_threads():
+    """Threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -53,10 +65,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self._stop = gpu_index, [], threading.Event()
+        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
@@ -64,10 +76,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
         reasons = set()
@@ -99,7 +111,7 @@ def cpu_sample(budget_s=15.0, n_weight_sets=2, threads=0):
         s13 = ((rng.uniform(0.004, 0.012, (E, H // 128, 2 * I)).astype(np.float32).view(np.uint32) + 0x8000) >> 16).astype(np.uint16)
         s2 = ((rng.uniform(0.004, 0.012, (E, I // 128, H)).astype(np.float32).view(np.uint32) + 0x8000) >> 16).astype(np.uint16)
         sets.append((w13, s13, w2, s2))
-    nthreads = threads or (os.cpu_count() or 1)
+    avail = host_threads()
 
     def run(n_tok):
         x = rng.normal(0, 1, (n_tok, H)).astype(np.float32)
@@ -112,11 +124,23 @@ def cpu_sample(budget_s=15.0, n_weight_sets=2, threads=0):
             cpu_ref.moe_forward_int4(*sets[l % n_weight_sets], xb, ids, w, nthreads=nthreads)
         return time.perf_counter() - t0
 
+    # "all the host threads it can use": the flattened dispatch has 40-80 work items per phase
+    # (src/moe.rs:727-740), so more threads than that only add barrier cost; pick the fastest of a few
+    # thread counts on a 2-token probe and say which.
+    nthreads = threads or avail
     run(1)                                                # warms the thread pool, first-touches the weights
+    if not threads:
+        best = None
+        for cand in sorted({c for c in (8, 16, 32, 64, avail) if c <= avail}):
+            nthreads = cand
+            t = run(2) / 2
+            if best is None or t < best[0]:
+                best = (t, cand)
+        nthreads = best[1]
     t1 = run(4) / 4                                       # calibration
     n_tok = int(max(2, min(4096, budget_s / max(t1, 1e-4))))
     dt = run(n_tok)
-    return dict(value=n_tok / dt, unit="tokens/s", cores=nthreads, kind="port",
+    return dict(value=n_tok / dt, unit="tokens/s", cores=nthreads, host_threads_available=avail, kind="port",
                 sample=f"{n_tok} tokens x {L} MoE layer passes, QCN geometry, {n_weight_sets} random weight sets cycled; "
                        f"C/AVX2 port of src/moe.rs:572-715 + src/kernel/avx2.rs:1066-1206 ({dt:.1f}s)"), n_tok, dt
 

@@ -309,8 +309,8 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
                     int32_t M, int32_t routed_only, const void* shared, void* stream) {
   if (int r = check_layer(e, layer)) return r;
   LayerWeights& L = e->layers[layer];
-  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
   if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
   if (M == 0) return KB2_OK;
   if (!x || !ids || !wts || !out) return fail(KB2_ERR_VALUE, "null argument");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
