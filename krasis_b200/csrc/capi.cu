@@ -12,14 +12,17 @@
 #include "moe_common.cuh"
 
 namespace kb2 {
-cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, const void* tmap_b, int num_sms,
+                                cudaStream_t stream);
+cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
+int gemm_b_box_rows();
 cudaError_t launch_router_logits(const void* h, const void* gate, const float* bias, float* logits, int M, int E,
                                  int H, cudaStream_t s);
 cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int M, int E, int top_k, int scoring,
                                int renorm, int* ids, float* wts, cudaStream_t s);
 cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
-                           int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, int* sorted_token,
-                           float* sorted_w, int* slot_of, cudaStream_t s);
+                           int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
+                           const void* x, void* x_sorted, int H, cudaStream_t s);
 cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
                            const void* shared, void* out, cudaStream_t s);
 cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,
@@ -65,7 +68,10 @@ struct kb2_engine {
   // scratch (sized for cfg.max_tokens)
   int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *n_chunks = nullptr;
   ChunkDesc* chunks = nullptr;
-  int *sorted_token = nullptr, *slot_of = nullptr;
+  int* slot_of = nullptr;
+  void* x_sorted = nullptr;                        // [max_tokens*k][H] bf16: per-expert contiguous token tiles
+  alignas(64) unsigned char tmap_x[128];           // CUtensorMap over x_sorted (GEMM1 B operand)
+  alignas(64) unsigned char tmap_act[128];         // CUtensorMap over act      (GEMM2 B operand)
   float* sorted_w = nullptr;
   void *act = nullptr, *c3 = nullptr;
   float* logits = nullptr;
@@ -156,7 +162,7 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   ALLOC(e->cursor, sizeof(int) * e->e_local);
   ALLOC(e->n_chunks, sizeof(int));
   ALLOC(e->chunks, sizeof(ChunkDesc) * max_chunks);
-  ALLOC(e->sorted_token, sizeof(int) * MK);
+  ALLOC(e->x_sorted, MK * c->hidden_size * 2);
   ALLOC(e->slot_of, sizeof(int) * MK);
   ALLOC(e->sorted_w, sizeof(float) * MK);
   ALLOC(e->act, MK * c->moe_intermediate_size * 2);
@@ -167,6 +173,8 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   ALLOC(e->x_tmp, (size_t)c->max_tokens * c->hidden_size * 2);
   ALLOC(e->out_tmp, (size_t)c->max_tokens * c->hidden_size * 2);
 #undef ALLOC
+  CUDA_TRY(make_tmap_bf16_rows(e->tmap_x, e->x_sorted, (long long)MK, c->hidden_size, gemm_b_box_rows()));
+  CUDA_TRY(make_tmap_bf16_rows(e->tmap_act, e->act, (long long)MK, c->moe_intermediate_size, gemm_b_box_rows()));
   *out = e;
   return KB2_OK;
 }
@@ -187,7 +195,7 @@ KB2_API void kb2_destroy(kb2_engine* e) {
     cudaFree(L.gate); cudaFree(L.gate_bias); cudaFree(L.corr_bias);
   }
   cudaFree(e->counts); cudaFree(e->offsets); cudaFree(e->cursor); cudaFree(e->n_chunks); cudaFree(e->chunks);
-  cudaFree(e->sorted_token); cudaFree(e->slot_of); cudaFree(e->sorted_w); cudaFree(e->act); cudaFree(e->c3);
+  cudaFree(e->x_sorted); cudaFree(e->slot_of); cudaFree(e->sorted_w); cudaFree(e->act); cudaFree(e->c3);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   cudaFree(e->logits); cudaFree(e->ids_tmp); cudaFree(e->w_tmp); cudaFree(e->x_tmp); cudaFree(e->out_tmp);
   delete e;
@@ -320,7 +328,7 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
 
   { ProfSpan ps(e, KB2_PROF_BINNING, s);
     CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
-                            e->n_chunks, e->sorted_token, e->sorted_w, e->slot_of, s)); }
+                            e->n_chunks, e->sorted_w, e->slot_of, x, e->x_sorted, H, s)); }
   e->launches += 3;
 
   GemmParams g1{};
@@ -329,11 +337,10 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
   g1.ws_expert_stride = (long long)(tiled_bytes(e, 1) / e->e_local);
   g1.n_kblocks = H / kBlockK;
   g1.items_per_chunk = I / kTileRows; g1.tile1_offset = I / kTileRows; g1.tile0_mul = 1;
-  g1.b_src = (const __nv_bfloat16*)x; g1.b_ld = H; g1.b_row_index = e->sorted_token;
   g1.chunks = e->chunks; g1.n_chunks = e->n_chunks;
   g1.out = (__nv_bfloat16*)e->act; g1.out_ld = I; g1.slot_weight = nullptr;
   { ProfSpan ps(e, KB2_PROF_GEMM1, s);
-    CUDA_TRY(launch_grouped_gemm(fmt, true, g1, e->num_sms, s)); }
+    CUDA_TRY(launch_grouped_gemm(fmt, true, g1, e->tmap_x, e->num_sms, s)); }
 
   GemmParams g2{};
   g2.wq = L.w2_q; g2.ws = L.w2_s;
@@ -341,11 +348,10 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
   g2.ws_expert_stride = (long long)(tiled_bytes(e, 3) / e->e_local);
   g2.n_kblocks = I / kBlockK;
   g2.items_per_chunk = H / (2 * kTileRows); g2.tile1_offset = 1; g2.tile0_mul = 2;
-  g2.b_src = (const __nv_bfloat16*)e->act; g2.b_ld = I; g2.b_row_index = nullptr;
   g2.chunks = e->chunks; g2.n_chunks = e->n_chunks;
   g2.out = (__nv_bfloat16*)e->c3; g2.out_ld = H; g2.slot_weight = e->sorted_w;
   { ProfSpan ps(e, KB2_PROF_GEMM2, s);
-    CUDA_TRY(launch_grouped_gemm(fmt, false, g2, e->num_sms, s)); }
+    CUDA_TRY(launch_grouped_gemm(fmt, false, g2, e->tmap_act, e->num_sms, s)); }
 
   const int apply = routed_only ? 0 : 1;
   { ProfSpan ps(e, KB2_PROF_COMBINE, s);

@@ -1,38 +1,50 @@
-// Grouped W4A16 / W8A16 expert GEMM for MoE prefill on sm_100a (tcgen05 + TMEM + bulk TMA).
+// Grouped W4A16 / W8A16 expert GEMM for MoE prefill on sm_100a (tcgen05 + TMEM + TMA).
 //
 // Replaces the two `moe_wna16_marlin_gemm` launches + `silu_and_mul` of the reference's
 // `fused_marlin_moe` call sequence (python/krasis/gpu_prefill.py:152-226; survey K3/K4/K5).
 //
 // Orientation ("swap-AB"): per expert the weight matrix is the UMMA *A* operand (M = 128 weight rows
-// per MMA) and the expert's token rows are the *B* operand (N = tokens, any multiple of 16 up to 256),
+// per MMA) and the expert's token rows are the *B* operand (N = tokens, any multiple of 16 up to 192),
 // so an expert with 160 routed tokens costs exactly N=160, not a 128-row token tile padded to 256.
 // The accumulator D^T[weight_row, token] lives in TMEM (lane = weight row, column = token).
 //
-// One CTA per SM, persistent over work items (chunk of tokens of one expert) x (pair of weight tiles):
+// Dataflow per CTA (one per SM, persistent over (token chunk of one expert) x (pair of weight tiles)):
+//   HBM --bulk TMA--> packed INT4/INT8 tiles in smem --dequant warps--> BF16 x group scale
+//       --tcgen05.st--> A operand in TENSOR MEMORY (never touches shared memory as BF16)
+//   sorted token rows --2-D TMA, 128B swizzle--> B operand in smem
+//   tcgen05.mma (A from TMEM, B from smem) --> two FP32 accumulators in TMEM
+//   epilogue warps: tcgen05.ld -> SiLU(gate)*up | x routing weight -> BF16 -> smem staging -> 16 B coalesced stores
+// Keeping the dequantised A operand out of shared memory matters: a BF16 SS-MMA at M=128 reads
+// (128+N)*32 B of smem per N/2 cycles (~115 B/clk at N=160), which together with the dequant stores
+// exceeded the 128 B/clk smem port in the first version of this kernel (profiles/r01a_*).
 //   GEMM1: the pair is (gate tile t, up tile t) -> SiLU(gate)*up fused in the epilogue, BF16 act out
 //   GEMM2: the pair is two consecutive down-proj tiles -> x routing weight, BF16 c3 out
 // Warp roles (384 threads):
 //   warp 0      : bulk-TMA producer of packed weight tiles + scale tiles (one elected lane)
 //   warp 1      : tcgen05.mma issuer (one elected lane)
-//   warps 2-3   : token-row gather (cp.async 16 B, writes the 128B-swizzled K-major B operand)
-//   warps 4-7   : dequantisers: packed INT4/INT8 (smem) -> BF16 x group scale -> 128B-swizzled A operand
-//   warps 8-11  : epilogue: tcgen05.ld -> activation / weight -> global
+//   warp 2      : 2-D TMA producer of the token (B) operand (one elected lane)
+//   warps 4-7   : dequantisers (thread t owns weight row t of both tiles = TMEM lane t)
+//   warps 8-11  : epilogue
+// TMEM columns: [0,192) acc0 | [192,384) acc1 | [384,512) two A stages x (tile0 32 cols | tile1 32 cols)
 // Numerics (oracle/moe.py, GPU-path): W = bf16((nib-8)*scale) exactly as Marlin's BF16 dequant,
 // fp32 accumulation in TMEM, BF16 rounding at C1, A and C3.
+#include <cuda.h>
+
 #include "moe_common.cuh"
 #include "ptx.cuh"
 
 namespace kb2 {
 
 constexpr int kNumThreads = 384;
-constexpr int kStagesA = 2;   // dequantised A ring
-constexpr int kStagesB = 3;   // token (B operand) ring
-constexpr int kATileBytes = kTileRows * kBlockK * 2;            // 16 KB (bf16)
-constexpr int kAStageBytes = 2 * kATileBytes;                   // two weight tiles per stage
-constexpr int kBStageBytes = kMaxChunkTokens * kBlockK * 2;     // 32 KB
+constexpr int kStagesA = 2;                                     // A operand stages in TMEM
+constexpr int kStagesB = 3;                                     // token (B operand) ring in smem
+constexpr int kBStageBytes = kMaxChunkTokens * kBlockK * 2;     // 24 KB
+constexpr int kBBoxRows = 32;                                   // TMA box = 32 token rows x 64 K
+constexpr int kBBoxBytes = kBBoxRows * kBlockK * 2;             // 4 KB
 constexpr int kTmemCols = 512;
-constexpr int kAcc1Col = 256;
-constexpr int kNumLoaderThreads = 64;
+constexpr int kAcc1Col = kMaxChunkTokens;                       // 192
+constexpr int kATmemCol = 2 * kMaxChunkTokens;                  // 384
+constexpr int kATileCols = kBlockK / 2;                         // 32 columns = 128 rows x 64 bf16
 constexpr int kNumDequantThreads = 128;
 constexpr int kNumEpiThreads = 128;
 
@@ -46,22 +58,23 @@ struct Fmt<kFmtInt4G128> {
 template <>
 struct Fmt<kFmtInt8G128> {
   static constexpr int kTileBytes = kInt8TileBytes;
-  static constexpr int kStagesW = 2;   // 16.5 KB per stage: keep the CTA under 227 KB
+  static constexpr int kStagesW = 2;
 };
 
-template <int FMT>
+template <int FMT, bool kGemm1>
 struct SmemLayout {
   static constexpr int kStagesW = Fmt<FMT>::kStagesW;
   static constexpr int kWStageBytes = 2 * Fmt<FMT>::kTileBytes + 2 * kScaleTileBytes;
-  static constexpr int kOffA = 0;
-  static constexpr int kOffB = kOffA + kStagesA * kAStageBytes;
-  static constexpr int kOffW = kOffB + kStagesB * kBStageBytes;
+  static constexpr int kStageRowBytes = (kGemm1 ? 1 : 2) * kTileRows * 2;      // epilogue staging: 256 B | 512 B per token
+  static constexpr int kOffB = 0;                                               // 1024-aligned (swizzle atoms)
+  static constexpr int kOffStage = kOffB + kStagesB * kBStageBytes;
+  static constexpr int kOffW = kOffStage + kMaxChunkTokens * kStageRowBytes;
   static constexpr int kOffBar = kOffW + kStagesW * kWStageBytes;
   static constexpr int kNumBars = 2 * kStagesW + 2 * kStagesA + 2 * kStagesB + 2;
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
-  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024 B alignment
-  static_assert(kDynamic <= 227 * 1024, "CTA shared memory exceeds the 227 KB sm_100 limit");
+  static_assert(kTotal <= 227 * 1024, "CTA shared memory exceeds the 227 KB sm_100 limit");
+  static_assert(kOffW % 16 == 0 && kOffBar % 8 == 0, "alignment");
 };
 
 struct Ring {
@@ -90,11 +103,12 @@ __device__ __forceinline__ uint32_t deq_pair_int4(uint32_t w_shifted, __nv_bfloa
 }
 
 template <int FMT, bool kGemm1>
-__global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const GemmParams p) {
-  using L = SmemLayout<FMT>;
+__global__ void __launch_bounds__(kNumThreads, 1)
+    grouped_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_b) {
+  using L = SmemLayout<FMT, kGemm1>;
   constexpr int kStagesW = L::kStagesW;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int TB = Fmt<FMT>::kTileBytes;
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* w_full = bars;
   uint64_t* w_empty = w_full + kStagesW;
@@ -110,6 +124,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 32) {
+    if (smem_u32(smem) & 1023u) __trap();   // the 128B-swizzle atoms need a 1024 B aligned base
     for (int i = 0; i < kStagesW; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], kNumDequantThreads);
@@ -119,7 +134,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < kStagesB; ++i) {
-      mbar_init(&b_full[i], kNumLoaderThreads);
+      mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
     mbar_init(tmem_full, 1);
@@ -127,6 +142,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  if (threadIdx.x == 64) prefetch_tmap(&tmap_b);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -151,7 +167,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
           mbar_wait(&w_empty[rw.stage], rw.phase ^ 1);
           uint8_t* dst = smem + L::kOffW + rw.stage * L::kWStageBytes;
           mbar_arrive_expect_tx(&w_full[rw.stage], L::kWStageBytes);
-          constexpr int TB = Fmt<FMT>::kTileBytes;
           bulk_g2s(dst, wq_e + ((long long)t0 * nkb + kb) * TB, TB, &w_full[rw.stage]);
           bulk_g2s(dst + TB, wq_e + ((long long)t1 * nkb + kb) * TB, TB, &w_full[rw.stage]);
           bulk_g2s(dst + 2 * TB, ws_e + ((long long)t0 * ngroups + (kb >> 1)) * kScaleTileBytes, kScaleTileBytes,
@@ -178,16 +193,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
           mbar_wait(&a_full[ra.stage], ra.phase);
           mbar_wait(&b_full[rb.stage], rb.phase);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + L::kOffA + ra.stage * kAStageBytes);
-          const uint32_t b_addr = smem_u32(smem + L::kOffB + rb.stage * kBStageBytes);
-          const uint64_t a0 = umma_desc_k_sw128(a_addr);
-          const uint64_t a1 = umma_desc_k_sw128(a_addr + kATileBytes);
-          const uint64_t b0 = umma_desc_k_sw128(b_addr);
+          const uint32_t a_t = tmem_base + kATmemCol + ra.stage * 2 * kATileCols;
+          const uint64_t b0 = umma_desc_k_sw128(smem_u32(smem + L::kOffB + rb.stage * kBStageBytes));
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_bf16(tmem_base, a0 + 2 * k, b0 + 2 * k, idesc, acc);
-            umma_bf16(tmem_base + kAcc1Col, a1 + 2 * k, b0 + 2 * k, idesc, acc);
+            umma_bf16_ts(tmem_base, a_t + 8 * k, b0 + 2 * k, idesc, acc);
+            umma_bf16_ts(tmem_base + kAcc1Col, a_t + kATileCols + 8 * k, b0 + 2 * k, idesc, acc);
           }
           umma_commit(&a_empty[ra.stage]);
           umma_commit(&b_empty[rb.stage]);
@@ -199,112 +211,80 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ------------------------------------------------------------ token-row gather (B operand)
-    const int lt = threadIdx.x - 64;   // 0..63
-    const int c = lt & 7;              // 16-byte chunk within the 128 B k-block row
-    const int r0 = lt >> 3;            // row within the 8-row swizzle group
-    Ring rb;
-    int pending_stage = -1;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
-      const int n_pad = (cd.n_tok + 15) & ~15;
-      const int n_pass = n_pad >> 3;
-      long long roff[kMaxChunkTokens / 8];
-#pragma unroll
-      for (int i = 0; i < kMaxChunkTokens / 8; ++i) {
-        int row = i * 8 + r0;
-        int slot = cd.slot_begin + (row < cd.n_tok ? row : 0);
-        int src_row = p.b_row_index ? p.b_row_index[slot] : slot;
-        roff[i] = (long long)src_row * p.b_ld + c * 8;
-        if (i >= n_pass) roff[i] = roff[0];
-      }
-      const uint32_t dst_off = r0 * 128 + ((c ^ r0) << 4);
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
-        uint8_t* dst = smem + L::kOffB + rb.stage * kBStageBytes + dst_off;
-        const __nv_bfloat16* src = p.b_src + kb * kBlockK;
-#pragma unroll
-        for (int i = 0; i < kMaxChunkTokens / 8; ++i) {
-          if (i < n_pass) cp_async16(dst + i * 1024, src + roff[i]);
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ token (B operand) producer: 2-D TMA
+    if (lane == 0) {
+      Ring rb;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
+        const int n_pad = (cd.n_tok + 15) & ~15;
+        const int n_box = (n_pad + kBBoxRows - 1) / kBBoxRows;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
+          uint8_t* dst = smem + L::kOffB + rb.stage * kBStageBytes;
+          mbar_arrive_expect_tx(&b_full[rb.stage], n_box * kBBoxBytes);
+          for (int b = 0; b < n_box; ++b)
+            tma_load_2d(dst + b * kBBoxBytes, &tmap_b, kb * kBlockK, cd.slot_begin + b * kBBoxRows, &b_full[rb.stage]);
+          rb.advance(kStagesB);
         }
-        cp_async_commit();
-        if (pending_stage >= 0) {
-          cp_async_wait<1>();
-          fence_proxy_async_smem();
-          mbar_arrive(&b_full[pending_stage]);
-        }
-        pending_stage = rb.stage;
-        rb.advance(kStagesB);
       }
     }
-    if (pending_stage >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      mbar_arrive(&b_full[pending_stage]);
-    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // idle
   } else if (warp < 8) {
-    // ------------------------------------------------------------ dequantisers (A operand)
-    const int t = threadIdx.x - 128;   // weight row within the tile, 0..127
+    // ------------------------------------------------------------ dequantisers -> A operand in TMEM
+    const int t = threadIdx.x - 128;   // weight row within the tile == TMEM lane
     Ring rw, ra;
-    const uint32_t row_off = (t >> 3) * 1024 + (t & 7) * 128;
-    const uint32_t sw = (t & 7);
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kATmemCol;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&w_full[rw.stage], rw.phase);
-        mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
         const uint8_t* wsrc = smem + L::kOffW + rw.stage * L::kWStageBytes;
-        uint8_t* adst = smem + L::kOffA + ra.stage * kAStageBytes + row_off;
-        constexpr int TB = Fmt<FMT>::kTileBytes;
         const __nv_bfloat16* sc = reinterpret_cast<const __nv_bfloat16*>(wsrc + 2 * TB);
+        mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
+        tc_fence_after_sync();
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile) {
           const __nv_bfloat16 s = sc[tile * kTileRows + t];
-          const __nv_bfloat162 s2 = __halves2bfloat162(s, s);
+          uint32_t o[32];
           if constexpr (FMT == kFmtInt4G128) {
+            const __nv_bfloat162 s2 = __halves2bfloat162(s, s);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + h * 2048 + t * 16);
               const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = deq_pair_int4(ww[j], s2);
-                o.y = deq_pair_int4(ww[j] >> 4, s2);
-                o.z = deq_pair_int4(ww[j] >> 8, s2);
-                o.w = deq_pair_int4(ww[j] >> 12, s2);
-                const uint32_t chunk = h * 4 + j;
-                *reinterpret_cast<uint4*>(adst + tile * kATileBytes + ((chunk ^ sw) << 4)) = o;
+                o[h * 16 + j * 4 + 0] = deq_pair_int4(ww[j], s2);
+                o[h * 16 + j * 4 + 1] = deq_pair_int4(ww[j] >> 4, s2);
+                o[h * 16 + j * 4 + 2] = deq_pair_int4(ww[j] >> 8, s2);
+                o[h * 16 + j * 4 + 3] = deq_pair_int4(ww[j] >> 12, s2);
               }
             }
           } else {
-            // INT8: [quarter q in 0..3][row][16 B] = 16 consecutive K columns per 16 B
+            // INT8 tile: [quarter q in 0..3][row][16 B], 16 consecutive K columns per 16 B
             const float sf = __bfloat162float(s);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + q * 2048 + t * 16);
               const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const uint32_t word = ww[hh * 2 + (e >> 1)];
-                  const int b0 = (int)(int8_t)((word >> ((e & 1) * 16)) & 0xFF);
-                  const int b1 = (int)(int8_t)((word >> ((e & 1) * 16 + 8)) & 0xFF);
-                  __nv_bfloat162 v = __floats2bfloat162_rn((float)b0 * sf, (float)b1 * sf);
-                  o[e] = *reinterpret_cast<uint32_t*>(&v);
-                }
-                const uint32_t chunk = q * 2 + hh;
-                *reinterpret_cast<uint4*>(adst + tile * kATileBytes + ((chunk ^ sw) << 4)) =
-                    make_uint4(o[0], o[1], o[2], o[3]);
+              for (int e = 0; e < 8; ++e) {
+                const uint32_t word = ww[e >> 1];
+                const int b0 = (int)(int8_t)((word >> ((e & 1) * 16)) & 0xFF);
+                const int b1 = (int)(int8_t)((word >> ((e & 1) * 16 + 8)) & 0xFF);
+                __nv_bfloat162 v = __floats2bfloat162_rn((float)b0 * sf, (float)b1 * sf);
+                o[q * 8 + e] = *reinterpret_cast<uint32_t*>(&v);
               }
             }
           }
+          tmem_st32(lane_base + ra.stage * 2 * kATileCols + tile * kATileCols, o);
         }
-        fence_proxy_async_smem();
+        mbar_arrive(&w_empty[rw.stage]);     // packed words are in registers / TMEM stores issued
+        tmem_st_wait();
+        tc_fence_before_sync();
         mbar_arrive(&a_full[ra.stage]);
-        mbar_arrive(&w_empty[rw.stage]);
         rw.advance(kStagesW);
         ra.advance(kStagesA);
       }
@@ -313,6 +293,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;             // weight row within the 128-row tile
+    const int et = threadIdx.x - 256;          // 0..127
+    uint8_t* stage = smem + L::kOffStage;
+    constexpr int kRowB = L::kStageRowBytes;
+    constexpr int kVecPerRow = kRowB / 16;
     uint32_t tphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
@@ -329,26 +313,34 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int tok = c0 + j;
-          if (tok < cd.n_tok) {
-            const long long slot = cd.slot_begin + tok;
-            const float v0 = __uint_as_float(r0v[j]);
-            const float v1 = __uint_as_float(r1v[j]);
-            if constexpr (kGemm1) {
-              const float g = __bfloat162float(__float2bfloat16_rn(v0));
-              const float u = __bfloat162float(__float2bfloat16_rn(v1));
-              p.out[slot * p.out_ld + rt * kTileRows + row] = __float2bfloat16_rn(silu_f(g) * u);
-            } else {
-              const float wgt = p.slot_weight[slot];
-              __nv_bfloat16* o = p.out + slot * p.out_ld + rt * 2 * kTileRows + row;
-              o[0] = __float2bfloat16_rn(wgt * v0);
-              o[kTileRows] = __float2bfloat16_rn(wgt * v1);
-            }
+          const float v0 = __uint_as_float(r0v[j]);
+          const float v1 = __uint_as_float(r1v[j]);
+          __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + tok * kRowB);
+          if constexpr (kGemm1) {
+            const float g = __bfloat162float(__float2bfloat16_rn(v0));
+            const float u = __bfloat162float(__float2bfloat16_rn(v1));
+            srow[row] = __float2bfloat16_rn(silu_f(g) * u);
+          } else {
+            const float wgt = (tok < cd.n_tok) ? p.slot_weight[cd.slot_begin + tok] : 0.f;
+            srow[row] = __float2bfloat16_rn(wgt * v0);
+            srow[kTileRows + row] = __float2bfloat16_rn(wgt * v1);
           }
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(tmem_empty);
+      mbar_arrive(tmem_empty);                 // accumulators drained: the next tile's MMAs may start
       tphase ^= 1;
+      named_bar_sync(1, kNumEpiThreads);       // staging tile complete
+      {
+        const int n_vec = cd.n_tok * kVecPerRow;
+        const long long col0 = (long long)rt * (kGemm1 ? 1 : 2) * kTileRows;
+        for (int idx = et; idx < n_vec; idx += kNumEpiThreads) {
+          const int tok = idx / kVecPerRow, v = idx % kVecPerRow;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + tok * kRowB + v * 16);
+          *reinterpret_cast<uint4*>(p.out + (long long)(cd.slot_begin + tok) * p.out_ld + col0 + v * 8) = val;
+        }
+      }
+      named_bar_sync(1, kNumEpiThreads);       // staging free again
     }
   }
 
@@ -357,28 +349,65 @@ __global__ void __launch_bounds__(kNumThreads, 1) grouped_gemm_kernel(const Gemm
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// rows x cols BF16 row-major matrix, box = box_rows x 64 columns, 128 B swizzle (matches the UMMA K-major SW128 atom)
+cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_tmap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+int gemm_b_box_rows() { return kBBoxRows; }
+
 template <int FMT, bool kGemm1>
-static cudaError_t launch_one(const GemmParams& p, int num_sms, cudaStream_t stream) {
+static cudaError_t launch_one(const GemmParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   auto kern = grouped_gemm_kernel<FMT, kGemm1>;
-  constexpr int smem = SmemLayout<FMT>::kDynamic;
+  constexpr int smem = SmemLayout<FMT, kGemm1>::kTotal;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<num_sms, kNumThreads, smem, stream>>>(p);
+  kern<<<num_sms, kNumThreads, smem, stream>>>(p, tmap);
   return cudaGetLastError();
 }
 
-cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, const void* tmap_b, int num_sms,
+                                cudaStream_t stream) {
+  const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(tmap_b);
   if (fmt == kFmtInt4G128) {
-    return gemm1 ? launch_one<kFmtInt4G128, true>(p, num_sms, stream)
-                 : launch_one<kFmtInt4G128, false>(p, num_sms, stream);
+    return gemm1 ? launch_one<kFmtInt4G128, true>(p, tm, num_sms, stream)
+                 : launch_one<kFmtInt4G128, false>(p, tm, num_sms, stream);
   }
   if (fmt == kFmtInt8G128) {
-    return gemm1 ? launch_one<kFmtInt8G128, true>(p, num_sms, stream)
-                 : launch_one<kFmtInt8G128, false>(p, num_sms, stream);
+    return gemm1 ? launch_one<kFmtInt8G128, true>(p, tm, num_sms, stream)
+                 : launch_one<kFmtInt8G128, false>(p, tm, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -33,15 +33,15 @@ enum WeightFormat : int {
   kFmtInt8G128 = 1,   // Krasis symmetric INT8, group 128
 };
 
-// One unit of grouped-GEMM work along the token axis: a run of <= 256 sorted slots of one expert.
+// One unit of grouped-GEMM work along the token axis: a run of <= kMaxChunkTokens sorted slots of one expert.
 struct ChunkDesc {
   int expert;      // local expert index
   int slot_begin;  // first sorted slot
-  int n_tok;       // real token slots in this chunk (1..256)
+  int n_tok;       // real token slots in this chunk (1..kMaxChunkTokens)
   int pad_;
 };
 
-constexpr int kMaxChunkTokens = 256;
+constexpr int kMaxChunkTokens = 192;   // UMMA N per chunk; 2 accumulators x 192 + 2 A stages x 64 = 512 TMEM columns
 
 struct GemmParams {
   const uint8_t* wq;          // packed tiles, all local experts
@@ -52,9 +52,6 @@ struct GemmParams {
   int items_per_chunk;        // GEMM1: I/128 (gate tile + up tile)   GEMM2: H/256 (two consecutive tiles)
   int tile1_offset;           // GEMM1: I/128   GEMM2: 1
   int tile0_mul;              // GEMM1: 1       GEMM2: 2          tile0 = rt * tile0_mul, tile1 = tile0 + tile1_offset
-  const __nv_bfloat16* b_src; // token rows
-  long long b_ld;             // elements between rows
-  const int* b_row_index;     // slot -> source row, or nullptr for identity
   const ChunkDesc* chunks;
   const int* n_chunks;        // device scalar
   __nv_bfloat16* out;         // GEMM1: act[slot][I]   GEMM2: c3[slot][H]

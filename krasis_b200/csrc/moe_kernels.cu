@@ -225,21 +225,32 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ coun
   }
 }
 
-__global__ void scatter_kernel(const int* __restrict__ ids, const float* __restrict__ wts, int n, int top_k,
-                               int e_start, int e_end, const int* __restrict__ offsets, int* __restrict__ cursor,
-                               int* __restrict__ sorted_token, float* __restrict__ sorted_w,
-                               int* __restrict__ slot_of) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Token scatter: one warp per (token, k) routing entry.  Lane 0 claims a slot in the expert's contiguous run,
+// then the warp copies the token's hidden row into x_sorted[slot] (16 B per lane per step, coalesced) so that
+// every expert's tokens form one contiguous K-major tile the GEMM can fetch with 2-D TMA.
+__global__ void __launch_bounds__(256) scatter_kernel(const int* __restrict__ ids, const float* __restrict__ wts, int n,
+                                                      int top_k, int e_start, int e_end,
+                                                      const int* __restrict__ offsets, int* __restrict__ cursor,
+                                                      float* __restrict__ sorted_w, int* __restrict__ slot_of,
+                                                      const uint4* __restrict__ x, uint4* __restrict__ x_sorted,
+                                                      int vec_per_row) {
+  const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
   const int e = ids[i];
   int slot = -1;
   if (e >= e_start && e < e_end) {
-    const int le = e - e_start;
-    slot = offsets[le] + atomicAdd(&cursor[le], 1);
-    sorted_token[slot] = i / top_k;
-    sorted_w[slot] = wts[i];
+    if (lane == 0) {
+      const int le = e - e_start;
+      slot = offsets[le] + atomicAdd(&cursor[le], 1);
+      sorted_w[slot] = wts[i];
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    const uint4* src = x + (long long)(i / top_k) * vec_per_row;
+    uint4* dst = x_sorted + (long long)slot * vec_per_row;
+    for (int v = lane; v < vec_per_row; v += 32) dst[v] = src[v];
   }
-  slot_of[i] = slot;
+  if (lane == 0) slot_of[i] = slot;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -372,8 +383,8 @@ cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int 
 }
 
 cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
-                           int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, int* sorted_token,
-                           float* sorted_w, int* slot_of, cudaStream_t s) {
+                           int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
+                           const void* x, void* x_sorted, int H, cudaStream_t s) {
   const int n = M * top_k, E = e_end - e_start;
   if (E > 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * E, s);
@@ -381,8 +392,8 @@ cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, i
   if (n > 0) count_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, n, e_start, e_end, counts);
   scan_kernel<<<1, 1024, 0, s>>>(counts, E, offsets, cursor, chunks, n_chunks);
   if (n > 0)
-    scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, wts, n, top_k, e_start, e_end, offsets, cursor, sorted_token,
-                                                   sorted_w, slot_of);
+    scatter_kernel<<<(n + 7) / 8, 256, 0, s>>>(ids, wts, n, top_k, e_start, e_end, offsets, cursor, sorted_w, slot_of,
+                                               (const uint4*)x, (uint4*)x_sorted, H / 8);
   return cudaGetLastError();
 }
 
