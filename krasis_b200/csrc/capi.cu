@@ -18,6 +18,9 @@ cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows
 int gemm_b_box_rows();
 cudaError_t launch_router_logits(const void* h, const void* gate, const float* bias, float* logits, int M, int E,
                                  int H, cudaStream_t s);
+bool router_gemm_supported(int E, int H);
+cudaError_t launch_router_gemm(const void* x, const void* tmap_g, const float* bias, float* logits, int M, int E,
+                               int H, cudaStream_t s);
 cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int M, int E, int top_k, int scoring,
                                int renorm, int* ids, float* wts, cudaStream_t s);
 cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
@@ -58,6 +61,8 @@ struct LayerWeights {
   void* gate = nullptr;        // [E][H] bf16
   float* gate_bias = nullptr;  // [E]
   float* corr_bias = nullptr;  // [E]
+  alignas(64) unsigned char tmap_gate[128];   // CUtensorMap over gate (router GEMM B operand)
+  bool has_tmap_gate = false;
 };
 
 struct kb2_engine {
@@ -284,6 +289,11 @@ KB2_API int kb2_set_router_host(kb2_engine* e, int layer, const void* gate, cons
   L.gate = nullptr; L.gate_bias = nullptr; L.corr_bias = nullptr;
   CUDA_TRY(cudaMalloc(&L.gate, E * H * 2));
   CUDA_TRY(cudaMemcpy(L.gate, gate, E * H * 2, cudaMemcpyHostToDevice));
+  L.has_tmap_gate = false;
+  if (router_gemm_supported((int)E, (int)H)) {
+    CUDA_TRY(make_tmap_bf16_rows(L.tmap_gate, L.gate, (long long)E, (long long)H, 64));
+    L.has_tmap_gate = true;
+  }
   if (bias) {
     CUDA_TRY(cudaMalloc((void**)&L.gate_bias, E * 4));
     CUDA_TRY(cudaMemcpy(L.gate_bias, bias, E * 4, cudaMemcpyHostToDevice));
@@ -305,7 +315,10 @@ KB2_API int kb2_route(kb2_engine* e, int layer, const void* hidden, int32_t M, i
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   { ProfSpan ps(e, KB2_PROF_ROUTER_LOGITS, s);
-    CUDA_TRY(launch_router_logits(hidden, L.gate, L.gate_bias, e->logits, M, e->cfg.n_routed_experts, e->cfg.hidden_size, s)); }
+    if (L.has_tmap_gate)   // tcgen05 path (E <= 512); the fp32-FMA kernel remains for larger / odd expert counts
+      CUDA_TRY(launch_router_gemm(hidden, L.tmap_gate, L.gate_bias, e->logits, M, e->cfg.n_routed_experts, e->cfg.hidden_size, s));
+    else
+      CUDA_TRY(launch_router_logits(hidden, L.gate, L.gate_bias, e->logits, M, e->cfg.n_routed_experts, e->cfg.hidden_size, s)); }
   ProfSpan ps2(e, KB2_PROF_ROUTER_TOPK, s);
   CUDA_TRY(launch_router_topk(e->logits, L.corr_bias, M, e->cfg.n_routed_experts, e->cfg.num_experts_per_tok,
                               e->cfg.scoring_func, e->cfg.norm_topk_prob, ids, wts, s));

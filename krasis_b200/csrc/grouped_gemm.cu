@@ -19,12 +19,13 @@
 // exceeded the 128 B/clk smem port in the first version of this kernel (profiles/r01a_*).
 //   GEMM1: the pair is (gate tile t, up tile t) -> SiLU(gate)*up fused in the epilogue, BF16 act out
 //   GEMM2: the pair is two consecutive down-proj tiles -> x routing weight, BF16 c3 out
-// Warp roles (384 threads):
+// Warp roles (512 threads):
 //   warp 0      : bulk-TMA producer of packed weight tiles + scale tiles (one elected lane)
 //   warp 1      : tcgen05.mma issuer (one elected lane)
 //   warp 2      : 2-D TMA producer of the token (B) operand (one elected lane)
-//   warps 4-7   : dequantisers (thread t owns weight row t of both tiles = TMEM lane t)
+//   warps 4-7   : dequantisers of weight tile 0 (thread t owns weight row t = TMEM lane t)
 //   warps 8-11  : epilogue
+//   warps 12-15 : dequantisers of weight tile 1
 // TMEM columns: [0,192) acc0 | [192,384) acc1 | [384,512) two A stages x (tile0 32 cols | tile1 32 cols)
 // Numerics (oracle/moe.py, GPU-path): W = bf16((nib-8)*scale) exactly as Marlin's BF16 dequant,
 // fp32 accumulation in TMEM, BF16 rounding at C1, A and C3.
@@ -35,7 +36,7 @@
 
 namespace kb2 {
 
-constexpr int kNumThreads = 384;
+constexpr int kNumThreads = 512;
 constexpr int kStagesA = 2;                                     // A operand stages in TMEM
 constexpr int kStagesB = 3;                                     // token (B operand) ring in smem
 constexpr int kBStageBytes = kMaxChunkTokens * kBlockK * 2;     // 24 KB
@@ -45,7 +46,7 @@ constexpr int kTmemCols = 512;
 constexpr int kAcc1Col = kMaxChunkTokens;                       // 192
 constexpr int kATmemCol = 2 * kMaxChunkTokens;                  // 384
 constexpr int kATileCols = kBlockK / 2;                         // 32 columns = 128 rows x 64 bf16
-constexpr int kNumDequantThreads = 128;
+constexpr int kNumDequantThreads = 256;
 constexpr int kNumEpiThreads = 128;
 
 template <int FMT>
@@ -65,7 +66,7 @@ template <int FMT, bool kGemm1>
 struct SmemLayout {
   static constexpr int kStagesW = Fmt<FMT>::kStagesW;
   static constexpr int kWStageBytes = 2 * Fmt<FMT>::kTileBytes + 2 * kScaleTileBytes;
-  static constexpr int kStageRowBytes = (kGemm1 ? 1 : 2) * kTileRows * 2;      // epilogue staging: 256 B | 512 B per token
+  static constexpr int kStageRowBytes = 2 * kTileRows * 2;   // epilogue staging: 512 B per token (gate|up or two down tiles)
   static constexpr int kOffB = 0;                                               // 1024-aligned (swizzle atoms)
   static constexpr int kOffStage = kOffB + kStagesB * kBStageBytes;
   static constexpr int kOffW = kOffStage + kMaxChunkTokens * kStageRowBytes;
@@ -88,7 +89,7 @@ struct Ring {
   }
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // (w & 0x000F000F) | 0x43004300 == bf16x2 {128 + nib_lo, 128 + nib_hi}; subtracting 136 gives the
 // signed value exactly, the multiply by the BF16 group scale then rounds once (RNE) — identical to
@@ -232,56 +233,53 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     __syncwarp();
   } else if (warp == 3) {
     // idle
-  } else if (warp < 8) {
+  } else if (warp < 8 || warp >= 12) {
     // ------------------------------------------------------------ dequantisers -> A operand in TMEM
-    const int t = threadIdx.x - 128;   // weight row within the tile == TMEM lane
+    const int tile = warp >= 12 ? 1 : 0;                 // warps 4-7: weight tile 0, warps 12-15: tile 1
+    const int t = (warp & 3) * 32 + lane;                // weight row within the tile == TMEM lane
     Ring rw, ra;
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kATmemCol;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kATmemCol + tile * kATileCols;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&w_full[rw.stage], rw.phase);
         const uint8_t* wsrc = smem + L::kOffW + rw.stage * L::kWStageBytes;
-        const __nv_bfloat16* sc = reinterpret_cast<const __nv_bfloat16*>(wsrc + 2 * TB);
-        mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
-        tc_fence_after_sync();
+        const __nv_bfloat16 s = reinterpret_cast<const __nv_bfloat16*>(wsrc + 2 * TB)[tile * kTileRows + t];
+        uint32_t o[32];
+        if constexpr (FMT == kFmtInt4G128) {
+          const __nv_bfloat162 s2 = __halves2bfloat162(s, s);
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
-          const __nv_bfloat16 s = sc[tile * kTileRows + t];
-          uint32_t o[32];
-          if constexpr (FMT == kFmtInt4G128) {
-            const __nv_bfloat162 s2 = __halves2bfloat162(s, s);
+          for (int h = 0; h < 2; ++h) {
+            const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + h * 2048 + t * 16);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + h * 2048 + t * 16);
-              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                o[h * 16 + j * 4 + 0] = deq_pair_int4(ww[j], s2);
-                o[h * 16 + j * 4 + 1] = deq_pair_int4(ww[j] >> 4, s2);
-                o[h * 16 + j * 4 + 2] = deq_pair_int4(ww[j] >> 8, s2);
-                o[h * 16 + j * 4 + 3] = deq_pair_int4(ww[j] >> 12, s2);
-              }
-            }
-          } else {
-            // INT8 tile: [quarter q in 0..3][row][16 B], 16 consecutive K columns per 16 B
-            const float sf = __bfloat162float(s);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + q * 2048 + t * 16);
-              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const uint32_t word = ww[e >> 1];
-                const int b0 = (int)(int8_t)((word >> ((e & 1) * 16)) & 0xFF);
-                const int b1 = (int)(int8_t)((word >> ((e & 1) * 16 + 8)) & 0xFF);
-                __nv_bfloat162 v = __floats2bfloat162_rn((float)b0 * sf, (float)b1 * sf);
-                o[q * 8 + e] = *reinterpret_cast<uint32_t*>(&v);
-              }
+            for (int j = 0; j < 4; ++j) {
+              o[h * 16 + j * 4 + 0] = deq_pair_int4(ww[j], s2);
+              o[h * 16 + j * 4 + 1] = deq_pair_int4(ww[j] >> 4, s2);
+              o[h * 16 + j * 4 + 2] = deq_pair_int4(ww[j] >> 8, s2);
+              o[h * 16 + j * 4 + 3] = deq_pair_int4(ww[j] >> 12, s2);
             }
           }
-          tmem_st32(lane_base + ra.stage * 2 * kATileCols + tile * kATileCols, o);
+        } else {
+          // INT8 tile: [quarter q in 0..3][row][16 B], 16 consecutive K columns per 16 B
+          const float sf = __bfloat162float(s);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + q * 2048 + t * 16);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t word = ww[e >> 1];
+              const int b0 = (int)(int8_t)((word >> ((e & 1) * 16)) & 0xFF);
+              const int b1 = (int)(int8_t)((word >> ((e & 1) * 16 + 8)) & 0xFF);
+              __nv_bfloat162 v = __floats2bfloat162_rn((float)b0 * sf, (float)b1 * sf);
+              o[q * 8 + e] = *reinterpret_cast<uint32_t*>(&v);
+            }
+          }
         }
-        mbar_arrive(&w_empty[rw.stage]);     // packed words are in registers / TMEM stores issued
+        mbar_arrive(&w_empty[rw.stage]);     // packed words are now in registers
+        mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
+        tc_fence_after_sync();
+        tmem_st32(lane_base + ra.stage * 2 * kATileCols, o);
         tmem_st_wait();
         tc_fence_before_sync();
         mbar_arrive(&a_full[ra.stage]);
@@ -291,12 +289,14 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     }
   } else {
     // ------------------------------------------------------------ epilogue
+    // Phase 1 (holds TMEM): accumulators -> BF16 -> smem staging [token][tile0 128 | tile1 128]; then TMEM is
+    // released so the next tile's MMAs overlap phase 2.
+    // Phase 2: staging -> (GEMM1: SiLU(gate)*up) -> 16 B coalesced global stores.
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;             // weight row within the 128-row tile
     const int et = threadIdx.x - 256;          // 0..127
     uint8_t* stage = smem + L::kOffStage;
-    constexpr int kRowB = L::kStageRowBytes;
-    constexpr int kVecPerRow = kRowB / 16;
+    constexpr int kRowB = L::kStageRowBytes;   // 512
     uint32_t tphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
@@ -313,31 +313,48 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int tok = c0 + j;
-          const float v0 = __uint_as_float(r0v[j]);
-          const float v1 = __uint_as_float(r1v[j]);
-          __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + tok * kRowB);
-          if constexpr (kGemm1) {
-            const float g = __bfloat162float(__float2bfloat16_rn(v0));
-            const float u = __bfloat162float(__float2bfloat16_rn(v1));
-            srow[row] = __float2bfloat16_rn(silu_f(g) * u);
-          } else {
+          float v0 = __uint_as_float(r0v[j]);
+          float v1 = __uint_as_float(r1v[j]);
+          if constexpr (!kGemm1) {
             const float wgt = (tok < cd.n_tok) ? p.slot_weight[cd.slot_begin + tok] : 0.f;
-            srow[row] = __float2bfloat16_rn(wgt * v0);
-            srow[kTileRows + row] = __float2bfloat16_rn(wgt * v1);
+            v0 *= wgt;
+            v1 *= wgt;
           }
+          __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + tok * kRowB);
+          srow[row] = __float2bfloat16_rn(v0);
+          srow[kTileRows + row] = __float2bfloat16_rn(v1);
         }
       }
       tc_fence_before_sync();
       mbar_arrive(tmem_empty);                 // accumulators drained: the next tile's MMAs may start
       tphase ^= 1;
       named_bar_sync(1, kNumEpiThreads);       // staging tile complete
-      {
+      if constexpr (kGemm1) {
+        // 16 outputs per step: gate chunk v and up chunk v of one token -> 8 activations (16 B store)
+        constexpr int kVecPerRow = kTileRows / 8;          // 16
         const int n_vec = cd.n_tok * kVecPerRow;
-        const long long col0 = (long long)rt * (kGemm1 ? 1 : 2) * kTileRows;
+        for (int idx = et; idx < n_vec; idx += kNumEpiThreads) {
+          const int tok = idx / kVecPerRow, v = idx % kVecPerRow;
+          const uint4 g4 = *reinterpret_cast<const uint4*>(stage + tok * kRowB + v * 16);
+          const uint4 u4 = *reinterpret_cast<const uint4*>(stage + tok * kRowB + kTileRows * 2 + v * 16);
+          const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g4);
+          const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u4);
+          uint4 o4;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 g = __bfloat1622float2(g2[i]), u = __bfloat1622float2(u2[i]);
+            o2[i] = __floats2bfloat162_rn(silu_f(g.x) * u.x, silu_f(g.y) * u.y);
+          }
+          *reinterpret_cast<uint4*>(p.out + (long long)(cd.slot_begin + tok) * p.out_ld + (long long)rt * kTileRows + v * 8) = o4;
+        }
+      } else {
+        constexpr int kVecPerRow = 2 * kTileRows / 8;      // 32
+        const int n_vec = cd.n_tok * kVecPerRow;
         for (int idx = et; idx < n_vec; idx += kNumEpiThreads) {
           const int tok = idx / kVecPerRow, v = idx % kVecPerRow;
           const uint4 val = *reinterpret_cast<const uint4*>(stage + tok * kRowB + v * 16);
-          *reinterpret_cast<uint4*>(p.out + (long long)(cd.slot_begin + tok) * p.out_ld + col0 + v * 8) = val;
+          *reinterpret_cast<uint4*>(p.out + (long long)(cd.slot_begin + tok) * p.out_ld + (long long)rt * 2 * kTileRows + v * 8) = val;
         }
       }
       named_bar_sync(1, kNumEpiThreads);       // staging free again

@@ -86,7 +86,9 @@ def test_retile_int4_bit_exact():
 
 # ------------------------------------------------------------------ router
 
-@pytest.mark.parametrize("E,k,H,M,norm", [(64, 6, 256, 200, False), (512, 10, 512, 333, True), (256, 8, 256, 64, True)])
+@pytest.mark.parametrize("E,k,H,M,norm", [(64, 6, 256, 200, False), (512, 10, 512, 333, True), (256, 8, 256, 64, True),
+                                          (96, 4, 256, 130, True),      # E % 64 != 0 -> fp32-FMA fallback kernel
+                                          (384, 8, 2048, 1000, True)])  # two accumulators (256 + 128), M % 128 != 0
 def test_router_ids_bit_exact_and_weights_close(E, k, H, M, norm):
     from krasis_b200 import KrasisEngine
     rng = np.random.default_rng(E + k)
@@ -101,7 +103,10 @@ def test_router_ids_bit_exact_and_weights_close(E, k, H, M, norm):
     ok = router.min_topk_gap(lg, k) > 1e-5          # documented near-tie policy
     assert ok.mean() > 0.95
     assert np.array_equal(ids.cpu().numpy()[ok], ids_o[ok]), "top-k ids must be bit-exact away from near-ties"
-    assert np.allclose(w.cpu().numpy()[ok], w_o[ok], rtol=5e-6, atol=1e-9)
+    # weights: fp32 softmax of logits whose fp32 accumulation order differs (tensor-core partial sums vs the
+    # oracle's single rounding of an exact sum): |d logit| <~ 2e-6 at H=2048 => relative weight error <~ 1e-5
+    rel = np.abs(w.cpu().numpy()[ok] - w_o[ok]) / w_o[ok]
+    assert rel.max() < 3e-5, f"max relative routing-weight error {rel.max():.3e}"
 
 
 def test_router_exact_ties_go_to_lower_index():
