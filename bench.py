@@ -15,9 +15,11 @@ are NOT in this round's step (DESIGN.md "scope this round"); the workload name s
   roofline  dominant kernel = grouped gate/up expert GEMM (tensor-bound; algorithmic FLOPs / event time)
   cpu_baseline  the reference's CPU expert path (C/AVX2 port, oracle/cpu_moe.c) on a bounded token sample
 
-N>1 (torchrun, one rank per GPU): expert-parallel like the reference (python/krasis/gpu_prefill.py:353-359):
-each rank owns E/N experts of every layer, the 8192 tokens are replicated, partial sums are all-reduced
-over NCCL (the reference adds them on GPU0, python/krasis/model.py:3183-3211).  scaling = "strong".
+N>1 (torchrun, one rank per GPU): expert-parallel.  Experts are sliced like the reference
+(python/krasis/gpu_prefill.py:353-359: rank r owns E/N contiguous experts of every layer); unlike the reference
+(tokens replicated through pinned host memory, partial sums added on GPU0, python/krasis/model.py:3086-3211) the
+8192 tokens are SHARDED over the ranks and only routed rows travel: NCCL all-to-all dispatch -> grouped expert
+GEMMs on the owner -> all-to-all back -> weighted combine at home (krasis_b200/parallel.py).  scaling = "strong".
 """
 import argparse
 import json
@@ -194,7 +196,7 @@ def run_ours(args):
     M = args.tokens
     eng = KrasisEngine(**cfg, rank=rank, num_ranks=world, max_tokens=M, device=local)
 
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)   # expert weights differ per rank (different experts)
     weights = []
     for l in range(args.layers):
         ts = []
@@ -209,19 +211,27 @@ def run_ours(args):
         gate = (torch.randn(cfg["n_routed_experts"], cfg["hidden_size"], device=dev,
                             generator=torch.Generator(device=dev).manual_seed(77 + l)) * 0.02).to(torch.bfloat16)
         eng.set_routing_weights(l, gate)
-    gx = torch.Generator(device=dev).manual_seed(42)
+    gx = torch.Generator(device=dev).manual_seed(42)   # identical on every rank
     x = torch.randn(M, cfg["hidden_size"], device=dev, generator=gx)
     x = (x / x.pow(2).mean(-1, keepdim=True).sqrt()).to(torch.bfloat16)
     x_host = x.cpu().pin_memory()
     out_host = torch.empty_like(x_host).pin_memory()
 
+    ep = None
+    if world > 1:
+        from krasis_b200.parallel import ExpertParallelMoE
+        ep = ExpertParallelMoE(eng)
+        lo, hi = rank * M // world, (rank + 1) * M // world
+        x_local = x[lo:hi].contiguous()            # token shard of this rank (same global x on every rank: seed 42)
+
     def step():
         out = None
         for l in range(args.layers):
-            ids, w = eng.compute_routing(l, x)
-            out = eng.moe_forward(l, x, ids, w, routed_only=(world > 1))
             if world > 1:
-                dist.all_reduce(out)            # EP combine of partial sums (model.py:3183-3211)
+                out = ep.forward(l, x_local)       # route -> all-to-all dispatch -> experts -> all-to-all -> combine
+            else:
+                ids, w = eng.compute_routing(l, x)
+                out = eng.moe_forward(l, x, ids, w)
         return out
 
     def barrier():

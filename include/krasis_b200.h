@@ -116,6 +116,26 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int moe_layer_idx, const void* x_dev,
                     const float* topk_weights_dev, void* out_dev, int32_t num_tokens, int32_t routed_only,
                     const void* shared_dev, void* stream);
 
+/* ---- Expert-parallel building blocks (one process per GPU; the collective between them is the caller's NCCL
+ * all-to-all).  They replace the reference's replicated-token EP loop (python/krasis/model.py:3086-3211) with
+ * dispatch of ROUTED ROWS ONLY:
+ *   source rank : kb2_route -> kb2_ep_bin_rows (rows grouped by GLOBAL expert id, hence by owner rank)
+ *                 -> all-to-all(rows, weights, ids) ->
+ *   owner rank  : kb2_moe_forward_rows (one routing entry per row; returns bf16(w * expert(row)) in input order)
+ *                 -> all-to-all back ->
+ *   source rank : kb2_ep_combine_rows (sum over the k entries of each token in k order, rsf, + shared)
+ * kb2_ep_bin_rows: x [M][H], ids/w [M][k] -> x_sorted [M*k][H], w_sorted/ids_sorted [M*k], slot_of [M][k]
+ * (position of each (token, j) in the sorted order, -1 never occurs here), counts [E] int32. */
+KB2_API int kb2_ep_bin_rows(kb2_engine* e, const void* x_dev, const int32_t* topk_ids_dev, const float* topk_weights_dev,
+                            int32_t num_tokens, void* x_sorted_dev, float* w_sorted_dev, int32_t* ids_sorted_dev,
+                            int32_t* slot_of_dev, int32_t* counts_dev, void* stream);
+/* rows [n][H] bf16, expert_ids [n] int32 (GLOBAL ids; rows whose expert is not local yield zeros), weights [n] f32
+ * -> out_rows [n][H] bf16.  n <= max_tokens * top_k. */
+KB2_API int kb2_moe_forward_rows(kb2_engine* e, int moe_layer_idx, const void* rows_dev, const int32_t* expert_ids_dev,
+                                 const float* weights_dev, void* out_rows_dev, int32_t n_rows, void* stream);
+KB2_API int kb2_ep_combine_rows(kb2_engine* e, const void* rows_sorted_dev, const int32_t* slot_of_dev, int32_t num_tokens,
+                                int32_t routed_only, const void* shared_dev, void* out_dev, void* stream);
+
 /* Host-buffer variant of route + forward for callers that hold activations in (pinned) host memory —
  * the shape of KrasisEngine.submit_forward/sync_forward (src/moe.rs:2722,2809: bytes in, bytes out).
  * If topk_ids_host is NULL the engine routes with its own router weights.  Copies H2D, computes,

@@ -38,6 +38,10 @@ SIGNATURES = {
     "kb2_route": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kb2_moe_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "kb2_ep_bin_rows": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 6),
+    "kb2_moe_forward_rows": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
+    "kb2_ep_combine_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
     "kb2_moe_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_void_p]),
     "kb2_prefill_moe_stack_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

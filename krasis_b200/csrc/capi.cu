@@ -25,7 +25,7 @@ cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int 
                                int renorm, int* ids, float* wts, cudaStream_t s);
 cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
                            int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
-                           const void* x, void* x_sorted, int H, cudaStream_t s);
+                           int* sorted_ids, const void* x, void* x_sorted, int H, cudaStream_t s);
 cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
                            const void* shared, void* out, cudaStream_t s);
 cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,
@@ -160,11 +160,11 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   e->layers.resize(c->num_moe_layers);
   const size_t MK = (size_t)c->max_tokens * c->num_experts_per_tok;
-  const size_t max_chunks = e->e_local + MK / kMaxChunkTokens + 1;
+  const size_t max_chunks = c->n_routed_experts + MK / kMaxChunkTokens + 1;
 #define ALLOC(ptr, bytes) CUDA_TRY(cudaMalloc((void**)&(ptr), (bytes)))
-  ALLOC(e->counts, sizeof(int) * e->e_local);
-  ALLOC(e->offsets, sizeof(int) * (e->e_local + 1));
-  ALLOC(e->cursor, sizeof(int) * e->e_local);
+  ALLOC(e->counts, sizeof(int) * c->n_routed_experts);
+  ALLOC(e->offsets, sizeof(int) * (c->n_routed_experts + 1));
+  ALLOC(e->cursor, sizeof(int) * c->n_routed_experts);
   ALLOC(e->n_chunks, sizeof(int));
   ALLOC(e->chunks, sizeof(ChunkDesc) * max_chunks);
   ALLOC(e->x_sorted, MK * c->hidden_size * 2);
@@ -326,22 +326,16 @@ KB2_API int kb2_route(kb2_engine* e, int layer, const void* hidden, int32_t M, i
   return KB2_OK;
 }
 
-KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32_t* ids, const float* wts, void* out,
-                    int32_t M, int32_t routed_only, const void* shared, void* stream) {
-  if (int r = check_layer(e, layer)) return r;
+// Shared implementation: `n_rows` activation rows, `K` routing entries per row.
+static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32_t* ids, const float* wts, void* out,
+                            int M, int K, int apply_rsf, const void* shared, cudaStream_t s) {
   LayerWeights& L = e->layers[layer];
-  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
-  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
-  if (M == 0) return KB2_OK;
-  if (!x || !ids || !wts || !out) return fail(KB2_ERR_VALUE, "null argument");
-  CUDA_TRY(cudaSetDevice(e->cfg.device));
-  cudaStream_t s = (cudaStream_t)stream;
-  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, K = e->cfg.num_experts_per_tok;
+  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size;
   const int fmt = e->cfg.weight_format;
 
   { ProfSpan ps(e, KB2_PROF_BINNING, s);
     CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
-                            e->n_chunks, e->sorted_w, e->slot_of, x, e->x_sorted, H, s)); }
+                            e->n_chunks, e->sorted_w, e->slot_of, nullptr, x, e->x_sorted, H, s)); }
   e->launches += 3;
 
   GemmParams g1{};
@@ -366,11 +360,67 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
   { ProfSpan ps(e, KB2_PROF_GEMM2, s);
     CUDA_TRY(launch_grouped_gemm(fmt, false, g2, e->tmap_act, e->num_sms, s)); }
 
-  const int apply = routed_only ? 0 : 1;
   { ProfSpan ps(e, KB2_PROF_COMBINE, s);
-    CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply,
-                            routed_only ? nullptr : shared, out, s)); }
+    CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply_rsf, shared, out, s)); }
   e->launches += 3;
+  return KB2_OK;
+}
+
+KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32_t* ids, const float* wts, void* out,
+                    int32_t M, int32_t routed_only, const void* shared, void* stream) {
+  if (int r = check_layer(e, layer)) return r;
+  LayerWeights& L = e->layers[layer];
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
+  if (M == 0) return KB2_OK;
+  if (!x || !ids || !wts || !out) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  return moe_forward_impl(e, layer, x, ids, wts, out, M, e->cfg.num_experts_per_tok, routed_only ? 0 : 1,
+                          routed_only ? nullptr : shared, (cudaStream_t)stream);
+}
+
+// ---- expert-parallel building blocks (all-to-all dispatch / combine) -------------------------
+KB2_API int kb2_ep_bin_rows(kb2_engine* e, const void* x, const int32_t* ids, const float* wts, int32_t M, void* x_sorted,
+                    float* w_sorted, int32_t* ids_sorted, int32_t* slot_of, int32_t* counts, void* stream) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (M == 0) return KB2_OK;
+  if (!x || !ids || !wts || !x_sorted || !w_sorted || !ids_sorted || !slot_of || !counts) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfSpan ps(e, KB2_PROF_BINNING, s);
+  CUDA_TRY(launch_binning(ids, wts, M, e->cfg.num_experts_per_tok, 0, e->cfg.n_routed_experts, counts, e->offsets,
+                          e->cursor, e->chunks, e->n_chunks, w_sorted, slot_of, ids_sorted, x, x_sorted,
+                          e->cfg.hidden_size, s));
+  e->launches += 3;
+  return KB2_OK;
+}
+
+KB2_API int kb2_moe_forward_rows(kb2_engine* e, int layer, const void* rows, const int32_t* expert_ids, const float* wts,
+                         void* out_rows, int32_t n_rows, void* stream) {
+  if (int r = check_layer(e, layer)) return r;
+  LayerWeights& L = e->layers[layer];
+  const long long cap = (long long)e->cfg.max_tokens * e->cfg.num_experts_per_tok;
+  if (n_rows < 0 || n_rows > cap) return fail(KB2_ERR_VALUE, "n_rows %d outside [0, max_tokens*top_k=%lld]", n_rows, cap);
+  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
+  if (n_rows == 0) return KB2_OK;
+  if (!rows || !expert_ids || !wts || !out_rows) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  return moe_forward_impl(e, layer, rows, expert_ids, wts, out_rows, n_rows, 1, 0, nullptr, (cudaStream_t)stream);
+}
+
+KB2_API int kb2_ep_combine_rows(kb2_engine* e, const void* rows_sorted, const int32_t* slot_of, int32_t M, int32_t routed_only,
+                        const void* shared, void* out, void* stream) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (M == 0) return KB2_OK;
+  if (!rows_sorted || !slot_of || !out) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfSpan ps(e, KB2_PROF_COMBINE, s);
+  CUDA_TRY(launch_combine(rows_sorted, slot_of, M, e->cfg.hidden_size, e->cfg.num_experts_per_tok,
+                          e->cfg.routed_scaling_factor, routed_only ? 0 : 1, routed_only ? nullptr : shared, out, s));
+  e->launches += 1;
   return KB2_OK;
 }
 

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int* __restrict__ id
                                                       int top_k, int e_start, int e_end,
                                                       const int* __restrict__ offsets, int* __restrict__ cursor,
                                                       float* __restrict__ sorted_w, int* __restrict__ slot_of,
+                                                      int* __restrict__ sorted_ids,
                                                       const uint4* __restrict__ x, uint4* __restrict__ x_sorted,
                                                       int vec_per_row) {
   const int i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int* __restrict__ id
       const int le = e - e_start;
       slot = offsets[le] + atomicAdd(&cursor[le], 1);
       sorted_w[slot] = wts[i];
+      if (sorted_ids) sorted_ids[slot] = e;
     }
     slot = __shfl_sync(0xffffffffu, slot, 0);
     const uint4* src = x + (long long)(i / top_k) * vec_per_row;
@@ -384,7 +386,7 @@ cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int 
 
 cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
                            int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
-                           const void* x, void* x_sorted, int H, cudaStream_t s) {
+                           int* sorted_ids, const void* x, void* x_sorted, int H, cudaStream_t s) {
   const int n = M * top_k, E = e_end - e_start;
   if (E > 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * E, s);
@@ -393,7 +395,7 @@ cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, i
   scan_kernel<<<1, 1024, 0, s>>>(counts, E, offsets, cursor, chunks, n_chunks);
   if (n > 0)
     scatter_kernel<<<(n + 7) / 8, 256, 0, s>>>(ids, wts, n, top_k, e_start, e_end, offsets, cursor, sorted_w, slot_of,
-                                               (const uint4*)x, (uint4*)x_sorted, H / 8);
+                                               sorted_ids, (const uint4*)x, (uint4*)x_sorted, H / 8);
   return cudaGetLastError();
 }
 

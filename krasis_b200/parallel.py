@@ -1,0 +1,107 @@
+"""Expert-parallel prefill across GPUs: one process per GPU, torch.distributed (NCCL) for the exchange.
+
+The reference's "EP" (python/krasis/model.py:3086-3211) replicates every token to every GPU through pinned host
+memory, zeroes non-local routing weights and adds the partial sums on GPU0.  Here tokens are SHARDED across
+ranks and only routed rows travel:
+
+    route(x_local) -> bin rows by global expert id (=> by owner rank) -> all-to-all(v) rows/weights/ids
+    -> owner: grouped expert GEMMs on the received rows -> all-to-all(v) back -> weighted combine at home.
+
+All arithmetic and all row movement inside a rank is done by libkrasis_b200 kernels (kb2_ep_bin_rows,
+kb2_moe_forward_rows, kb2_ep_combine_rows); torch supplies buffers, streams and the collective only.
+The split-size bookkeeping below is pure host logic and is tested on CPU with the gloo backend.
+"""
+import ctypes as C
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+
+def expert_range(rank: int, num_ranks: int, num_experts: int):
+    """python/krasis/gpu_prefill.py:353-359: contiguous ranges, the last rank takes the remainder."""
+    per = num_experts // num_ranks
+    start = rank * per
+    end = num_experts if rank == num_ranks - 1 else (rank + 1) * per
+    return start, end
+
+
+def send_splits_from_counts(counts: List[int], num_ranks: int) -> List[int]:
+    """Rows grouped by global expert id are also grouped by owner rank: split sizes = per-owner sums."""
+    E = len(counts)
+    out = []
+    for r in range(num_ranks):
+        s, e = expert_range(r, num_ranks, E)
+        out.append(int(sum(counts[s:e])))
+    return out
+
+
+def exchange_splits(send_splits: List[int], group=None, device="cpu") -> List[int]:
+    """all-to-all of the split sizes: recv_splits[src] = rows rank `src` sends to this rank."""
+    world = dist.get_world_size(group)
+    t_in = torch.tensor(send_splits, dtype=torch.int64, device=device)
+    t_out = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(t_out, t_in, group=group)
+    return [int(v) for v in t_out.tolist()]
+
+
+def all_to_all_rows(src: torch.Tensor, send_splits: List[int], recv_splits: List[int], group=None) -> torch.Tensor:
+    """Variable-size all-to-all of rows (dim 0)."""
+    out = torch.empty((sum(recv_splits),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    dist.all_to_all_single(out, src[: sum(send_splits)], output_split_sizes=recv_splits,
+                           input_split_sizes=send_splits, group=group)
+    return out
+
+
+class ExpertParallelMoE:
+    """Prefill MoE forward for a token shard, experts sharded over the ranks of `group`."""
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        cfg = engine._cfg
+        if cfg.num_ranks != self.world or cfg.rank != self.rank:
+            raise ValueError("engine rank/num_ranks must match the process group")
+        self.k, self.H, self.E = cfg.num_experts_per_tok, cfg.hidden_size, cfg.n_routed_experts
+        dev = engine.device
+        cap = cfg.max_tokens * self.k
+        self._xs = torch.empty((cap, self.H), dtype=torch.bfloat16, device=dev)
+        self._ws = torch.empty(cap, dtype=torch.float32, device=dev)
+        self._is = torch.empty(cap, dtype=torch.int32, device=dev)
+        self._slot = torch.empty(cap, dtype=torch.int32, device=dev)
+        self._counts = torch.empty(self.E, dtype=torch.int32, device=dev)
+        self._yrows = torch.empty((cap, self.H), dtype=torch.bfloat16, device=dev)
+
+    def forward(self, moe_layer_idx: int, x_local: torch.Tensor, topk_ids: Optional[torch.Tensor] = None,
+                topk_weights: Optional[torch.Tensor] = None, routed_only: bool = False,
+                shared: Optional[torch.Tensor] = None) -> torch.Tensor:
+        eng, lib, h = self.engine, self.engine._lib, self.engine._h
+        eng._check_act(x_local, "x_local")
+        M = x_local.shape[0]
+        stream = torch.cuda.current_stream(x_local.device).cuda_stream
+        if topk_ids is None:
+            topk_ids, topk_weights = eng.compute_routing(moe_layer_idx, x_local)
+        capi.check(lib.kb2_ep_bin_rows(h, x_local.data_ptr(), topk_ids.data_ptr(), topk_weights.data_ptr(), M,
+                                       self._xs.data_ptr(), self._ws.data_ptr(), self._is.data_ptr(),
+                                       self._slot.data_ptr(), self._counts.data_ptr(), stream))
+        counts = self._counts.cpu().tolist()                       # the one host sync per layer (split sizes)
+        send = send_splits_from_counts(counts, self.world)
+        recv = exchange_splits(send, self.group, device=x_local.device)
+        n_send = sum(send)
+        rows = all_to_all_rows(self._xs[:n_send], send, recv, self.group)
+        wts = all_to_all_rows(self._ws[:n_send], send, recv, self.group)
+        ids = all_to_all_rows(self._is[:n_send], send, recv, self.group)
+        n_recv = rows.shape[0]
+        out_rows = torch.empty_like(rows)
+        capi.check(lib.kb2_moe_forward_rows(h, moe_layer_idx, rows.data_ptr(), ids.data_ptr(), wts.data_ptr(),
+                                            out_rows.data_ptr(), n_recv, stream))
+        back = self._yrows[:n_send]
+        dist.all_to_all_single(back, out_rows, output_split_sizes=send, input_split_sizes=recv, group=self.group)
+        out = torch.empty_like(x_local)
+        capi.check(lib.kb2_ep_combine_rows(h, back.data_ptr(), self._slot.data_ptr(), M, int(bool(routed_only)),
+                                           shared.data_ptr() if shared is not None else None, out.data_ptr(), stream))
+        return out

@@ -1,0 +1,77 @@
+"""Expert-parallel path on GPUs: all-to-all dispatch/combine must reproduce the single-engine result.
+World size 1 runs on any GPU box; world size 2 needs two GPUs (skipped otherwise)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+from oracle import moe as omoe, router  # noqa: E402
+from oracle.bf16 import f32_to_bf16_bits, round_bf16  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _problem():
+    rng = np.random.default_rng(21)
+    E, H, I, k, M = 12, 256, 128, 3, 96
+    layer = omoe.make_int_layer(rng, E, H, I)
+    gate = round_bf16(rng.normal(0, 0.05, (E, H)).astype(np.float32))
+    x = round_bf16(rng.normal(0, 1, (M, H)).astype(np.float32))
+    return layer, gate, x, (E, H, I, k, M)
+
+
+def _worker(rank, world, port, ret):
+    from krasis_b200 import KrasisEngine, QuantizedExperts
+    from krasis_b200.parallel import ExpertParallelMoE
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        layer, gate, x, (E, H, I, k, M) = _problem()
+        eng = KrasisEngine(hidden_size=H, moe_intermediate_size=I, n_routed_experts=E, num_experts_per_tok=k,
+                           num_moe_layers=1, rank=rank, num_ranks=world, max_tokens=M, norm_topk_prob=True, device=rank)
+        s, t = eng.expert_start, eng.expert_end
+        eng.load_quantized_layer(0, QuantizedExperts(layer.w13_q[s:t], layer.w13_s[s:t], layer.w2_q[s:t], layer.w2_s[s:t]))
+        eng.set_routing_weights(0, f32_to_bf16_bits(gate))
+        ep = ExpertParallelMoE(eng)
+        lo, hi = rank * M // world, (rank + 1) * M // world           # token shard of this rank
+        xl = torch.from_numpy(x[lo:hi]).to(torch.bfloat16).cuda(rank)
+        out = ep.forward(0, xl, routed_only=True)
+        torch.cuda.synchronize()
+        ret[rank] = (lo, hi, out.float().cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _check(ret):
+    layer, gate, x, (E, H, I, k, M) = _problem()
+    ids, w = router.compute_routing(x, gate, k, norm_topk_prob=True)
+    want = omoe.moe_forward_gpu_path(layer, x, ids, w)
+    got = np.zeros_like(want)
+    for lo, hi, o in ret.values():
+        got[lo:hi] = o
+    rowmax = np.abs(want).max(axis=1, keepdims=True)
+    assert (np.abs(got - want) <= 2 * rowmax * 2.0 ** -8 + 1e-30).all()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_ep_all_to_all_matches_oracle(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    _check(ret)
