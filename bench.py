@@ -172,7 +172,7 @@ def run_reference_arm(args):
 
 def workload_config(args, n):
     return {"workload": f"qcn_moe_stack: {args.layers} MoE layers x {args.tokens} tokens, H2048 I512 E512 top-10, INT4 g128",
-            "tokens": args.tokens, "layers": args.layers, "parallelism": f"ep{n}" if n > 1 else "single",
+            "tokens": args.tokens, "layers": args.layers, "parallelism": f"ep{n}-{args.ep_mode}" if n > 1 else "single",
             "l2_policy": "inputs larger than L2: 792 MiB of expert weights streamed per layer",
             "attention": "not in this step (round 1)"}
 
@@ -227,8 +227,13 @@ def run_ours(args):
     def step():
         out = None
         for l in range(args.layers):
-            if world > 1:
+            if world > 1 and args.ep_mode == "a2a":
                 out = ep.forward(l, x_local)       # route -> all-to-all dispatch -> experts -> all-to-all -> combine
+            elif world > 1:
+                # reference semantics (model.py:3086-3211) on NVLink: tokens replicated, partial sums all-reduced
+                ids, w = eng.compute_routing(l, x)
+                out = eng.moe_forward(l, x, ids, w, routed_only=True)
+                dist.all_reduce(out)
             else:
                 ids, w = eng.compute_routing(l, x)
                 out = eng.moe_forward(l, x, ids, w)
@@ -320,6 +325,8 @@ def main():
     ap.add_argument("--tokens", type=int, default=TOKENS)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ep-mode", default="a2a", choices=["a2a", "replicate"],
+                    help="N>1: all-to-all dispatch of routed rows (default) or the reference's replicated-token scheme")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -55,6 +55,16 @@ def all_to_all_rows(src: torch.Tensor, send_splits: List[int], recv_splits: List
     return out
 
 
+def splits_from_count_matrix(count_matrix: List[List[int]], rank: int):
+    """count_matrix[src][e] = rows rank `src` routes to global expert e (all-gathered).  Returns
+    (send_splits, recv_splits) of `rank` — all split bookkeeping from ONE gathered matrix, one host sync."""
+    world = len(count_matrix)
+    send = send_splits_from_counts(count_matrix[rank], world)
+    s, e = expert_range(rank, world, len(count_matrix[rank]))
+    recv = [int(sum(count_matrix[src][s:e])) for src in range(world)]
+    return send, recv
+
+
 class ExpertParallelMoE:
     """Prefill MoE forward for a token shard, experts sharded over the ranks of `group`."""
 
@@ -69,12 +79,17 @@ class ExpertParallelMoE:
         self.k, self.H, self.E = cfg.num_experts_per_tok, cfg.hidden_size, cfg.n_routed_experts
         dev = engine.device
         cap = cfg.max_tokens * self.k
-        self._xs = torch.empty((cap, self.H), dtype=torch.bfloat16, device=dev)
-        self._ws = torch.empty(cap, dtype=torch.float32, device=dev)
-        self._is = torch.empty(cap, dtype=torch.int32, device=dev)
-        self._slot = torch.empty(cap, dtype=torch.int32, device=dev)
-        self._counts = torch.empty(self.E, dtype=torch.int32, device=dev)
-        self._yrows = torch.empty((cap, self.H), dtype=torch.bfloat16, device=dev)
+        self.cap = cap
+        bf, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+        self._xs = torch.empty((cap, self.H), dtype=bf, device=dev)      # rows grouped by expert (send order)
+        self._meta = torch.empty((cap, 2), dtype=i32, device=dev)        # [:,0] expert id, [:,1] weight bits
+        self._slot = torch.empty(cap, dtype=i32, device=dev)
+        self._counts = torch.empty(self.E, dtype=i32, device=dev)
+        self._all_counts = torch.empty((self.world, self.E), dtype=i32, device=dev)
+        self._rows = torch.empty((cap, self.H), dtype=bf, device=dev)    # received rows
+        self._rmeta = torch.empty((cap, 2), dtype=i32, device=dev)
+        self._orows = torch.empty((cap, self.H), dtype=bf, device=dev)   # expert outputs for received rows
+        self._yrows = torch.empty((cap, self.H), dtype=bf, device=dev)   # returned rows (send order)
 
     def forward(self, moe_layer_idx: int, x_local: torch.Tensor, topk_ids: Optional[torch.Tensor] = None,
                 topk_weights: Optional[torch.Tensor] = None, routed_only: bool = False,
@@ -86,17 +101,18 @@ class ExpertParallelMoE:
         if topk_ids is None:
             topk_ids, topk_weights = eng.compute_routing(moe_layer_idx, x_local)
         capi.check(lib.kb2_ep_bin_rows(h, x_local.data_ptr(), topk_ids.data_ptr(), topk_weights.data_ptr(), M,
-                                       self._xs.data_ptr(), self._ws.data_ptr(), self._is.data_ptr(),
+                                       self._xs.data_ptr(), self._ws_buf().data_ptr(), self._is_buf().data_ptr(),
                                        self._slot.data_ptr(), self._counts.data_ptr(), stream))
-        counts = self._counts.cpu().tolist()                       # the one host sync per layer (split sizes)
-        send = send_splits_from_counts(counts, self.world)
-        recv = exchange_splits(send, self.group, device=x_local.device)
-        n_send = sum(send)
-        rows = all_to_all_rows(self._xs[:n_send], send, recv, self.group)
-        wts = all_to_all_rows(self._ws[:n_send], send, recv, self.group)
-        ids = all_to_all_rows(self._is[:n_send], send, recv, self.group)
-        n_recv = rows.shape[0]
-        out_rows = torch.empty_like(rows)
+        dist.all_gather_into_tensor(self._all_counts.view(-1), self._counts, group=self.group)
+        send, recv = splits_from_count_matrix(self._all_counts.cpu().tolist(), self.rank)   # the one host sync per layer
+        n_send, n_recv = sum(send), sum(recv)
+        if n_recv > self.cap:
+            raise ValueError(f"received {n_recv} rows > capacity {self.cap}; raise max_tokens")
+        rows, ids, wts = self._rows[:n_recv], self._rid_buf()[:n_recv], self._rw_buf()[:n_recv]
+        dist.all_to_all_single(rows, self._xs[:n_send], output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        dist.all_to_all_single(ids, self._is_buf()[:n_send], output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        dist.all_to_all_single(wts, self._ws_buf()[:n_send], output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        out_rows = self._orows[:n_recv]
         capi.check(lib.kb2_moe_forward_rows(h, moe_layer_idx, rows.data_ptr(), ids.data_ptr(), wts.data_ptr(),
                                             out_rows.data_ptr(), n_recv, stream))
         back = self._yrows[:n_send]
@@ -105,3 +121,9 @@ class ExpertParallelMoE:
         capi.check(lib.kb2_ep_combine_rows(h, back.data_ptr(), self._slot.data_ptr(), M, int(bool(routed_only)),
                                            shared.data_ptr() if shared is not None else None, out.data_ptr(), stream))
         return out
+
+    # contiguous metadata buffers (the [cap,2] tensor is split into two contiguous halves)
+    def _is_buf(self): return self._meta.view(-1)[: self.cap]
+    def _ws_buf(self): return self._meta.view(-1)[self.cap:].view(torch.float32)
+    def _rid_buf(self): return self._rmeta.view(-1)[: self.cap]
+    def _rw_buf(self): return self._rmeta.view(-1)[self.cap:].view(torch.float32)

@@ -25,6 +25,16 @@ def test_send_splits_from_counts():
     assert sum(P.send_splits_from_counts(counts, 5)) == sum(counts)
 
 
+def test_splits_from_count_matrix_is_consistent():
+    rng = np.random.default_rng(0)
+    cm = rng.integers(0, 50, (4, 16)).tolist()
+    sends, recvs = zip(*(P.splits_from_count_matrix(cm, r) for r in range(4)))
+    for a in range(4):
+        for b in range(4):
+            assert sends[a][b] == recvs[b][a]          # what a sends to b is what b expects from a
+    assert [sum(s) for s in sends] == [sum(row) for row in cm]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
