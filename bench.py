@@ -325,8 +325,8 @@ def main():
     ap.add_argument("--tokens", type=int, default=TOKENS)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ep-mode", default="a2a", choices=["a2a", "replicate"],
-                    help="N>1: all-to-all dispatch of routed rows (default) or the reference's replicated-token scheme")
+    ap.add_argument("--ep-mode", default="replicate", choices=["a2a", "replicate"],
+                    help="N>1: replicate = tokens on every rank, partial sums all-reduced over NVLink (default; moves ~k x fewer bytes at top-10); a2a = all-to-all dispatch of routed rows")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,222 @@
+"""Attention-block oracles (torch on CPU, float32/float64; test infrastructure only).
+
+Gated DeltaNet (Qwen3-Next linear attention)
+  definitional recurrence        python/krasis/linear_attention.py:542-561 (== SURVEY.md A.4)
+  chunk-64 prefill               python/krasis/linear_attention.py:593-693 (_chunked_inner), :695-844 (_forward_chunked)
+  un-interleave qkvz / ba        python/krasis/linear_attention.py:337-391
+  causal depthwise conv(4)+SiLU  python/krasis/linear_attention.py:722-741
+  l2norm                         python/krasis/linear_attention.py:114-117
+  gated RMSNorm                  python/krasis/linear_attention.py:987-1004
+
+GQA (Qwen3 / Qwen3-Next gated)   python/krasis/attention.py:496-687
+  partial half-split RoPE, bf16 tables   :443-494
+  per-head RMSNorm (flashinfer.norm.rmsnorm)  :555-559
+  KV cast to cache dtype (FP8 E4M3, unscaled) :582-583
+  causal softmax(QK^T * d^-1/2) V             :596-642
+  sigmoid output gate                          :665-666
+
+tests/golden/make_attention_golden.py imports the REFERENCE's own linear_attention module (CPU, eager) to
+generate fixtures these functions are pinned against.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------- Gated DeltaNet
+
+def l2norm(x, eps=1e-6):
+    return x * torch.rsqrt((x * x).sum(dim=-1, keepdim=True) + eps)
+
+
+def gdn_unsplit(mixed_qkvz, mixed_ba, nk, nv, dk, dv):
+    """linear_attention.py:337-391: per key-head group [q(dk) k(dk) v(r*dv) z(r*dv)], [b(r) a(r)]."""
+    M = mixed_qkvz.shape[0]
+    r = nv // nk
+    g = mixed_qkvz.view(M, nk, 2 * dk + 2 * dv * r)
+    q, k, v, z = torch.split(g, [dk, dk, r * dv, r * dv], dim=2)
+    v, z = v.reshape(M, nv, dv), z.reshape(M, nv, dv)
+    b, a = torch.split(mixed_ba.view(M, nk, 2 * r), [r, r], dim=2)
+    return q, k, v, z, b.reshape(M, nv), a.reshape(M, nv)
+
+
+def gdn_conv_silu(q, k, v, conv_weight, conv_state=None):
+    """Depthwise causal conv (kernel K=4) over [q|k|v] channels + SiLU; returns (conv_out [M,C] in the input
+    dtype, new_state [C,K]).  conv_weight [C, K]; state = last K inputs (linear_attention.py:725-728)."""
+    M = q.shape[0]
+    mixed = torch.cat([q.reshape(M, -1), k.reshape(M, -1), v.reshape(M, -1)], dim=-1)     # [M, C]
+    C, K = conv_weight.shape
+    if conv_state is None:
+        conv_state = torch.zeros(C, K, dtype=mixed.dtype)
+    inp = torch.cat([conv_state, mixed.t()], dim=-1)                                      # [C, K+M]
+    new_state = inp[:, -K:].clone()
+    out = F.conv1d(inp.unsqueeze(0).to(conv_weight.dtype), conv_weight.unsqueeze(1), groups=C)[0]   # [C, M+1]
+    out = F.silu(out[:, -M:]).to(mixed.dtype)
+    return out.t().contiguous(), new_state
+
+
+def gdn_gates(b, a, A_log, dt_bias):
+    """beta = sigmoid(b);  g = -exp(A_log) * softplus(a + dt_bias)   (linear_attention.py:523-524)."""
+    return torch.sigmoid(b), -A_log.float().exp() * F.softplus(a.float() + dt_bias)
+
+
+def gdn_recurrent(q, k, v, beta, g, state=None):
+    """Definitional oracle.  q,k [M,nv,dk] (already l2-normed, q scaled), v [M,nv,dv], beta,g [M,nv].
+    Returns (out [M,nv,dv], state [nv,dk,dv]); float64 internally."""
+    M, nv, dk = q.shape
+    dv = v.shape[-1]
+    S = torch.zeros(nv, dk, dv, dtype=torch.float64) if state is None else state.double().clone()
+    q, k, v, beta, g = q.double(), k.double(), v.double(), beta.double(), g.double()
+    out = torch.empty(M, nv, dv, dtype=torch.float64)
+    for t in range(M):
+        S = S * g[t].exp()[:, None, None]
+        mem = (S * k[t][:, :, None]).sum(dim=1)
+        delta = (v[t] - mem) * beta[t][:, None]
+        S = S + k[t][:, :, None] * delta[:, None, :]
+        out[t] = (S * q[t][:, :, None]).sum(dim=1)
+    return out, S
+
+
+def gdn_chunked(q, k, v, beta, g, state=None, chunk=64, dtype=torch.float32):
+    """The reference's chunked prefill math (linear_attention.py:593-693,776-811) in `dtype`."""
+    M, nv, dk = q.shape
+    dv = v.shape[-1]
+    pad = (chunk - M % chunk) % chunk
+    def padt(x):
+        return F.pad(x, (0, 0) * (x.dim() - 1) + (0, pad)) if pad else x
+    q_, k_, v_ = [padt(x.to(dtype)).transpose(0, 1) for x in (q, k, v)]                  # [nv, T, d]
+    beta_, g_ = padt(beta.to(dtype)).t(), padt(g.to(dtype)).t()                          # [nv, T]
+    T = M + pad
+    n = T // chunk
+    qc, kc, vc = [x.reshape(nv, n, chunk, -1) for x in (q_, k_, v_)]
+    bc, gc = beta_.reshape(nv, n, chunk), g_.reshape(nv, n, chunk)
+    vb, kb = vc * bc[..., None], kc * bc[..., None]
+    gcum = gc.cumsum(dim=-1)
+    decay = (gcum[..., :, None] - gcum[..., None, :]).tril().exp().tril()
+    A = -(kb @ kc.transpose(-1, -2)) * decay
+    A = A.masked_fill(torch.triu(torch.ones(chunk, chunk, dtype=torch.bool), 0), 0)
+    value_corr = torch.linalg.solve_triangular(-A, vb, upper=False, unitriangular=True)
+    k_cumdecay = torch.linalg.solve_triangular(-A, kb * gcum.exp()[..., None], upper=False, unitriangular=True)
+    S = torch.zeros(nv, dk, dv, dtype=dtype) if state is None else state.to(dtype).clone()
+    out = torch.zeros(nv, n, chunk, dv, dtype=dtype)
+    strict = torch.triu(torch.ones(chunk, chunk, dtype=torch.bool), 1)
+    for i in range(n):
+        qi, ki, vi, gi, kcd, dm = qc[:, i], kc[:, i], value_corr[:, i], gcum[:, i], k_cumdecay[:, i], decay[:, i]
+        intra = ((qi @ ki.transpose(-1, -2)) * dm).masked_fill(strict, 0)
+        v_new = vi - kcd @ S
+        out[:, i] = (qi * gi[..., None].exp()) @ S + intra @ v_new
+        gl = gi[:, -1]
+        S = S * gl[:, None, None].exp() + (ki * (gl[:, None] - gi).exp()[..., None]).transpose(-1, -2) @ v_new
+    out = out.reshape(nv, T, dv)[:, :M].transpose(0, 1)
+    return out, S
+
+
+def gated_rmsnorm(x, gate, weight, eps):
+    """linear_attention.py:987-1004 (norm in fp32 -> input dtype; gate silu in fp32 -> input dtype; product)."""
+    dt = x.dtype
+    xf = x.float()
+    xn = (weight.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))).to(dt)
+    return xn * F.silu(gate.float()).to(dt)
+
+
+def gdn_layer_prefill(hidden, w, cfg, conv_state=None, state=None, recurrent=False):
+    """Whole GatedDeltaNetAttention._forward_chunked (BF16 weights path): hidden [M,H] bf16 -> [M,H] bf16.
+    w: dict(in_proj_qkvz, in_proj_ba, conv1d_weight [C,1,K], A_log, dt_bias, norm_weight, out_proj)."""
+    nk, nv, dk, dv = cfg["nk"], cfg["nv"], cfg["dk"], cfg["dv"]
+    M = hidden.shape[0]
+    qkvz = F.linear(hidden, w["in_proj_qkvz"])
+    ba = F.linear(hidden, w["in_proj_ba"])
+    q, k, v, z, b, a = gdn_unsplit(qkvz, ba, nk, nv, dk, dv)
+    conv_out, new_conv = gdn_conv_silu(q, k, v, w["conv1d_weight"].squeeze(1), conv_state)
+    kd = nk * dk
+    qa = conv_out[:, :kd].reshape(M, nk, dk)
+    ka = conv_out[:, kd:2 * kd].reshape(M, nk, dk)
+    va = conv_out[:, 2 * kd:].reshape(M, nv, dv)
+    beta, g = gdn_gates(b, a, w["A_log"], w["dt_bias"])
+    r = nv // nk
+    if r > 1:
+        qa, ka = qa.repeat_interleave(r, dim=1), ka.repeat_interleave(r, dim=1)
+    qa, ka = l2norm(qa), l2norm(ka)
+    qa = qa * (1.0 / dk ** 0.5)
+    if recurrent:
+        core, S = gdn_recurrent(qa.float(), ka.float(), va.float(), beta.float(), g, state)
+        core = core.float()
+    else:
+        core, S = gdn_chunked(qa.float(), ka.float(), va.float(), beta.float(), g, state)
+    core = core.to(hidden.dtype)
+    out = gated_rmsnorm(core, z, w["norm_weight"], cfg["eps"])
+    flat = out.reshape(M, nv * dv).to(torch.bfloat16)
+    return F.linear(flat, w["out_proj"]), new_conv, S
+
+
+# --------------------------------------------------------------------------------------------- GQA
+
+def rmsnorm(x, weight, eps):
+    """flashinfer.norm.rmsnorm semantics: fp32 accumulate, output in x.dtype."""
+    xf = x.float()
+    return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * weight.float()).to(x.dtype)
+
+
+def rope_tables(max_len, rotary_dim, theta):
+    """attention.py:443-459: fp32 angles, tables stored in BF16."""
+    freqs = 1.0 / (theta ** (torch.arange(0, rotary_dim, 2).float() / rotary_dim))
+    ang = torch.outer(torch.arange(max_len, dtype=torch.float32), freqs)
+    return ang.cos().to(torch.bfloat16), ang.sin().to(torch.bfloat16)
+
+
+def apply_rope(x, cos, sin):
+    """attention.py:480-490: half-split rotation of the first 2*d2 dims, rest pass through (bf16 arithmetic)."""
+    d2 = cos.shape[-1]
+    c, s = cos.unsqueeze(1), sin.unsqueeze(1)
+    x1, x2 = x[..., :d2], x[..., d2:2 * d2]
+    rot = torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1)
+    return torch.cat([rot, x[..., 2 * d2:]], dim=-1) if 2 * d2 < x.shape[-1] else rot
+
+
+def gqa_core(q, k_cache, v_cache, q_pos, sm_scale):
+    """Causal attention of M new queries at positions q_pos over a cache of L keys (positions 0..L-1).
+    q [M,nh,d] bf16; k_cache/v_cache [L,nkv,d] (already cast through the KV dtype, e.g. fp8 -> float).
+    fp32 softmax, like FlashInfer; returns [M,nh,d] bf16."""
+    M, nh, d = q.shape
+    nkv = k_cache.shape[1]
+    grp = nh // nkv
+    kf = k_cache.float().repeat_interleave(grp, dim=1)          # [L, nh, d]
+    vf = v_cache.float().repeat_interleave(grp, dim=1)
+    s = torch.einsum("mhd,lhd->hml", q.float(), kf) * sm_scale
+    L = k_cache.shape[0]
+    mask = torch.arange(L)[None, :] > q_pos[:, None]
+    s = s.masked_fill(mask[None], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return torch.einsum("hml,lhd->mhd", p, vf).to(torch.bfloat16)
+
+
+def gqa_layer_prefill(hidden, w, cfg, positions, k_cache=None, v_cache=None, kv_dtype=torch.float8_e4m3fn):
+    """GQAAttention.forward (attention.py:496-687) for BF16 weights: returns (out [M,H] bf16, k_cache, v_cache)
+    with the caches holding values already rounded through kv_dtype (stored as that dtype)."""
+    nh, nkv, d = cfg["nh"], cfg["nkv"], cfg["d"]
+    M = hidden.shape[0]
+    q_raw = F.linear(hidden, w["q_proj"])
+    k = F.linear(hidden, w["k_proj"]).reshape(M, nkv, d)
+    v = F.linear(hidden, w["v_proj"]).reshape(M, nkv, d)
+    gated = q_raw.shape[1] == 2 * nh * d
+    if gated:
+        q, gate = q_raw.view(M, nh, 2 * d).chunk(2, dim=-1)
+        gate = gate.reshape(M, nh * d)
+    else:
+        q = q_raw.reshape(M, nh, d)
+    if w.get("q_norm") is not None:
+        q = rmsnorm(q, w["q_norm"], cfg["eps"])
+    if w.get("k_norm") is not None:
+        k = rmsnorm(k, w["k_norm"], cfg["eps"])
+    cos, sin = rope_tables(int(positions.max()) + 1, cfg["rotary_dim"], cfg["theta"])
+    q = apply_rope(q, cos[positions], sin[positions])
+    k = apply_rope(k, cos[positions], sin[positions])
+    k_new, v_new = k.to(kv_dtype), v.to(kv_dtype)
+    k_cache = k_new if k_cache is None else torch.cat([k_cache, k_new], dim=0)
+    v_cache = v_new if v_cache is None else torch.cat([v_cache, v_new], dim=0)
+    attn = gqa_core(q.to(torch.bfloat16), k_cache, v_cache, positions, 1.0 / math.sqrt(d))
+    flat = attn.reshape(M, nh * d)
+    if gated:
+        flat = flat * torch.sigmoid(gate)
+    return F.linear(flat.to(torch.bfloat16), w["o_proj"]), k_cache, v_cache

@@ -1,0 +1,77 @@
+"""Pins oracle/attention.py against fixtures produced by EXECUTING the reference's own
+python/krasis/linear_attention.py on CPU (tests/golden/make_attention_golden.py), and checks the
+chunked form against the definitional recurrence."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import attention as A
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "gdn_reference.npz"))
+
+
+def _w():
+    bf = torch.bfloat16
+    return {k[2:]: torch.from_numpy(G[k]).to(bf) for k in G.files if k.startswith("w_")}
+
+
+def _cfg():
+    nk, nv, dk, dv, H, K = [int(v) for v in G["cfg"]]
+    return dict(nk=nk, nv=nv, dk=dk, dv=dv, H=H, K=K, eps=1e-6)
+
+
+def test_gdn_layer_matches_reference_execution_two_calls_with_state_carry():
+    w, cfg = _w(), _cfg()
+    x1 = torch.from_numpy(G["x1"]).to(torch.bfloat16)
+    x2 = torch.from_numpy(G["x2"]).to(torch.bfloat16)
+    y1, conv1, st1 = A.gdn_layer_prefill(x1, w, cfg)
+    assert torch.equal(conv1.float(), torch.from_numpy(G["conv1"])[0])           # conv state: exact
+    assert np.abs(st1.numpy() - G["st1"][0]).max() < 1e-5 * max(1.0, np.abs(G["st1"]).max())
+    d1 = np.abs(y1.float().numpy() - G["y1"])
+    assert d1.max() <= 2 ** -7 * np.abs(G["y1"]).max(), d1.max()                # <= 1 bf16 ulp of the max
+    y2, conv2, st2 = A.gdn_layer_prefill(x2, w, cfg, conv_state=conv1, state=st1)
+    assert torch.equal(conv2.float(), torch.from_numpy(G["conv2"])[0])
+    assert np.abs(st2.numpy() - G["st2"][0]).max() < 1e-5 * max(1.0, np.abs(G["st2"]).max())
+    assert np.abs(y2.float().numpy() - G["y2"]).max() <= 2 ** -7 * np.abs(G["y2"]).max()
+
+
+def test_gdn_chunked_equals_definitional_recurrence():
+    torch.manual_seed(0)
+    M, nv, dk, dv = 200, 3, 16, 24
+    q = A.l2norm(torch.randn(M, nv, dk)) / dk ** 0.5
+    k = A.l2norm(torch.randn(M, nv, dk))
+    v = torch.randn(M, nv, dv)
+    beta = torch.sigmoid(torch.randn(M, nv))
+    g = -torch.rand(M, nv) * 0.5
+    s0 = torch.randn(nv, dk, dv) * 0.1
+    o_r, s_r = A.gdn_recurrent(q, k, v, beta, g, s0)
+    o_c, s_c = A.gdn_chunked(q, k, v, beta, g, s0, dtype=torch.float64)
+    assert (o_r - o_c).abs().max() < 1e-10 and (s_r - s_c).abs().max() < 1e-10
+    o_f, s_f = A.gdn_chunked(q, k, v, beta, g, s0, dtype=torch.float32)
+    assert (o_r - o_f.double()).abs().max() < 2e-5
+
+
+def test_gqa_rope_and_cache_semantics():
+    torch.manual_seed(1)
+    cfg = dict(nh=4, nkv=2, d=32, rotary_dim=8, theta=10000.0, eps=1e-6)
+    H = 64
+    bf = torch.bfloat16
+    w = dict(q_proj=(torch.randn(2 * cfg["nh"] * cfg["d"], H) * 0.2).to(bf), k_proj=(torch.randn(cfg["nkv"] * cfg["d"], H) * 0.2).to(bf),
+             v_proj=(torch.randn(cfg["nkv"] * cfg["d"], H) * 0.2).to(bf), o_proj=(torch.randn(H, cfg["nh"] * cfg["d"]) * 0.2).to(bf),
+             q_norm=(1 + 0.1 * torch.randn(cfg["d"])).to(bf), k_norm=(1 + 0.1 * torch.randn(cfg["d"])).to(bf))
+    x = torch.randn(40, H).to(bf)
+    pos = torch.arange(40)
+    y, kc, vc = A.gqa_layer_prefill(x, w, cfg, pos)
+    assert kc.dtype == torch.float8_e4m3fn and kc.shape == (40, 2, 32)
+    # chunked prefill (two calls appending to the cache) equals one call: causal attention over the paged cache
+    y_a, kc_a, vc_a = A.gqa_layer_prefill(x[:25], w, cfg, pos[:25])
+    y_b, _, _ = A.gqa_layer_prefill(x[25:], w, cfg, pos[25:], kc_a, vc_a)
+    assert torch.equal(torch.cat([y_a, y_b]), y)
+    # token 0 attends only to itself: output = o_proj(sigmoid(gate) * v0 expanded over the query groups)
+    # partial RoPE leaves dims >= rotary_dim untouched
+    q = torch.randn(3, 4, 32).to(bf)
+    cos, sin = A.rope_tables(8, 8, 10000.0)
+    r = A.apply_rope(q, cos[torch.tensor([0, 3, 7])], sin[torch.tensor([0, 3, 7])])
+    assert torch.equal(r[..., 8:], q[..., 8:]) and torch.equal(r[0], q[0])
