@@ -159,6 +159,46 @@ KB2_API int kb2_last_expert_counts(kb2_engine* e, int32_t* counts_host, void* st
 /* Number of kernels this library has launched since creation (bench.py reports it as gpu_launches). */
 KB2_API int64_t kb2_launch_count(const kb2_engine* e);
 
+/* ================================================================================================
+ * Attention blocks that feed the MoE path.
+ * ================================================================================================ */
+
+/* torch.nn.functional.linear for BF16 weights (the reference keeps attention projections in BF16,
+ * python/krasis/attention.py:526-529, config.py:209): out[M][N] = x[M][K] . w[N][K]^T (+ bias[N] f32),
+ * fp32 accumulate, BF16 (out_f32=0) or FP32 output.  K % 64 == 0, N % 16 == 0. */
+KB2_API int kb2_linear_bf16(const void* x_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
+                            int32_t N, int32_t K, int32_t out_f32, int32_t device, void* stream);
+
+/* Gated DeltaNet linear attention — python/krasis/linear_attention.py:GatedDeltaNetAttention (prefill path
+ * `_forward_chunked`, :695-844).  One handle holds the weights and the per-layer conv / recurrent state the
+ * reference keeps on the object (:180-205); kb2_gdn_forward == forward(hidden, is_decode=False) for M tokens and
+ * carries the state to the next call; kb2_gdn_reset_state == reset_state() (:207-214). */
+typedef struct kb2_gdn kb2_gdn;
+typedef struct kb2_gdn_config {
+  int32_t hidden_size;      /* cfg.hidden_size */
+  int32_t num_k_heads;      /* cfg.linear_num_key_heads   (16) */
+  int32_t num_v_heads;      /* cfg.linear_num_value_heads (32) */
+  int32_t k_head_dim;       /* cfg.linear_key_head_dim    (128) */
+  int32_t v_head_dim;       /* cfg.linear_value_head_dim  (128) */
+  int32_t conv_kernel;      /* cfg.linear_conv_kernel_dim (4) */
+  float rms_norm_eps;
+  int32_t max_tokens;
+  int32_t num_layers;
+  int32_t device;
+} kb2_gdn_config;
+KB2_API int kb2_gdn_create(const kb2_gdn_config* cfg, kb2_gdn** out);
+KB2_API void kb2_gdn_destroy(kb2_gdn* h);
+/* All weights BF16, host pointers, shapes as in the HF checkpoint (linear_attention.py:131-139):
+ * in_proj_qkvz [2*kd+2*vd][H], in_proj_ba [2*nv][H], conv1d.weight [2*kd+vd][1][K], A_log [nv], dt_bias [nv],
+ * norm.weight [dv], out_proj [H][vd]. */
+KB2_API int kb2_gdn_set_weights_host(kb2_gdn* h, int layer, const void* in_proj_qkvz, const void* in_proj_ba,
+                                     const void* conv1d_weight, const void* A_log, const void* dt_bias,
+                                     const void* norm_weight, const void* out_proj);
+KB2_API int kb2_gdn_forward(kb2_gdn* h, int layer, const void* hidden_dev, void* out_dev, int32_t num_tokens, void* stream);
+KB2_API int kb2_gdn_reset_state(kb2_gdn* h, int layer, void* stream);
+/* conv state [C][K] bf16 and recurrent state [nv][dk][dv] f32 (either pointer may be NULL); synchronises. */
+KB2_API int kb2_gdn_get_state_host(kb2_gdn* h, int layer, void* conv_state_bf16_host, float* recurrent_state_host);
+
 /* Per-kernel device timing with CUDA events recorded on the launching stream (the reference's
  * KRASIS_LAYER_TIMING / EP breakdown, python/krasis/model.py:2839-2860).  kb2_profile_collect synchronises the
  * device and returns, per kernel class, the summed milliseconds and the number of launches since enable. */

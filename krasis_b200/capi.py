@@ -22,6 +22,13 @@ class Config(C.Structure):
     ]
 
 
+class GdnConfig(C.Structure):
+    _fields_ = [("hidden_size", C.c_int32), ("num_k_heads", C.c_int32), ("num_v_heads", C.c_int32),
+                ("k_head_dim", C.c_int32), ("v_head_dim", C.c_int32), ("conv_kernel", C.c_int32),
+                ("rms_norm_eps", C.c_float), ("max_tokens", C.c_int32), ("num_layers", C.c_int32),
+                ("device", C.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/krasis_b200.h declares
 SIGNATURES = {
     "kb2_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -48,6 +55,13 @@ SIGNATURES = {
                                              C.c_void_p]),
     "kb2_last_expert_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "kb2_launch_count": (C.c_int64, [C.c_void_p]),
+    "kb2_linear_bf16": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_void_p]),
+    "kb2_gdn_create": (C.c_int, [C.POINTER(GdnConfig), C.POINTER(C.c_void_p)]),
+    "kb2_gdn_destroy": (None, [C.c_void_p]),
+    "kb2_gdn_set_weights_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7),
+    "kb2_gdn_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "kb2_gdn_reset_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "kb2_gdn_get_state_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "kb2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "kb2_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

@@ -46,6 +46,11 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+extern "C" int kb2_set_error_(int code, const char* msg) {   // shared with capi_attn.cu (not exported)
+  g_err = msg;
+  return code;
+}
+
 #define CUDA_TRY(expr)                                                                      \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

@@ -1,0 +1,220 @@
+// C-ABI for the attention blocks that feed the MoE path (include/krasis_b200.h, "attention" section).
+// Host state mirrors python/krasis/linear_attention.py:GatedDeltaNetAttention (weights + conv/recurrent state).
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/krasis_b200.h"
+#include "moe_common.cuh"
+
+namespace kb2 {
+struct GdnDims {
+  int H, nk, nv, dk, dv, K;
+  float eps, scale;
+};
+cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
+                              long long ldo, bool out_f32, int num_sms, cudaStream_t s);
+cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, const void* conv_w, void* conv_state,
+                            const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
+                            void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
+                            float* gcum, float* core, void* normed_out, int M, cudaStream_t s);
+}  // namespace kb2
+using namespace kb2;
+
+extern "C" int kb2_set_error_(int code, const char* msg);   // defined in capi.cu
+
+static int failf(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return kb2_set_error_(code, buf);
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) return failf(KB2_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int device_sms(int device) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) return 148;
+  if (!cached[device]) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) == cudaSuccess) cached[device] = p.multiProcessorCount;
+    else cached[device] = 148;
+  }
+  return cached[device];
+}
+
+struct GdnLayer {
+  void *w_qkvz = nullptr, *w_ba = nullptr, *w_out = nullptr, *conv_w = nullptr, *conv_state = nullptr;
+  float *A_log = nullptr, *dt_bias = nullptr, *norm_w = nullptr, *rec_state = nullptr;
+  bool loaded = false;
+};
+
+struct kb2_gdn {
+  kb2_gdn_config cfg{};
+  GdnDims d{};
+  std::vector<GdnLayer> layers;
+  void *qkvz = nullptr, *ba = nullptr, *qn = nullptr, *kn = nullptr, *vc = nullptr, *normed = nullptr;
+  float *beta = nullptr, *g = nullptr, *vcorr = nullptr, *kcd = nullptr, *intra = nullptr, *gcum = nullptr, *core = nullptr;
+};
+
+static std::vector<float> bf16_to_f32_host(const void* p, size_t n) {
+  std::vector<float> out(n);
+  const uint16_t* u = (const uint16_t*)p;
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t b = (uint32_t)u[i] << 16;
+    memcpy(&out[i], &b, 4);
+  }
+  return out;
+}
+
+extern "C" {
+
+KB2_API int kb2_linear_bf16(const void* x_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
+                            int32_t N, int32_t K, int32_t out_f32, int32_t device, void* stream) {
+  if (!x_dev || !w_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (M <= 0 || N <= 0 || K <= 0 || K % 64 || N % 16) return failf(KB2_ERR_VALUE, "linear: need M>0, K %% 64 == 0, N %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_dense_gemm(x_dev, w_dev, out_dev, bias_dev, M, N, K, N, out_f32 != 0, device_sms(device), (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_gdn_create(const kb2_gdn_config* c, kb2_gdn** out) {
+  if (!c || !out) return failf(KB2_ERR_VALUE, "null argument");
+  if (c->num_k_heads < 1 || c->num_v_heads % c->num_k_heads) return failf(KB2_ERR_VALUE, "num_v_heads must be a multiple of num_k_heads");
+  if (c->k_head_dim > 128 || c->v_head_dim > 128 || c->v_head_dim % 32 || c->k_head_dim % 8) return failf(KB2_ERR_VALUE, "head dims must be <= 128 (v_head_dim %% 32 == 0)");
+  if (c->conv_kernel < 1 || c->conv_kernel > 8) return failf(KB2_ERR_VALUE, "conv_kernel must be in [1,8]");
+  if (c->hidden_size % 64) return failf(KB2_ERR_VALUE, "hidden_size must be a multiple of 64");
+  const int kd = c->num_k_heads * c->k_head_dim, vd = c->num_v_heads * c->v_head_dim;
+  if ((2 * kd + 2 * vd) % 16 || (2 * c->num_v_heads) % 16 || vd % 64) return failf(KB2_ERR_VALUE, "projection widths must be multiples of 16 (qkvz %d, ba %d) and value_dim of 64", 2 * kd + 2 * vd, 2 * c->num_v_heads);
+  if (c->max_tokens < 1 || c->num_layers < 1) return failf(KB2_ERR_VALUE, "max_tokens and num_layers must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return failf(KB2_ERR_CUDA, "no CUDA device: krasis_b200 has no CPU fallback");
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  kb2_gdn* h = new kb2_gdn();
+  h->cfg = *c;
+  h->d = GdnDims{c->hidden_size, c->num_k_heads, c->num_v_heads, c->k_head_dim, c->v_head_dim, c->conv_kernel,
+                 c->rms_norm_eps, 1.0f / sqrtf((float)c->k_head_dim)};
+  h->layers.resize(c->num_layers);
+  const size_t M = c->max_tokens, nch = (M + 63) / 64, nv = c->num_v_heads;
+#define ALLOC(ptr, bytes) CUDA_TRY(cudaMalloc((void**)&(ptr), (bytes)))
+  ALLOC(h->qkvz, M * (2 * kd + 2 * vd) * 2);
+  ALLOC(h->ba, M * 2 * nv * 2);
+  ALLOC(h->qn, M * kd * 2);
+  ALLOC(h->kn, M * kd * 2);
+  ALLOC(h->vc, M * vd * 2);
+  ALLOC(h->normed, M * vd * 2);
+  ALLOC(h->beta, M * nv * 4);
+  ALLOC(h->g, M * nv * 4);
+  ALLOC(h->vcorr, nv * nch * 64 * c->v_head_dim * 4);
+  ALLOC(h->kcd, nv * nch * 64 * c->k_head_dim * 4);
+  ALLOC(h->intra, nv * nch * 64 * 64 * 4);
+  ALLOC(h->gcum, nv * nch * 64 * 4);
+  ALLOC(h->core, M * vd * 4);
+#undef ALLOC
+  *out = h;
+  return KB2_OK;
+}
+
+KB2_API void kb2_gdn_destroy(kb2_gdn* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (auto& L : h->layers) {
+    cudaFree(L.w_qkvz); cudaFree(L.w_ba); cudaFree(L.w_out); cudaFree(L.conv_w); cudaFree(L.conv_state);
+    cudaFree(L.A_log); cudaFree(L.dt_bias); cudaFree(L.norm_w); cudaFree(L.rec_state);
+  }
+  cudaFree(h->qkvz); cudaFree(h->ba); cudaFree(h->qn); cudaFree(h->kn); cudaFree(h->vc); cudaFree(h->normed);
+  cudaFree(h->beta); cudaFree(h->g); cudaFree(h->vcorr); cudaFree(h->kcd); cudaFree(h->intra); cudaFree(h->gcum);
+  cudaFree(h->core);
+  delete h;
+}
+
+static int gdn_check(kb2_gdn* h, int layer) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  if (layer < 0 || layer >= (int)h->layers.size()) return failf(KB2_ERR_VALUE, "layer %d out of range [0, %d)", layer, (int)h->layers.size());
+  return KB2_OK;
+}
+
+KB2_API int kb2_gdn_set_weights_host(kb2_gdn* h, int layer, const void* in_proj_qkvz, const void* in_proj_ba,
+                                     const void* conv1d_weight, const void* A_log, const void* dt_bias,
+                                     const void* norm_weight, const void* out_proj) {
+  if (int r = gdn_check(h, layer)) return r;
+  if (!in_proj_qkvz || !in_proj_ba || !conv1d_weight || !A_log || !dt_bias || !norm_weight || !out_proj) return failf(KB2_ERR_VALUE, "null weight pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const auto& c = h->cfg;
+  const size_t kd = c.num_k_heads * c.k_head_dim, vd = c.num_v_heads * c.v_head_dim, C = 2 * kd + vd, H = c.hidden_size;
+  GdnLayer& L = h->layers[layer];
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!*dst) { cudaError_t e = cudaMalloc(dst, bytes); if (e != cudaSuccess) return e; }
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  CUDA_TRY(up(&L.w_qkvz, in_proj_qkvz, (2 * kd + 2 * vd) * H * 2));
+  CUDA_TRY(up(&L.w_ba, in_proj_ba, 2 * c.num_v_heads * H * 2));
+  CUDA_TRY(up(&L.w_out, out_proj, H * vd * 2));
+  CUDA_TRY(up(&L.conv_w, conv1d_weight, C * c.conv_kernel * 2));
+  auto a = bf16_to_f32_host(A_log, c.num_v_heads), b = bf16_to_f32_host(dt_bias, c.num_v_heads), n = bf16_to_f32_host(norm_weight, c.v_head_dim);
+  CUDA_TRY(up((void**)&L.A_log, a.data(), a.size() * 4));
+  CUDA_TRY(up((void**)&L.dt_bias, b.data(), b.size() * 4));
+  CUDA_TRY(up((void**)&L.norm_w, n.data(), n.size() * 4));
+  if (!L.conv_state) CUDA_TRY(cudaMalloc(&L.conv_state, C * c.conv_kernel * 2));
+  if (!L.rec_state) CUDA_TRY(cudaMalloc((void**)&L.rec_state, (size_t)c.num_v_heads * c.k_head_dim * c.v_head_dim * 4));
+  CUDA_TRY(cudaMemset(L.conv_state, 0, C * c.conv_kernel * 2));
+  CUDA_TRY(cudaMemset(L.rec_state, 0, (size_t)c.num_v_heads * c.k_head_dim * c.v_head_dim * 4));
+  L.loaded = true;
+  return KB2_OK;
+}
+
+KB2_API int kb2_gdn_reset_state(kb2_gdn* h, int layer, void* stream) {
+  if (int r = gdn_check(h, layer)) return r;
+  GdnLayer& L = h->layers[layer];
+  if (!L.loaded) return failf(KB2_ERR_STATE, "GDN weights not set for layer %d", layer);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const auto& c = h->cfg;
+  const size_t C = 2 * c.num_k_heads * c.k_head_dim + c.num_v_heads * c.v_head_dim;
+  CUDA_TRY(cudaMemsetAsync(L.conv_state, 0, C * c.conv_kernel * 2, (cudaStream_t)stream));
+  CUDA_TRY(cudaMemsetAsync(L.rec_state, 0, (size_t)c.num_v_heads * c.k_head_dim * c.v_head_dim * 4, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_gdn_get_state_host(kb2_gdn* h, int layer, void* conv_state_bf16_host, float* recurrent_state_host) {
+  if (int r = gdn_check(h, layer)) return r;
+  GdnLayer& L = h->layers[layer];
+  if (!L.loaded) return failf(KB2_ERR_STATE, "GDN weights not set for layer %d", layer);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const auto& c = h->cfg;
+  const size_t C = 2 * c.num_k_heads * c.k_head_dim + c.num_v_heads * c.v_head_dim;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (conv_state_bf16_host) CUDA_TRY(cudaMemcpy(conv_state_bf16_host, L.conv_state, C * c.conv_kernel * 2, cudaMemcpyDeviceToHost));
+  if (recurrent_state_host) CUDA_TRY(cudaMemcpy(recurrent_state_host, L.rec_state, (size_t)c.num_v_heads * c.k_head_dim * c.v_head_dim * 4, cudaMemcpyDeviceToHost));
+  return KB2_OK;
+}
+
+KB2_API int kb2_gdn_forward(kb2_gdn* h, int layer, const void* hidden_dev, void* out_dev, int32_t M, void* stream) {
+  if (int r = gdn_check(h, layer)) return r;
+  GdnLayer& L = h->layers[layer];
+  if (M < 0 || M > h->cfg.max_tokens) return failf(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, h->cfg.max_tokens);
+  if (!L.loaded) return failf(KB2_ERR_STATE, "GDN weights not set for layer %d", layer);
+  if (M == 0) return KB2_OK;
+  if (!hidden_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const auto& c = h->cfg;
+  const int kd = c.num_k_heads * c.k_head_dim, vd = c.num_v_heads * c.v_head_dim, H = c.hidden_size;
+  const int sms = device_sms(c.device);
+  CUDA_TRY(launch_dense_gemm(hidden_dev, L.w_qkvz, h->qkvz, nullptr, M, 2 * kd + 2 * vd, H, 2 * kd + 2 * vd, false, sms, s));
+  CUDA_TRY(launch_dense_gemm(hidden_dev, L.w_ba, h->ba, nullptr, M, 2 * c.num_v_heads, H, 2 * c.num_v_heads, false, sms, s));
+  CUDA_TRY(launch_gdn_core(h->d, h->qkvz, h->ba, L.conv_w, L.conv_state, L.A_log, L.dt_bias, L.norm_w, L.rec_state,
+                           h->qn, h->kn, h->vc, h->beta, h->g, h->vcorr, h->kcd, h->intra, h->gcum, h->core, h->normed, M, s));
+  CUDA_TRY(launch_dense_gemm(h->normed, L.w_out, out_dev, nullptr, M, H, vd, H, false, sms, s));
+  return KB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// Dense BF16 linear layer on tcgen05:  Y[M,N] = X[M,K] (bf16) x W[N,K]^T (bf16), fp32 accumulate in TMEM,
+// BF16 (or FP32) output.  This is `torch.nn.functional.linear` for the attention projections the reference
+// keeps in BF16 (python/krasis/attention.py:526-529,672; python/krasis/linear_attention.py:709-710,815 —
+// "attention weights BF16 only", python/krasis/config.py:209).
+//
+// Persistent CTAs, 128 x 256 output tiles, 64-wide K blocks, 4-stage TMA ring (2-D tensor maps, 128 B swizzle),
+// one MMA thread (SS-MMA, M=128, N=256), two 256-column TMEM accumulators so the epilogue of tile i overlaps the
+// main loop of tile i+1, four epilogue warps writing 32 B per thread per tcgen05.ld.
+#include <cuda.h>
+
+#include "moe_common.cuh"
+#include "ptx.cuh"
+
+namespace kb2 {
+
+constexpr int kDThreads = 256;
+constexpr int kDStages = 4;
+constexpr int kDTileM = 128, kDTileN = 256;
+constexpr int kDABytes = kDTileM * kBlockK * 2;   // 16 KB
+constexpr int kDBBytes = kDTileN * kBlockK * 2;   // 32 KB
+constexpr int kDStage = kDABytes + kDBBytes;
+constexpr int kDOffBar = kDStages * kDStage;
+constexpr int kDSmem = kDOffBar + 128;
+
+template <bool kOutF32>
+__global__ void __launch_bounds__(kDThreads, 1)
+    dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                      void* __restrict__ out, const float* __restrict__ bias, int M, int N, int K, long long ldo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDOffBar);
+  uint64_t* empty = full + kDStages;
+  uint64_t* acc_full = empty + kDStages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (N + kDTileN - 1) / kDTileN, m_tiles = (M + kDTileM - 1) / kDTileM;
+  const int total = n_tiles * m_tiles;
+  const int nkb = K / kBlockK;
+
+  if (threadIdx.x == 32) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int i = 0; i < kDStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr_smem, 512);
+  if (threadIdx.x == 64) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * kDTileM, n0 = (t % n_tiles) * kDTileN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a = smem + stage * kDStage;
+          mbar_arrive_expect_tx(&full[stage], kDStage);
+          tma_load_2d(a, &tmap_x, kb * kBlockK, m0, &full[stage]);
+          tma_load_2d(a + kDABytes, &tmap_w, kb * kBlockK, n0, &full[stage]);               // rows n0..n0+127
+          tma_load_2d(a + kDABytes + kDABytes, &tmap_w, kb * kBlockK, n0 + 128, &full[stage]); // rows n0+128..+255
+          if (++stage == kDStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t aphase[2] = {0, 0};
+      const uint32_t idesc = umma_idesc_bf16_m128(kDTileN);
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        mbar_wait(&acc_empty[b], aphase[b] ^ 1);
+        aphase[b] ^= 1;
+        tc_fence_after_sync();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * kDStage);
+          const uint64_t ad = umma_desc_k_sw128(a_addr);
+          const uint64_t bd = umma_desc_k_sw128(a_addr + kDABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == kDStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[b]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    uint32_t fphase[2] = {0, 0};
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int b = it & 1;
+      const int m = (t / n_tiles) * kDTileM + q * 32 + lane, n0 = (t % n_tiles) * kDTileN;
+      mbar_wait(&acc_full[b], fphase[b]);
+      fphase[b] ^= 1;
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * kDTileN;
+#pragma unroll 2
+      for (int c0 = 0; c0 < kDTileN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (m < M && n < N) {          // N % 16 == 0 is required by the launcher
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (bias ? bias[n + j] : 0.f);
+          if constexpr (kOutF32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)m * ldo + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ldo + n);
+            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[b]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
+
+// X [M][K] bf16 row-major, W [N][K] bf16 row-major, out [M][ldo] (bf16 or f32).  K % 64 == 0, N % 16 == 0.
+cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
+                              long long ldo, bool out_f32, int num_sms, cudaStream_t s) {
+  if (K % kBlockK || N % 16 || M <= 0) return cudaErrorInvalidValue;
+  alignas(64) CUtensorMap tx, tw;
+  cudaError_t e = make_tmap_bf16_rows(&tx, x, M, K, 128);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tw, w, N, K, 128);
+  if (e != cudaSuccess) return e;
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(dense_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dense_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int total = ((M + kDTileM - 1) / kDTileM) * ((N + kDTileN - 1) / kDTileN);
+  const int grid = total < num_sms ? total : num_sms;
+  if (out_f32)
+    dense_gemm_kernel<true><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo);
+  else
+    dense_gemm_kernel<false><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo);
+  return cudaGetLastError();
+}
+
+}  // namespace kb2
