@@ -12,6 +12,7 @@ namespace kb2 {
 struct GdnDims {
   int H, nk, nv, dk, dv, K;
   float eps, scale;
+  int ba_ld;
 };
 cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
                               long long ldo, bool out_f32, int num_sms, cudaStream_t s);
@@ -91,7 +92,7 @@ KB2_API int kb2_gdn_create(const kb2_gdn_config* c, kb2_gdn** out) {
   if (c->conv_kernel < 1 || c->conv_kernel > 8) return failf(KB2_ERR_VALUE, "conv_kernel must be in [1,8]");
   if (c->hidden_size % 64) return failf(KB2_ERR_VALUE, "hidden_size must be a multiple of 64");
   const int kd = c->num_k_heads * c->k_head_dim, vd = c->num_v_heads * c->v_head_dim;
-  if ((2 * kd + 2 * vd) % 16 || (2 * c->num_v_heads) % 16 || vd % 64) return failf(KB2_ERR_VALUE, "projection widths must be multiples of 16 (qkvz %d, ba %d) and value_dim of 64", 2 * kd + 2 * vd, 2 * c->num_v_heads);
+  if ((2 * kd + 2 * vd) % 16 || vd % 64) return failf(KB2_ERR_VALUE, "qkvz width (%d) must be a multiple of 16 and value_dim (%d) of 64", 2 * kd + 2 * vd, vd);
   if (c->max_tokens < 1 || c->num_layers < 1) return failf(KB2_ERR_VALUE, "max_tokens and num_layers must be >= 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -102,12 +103,12 @@ KB2_API int kb2_gdn_create(const kb2_gdn_config* c, kb2_gdn** out) {
   kb2_gdn* h = new kb2_gdn();
   h->cfg = *c;
   h->d = GdnDims{c->hidden_size, c->num_k_heads, c->num_v_heads, c->k_head_dim, c->v_head_dim, c->conv_kernel,
-                 c->rms_norm_eps, 1.0f / sqrtf((float)c->k_head_dim)};
+                 c->rms_norm_eps, 1.0f / sqrtf((float)c->k_head_dim), (2 * c->num_v_heads + 15) & ~15};
   h->layers.resize(c->num_layers);
   const size_t M = c->max_tokens, nch = (M + 63) / 64, nv = c->num_v_heads;
 #define ALLOC(ptr, bytes) CUDA_TRY(cudaMalloc((void**)&(ptr), (bytes)))
   ALLOC(h->qkvz, M * (2 * kd + 2 * vd) * 2);
-  ALLOC(h->ba, M * 2 * nv * 2);
+  ALLOC(h->ba, M * (size_t)h->d.ba_ld * 2);
   ALLOC(h->qn, M * kd * 2);
   ALLOC(h->kn, M * kd * 2);
   ALLOC(h->vc, M * vd * 2);
@@ -157,7 +158,9 @@ KB2_API int kb2_gdn_set_weights_host(kb2_gdn* h, int layer, const void* in_proj_
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
   };
   CUDA_TRY(up(&L.w_qkvz, in_proj_qkvz, (2 * kd + 2 * vd) * H * 2));
-  CUDA_TRY(up(&L.w_ba, in_proj_ba, 2 * c.num_v_heads * H * 2));
+  if (!L.w_ba) CUDA_TRY(cudaMalloc(&L.w_ba, (size_t)h->d.ba_ld * H * 2));
+  CUDA_TRY(cudaMemset(L.w_ba, 0, (size_t)h->d.ba_ld * H * 2));            // rows padded to a multiple of 16 with zeros
+  CUDA_TRY(cudaMemcpy(L.w_ba, in_proj_ba, 2 * c.num_v_heads * H * 2, cudaMemcpyHostToDevice));
   CUDA_TRY(up(&L.w_out, out_proj, H * vd * 2));
   CUDA_TRY(up(&L.conv_w, conv1d_weight, C * c.conv_kernel * 2));
   auto a = bf16_to_f32_host(A_log, c.num_v_heads), b = bf16_to_f32_host(dt_bias, c.num_v_heads), n = bf16_to_f32_host(norm_weight, c.v_head_dim);
@@ -210,7 +213,7 @@ KB2_API int kb2_gdn_forward(kb2_gdn* h, int layer, const void* hidden_dev, void*
   const int kd = c.num_k_heads * c.k_head_dim, vd = c.num_v_heads * c.v_head_dim, H = c.hidden_size;
   const int sms = device_sms(c.device);
   CUDA_TRY(launch_dense_gemm(hidden_dev, L.w_qkvz, h->qkvz, nullptr, M, 2 * kd + 2 * vd, H, 2 * kd + 2 * vd, false, sms, s));
-  CUDA_TRY(launch_dense_gemm(hidden_dev, L.w_ba, h->ba, nullptr, M, 2 * c.num_v_heads, H, 2 * c.num_v_heads, false, sms, s));
+  CUDA_TRY(launch_dense_gemm(hidden_dev, L.w_ba, h->ba, nullptr, M, h->d.ba_ld, H, h->d.ba_ld, false, sms, s));
   CUDA_TRY(launch_gdn_core(h->d, h->qkvz, h->ba, L.conv_w, L.conv_state, L.A_log, L.dt_bias, L.norm_w, L.rec_state,
                            h->qn, h->kn, h->vc, h->beta, h->g, h->vcorr, h->kcd, h->intra, h->gcum, h->core, h->normed, M, s));
   CUDA_TRY(launch_dense_gemm(h->normed, L.w_out, out_dev, nullptr, M, H, vd, H, false, sms, s));

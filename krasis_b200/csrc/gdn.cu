@@ -20,6 +20,7 @@ constexpr int kGC = 64;   // chunk size (linear_attention.py:702)
 struct GdnDims {
   int H, nk, nv, dk, dv, K;   // K = conv kernel size (4)
   float eps, scale;
+  int ba_ld;                  // row stride of the ba projection output (2*nv rounded up to 16)
 };
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -86,8 +87,8 @@ __global__ void __launch_bounds__(256) gdn_prep_kernel(GdnDims d, const __nv_bfl
   const int r = d.nv / d.nk;
   for (int h = threadIdx.x; h < d.nv; h += blockDim.x) {
     const int kh = h / r, j = h % r;
-    const float b = __bfloat162float(ba[(long long)t * 2 * d.nv + kh * 2 * r + j]);
-    const float a = __bfloat162float(ba[(long long)t * 2 * d.nv + kh * 2 * r + r + j]);
+    const float b = __bfloat162float(ba[(long long)t * d.ba_ld + kh * 2 * r + j]);
+    const float a = __bfloat162float(ba[(long long)t * d.ba_ld + kh * 2 * r + r + j]);
     beta[(long long)t * d.nv + h] = bf16r(1.0f / (1.0f + expf(-b)));          // sigmoid on a BF16 tensor
     const float x = a + dt_bias[h];
     const float sp = x > 20.f ? x : log1pf(expf(x));                           // F.softplus (threshold 20)
