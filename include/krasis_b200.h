@@ -199,6 +199,38 @@ KB2_API int kb2_gdn_reset_state(kb2_gdn* h, int layer, void* stream);
 /* conv state [C][K] bf16 and recurrent state [nv][dk][dv] f32 (either pointer may be NULL); synchronises. */
 KB2_API int kb2_gdn_get_state_host(kb2_gdn* h, int layer, void* conv_state_bf16_host, float* recurrent_state_host);
 
+/* GQA attention — python/krasis/attention.py:GQAAttention.forward (:496-687): q/k/v projections (BF16), gated-q split,
+ * per-head RMSNorm, partial half-split RoPE, FP8-E4M3 paged KV append (page = 16 tokens, NHD, unscaled cast), causal
+ * attention over the paged cache, sigmoid output gate, o_proj.  The KV cache tensors stay with the caller, exactly like
+ * PagedKVCache.get_gqa_layer_caches(layer_offset) + SequenceKVState.kv_indices (python/krasis/kv_cache.py). */
+typedef struct kb2_gqa kb2_gqa;
+typedef struct kb2_gqa_config {
+  int32_t hidden_size;
+  int32_t num_heads;        /* cfg.num_attention_heads */
+  int32_t num_kv_heads;     /* cfg.num_key_value_heads */
+  int32_t head_dim;         /* cfg.gqa_head_dim: 128 or 256 */
+  int32_t rotary_dim;       /* int(head_dim * partial_rotary_factor) (config.py:469-473) */
+  int32_t gated;            /* q_proj emits [q | gate] per head (attention.py:398-406) */
+  float rope_theta;
+  float rms_norm_eps;
+  int32_t page_size;        /* 16 (kv_cache.py:26) */
+  int32_t max_tokens;
+  int32_t num_layers;
+  int32_t device;
+} kb2_gqa_config;
+KB2_API int kb2_gqa_create(const kb2_gqa_config* cfg, kb2_gqa** out);
+KB2_API void kb2_gqa_destroy(kb2_gqa* h);
+/* BF16 host weights: q_proj [nh*d*(1+gated)][H], k_proj/v_proj [nkv*d][H], o_proj [H][nh*d], q_norm/k_norm [d] or NULL
+ * (already shifted by +1 for Qwen3-Next, like the reference does at load, weight_loader.py:259-265). */
+KB2_API int kb2_gqa_set_weights_host(kb2_gqa* h, int layer, const void* q_proj, const void* k_proj, const void* v_proj,
+                                     const void* o_proj, const void* q_norm, const void* k_norm);
+/* hidden [M][H] bf16; positions [M] int32 = first_position .. first_position+M-1 (prefill appends contiguously);
+ * k/v cache of THIS layer: [num_pages][16][nkv][d] FP8-E4M3; kv_indices: page ids of the sequence covering
+ * kv_len_after = first_position + M tokens; out [M][H] bf16. */
+KB2_API int kb2_gqa_forward(kb2_gqa* h, int layer, const void* hidden_dev, const int32_t* positions_dev, int32_t first_position,
+                            void* k_cache_layer_dev, void* v_cache_layer_dev, const int32_t* kv_indices_dev,
+                            int32_t kv_len_after, void* out_dev, int32_t num_tokens, void* stream);
+
 /* Per-kernel device timing with CUDA events recorded on the launching stream (the reference's
  * KRASIS_LAYER_TIMING / EP breakdown, python/krasis/model.py:2839-2860).  kb2_profile_collect synchronises the
  * device and returns, per kernel class, the summed milliseconds and the number of launches since enable. */

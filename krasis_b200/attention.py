@@ -95,3 +95,120 @@ class GatedDeltaNetAttention:
         rec = np.zeros((c.num_v_heads, c.k_head_dim, c.v_head_dim), np.float32)
         capi.check(self._lib.kb2_gdn_get_state_host(self._h, 0, conv.ctypes.data, rec.ctypes.data))
         return (conv.astype(np.uint32) << 16).view(np.float32), rec
+
+
+PAGE_SIZE = 16   # python/krasis/kv_cache.py:26
+
+
+class PagedKVCache:
+    """GQA part of python/krasis/kv_cache.py:PagedKVCache (:31-186): FP8-E4M3 K/V pools
+    [num_layers, max_pages, 16, num_kv_heads, head_dim] and a free-list page allocator."""
+
+    def __init__(self, num_layers: int, num_kv_heads: int, head_dim: int, device, max_pages: int,
+                 kv_dtype=torch.float8_e4m3fn, page_size: int = PAGE_SIZE):
+        if page_size != PAGE_SIZE or kv_dtype != torch.float8_e4m3fn:
+            raise ValueError("only page_size=16 and float8_e4m3fn are supported (the reference defaults)")
+        self.num_layers, self.num_kv_heads, self.gqa_head_dim = num_layers, num_kv_heads, head_dim
+        self.page_size, self.kv_dtype, self.max_pages = page_size, kv_dtype, max_pages
+        self.device = torch.device(device)
+        shape = (num_layers, max_pages, page_size, num_kv_heads, head_dim)
+        self.k_cache = torch.zeros(shape, dtype=kv_dtype, device=self.device)
+        self.v_cache = torch.zeros(shape, dtype=kv_dtype, device=self.device)
+        self._free = list(range(max_pages - 1, -1, -1))
+
+    def get_gqa_layer_caches(self, layer_offset: int):
+        return self.k_cache[layer_offset], self.v_cache[layer_offset]
+
+    def alloc_page(self) -> int:
+        if not self._free:
+            raise RuntimeError("KV cache out of pages")
+        return self._free.pop()
+
+    def free_pages(self, pages):
+        self._free.extend(pages)
+
+
+class SequenceKVState:
+    """python/krasis/kv_cache.py:SequenceKVState (:189-272): page list + seq_len of one sequence."""
+
+    def __init__(self, cache: PagedKVCache, seq_id: int = 0):
+        self.cache, self.seq_id, self.pages, self.seq_len = cache, seq_id, [], 0
+        self._idx = None
+
+    def ensure_capacity(self, num_new_tokens: int):
+        need = (self.seq_len + num_new_tokens + self.cache.page_size - 1) // self.cache.page_size
+        while len(self.pages) < need:
+            self.pages.append(self.cache.alloc_page())
+            self._idx = None
+
+    def advance(self, num_new_tokens: int):
+        self.seq_len += num_new_tokens
+
+    def kv_indices(self, device) -> torch.Tensor:
+        if self._idx is None or self._idx.numel() != len(self.pages):
+            self._idx = torch.tensor(self.pages, dtype=torch.int32, device=device)
+        return self._idx
+
+    def last_page_len(self) -> int:
+        r = self.seq_len % self.cache.page_size
+        return r if r else self.cache.page_size
+
+    def free(self):
+        self.cache.free_pages(self.pages)
+        self.pages, self.seq_len, self._idx = [], 0, None
+
+
+class GQAAttention:
+    """Drop-in for python/krasis/attention.py:GQAAttention (prefill): forward(hidden, positions, kv_cache,
+    seq_state, layer_offset, num_new_tokens) -> [M, hidden] bf16.  `cfg` needs hidden_size, num_attention_heads,
+    num_key_value_heads, gqa_head_dim, rotary_dim, rope_theta, rms_norm_eps.  weights: q_proj, k_proj, v_proj, o_proj
+    (+ optional q_norm, k_norm) BF16 tensors; gated attention is detected from q_proj's row count (:398-406)."""
+
+    def __init__(self, cfg, layer_idx: int, weights: dict, device, max_tokens: int = 8192):
+        self.cfg, self.layer_idx, self.device = cfg, layer_idx, torch.device(device)
+        for k in ("q_proj_bias", "k_proj_bias", "v_proj_bias", "o_proj_bias", "sinks"):
+            if weights.get(k) is not None:
+                raise NotImplementedError(f"{k}: GLM / GPT-OSS attention variants are out of scope (SURVEY.md §8a)")
+        nh, nkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.gqa_head_dim
+        q_rows = weights["q_proj"].shape[0]
+        self.gated_attention = q_rows == 2 * nh * d
+        if not self.gated_attention and q_rows != nh * d:
+            raise ValueError(f"q_proj has {q_rows} rows, expected {nh * d} or {2 * nh * d}")
+        self._lib = capi.load()
+        c = capi.GqaConfig(cfg.hidden_size, nh, nkv, d, cfg.rotary_dim, int(self.gated_attention), float(cfg.rope_theta),
+                           float(cfg.rms_norm_eps), PAGE_SIZE, max_tokens, 1, self.device.index or 0)
+        self._h = C.c_void_p()
+        capi.check(self._lib.kb2_gqa_create(C.byref(c), C.byref(self._h)))
+        arrs = [_bf16_host(weights[k]) for k in ("q_proj", "k_proj", "v_proj", "o_proj")]
+        qn = _bf16_host(weights["q_norm"]) if weights.get("q_norm") is not None else None
+        kn = _bf16_host(weights["k_norm"]) if weights.get("k_norm") is not None else None
+        capi.check(self._lib.kb2_gqa_set_weights_host(self._h, 0, *[a.ctypes.data for a in arrs],
+                                                      qn.ctypes.data if qn is not None else None,
+                                                      kn.ctypes.data if kn is not None else None))
+        self._c = c
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.kb2_gqa_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def forward(self, hidden: torch.Tensor, positions: torch.Tensor, kv_cache: PagedKVCache, seq_state: SequenceKVState,
+                layer_offset: int, num_new_tokens: int = 0) -> torch.Tensor:
+        if not hidden.is_cuda or hidden.dtype != torch.bfloat16 or hidden.dim() != 2 or not hidden.is_contiguous() \
+                or hidden.shape[1] != self._c.hidden_size:
+            raise ValueError(f"hidden: expected contiguous CUDA bf16 [M, {self._c.hidden_size}]")
+        M = hidden.shape[0]
+        if num_new_tokens not in (0, M):
+            raise ValueError("num_new_tokens must equal the number of rows of hidden")
+        seq_state.ensure_capacity(M)
+        k_layer, v_layer = kv_cache.get_gqa_layer_caches(layer_offset)
+        pos = positions.to(device=hidden.device, dtype=torch.int32).contiguous()
+        out = torch.empty_like(hidden)
+        capi.check(self._lib.kb2_gqa_forward(self._h, 0, hidden.data_ptr(), pos.data_ptr(), seq_state.seq_len,
+                                             k_layer.data_ptr(), v_layer.data_ptr(),
+                                             seq_state.kv_indices(hidden.device).data_ptr(), seq_state.seq_len + M,
+                                             out.data_ptr(), M, _stream(hidden.device)))
+        return out

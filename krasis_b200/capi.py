@@ -29,6 +29,13 @@ class GdnConfig(C.Structure):
                 ("device", C.c_int32)]
 
 
+class GqaConfig(C.Structure):
+    _fields_ = [("hidden_size", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
+                ("head_dim", C.c_int32), ("rotary_dim", C.c_int32), ("gated", C.c_int32), ("rope_theta", C.c_float),
+                ("rms_norm_eps", C.c_float), ("page_size", C.c_int32), ("max_tokens", C.c_int32),
+                ("num_layers", C.c_int32), ("device", C.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/krasis_b200.h declares
 SIGNATURES = {
     "kb2_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -62,6 +69,11 @@ SIGNATURES = {
     "kb2_gdn_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "kb2_gdn_reset_state": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "kb2_gdn_get_state_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "kb2_gqa_create": (C.c_int, [C.POINTER(GqaConfig), C.POINTER(C.c_void_p)]),
+    "kb2_gqa_destroy": (None, [C.c_void_p]),
+    "kb2_gqa_set_weights_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 6),
+    "kb2_gqa_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "kb2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "kb2_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }

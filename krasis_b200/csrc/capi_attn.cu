@@ -20,6 +20,13 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
                             void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
                             float* gcum, float* core, void* normed_out, int M, cudaStream_t s);
+struct GqaDims {
+  int H, nh, nkv, d, rotary_dim, gated;
+  float theta, eps;
+};
+cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_raw, const void* v_raw, const float* q_norm,
+                            const float* k_norm, const int* positions, const int* kv_indices, void* q_rot, void* k_cache,
+                            void* v_cache, void* attn_out, int M, int q_start, int kv_len, cudaStream_t s);
 }  // namespace kb2
 using namespace kb2;
 
@@ -217,6 +224,102 @@ KB2_API int kb2_gdn_forward(kb2_gdn* h, int layer, const void* hidden_dev, void*
   CUDA_TRY(launch_gdn_core(h->d, h->qkvz, h->ba, L.conv_w, L.conv_state, L.A_log, L.dt_bias, L.norm_w, L.rec_state,
                            h->qn, h->kn, h->vc, h->beta, h->g, h->vcorr, h->kcd, h->intra, h->gcum, h->core, h->normed, M, s));
   CUDA_TRY(launch_dense_gemm(h->normed, L.w_out, out_dev, nullptr, M, H, vd, H, false, sms, s));
+  return KB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GQA
+struct GqaLayer {
+  void *wq = nullptr, *wk = nullptr, *wv = nullptr, *wo = nullptr;
+  float *q_norm = nullptr, *k_norm = nullptr;
+  bool loaded = false;
+};
+struct kb2_gqa {
+  kb2_gqa_config cfg{};
+  GqaDims g{};
+  std::vector<GqaLayer> layers;
+  void *q_raw = nullptr, *k_raw = nullptr, *v_raw = nullptr, *q_rot = nullptr, *attn = nullptr;
+};
+
+KB2_API int kb2_gqa_create(const kb2_gqa_config* c, kb2_gqa** out) {
+  if (!c || !out) return failf(KB2_ERR_VALUE, "null argument");
+  if (c->head_dim != 128 && c->head_dim != 256) return failf(KB2_ERR_VALUE, "head_dim must be 128 or 256 (got %d)", c->head_dim);
+  if (c->num_kv_heads < 1 || c->num_heads % c->num_kv_heads) return failf(KB2_ERR_VALUE, "num_heads must be a multiple of num_kv_heads");
+  if (c->rotary_dim < 0 || c->rotary_dim > c->head_dim || c->rotary_dim % 2) return failf(KB2_ERR_VALUE, "bad rotary_dim %d", c->rotary_dim);
+  if (c->hidden_size % 64 || c->page_size != 16) return failf(KB2_ERR_VALUE, "hidden_size %% 64 == 0 and page_size == 16 required");
+  if (c->max_tokens < 1 || c->num_layers < 1) return failf(KB2_ERR_VALUE, "max_tokens and num_layers must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return failf(KB2_ERR_CUDA, "no CUDA device: krasis_b200 has no CPU fallback");
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  kb2_gqa* h = new kb2_gqa();
+  h->cfg = *c;
+  h->g = GqaDims{c->hidden_size, c->num_heads, c->num_kv_heads, c->head_dim, c->rotary_dim, c->gated ? 1 : 0, c->rope_theta, c->rms_norm_eps};
+  h->layers.resize(c->num_layers);
+  const size_t M = c->max_tokens, qd = (size_t)c->num_heads * c->head_dim, kvd = (size_t)c->num_kv_heads * c->head_dim;
+  CUDA_TRY(cudaMalloc(&h->q_raw, M * qd * (c->gated ? 2 : 1) * 2));
+  CUDA_TRY(cudaMalloc(&h->k_raw, M * kvd * 2));
+  CUDA_TRY(cudaMalloc(&h->v_raw, M * kvd * 2));
+  CUDA_TRY(cudaMalloc(&h->q_rot, M * qd * 2));
+  CUDA_TRY(cudaMalloc(&h->attn, M * qd * 2));
+  *out = h;
+  return KB2_OK;
+}
+
+KB2_API void kb2_gqa_destroy(kb2_gqa* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (auto& L : h->layers) { cudaFree(L.wq); cudaFree(L.wk); cudaFree(L.wv); cudaFree(L.wo); cudaFree(L.q_norm); cudaFree(L.k_norm); }
+  cudaFree(h->q_raw); cudaFree(h->k_raw); cudaFree(h->v_raw); cudaFree(h->q_rot); cudaFree(h->attn);
+  delete h;
+}
+
+KB2_API int kb2_gqa_set_weights_host(kb2_gqa* h, int layer, const void* q_proj, const void* k_proj, const void* v_proj,
+                                     const void* o_proj, const void* q_norm, const void* k_norm) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  if (layer < 0 || layer >= (int)h->layers.size()) return failf(KB2_ERR_VALUE, "layer %d out of range", layer);
+  if (!q_proj || !k_proj || !v_proj || !o_proj) return failf(KB2_ERR_VALUE, "null weight pointer");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const auto& c = h->cfg;
+  const size_t qd = (size_t)c.num_heads * c.head_dim, kvd = (size_t)c.num_kv_heads * c.head_dim, H = c.hidden_size;
+  GqaLayer& L = h->layers[layer];
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!*dst) { cudaError_t e = cudaMalloc(dst, bytes); if (e != cudaSuccess) return e; }
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  CUDA_TRY(up(&L.wq, q_proj, qd * (c.gated ? 2 : 1) * H * 2));
+  CUDA_TRY(up(&L.wk, k_proj, kvd * H * 2));
+  CUDA_TRY(up(&L.wv, v_proj, kvd * H * 2));
+  CUDA_TRY(up(&L.wo, o_proj, H * qd * 2));
+  if (q_norm) { auto v = bf16_to_f32_host(q_norm, c.head_dim); CUDA_TRY(up((void**)&L.q_norm, v.data(), v.size() * 4)); }
+  if (k_norm) { auto v = bf16_to_f32_host(k_norm, c.head_dim); CUDA_TRY(up((void**)&L.k_norm, v.data(), v.size() * 4)); }
+  L.loaded = true;
+  return KB2_OK;
+}
+
+KB2_API int kb2_gqa_forward(kb2_gqa* h, int layer, const void* hidden_dev, const int32_t* positions_dev, int32_t first_position,
+                            void* k_cache_layer_dev, void* v_cache_layer_dev, const int32_t* kv_indices_dev,
+                            int32_t kv_len_after, void* out_dev, int32_t M, void* stream) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  if (layer < 0 || layer >= (int)h->layers.size()) return failf(KB2_ERR_VALUE, "layer %d out of range", layer);
+  GqaLayer& L = h->layers[layer];
+  if (M < 0 || M > h->cfg.max_tokens) return failf(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, h->cfg.max_tokens);
+  if (!L.loaded) return failf(KB2_ERR_STATE, "GQA weights not set for layer %d", layer);
+  if (M == 0) return KB2_OK;
+  if (!hidden_dev || !positions_dev || !k_cache_layer_dev || !v_cache_layer_dev || !kv_indices_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (first_position < 0 || kv_len_after != first_position + M) return failf(KB2_ERR_VALUE, "positions must be contiguous: kv_len_after (%d) != first_position (%d) + M (%d)", kv_len_after, first_position, M);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const auto& c = h->cfg;
+  const int qd = c.num_heads * c.head_dim, kvd = c.num_kv_heads * c.head_dim, H = c.hidden_size, sms = device_sms(c.device);
+  const int qw = qd * (c.gated ? 2 : 1);
+  CUDA_TRY(launch_dense_gemm(hidden_dev, L.wq, h->q_raw, nullptr, M, qw, H, qw, false, sms, s));
+  CUDA_TRY(launch_dense_gemm(hidden_dev, L.wk, h->k_raw, nullptr, M, kvd, H, kvd, false, sms, s));
+  CUDA_TRY(launch_dense_gemm(hidden_dev, L.wv, h->v_raw, nullptr, M, kvd, H, kvd, false, sms, s));
+  CUDA_TRY(launch_gqa_core(h->g, h->q_raw, h->k_raw, h->v_raw, L.q_norm, L.k_norm, positions_dev, kv_indices_dev, h->q_rot,
+                           k_cache_layer_dev, v_cache_layer_dev, h->attn, M, first_position, kv_len_after, s));
+  CUDA_TRY(launch_dense_gemm(h->attn, L.wo, out_dev, nullptr, M, H, qd, H, false, sms, s));
   return KB2_OK;
 }
 

@@ -1,0 +1,458 @@
+// GQA prefill attention for sm_100a: per-head RMSNorm + partial RoPE + FP8 paged-KV append, then a causal
+// flash-attention kernel on tcgen05 (QK^T and PV on tensor cores, S/P/O in tensor memory).
+//
+// Restates python/krasis/attention.py:496-687 (GQAAttention.forward):
+//   gqa_prep_kernel   split [q | gate] per head (:531-535), flashinfer.norm.rmsnorm per head (:555-559),
+//                     half-split partial RoPE with BF16 tables and BF16 arithmetic (:443-494), K/V cast to the cache
+//                     dtype (FP8 E4M3, unscaled) and append to the paged cache, page = 16 tokens, NHD (:582-590, kv_cache.py)
+//   gqa_fmha_kernel   BatchPrefillWithPagedKVCacheWrapper.run: causal softmax(q k^T / sqrt(d)) v over the paged FP8
+//                     cache (:596-642), then attn * sigmoid(gate) (:665-666)
+// The q/k/v/o projections are dense_gemm_kernel.
+//
+// FMHA layout: one CTA = 128 query rows of one head; KV tiles of 64 keys.  12 warps:
+//   warps 0-3  KV loaders: FP8 pages -> BF16 -> 128B-swizzled smem (K as K-major B operand, V as MN-major B operand)
+//   warp  4    tcgen05.mma issuer: S = Q K^T (SS), O += P V (P from TMEM)
+//   warp  5    Q loader (2-D TMA)
+//   warps 8-11 softmax: S (TMEM) -> exp2 -> P (BF16, TMEM); running max with lazy rescale of O in TMEM; epilogue
+// TMEM: S [0,64) | P [64,96) | O [128,128+D).
+#include <cuda.h>
+#include <cuda_fp8.h>
+
+#include "moe_common.cuh"
+#include "ptx.cuh"
+
+namespace kb2 {
+
+struct GqaDims {
+  int H, nh, nkv, d, rotary_dim, gated;
+  float theta, eps;
+};
+
+__device__ __forceinline__ float bf16r_(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------
+// prep: one CTA per token, one warp per head (q heads then k heads then v heads)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gqa_prep_kernel(GqaDims g, const __nv_bfloat16* __restrict__ q_raw,   // [M][nh*d*(1+gated)]
+                                                       const __nv_bfloat16* __restrict__ k_raw,             // [M][nkv*d]
+                                                       const __nv_bfloat16* __restrict__ v_raw,
+                                                       const float* __restrict__ q_norm, const float* __restrict__ k_norm,
+                                                       const int* __restrict__ positions, const int* __restrict__ kv_indices,
+                                                       __nv_bfloat16* __restrict__ q_out,                    // [M][nh*d]
+                                                       uint8_t* __restrict__ k_cache, uint8_t* __restrict__ v_cache,  // [P][16][nkv][d] fp8
+                                                       int M) {
+  const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int d = g.d, d2 = g.rotary_dim / 2;
+  const int pos = positions[t];
+  const long long slot = ((long long)kv_indices[pos >> 4] * 16 + (pos & 15)) * g.nkv;
+  extern __shared__ float sx[];              // [nw][d]
+  float* x = sx + warp * d;
+  for (int hh = warp; hh < g.nh + 2 * g.nkv; hh += nw) {
+    const bool is_q = hh < g.nh, is_k = !is_q && hh < g.nh + g.nkv;
+    const int h = is_q ? hh : (is_k ? hh - g.nh : hh - g.nh - g.nkv);
+    const __nv_bfloat16* src = is_q ? q_raw + (long long)t * g.nh * d * (1 + g.gated) + (long long)h * d * (1 + g.gated)
+                                    : (is_k ? k_raw : v_raw) + (long long)t * g.nkv * d + (long long)h * d;
+    float ss = 0.f;
+    for (int i = lane; i < d; i += 32) {
+      const float v = __bfloat162float(src[i]);
+      x[i] = v;
+      ss += v * v;
+    }
+    if (!is_q && !is_k) {                    // V: plain cast to FP8
+      __syncwarp();
+      for (int i = lane; i < d; i += 32)
+        v_cache[(slot + h) * d + i] = (uint8_t)__nv_cvt_float_to_fp8(x[i], __NV_SATFINITE, __NV_E4M3);
+      __syncwarp();
+      continue;
+    }
+    const float* nwt = is_q ? q_norm : k_norm;
+    if (nwt) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = rsqrtf(ss / d + g.eps);
+      __syncwarp();
+      for (int i = lane; i < d; i += 32) x[i] = bf16r_(x[i] * inv * nwt[i]);
+    }
+    __syncwarp();
+    // RoPE on the first rotary_dim dims: (x1, x2) = (x[i], x[i + d2]); BF16 tables, every product / sum rounded to BF16
+    for (int i = lane; i < d2; i += 32) {
+      const float freq = 1.0f / powf(g.theta, (float)(2 * i) / (float)g.rotary_dim);
+      const float ang = (float)pos * freq;
+      const float c = bf16r_(cosf(ang)), s = bf16r_(sinf(ang));
+      const float x1 = x[i], x2 = x[i + d2];
+      const float r1 = bf16r_(bf16r_(x1 * c) - bf16r_(x2 * s));
+      const float r2 = bf16r_(bf16r_(x2 * c) + bf16r_(x1 * s));
+      x[i] = r1;
+      x[i + d2] = r2;
+    }
+    __syncwarp();
+    if (is_q) {
+      for (int i = lane; i < d; i += 32) q_out[(long long)t * g.nh * d + (long long)h * d + i] = __float2bfloat16_rn(x[i]);
+    } else {
+      for (int i = lane; i < d; i += 32)
+        k_cache[(slot + h) * d + i] = (uint8_t)__nv_cvt_float_to_fp8(x[i], __NV_SATFINITE, __NV_E4M3);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FMHA
+// ------------------------------------------------------------------------------------------------
+constexpr int kFQ = 128;        // query rows per CTA
+constexpr int kFK = 64;         // keys per KV tile
+constexpr int kFThreads = 384;
+constexpr int kFStages = 2;
+
+template <int D>
+struct FmhaSmem {
+  static constexpr int kQBytes = kFQ * D * 2;
+  static constexpr int kKBytes = kFK * D * 2;
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = kOffQ + kQBytes;
+  static constexpr int kOffV = kOffK + kFStages * kKBytes;
+  static constexpr int kOffBar = kOffV + kFStages * kKBytes;
+  static constexpr int kTotal = kOffBar + 128;
+  static_assert(kTotal <= 227 * 1024, "smem");
+};
+
+__device__ __forceinline__ uint32_t umma_idesc_bf16_m128_bmn(uint32_t n) {   // B operand MN-major
+  return umma_idesc_bf16_m128(n) | (1u << 16);
+}
+// MN-major, SWIZZLE_128B: 64-element (128 B) rows along MN, 8 K-rows per 1024 B atom; LBO = stride between
+// 64-wide MN chunks, SBO = stride between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t dsc = 0;
+  dsc |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  dsc |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  dsc |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  dsc |= static_cast<uint64_t>(1) << 46;
+  dsc |= static_cast<uint64_t>(2) << 61;
+  return dsc;
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(kFThreads, 1)
+    gqa_fmha_kernel(const __grid_constant__ CUtensorMap tmap_q, GqaDims g, const uint8_t* __restrict__ k_cache,
+                    const uint8_t* __restrict__ v_cache, const int* __restrict__ kv_indices,
+                    const __nv_bfloat16* __restrict__ q_raw,     // for the output gate
+                    __nv_bfloat16* __restrict__ out,             // [M][nh*D]
+                    int M, int q_start, int kv_len, float sm_scale_log2) {
+  using L = FmhaSmem<D>;
+  constexpr int NC = D / 64;                       // 64-wide d chunks
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;      // [2]
+  uint64_t* kv_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_cons = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;       // heavy (late) query tiles first
+  const int head = blockIdx.y, kvh = head / (g.nh / g.nkv);
+  const int q0 = qt * kFQ;
+  // keys visible to this tile: positions <= q_start + min(q0 + 127, M - 1)
+  const int last_q = min(q0 + kFQ - 1, M - 1);
+  const int n_keys = min(kv_len, q_start + last_q + 1);
+  const int n_tiles = (n_keys + kFK - 1) / kFK;
+
+  if (threadIdx.x == 128) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 128);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_cons, 128);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kColS = 0, kColP = 64, kColO = 128;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ KV loaders
+    const int tid = threadIdx.x;           // 0..127
+    const int j = tid >> 1, half = tid & 1;    // key within tile, which half of the head dim
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_tiles; ++it) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      const int key = it * kFK + j;
+      const bool valid = key < kv_len;
+      const long long row = valid ? (((long long)kv_indices[key >> 4] * 16 + (key & 15)) * g.nkv + kvh) * D : 0;
+      uint8_t* ks = smem + L::kOffK + stage * L::kKBytes;
+      uint8_t* vs = smem + L::kOffV + stage * L::kKBytes;
+      const uint32_t rowoff = (j >> 3) * 1024 + (j & 7) * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < D / 32; ++c16) {          // 16 fp8 per step within this thread's half
+        const int dd = half * (D / 2) + c16 * 16;        // first head-dim index of this step
+        uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
+        if (valid) {
+          kq = *reinterpret_cast<const uint4*>(k_cache + row + dd);
+          vq = *reinterpret_cast<const uint4*>(v_cache + row + dd);
+        }
+        const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
+        uint32_t ko[8], vo[8];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            const __half2_raw hk = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((kw[w] >> (16 * hp)) & 0xFFFF), __NV_E4M3);
+            const __half2_raw hv = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((vw[w] >> (16 * hp)) & 0xFFFF), __NV_E4M3);
+            const float2 fk = __half22float2(*reinterpret_cast<const __half2*>(&hk));
+            const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&hv));
+            __nv_bfloat162 bk = __floats2bfloat162_rn(fk.x, fk.y), bv = __floats2bfloat162_rn(fv.x, fv.y);
+            ko[w * 2 + hp] = *reinterpret_cast<uint32_t*>(&bk);
+            vo[w * 2 + hp] = *reinterpret_cast<uint32_t*>(&bv);
+          }
+        }
+        // 16 bf16 = two 16-byte pieces p, p+1 of d-chunk c
+        const int c = dd / 64, p = (dd % 64) / 8;
+        uint8_t* kd = ks + c * (kFK * 128) + rowoff;
+        uint8_t* vd = vs + c * (kFK * 128) + rowoff;
+        *reinterpret_cast<uint4*>(kd + (((p) ^ (j & 7)) << 4)) = make_uint4(ko[0], ko[1], ko[2], ko[3]);
+        *reinterpret_cast<uint4*>(kd + (((p + 1) ^ (j & 7)) << 4)) = make_uint4(ko[4], ko[5], ko[6], ko[7]);
+        *reinterpret_cast<uint4*>(vd + (((p) ^ (j & 7)) << 4)) = make_uint4(vo[0], vo[1], vo[2], vo[3]);
+        *reinterpret_cast<uint4*>(vd + (((p + 1) ^ (j & 7)) << 4)) = make_uint4(vo[4], vo[5], vo[6], vo[7]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&kv_full[stage]);
+      if (++stage == kFStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0 && n_tiles > 0) {
+      const uint32_t id_s = umma_idesc_bf16_m128(kFK);
+      const uint32_t id_o = umma_idesc_bf16_m128_bmn(D);
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0, sc_phase = 0, pf_phase = 0;
+      const uint32_t q_addr = smem_u32(smem + L::kOffQ);
+      auto issue_pv = [&](int st, bool first) {
+        const uint32_t v_addr = smem_u32(smem + L::kOffV + st * L::kKBytes);
+#pragma unroll
+        for (int k = 0; k < kFK / 16; ++k) {
+          const uint64_t bd = umma_desc_mn_sw128(v_addr + k * 2048, kFK * 128, 1024);
+          umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + 8 * k, bd, id_o, (first && k == 0) ? 0u : 1u);
+        }
+      };
+      int prev_stage = 0;
+      for (int it = 0; it < n_tiles; ++it) {
+        mbar_wait(&kv_full[stage], phase);
+        if (it > 0) {
+          mbar_wait(s_cons, sc_phase);
+          sc_phase ^= 1;
+        }
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(smem + L::kOffK + stage * L::kKBytes);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint64_t ad = umma_desc_k_sw128(q_addr + c * (kFQ * 128));
+          const uint64_t bd = umma_desc_k_sw128(k_addr + c * (kFK * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS, ad + 2 * k, bd + 2 * k, id_s, (c > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        if (it > 0) {
+          mbar_wait(p_full, pf_phase);
+          pf_phase ^= 1;
+          tc_fence_after_sync();
+          issue_pv(prev_stage, it == 1);
+          umma_commit(pv_done);
+          umma_commit(&kv_empty[prev_stage]);
+        }
+        prev_stage = stage;
+        if (++stage == kFStages) { stage = 0; phase ^= 1; }
+      }
+      mbar_wait(p_full, pf_phase);
+      tc_fence_after_sync();
+      issue_pv(prev_stage, n_tiles == 1);
+      umma_commit(pv_done);
+      umma_commit(&kv_empty[prev_stage]);
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0 && n_tiles > 0) {
+      mbar_arrive_expect_tx(q_full, L::kQBytes);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        tma_load_2d(smem + L::kOffQ + c * (kFQ * 128), &tmap_q, head * D + c * 64, q0, q_full);
+    }
+    __syncwarp();
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------ softmax + epilogue (thread = query row)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int qi = q0 + row;                       // query index within this call
+    const int q_pos = q_start + qi;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m_ref = -INFINITY, l_sum = 0.f;
+    uint32_t sf_phase = 0, pv_phase = 0;
+    for (int it = 0; it < n_tiles; ++it) {
+      mbar_wait(s_full, sf_phase);
+      sf_phase ^= 1;
+      tc_fence_after_sync();
+      float s[kFK];
+#pragma unroll
+      for (int c0 = 0; c0 < kFK; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + kColS + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) s[c0 + jj] = __uint_as_float(r[jj]) * sm_scale_log2;
+      }
+      tc_fence_before_sync();
+      mbar_arrive(s_cons);                         // S may be overwritten by the next QK^T
+      const int key0 = it * kFK;
+      float m_tile = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < kFK; ++jj) {
+        if (key0 + jj > q_pos || key0 + jj >= kv_len) s[jj] = -INFINITY;
+        m_tile = fmaxf(m_tile, s[jj]);
+      }
+      // lazy rescale: keep the reference max until the true max exceeds it by 8 (p stays <= 2^8)
+      float scale_o = 1.f;
+      bool rescale = false;
+      if (m_tile > m_ref + 8.f || m_ref == -INFINITY) {
+        const float m_new = fmaxf(m_tile, m_ref);
+        if (m_new != -INFINITY) {
+          scale_o = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+          rescale = (m_ref != -INFINITY);
+          m_ref = m_new;
+        }
+      }
+      float psum = 0.f;
+      uint32_t pk[kFK / 2];
+#pragma unroll
+      for (int jj = 0; jj < kFK; jj += 2) {
+        const float p0 = (m_ref == -INFINITY) ? 0.f : exp2f(s[jj] - m_ref);
+        const float p1 = (m_ref == -INFINITY) ? 0.f : exp2f(s[jj + 1] - m_ref);
+        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+        psum += __low2float(pb) + __high2float(pb);     // normalise with the values the MMA actually uses
+        pk[jj / 2] = *reinterpret_cast<uint32_t*>(&pb);
+      }
+      l_sum = l_sum * scale_o + psum;
+      if (it > 0) {                                // O of the previous tile must be complete before we touch it / before PV(it)
+        mbar_wait(pv_done, pv_phase);
+        pv_phase ^= 1;
+        tc_fence_after_sync();
+      }
+      if (rescale) {
+#pragma unroll 2
+        for (int c0 = 0; c0 < D; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + kColO + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) r[jj] = __float_as_uint(__uint_as_float(r[jj]) * scale_o);
+          tmem_st16(lane_addr + kColO + c0, r);
+        }
+      }
+      {
+        uint32_t a[16], b[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          a[jj] = pk[jj];
+          b[jj] = pk[16 + jj];
+        }
+        tmem_st16(lane_addr + kColP, a);
+        tmem_st16(lane_addr + kColP + 16, b);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(p_full);
+    }
+    if (n_tiles > 0) {
+      mbar_wait(pv_done, pv_phase);
+      tc_fence_after_sync();
+      const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
+      const bool live = qi < M;
+      const long long obase = (long long)qi * g.nh * D + (long long)head * D;
+      const long long gbase = (long long)qi * g.nh * D * 2 + (long long)head * 2 * D + D;   // gate half of q_raw
+#pragma unroll 2
+      for (int c0 = 0; c0 < D; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + kColO + c0, r);
+        tmem_ld_wait();
+        if (live) {
+          uint32_t o[8];
+          uint4 gq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (g.gated) {
+            gq[0] = *reinterpret_cast<const uint4*>(q_raw + gbase + c0);
+            gq[1] = *reinterpret_cast<const uint4*>(q_raw + gbase + c0 + 8);
+          }
+          const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(gq);
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            float a0 = bf16r_(__uint_as_float(r[jj]) * inv_l), a1 = bf16r_(__uint_as_float(r[jj + 1]) * inv_l);
+            if (g.gated) {
+              a0 *= bf16r_(1.0f / (1.0f + expf(-__bfloat162float(gp[jj]))));
+              a1 *= bf16r_(1.0f / (1.0f + expf(-__bfloat162float(gp[jj + 1]))));
+            }
+            __nv_bfloat162 ob = __floats2bfloat162_rn(a0, a1);
+            o[jj / 2] = *reinterpret_cast<uint32_t*>(&ob);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + obase + c0);
+          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
+
+cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_raw, const void* v_raw, const float* q_norm,
+                            const float* k_norm, const int* positions, const int* kv_indices, void* q_rot, void* k_cache,
+                            void* v_cache, void* attn_out, int M, int q_start, int kv_len, cudaStream_t s) {
+  if (g.d != 128 && g.d != 256) return cudaErrorInvalidValue;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gqa_fmha_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<128>::kTotal);
+    cudaFuncSetAttribute(gqa_fmha_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<256>::kTotal);
+    configured = true;
+  }
+  gqa_prep_kernel<<<M, 256, 8 * g.d * sizeof(float), s>>>(g, (const __nv_bfloat16*)q_raw, (const __nv_bfloat16*)k_raw,
+                                                          (const __nv_bfloat16*)v_raw, q_norm, k_norm, positions,
+                                                          kv_indices, (__nv_bfloat16*)q_rot, (uint8_t*)k_cache,
+                                                          (uint8_t*)v_cache, M);
+  alignas(64) CUtensorMap tq;
+  cudaError_t e = make_tmap_bf16_rows(&tq, q_rot, M, (long long)g.nh * g.d, kFQ);
+  if (e != cudaSuccess) return e;
+  const float sl2 = (1.0f / sqrtf((float)g.d)) * 1.4426950408889634f;
+  dim3 grid((M + kFQ - 1) / kFQ, g.nh);
+  if (g.d == 256)
+    gqa_fmha_kernel<256><<<grid, kFThreads, FmhaSmem<256>::kTotal, s>>>(tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache,
+                                                                    kv_indices, (const __nv_bfloat16*)q_raw,
+                                                                    (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2);
+  else
+    gqa_fmha_kernel<128><<<grid, kFThreads, FmhaSmem<128>::kTotal, s>>>(tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache,
+                                                                    kv_indices, (const __nv_bfloat16*)q_raw,
+                                                                    (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2);
+  return cudaGetLastError();
+}
+
+}  // namespace kb2
