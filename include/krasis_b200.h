@@ -169,6 +169,24 @@ KB2_API int64_t kb2_launch_count(const kb2_engine* e);
 KB2_API int kb2_linear_bf16(const void* x_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t M,
                             int32_t N, int32_t K, int32_t out_f32, int32_t device, void* stream);
 
+/* flashinfer.norm.rmsnorm (residual_dev == NULL) / fused_add_rmsnorm (residual_dev != NULL: residual += x, in place)
+ * as used at python/krasis/layer.py:163-183,283-308.  x, residual, out: [M][H] bf16 (out may alias x); weight [H] f32. */
+KB2_API int kb2_rmsnorm(void* x_dev, void* residual_dev, const float* weight_dev, void* out_dev, int32_t M, int32_t H,
+                        float eps, int32_t device, void* stream);
+/* Per-row symmetric INT8 quantisation: quantize_to_int8 for weights (python/krasis/weight_loader.py:25-43, bf16 scale
+ * out) and the activation half of int8_linear (:66-70, f32 scale out). */
+KB2_API int kb2_quantize_rows_int8(const void* x_dev, void* q_dev, float* scale_f32_dev, void* scale_bf16_dev, int32_t rows,
+                                   int32_t K, int32_t device, void* stream);
+/* int8_linear (python/krasis/weight_loader.py:46-99): W8A8, exact INT32 accumulation on tcgen05 kind::i8, then
+ * bf16(float(acc) * (x_scale * w_scale)).  Scratch: xq [M][K] int8, xs [M] f32. */
+KB2_API int kb2_int8_linear(const void* x_dev, const void* wq_dev, const void* w_scale_bf16_dev, void* out_dev, void* xq_scratch_dev,
+                            float* xs_scratch_dev, int32_t M, int32_t N, int32_t K, int32_t device, void* stream);
+/* flashinfer.activation.silu_and_mul (layer.py:512): x [rows][2N] -> out [rows][N] bf16. */
+KB2_API int kb2_silu_and_mul(const void* x_dev, void* out_dev, int32_t rows, int32_t N, int32_t device, void* stream);
+/* Qwen3-Next shared-expert gate (layer.py:518-522): y[m][:] *= sigmoid(hidden[m] . gate_w), y [M][N], gate_w [H] bf16. */
+KB2_API int kb2_sigmoid_gate_mul(const void* hidden_dev, const void* gate_w_dev, void* y_dev, int32_t M, int32_t H, int32_t N,
+                                 int32_t device, void* stream);
+
 /* Gated DeltaNet linear attention — python/krasis/linear_attention.py:GatedDeltaNetAttention (prefill path
  * `_forward_chunked`, :695-844).  One handle holds the weights and the per-layer conv / recurrent state the
  * reference keeps on the object (:180-205); kb2_gdn_forward == forward(hidden, is_decode=False) for M tokens and

@@ -20,6 +20,12 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
                             void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
                             float* gcum, float* core, void* normed_out, int M, cudaStream_t s);
+cudaError_t launch_dense_gemm_i8(const void* xq, const float* x_scale, const void* wq, const void* w_scale, void* out,
+                                 int M, int N, int K, long long ldo, int num_sms, cudaStream_t s);
+cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, int M, int H, float eps, cudaStream_t s);
+cudaError_t launch_quant_rows_int8(const void* x, void* q, float* scale_f32, void* scale_bf16, int rows, int K, cudaStream_t s);
+cudaError_t launch_silu_and_mul(const void* x, void* out, int rows, int N, cudaStream_t s);
+cudaError_t launch_sigmoid_gate_mul(const void* h, const void* w, void* y, int M, int H, int N, cudaStream_t s);
 struct GqaDims {
   int H, nh, nkv, d, rotary_dim, gated;
   float theta, eps;
@@ -89,6 +95,52 @@ KB2_API int kb2_linear_bf16(const void* x_dev, const void* w_dev, const float* b
   if (M <= 0 || N <= 0 || K <= 0 || K % 64 || N % 16) return failf(KB2_ERR_VALUE, "linear: need M>0, K %% 64 == 0, N %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(launch_dense_gemm(x_dev, w_dev, out_dev, bias_dev, M, N, K, N, out_f32 != 0, device_sms(device), (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_rmsnorm(void* x_dev, void* residual_dev, const float* weight_dev, void* out_dev, int32_t M, int32_t H,
+                        float eps, int32_t device, void* stream) {
+  if (!x_dev || !weight_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (M <= 0 || H <= 0 || H % 8) return failf(KB2_ERR_VALUE, "rmsnorm: need M > 0 and H %% 8 == 0");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_rmsnorm(x_dev, residual_dev, weight_dev, out_dev, M, H, eps, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_quantize_rows_int8(const void* x_dev, void* q_dev, float* scale_f32_dev, void* scale_bf16_dev, int32_t rows,
+                                   int32_t K, int32_t device, void* stream) {
+  if (!x_dev || !q_dev || (!scale_f32_dev && !scale_bf16_dev)) return failf(KB2_ERR_VALUE, "null argument");
+  if (rows <= 0 || K <= 0) return failf(KB2_ERR_VALUE, "quantize: rows and K must be positive");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_quant_rows_int8(x_dev, q_dev, scale_f32_dev, scale_bf16_dev, rows, K, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_int8_linear(const void* x_dev, const void* wq_dev, const void* w_scale_bf16_dev, void* out_dev, void* xq_scratch_dev,
+                            float* xs_scratch_dev, int32_t M, int32_t N, int32_t K, int32_t device, void* stream) {
+  if (!x_dev || !wq_dev || !w_scale_bf16_dev || !out_dev || !xq_scratch_dev || !xs_scratch_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (M <= 0 || K % 128 || N % 16) return failf(KB2_ERR_VALUE, "int8_linear: need M > 0, K %% 128 == 0, N %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(launch_quant_rows_int8(x_dev, xq_scratch_dev, xs_scratch_dev, nullptr, M, K, s));
+  CUDA_TRY(launch_dense_gemm_i8(xq_scratch_dev, xs_scratch_dev, wq_dev, w_scale_bf16_dev, out_dev, M, N, K, N, device_sms(device), s));
+  return KB2_OK;
+}
+
+KB2_API int kb2_silu_and_mul(const void* x_dev, void* out_dev, int32_t rows, int32_t N, int32_t device, void* stream) {
+  if (!x_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (rows <= 0 || N % 8) return failf(KB2_ERR_VALUE, "silu_and_mul: need rows > 0 and N %% 8 == 0");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_silu_and_mul(x_dev, out_dev, rows, N, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_sigmoid_gate_mul(const void* hidden_dev, const void* gate_w_dev, void* y_dev, int32_t M, int32_t H, int32_t N,
+                                 int32_t device, void* stream) {
+  if (!hidden_dev || !gate_w_dev || !y_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (M <= 0) return failf(KB2_ERR_VALUE, "sigmoid_gate_mul: M must be positive");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_sigmoid_gate_mul(hidden_dev, gate_w_dev, y_dev, M, H, N, (cudaStream_t)stream));
   return KB2_OK;
 }
 

@@ -22,10 +22,15 @@ constexpr int kDStage = kDABytes + kDBBytes;
 constexpr int kDOffBar = kDStages * kDStage;
 constexpr int kDSmem = kDOffBar + 128;
 
-template <bool kOutF32>
+// MODE 0: bf16 x bf16 -> bf16   1: bf16 x bf16 -> f32   2: int8 x int8 -> int32 -> bf16( float(acc) * (xs[m] * ws[n]) )
+// (W8A8 `int8_linear`, python/krasis/weight_loader.py:46-99: exact integer accumulation, fp32 dequant).
+template <int MODE>
 __global__ void __launch_bounds__(kDThreads, 1)
     dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      void* __restrict__ out, const float* __restrict__ bias, int M, int N, int K, long long ldo) {
+                      void* __restrict__ out, const float* __restrict__ bias, int M, int N, int K, long long ldo,
+                      const float* __restrict__ row_scale, const __nv_bfloat16* __restrict__ col_scale) {
+  constexpr bool kOutF32 = MODE == 1;
+  constexpr int kElemsPerBlock = MODE == 2 ? 128 : 64;     // 128 B of K per smem row
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDOffBar);
   uint64_t* empty = full + kDStages;
@@ -35,7 +40,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (N + kDTileN - 1) / kDTileN, m_tiles = (M + kDTileM - 1) / kDTileM;
   const int total = n_tiles * m_tiles;
-  const int nkb = K / kBlockK;
+  const int nkb = K / kElemsPerBlock;
 
   if (threadIdx.x == 32) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -69,9 +74,9 @@ __global__ void __launch_bounds__(kDThreads, 1)
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = smem + stage * kDStage;
           mbar_arrive_expect_tx(&full[stage], kDStage);
-          tma_load_2d(a, &tmap_x, kb * kBlockK, m0, &full[stage]);
-          tma_load_2d(a + kDABytes, &tmap_w, kb * kBlockK, n0, &full[stage]);               // rows n0..n0+127
-          tma_load_2d(a + kDABytes + kDABytes, &tmap_w, kb * kBlockK, n0 + 128, &full[stage]); // rows n0+128..+255
+          tma_load_2d(a, &tmap_x, kb * kElemsPerBlock, m0, &full[stage]);
+          tma_load_2d(a + kDABytes, &tmap_w, kb * kElemsPerBlock, n0, &full[stage]);               // rows n0..n0+127
+          tma_load_2d(a + kDABytes + kDABytes, &tmap_w, kb * kElemsPerBlock, n0 + 128, &full[stage]); // rows n0+128..+255
           if (++stage == kDStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -82,7 +87,9 @@ __global__ void __launch_bounds__(kDThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       uint32_t aphase[2] = {0, 0};
-      const uint32_t idesc = umma_idesc_bf16_m128(kDTileN);
+      // kind::i8: c_format S32 (2) at [4,6), a/b format INT8 (1) at [7,10)/[10,13)
+      const uint32_t idesc = MODE == 2 ? ((2u << 4) | (1u << 7) | (1u << 10) | ((kDTileN >> 3) << 17) | ((128u >> 4) << 24))
+                                       : umma_idesc_bf16_m128(kDTileN);
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int b = it & 1;
@@ -96,8 +103,12 @@ __global__ void __launch_bounds__(kDThreads, 1)
           const uint64_t ad = umma_desc_k_sw128(a_addr);
           const uint64_t bd = umma_desc_k_sw128(a_addr + kDABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {          // 4 x 32 B of K per 128 B row (K=16 bf16 or K=32 int8 per MMA)
+            if constexpr (MODE == 2)
+              umma_i8(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&empty[stage]);
           if (++stage == kDStages) { stage = 0; phase ^= 1; }
         }
@@ -124,8 +135,14 @@ __global__ void __launch_bounds__(kDThreads, 1)
         const int n = n0 + c0;
         if (m < M && n < N) {          // N % 16 == 0 is required by the launcher
           float v[16];
+          if constexpr (MODE == 2) {
+            const float xs = row_scale[m];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (bias ? bias[n + j] : 0.f);
+            for (int j = 0; j < 16; ++j) v[j] = (float)(int)r[j] * (xs * __bfloat162float(col_scale[n + j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (bias ? bias[n + j] : 0.f);
+          }
           if constexpr (kOutF32) {
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)m * ldo + n);
 #pragma unroll
@@ -153,6 +170,20 @@ __global__ void __launch_bounds__(kDThreads, 1)
 }
 
 cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
+cudaError_t make_tmap_u8_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
+
+static cudaError_t dense_configure() {
+  static bool configured = false;
+  if (configured) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(dense_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dense_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(dense_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
+  if (e != cudaSuccess) return e;
+  configured = true;
+  return cudaSuccess;
+}
 
 // X [M][K] bf16 row-major, W [N][K] bf16 row-major, out [M][ldo] (bf16 or f32).  K % 64 == 0, N % 16 == 0.
 cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
@@ -163,20 +194,32 @@ cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const flo
   if (e != cudaSuccess) return e;
   e = make_tmap_bf16_rows(&tw, w, N, K, 128);
   if (e != cudaSuccess) return e;
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(dense_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dense_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  e = dense_configure();
+  if (e != cudaSuccess) return e;
   const int total = ((M + kDTileM - 1) / kDTileM) * ((N + kDTileN - 1) / kDTileN);
   const int grid = total < num_sms ? total : num_sms;
   if (out_f32)
-    dense_gemm_kernel<true><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo);
+    dense_gemm_kernel<1><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo, nullptr, nullptr);
   else
-    dense_gemm_kernel<false><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo);
+    dense_gemm_kernel<0><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo, nullptr, nullptr);
+  return cudaGetLastError();
+}
+
+// W8A8: xq [M][K] int8, x_scale [M] f32, wq [N][K] int8, w_scale [N] bf16 -> out [M][ldo] bf16.  K % 128 == 0, N % 16 == 0.
+cudaError_t launch_dense_gemm_i8(const void* xq, const float* x_scale, const void* wq, const void* w_scale, void* out,
+                                 int M, int N, int K, long long ldo, int num_sms, cudaStream_t s) {
+  if (K % 128 || N % 16 || M <= 0) return cudaErrorInvalidValue;
+  alignas(64) CUtensorMap tx, tw;
+  cudaError_t e = make_tmap_u8_rows(&tx, xq, M, K, 128);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_u8_rows(&tw, wq, N, K, 128);
+  if (e != cudaSuccess) return e;
+  e = dense_configure();
+  if (e != cudaSuccess) return e;
+  const int total = ((M + kDTileM - 1) / kDTileM) * ((N + kDTileN - 1) / kDTileN);
+  const int grid = total < num_sms ? total : num_sms;
+  dense_gemm_kernel<2><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, nullptr, M, N, K, ldo, x_scale,
+                                                      (const __nv_bfloat16*)w_scale);
   return cudaGetLastError();
 }
 

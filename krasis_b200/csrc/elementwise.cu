@@ -1,0 +1,160 @@
+// Row-wise HBM-bound kernels around the GEMMs: RMSNorm, fused residual-add + RMSNorm, per-row INT8 quantisation,
+// SiLU*mul, sigmoid-gated scaling.
+//   rmsnorm / fused_add_rmsnorm   flashinfer.norm.{rmsnorm,fused_add_rmsnorm} as used at python/krasis/layer.py:163-183,
+//                                 283-308 (x = input + residual in fp32; residual <- bf16(x); out <- bf16(x * rsqrt(mean x^2 + eps) * w))
+//   quant_rows_int8               python/krasis/weight_loader.py:25-43 (weights) and :66-70 (activations):
+//                                 scale = clamp(amax, 1e-10) / 127 (fp32); q = clamp(round_half_even(x / scale), -128, 127)
+//   silu_and_mul                  flashinfer.activation.silu_and_mul (layer.py:512): bf16(silu(x[:N]) * x[N:]) in fp32
+//   sigmoid_gate_mul              layer.py:518-522: out *= sigmoid(F.linear(hidden, w[1,H])) with BF16 rounding at every tensor op
+#include "moe_common.cuh"
+
+namespace kb2 {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t = fmaxf(t, red[i]);
+  __syncthreads();
+  return t;
+}
+
+// one CTA per row; H % 8 == 0; each thread owns 8-element vectors
+template <bool kAdd>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
+                                                      const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                      int H, float eps) {
+  __shared__ float red[8];
+  extern __shared__ float xs[];    // [H] fp32 copy of the (summed) row
+  const long long row = blockIdx.x;
+  float ss = 0.f;
+  for (int v = threadIdx.x; v < H / 8; v += blockDim.x) {
+    uint4 a = *reinterpret_cast<const uint4*>(x + row * H + v * 8);
+    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = __bfloat162float(pa[i]);
+    if constexpr (kAdd) {
+      uint4 r = *reinterpret_cast<const uint4*>(residual + row * H + v * 8);
+      const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(&r);
+      uint4 o;
+      __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[i] += __bfloat162float(pr[i]);
+        po[i] = __float2bfloat16_rn(f[i]);
+      }
+      *reinterpret_cast<uint4*>(residual + row * H + v * 8) = o;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xs[v * 8 + i] = f[i];
+      ss += f[i] * f[i];
+    }
+  }
+  ss = block_sum(ss, red);
+  const float inv = rsqrtf(ss / H + eps);
+  for (int v = threadIdx.x; v < H / 8; v += blockDim.x) {
+    uint4 o;
+    __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) po[i] = __float2bfloat16_rn(xs[v * 8 + i] * inv * w[v * 8 + i]);
+    *reinterpret_cast<uint4*>(out + row * H + v * 8) = o;
+  }
+}
+
+// one CTA per row of x [rows][K] bf16 -> q int8, scale (f32 and/or bf16)
+__global__ void __launch_bounds__(256) quant_rows_int8_kernel(const __nv_bfloat16* __restrict__ x, int8_t* __restrict__ q,
+                                                              float* __restrict__ scale_f32,
+                                                              __nv_bfloat16* __restrict__ scale_bf16, int K) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) mx = fmaxf(mx, fabsf(__bfloat162float(x[row * K + i])));
+  mx = block_max(mx, red);
+  const float scale = fmaxf(mx, 1e-10f) / 127.0f;
+  if (threadIdx.x == 0) {
+    if (scale_f32) scale_f32[row] = scale;
+    if (scale_bf16) scale_bf16[row] = __float2bfloat16_rn(scale);
+  }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const float v = rintf(__bfloat162float(x[row * K + i]) / scale);       // torch.round: half to even
+    q[row * K + i] = (int8_t)fminf(fmaxf(v, -128.f), 127.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) silu_and_mul_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           long long rows, int N) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * (N / 8)) return;
+  const long long r = idx / (N / 8);
+  const int v = (int)(idx % (N / 8));
+  const uint4 g4 = *reinterpret_cast<const uint4*>(x + r * 2 * N + v * 8);
+  const uint4 u4 = *reinterpret_cast<const uint4*>(x + r * 2 * N + N + v * 8);
+  const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&g4);
+  const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(&u4);
+  uint4 o;
+  __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float gv = __bfloat162float(g[i]);
+    po[i] = __float2bfloat16_rn(gv / (1.0f + __expf(-gv)) * __bfloat162float(u[i]));
+  }
+  *reinterpret_cast<uint4*>(out + r * N + v * 8) = o;
+}
+
+// y[m] *= bf16(sigmoid(bf16(dot(h[m], w)))) ; one CTA per row
+__global__ void __launch_bounds__(256) sigmoid_gate_mul_kernel(const __nv_bfloat16* __restrict__ h,
+                                                               const __nv_bfloat16* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ y, int H, int N) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) acc = fmaf(__bfloat162float(h[row * H + i]), __bfloat162float(w[i]), acc);
+  acc = block_sum(acc, red);
+  const float lin = __bfloat162float(__float2bfloat16_rn(acc));
+  const float gv = __bfloat162float(__float2bfloat16_rn(1.0f / (1.0f + expf(-lin))));
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    y[row * N + i] = __float2bfloat16_rn(gv * __bfloat162float(y[row * N + i]));
+}
+
+cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, int M, int H, float eps, cudaStream_t s) {
+  if (H % 8 || M <= 0) return cudaErrorInvalidValue;
+  if (residual)
+    rmsnorm_kernel<true><<<M, 256, H * sizeof(float), s>>>((__nv_bfloat16*)x, (__nv_bfloat16*)residual, w, (__nv_bfloat16*)out, H, eps);
+  else
+    rmsnorm_kernel<false><<<M, 256, H * sizeof(float), s>>>((__nv_bfloat16*)x, nullptr, w, (__nv_bfloat16*)out, H, eps);
+  return cudaGetLastError();
+}
+cudaError_t launch_quant_rows_int8(const void* x, void* q, float* scale_f32, void* scale_bf16, int rows, int K, cudaStream_t s) {
+  if (rows <= 0) return cudaErrorInvalidValue;
+  quant_rows_int8_kernel<<<rows, 256, 0, s>>>((const __nv_bfloat16*)x, (int8_t*)q, scale_f32, (__nv_bfloat16*)scale_bf16, K);
+  return cudaGetLastError();
+}
+cudaError_t launch_silu_and_mul(const void* x, void* out, int rows, int N, cudaStream_t s) {
+  if (N % 8 || rows <= 0) return cudaErrorInvalidValue;
+  const long long total = (long long)rows * (N / 8);
+  silu_and_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, N);
+  return cudaGetLastError();
+}
+cudaError_t launch_sigmoid_gate_mul(const void* h, const void* w, void* y, int M, int H, int N, cudaStream_t s) {
+  if (M <= 0) return cudaErrorInvalidValue;
+  sigmoid_gate_mul_kernel<<<M, 256, 0, s>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, H, N);
+  return cudaGetLastError();
+}
+
+}  // namespace kb2

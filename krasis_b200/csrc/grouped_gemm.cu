@@ -399,6 +399,20 @@ cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// rows x cols 8-bit row-major matrix, box = box_rows x 128 columns (128 B), 128 B swizzle
+cudaError_t make_tmap_u8_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols};
+  cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out_tmap), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 int gemm_b_box_rows() { return kBBoxRows; }
 
 template <int FMT, bool kGemm1>
