@@ -187,6 +187,9 @@ KB2_API int kb2_silu_and_mul(const void* x_dev, void* out_dev, int32_t rows, int
 KB2_API int kb2_sigmoid_gate_mul(const void* hidden_dev, const void* gate_w_dev, void* y_dev, int32_t M, int32_t H, int32_t N,
                                  int32_t device, void* stream);
 
+/* out = a + b on BF16 tensors (the `output + shared` add of python/krasis/layer.py:684-685 in the EP path). */
+KB2_API int kb2_add_bf16(const void* a_dev, const void* b_dev, void* out_dev, int64_t n, int32_t device, void* stream);
+
 /* Gated DeltaNet linear attention — python/krasis/linear_attention.py:GatedDeltaNetAttention (prefill path
  * `_forward_chunked`, :695-844).  One handle holds the weights and the per-layer conv / recurrent state the
  * reference keeps on the object (:180-205); kb2_gdn_forward == forward(hidden, is_decode=False) for M tokens and

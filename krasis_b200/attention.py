@@ -48,33 +48,44 @@ class GatedDeltaNetAttention:
     `weights` keys as in the reference (:167-176): in_proj_qkvz, in_proj_ba, out_proj, conv1d_weight, A_log,
     dt_bias, norm_weight — BF16 tensors (INT8 attention weights are disabled in the reference, config.py:209)."""
 
-    def __init__(self, cfg, layer_idx: int, weights: dict, device, max_tokens: int = 8192):
+    _MAX_SHARED = 128      # layers one native handle (= one set of scratch buffers) can serve
+
+    def __init__(self, cfg, layer_idx: int, weights: dict, device, max_tokens: int = 8192, share_scratch_with=None):
         self.cfg, self.layer_idx = cfg, layer_idx
         self.device = torch.device(device)
         self._lib = capi.load()
         for k, v in weights.items():
             if isinstance(v, tuple):
                 raise ValueError(f"{k}: INT8 attention weights are not supported (the reference disables them, config.py:209)")
-        c = capi.GdnConfig(cfg.hidden_size, cfg.linear_num_key_heads, cfg.linear_num_value_heads,
-                           cfg.linear_key_head_dim, cfg.linear_value_head_dim, cfg.linear_conv_kernel_dim,
-                           float(cfg.rms_norm_eps), max_tokens, 1, self.device.index or 0)
-        self._h = C.c_void_p()
-        capi.check(self._lib.kb2_gdn_create(C.byref(c), C.byref(self._h)))
+        if share_scratch_with is None:
+            c = capi.GdnConfig(cfg.hidden_size, cfg.linear_num_key_heads, cfg.linear_num_value_heads,
+                               cfg.linear_key_head_dim, cfg.linear_value_head_dim, cfg.linear_conv_kernel_dim,
+                               float(cfg.rms_norm_eps), max_tokens, self._MAX_SHARED, self.device.index or 0)
+            self._h = C.c_void_p()
+            capi.check(self._lib.kb2_gdn_create(C.byref(c), C.byref(self._h)))
+            self._owner, self._slot, self._n_slots = None, 0, [1]
+            self._c = c
+        else:                                   # same native handle: layers of one model share the scratch buffers
+            o = share_scratch_with
+            self._h, self._owner, self._c, self._n_slots = o._h, o, o._c, o._n_slots
+            self._slot = self._n_slots[0]
+            self._n_slots[0] += 1
+            if self._slot >= self._MAX_SHARED:
+                raise ValueError("too many layers share one GDN handle")
         arrs = [_bf16_host(weights[k]) for k in ("in_proj_qkvz", "in_proj_ba", "conv1d_weight", "A_log", "dt_bias",
                                                  "norm_weight", "out_proj")]
-        capi.check(self._lib.kb2_gdn_set_weights_host(self._h, 0, *[a.ctypes.data for a in arrs]))
-        self._c = c
+        capi.check(self._lib.kb2_gdn_set_weights_host(self._h, self._slot, *[a.ctypes.data for a in arrs]))
 
     def __del__(self):
         try:
-            if self._h:
+            if self._owner is None and self._h:
                 self._lib.kb2_gdn_destroy(self._h)
                 self._h = C.c_void_p()
         except Exception:
             pass
 
     def reset_state(self):
-        capi.check(self._lib.kb2_gdn_reset_state(self._h, 0, _stream(self.device)))
+        capi.check(self._lib.kb2_gdn_reset_state(self._h, self._slot, _stream(self.device)))
 
     def forward(self, hidden: torch.Tensor, is_decode: bool = False) -> torch.Tensor:
         if is_decode:
@@ -83,7 +94,7 @@ class GatedDeltaNetAttention:
                 or hidden.shape[1] != self._c.hidden_size:
             raise ValueError(f"hidden: expected contiguous CUDA bf16 [M, {self._c.hidden_size}]")
         out = torch.empty_like(hidden)
-        capi.check(self._lib.kb2_gdn_forward(self._h, 0, hidden.data_ptr(), out.data_ptr(), hidden.shape[0],
+        capi.check(self._lib.kb2_gdn_forward(self._h, self._slot, hidden.data_ptr(), out.data_ptr(), hidden.shape[0],
                                              _stream(hidden.device)))
         return out
 
@@ -93,7 +104,7 @@ class GatedDeltaNetAttention:
         Cc = 2 * c.num_k_heads * c.k_head_dim + c.num_v_heads * c.v_head_dim
         conv = np.zeros((Cc, c.conv_kernel), np.uint16)
         rec = np.zeros((c.num_v_heads, c.k_head_dim, c.v_head_dim), np.float32)
-        capi.check(self._lib.kb2_gdn_get_state_host(self._h, 0, conv.ctypes.data, rec.ctypes.data))
+        capi.check(self._lib.kb2_gdn_get_state_host(self._h, self._slot, conv.ctypes.data, rec.ctypes.data))
         return (conv.astype(np.uint32) << 16).view(np.float32), rec
 
 
@@ -164,7 +175,9 @@ class GQAAttention:
     num_key_value_heads, gqa_head_dim, rotary_dim, rope_theta, rms_norm_eps.  weights: q_proj, k_proj, v_proj, o_proj
     (+ optional q_norm, k_norm) BF16 tensors; gated attention is detected from q_proj's row count (:398-406)."""
 
-    def __init__(self, cfg, layer_idx: int, weights: dict, device, max_tokens: int = 8192):
+    _MAX_SHARED = 128
+
+    def __init__(self, cfg, layer_idx: int, weights: dict, device, max_tokens: int = 8192, share_scratch_with=None):
         self.cfg, self.layer_idx, self.device = cfg, layer_idx, torch.device(device)
         for k in ("q_proj_bias", "k_proj_bias", "v_proj_bias", "o_proj_bias", "sinks"):
             if weights.get(k) is not None:
@@ -175,21 +188,29 @@ class GQAAttention:
         if not self.gated_attention and q_rows != nh * d:
             raise ValueError(f"q_proj has {q_rows} rows, expected {nh * d} or {2 * nh * d}")
         self._lib = capi.load()
-        c = capi.GqaConfig(cfg.hidden_size, nh, nkv, d, cfg.rotary_dim, int(self.gated_attention), float(cfg.rope_theta),
-                           float(cfg.rms_norm_eps), PAGE_SIZE, max_tokens, 1, self.device.index or 0)
-        self._h = C.c_void_p()
-        capi.check(self._lib.kb2_gqa_create(C.byref(c), C.byref(self._h)))
+        if share_scratch_with is None:
+            c = capi.GqaConfig(cfg.hidden_size, nh, nkv, d, cfg.rotary_dim, int(self.gated_attention), float(cfg.rope_theta),
+                               float(cfg.rms_norm_eps), PAGE_SIZE, max_tokens, self._MAX_SHARED, self.device.index or 0)
+            self._h = C.c_void_p()
+            capi.check(self._lib.kb2_gqa_create(C.byref(c), C.byref(self._h)))
+            self._owner, self._slot, self._n_slots, self._c = None, 0, [1], c
+        else:
+            o = share_scratch_with
+            if o.gated_attention != self.gated_attention:
+                raise ValueError("layers sharing a GQA handle must agree on gated attention")
+            self._h, self._owner, self._c, self._n_slots = o._h, o, o._c, o._n_slots
+            self._slot = self._n_slots[0]
+            self._n_slots[0] += 1
         arrs = [_bf16_host(weights[k]) for k in ("q_proj", "k_proj", "v_proj", "o_proj")]
         qn = _bf16_host(weights["q_norm"]) if weights.get("q_norm") is not None else None
         kn = _bf16_host(weights["k_norm"]) if weights.get("k_norm") is not None else None
-        capi.check(self._lib.kb2_gqa_set_weights_host(self._h, 0, *[a.ctypes.data for a in arrs],
+        capi.check(self._lib.kb2_gqa_set_weights_host(self._h, self._slot, *[a.ctypes.data for a in arrs],
                                                       qn.ctypes.data if qn is not None else None,
                                                       kn.ctypes.data if kn is not None else None))
-        self._c = c
 
     def __del__(self):
         try:
-            if self._h:
+            if self._owner is None and self._h:
                 self._lib.kb2_gqa_destroy(self._h)
                 self._h = C.c_void_p()
         except Exception:
@@ -207,7 +228,7 @@ class GQAAttention:
         k_layer, v_layer = kv_cache.get_gqa_layer_caches(layer_offset)
         pos = positions.to(device=hidden.device, dtype=torch.int32).contiguous()
         out = torch.empty_like(hidden)
-        capi.check(self._lib.kb2_gqa_forward(self._h, 0, hidden.data_ptr(), pos.data_ptr(), seq_state.seq_len,
+        capi.check(self._lib.kb2_gqa_forward(self._h, self._slot, hidden.data_ptr(), pos.data_ptr(), seq_state.seq_len,
                                              k_layer.data_ptr(), v_layer.data_ptr(),
                                              seq_state.kv_indices(hidden.device).data_ptr(), seq_state.seq_len + M,
                                              out.data_ptr(), M, _stream(hidden.device)))

@@ -26,6 +26,7 @@ cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, i
 cudaError_t launch_quant_rows_int8(const void* x, void* q, float* scale_f32, void* scale_bf16, int rows, int K, cudaStream_t s);
 cudaError_t launch_silu_and_mul(const void* x, void* out, int rows, int N, cudaStream_t s);
 cudaError_t launch_sigmoid_gate_mul(const void* h, const void* w, void* y, int M, int H, int N, cudaStream_t s);
+cudaError_t launch_add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t s);
 struct GqaDims {
   int H, nh, nkv, d, rotary_dim, gated;
   float theta, eps;
@@ -141,6 +142,14 @@ KB2_API int kb2_sigmoid_gate_mul(const void* hidden_dev, const void* gate_w_dev,
   if (M <= 0) return failf(KB2_ERR_VALUE, "sigmoid_gate_mul: M must be positive");
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(launch_sigmoid_gate_mul(hidden_dev, gate_w_dev, y_dev, M, H, N, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_add_bf16(const void* a_dev, const void* b_dev, void* out_dev, int64_t n, int32_t device, void* stream) {
+  if (!a_dev || !b_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (n <= 0 || n % 8) return failf(KB2_ERR_VALUE, "add_bf16: n must be a positive multiple of 8");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_add_bf16(a_dev, b_dev, out_dev, n, (cudaStream_t)stream));
   return KB2_OK;
 }
 

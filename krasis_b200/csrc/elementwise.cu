@@ -132,6 +132,26 @@ __global__ void __launch_bounds__(256) sigmoid_gate_mul_kernel(const __nv_bfloat
     y[row * N + i] = __float2bfloat16_rn(gv * __bfloat162float(y[row * N + i]));
 }
 
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ out, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 x = reinterpret_cast<const uint4*>(a)[i], y = reinterpret_cast<const uint4*>(b)[i];
+  const __nv_bfloat162* px = reinterpret_cast<const __nv_bfloat162*>(&x);
+  const __nv_bfloat162* py = reinterpret_cast<const __nv_bfloat162*>(&y);
+  uint4 o;
+  __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) po[j] = __hadd2(px[j], py[j]);
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+cudaError_t launch_add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t s) {
+  if (n % 8 || n <= 0) return cudaErrorInvalidValue;
+  add_bf16_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                                 (__nv_bfloat16*)out, n / 8);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, int M, int H, float eps, cudaStream_t s) {
   if (H % 8 || M <= 0) return cudaErrorInvalidValue;
   if (residual)

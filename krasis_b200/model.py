@@ -1,0 +1,209 @@
+"""Lean prefill re-host of the reference's model loop for hybrid linear-attention + GQA MoE models
+(Qwen3-Coder-Next, Qwen3.5-35B-A3B) and pure-GQA MoE models (Qwen3-235B).
+
+Mirrors, for M > 1 (prefill):
+  KrasisModel.forward                 python/krasis/model.py:2167-2207  (token_ids, positions, seq_states, return_all_logits)
+  forward_prefill_layer_grouped       python/krasis/model.py:2719-2955  — without layer groups, expert streaming or
+                                      token chunking: on a 180 GB B200 every expert is resident and 8K tokens fit one pass
+  TransformerLayer.forward            python/krasis/layer.py:242-460    (pre-norm, attention, fused_add_rmsnorm, MoE)
+  final norm + lm_head                python/krasis/model.py:3380-3399
+Layer pattern: full attention iff (i + 1) % full_attention_interval == 0 (python/krasis/config.py:336-342).
+Multi-GPU (one process per GPU): attention replicated on every rank (SURVEY.md §8e option 2), experts sliced by
+rank, partial routed sums all-reduced over NCCL (reference semantics, python/krasis/model.py:3086-3211).
+
+All arithmetic is in libkrasis_b200 kernels; torch holds buffers, does the embedding row gather and the collective.
+"""
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+
+from . import capi
+from .attention import GatedDeltaNetAttention, GQAAttention, PagedKVCache, SequenceKVState
+from .engine import KrasisEngine
+from . import layers as L
+
+
+@dataclass
+class HybridMoEConfig:
+    """The subset of python/krasis/config.py:ModelConfig the prefill path reads."""
+    hidden_size: int = 2048
+    num_hidden_layers: int = 48
+    full_attention_interval: int = 4            # 0 => every layer is full attention
+    vocab_size: int = 151936
+    rms_norm_eps: float = 1e-6
+    # MoE
+    n_routed_experts: int = 512
+    num_experts_per_tok: int = 10
+    moe_intermediate_size: int = 512
+    shared_expert_intermediate_size: int = 512
+    shared_expert_gate: bool = True
+    norm_topk_prob: bool = True
+    routed_scaling_factor: float = 1.0
+    scoring_func: str = "softmax"
+    expert_bits: int = 4
+    # GQA
+    num_attention_heads: int = 16
+    num_key_value_heads: int = 2
+    gqa_head_dim: int = 256
+    partial_rotary_factor: float = 0.25
+    rope_theta: float = 10000000.0
+    gated_attention: bool = True
+    # Gated DeltaNet
+    linear_num_key_heads: int = 16
+    linear_num_value_heads: int = 32
+    linear_key_head_dim: int = 128
+    linear_value_head_dim: int = 128
+    linear_conv_kernel_dim: int = 4
+
+    @property
+    def rotary_dim(self) -> int:                 # config.py:469-473
+        return int(self.gqa_head_dim * self.partial_rotary_factor)
+
+    def is_full_attention_layer(self, i: int) -> bool:
+        return self.full_attention_interval <= 0 or (i + 1) % self.full_attention_interval == 0
+
+
+QWEN3_CODER_NEXT = HybridMoEConfig()
+
+
+class KrasisModel:
+    """Prefill forward of a hybrid MoE transformer with SYNTHETIC (random) weights of the real architecture.
+    Loading real checkpoints goes through the same setters; this class exists so the whole
+    prefill path can be measured end to end without model files."""
+
+    def __init__(self, cfg: HybridMoEConfig, device: int = 0, max_tokens: int = 8192, rank: int = 0, num_ranks: int = 1,
+                 seed: int = 0, group=None, keep_weights: bool = False):
+        self.cfg, self.rank, self.num_ranks, self.group = cfg, rank, num_ranks, group
+        self._keep = keep_weights            # tests: keep torch copies of the synthetic weights for the oracle
+        self.device = torch.device("cuda", device)
+        self.max_tokens = max_tokens
+        dev, bf = self.device, torch.bfloat16
+        H, nl = cfg.hidden_size, cfg.num_hidden_layers
+        g = torch.Generator(device=dev).manual_seed(1000 + seed)          # identical on every rank (replicated weights)
+
+        def rnd(*shape, std=0.02):
+            return (torch.randn(*shape, device=dev, generator=g) * std).to(bf)
+
+        self.embedding = rnd(cfg.vocab_size, H, std=0.02)
+        self.final_norm = (1 + 0.05 * torch.randn(H, device=dev, generator=g)).to(bf).float()
+        lm = rnd(cfg.vocab_size, H, std=0.02)
+        self.lm_head = L.quantize_to_int8(lm)
+        self._lm_head_bf16 = lm if keep_weights else None
+        self.engine = KrasisEngine(hidden_size=H, moe_intermediate_size=cfg.moe_intermediate_size,
+                                   n_routed_experts=cfg.n_routed_experts, num_experts_per_tok=cfg.num_experts_per_tok,
+                                   num_moe_layers=nl, num_bits=cfg.expert_bits, rank=rank, num_ranks=num_ranks,
+                                   scoring_func=cfg.scoring_func, norm_topk_prob=cfg.norm_topk_prob,
+                                   routed_scaling_factor=cfg.routed_scaling_factor, max_tokens=max_tokens, device=device)
+        self.layer_types = ["full_attention" if cfg.is_full_attention_layer(i) else "linear_attention" for i in range(nl)]
+        n_full = sum(t == "full_attention" for t in self.layer_types)
+        self._kv_layer_offsets = []
+        off = 0
+        for t in self.layer_types:                                      # model.py:485-487: -1 for linear layers
+            self._kv_layer_offsets.append(off if t == "full_attention" else -1)
+            off += t == "full_attention"
+        pages = (max_tokens + 15) // 16 + 1
+        self.kv_cache = PagedKVCache(max(n_full, 1), cfg.num_key_value_heads, cfg.gqa_head_dim, dev, max_pages=pages)
+        self.layers = []
+        ge = torch.Generator(device=dev).manual_seed(5000 + 17 * rank + seed)   # expert slices differ per rank
+        acfg = SimpleNamespace(hidden_size=H, num_attention_heads=cfg.num_attention_heads,
+                               num_key_value_heads=cfg.num_key_value_heads, gqa_head_dim=cfg.gqa_head_dim,
+                               rotary_dim=cfg.rotary_dim, rope_theta=cfg.rope_theta, rms_norm_eps=cfg.rms_norm_eps,
+                               linear_num_key_heads=cfg.linear_num_key_heads, linear_num_value_heads=cfg.linear_num_value_heads,
+                               linear_key_head_dim=cfg.linear_key_head_dim, linear_value_head_dim=cfg.linear_value_head_dim,
+                               linear_conv_kernel_dim=cfg.linear_conv_kernel_dim)
+        self._gdn_shared = self._gqa_shared = None
+        for i, lt in enumerate(self.layer_types):
+            lay = SimpleNamespace(layer_type=lt)
+            lay.input_norm = (1 + 0.05 * torch.randn(H, device=dev, generator=g)).to(bf).float()
+            lay.post_attn_norm = (1 + 0.05 * torch.randn(H, device=dev, generator=g)).to(bf).float()
+            if lt == "linear_attention":
+                kd = cfg.linear_num_key_heads * cfg.linear_key_head_dim
+                vd = cfg.linear_num_value_heads * cfg.linear_value_head_dim
+                w = dict(in_proj_qkvz=rnd(2 * kd + 2 * vd, H), in_proj_ba=rnd(2 * cfg.linear_num_value_heads, H),
+                         out_proj=rnd(H, vd), conv1d_weight=rnd(2 * kd + vd, 1, cfg.linear_conv_kernel_dim, std=0.3),
+                         A_log=rnd(cfg.linear_num_value_heads, std=0.5), dt_bias=rnd(cfg.linear_num_value_heads, std=0.5),
+                         norm_weight=(1 + 0.05 * torch.randn(cfg.linear_value_head_dim, device=dev, generator=g)).to(bf))
+                lay.attention = GatedDeltaNetAttention(acfg, i, w, dev, max_tokens=max_tokens, share_scratch_with=self._gdn_shared)
+                self._gdn_shared = self._gdn_shared or lay.attention
+                lay._w = w if keep_weights else None
+            else:
+                nh, nkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.gqa_head_dim
+                w = dict(q_proj=rnd(nh * d * (2 if cfg.gated_attention else 1), H), k_proj=rnd(nkv * d, H), v_proj=rnd(nkv * d, H),
+                         o_proj=rnd(H, nh * d), q_norm=(1 + 0.05 * torch.randn(d, device=dev, generator=g)).to(bf),
+                         k_norm=(1 + 0.05 * torch.randn(d, device=dev, generator=g)).to(bf))
+                lay.attention = GQAAttention(acfg, i, w, dev, max_tokens=max_tokens, share_scratch_with=self._gqa_shared)
+                self._gqa_shared = self._gqa_shared or lay.attention
+                lay._w = w if keep_weights else None
+            # routed experts: random packed nibbles + BF16 group scales in the B200 tile layout (bandwidth-faithful)
+            ts = []
+            for which in range(4):
+                n = self.engine.tiled_bytes(which)
+                if which in (0, 2):
+                    ts.append(torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=ge))
+                else:
+                    ts.append((torch.rand(n // 2, device=dev, generator=ge) * 0.008 + 0.004).to(bf))
+            self.engine.attach_tiled_layer(i, *ts)
+            gate = rnd(cfg.n_routed_experts, H)
+            self.engine.set_routing_weights(i, gate)
+            lay._experts, lay._gate = (ts, gate) if keep_weights else (None, None)
+            lay.shared_expert = None
+            if cfg.shared_expert_intermediate_size > 0:
+                Is = cfg.shared_expert_intermediate_size
+                sw = (rnd(2 * Is, H), rnd(H, Is), rnd(1, H, std=0.05) if cfg.shared_expert_gate else None)
+                lay.shared_expert = L.SharedExpert(*sw)
+                lay._shared_w = sw if keep_weights else None
+            self.layers.append(lay)
+
+    def new_sequence(self) -> List[SequenceKVState]:
+        for lay in self.layers:
+            if lay.layer_type == "linear_attention":
+                lay.attention.reset_state()
+        return [SequenceKVState(self.kv_cache)]
+
+    def forward(self, token_ids: torch.Tensor, positions: torch.Tensor, seq_states: List[SequenceKVState],
+                return_all_logits: bool = False) -> torch.Tensor:
+        """model.py:2167: token_ids [M] int64/int32 on the device, positions [M]; returns logits [1, V] (last token)
+        or [M, V] (return_all_logits) in float32."""
+        cfg = self.cfg
+        M = token_ids.shape[0]
+        if M > self.max_tokens:
+            raise ValueError(f"{M} tokens > max_tokens={self.max_tokens}")
+        st = seq_states[0]
+        hidden = self.embedding[token_ids.long()]                        # row gather (model.py:2744)
+        residual = None
+        eps = cfg.rms_norm_eps
+        for i, lay in enumerate(self.layers):
+            if residual is None:                                           # layer.py:275-285
+                residual = hidden
+                hidden = L.rmsnorm(hidden, lay.input_norm, eps)
+            else:
+                L.fused_add_rmsnorm(hidden, residual, lay.input_norm, eps)
+            if lay.layer_type == "linear_attention":
+                attn = lay.attention.forward(hidden, is_decode=False)
+            else:
+                attn = lay.attention.forward(hidden, positions, self.kv_cache, st, self._kv_layer_offsets[i], num_new_tokens=M)
+            L.fused_add_rmsnorm(attn, residual, lay.post_attn_norm, eps)   # layer.py:305-309
+            h = attn
+            ids, w = self.engine.compute_routing(i, h)
+            shared = lay.shared_expert.forward(h) if lay.shared_expert is not None else None
+            if self.num_ranks > 1:
+                import torch.distributed as dist
+                part = self.engine.moe_forward(i, h, ids, w, routed_only=True)
+                dist.all_reduce(part, group=self.group)                    # EP combine of partial sums
+                hidden = self._finish(part, shared)
+            else:
+                hidden = self.engine.moe_forward(i, h, ids, w, shared=shared)
+        st.advance(M)
+        L.fused_add_rmsnorm(hidden, residual, self.final_norm, eps)        # model.py:3380-3386
+        last = hidden if return_all_logits else hidden[-1:].contiguous()
+        return L.int8_linear(last, *self.lm_head).float()
+
+    def _finish(self, routed, shared):
+        # rsf == 1 for the supported configs; shared add = one BF16 add kernel via the combine entry point
+        if shared is None:
+            return routed
+        capi.check(capi.load().kb2_add_bf16(routed.data_ptr(), shared.data_ptr(), routed.data_ptr(), routed.numel(),
+                                            routed.device.index or 0, torch.cuda.current_stream(routed.device).cuda_stream))
+        return routed
