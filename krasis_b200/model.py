@@ -160,7 +160,10 @@ class KrasisModel:
         for lay in self.layers:
             if lay.layer_type == "linear_attention":
                 lay.attention.reset_state()
-        return [SequenceKVState(self.kv_cache)]
+        for old in getattr(self, "_live_seqs", []):      # single request at a time (src/server.rs header): recycle pages
+            old.free()
+        self._live_seqs = [SequenceKVState(self.kv_cache)]
+        return self._live_seqs
 
     def forward(self, token_ids: torch.Tensor, positions: torch.Tensor, seq_states: List[SequenceKVState],
                 return_all_logits: bool = False) -> torch.Tensor:
