@@ -224,6 +224,7 @@ def run_full_model(args):
     if sampler:
         sampler.start()
     eng.profile(True)
+    model.timing_start()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -235,6 +236,7 @@ def run_full_model(args):
     ms = ev0.elapsed_time(ev1)
     moe_launches = eng.launch_count() - l0
     prof = eng.profile_collect()
+    comp = {kk: v / args.steps for kk, v in model.timing_collect().items()}
     eng.profile(False)
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -283,7 +285,8 @@ def run_full_model(args):
                 "traffic": None, "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                 "algorithmic": f"2*M*k*H*2I/ranks = {flops_per_launch:.3e} FLOP per launch", "avg_launch_ms": g1_ms / max(1, g1_n),
                 "moe_kernel_ms_per_step": {kk: v[0] / args.steps for kk, v in prof.items()},
-                "moe_ms_per_step": moe_ms, "attention_dense_other_ms_per_step": ms_per_step - moe_ms}
+                "moe_ms_per_step": moe_ms, "attention_dense_other_ms_per_step": ms_per_step - moe_ms,
+                "component_ms_per_step": comp}
     cpu_b = None
     if not args.no_cpu_baseline:
         cpu_b, _, _ = cpu_sample(budget_s=args.cpu_budget)

@@ -112,6 +112,55 @@ __global__ void gdn_conv_state_kernel(GdnDims d, const __nv_bfloat16* __restrict
   for (int j = 0; j < d.K; ++j) conv_state[c * d.K + j] = nw[j];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Warp-level 16x8 output tiles on mma.sync m16n8k8 TF32 with fp32-grade accuracy: an fp32 operand is split into
+// hi = tf32(x), lo = tf32(x - hi) and the product is a_hi*b_hi + a_hi*b_lo + a_lo*b_hi ("3xTF32"); operands that hold
+// BF16 values (q, k) are exact in TF32 and need no split.  The delta-rule recurrences stay at fp32 accuracy like the
+// reference (python/krasis/linear_attention.py:776-779 casts everything to float32) while the small per-chunk matmuls
+// leave the CUDA cores.  (These 64x64x128 blocks are below the tcgen05 M=64 tile and strictly sequential across chunks.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c[NT][4] (16 rows x NT*8 cols) += A[16 x K] * B[K x NT*8];  A(r,k) = A[r*sar + k*sak], B(k,n) = B[k*sbk + n*sbn]
+template <int NT, bool SPLIT_A, bool SPLIT_B>
+__device__ __forceinline__ void warp_mma_tiles(float (&c)[NT][4], const float* __restrict__ A, int sar, int sak,
+                                               const float* __restrict__ B, int sbk, int sbn, int k_begin, int k_end) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int k0 = k_begin; k0 < k_end; k0 += 8) {
+    float af[4] = {A[g * sar + (k0 + t) * sak], A[(g + 8) * sar + (k0 + t) * sak], A[g * sar + (k0 + t + 4) * sak],
+                   A[(g + 8) * sar + (k0 + t + 4) * sak]};
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ah[i] = to_tf32(af[i]);
+      if (SPLIT_A) al[i] = to_tf32(af[i] - __uint_as_float(ah[i]));
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float bf[2] = {B[(k0 + t) * sbk + (nt * 8 + g) * sbn], B[(k0 + t + 4) * sbk + (nt * 8 + g) * sbn]};
+      uint32_t bh[2], bl[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        bh[i] = to_tf32(bf[i]);
+        if (SPLIT_B) bl[i] = to_tf32(bf[i] - __uint_as_float(bh[i]));
+      }
+      if (SPLIT_A) mma_tf32(c[nt], al, bh);
+      if (SPLIT_B) mma_tf32(c[nt], ah, bl);
+      mma_tf32(c[nt], ah, bh);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // chunk prepare: grid (n_chunks, nv), 256 threads.  dk, dv <= 128, dk + dv == 256 is NOT required.
 // outputs per (head, chunk): vcorr [64][dv], kcd [64][dk], intra [64][64], gcum [64]   (all fp32)
@@ -126,14 +175,15 @@ __global__ void __launch_bounds__(256) gdn_chunk_prepare_kernel(GdnDims d, const
   extern __shared__ float sm[];
   const int ch = blockIdx.x, h = blockIdx.y, r = d.nv / d.nk, kh = h / r;
   const int dk = d.dk, dv = d.dv, kd = d.nk * dk, vd = d.nv * dv;
-  float* sq = sm;                       // [64][dk+1]
-  float* sk = sq + kGC * (dk + 1);      // [64][dk+1]
-  float* sA = sk + kGC * (dk + 1);      // [64][65]
-  float* sB = sA + kGC * 65;            // [64][dv + dk]   right-hand sides / solution
-  float* sg = sB + kGC * (dv + dk);     // [64] gcum
+  const int ldk = dk + 4, ldb = dv + dk + 8, ldA = kGC + 4;
+  float* sq = sm;                       // [64][ldk]
+  float* sk = sq + kGC * ldk;           // [64][ldk]
+  float* sA = sk + kGC * ldk;           // [64][ldA]
+  float* sB = sA + kGC * ldA;           // [64][ldb]   right-hand sides -> solution
+  float* sg = sB + kGC * ldb;           // [64] gcum
   float* sb = sg + kGC;                 // [64] beta
   const int t0 = ch * kGC;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   for (int i = tid; i < kGC; i += 256) {
     const int t = t0 + i;
     sb[i] = t < M ? beta[(long long)t * d.nv + h] : 0.f;
@@ -141,8 +191,8 @@ __global__ void __launch_bounds__(256) gdn_chunk_prepare_kernel(GdnDims d, const
   }
   for (int idx = tid; idx < kGC * dk; idx += 256) {
     const int i = idx / dk, c = idx % dk, t = t0 + i;
-    sq[i * (dk + 1) + c] = t < M ? __bfloat162float(qn[(long long)t * kd + kh * dk + c]) : 0.f;
-    sk[i * (dk + 1) + c] = t < M ? __bfloat162float(kn[(long long)t * kd + kh * dk + c]) : 0.f;
+    sq[i * ldk + c] = t < M ? __bfloat162float(qn[(long long)t * kd + kh * dk + c]) : 0.f;
+    sk[i * ldk + c] = t < M ? __bfloat162float(kn[(long long)t * kd + kh * dk + c]) : 0.f;
   }
   __syncthreads();
   if (tid == 0) {                         // cumulative sum in token order (matches torch.cumsum)
@@ -158,44 +208,76 @@ __global__ void __launch_bounds__(256) gdn_chunk_prepare_kernel(GdnDims d, const
     const int i = idx / (dv + dk), c = idx % (dv + dk), t = t0 + i;
     float val;
     if (c < dv) val = t < M ? __bfloat162float(vc[(long long)t * vd + h * dv + c]) * sb[i] : 0.f;
-    else val = sk[i * (dk + 1) + (c - dv)] * sb[i] * expf(sg[i]);
-    sB[i * (dv + dk) + c] = val;
+    else val = sk[i * ldk + (c - dv)] * sb[i] * expf(sg[i]);
+    sB[i * ldb + c] = val;
   }
-  // A[i][j] = -(k_i.beta_i . k_j) * exp(gcum_i - gcum_j), j < i ; intra[i][j] = (q_i . k_j) * exp(gcum_i - gcum_j), j <= i
-  float* o_intra = intra + ((long long)h * n_chunks + ch) * kGC * kGC;
-  for (int idx = tid; idx < kGC * kGC; idx += 256) {
-    const int i = idx / kGC, j = idx % kGC;
-    float a = 0.f, qk = 0.f;
-    if (j <= i) {
-      float kk = 0.f;
-      for (int c = 0; c < dk; ++c) {
-        const float kj = sk[j * (dk + 1) + c];
-        kk = fmaf(sk[i * (dk + 1) + c], kj, kk);
-        qk = fmaf(sq[i * (dk + 1) + c], kj, qk);
+  // K K^T (warps 0-3) and Q K^T (warps 4-7): q, k hold BF16 values -> exact in TF32, fp32 accumulate
+  {
+    const int mt = warp & 3;
+    float acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const float* Am = (warp < 4 ? sk : sq) + mt * 16 * ldk;
+    warp_mma_tiles<8, false, false>(acc, Am, ldk, 1, sk, 1, ldk, 0, dk);      // B(k=c, n=j) = sk[j*ldk + c]
+    float* o_intra = intra + ((long long)h * n_chunks + ch) * kGC * kGC;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = mt * 16 + gq + (e >= 2 ? 8 : 0), j = nt * 8 + 2 * tq + (e & 1);
+        const float dec = expf(sg[i] - sg[j]);
+        if (warp < 4) sA[i * ldA + j] = j < i ? -(acc[nt][e] * sb[i]) * dec : 0.f;
+        else o_intra[i * kGC + j] = j <= i ? acc[nt][e] * dec : 0.f;
       }
-      const float dec = expf(sg[i] - sg[j]);
-      qk *= dec;
-      a = j < i ? -(kk * sb[i]) * dec : 0.f;
     }
-    sA[i * 65 + j] = a;
-    o_intra[idx] = qk;
   }
   __syncthreads();
-  // forward substitution in place: X[i] = B[i] + sum_{j<i} A[i][j] X[j]; one thread owns one column of sB
-  // (bank = column % 32 -> conflict-free; A[i][j] is a warp-wide broadcast)
-  for (int c = tid; c < dv + dk; c += 256) {
-    const int ldb = dv + dk;
-    for (int i = 1; i < kGC; ++i) {
-      float acc = sB[i * ldb + c];
-      const float* arow = sA + i * 65;
-#pragma unroll 4
-      for (int j = 0; j < i; ++j) acc = fmaf(arow[j], sB[j * ldb + c], acc);
-      sB[i * ldb + c] = acc;
+  // blocked forward substitution X = (I - A)^-1 B: 16-row blocks; off-diagonal blocks on mma (3xTF32), the 16x16
+  // diagonal block sequentially (one thread per column; conflict-free, A[i][j] is a warp-wide broadcast)
+  const int ncols = dv + dk;
+  for (int b = 0; b < kGC / 16; ++b) {
+    if (b > 0) {
+      for (int nt0 = warp * 4; nt0 * 8 < ncols; nt0 += 32) {        // 8 warps x 4 n-tiles = 256 columns per pass
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r0 = b * 16 + gq, c0 = (nt0 + nt) * 8 + 2 * tq;
+          const bool ok = c0 < ncols;
+          acc[nt][0] = ok ? sB[r0 * ldb + c0] : 0.f;
+          acc[nt][1] = ok ? sB[r0 * ldb + c0 + 1] : 0.f;
+          acc[nt][2] = ok ? sB[(r0 + 8) * ldb + c0] : 0.f;
+          acc[nt][3] = ok ? sB[(r0 + 8) * ldb + c0 + 1] : 0.f;
+        }
+        warp_mma_tiles<4, true, true>(acc, sA + b * 16 * ldA, ldA, 1, sB + nt0 * 8, ldb, 1, 0, b * 16);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r0 = b * 16 + gq, c0 = (nt0 + nt) * 8 + 2 * tq;
+          if (c0 < ncols) {
+            sB[r0 * ldb + c0] = acc[nt][0];
+            sB[r0 * ldb + c0 + 1] = acc[nt][1];
+            sB[(r0 + 8) * ldb + c0] = acc[nt][2];
+            sB[(r0 + 8) * ldb + c0 + 1] = acc[nt][3];
+          }
+        }
+      }
+      __syncthreads();
     }
-    float* dst = c < dv ? vcorr + ((long long)h * n_chunks + ch) * kGC * dv + c
-                        : kcd + ((long long)h * n_chunks + ch) * kGC * dk + (c - dv);
-    const int ldd = c < dv ? dv : dk;
-    for (int i = 0; i < kGC; ++i) dst[i * ldd] = sB[i * ldb + c];
+    for (int c = tid; c < ncols; c += 256) {
+      for (int i = b * 16 + 1; i < b * 16 + 16; ++i) {
+        float acc = sB[i * ldb + c];
+        const float* arow = sA + i * ldA;
+        for (int j = b * 16; j < i; ++j) acc = fmaf(arow[j], sB[j * ldb + c], acc);
+        sB[i * ldb + c] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < kGC * ncols; idx += 256) {
+    const int i = idx / ncols, c = idx % ncols;
+    if (c < dv) vcorr[((long long)h * n_chunks + ch) * kGC * dv + i * dv + c] = sB[i * ldb + c];
+    else kcd[((long long)h * n_chunks + ch) * kGC * dk + i * dk + (c - dv)] = sB[i * ldb + c];
   }
   for (int i = tid; i < kGC; i += 256) gcum_out[((long long)h * n_chunks + ch) * kGC + i] = sg[i];
 }
@@ -204,6 +286,8 @@ __global__ void __launch_bounds__(256) gdn_chunk_prepare_kernel(GdnDims d, const
 // chunk scan: grid (nv, dv/32), 256 threads; state slice S[dk][32] in smem (fp32), updated in place.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSV = 32;   // dv slice width
+constexpr int kLdS = kSV + 8;   // [k][n] operands: row stride = 8 mod 32 -> conflict-free B fragments
+constexpr int kLdI = kGC + 4;   // [row][k] operands: row stride = 4 mod 32 -> conflict-free A fragments
 
 __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qn,
                                                              const __nv_bfloat16* __restrict__ kn,
@@ -216,92 +300,119 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
   extern __shared__ float sm[];
   const int h = blockIdx.x, sl = blockIdx.y, r = d.nv / d.nk, kh = h / r;
   const int dk = d.dk, dv = d.dv, kd = d.nk * dk, vd = d.nv * dv;
-  float* S = sm;                          // [dk][kSV]
-  float* sq = S + dk * kSV;               // [64][dk+1]
-  float* sk = sq + kGC * (dk + 1);        // [64][dk+1]
-  float* skc = sk + kGC * (dk + 1);       // [64][dk+1]  k_cumdecay
-  float* sI = skc + kGC * (dk + 1);       // [64][65]
-  float* sV = sI + kGC * 65;              // [64][kSV]   value_corrected slice -> v_new
-  float* sO = sV + kGC * kSV;             // [64][kSV]
-  float* sg = sO + kGC * kSV;             // [64]
-  const int tid = threadIdx.x;
+  const int ldk = dk + 4;
+  float* S = sm;                          // [dk][kLdS]
+  float* sq = S + dk * kLdS;              // [64][ldk]
+  float* sk = sq + kGC * ldk;             // [64][ldk]
+  float* skc = sk + kGC * ldk;            // [64][ldk]  k_cumdecay
+  float* sI = skc + kGC * ldk;            // [64][kLdI]
+  float* sV = sI + kGC * kLdI;            // [64][kLdS] value_corrected slice -> v_new
+  float* sO = sV + kGC * kLdS;            // [64][kLdS] decayed v_new
+  float* sg = sO + kGC * kLdS;            // [64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   for (int idx = tid; idx < dk * kSV; idx += 256) {
     const int k = idx / kSV, c = idx % kSV;
-    S[idx] = state[((long long)h * dk + k) * dv + sl * kSV + c];
+    S[k * kLdS + c] = state[((long long)h * dk + k) * dv + sl * kSV + c];
   }
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int t0 = ch * kGC;
     const long long hc = (long long)h * n_chunks + ch;
     __syncthreads();
     for (int idx = tid; idx < kGC * dk; idx += 256) {
-      const int i = idx / dk, c = idx % dk, t = t0 + i;
-      sq[i * (dk + 1) + c] = t < M ? __bfloat162float(qn[(long long)t * kd + kh * dk + c]) : 0.f;
-      sk[i * (dk + 1) + c] = t < M ? __bfloat162float(kn[(long long)t * kd + kh * dk + c]) : 0.f;
-      skc[i * (dk + 1) + c] = kcd[hc * kGC * dk + idx];
+      const int i = idx / dk, c = idx % dk, tt = t0 + i;
+      sq[i * ldk + c] = tt < M ? __bfloat162float(qn[(long long)tt * kd + kh * dk + c]) : 0.f;
+      sk[i * ldk + c] = tt < M ? __bfloat162float(kn[(long long)tt * kd + kh * dk + c]) : 0.f;
+      skc[i * ldk + c] = kcd[hc * kGC * dk + idx];
     }
-    for (int idx = tid; idx < kGC * kGC; idx += 256) sI[(idx / kGC) * 65 + (idx % kGC)] = intra[hc * kGC * kGC + idx];
+    for (int idx = tid; idx < kGC * kGC; idx += 256) sI[(idx / kGC) * kLdI + (idx % kGC)] = intra[hc * kGC * kGC + idx];
     for (int idx = tid; idx < kGC * kSV; idx += 256) {
       const int i = idx / kSV, c = idx % kSV;
-      sV[idx] = vcorr[hc * kGC * dv + i * dv + sl * kSV + c];
+      sV[i * kLdS + c] = vcorr[hc * kGC * dv + i * dv + sl * kSV + c];
     }
     for (int i = tid; i < kGC; i += 256) sg[i] = gcum[hc * kGC + i];
     __syncthreads();
-    // (1) v_new = vcorr - kcd @ S ;  inter = exp(gcum_i) * (q_i @ S)      [64 x 32], 8 outputs per thread
-    {
-      const int c = tid % kSV, i0 = tid / kSV;                 // i0 in 0..7, rows i0, i0+8, ...
-      float vp[8], it[8];
+    // (1) warps 0-3: VP = kcd @ S (both fp32 -> 3xTF32);  warps 4-7: IT = q @ S (q exact in TF32)
+    float acc[4][4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) vp[u] = it[u] = 0.f;
-      for (int k = 0; k < dk; ++k) {
-        const float s = S[k * kSV + c];
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + 8 * u;
-          vp[u] = fmaf(skc[i * (dk + 1) + k], s, vp[u]);
-          it[u] = fmaf(sq[i * (dk + 1) + k], s, it[u]);
-        }
-      }
-      __syncthreads();                                           // everyone done reading S/sV inputs? (sV read below)
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const int mt = warp & 3;
+    if (warp < 4)
+      warp_mma_tiles<4, true, true>(acc, skc + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
+    else
+      warp_mma_tiles<4, false, true>(acc, sq + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
+    __syncthreads();
+    if (warp < 4) {          // v_new = vcorr - VP   (in place in sV)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + 8 * u;
-        sV[i * kSV + c] = sV[i * kSV + c] - vp[u];              // v_new (own element only)
-        sO[i * kSV + c] = it[u] * expf(sg[i]);
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r0 = mt * 16 + g, c0 = nt * 8 + 2 * t;
+        sV[r0 * kLdS + c0] -= acc[nt][0];
+        sV[r0 * kLdS + c0 + 1] -= acc[nt][1];
+        sV[(r0 + 8) * kLdS + c0] -= acc[nt][2];
+        sV[(r0 + 8) * kLdS + c0 + 1] -= acc[nt][3];
       }
     }
     __syncthreads();
-    // (2) out = inter + intra @ v_new
-    {
-      const int c = tid % kSV, i0 = tid / kSV;
+    // (2) out = exp(gcum_i) * IT + intra @ v_new : warps 4-7 keep IT in registers and add the (lower-triangular) product
+    if (warp >= 4) {
+      const float e0 = expf(sg[mt * 16 + g]), e1 = expf(sg[mt * 16 + g + 8]);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + 8 * u;
-        float acc = sO[i * kSV + c];
-        for (int j = 0; j <= i; ++j) acc = fmaf(sI[i * 65 + j], sV[j * kSV + c], acc);
-        const int t = t0 + i;
-        if (t < M) core_out[(long long)t * vd + h * dv + sl * kSV + c] = acc;
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[nt][0] *= e0; acc[nt][1] *= e0; acc[nt][2] *= e1; acc[nt][3] *= e1;
+      }
+      warp_mma_tiles<4, true, true>(acc, sI + mt * 16 * kLdI, kLdI, 1, sV, kLdS, 1, 0, (mt + 1) * 16);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r0 = mt * 16 + g, c0 = sl * kSV + nt * 8 + 2 * t;
+        const int ta = t0 + r0, tb = t0 + r0 + 8;
+        if (ta < M) {
+          core_out[(long long)ta * vd + h * dv + c0] = acc[nt][0];
+          core_out[(long long)ta * vd + h * dv + c0 + 1] = acc[nt][1];
+        }
+        if (tb < M) {
+          core_out[(long long)tb * vd + h * dv + c0] = acc[nt][2];
+          core_out[(long long)tb * vd + h * dv + c0 + 1] = acc[nt][3];
+        }
+      }
+    } else {                 // warps 0-3 meanwhile: decayed v_new for the state update
+      const float gl = sg[kGC - 1];
+      for (int idx = tid; idx < kGC * kSV; idx += 128) {
+        const int i = idx / kSV, c = idx % kSV;
+        sO[i * kLdS + c] = expf(gl - sg[i]) * sV[i * kLdS + c];
       }
     }
-    // (3) S = S * exp(g_last) + sum_i k_i^T * (exp(g_last - gcum_i) * v_new_i)     [dk x 32], dk/8 rows per thread
-    __syncthreads();                                             // (2) is done with sO
+    __syncthreads();
+    // (3) S = S * exp(g_last) + K^T @ (decayed v_new): warp w owns state rows [16w, 16w+16) (dk = 128 -> 8 warps)
     {
-      const float gl = sg[kGC - 1];
-      for (int idx = tid; idx < kGC * kSV; idx += 256) sO[idx] = expf(gl - sg[idx / kSV]) * sV[idx];   // decayed v_new
-      __syncthreads();
-      const float egl = expf(gl);
-      const int c = tid % kSV, k0 = tid / kSV;                  // k rows k0, k0+8, ...
-      for (int kk = k0; kk < dk; kk += 8) {
-        float acc = S[kk * kSV + c] * egl;
-#pragma unroll 8
-        for (int i = 0; i < kGC; ++i) acc = fmaf(sk[i * (dk + 1) + kk], sO[i * kSV + c], acc);
-        S[kk * kSV + c] = acc;
+      const float egl = expf(sg[kGC - 1]);
+      for (int mt3 = warp; mt3 < dk / 16; mt3 += 8) {
+        float sc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r0 = mt3 * 16 + g, c0 = nt * 8 + 2 * t;
+          sc[nt][0] = S[r0 * kLdS + c0] * egl;
+          sc[nt][1] = S[r0 * kLdS + c0 + 1] * egl;
+          sc[nt][2] = S[(r0 + 8) * kLdS + c0] * egl;
+          sc[nt][3] = S[(r0 + 8) * kLdS + c0 + 1] * egl;
+        }
+        // A = K^T: A(row = kk, k = i) = sk[i*ldk + kk]
+        warp_mma_tiles<4, false, true>(sc, sk + mt3 * 16, 1, ldk, sO, kLdS, 1, 0, kGC);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r0 = mt3 * 16 + g, c0 = nt * 8 + 2 * t;
+          S[r0 * kLdS + c0] = sc[nt][0];
+          S[r0 * kLdS + c0 + 1] = sc[nt][1];
+          S[(r0 + 8) * kLdS + c0] = sc[nt][2];
+          S[(r0 + 8) * kLdS + c0 + 1] = sc[nt][3];
+        }
       }
     }
   }
   __syncthreads();
   for (int idx = tid; idx < dk * kSV; idx += 256) {
     const int k = idx / kSV, c = idx % kSV;
-    state[((long long)h * dk + k) * dv + sl * kSV + c] = S[idx];
+    state[((long long)h * dk + k) * dv + sl * kSV + c] = S[k * kLdS + c];
   }
 }
 
@@ -334,17 +445,17 @@ __global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const float* _
 
 // ------------------------------------------------------------------------------------------------
 size_t gdn_prepare_smem(const GdnDims& d) {
-  return sizeof(float) * (2 * kGC * (d.dk + 1) + kGC * 65 + kGC * (d.dv + d.dk) + 2 * kGC);
+  return sizeof(float) * (2 * kGC * (d.dk + 4) + kGC * (kGC + 4) + kGC * (d.dv + d.dk + 8) + 2 * kGC);
 }
 size_t gdn_scan_smem(const GdnDims& d) {
-  return sizeof(float) * (d.dk * kSV + 3 * kGC * (d.dk + 1) + kGC * 65 + 2 * kGC * kSV + kGC);
+  return sizeof(float) * (d.dk * kLdS + 3 * kGC * (d.dk + 4) + kGC * kLdI + 2 * kGC * kLdS + kGC);
 }
 
 cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, const void* conv_w, void* conv_state,
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
                             void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
                             float* gcum, float* core, void* normed_out, int M, cudaStream_t s) {
-  if (d.dv % kSV || d.dk > 128 || d.dv > 128 || d.K > 8) return cudaErrorInvalidValue;
+  if (d.dv % kSV || d.dk > 128 || d.dk % 16 || d.dv > 128 || d.K > 8) return cudaErrorInvalidValue;
   const int C = 2 * d.nk * d.dk + d.nv * d.dv;
   const int n_chunks = (M + kGC - 1) / kGC;
   static bool configured = false;

@@ -173,35 +173,77 @@ class KrasisModel:
         M = token_ids.shape[0]
         if M > self.max_tokens:
             raise ValueError(f"{M} tokens > max_tokens={self.max_tokens}")
+        tm = self._timer
         st = seq_states[0]
         hidden = self.embedding[token_ids.long()]                        # row gather (model.py:2744)
         residual = None
         eps = cfg.rms_norm_eps
         for i, lay in enumerate(self.layers):
-            if residual is None:                                           # layer.py:275-285
-                residual = hidden
-                hidden = L.rmsnorm(hidden, lay.input_norm, eps)
-            else:
-                L.fused_add_rmsnorm(hidden, residual, lay.input_norm, eps)
+            with tm("norms"):
+                if residual is None:                                       # layer.py:275-285
+                    residual = hidden
+                    hidden = L.rmsnorm(hidden, lay.input_norm, eps)
+                else:
+                    L.fused_add_rmsnorm(hidden, residual, lay.input_norm, eps)
             if lay.layer_type == "linear_attention":
-                attn = lay.attention.forward(hidden, is_decode=False)
+                with tm("gdn_attention"):
+                    attn = lay.attention.forward(hidden, is_decode=False)
             else:
-                attn = lay.attention.forward(hidden, positions, self.kv_cache, st, self._kv_layer_offsets[i], num_new_tokens=M)
-            L.fused_add_rmsnorm(attn, residual, lay.post_attn_norm, eps)   # layer.py:305-309
+                with tm("gqa_attention"):
+                    attn = lay.attention.forward(hidden, positions, self.kv_cache, st, self._kv_layer_offsets[i], num_new_tokens=M)
+            with tm("norms"):
+                L.fused_add_rmsnorm(attn, residual, lay.post_attn_norm, eps)   # layer.py:305-309
             h = attn
-            ids, w = self.engine.compute_routing(i, h)
-            shared = lay.shared_expert.forward(h) if lay.shared_expert is not None else None
-            if self.num_ranks > 1:
-                import torch.distributed as dist
-                part = self.engine.moe_forward(i, h, ids, w, routed_only=True)
-                dist.all_reduce(part, group=self.group)                    # EP combine of partial sums
-                hidden = self._finish(part, shared)
-            else:
-                hidden = self.engine.moe_forward(i, h, ids, w, shared=shared)
+            with tm("router"):
+                ids, w = self.engine.compute_routing(i, h)
+            with tm("shared_expert"):
+                shared = lay.shared_expert.forward(h) if lay.shared_expert is not None else None
+            with tm("routed_experts"):
+                if self.num_ranks > 1:
+                    import torch.distributed as dist
+                    part = self.engine.moe_forward(i, h, ids, w, routed_only=True)
+                    dist.all_reduce(part, group=self.group)                # EP combine of partial sums
+                    hidden = self._finish(part, shared)
+                else:
+                    hidden = self.engine.moe_forward(i, h, ids, w, shared=shared)
         st.advance(M)
-        L.fused_add_rmsnorm(hidden, residual, self.final_norm, eps)        # model.py:3380-3386
-        last = hidden if return_all_logits else hidden[-1:].contiguous()
-        return L.int8_linear(last, *self.lm_head).float()
+        with tm("final_norm_lm_head"):
+            L.fused_add_rmsnorm(hidden, residual, self.final_norm, eps)    # model.py:3380-3386
+            last = hidden if return_all_logits else hidden[-1:].contiguous()
+            out = L.int8_linear(last, *self.lm_head).float()
+        return out
+
+    # ---- optional per-component device timing (the reference's KRASIS_LAYER_TIMING, model.py:2832,3355-3373)
+    class _Span:
+        def __init__(self, model, name):
+            self.m, self.n = model, name
+
+        def __enter__(self):
+            if self.m.timing:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.m.timing:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.m._spans.append((self.n, self.e0, e1))
+
+    timing = False
+
+    def _timer(self, name):
+        return KrasisModel._Span(self, name)
+
+    def timing_start(self):
+        self.timing, self._spans = True, []
+
+    def timing_collect(self):
+        torch.cuda.synchronize()
+        out = {}
+        for n, a, b in self._spans:
+            out[n] = out.get(n, 0.0) + a.elapsed_time(b)
+        self.timing, self._spans = False, []
+        return out
 
     def _finish(self, routed, shared):
         # rsf == 1 for the supported configs; shared add = one BF16 add kernel via the combine entry point
