@@ -8,8 +8,10 @@ Mirrors, for M > 1 (prefill):
   TransformerLayer.forward            python/krasis/layer.py:242-460    (pre-norm, attention, fused_add_rmsnorm, MoE)
   final norm + lm_head                python/krasis/model.py:3380-3399
 Layer pattern: full attention iff (i + 1) % full_attention_interval == 0 (python/krasis/config.py:336-342).
-Multi-GPU (one process per GPU): attention replicated on every rank (SURVEY.md §8e option 2), experts sliced by
-rank, partial routed sums all-reduced over NCCL (reference semantics, python/krasis/model.py:3086-3211).
+Multi-GPU (one process per GPU): attention is HEAD-parallel (SURVEY.md §8e option 1): every rank holds the
+projection rows / conv channels / out-projection columns of its own heads and the partial o_proj outputs are
+all-reduced over NCCL; experts are sliced by rank and the partial routed sums all-reduced (reference semantics,
+python/krasis/model.py:3086-3211).  Norms, router and shared expert are replicated.
 
 All arithmetic is in libkrasis_b200 kernels; torch holds buffers, does the embedding row gather and the collective.
 """
@@ -68,6 +70,35 @@ class HybridMoEConfig:
 QWEN3_CODER_NEXT = HybridMoEConfig()
 
 
+def shard_gdn_weights(w: dict, cfg: HybridMoEConfig, rank: int, num_ranks: int) -> dict:
+    """Head-parallel slice of a Gated-DeltaNet layer: key-head groups [rank*nk/R, (rank+1)*nk/R).
+    in_proj_qkvz / in_proj_ba rows are already grouped per key head (linear_attention.py:337-391)."""
+    nk, nv, dk, dv = cfg.linear_num_key_heads, cfg.linear_num_value_heads, cfg.linear_key_head_dim, cfg.linear_value_head_dim
+    r = nv // nk
+    k0, k1 = rank * nk // num_ranks, (rank + 1) * nk // num_ranks
+    G = 2 * dk + 2 * r * dv
+    kd, vd = nk * dk, nv * dv
+    cw = w["conv1d_weight"]
+    conv = torch.cat([cw[k0 * dk:k1 * dk], cw[kd + k0 * dk:kd + k1 * dk], cw[2 * kd + k0 * r * dv:2 * kd + k1 * r * dv]], dim=0)
+    return dict(in_proj_qkvz=w["in_proj_qkvz"][k0 * G:k1 * G].contiguous(), in_proj_ba=w["in_proj_ba"][k0 * 2 * r:k1 * 2 * r].contiguous(),
+                conv1d_weight=conv.contiguous(), A_log=w["A_log"][k0 * r:k1 * r].contiguous(), dt_bias=w["dt_bias"][k0 * r:k1 * r].contiguous(),
+                norm_weight=w["norm_weight"], out_proj=w["out_proj"][:, k0 * r * dv:k1 * r * dv].contiguous())
+
+
+def shard_gqa_weights(w: dict, cfg: HybridMoEConfig, rank: int, num_ranks: int):
+    """Head-parallel slice of a GQA layer: query heads split evenly; a KV head is replicated on the ranks that
+    hold query heads of its group.  Returns (weights, num_heads_local, num_kv_heads_local)."""
+    nh, nkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.gqa_head_dim
+    h0, h1 = rank * nh // num_ranks, (rank + 1) * nh // num_ranks
+    grp = nh // nkv
+    kv0, kv1 = h0 // grp, (h1 - 1) // grp + 1
+    qw = d * (2 if cfg.gated_attention else 1)
+    out = dict(q_proj=w["q_proj"][h0 * qw:h1 * qw].contiguous(), k_proj=w["k_proj"][kv0 * d:kv1 * d].contiguous(),
+               v_proj=w["v_proj"][kv0 * d:kv1 * d].contiguous(), o_proj=w["o_proj"][:, h0 * d:h1 * d].contiguous(),
+               q_norm=w.get("q_norm"), k_norm=w.get("k_norm"))
+    return out, h1 - h0, kv1 - kv0
+
+
 class KrasisModel:
     """Prefill forward of a hybrid MoE transformer with SYNTHETIC (random) weights of the real architecture.
     Loading real checkpoints goes through the same setters; this class exists so the whole
@@ -103,8 +134,6 @@ class KrasisModel:
         for t in self.layer_types:                                      # model.py:485-487: -1 for linear layers
             self._kv_layer_offsets.append(off if t == "full_attention" else -1)
             off += t == "full_attention"
-        pages = (max_tokens + 15) // 16 + 1
-        self.kv_cache = PagedKVCache(max(n_full, 1), cfg.num_key_value_heads, cfg.gqa_head_dim, dev, max_pages=pages)
         self.layers = []
         ge = torch.Generator(device=dev).manual_seed(5000 + 17 * rank + seed)   # expert slices differ per rank
         acfg = SimpleNamespace(hidden_size=H, num_attention_heads=cfg.num_attention_heads,
@@ -114,6 +143,16 @@ class KrasisModel:
                                linear_key_head_dim=cfg.linear_key_head_dim, linear_value_head_dim=cfg.linear_value_head_dim,
                                linear_conv_kernel_dim=cfg.linear_conv_kernel_dim)
         self._gdn_shared = self._gqa_shared = None
+        R = num_ranks
+        if R > 1:
+            if cfg.linear_num_key_heads % R or cfg.num_attention_heads % R:
+                raise ValueError("head-parallel attention needs the head counts to be divisible by the number of ranks")
+            grp = cfg.num_attention_heads // cfg.num_key_value_heads
+            if (cfg.num_attention_heads // R) % grp and grp % (cfg.num_attention_heads // R):
+                raise ValueError("query heads per rank must align with the KV groups")
+        gdn_cfg = SimpleNamespace(**{**acfg.__dict__, "linear_num_key_heads": cfg.linear_num_key_heads // R,
+                                     "linear_num_value_heads": cfg.linear_num_value_heads // R})
+        self.kv_heads_local = cfg.num_key_value_heads
         for i, lt in enumerate(self.layer_types):
             lay = SimpleNamespace(layer_type=lt)
             lay.input_norm = (1 + 0.05 * torch.randn(H, device=dev, generator=g)).to(bf).float()
@@ -125,7 +164,8 @@ class KrasisModel:
                          out_proj=rnd(H, vd), conv1d_weight=rnd(2 * kd + vd, 1, cfg.linear_conv_kernel_dim, std=0.3),
                          A_log=rnd(cfg.linear_num_value_heads, std=0.5), dt_bias=rnd(cfg.linear_num_value_heads, std=0.5),
                          norm_weight=(1 + 0.05 * torch.randn(cfg.linear_value_head_dim, device=dev, generator=g)).to(bf))
-                lay.attention = GatedDeltaNetAttention(acfg, i, w, dev, max_tokens=max_tokens, share_scratch_with=self._gdn_shared)
+                wl = shard_gdn_weights(w, cfg, rank, R) if R > 1 else w
+                lay.attention = GatedDeltaNetAttention(gdn_cfg, i, wl, dev, max_tokens=max_tokens, share_scratch_with=self._gdn_shared)
                 self._gdn_shared = self._gdn_shared or lay.attention
                 lay._w = w if keep_weights else None
             else:
@@ -133,7 +173,13 @@ class KrasisModel:
                 w = dict(q_proj=rnd(nh * d * (2 if cfg.gated_attention else 1), H), k_proj=rnd(nkv * d, H), v_proj=rnd(nkv * d, H),
                          o_proj=rnd(H, nh * d), q_norm=(1 + 0.05 * torch.randn(d, device=dev, generator=g)).to(bf),
                          k_norm=(1 + 0.05 * torch.randn(d, device=dev, generator=g)).to(bf))
-                lay.attention = GQAAttention(acfg, i, w, dev, max_tokens=max_tokens, share_scratch_with=self._gqa_shared)
+                if R > 1:
+                    wl, nh_l, nkv_l = shard_gqa_weights(w, cfg, rank, R)
+                    gcfg = SimpleNamespace(**{**acfg.__dict__, "num_attention_heads": nh_l, "num_key_value_heads": nkv_l})
+                    self.kv_heads_local = nkv_l
+                else:
+                    wl, gcfg = w, acfg
+                lay.attention = GQAAttention(gcfg, i, wl, dev, max_tokens=max_tokens, share_scratch_with=self._gqa_shared)
                 self._gqa_shared = self._gqa_shared or lay.attention
                 lay._w = w if keep_weights else None
             # routed experts: random packed nibbles + BF16 group scales in the B200 tile layout (bandwidth-faithful)
@@ -156,7 +202,14 @@ class KrasisModel:
                 lay._shared_w = sw if keep_weights else None
             self.layers.append(lay)
 
+    def _make_kv_cache(self):
+        n_full = sum(t == "full_attention" for t in self.layer_types)
+        pages = (self.max_tokens + 15) // 16 + 1
+        self.kv_cache = PagedKVCache(max(n_full, 1), self.kv_heads_local, self.cfg.gqa_head_dim, self.device, max_pages=pages)
+
     def new_sequence(self) -> List[SequenceKVState]:
+        if not hasattr(self, "kv_cache"):
+            self._make_kv_cache()
         for lay in self.layers:
             if lay.layer_type == "linear_attention":
                 lay.attention.reset_state()
@@ -191,6 +244,10 @@ class KrasisModel:
             else:
                 with tm("gqa_attention"):
                     attn = lay.attention.forward(hidden, positions, self.kv_cache, st, self._kv_layer_offsets[i], num_new_tokens=M)
+            if self.num_ranks > 1:
+                with tm("attention_allreduce"):
+                    import torch.distributed as dist
+                    dist.all_reduce(attn, group=self.group)                # head-parallel: sum of partial o_proj outputs
             with tm("norms"):
                 L.fused_add_rmsnorm(attn, residual, lay.post_attn_norm, eps)   # layer.py:305-309
             h = attn

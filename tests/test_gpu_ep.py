@@ -75,3 +75,42 @@ def test_ep_all_to_all_matches_oracle(world):
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world
     _check(ret)
+
+
+# ------------------------------------------------------------------------------------------------ whole model, head-parallel attention
+
+def _model_worker(rank, world, port, ret):
+    from krasis_b200.model import HybridMoEConfig, KrasisModel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg = HybridMoEConfig(hidden_size=256, num_hidden_layers=4, full_attention_interval=4, vocab_size=512,
+                              n_routed_experts=8, num_experts_per_tok=2, moe_intermediate_size=128,
+                              shared_expert_intermediate_size=128, num_attention_heads=4, num_key_value_heads=2,
+                              gqa_head_dim=128, partial_rotary_factor=0.5, rope_theta=10000.0,
+                              linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=32, linear_value_head_dim=32)
+        M = 150
+        model = KrasisModel(cfg, device=rank, max_tokens=M, rank=rank, num_ranks=world)
+        tok = torch.randint(0, cfg.vocab_size, (M,), generator=torch.Generator().manual_seed(9)).cuda(rank)
+        logits = model.forward(tok, torch.arange(M).cuda(rank), model.new_sequence(), return_all_logits=True)
+        torch.cuda.synchronize()
+        ret[rank] = logits.cpu().numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_whole_model_two_ranks_matches_one_rank():
+    """Head-parallel attention + expert-parallel MoE on 2 GPUs == the single-GPU forward (up to BF16 partial-sum
+    rounding and the router near-ties it can flip)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    r1, r2 = mgr.dict(), mgr.dict()
+    mp.spawn(_model_worker, args=(1, _free_port(), r1), nprocs=1, join=True)
+    mp.spawn(_model_worker, args=(2, _free_port(), r2), nprocs=2, join=True)
+    a, b0, b1 = torch.from_numpy(r1[0]), torch.from_numpy(r2[0]), torch.from_numpy(r2[1])
+    assert torch.equal(b0, b1)                                    # both ranks hold the same logits
+    cos = torch.nn.functional.cosine_similarity(a, b0, dim=1)
+    assert cos[:16].min().item() > 0.999 and (cos > 0.995).float().mean().item() > 0.8
+    assert (a.argmax(1) == b0.argmax(1)).float().mean().item() > 0.8
