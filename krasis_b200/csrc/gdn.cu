@@ -285,10 +285,12 @@ __global__ void __launch_bounds__(256) gdn_chunk_prepare_kernel(GdnDims d, const
 // ------------------------------------------------------------------------------------------------
 // chunk scan: grid (nv, dv/32), 256 threads; state slice S[dk][32] in smem (fp32), updated in place.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSV = 32;   // dv slice width
-constexpr int kLdS = kSV + 8;   // [k][n] operands: row stride = 8 mod 32 -> conflict-free B fragments
+constexpr int kSVMax = 32;   // widest dv slice per CTA
+constexpr int kLdS = kSVMax + 8;   // [k][n] operands: row stride = 8 mod 32 -> conflict-free B fragments
 constexpr int kLdI = kGC + 4;   // [row][k] operands: row stride = 4 mod 32 -> conflict-free A fragments
 
+// kSV = dv slice width per CTA (32, 16 or 8): narrower slices keep every SM busy when a rank holds few heads
+template <int kSV>
 __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qn,
                                                              const __nv_bfloat16* __restrict__ kn,
                                                              const float* __restrict__ vcorr,
@@ -332,20 +334,21 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
     for (int i = tid; i < kGC; i += 256) sg[i] = gcum[hc * kGC + i];
     __syncthreads();
     // (1) warps 0-3: VP = kcd @ S (both fp32 -> 3xTF32);  warps 4-7: IT = q @ S (q exact in TF32)
-    float acc[4][4];
+    constexpr int NT = kSV / 8;
+    float acc[NT][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     const int mt = warp & 3;
     if (warp < 4)
-      warp_mma_tiles<4, true, true>(acc, skc + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
+      warp_mma_tiles<NT, true, true>(acc, skc + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
     else
-      warp_mma_tiles<4, false, true>(acc, sq + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
+      warp_mma_tiles<NT, false, true>(acc, sq + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
     __syncthreads();
     if (warp < 4) {          // v_new = vcorr - VP   (in place in sV)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         const int r0 = mt * 16 + g, c0 = nt * 8 + 2 * t;
         sV[r0 * kLdS + c0] -= acc[nt][0];
         sV[r0 * kLdS + c0 + 1] -= acc[nt][1];
@@ -358,12 +361,12 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
     if (warp >= 4) {
       const float e0 = expf(sg[mt * 16 + g]), e1 = expf(sg[mt * 16 + g + 8]);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         acc[nt][0] *= e0; acc[nt][1] *= e0; acc[nt][2] *= e1; acc[nt][3] *= e1;
       }
-      warp_mma_tiles<4, true, true>(acc, sI + mt * 16 * kLdI, kLdI, 1, sV, kLdS, 1, 0, (mt + 1) * 16);
+      warp_mma_tiles<NT, true, true>(acc, sI + mt * 16 * kLdI, kLdI, 1, sV, kLdS, 1, 0, (mt + 1) * 16);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         const int r0 = mt * 16 + g, c0 = sl * kSV + nt * 8 + 2 * t;
         const int ta = t0 + r0, tb = t0 + r0 + 8;
         if (ta < M) {
@@ -387,9 +390,9 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
     {
       const float egl = expf(sg[kGC - 1]);
       for (int mt3 = warp; mt3 < dk / 16; mt3 += 8) {
-        float sc[4][4];
+        float sc[NT][4];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
           const int r0 = mt3 * 16 + g, c0 = nt * 8 + 2 * t;
           sc[nt][0] = S[r0 * kLdS + c0] * egl;
           sc[nt][1] = S[r0 * kLdS + c0 + 1] * egl;
@@ -397,9 +400,9 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
           sc[nt][3] = S[(r0 + 8) * kLdS + c0 + 1] * egl;
         }
         // A = K^T: A(row = kk, k = i) = sk[i*ldk + kk]
-        warp_mma_tiles<4, false, true>(sc, sk + mt3 * 16, 1, ldk, sO, kLdS, 1, 0, kGC);
+        warp_mma_tiles<NT, false, true>(sc, sk + mt3 * 16, 1, ldk, sO, kLdS, 1, 0, kGC);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
           const int r0 = mt3 * 16 + g, c0 = nt * 8 + 2 * t;
           S[r0 * kLdS + c0] = sc[nt][0];
           S[r0 * kLdS + c0 + 1] = sc[nt][1];
@@ -448,20 +451,22 @@ size_t gdn_prepare_smem(const GdnDims& d) {
   return sizeof(float) * (2 * kGC * (d.dk + 4) + kGC * (kGC + 4) + kGC * (d.dv + d.dk + 8) + 2 * kGC);
 }
 size_t gdn_scan_smem(const GdnDims& d) {
-  return sizeof(float) * (d.dk * kLdS + 3 * kGC * (d.dk + 4) + kGC * kLdI + 2 * kGC * kLdS + kGC);
+  return sizeof(float) * (d.dk * kLdS + 3 * kGC * (d.dk + 4) + kGC * kLdI + 2 * kGC * kLdS + kGC);   // same for every slice width
 }
 
 cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, const void* conv_w, void* conv_state,
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
                             void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
                             float* gcum, float* core, void* normed_out, int M, cudaStream_t s) {
-  if (d.dv % kSV || d.dk > 128 || d.dk % 16 || d.dv > 128 || d.K > 8) return cudaErrorInvalidValue;
+  if (d.dv % kSVMax || d.dk > 128 || d.dk % 16 || d.dv > 128 || d.K > 8) return cudaErrorInvalidValue;
   const int C = 2 * d.nk * d.dk + d.nv * d.dv;
   const int n_chunks = (M + kGC - 1) / kGC;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(gdn_chunk_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gdn_chunk_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     configured = true;
   }
@@ -473,8 +478,13 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
   gdn_chunk_prepare_kernel<<<dim3(n_chunks, d.nv), 256, gdn_prepare_smem(d), s>>>(
       d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, (const __nv_bfloat16*)vc, beta, g, M, n_chunks, vcorr, kcd,
       intra, gcum);
-  gdn_chunk_scan_kernel<<<dim3(d.nv, d.dv / kSV), 256, gdn_scan_smem(d), s>>>(
-      d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, vcorr, kcd, intra, gcum, M, n_chunks, rec_state, core);
+  // slice width: keep >= ~128 CTAs in flight (one per SM) when a rank holds only a few heads
+  const int sv = d.nv * (d.dv / 32) >= 96 ? 32 : (d.nv * (d.dv / 16) >= 96 ? 16 : 8);
+#define KB2_SCAN(SV)                                                                                                  \
+  gdn_chunk_scan_kernel<SV><<<dim3(d.nv, d.dv / SV), 256, gdn_scan_smem(d), s>>>(                                      \
+      d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, vcorr, kcd, intra, gcum, M, n_chunks, rec_state, core)
+  if (sv == 32) KB2_SCAN(32); else if (sv == 16) KB2_SCAN(16); else KB2_SCAN(8);
+#undef KB2_SCAN
   const long long nw = (long long)M * d.nv;
   gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, core, (const __nv_bfloat16*)qkvz, norm_w, M,
                                                                   (__nv_bfloat16*)normed_out);

@@ -135,7 +135,7 @@ class KrasisModel:
             self._kv_layer_offsets.append(off if t == "full_attention" else -1)
             off += t == "full_attention"
         self.layers = []
-        ge = torch.Generator(device=dev).manual_seed(5000 + 17 * rank + seed)   # expert slices differ per rank
+        ge = torch.Generator(device=dev).manual_seed(5000 + seed)   # global expert tensors, identical on every rank; each rank keeps its slice
         acfg = SimpleNamespace(hidden_size=H, num_attention_heads=cfg.num_attention_heads,
                                num_key_value_heads=cfg.num_key_value_heads, gqa_head_dim=cfg.gqa_head_dim,
                                rotary_dim=cfg.rotary_dim, rope_theta=cfg.rope_theta, rms_norm_eps=cfg.rms_norm_eps,
@@ -184,12 +184,17 @@ class KrasisModel:
                 lay._w = w if keep_weights else None
             # routed experts: random packed nibbles + BF16 group scales in the B200 tile layout (bandwidth-faithful)
             ts = []
+            e_loc, e_all = self.engine.expert_end - self.engine.expert_start, cfg.n_routed_experts
             for which in range(4):
-                n = self.engine.tiled_bytes(which)
+                n = self.engine.tiled_bytes(which)              # bytes of this rank's experts; tiles are [expert][...]
+                n_all, off = n // e_loc * e_all, n // e_loc * self.engine.expert_start
                 if which in (0, 2):
-                    ts.append(torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=ge))
+                    full = torch.randint(0, 256, (n_all,), dtype=torch.uint8, device=dev, generator=ge)
+                    ts.append(full[off:off + n].clone() if R > 1 else full)
                 else:
-                    ts.append((torch.rand(n // 2, device=dev, generator=ge) * 0.008 + 0.004).to(bf))
+                    full = (torch.rand(n_all // 2, device=dev, generator=ge) * 0.008 + 0.004).to(bf)
+                    ts.append(full[off // 2:(off + n) // 2].clone() if R > 1 else full)
+                del full
             self.engine.attach_tiled_layer(i, *ts)
             gate = rnd(cfg.n_routed_experts, H)
             self.engine.set_routing_weights(i, gate)
