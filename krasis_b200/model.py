@@ -58,6 +58,7 @@ class HybridMoEConfig:
     linear_key_head_dim: int = 128
     linear_value_head_dim: int = 128
     linear_conv_kernel_dim: int = 4
+    synthetic_router_std: float = 0.02          # std of the random router weights KrasisModel generates
 
     @property
     def rotary_dim(self) -> int:                 # config.py:469-473
@@ -196,7 +197,7 @@ class KrasisModel:
                     ts.append(full[off // 2:(off + n) // 2].clone() if R > 1 else full)
                 del full
             self.engine.attach_tiled_layer(i, *ts)
-            gate = rnd(cfg.n_routed_experts, H)
+            gate = rnd(cfg.n_routed_experts, H, std=cfg.synthetic_router_std)
             self.engine.set_routing_weights(i, gate)
             lay._experts, lay._gate = (ts, gate) if keep_weights else (None, None)
             lay.shared_expert = None

