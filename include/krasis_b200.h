@@ -41,6 +41,8 @@ extern "C" {
 
 #define KB2_FMT_INT4_G128 0 /* Krasis symmetric INT4, group 128 (src/weights/marlin.rs:145-207) */
 #define KB2_FMT_INT8_G128 1 /* Krasis symmetric INT8, group 128 (src/weights/marlin.rs:65-114)  */
+#define KB2_FMT_GGUF_Q8_0 2 /* native GGUF Q8_0 blocks (src/gguf.rs:574-593), losslessly re-tiled */
+#define KB2_FMT_GGUF_Q4_K 3 /* native GGUF Q4_K super-blocks (src/gguf.rs:681-738), losslessly re-tiled */
 
 typedef struct kb2_engine kb2_engine;
 
@@ -60,6 +62,8 @@ typedef struct kb2_config {
   float routed_scaling_factor;
   int32_t max_tokens;             /* largest M a forward call may pass (sizes the scratch buffers) */
   int32_t device;                 /* CUDA device ordinal; forward calls cudaSetDevice(device) like gpu_prefill.py:4401 */
+  int32_t w2_weight_format;       /* KB2_FMT_* of the down projection, or -1 = same as weight_format (GGUF files mix types:
+                                     Q4_K gate/up with Q8_0 / Q6_K down, src/weights/mod.rs:646-647) */
 } kb2_config;
 
 /* lifecycle — KrasisEngine(...) + GpuPrefillManager(...) (src/moe.rs:1482, gpu_prefill.py:326) */
@@ -85,6 +89,13 @@ KB2_API size_t kb2_tiled_bytes(const kb2_engine* e, int which);
  * (src/weights/mod.rs:346-349).  The engine re-tiles them on the device and owns the result. */
 KB2_API int kb2_load_experts_host(kb2_engine* e, int moe_layer_idx, const void* w13_q_host, const void* w13_s_host,
                           const void* w2_q_host, const void* w2_s_host);
+
+/* GGUF expert tensors kept as native blocks (new capability; in the reference GGUF feeds only the CPU experts,
+ * src/weights/mod.rs:3251-3585, src/gguf_kernels.rs:690-756).  gate/up: [E_local][I][row_bytes(H)], down: [E_local][H][row_bytes(I)]
+ * with the block types given by weight_format / w2_weight_format; rows are [N][K] with K contiguous in blocks
+ * (src/gguf_kernels.rs:9).  Merged `ffn_*_exps` tensors are exactly this layout per layer (src/weights/mod.rs:3455-3487). */
+KB2_API int kb2_load_experts_gguf_host(kb2_engine* e, int moe_layer_idx, const void* gate_host, const void* up_host,
+                                       const void* down_host);
 
 /* Same, but the caller already holds device buffers in the B200 tile layout (sizes = kb2_tiled_bytes);
  * the engine only records the pointers (caller keeps ownership).  Used to build synthetic full-size

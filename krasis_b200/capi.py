@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "_lib", "libkrasis_b200.so")
 
 KB2_OK, KB2_ERR_STATE, KB2_ERR_VALUE, KB2_ERR_CUDA = 0, 1, 2, 3
 SCORE_SOFTMAX, SCORE_SIGMOID, SCORE_TOPK_SOFTMAX = 0, 1, 2
-FMT_INT4_G128, FMT_INT8_G128 = 0, 1
+FMT_INT4_G128, FMT_INT8_G128, FMT_GGUF_Q8_0, FMT_GGUF_Q4_K = 0, 1, 2, 3
 
 
 class Config(C.Structure):
@@ -18,7 +18,7 @@ class Config(C.Structure):
         ("num_experts_per_tok", C.c_int32), ("num_moe_layers", C.c_int32), ("weight_format", C.c_int32),
         ("rank", C.c_int32), ("num_ranks", C.c_int32), ("scoring_func", C.c_int32),
         ("norm_topk_prob", C.c_int32), ("routed_scaling_factor", C.c_float), ("max_tokens", C.c_int32),
-        ("device", C.c_int32),
+        ("device", C.c_int32), ("w2_weight_format", C.c_int32),
     ]
 
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     "kb2_expert_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "kb2_tiled_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "kb2_load_experts_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
+    "kb2_load_experts_gguf_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 3),
     "kb2_attach_experts_tiled_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
     "kb2_retile_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
     "kb2_set_router_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

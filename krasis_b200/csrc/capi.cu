@@ -28,6 +28,8 @@ cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, i
                            int* sorted_ids, const void* x, void* x_sorted, int H, cudaStream_t s);
 cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
                            const void* shared, void* out, cudaStream_t s);
+cudaError_t launch_retile_gguf(int fmt, const void* a, const void* b, int n_a, void* dst, int E, int N, int K,
+                               cudaStream_t s);
 cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,
                           cudaStream_t s);
 }  // namespace kb2
@@ -113,16 +115,28 @@ struct ProfSpan {
   }
 };
 
-static size_t tile_bytes_per_weight(int fmt) { return fmt == KB2_FMT_INT4_G128 ? 1 : 2; }  // half-bytes x2
+static int fmt13(const kb2_engine* e) { return e->cfg.weight_format; }
+static int fmt2(const kb2_engine* e) { return e->cfg.w2_weight_format >= 0 ? e->cfg.w2_weight_format : e->cfg.weight_format; }
+
+// bytes of one (128-row x 64-K) tile blob, and of the separate scale tile (0 for self-contained GGUF blobs)
+static size_t blob_bytes(int fmt) {
+  switch (fmt) {
+    case KB2_FMT_INT4_G128: return kInt4TileBytes;
+    case KB2_FMT_INT8_G128: return kInt8TileBytes;
+    case KB2_FMT_GGUF_Q8_0: return kQ8_0TileBytes;
+    case KB2_FMT_GGUF_Q4_K: return kQ4KTileBytes;
+  }
+  return 0;
+}
+static bool has_scale_tiles(int fmt) { return fmt == KB2_FMT_INT4_G128 || fmt == KB2_FMT_INT8_G128; }
 
 static size_t tiled_bytes(const kb2_engine* e, int which) {
   const size_t H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, E = e->e_local;
-  const size_t hb = tile_bytes_per_weight(e->cfg.weight_format);  // in half-bytes
   switch (which) {
-    case 0: return E * 2 * I * H * hb / 2;
-    case 1: return E * 2 * I * (H / kGroup) * 2;
-    case 2: return E * H * I * hb / 2;
-    case 3: return E * H * (I / kGroup) * 2;
+    case 0: return E * (2 * I / kTileRows) * (H / kBlockK) * blob_bytes(fmt13(e));
+    case 1: return has_scale_tiles(fmt13(e)) ? E * 2 * I * (H / kGroup) * 2 : 0;
+    case 2: return E * (H / kTileRows) * (I / kBlockK) * blob_bytes(fmt2(e));
+    case 3: return has_scale_tiles(fmt2(e)) ? E * H * (I / kGroup) * 2 : 0;
   }
   return 0;
 }
@@ -141,8 +155,14 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   if (c->num_ranks < 1 || c->rank < 0 || c->rank >= c->num_ranks) return fail(KB2_ERR_VALUE, "bad rank %d/%d", c->rank, c->num_ranks);
   if (c->n_routed_experts < c->num_ranks) return fail(KB2_ERR_VALUE, "fewer experts than ranks");
   if (c->num_experts_per_tok < 1 || c->num_experts_per_tok > 32) return fail(KB2_ERR_VALUE, "top-k must be in [1,32]");
-  if (c->weight_format != KB2_FMT_INT4_G128 && c->weight_format != KB2_FMT_INT8_G128)
+  if (c->weight_format < KB2_FMT_INT4_G128 || c->weight_format > KB2_FMT_GGUF_Q4_K)
     return fail(KB2_ERR_VALUE, "unknown weight_format %d", c->weight_format);
+  if (c->w2_weight_format > KB2_FMT_GGUF_Q4_K) return fail(KB2_ERR_VALUE, "unknown w2_weight_format %d", c->w2_weight_format);
+  {
+    const int f2 = c->w2_weight_format >= 0 ? c->w2_weight_format : c->weight_format;
+    if (c->weight_format == KB2_FMT_GGUF_Q4_K && c->hidden_size % 256) return fail(KB2_ERR_VALUE, "Q4_K gate/up needs hidden_size %% 256 == 0");
+    if (f2 == KB2_FMT_GGUF_Q4_K && c->moe_intermediate_size % 256) return fail(KB2_ERR_VALUE, "Q4_K down needs moe_intermediate_size %% 256 == 0");
+  }
   if (c->max_tokens < 1 || c->num_moe_layers < 1) return fail(KB2_ERR_VALUE, "max_tokens and num_moe_layers must be >= 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -251,6 +271,8 @@ KB2_API int kb2_load_experts_host(kb2_engine* e, int layer, const void* w13_q, c
   LayerWeights& L = e->layers[layer];
   free_layer(L);
   const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, fmt = e->cfg.weight_format;
+  if (!has_scale_tiles(fmt13(e)) || !has_scale_tiles(fmt2(e)) || fmt13(e) != fmt2(e))
+    return fail(KB2_ERR_STATE, "kb2_load_experts_host takes the INT4/INT8 group-quantised layout; this engine was created for GGUF blocks");
   void* dst[4];
   const void* src[4] = {w13_q, w13_s, w2_q, w2_s};
   void* tmp[4];
@@ -272,10 +294,38 @@ KB2_API int kb2_load_experts_host(kb2_engine* e, int layer, const void* w13_q, c
   return KB2_OK;
 }
 
+KB2_API int kb2_load_experts_gguf_host(kb2_engine* e, int layer, const void* gate_host, const void* up_host, const void* down_host) {
+  if (int r = check_layer(e, layer)) return r;
+  if (!gate_host || !up_host || !down_host) return fail(KB2_ERR_VALUE, "null weight pointer");
+  const int f13 = fmt13(e), f2 = fmt2(e);
+  if (has_scale_tiles(f13) || has_scale_tiles(f2)) return fail(KB2_ERR_STATE, "this engine was not created for GGUF block formats");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  LayerWeights& L = e->layers[layer];
+  free_layer(L);
+  const size_t H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, E = e->e_local;
+  auto row_bytes = [](int fmt, size_t k) { return fmt == KB2_FMT_GGUF_Q8_0 ? k / 32 * 34 : k / 256 * 144; };
+  const size_t gu_bytes = E * I * row_bytes(f13, H), dn_bytes = E * H * row_bytes(f2, I);
+  void *dg = nullptr, *du = nullptr, *dd = nullptr, *t13 = nullptr, *t2 = nullptr;
+  CUDA_TRY(cudaMalloc(&dg, gu_bytes)); CUDA_TRY(cudaMalloc(&du, gu_bytes)); CUDA_TRY(cudaMalloc(&dd, dn_bytes));
+  CUDA_TRY(cudaMemcpy(dg, gate_host, gu_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(du, up_host, gu_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(dd, down_host, dn_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&t13, tiled_bytes(e, 0))); CUDA_TRY(cudaMalloc(&t2, tiled_bytes(e, 2)));
+  cudaError_t r1 = launch_retile_gguf(f13, dg, du, (int)I, t13, (int)E, (int)(2 * I), (int)H, 0);
+  cudaError_t r2 = launch_retile_gguf(f2, dd, dd, (int)H, t2, (int)E, (int)H, (int)I, 0);
+  e->launches += 2;
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaFree(dg); cudaFree(du); cudaFree(dd);
+  if (r1 != cudaSuccess || r2 != cudaSuccess) { cudaFree(t13); cudaFree(t2); return fail(KB2_ERR_CUDA, "GGUF re-tiling failed"); }
+  L.w13_q = (const uint8_t*)t13; L.w2_q = (const uint8_t*)t2; L.w13_s = nullptr; L.w2_s = nullptr;
+  L.owned = true;
+  return KB2_OK;
+}
+
 KB2_API int kb2_attach_experts_tiled_dev(kb2_engine* e, int layer, const void* w13_q, const void* w13_s, const void* w2_q,
                                  const void* w2_s) {
   if (int r = check_layer(e, layer)) return r;
-  if (!w13_q || !w13_s || !w2_q || !w2_s) return fail(KB2_ERR_VALUE, "null weight pointer");
+  if (!w13_q || !w2_q || (has_scale_tiles(fmt13(e)) && !w13_s) || (has_scale_tiles(fmt2(e)) && !w2_s)) return fail(KB2_ERR_VALUE, "null weight pointer");
   LayerWeights& L = e->layers[layer];
   free_layer(L);
   L.w13_q = (const uint8_t*)w13_q; L.w13_s = (const uint8_t*)w13_s;
@@ -336,7 +386,7 @@ static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32
                             int M, int K, int apply_rsf, const void* shared, cudaStream_t s) {
   LayerWeights& L = e->layers[layer];
   const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size;
-  const int fmt = e->cfg.weight_format;
+  const int f13 = fmt13(e), f2 = fmt2(e);
 
   { ProfSpan ps(e, KB2_PROF_BINNING, s);
     CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
@@ -346,13 +396,13 @@ static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32
   GemmParams g1{};
   g1.wq = L.w13_q; g1.ws = L.w13_s;
   g1.wq_expert_stride = (long long)(tiled_bytes(e, 0) / e->e_local);
-  g1.ws_expert_stride = (long long)(tiled_bytes(e, 1) / e->e_local);
+  g1.ws_expert_stride = (long long)(tiled_bytes(e, 1) / e->e_local);   // 0 for GGUF blobs
   g1.n_kblocks = H / kBlockK;
   g1.items_per_chunk = I / kTileRows; g1.tile1_offset = I / kTileRows; g1.tile0_mul = 1;
   g1.chunks = e->chunks; g1.n_chunks = e->n_chunks;
   g1.out = (__nv_bfloat16*)e->act; g1.out_ld = I; g1.slot_weight = nullptr;
   { ProfSpan ps(e, KB2_PROF_GEMM1, s);
-    CUDA_TRY(launch_grouped_gemm(fmt, true, g1, e->tmap_x, e->num_sms, s)); }
+    CUDA_TRY(launch_grouped_gemm(f13, true, g1, e->tmap_x, e->num_sms, s)); }
 
   GemmParams g2{};
   g2.wq = L.w2_q; g2.ws = L.w2_s;
@@ -363,7 +413,7 @@ static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32
   g2.chunks = e->chunks; g2.n_chunks = e->n_chunks;
   g2.out = (__nv_bfloat16*)e->c3; g2.out_ld = H; g2.slot_weight = e->sorted_w;
   { ProfSpan ps(e, KB2_PROF_GEMM2, s);
-    CUDA_TRY(launch_grouped_gemm(fmt, false, g2, e->tmap_act, e->num_sms, s)); }
+    CUDA_TRY(launch_grouped_gemm(f2, false, g2, e->tmap_act, e->num_sms, s)); }
 
   { ProfSpan ps(e, KB2_PROF_COMBINE, s);
     CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply_rsf, shared, out, s)); }

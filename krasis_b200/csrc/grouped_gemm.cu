@@ -61,11 +61,23 @@ struct Fmt<kFmtInt8G128> {
   static constexpr int kTileBytes = kInt8TileBytes;
   static constexpr int kStagesW = 2;
 };
+template <>
+struct Fmt<kFmtQ8_0> {
+  static constexpr int kTileBytes = kQ8_0TileBytes;
+  static constexpr int kStagesW = 2;
+};
+template <>
+struct Fmt<kFmtQ4_K> {
+  static constexpr int kTileBytes = kQ4KTileBytes;
+  static constexpr int kStagesW = 3;
+};
+template <int FMT>
+constexpr bool kHasScaleTiles = (FMT == kFmtInt4G128 || FMT == kFmtInt8G128);
 
 template <int FMT, bool kGemm1>
 struct SmemLayout {
   static constexpr int kStagesW = Fmt<FMT>::kStagesW;
-  static constexpr int kWStageBytes = 2 * Fmt<FMT>::kTileBytes + 2 * kScaleTileBytes;
+  static constexpr int kWStageBytes = 2 * Fmt<FMT>::kTileBytes + (kHasScaleTiles<FMT> ? 2 * kScaleTileBytes : 0);
   static constexpr int kStageRowBytes = 2 * kTileRows * 2;   // epilogue staging: 512 B per token (gate|up or two down tiles)
   static constexpr int kOffB = 0;                                               // 1024-aligned (swizzle atoms)
   static constexpr int kOffStage = kOffB + kStagesB * kBStageBytes;
@@ -170,10 +182,12 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           mbar_arrive_expect_tx(&w_full[rw.stage], L::kWStageBytes);
           bulk_g2s(dst, wq_e + ((long long)t0 * nkb + kb) * TB, TB, &w_full[rw.stage]);
           bulk_g2s(dst + TB, wq_e + ((long long)t1 * nkb + kb) * TB, TB, &w_full[rw.stage]);
-          bulk_g2s(dst + 2 * TB, ws_e + ((long long)t0 * ngroups + (kb >> 1)) * kScaleTileBytes, kScaleTileBytes,
-                   &w_full[rw.stage]);
-          bulk_g2s(dst + 2 * TB + kScaleTileBytes, ws_e + ((long long)t1 * ngroups + (kb >> 1)) * kScaleTileBytes,
-                   kScaleTileBytes, &w_full[rw.stage]);
+          if constexpr (kHasScaleTiles<FMT>) {
+            bulk_g2s(dst + 2 * TB, ws_e + ((long long)t0 * ngroups + (kb >> 1)) * kScaleTileBytes, kScaleTileBytes,
+                     &w_full[rw.stage]);
+            bulk_g2s(dst + 2 * TB + kScaleTileBytes, ws_e + ((long long)t1 * ngroups + (kb >> 1)) * kScaleTileBytes,
+                     kScaleTileBytes, &w_full[rw.stage]);
+          }
           rw.advance(kStagesW);
         }
       }
@@ -243,9 +257,58 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&w_full[rw.stage], rw.phase);
         const uint8_t* wsrc = smem + L::kOffW + rw.stage * L::kWStageBytes;
-        const __nv_bfloat16 s = reinterpret_cast<const __nv_bfloat16*>(wsrc + 2 * TB)[tile * kTileRows + t];
+        __nv_bfloat16 s = __float2bfloat16_rn(0.f);
+        if constexpr (kHasScaleTiles<FMT>) s = reinterpret_cast<const __nv_bfloat16*>(wsrc + 2 * TB)[tile * kTileRows + t];
         uint32_t o[32];
-        if constexpr (FMT == kFmtInt4G128) {
+        if constexpr (FMT == kFmtQ8_0) {
+          // w = bf16(f32(d) * q): the f32 product of an fp16 and an int8 is exact, so this is one rounding (src/gguf.rs:574-593)
+          const uint32_t dd = *reinterpret_cast<const uint32_t*>(wsrc + tile * TB + kTileRows * kBlockK + t * 4);
+          const float d0 = __half2float(__ushort_as_half((unsigned short)(dd & 0xFFFF)));
+          const float d1 = __half2float(__ushort_as_half((unsigned short)(dd >> 16)));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + q * 2048 + t * 16);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            const float sf = q < 2 ? d0 : d1;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t word = ww[e >> 1];
+              const int b0 = (int)(int8_t)((word >> ((e & 1) * 16)) & 0xFF);
+              const int b1 = (int)(int8_t)((word >> ((e & 1) * 16 + 8)) & 0xFF);
+              __nv_bfloat162 v = __floats2bfloat162_rn((float)b0 * sf, (float)b1 * sf);
+              o[q * 8 + e] = *reinterpret_cast<uint32_t*>(&v);
+            }
+          }
+        } else if constexpr (FMT == kFmtQ4_K) {
+          // w = bf16((d*sc)*q - (dmin*mn)) evaluated like src/gguf.rs:711-730: d*sc and dmin*mn exact in f32,
+          // (d*sc)*q exact, one f32 rounding at the subtraction (fmaf), then BF16.
+          const uint2 hd = *reinterpret_cast<const uint2*>(wsrc + tile * TB + kTileRows * kBlockK / 2 + t * 8);
+          const float d = __half2float(__ushort_as_half((unsigned short)(hd.x & 0xFFFF)));
+          const float dmin = __half2float(__ushort_as_half((unsigned short)(hd.x >> 16)));
+          const float dl = d * (float)(hd.y & 0xFF), ml = dmin * (float)((hd.y >> 8) & 0xFF);
+          const float dh = d * (float)((hd.y >> 16) & 0xFF), mh = dmin * (float)(hd.y >> 24);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + h * 2048 + t * 16);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+              for (int bp = 0; bp < 2; ++bp) {           // byte pair (2bp, 2bp+1) of word j = elements l, l+1 (and 32+l, 33+l)
+                const uint32_t b0 = (ww[j] >> (16 * bp)) & 0xFF, b1 = (ww[j] >> (16 * bp + 8)) & 0xFF;
+                const float l0 = __uint_as_float(0x4B000000u | (b0 & 0xF)) - 8388608.0f;
+                const float l1 = __uint_as_float(0x4B000000u | (b1 & 0xF)) - 8388608.0f;
+                const float h0 = __uint_as_float(0x4B000000u | (b0 >> 4)) - 8388608.0f;
+                const float h1 = __uint_as_float(0x4B000000u | (b1 >> 4)) - 8388608.0f;
+                __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(dl, l0, -ml), fmaf(dl, l1, -ml));
+                __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(dh, h0, -mh), fmaf(dh, h1, -mh));
+                const int l = h * 16 + j * 4 + bp * 2;                       // element index of b0's low nibble
+                o[l / 2] = *reinterpret_cast<uint32_t*>(&lo);
+                o[16 + l / 2] = *reinterpret_cast<uint32_t*>(&hi);
+              }
+            }
+          }
+        } else if constexpr (FMT == kFmtInt4G128) {
           const __nv_bfloat162 s2 = __halves2bfloat162(s, s);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -439,6 +502,12 @@ cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, const 
   if (fmt == kFmtInt8G128) {
     return gemm1 ? launch_one<kFmtInt8G128, true>(p, tm, num_sms, stream)
                  : launch_one<kFmtInt8G128, false>(p, tm, num_sms, stream);
+  }
+  if (fmt == kFmtQ8_0) {
+    return gemm1 ? launch_one<kFmtQ8_0, true>(p, tm, num_sms, stream) : launch_one<kFmtQ8_0, false>(p, tm, num_sms, stream);
+  }
+  if (fmt == kFmtQ4_K) {
+    return gemm1 ? launch_one<kFmtQ4_K, true>(p, tm, num_sms, stream) : launch_one<kFmtQ4_K, false>(p, tm, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -31,7 +31,17 @@ constexpr int kScaleTileBytes = kTileRows * 2;            // 256
 enum WeightFormat : int {
   kFmtInt4G128 = 0,   // Krasis symmetric INT4, group 128
   kFmtInt8G128 = 1,   // Krasis symmetric INT8, group 128
+  kFmtQ8_0 = 2,       // GGUF Q8_0 blocks (fp16 d + 32 x i8), re-tiled losslessly
+  kFmtQ4_K = 3,       // GGUF Q4_K super-blocks (fp16 d, dmin, 6-bit scales/mins, 4-bit quants), re-tiled losslessly
 };
+
+// GGUF tile blobs are self-contained (block scales travel with the quants):
+//   Q8_0 (128 rows x 64 K): [quarter 0..3][row][16 B] int8 (8192 B) | [row][2] fp16 d of the two 32-element blocks (512 B)
+//   Q4_K (128 rows x 64 K = one 64-element chunk j of the 256-element super-block, src/gguf.rs:681-738):
+//        [half 0..1][row][16 B] qs bytes (byte l: low nibble = element l, high nibble = element 32+l) (4096 B)
+//        | [row][8 B] = fp16 d, fp16 dmin, u8 sc_lo, mn_lo, sc_hi, mn_hi (get_scale_min_k4 already applied) (1024 B)
+constexpr int kQ8_0TileBytes = kTileRows * kBlockK + kTileRows * 4;   // 8704
+constexpr int kQ4KTileBytes = kTileRows * kBlockK / 2 + kTileRows * 8; // 5120
 
 // One unit of grouped-GEMM work along the token axis: a run of <= kMaxChunkTokens sorted slots of one expert.
 struct ChunkDesc {

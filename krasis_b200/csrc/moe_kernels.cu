@@ -356,6 +356,69 @@ __global__ void repack_scales_kernel(const uint16_t* __restrict__ src, uint16_t*
   dst[i] = src[((long long)e * N + tile * kTileRows + row) * G + g];
 }
 
+// GGUF re-tiling (lossless): rows come from `a` (first n_a rows, e.g. gate) then `b` (e.g. up); src rows are native
+// GGUF block rows [N][K/bs * bb] (src/gguf_kernels.rs:9).  One thread per destination (expert, tile, k-block, row).
+__device__ __forceinline__ void k4_scale_min(int j, const uint8_t* sc, uint8_t& s, uint8_t& m) {   // src/gguf.rs:666-674
+  if (j < 4) {
+    s = sc[j] & 63;
+    m = sc[j + 4] & 63;
+  } else {
+    s = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4);
+    m = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4);
+  }
+}
+
+__global__ void retile_gguf_kernel(int fmt, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n_a,
+                                   uint8_t* __restrict__ dst, int E, int N, int K) {
+  const int nkb = K / kBlockK, ntile = N / kTileRows;
+  const long long total = (long long)E * ntile * nkb * kTileRows;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int row = (int)(i % kTileRows);
+  const int kb = (int)((i / kTileRows) % nkb);
+  const int tile = (int)((i / kTileRows / nkb) % ntile);
+  const int e = (int)(i / kTileRows / nkb / ntile);
+  const int n = tile * kTileRows + row;
+  const bool from_a = n < n_a;
+  const int n_src = from_a ? n : n - n_a, rows_src = from_a ? n_a : N - n_a;
+  if (fmt == kFmtQ8_0) {
+    const long long row_bytes = (long long)K / 32 * 34;
+    const uint8_t* src = (from_a ? a : b) + ((long long)e * rows_src + n_src) * row_bytes + (long long)kb * 2 * 34;
+    uint8_t* blob = dst + (((long long)e * ntile + tile) * nkb + kb) * kQ8_0TileBytes;
+    for (int blk = 0; blk < 2; ++blk) {
+      const uint8_t* sb = src + blk * 34;
+      blob[kTileRows * kBlockK + row * 4 + blk * 2] = sb[0];
+      blob[kTileRows * kBlockK + row * 4 + blk * 2 + 1] = sb[1];
+      for (int l = 0; l < 32; ++l) {
+        const int k = blk * 32 + l;                      // element within the 64-wide k-block
+        blob[(k / 16) * 2048 + row * 16 + (k % 16)] = sb[2 + l];
+      }
+    }
+  } else {   // Q4_K
+    const long long row_bytes = (long long)K / 256 * 144;
+    const uint8_t* sb = (from_a ? a : b) + ((long long)e * rows_src + n_src) * row_bytes + (long long)(kb / 4) * 144;
+    const int j = kb % 4;
+    uint8_t* blob = dst + (((long long)e * ntile + tile) * nkb + kb) * kQ4KTileBytes;
+    const uint8_t* qs = sb + 16 + j * 32;
+    for (int l = 0; l < 32; ++l) blob[(l / 16) * 2048 + row * 16 + (l % 16)] = qs[l];
+    uint8_t* hdr = blob + kTileRows * kBlockK / 2 + row * 8;
+    hdr[0] = sb[0]; hdr[1] = sb[1]; hdr[2] = sb[2]; hdr[3] = sb[3];
+    uint8_t s0, m0, s1, m1;
+    k4_scale_min(2 * j, sb + 4, s0, m0);
+    k4_scale_min(2 * j + 1, sb + 4, s1, m1);
+    hdr[4] = s0; hdr[5] = m0; hdr[6] = s1; hdr[7] = m1;
+  }
+}
+
+cudaError_t launch_retile_gguf(int fmt, const void* a, const void* b, int n_a, void* dst, int E, int N, int K,
+                               cudaStream_t s) {
+  if (N % kTileRows || K % kBlockK || (fmt == kFmtQ4_K && K % 256) || (fmt != kFmtQ4_K && fmt != kFmtQ8_0)) return cudaErrorInvalidValue;
+  const long long total = (long long)E * (N / kTileRows) * (K / kBlockK) * kTileRows;
+  retile_gguf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(fmt, (const uint8_t*)a, (const uint8_t*)b, n_a,
+                                                                    (uint8_t*)dst, E, N, K);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------

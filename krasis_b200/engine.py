@@ -48,6 +48,7 @@ class KrasisEngine:
 
     def __init__(self, *, hidden_size: int, moe_intermediate_size: int, n_routed_experts: int,
                  num_experts_per_tok: int, num_moe_layers: int, num_bits: int = 4, group_size: int = 128,
+                 gguf_gate_up_type: Optional[str] = None, gguf_down_type: Optional[str] = None,
                  rank: int = 0, num_ranks: int = 1, scoring_func: str = "softmax", norm_topk_prob: bool = False,
                  routed_scaling_factor: float = 1.0, max_tokens: int = 8192, device: int = 0):
         if num_bits not in (4, 8):
@@ -57,10 +58,17 @@ class KrasisEngine:
         if scoring_func not in _SCORING:
             raise ValueError(f"unknown scoring_func {scoring_func!r}")
         self._lib = capi.load()
+        gg = {"Q8_0": capi.FMT_GGUF_Q8_0, "Q4_K": capi.FMT_GGUF_Q4_K}
+        if gguf_gate_up_type is not None:        # gguf_native=True in KrasisEngine.load (src/moe.rs:1538): keep GGUF blocks
+            if gguf_gate_up_type not in gg or (gguf_down_type or gguf_gate_up_type) not in gg:
+                raise ValueError("GGUF expert types supported on the GPU path: Q4_K, Q8_0")
+            f13, f2 = gg[gguf_gate_up_type], gg[gguf_down_type or gguf_gate_up_type]
+        else:
+            f13, f2 = (capi.FMT_INT4_G128 if num_bits == 4 else capi.FMT_INT8_G128), -1
+        self._gguf = gguf_gate_up_type is not None
         self._cfg = capi.Config(hidden_size, moe_intermediate_size, n_routed_experts, num_experts_per_tok,
-                                num_moe_layers, capi.FMT_INT4_G128 if num_bits == 4 else capi.FMT_INT8_G128,
-                                rank, num_ranks, _SCORING[scoring_func], int(bool(norm_topk_prob)),
-                                float(routed_scaling_factor), max_tokens, device)
+                                num_moe_layers, f13, rank, num_ranks, _SCORING[scoring_func], int(bool(norm_topk_prob)),
+                                float(routed_scaling_factor), max_tokens, device, f2)
         self._h = C.c_void_p()
         capi.check(self._lib.kb2_create(C.byref(self._cfg), C.byref(self._h)))
         self._num_bits, self._group_size = num_bits, group_size
@@ -111,6 +119,25 @@ class KrasisEngine:
                 raise ValueError(f"{name}: expected shape {shp}, got {tuple(a.shape)}")   # moe.rs:2285-2300
             arrs.append(a)
         capi.check(self._lib.kb2_load_experts_host(self._h, moe_layer_idx, *[a.ctypes.data for a in arrs]))
+
+    def load_gguf_layer(self, moe_layer_idx: int, gate: np.ndarray, up: np.ndarray, down: np.ndarray):
+        """Native GGUF expert blocks of the LOCAL experts: gate/up uint8 [E, I, row_bytes(H)], down uint8 [E, H, row_bytes(I)]
+        (blk.{L}.ffn_{gate,up,down}_exps.weight sliced per expert, src/weights/mod.rs:3439-3488)."""
+        if not self._gguf:
+            raise capi.Kb2Error("engine was not created with gguf_gate_up_type")
+        E = self.expert_end - self.expert_start
+        H, I = self._cfg.hidden_size, self._cfg.moe_intermediate_size
+        rb = {capi.FMT_GGUF_Q8_0: lambda k: k // 32 * 34, capi.FMT_GGUF_Q4_K: lambda k: k // 256 * 144}
+        f13 = self._cfg.weight_format
+        f2 = self._cfg.w2_weight_format if self._cfg.w2_weight_format >= 0 else f13
+        want = ((E, I, rb[f13](H)), (E, I, rb[f13](H)), (E, H, rb[f2](I)))
+        arrs = []
+        for name, a, shp in zip(("gate", "up", "down"), (gate, up, down), want):
+            a = np.ascontiguousarray(a, dtype=np.uint8)
+            if tuple(a.shape) != shp:
+                raise ValueError(f"{name}: expected uint8 {shp}, got {tuple(a.shape)}")
+            arrs.append(a)
+        capi.check(self._lib.kb2_load_experts_gguf_host(self._h, moe_layer_idx, *[a.ctypes.data for a in arrs]))
 
     def attach_tiled_layer(self, moe_layer_idx: int, w13_q: torch.Tensor, w13_s: torch.Tensor,
                            w2_q: torch.Tensor, w2_s: torch.Tensor):

@@ -27,19 +27,19 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_config_struct_matches_header(lib):
     from krasis_b200 import capi
-    assert C.sizeof(capi.Config) == 13 * 4
+    assert C.sizeof(capi.Config) == 14 * 4
     assert lib.kb2_version().decode().startswith("krasis_b200")
 
 
 def test_create_validates_shapes_like_the_reference(lib):
     from krasis_b200 import capi
     h = C.c_void_p()
-    bad = capi.Config(2000, 512, 64, 6, 1, 0, 0, 1, 0, 0, 1.0, 16, 0)        # H not a multiple of 256
+    bad = capi.Config(2000, 512, 64, 6, 1, 0, 0, 1, 0, 0, 1.0, 16, 0, -1)    # H not a multiple of 256
     assert lib.kb2_create(C.byref(bad), C.byref(h)) == capi.KB2_ERR_VALUE
     assert b"hidden_size" in lib.kb2_last_error()
-    bad = capi.Config(2048, 512, 64, 6, 1, 7, 0, 1, 0, 0, 1.0, 16, 0)        # unknown weight format
+    bad = capi.Config(2048, 512, 64, 6, 1, 7, 0, 1, 0, 0, 1.0, 16, 0, -1)    # unknown weight format
     assert lib.kb2_create(C.byref(bad), C.byref(h)) == capi.KB2_ERR_VALUE
-    bad = capi.Config(2048, 512, 64, 6, 1, 0, 3, 2, 0, 0, 1.0, 16, 0)        # rank >= num_ranks
+    bad = capi.Config(2048, 512, 64, 6, 1, 0, 3, 2, 0, 0, 1.0, 16, 0, -1)    # rank >= num_ranks
     assert lib.kb2_create(C.byref(bad), C.byref(h)) == capi.KB2_ERR_VALUE
 
 
@@ -49,7 +49,7 @@ def test_no_cpu_fallback_without_gpu(lib):
         pytest.skip("GPU present")
     from krasis_b200 import capi, KrasisEngine
     h = C.c_void_p()
-    ok = capi.Config(2048, 512, 64, 6, 1, 0, 0, 1, 0, 0, 1.0, 16, 0)
+    ok = capi.Config(2048, 512, 64, 6, 1, 0, 0, 1, 0, 0, 1.0, 16, 0, -1)
     assert lib.kb2_create(C.byref(ok), C.byref(h)) == capi.KB2_ERR_CUDA
     assert b"no CPU fallback" in lib.kb2_last_error()
     with pytest.raises(capi.Kb2Error):

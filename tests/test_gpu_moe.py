@@ -169,6 +169,25 @@ def test_moe_forward_matches_oracle(bits, E, H, I, k, M, skew):
     assert_close_bf16(to_np(out), want)
 
 
+@pytest.mark.parametrize("gu,dn", [("Q4_K", "Q8_0"), ("Q8_0", "Q8_0"), ("Q4_K", "Q4_K")])
+def test_moe_forward_native_gguf_blocks(gu, dn):
+    """GGUF expert tensors consumed as native blocks on the GPU (north_star: Q4_K / Q8_0).  The re-tiling is lossless and
+    the in-kernel dequant is bit-exact w.r.t. src/gguf.rs (W = bf16(dequant)), so the usual MoE tolerance applies."""
+    from krasis_b200 import KrasisEngine
+    from oracle import gguf_blocks as G
+    T = {"Q4_K": G.GGML_Q4_K, "Q8_0": G.GGML_Q8_0}
+    rng = np.random.default_rng(31)
+    E, H, I, k, M = 6, 512, 256, 2, 230
+    lay = omoe.make_gguf_layer(rng, E, H, I, gate_up_type=T[gu], down_type=T[dn])
+    x = round_bf16(rng.normal(0, 1, (M, H)).astype(np.float32))
+    ids, w = router.route_from_logits(rng.normal(0, 1, (M, E)).astype(np.float32), k, norm_topk_prob=True)
+    eng = KrasisEngine(hidden_size=H, moe_intermediate_size=I, n_routed_experts=E, num_experts_per_tok=k, num_moe_layers=1,
+                       max_tokens=M, gguf_gate_up_type=gu, gguf_down_type=dn)
+    eng.load_gguf_layer(0, lay.gate, lay.up, lay.down)
+    out = eng.moe_forward(0, bf16_t(x), torch.from_numpy(ids).cuda(), torch.from_numpy(w).cuda(), routed_only=True)
+    assert_close_bf16(to_np(out), omoe.moe_forward_gpu_path(lay, x, ids, w))
+
+
 def test_moe_scaling_and_shared_add():
     rng = np.random.default_rng(11)
     layer = omoe.make_int_layer(rng, 8, 256, 128)
