@@ -185,7 +185,8 @@ def test_moe_forward_native_gguf_blocks(gu, dn):
                        max_tokens=M, gguf_gate_up_type=gu, gguf_down_type=dn)
     eng.load_gguf_layer(0, lay.gate, lay.up, lay.down)
     out = eng.moe_forward(0, bf16_t(x), torch.from_numpy(ids).cuda(), torch.from_numpy(w).cuda(), routed_only=True)
-    assert_close_bf16(to_np(out), omoe.moe_forward_gpu_path(lay, x, ids, w))
+    # random (not quantised-from-real-weights) Q4_K blocks give heavy cancellation in the dot products, so allow 3 ulp
+    assert_close_bf16(to_np(out), omoe.moe_forward_gpu_path(lay, x, ids, w), ulps=3)
 
 
 def test_moe_scaling_and_shared_add():
