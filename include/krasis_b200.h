@@ -90,6 +90,15 @@ KB2_API size_t kb2_tiled_bytes(const kb2_engine* e, int which);
 KB2_API int kb2_load_experts_host(kb2_engine* e, int moe_layer_idx, const void* w13_q_host, const void* w13_s_host,
                           const void* w2_q_host, const void* w2_s_host);
 
+/* The Krasis group quantiser itself, on the device and bit-exact: quantize_int4 / quantize_int8
+ * (src/weights/marlin.rs:145-207, 65-114).  w [rows][K] bf16 -> q ([rows][K/8] u32 for 4 bits | [rows][K] i8 for 8 bits) and
+ * scales [rows][K/128] raw bf16 — the reference quantiser's output layout.  K % 128 == 0 (marlin.rs:152). */
+KB2_API int kb2_quantize_group_dev(const void* w_bf16_dev, int32_t num_bits, void* q_dev, void* scales_dev, int64_t rows,
+                                   int32_t k_cols, int32_t device, void* stream);
+/* kb2_load_experts_host with DEVICE pointers (e.g. straight out of kb2_quantize_group_dev): re-tiles and owns the result. */
+KB2_API int kb2_load_experts_dev(kb2_engine* e, int moe_layer_idx, const void* w13_q_dev, const void* w13_s_dev,
+                                 const void* w2_q_dev, const void* w2_s_dev, void* stream);
+
 /* GGUF expert tensors kept as native blocks (new capability; in the reference GGUF feeds only the CPU experts,
  * src/weights/mod.rs:3251-3585, src/gguf_kernels.rs:690-756).  gate/up: [E_local][I][row_bytes(H)], down: [E_local][H][row_bytes(I)]
  * with the block types given by weight_format / w2_weight_format; rows are [N][K] with K contiguous in blocks

@@ -46,6 +46,9 @@ SIGNATURES = {
     "kb2_expert_range": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "kb2_tiled_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "kb2_load_experts_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
+    "kb2_quantize_group_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                         C.c_void_p]),
+    "kb2_load_experts_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5),
     "kb2_load_experts_gguf_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 3),
     "kb2_attach_experts_tiled_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
     "kb2_retile_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),

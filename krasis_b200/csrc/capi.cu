@@ -28,6 +28,7 @@ cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, i
                            int* sorted_ids, const void* x, void* x_sorted, int H, cudaStream_t s);
 cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
                            const void* shared, void* out, cudaStream_t s);
+cudaError_t launch_quantize_group(const void* w, int bits, void* q_out, void* scales, long long rows, int K, cudaStream_t s);
 cudaError_t launch_retile_gguf(int fmt, const void* a, const void* b, int n_a, void* dst, int E, int N, int K,
                                cudaStream_t s);
 cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,
@@ -288,6 +289,37 @@ KB2_API int kb2_load_experts_host(kb2_engine* e, int layer, const void* w13_q, c
   CUDA_TRY(cudaDeviceSynchronize());
   for (int i = 0; i < 4; ++i) cudaFree(tmp[i]);
   if (r1 != cudaSuccess || r2 != cudaSuccess) return fail(KB2_ERR_CUDA, "retile failed");
+  L.w13_q = (const uint8_t*)dst[0]; L.w13_s = (const uint8_t*)dst[1];
+  L.w2_q = (const uint8_t*)dst[2]; L.w2_s = (const uint8_t*)dst[3];
+  L.owned = true;
+  return KB2_OK;
+}
+
+KB2_API int kb2_quantize_group_dev(const void* w_bf16_dev, int32_t num_bits, void* q_dev, void* scales_dev, int64_t rows,
+                                   int32_t k_cols, int32_t device, void* stream) {
+  if (!w_bf16_dev || !q_dev || !scales_dev) return fail(KB2_ERR_VALUE, "null argument");
+  if ((num_bits != 4 && num_bits != 8) || rows <= 0 || k_cols <= 0 || k_cols % kGroup)
+    return fail(KB2_ERR_VALUE, "quantize: num_bits must be 4 or 8 and cols (%d) divisible by group_size (128)", k_cols);   // marlin.rs:152
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_quantize_group(w_bf16_dev, num_bits, q_dev, scales_dev, rows, k_cols, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_load_experts_dev(kb2_engine* e, int layer, const void* w13_q_dev, const void* w13_s_dev, const void* w2_q_dev,
+                         const void* w2_s_dev, void* stream) {
+  if (int r = check_layer(e, layer)) return r;
+  if (!w13_q_dev || !w13_s_dev || !w2_q_dev || !w2_s_dev) return fail(KB2_ERR_VALUE, "null weight pointer");
+  if (!has_scale_tiles(fmt13(e)) || fmt13(e) != fmt2(e)) return fail(KB2_ERR_STATE, "engine was created for GGUF blocks");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  LayerWeights& L = e->layers[layer];
+  free_layer(L);
+  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, fmt = e->cfg.weight_format;
+  void* dst[4];
+  for (int i = 0; i < 4; ++i) CUDA_TRY(cudaMalloc(&dst[i], tiled_bytes(e, i)));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(launch_repack(fmt, w13_q_dev, w13_s_dev, dst[0], dst[1], e->e_local, 2 * I, H, s));
+  CUDA_TRY(launch_repack(fmt, w2_q_dev, w2_s_dev, dst[2], dst[3], e->e_local, H, I, s));
+  e->launches += 4;
   L.w13_q = (const uint8_t*)dst[0]; L.w13_s = (const uint8_t*)dst[1];
   L.w2_q = (const uint8_t*)dst[2]; L.w2_s = (const uint8_t*)dst[3];
   L.owned = true;

@@ -356,6 +356,63 @@ __global__ void repack_scales_kernel(const uint16_t* __restrict__ src, uint16_t*
   dst[i] = src[((long long)e * N + tile * kTileRows + row) * G + g];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Krasis symmetric group quantiser on the device — bit-exact restatement of src/weights/marlin.rs:145-207 (INT4) and
+// :65-114 (INT8): per row and 128-column group  scale = bf16_rne(amax / qmax)  (1.0 if amax == 0);
+// q = clamp(round_half_away(w * (1 / f32(scale))), qmin, qmax).  All steps are single IEEE f32 operations.
+// One warp per (row, group); output in the reference quantiser's layout (packed [N][K/8] u32 | i8 [N][K], scales [N][K/128]).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) quantize_group_kernel(const __nv_bfloat16* __restrict__ w, int bits,
+                                                             void* __restrict__ q_out, uint16_t* __restrict__ scales,
+                                                             long long rows, int K) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, G = K / kGroup;
+  if (wid >= rows * G) return;
+  const long long row = wid / G;
+  const int g = (int)(wid % G);
+  const __nv_bfloat16* src = w + row * K + g * kGroup + lane * 4;
+  float v[4];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = __bfloat162float(src[i]);
+    amax = fmaxf(amax, fabsf(v[i]));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  const float qmax = bits == 4 ? 7.0f : 127.0f;
+  const float sc_f = amax == 0.f ? 1.0f : __fdiv_rn(amax, qmax);
+  const __nv_bfloat16 sc_b = __float2bfloat16_rn(sc_f);
+  const float sc = __bfloat162float(sc_b);
+  const float inv = sc == 0.f ? 0.f : __fdiv_rn(1.0f, sc);
+  int q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float r = roundf(__fmul_rn(v[i], inv));                         // f32::round: half away from zero
+    q[i] = (int)fminf(fmaxf(r, bits == 4 ? -8.f : -128.f), qmax);
+  }
+  if (lane == 0) scales[row * G + g] = __bfloat16_as_ushort(sc_b);
+  if (bits == 4) {
+    uint32_t nib = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nib |= (uint32_t)((q[i] + 8) & 0xF) << (4 * i);   // 4 nibbles of this lane
+    const uint32_t hi = __shfl_down_sync(0xffffffffu, nib, 1);                      // odd lane's nibbles -> upper half
+    if ((lane & 1) == 0)
+      reinterpret_cast<uint32_t*>(q_out)[row * (K / 8) + g * (kGroup / 8) + (lane >> 1)] = nib | (hi << 16);
+  } else {
+    char4 c = make_char4((signed char)q[0], (signed char)q[1], (signed char)q[2], (signed char)q[3]);
+    reinterpret_cast<char4*>(q_out)[(row * K + g * kGroup) / 4 + lane] = c;
+  }
+}
+
+cudaError_t launch_quantize_group(const void* w, int bits, void* q_out, void* scales, long long rows, int K, cudaStream_t s) {
+  if ((bits != 4 && bits != 8) || K % kGroup || rows <= 0) return cudaErrorInvalidValue;
+  const long long warps = rows * (K / kGroup);
+  quantize_group_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)w, bits, q_out,
+                                                                            (uint16_t*)scales, rows, K);
+  return cudaGetLastError();
+}
+
 // GGUF re-tiling (lossless): rows come from `a` (first n_a rows, e.g. gate) then `b` (e.g. up); src rows are native
 // GGUF block rows [N][K/bs * bb] (src/gguf_kernels.rs:9).  One thread per destination (expert, tile, k-block, row).
 __device__ __forceinline__ void k4_scale_min(int j, const uint8_t* sc, uint8_t& s, uint8_t& m) {   // src/gguf.rs:666-674

@@ -120,6 +120,35 @@ class KrasisEngine:
             arrs.append(a)
         capi.check(self._lib.kb2_load_experts_host(self._h, moe_layer_idx, *[a.ctypes.data for a in arrs]))
 
+    def quantize_group(self, w_bf16: torch.Tensor, num_bits: Optional[int] = None):
+        """Krasis symmetric g128 quantiser on the device (src/weights/marlin.rs:145-207 / :65-114), bit-exact.
+        w [..., K] bf16 -> (q [..., K/8] int32 | [..., K] int8, scales [..., K/128] raw-bf16 int16)."""
+        bits = num_bits or self._num_bits
+        if w_bf16.dtype != torch.bfloat16 or not w_bf16.is_cuda or not w_bf16.is_contiguous():
+            raise ValueError("quantize_group: expected a contiguous CUDA bf16 tensor")
+        K = w_bf16.shape[-1]
+        rows = w_bf16.numel() // K
+        lead = tuple(w_bf16.shape[:-1])
+        q = (torch.empty(lead + (K // 8,), dtype=torch.int32, device=w_bf16.device) if bits == 4
+             else torch.empty(lead + (K,), dtype=torch.int8, device=w_bf16.device))
+        sc = torch.empty(lead + (K // 128,), dtype=torch.int16, device=w_bf16.device)
+        capi.check(self._lib.kb2_quantize_group_dev(w_bf16.data_ptr(), bits, q.data_ptr(), sc.data_ptr(), rows, K,
+                                                    w_bf16.device.index or 0, _stream_ptr(w_bf16.device)))
+        return q, sc
+
+    def load_bf16_layer(self, moe_layer_idx: int, w13_bf16: torch.Tensor, w2_bf16: torch.Tensor):
+        """HF BF16 experts ([E_local,2I,H] gate rows first, [E_local,H,I]) -> quantise on device -> B200 tiles
+        (the load_from_hf step of src/weights/mod.rs:5049-5091 without the Marlin repack)."""
+        E = self.expert_end - self.expert_start
+        H, I = self._cfg.hidden_size, self._cfg.moe_intermediate_size
+        if tuple(w13_bf16.shape) != (E, 2 * I, H) or tuple(w2_bf16.shape) != (E, H, I):
+            raise ValueError(f"load_bf16_layer: expected [{E},{2*I},{H}] and [{E},{H},{I}]")
+        q13, s13 = self.quantize_group(w13_bf16.to(self.device).contiguous())
+        q2, s2 = self.quantize_group(w2_bf16.to(self.device).contiguous())
+        capi.check(self._lib.kb2_load_experts_dev(self._h, moe_layer_idx, q13.data_ptr(), s13.data_ptr(), q2.data_ptr(),
+                                                  s2.data_ptr(), _stream_ptr(self.device)))
+        torch.cuda.synchronize(self.device)
+
     def load_gguf_layer(self, moe_layer_idx: int, gate: np.ndarray, up: np.ndarray, down: np.ndarray):
         """Native GGUF expert blocks of the LOCAL experts: gate/up uint8 [E, I, row_bytes(H)], down uint8 [E, H, row_bytes(I)]
         (blk.{L}.ffn_{gate,up,down}_exps.weight sliced per expert, src/weights/mod.rs:3439-3488)."""

@@ -1,0 +1,109 @@
+"""Device quantiser (bit-exact vs the oracle's restatement of marlin.rs) and the safetensors / GGUF load paths."""
+import json
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bf16 as B
+from oracle import quant as Q
+from oracle import moe as OM
+from oracle import gguf_blocks as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_tensor(u16: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(u16.view(np.int16)).view(torch.bfloat16)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_device_quantiser_bit_exact(bits):
+    from krasis_b200 import KrasisEngine
+    rng = np.random.default_rng(bits)
+    rows, K = 257, 1024
+    w = rng.normal(0, 0.05, (rows, K)).astype(np.float32)
+    w[3, :128] = 0.0                                   # all-zero group -> scale 1.0 path (marlin.rs:176)
+    w[5, 128:256] = 1e-30                              # tiny amax
+    w[7, 0] = 300.0                                    # large outlier
+    # exact half-way cases: w = (n + 0.5) * scale
+    w[9, :128] = (np.arange(128) % 15 - 7 + 0.5) * 0.125
+    wb = B.f32_to_bf16_bits(w)
+    eng = KrasisEngine(hidden_size=256, moe_intermediate_size=128, n_routed_experts=8, num_experts_per_tok=2,
+                       num_moe_layers=1, num_bits=bits, max_tokens=64)
+    q, s = eng.quantize_group(_bf16_tensor(wb).cuda(), bits)
+    torch.cuda.synchronize()
+    if bits == 4:
+        qr, sr = Q.quantize_int4(wb)
+    else:
+        qr, sr = Q.quantize_int8(wb)
+    assert np.array_equal(s.cpu().numpy().view(np.uint16), sr.view(np.uint16))
+    assert np.array_equal(q.cpu().numpy().view(qr.dtype), qr)
+
+
+def _write_safetensors(path, tensors):
+    hdr, blob, off = {}, [], 0
+    for name, arr in tensors.items():
+        raw = np.ascontiguousarray(arr).tobytes()
+        hdr[name] = {"dtype": "BF16", "shape": list(arr.shape), "data_offsets": [off, off + len(raw)]}
+        blob.append(raw)
+        off += len(raw)
+    h = json.dumps(hdr).encode()
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(h)) + h + b"".join(blob))
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_safetensors_to_moe_matches_oracle(tmp_path, bits):
+    """HF BF16 checkpoint -> loader -> device quantiser -> tiles -> MoE forward == oracle on oracle-quantised weights."""
+    from krasis_b200 import KrasisEngine
+    from krasis_b200.loader import load_experts_from_safetensors
+    from tests.test_gpu_moe import assert_close_bf16, bf16_t, to_np
+    rng = np.random.default_rng(10 + bits)
+    E, H, I, k, M = 8, 256, 128, 2, 96
+    qf = Q.quantize_int4 if bits == 4 else Q.quantize_int8
+    t, qs = {}, [[], [], [], []]
+    for e in range(E):
+        w13 = B.f32_to_bf16_bits(rng.normal(0, 0.02, (2 * I, H)).astype(np.float32))
+        w2 = B.f32_to_bf16_bits(rng.normal(0, 0.02, (H, I)).astype(np.float32))
+        base = f"model.layers.1.mlp.experts.{e}."
+        t[base + "gate_proj.weight"], t[base + "up_proj.weight"], t[base + "down_proj.weight"] = w13[:I], w13[I:], w2
+        q, sc = qf(w13); qs[0].append(q); qs[1].append(sc)
+        q, sc = qf(w2); qs[2].append(q); qs[3].append(sc)
+    lay = OM.Int4Layer(*[np.stack(a) for a in qs], bits, 128)
+    _write_safetensors(tmp_path / "model.safetensors", t)
+    eng = KrasisEngine(hidden_size=H, moe_intermediate_size=I, n_routed_experts=E, num_experts_per_tok=k,
+                       num_moe_layers=1, num_bits=bits, max_tokens=M)
+    load_experts_from_safetensors(eng, str(tmp_path), first_k_dense=1)
+    x = B.round_bf16(rng.normal(0, 1, (M, H)).astype(np.float32))
+    ids = np.stack([rng.choice(E, k, replace=False) for _ in range(M)]).astype(np.int32)
+    wts = rng.uniform(0.1, 1, (M, k)).astype(np.float32)
+    out = eng.moe_forward(0, bf16_t(x), torch.from_numpy(ids).cuda(), torch.from_numpy(wts).cuda(), routed_only=True)
+    assert_close_bf16(to_np(out), OM.moe_forward_gpu_path(lay, x, ids, wts))
+
+
+def test_gguf_file_to_moe_matches_oracle(tmp_path):
+    gguf = pytest.importorskip("gguf")
+    from krasis_b200 import KrasisEngine
+    from krasis_b200.loader import load_experts_from_gguf
+    from tests.test_gpu_moe import assert_close_bf16, bf16_t, to_np
+    rng = np.random.default_rng(5)
+    E, H, I, k, M = 4, 256, 256, 2, 64
+    lay = OM.make_gguf_layer(rng, E, H, I, G.GGML_Q4_K, G.GGML_Q8_0)
+    path = str(tmp_path / "m.gguf")
+    w = gguf.GGUFWriter(path, "llama")
+    w.add_uint32("llama.block_count", 1)
+    Qt = gguf.GGMLQuantizationType
+    w.add_tensor("blk.0.ffn_gate_exps.weight", lay.gate, raw_shape=lay.gate.shape, raw_dtype=Qt.Q4_K)
+    w.add_tensor("blk.0.ffn_up_exps.weight", lay.up, raw_shape=lay.up.shape, raw_dtype=Qt.Q4_K)
+    w.add_tensor("blk.0.ffn_down_exps.weight", lay.down, raw_shape=lay.down.shape, raw_dtype=Qt.Q8_0)
+    w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    eng = KrasisEngine(hidden_size=H, moe_intermediate_size=I, n_routed_experts=E, num_experts_per_tok=k,
+                       num_moe_layers=1, gguf_gate_up_type="Q4_K", gguf_down_type="Q8_0", max_tokens=M)
+    load_experts_from_gguf(eng, path)
+    x = B.round_bf16(rng.normal(0, 1, (M, H)).astype(np.float32))
+    ids = np.stack([rng.choice(E, k, replace=False) for _ in range(M)]).astype(np.int32)
+    wts = rng.uniform(0.1, 1, (M, k)).astype(np.float32)
+    out = eng.moe_forward(0, bf16_t(x), torch.from_numpy(ids).cuda(), torch.from_numpy(wts).cuda(), routed_only=True)
+    assert_close_bf16(to_np(out), OM.moe_forward_gpu_path(lay, x, ids, wts), ulps=3)
