@@ -12,6 +12,7 @@
 //   gdn_post_kernel        gated RMSNorm (:987-1004)
 // The in/out projections are dense_gemm_kernel (tcgen05).  All delta-rule math is fp32 like the reference.
 #include "moe_common.cuh"
+#include "ptx.cuh"
 
 namespace kb2 {
 
@@ -131,29 +132,39 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// operand element -> TF32 hi (and lo when SPLIT); BF16 bits shifted up ARE a TF32 value (no cvt, never split)
+template <bool SPLIT>
+__device__ __forceinline__ void ld_tf32(const float* p, uint32_t& hi, uint32_t& lo) {
+  const float x = *p;
+  hi = to_tf32(x);
+  if (SPLIT) lo = to_tf32(x - __uint_as_float(hi));
+}
+template <bool SPLIT>
+__device__ __forceinline__ void ld_tf32(const __nv_bfloat16* p, uint32_t& hi, uint32_t& lo) {
+  static_assert(!SPLIT, "BF16 operands are exact in TF32");
+  hi = (uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16;
+}
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src_gmem, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+               "r"(valid ? 16 : 0)
+               : "memory");
+}
 // c[NT][4] (16 rows x NT*8 cols) += A[16 x K] * B[K x NT*8];  A(r,k) = A[r*sar + k*sak], B(k,n) = B[k*sbk + n*sbn]
-template <int NT, bool SPLIT_A, bool SPLIT_B>
-__device__ __forceinline__ void warp_mma_tiles(float (&c)[NT][4], const float* __restrict__ A, int sar, int sak,
-                                               const float* __restrict__ B, int sbk, int sbn, int k_begin, int k_end) {
+template <int NT, bool SPLIT_A, bool SPLIT_B, typename TA, typename TB>
+__device__ __forceinline__ void warp_mma_tiles(float (&c)[NT][4], const TA* __restrict__ A, int sar, int sak,
+                                               const TB* __restrict__ B, int sbk, int sbn, int k_begin, int k_end) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   for (int k0 = k_begin; k0 < k_end; k0 += 8) {
-    float af[4] = {A[g * sar + (k0 + t) * sak], A[(g + 8) * sar + (k0 + t) * sak], A[g * sar + (k0 + t + 4) * sak],
-                   A[(g + 8) * sar + (k0 + t + 4) * sak]};
     uint32_t ah[4], al[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ah[i] = to_tf32(af[i]);
-      if (SPLIT_A) al[i] = to_tf32(af[i] - __uint_as_float(ah[i]));
-    }
+    ld_tf32<SPLIT_A>(A + g * sar + (k0 + t) * sak, ah[0], al[0]);
+    ld_tf32<SPLIT_A>(A + (g + 8) * sar + (k0 + t) * sak, ah[1], al[1]);
+    ld_tf32<SPLIT_A>(A + g * sar + (k0 + t + 4) * sak, ah[2], al[2]);
+    ld_tf32<SPLIT_A>(A + (g + 8) * sar + (k0 + t + 4) * sak, ah[3], al[3]);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      const float bf[2] = {B[(k0 + t) * sbk + (nt * 8 + g) * sbn], B[(k0 + t + 4) * sbk + (nt * 8 + g) * sbn]};
       uint32_t bh[2], bl[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        bh[i] = to_tf32(bf[i]);
-        if (SPLIT_B) bl[i] = to_tf32(bf[i] - __uint_as_float(bh[i]));
-      }
+      ld_tf32<SPLIT_B>(B + (k0 + t) * sbk + (nt * 8 + g) * sbn, bh[0], bl[0]);
+      ld_tf32<SPLIT_B>(B + (k0 + t + 4) * sbk + (nt * 8 + g) * sbn, bh[1], bl[1]);
       if (SPLIT_A) mma_tf32(c[nt], al, bh);
       if (SPLIT_B) mma_tf32(c[nt], ah, bl);
       mma_tf32(c[nt], ah, bh);
@@ -162,179 +173,279 @@ __device__ __forceinline__ void warp_mma_tiles(float (&c)[NT][4], const float* _
 }
 
 // ------------------------------------------------------------------------------------------------
-// chunk prepare: grid (n_chunks, nv), 256 threads.  dk, dv <= 128, dk + dv == 256 is NOT required.
+// chunk prepare: grid (n_chunks, nv), 256 threads, 2 CTAs / SM (~100 KB smem each).  dk, dv <= 128, multiples of 16.
 // outputs per (head, chunk): vcorr [64][dv], kcd [64][dk], intra [64][64], gcum [64]   (all fp32)
+//   smem: sk bf16 [64][dk+8] | sA f32 [64][68] | sB f32 [64][dv+dk+8] (its head doubles as the q tile until Q K^T is done)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gdn_chunk_prepare_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qn,
-                                                                const __nv_bfloat16* __restrict__ kn,
-                                                                const __nv_bfloat16* __restrict__ vc,
-                                                                const float* __restrict__ beta,
-                                                                const float* __restrict__ g, int M, int n_chunks,
-                                                                float* __restrict__ vcorr, float* __restrict__ kcd,
-                                                                float* __restrict__ intra, float* __restrict__ gcum_out) {
-  extern __shared__ float sm[];
+constexpr int kLdA = kGC + 4;   // [row][k] fp32 operands: row stride = 4 mod 32 words -> conflict-free A fragments
+
+__global__ void __launch_bounds__(256, 2) gdn_chunk_prepare_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qn,
+                                                                   const __nv_bfloat16* __restrict__ kn,
+                                                                   const __nv_bfloat16* __restrict__ vc,
+                                                                   const float* __restrict__ beta,
+                                                                   const float* __restrict__ g, int M, int n_chunks,
+                                                                   float* __restrict__ vcorr, float* __restrict__ kcd,
+                                                                   float* __restrict__ intra,
+                                                                   float* __restrict__ gcum_out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
   const int ch = blockIdx.x, h = blockIdx.y, r = d.nv / d.nk, kh = h / r;
   const int dk = d.dk, dv = d.dv, kd = d.nk * dk, vd = d.nv * dv;
-  const int ldk = dk + 4, ldb = dv + dk + 8, ldA = kGC + 4;
-  float* sq = sm;                       // [64][ldk]
-  float* sk = sq + kGC * ldk;           // [64][ldk]
-  float* sA = sk + kGC * ldk;           // [64][ldA]
-  float* sB = sA + kGC * ldA;           // [64][ldb]   right-hand sides -> solution
-  float* sg = sB + kGC * ldb;           // [64] gcum
-  float* sb = sg + kGC;                 // [64] beta
+  const int ldkb = dk + 8, ldb = dv + dk + 8;          // bf16 row stride (halves); fp32 RHS row stride (8 mod 32 words)
+  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(smraw);                   // [64][ldkb]
+  float* sA = reinterpret_cast<float*>(smraw + (size_t)kGC * ldkb * 2);          // [64][kLdA]
+  float* sB = sA + kGC * kLdA;                                                   // [64][ldb]  right-hand sides -> solution
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sB);                      // [64][ldkb] (dead before sB is written)
+  float* sg = sB + kGC * ldb;                                                    // [64] gcum
+  float* sb = sg + kGC;                                                          // [64] beta
   const int t0 = ch * kGC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-  for (int i = tid; i < kGC; i += 256) {
-    const int t = t0 + i;
-    sb[i] = t < M ? beta[(long long)t * d.nv + h] : 0.f;
-    sg[i] = t < M ? g[(long long)t * d.nv + h] : 0.f;
+  const long long hc = (long long)h * n_chunks + ch;
+  {
+    const int cpr = dk / 8;                            // 16-byte pieces per row
+    for (int idx = tid; idx < kGC * cpr; idx += 256) {
+      const int i = idx / cpr, c = (idx % cpr) * 8, t = t0 + i;
+      const bool ok = t < M;
+      const long long off = (long long)(ok ? t : 0) * kd + kh * dk + c;
+      cp_async16_zfill(sq + i * ldkb + c, qn + off, ok);
+      cp_async16_zfill(sk + i * ldkb + c, kn + off, ok);
+    }
+    cp_async_commit();
   }
-  for (int idx = tid; idx < kGC * dk; idx += 256) {
-    const int i = idx / dk, c = idx % dk, t = t0 + i;
-    sq[i * ldk + c] = t < M ? __bfloat162float(qn[(long long)t * kd + kh * dk + c]) : 0.f;
-    sk[i * ldk + c] = t < M ? __bfloat162float(kn[(long long)t * kd + kh * dk + c]) : 0.f;
+  if (tid < kGC) {
+    const int t = t0 + tid;
+    sb[tid] = t < M ? beta[(long long)t * d.nv + h] : 0.f;
+    sg[tid] = t < M ? g[(long long)t * d.nv + h] : 0.f;
   }
+  cp_async_wait<0>();
   __syncthreads();
-  if (tid == 0) {                         // cumulative sum in token order (matches torch.cumsum)
+  if (tid == 0) {                         // cumulative sum in token order (matches torch.cumsum), in registers
     float s = 0.f;
-    for (int i = 0; i < kGC; ++i) {
-      s += sg[i];
-      sg[i] = s;
+#pragma unroll
+    for (int i4 = 0; i4 < kGC / 4; ++i4) {
+      float4 v = *reinterpret_cast<float4*>(sg + i4 * 4);
+      v.x = s + v.x; v.y = v.x + v.y; v.z = v.y + v.z; v.w = v.z + v.w;
+      s = v.w;
+      *reinterpret_cast<float4*>(sg + i4 * 4) = v;
     }
   }
-  __syncthreads();
-  // right-hand sides: [ v*beta | k*beta*exp(gcum) ]
-  for (int idx = tid; idx < kGC * (dv + dk); idx += 256) {
-    const int i = idx / (dv + dk), c = idx % (dv + dk), t = t0 + i;
-    float val;
-    if (c < dv) val = t < M ? __bfloat162float(vc[(long long)t * vd + h * dv + c]) * sb[i] : 0.f;
-    else val = sk[i * ldk + (c - dv)] * sb[i] * expf(sg[i]);
-    sB[i * ldb + c] = val;
-  }
   // K K^T (warps 0-3) and Q K^T (warps 4-7): q, k hold BF16 values -> exact in TF32, fp32 accumulate
+  const int mt = warp & 3;
+  float acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  warp_mma_tiles<8, false, false>(acc, (warp < 4 ? sk : sq) + mt * 16 * ldkb, ldkb, 1, sk, 1, ldkb, 0, dk);   // B(k=c, n=j) = sk[j][c]
+  __syncthreads();                        // gcum ready; q tile dead -> sB may be written
   {
-    const int mt = warp & 3;
-    float acc[8][4];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    const float* Am = (warp < 4 ? sk : sq) + mt * 16 * ldk;
-    warp_mma_tiles<8, false, false>(acc, Am, ldk, 1, sk, 1, ldk, 0, dk);      // B(k=c, n=j) = sk[j*ldk + c]
-    float* o_intra = intra + ((long long)h * n_chunks + ch) * kGC * kGC;
+    float* o_intra = intra + hc * kGC * kGC;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = mt * 16 + gq + (e >= 2 ? 8 : 0), j = nt * 8 + 2 * tq + (e & 1);
-        const float dec = expf(sg[i] - sg[j]);
-        if (warp < 4) sA[i * ldA + j] = j < i ? -(acc[nt][e] * sb[i]) * dec : 0.f;
-        else o_intra[i * kGC + j] = j <= i ? acc[nt][e] * dec : 0.f;
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int i = mt * 16 + gq + e2 * 8, j = nt * 8 + 2 * tq;
+        const float gi = sg[i], d0 = expf(gi - sg[j]), d1 = expf(gi - sg[j + 1]);
+        const float a0 = acc[nt][e2 * 2], a1 = acc[nt][e2 * 2 + 1];
+        if (warp < 4) {
+          const float bi = sb[i];
+          *reinterpret_cast<float2*>(sA + i * kLdA + j) =
+              make_float2(j < i ? -(a0 * bi) * d0 : 0.f, j + 1 < i ? -(a1 * bi) * d1 : 0.f);
+        } else {
+          *reinterpret_cast<float2*>(o_intra + i * kGC + j) = make_float2(j <= i ? a0 * d0 : 0.f, j + 1 <= i ? a1 * d1 : 0.f);
+        }
       }
+    }
+  }
+  // right-hand sides: [ v*beta | k*beta*exp(gcum) ], 8 columns per thread step
+  {
+    const int cpr = (dv + dk) / 8;
+    for (int idx = tid; idx < kGC * cpr; idx += 256) {
+      const int i = idx / cpr, c = (idx % cpr) * 8, t = t0 + i;
+      const float bi = sb[i];
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      float f;
+      if (c < dv) {
+        if (t < M) raw = *reinterpret_cast<const uint4*>(vc + (long long)t * vd + h * dv + c);
+        f = bi;
+      } else {
+        raw = *reinterpret_cast<const uint4*>(sk + i * ldkb + (c - dv));
+        f = bi * expf(sg[i]);
+      }
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[2 * e] = __uint_as_float(w[e] << 16) * f;
+        o[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u) * f;
+      }
+      *reinterpret_cast<float4*>(sB + i * ldb + c) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(sB + i * ldb + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
   }
   __syncthreads();
   // blocked forward substitution X = (I - A)^-1 B: 16-row blocks; off-diagonal blocks on mma (3xTF32), the 16x16
-  // diagonal block sequentially (one thread per column; conflict-free, A[i][j] is a warp-wide broadcast)
+  // diagonal block in registers (one thread per column; A[i][j] is a warp-wide broadcast)
   const int ncols = dv + dk;
   for (int b = 0; b < kGC / 16; ++b) {
     if (b > 0) {
       for (int nt0 = warp * 4; nt0 * 8 < ncols; nt0 += 32) {        // 8 warps x 4 n-tiles = 256 columns per pass
-        float acc[4][4];
+        float ac[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int r0 = b * 16 + gq, c0 = (nt0 + nt) * 8 + 2 * tq;
           const bool ok = c0 < ncols;
-          acc[nt][0] = ok ? sB[r0 * ldb + c0] : 0.f;
-          acc[nt][1] = ok ? sB[r0 * ldb + c0 + 1] : 0.f;
-          acc[nt][2] = ok ? sB[(r0 + 8) * ldb + c0] : 0.f;
-          acc[nt][3] = ok ? sB[(r0 + 8) * ldb + c0 + 1] : 0.f;
+          const float2 lo = ok ? *reinterpret_cast<const float2*>(sB + r0 * ldb + c0) : make_float2(0.f, 0.f);
+          const float2 hi = ok ? *reinterpret_cast<const float2*>(sB + (r0 + 8) * ldb + c0) : make_float2(0.f, 0.f);
+          ac[nt][0] = lo.x; ac[nt][1] = lo.y; ac[nt][2] = hi.x; ac[nt][3] = hi.y;
         }
-        warp_mma_tiles<4, true, true>(acc, sA + b * 16 * ldA, ldA, 1, sB + nt0 * 8, ldb, 1, 0, b * 16);
+        warp_mma_tiles<4, true, true>(ac, sA + b * 16 * kLdA, kLdA, 1, sB + nt0 * 8, ldb, 1, 0, b * 16);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int r0 = b * 16 + gq, c0 = (nt0 + nt) * 8 + 2 * tq;
           if (c0 < ncols) {
-            sB[r0 * ldb + c0] = acc[nt][0];
-            sB[r0 * ldb + c0 + 1] = acc[nt][1];
-            sB[(r0 + 8) * ldb + c0] = acc[nt][2];
-            sB[(r0 + 8) * ldb + c0 + 1] = acc[nt][3];
+            *reinterpret_cast<float2*>(sB + r0 * ldb + c0) = make_float2(ac[nt][0], ac[nt][1]);
+            *reinterpret_cast<float2*>(sB + (r0 + 8) * ldb + c0) = make_float2(ac[nt][2], ac[nt][3]);
           }
         }
       }
       __syncthreads();
     }
     for (int c = tid; c < ncols; c += 256) {
-      for (int i = b * 16 + 1; i < b * 16 + 16; ++i) {
-        float acc = sB[i * ldb + c];
-        const float* arow = sA + i * ldA;
-        for (int j = b * 16; j < i; ++j) acc = fmaf(arow[j], sB[j * ldb + c], acc);
-        sB[i * ldb + c] = acc;
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = sB[(b * 16 + i) * ldb + c];
+#pragma unroll
+      for (int i = 1; i < 16; ++i) {
+        const float* arow = sA + (b * 16 + i) * kLdA + b * 16;
+        float a = x[i];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          if (j4 * 4 < i) {
+            const float4 av = *reinterpret_cast<const float4*>(arow + j4 * 4);
+            if (j4 * 4 + 0 < i) a = fmaf(av.x, x[j4 * 4 + 0], a);
+            if (j4 * 4 + 1 < i) a = fmaf(av.y, x[j4 * 4 + 1], a);
+            if (j4 * 4 + 2 < i) a = fmaf(av.z, x[j4 * 4 + 2], a);
+            if (j4 * 4 + 3 < i) a = fmaf(av.w, x[j4 * 4 + 3], a);
+          }
+        }
+        x[i] = a;
       }
+#pragma unroll
+      for (int i = 1; i < 16; ++i) sB[(b * 16 + i) * ldb + c] = x[i];
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < kGC * ncols; idx += 256) {
-    const int i = idx / ncols, c = idx % ncols;
-    if (c < dv) vcorr[((long long)h * n_chunks + ch) * kGC * dv + i * dv + c] = sB[i * ldb + c];
-    else kcd[((long long)h * n_chunks + ch) * kGC * dk + i * dk + (c - dv)] = sB[i * ldb + c];
+  {
+    const int cpr = ncols / 4;
+    for (int idx = tid; idx < kGC * cpr; idx += 256) {
+      const int i = idx / cpr, c = (idx % cpr) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(sB + i * ldb + c);
+      if (c < dv) *reinterpret_cast<float4*>(vcorr + hc * kGC * dv + i * dv + c) = v;
+      else *reinterpret_cast<float4*>(kcd + hc * kGC * dk + i * dk + (c - dv)) = v;
+    }
   }
-  for (int i = tid; i < kGC; i += 256) gcum_out[((long long)h * n_chunks + ch) * kGC + i] = sg[i];
+  if (tid < kGC) gcum_out[hc * kGC + tid] = sg[tid];
 }
 
 // ------------------------------------------------------------------------------------------------
-// chunk scan: grid (nv, dv/32), 256 threads; state slice S[dk][32] in smem (fp32), updated in place.
+// chunk scan: grid (nv, dv/kSV), 256 threads, one CTA per SM; state slice S[dk][kSV] in smem (fp32), updated in place.
+// The per-chunk operands (q, k bf16; k_cumdecay, intra, value_corrected slice, gcum fp32) are double-buffered with
+// cp.async: chunk c+1 streams in while chunk c runs its three mma phases.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSVMax = 32;   // widest dv slice per CTA
+constexpr int kSVMax = 32;         // widest dv slice per CTA
 constexpr int kLdS = kSVMax + 8;   // [k][n] operands: row stride = 8 mod 32 -> conflict-free B fragments
-constexpr int kLdI = kGC + 4;   // [row][k] operands: row stride = 4 mod 32 -> conflict-free A fragments
+
+struct ScanStage {                 // byte offsets inside one stage
+  int q, k, kc, I, V, g, bytes;
+};
+__host__ __device__ inline ScanStage scan_stage(int dk) {
+  ScanStage s;
+  s.q = 0;
+  s.k = s.q + kGC * (dk + 8) * 2;
+  s.kc = s.k + kGC * (dk + 8) * 2;
+  s.I = s.kc + kGC * (dk + 4) * 4;
+  s.V = s.I + kGC * kLdA * 4;
+  s.g = s.V + kGC * kLdS * 4;
+  s.bytes = s.g + kGC * 4;
+  return s;
+}
 
 // kSV = dv slice width per CTA (32, 16 or 8): narrower slices keep every SM busy when a rank holds few heads
 template <int kSV>
-__global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qn,
-                                                             const __nv_bfloat16* __restrict__ kn,
-                                                             const float* __restrict__ vcorr,
-                                                             const float* __restrict__ kcd,
-                                                             const float* __restrict__ intra,
-                                                             const float* __restrict__ gcum, int M, int n_chunks,
-                                                             float* __restrict__ state,       // [nv][dk][dv] in/out
-                                                             float* __restrict__ core_out) {  // [M][nv][dv]
-  extern __shared__ float sm[];
+__global__ void __launch_bounds__(256, 1) gdn_chunk_scan_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qn,
+                                                                const __nv_bfloat16* __restrict__ kn,
+                                                                const float* __restrict__ vcorr,
+                                                                const float* __restrict__ kcd,
+                                                                const float* __restrict__ intra,
+                                                                const float* __restrict__ gcum, int M, int n_chunks,
+                                                                float* __restrict__ state,       // [nv][dk][dv] in/out
+                                                                float* __restrict__ core_out) {  // [M][nv][dv]
+  extern __shared__ __align__(16) unsigned char smraw[];
   const int h = blockIdx.x, sl = blockIdx.y, r = d.nv / d.nk, kh = h / r;
   const int dk = d.dk, dv = d.dv, kd = d.nk * dk, vd = d.nv * dv;
-  const int ldk = dk + 4;
-  float* S = sm;                          // [dk][kLdS]
-  float* sq = S + dk * kLdS;              // [64][ldk]
-  float* sk = sq + kGC * ldk;             // [64][ldk]
-  float* skc = sk + kGC * ldk;            // [64][ldk]  k_cumdecay
-  float* sI = skc + kGC * ldk;            // [64][kLdI]
-  float* sV = sI + kGC * kLdI;            // [64][kLdS] value_corrected slice -> v_new
-  float* sO = sV + kGC * kLdS;            // [64][kLdS] decayed v_new
-  float* sg = sO + kGC * kLdS;            // [64]
+  const int ldk = dk + 4, ldkb = dk + 8;
+  const ScanStage L = scan_stage(dk);
+  float* S = reinterpret_cast<float*>(smraw);      // [dk][kLdS]
+  float* sO = S + dk * kLdS;                       // [64][kLdS] decayed v_new
+  unsigned char* stage0 = reinterpret_cast<unsigned char*>(sO + kGC * kLdS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  auto prefetch = [&](int ch, int buf) {
+    unsigned char* st = stage0 + (size_t)buf * L.bytes;
+    __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(st + L.q);
+    __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(st + L.k);
+    float* skc = reinterpret_cast<float*>(st + L.kc);
+    float* sI = reinterpret_cast<float*>(st + L.I);
+    float* sV = reinterpret_cast<float*>(st + L.V);
+    float* sg = reinterpret_cast<float*>(st + L.g);
+    const int t0 = ch * kGC;
+    const long long hc = (long long)h * n_chunks + ch;
+    const int cq = dk / 8;
+    for (int idx = tid; idx < kGC * cq; idx += 256) {
+      const int i = idx / cq, c = (idx % cq) * 8, tt = t0 + i;
+      const bool ok = tt < M;
+      const long long off = (long long)(ok ? tt : 0) * kd + kh * dk + c;
+      cp_async16_zfill(sq + i * ldkb + c, qn + off, ok);
+      cp_async16_zfill(sk + i * ldkb + c, kn + off, ok);
+    }
+    const int ck = dk / 4;
+    for (int idx = tid; idx < kGC * ck; idx += 256) {
+      const int i = idx / ck, c = (idx % ck) * 4;
+      cp_async16(skc + i * ldk + c, kcd + hc * kGC * dk + i * dk + c);
+    }
+    for (int idx = tid; idx < kGC * (kGC / 4); idx += 256) {
+      const int i = idx / (kGC / 4), c = (idx % (kGC / 4)) * 4;
+      cp_async16(sI + i * kLdA + c, intra + hc * kGC * kGC + i * kGC + c);
+    }
+    for (int idx = tid; idx < kGC * (kSV / 4); idx += 256) {
+      const int i = idx / (kSV / 4), c = (idx % (kSV / 4)) * 4;
+      cp_async16(sV + i * kLdS + c, vcorr + hc * kGC * dv + i * dv + sl * kSV + c);
+    }
+    if (tid < kGC / 4) cp_async16(sg + tid * 4, gcum + hc * kGC + tid * 4);
+  };
+
+  prefetch(0, 0);
+  cp_async_commit();
   for (int idx = tid; idx < dk * kSV; idx += 256) {
     const int k = idx / kSV, c = idx % kSV;
     S[k * kLdS + c] = state[((long long)h * dk + k) * dv + sl * kSV + c];
   }
+  constexpr int NT = kSV / 8;
   for (int ch = 0; ch < n_chunks; ++ch) {
-    const int t0 = ch * kGC;
-    const long long hc = (long long)h * n_chunks + ch;
-    __syncthreads();
-    for (int idx = tid; idx < kGC * dk; idx += 256) {
-      const int i = idx / dk, c = idx % dk, tt = t0 + i;
-      sq[i * ldk + c] = tt < M ? __bfloat162float(qn[(long long)tt * kd + kh * dk + c]) : 0.f;
-      sk[i * ldk + c] = tt < M ? __bfloat162float(kn[(long long)tt * kd + kh * dk + c]) : 0.f;
-      skc[i * ldk + c] = kcd[hc * kGC * dk + idx];
-    }
-    for (int idx = tid; idx < kGC * kGC; idx += 256) sI[(idx / kGC) * kLdI + (idx % kGC)] = intra[hc * kGC * kGC + idx];
-    for (int idx = tid; idx < kGC * kSV; idx += 256) {
-      const int i = idx / kSV, c = idx % kSV;
-      sV[i * kLdS + c] = vcorr[hc * kGC * dv + i * dv + sl * kSV + c];
-    }
-    for (int i = tid; i < kGC; i += 256) sg[i] = gcum[hc * kGC + i];
-    __syncthreads();
+    const int t0 = ch * kGC, buf = ch & 1;
+    unsigned char* st = stage0 + (size_t)buf * L.bytes;
+    const __nv_bfloat16* sq = reinterpret_cast<const __nv_bfloat16*>(st + L.q);
+    const __nv_bfloat16* sk = reinterpret_cast<const __nv_bfloat16*>(st + L.k);
+    const float* skc = reinterpret_cast<const float*>(st + L.kc);
+    const float* sI = reinterpret_cast<const float*>(st + L.I);
+    float* sV = reinterpret_cast<float*>(st + L.V);
+    const float* sg = reinterpret_cast<const float*>(st + L.g);
+    __syncthreads();                               // step ch-1 done with the other stage (and with S)
+    if (ch + 1 < n_chunks) prefetch(ch + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();                            // this chunk's stage has landed (for this thread) ...
+    __syncthreads();                               // ... and for everybody
     // (1) warps 0-3: VP = kcd @ S (both fp32 -> 3xTF32);  warps 4-7: IT = q @ S (q exact in TF32)
-    constexpr int NT = kSV / 8;
     float acc[NT][4];
 #pragma unroll
     for (int a = 0; a < NT; ++a)
@@ -344,16 +455,15 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
     if (warp < 4)
       warp_mma_tiles<NT, true, true>(acc, skc + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
     else
-      warp_mma_tiles<NT, false, true>(acc, sq + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
-    __syncthreads();
-    if (warp < 4) {          // v_new = vcorr - VP   (in place in sV)
+      warp_mma_tiles<NT, false, true>(acc, sq + mt * 16 * ldkb, ldkb, 1, S, kLdS, 1, 0, dk);
+    if (warp < 4) {          // v_new = vcorr - VP   (in place in sV; each element has exactly one owner thread)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int r0 = mt * 16 + g, c0 = nt * 8 + 2 * t;
-        sV[r0 * kLdS + c0] -= acc[nt][0];
-        sV[r0 * kLdS + c0 + 1] -= acc[nt][1];
-        sV[(r0 + 8) * kLdS + c0] -= acc[nt][2];
-        sV[(r0 + 8) * kLdS + c0 + 1] -= acc[nt][3];
+        float2 a = *reinterpret_cast<float2*>(sV + r0 * kLdS + c0), b = *reinterpret_cast<float2*>(sV + (r0 + 8) * kLdS + c0);
+        a.x -= acc[nt][0]; a.y -= acc[nt][1]; b.x -= acc[nt][2]; b.y -= acc[nt][3];
+        *reinterpret_cast<float2*>(sV + r0 * kLdS + c0) = a;
+        *reinterpret_cast<float2*>(sV + (r0 + 8) * kLdS + c0) = b;
       }
     }
     __syncthreads();
@@ -364,25 +474,21 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
       for (int nt = 0; nt < NT; ++nt) {
         acc[nt][0] *= e0; acc[nt][1] *= e0; acc[nt][2] *= e1; acc[nt][3] *= e1;
       }
-      warp_mma_tiles<NT, true, true>(acc, sI + mt * 16 * kLdI, kLdI, 1, sV, kLdS, 1, 0, (mt + 1) * 16);
+      warp_mma_tiles<NT, true, true>(acc, sI + mt * 16 * kLdA, kLdA, 1, sV, kLdS, 1, 0, (mt + 1) * 16);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int r0 = mt * 16 + g, c0 = sl * kSV + nt * 8 + 2 * t;
         const int ta = t0 + r0, tb = t0 + r0 + 8;
-        if (ta < M) {
-          core_out[(long long)ta * vd + h * dv + c0] = acc[nt][0];
-          core_out[(long long)ta * vd + h * dv + c0 + 1] = acc[nt][1];
-        }
-        if (tb < M) {
-          core_out[(long long)tb * vd + h * dv + c0] = acc[nt][2];
-          core_out[(long long)tb * vd + h * dv + c0 + 1] = acc[nt][3];
-        }
+        if (ta < M) *reinterpret_cast<float2*>(core_out + (long long)ta * vd + h * dv + c0) = make_float2(acc[nt][0], acc[nt][1]);
+        if (tb < M) *reinterpret_cast<float2*>(core_out + (long long)tb * vd + h * dv + c0) = make_float2(acc[nt][2], acc[nt][3]);
       }
     } else {                 // warps 0-3 meanwhile: decayed v_new for the state update
       const float gl = sg[kGC - 1];
-      for (int idx = tid; idx < kGC * kSV; idx += 128) {
-        const int i = idx / kSV, c = idx % kSV;
-        sO[i * kLdS + c] = expf(gl - sg[i]) * sV[i * kLdS + c];
+      for (int idx = tid; idx < kGC * (kSV / 2); idx += 128) {
+        const int i = idx / (kSV / 2), c = (idx % (kSV / 2)) * 2;
+        const float e = expf(gl - sg[i]);
+        const float2 v = *reinterpret_cast<const float2*>(sV + i * kLdS + c);
+        *reinterpret_cast<float2*>(sO + i * kLdS + c) = make_float2(e * v.x, e * v.y);
       }
     }
     __syncthreads();
@@ -394,24 +500,21 @@ __global__ void __launch_bounds__(256) gdn_chunk_scan_kernel(GdnDims d, const __
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int r0 = mt3 * 16 + g, c0 = nt * 8 + 2 * t;
-          sc[nt][0] = S[r0 * kLdS + c0] * egl;
-          sc[nt][1] = S[r0 * kLdS + c0 + 1] * egl;
-          sc[nt][2] = S[(r0 + 8) * kLdS + c0] * egl;
-          sc[nt][3] = S[(r0 + 8) * kLdS + c0 + 1] * egl;
+          const float2 a = *reinterpret_cast<const float2*>(S + r0 * kLdS + c0), b = *reinterpret_cast<const float2*>(S + (r0 + 8) * kLdS + c0);
+          sc[nt][0] = a.x * egl; sc[nt][1] = a.y * egl; sc[nt][2] = b.x * egl; sc[nt][3] = b.y * egl;
         }
-        // A = K^T: A(row = kk, k = i) = sk[i*ldk + kk]
-        warp_mma_tiles<NT, false, true>(sc, sk + mt3 * 16, 1, ldk, sO, kLdS, 1, 0, kGC);
+        // A = K^T: A(row = kk, k = i) = sk[i*ldkb + kk]
+        warp_mma_tiles<NT, false, true>(sc, sk + mt3 * 16, 1, ldkb, sO, kLdS, 1, 0, kGC);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int r0 = mt3 * 16 + g, c0 = nt * 8 + 2 * t;
-          S[r0 * kLdS + c0] = sc[nt][0];
-          S[r0 * kLdS + c0 + 1] = sc[nt][1];
-          S[(r0 + 8) * kLdS + c0] = sc[nt][2];
-          S[(r0 + 8) * kLdS + c0 + 1] = sc[nt][3];
+          *reinterpret_cast<float2*>(S + r0 * kLdS + c0) = make_float2(sc[nt][0], sc[nt][1]);
+          *reinterpret_cast<float2*>(S + (r0 + 8) * kLdS + c0) = make_float2(sc[nt][2], sc[nt][3]);
         }
       }
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
   for (int idx = tid; idx < dk * kSV; idx += 256) {
     const int k = idx / kSV, c = idx % kSV;
@@ -448,10 +551,10 @@ __global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const float* _
 
 // ------------------------------------------------------------------------------------------------
 size_t gdn_prepare_smem(const GdnDims& d) {
-  return sizeof(float) * (2 * kGC * (d.dk + 4) + kGC * (kGC + 4) + kGC * (d.dv + d.dk + 8) + 2 * kGC);
+  return (size_t)kGC * (d.dk + 8) * 2 + sizeof(float) * (kGC * kLdA + kGC * (d.dv + d.dk + 8) + 2 * kGC);
 }
-size_t gdn_scan_smem(const GdnDims& d) {
-  return sizeof(float) * (d.dk * kLdS + 3 * kGC * (d.dk + 4) + kGC * kLdI + 2 * kGC * kLdS + kGC);   // same for every slice width
+size_t gdn_scan_smem(const GdnDims& d) {   // same for every slice width
+  return sizeof(float) * (d.dk * kLdS + kGC * kLdS) + 2 * (size_t)scan_stage(d.dk).bytes;
 }
 
 cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, const void* conv_w, void* conv_state,
@@ -463,10 +566,10 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
   const int n_chunks = (M + kGC - 1) / kGC;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gdn_chunk_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gdn_chunk_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gdn_chunk_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gdn_chunk_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     configured = true;
   }
