@@ -97,6 +97,94 @@ __global__ void __launch_bounds__(256) gdn_prep_kernel(GdnDims d, const __nv_bfl
   }
 }
 
+// Tiled variant for dk == dv == 32*CPL, conv width KW: one warp per (32-token tile, head) slides down the tokens with the
+// last KW-1 inputs in registers, so every qkvz element is read once (the per-token kernel above reads it KW times) and the
+// l2norm needs no shared memory.  Same arithmetic, same rounding points, same summation order as gdn_prep_kernel.
+template <int CPL, int KW>
+__global__ void __launch_bounds__(256) gdn_prep_tiled_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qkvz,
+                                                             const __nv_bfloat16* __restrict__ ba,
+                                                             const __nv_bfloat16* __restrict__ conv_w,
+                                                             const __nv_bfloat16* __restrict__ conv_state,
+                                                             const float* __restrict__ A_log,
+                                                             const float* __restrict__ dt_bias,
+                                                             __nv_bfloat16* __restrict__ qn, __nv_bfloat16* __restrict__ kn,
+                                                             __nv_bfloat16* __restrict__ vc, float* __restrict__ beta,
+                                                             float* __restrict__ g, int M, int n_tiles) {
+  constexpr int TT = 32;
+  const int lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n_units = 2 * d.nk + d.nv + 1;
+  const int tile = (int)(wg / n_units), u = (int)(wg % n_units);
+  if (tile >= n_tiles) return;
+  const int t_begin = tile * TT, t_end = min(M, t_begin + TT);
+  const int kd = d.nk * d.dk, vd = d.nv * d.dv, ld = 2 * kd + 2 * vd, r = d.nv / d.nk;
+  if (u == 2 * d.nk + d.nv) {             // gates for this token tile
+    for (int t = t_begin; t < t_end; ++t)
+      for (int h = lane; h < d.nv; h += 32) {
+        const int kh = h / r, j = h % r;
+        const float b = __bfloat162float(ba[(long long)t * d.ba_ld + kh * 2 * r + j]);
+        const float a = __bfloat162float(ba[(long long)t * d.ba_ld + kh * 2 * r + r + j]);
+        beta[(long long)t * d.nv + h] = bf16r(1.0f / (1.0f + expf(-b)));
+        const float x = a + dt_bias[h];
+        const float sp = x > 20.f ? x : log1pf(expf(x));
+        g[(long long)t * d.nv + h] = -expf(A_log[h]) * sp;
+      }
+    return;
+  }
+  const bool is_q = u < d.nk, is_k = !is_q && u < 2 * d.nk;
+  const int c_base = is_q ? u * d.dk : (is_k ? kd + (u - d.nk) * d.dk : 2 * kd + (u - 2 * d.nk) * d.dv);
+  int col[CPL];
+  float w[CPL][KW], hist[CPL][KW - 1];
+#pragma unroll
+  for (int e = 0; e < CPL; ++e) {
+    const int c = c_base + lane + 32 * e;
+    col[e] = qkvz_col(d, c);
+#pragma unroll
+    for (int j = 0; j < KW; ++j) w[e][j] = __bfloat162float(conv_w[c * KW + j]);
+#pragma unroll
+    for (int j = 0; j < KW - 1; ++j) {
+      const int tt = t_begin - (KW - 1) + j;
+      hist[e][j] = tt >= 0 ? __bfloat162float(qkvz[(long long)tt * ld + col[e]])
+                           : __bfloat162float(conv_state[c * KW + (KW + tt)]);
+    }
+  }
+  for (int t = t_begin; t < t_end; ++t) {
+    float sv[CPL];
+#pragma unroll
+    for (int e = 0; e < CPL; ++e) {
+      const float x = __bfloat162float(qkvz[(long long)t * ld + col[e]]);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < KW - 1; ++j) acc = fmaf(w[e][j], hist[e][j], acc);
+      acc = fmaf(w[e][KW - 1], x, acc);
+#pragma unroll
+      for (int j = 0; j < KW - 2; ++j) hist[e][j] = hist[e][j + 1];
+      hist[e][KW - 2] = x;
+      const float y = bf16r(acc);
+      sv[e] = bf16r(y / (1.0f + expf(-y)));
+    }
+    if (!is_q && !is_k) {
+#pragma unroll
+      for (int e = 0; e < CPL; ++e)
+        vc[(long long)t * vd + (u - 2 * d.nk) * d.dv + lane + 32 * e] = __float2bfloat16_rn(sv[e]);
+      continue;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < CPL; ++e) ss += bf16r(sv[e] * sv[e]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = bf16r(rsqrtf(bf16r(bf16r(ss) + 1e-6f)));
+    __nv_bfloat16* dst = (is_q ? qn : kn) + (long long)t * kd + (is_q ? u : u - d.nk) * d.dk;
+#pragma unroll
+    for (int e = 0; e < CPL; ++e) {
+      float v = bf16r(sv[e] * inv);
+      if (is_q) v = bf16r(v * d.scale);
+      dst[lane + 32 * e] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 // new conv state = last K pre-conv inputs (older entries come from the previous state when M < K)
 __global__ void gdn_conv_state_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qkvz,
                                       __nv_bfloat16* __restrict__ conv_state, int M) {
@@ -133,11 +221,17 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 // operand element -> TF32 hi (and lo when SPLIT); BF16 bits shifted up ARE a TF32 value (no cvt, never split)
+// fp32 -> (hi, lo) with hi = x rounded to TF32 by integer arithmetic (cvt.rna.tf32 costs ~4 instructions) and
+// lo = x - hi (exact, <= 12 significant bits; the tensor core ignores the low 13 mantissa bits of a .tf32 register,
+// so at most one bit of lo is dropped: |x - hi - lo| <= 2^-23 |x|)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
 template <bool SPLIT>
 __device__ __forceinline__ void ld_tf32(const float* p, uint32_t& hi, uint32_t& lo) {
-  const float x = *p;
-  hi = to_tf32(x);
-  if (SPLIT) lo = to_tf32(x - __uint_as_float(hi));
+  if (SPLIT) split_tf32(*p, hi, lo);
+  else hi = to_tf32(*p);
 }
 template <bool SPLIT>
 __device__ __forceinline__ void ld_tf32(const __nv_bfloat16* p, uint32_t& hi, uint32_t& lo) {
@@ -430,7 +524,8 @@ __global__ void __launch_bounds__(256, 1) gdn_chunk_scan_kernel(GdnDims d, const
     const int k = idx / kSV, c = idx % kSV;
     S[k * kLdS + c] = state[((long long)h * dk + k) * dv + sl * kSV + c];
   }
-  constexpr int NT = kSV / 8;
+  constexpr int NT = kSV / 8, NTW = NT >= 2 ? NT / 2 : 1, NH = NT / NTW;   // n-tiles per warp in phases 1-2, column halves
+  const int mt = warp & 3, nh = warp >> 2, n0 = nh * NTW * 8;
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int t0 = ch * kGC, buf = ch & 1;
     unsigned char* st = stage0 + (size_t)buf * L.bytes;
@@ -440,59 +535,79 @@ __global__ void __launch_bounds__(256, 1) gdn_chunk_scan_kernel(GdnDims d, const
     const float* sI = reinterpret_cast<const float*>(st + L.I);
     float* sV = reinterpret_cast<float*>(st + L.V);
     const float* sg = reinterpret_cast<const float*>(st + L.g);
-    __syncthreads();                               // step ch-1 done with the other stage (and with S)
-    if (ch + 1 < n_chunks) prefetch(ch + 1, buf ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();                            // this chunk's stage has landed (for this thread) ...
-    __syncthreads();                               // ... and for everybody
-    // (1) warps 0-3: VP = kcd @ S (both fp32 -> 3xTF32);  warps 4-7: IT = q @ S (q exact in TF32)
-    float acc[NT][4];
+    cp_async_wait<0>();                            // this chunk's stage has landed (this thread's copies) ...
+    __syncthreads();                               // ... everybody's; and step ch-1 is done with the other stage and S
+    if (ch + 1 < n_chunks) {
+      prefetch(ch + 1, buf ^ 1);
+      cp_async_commit();
+    }
+    // (1) warp (mt, nh) owns rows [16mt, 16mt+16) x columns [n0, n0 + 8*NTW): VP = kcd @ S (fp32 x fp32 -> 3xTF32) and
+    //     IT = q @ S (q exact in TF32 -> 2 mma), sharing the S fragments; then v_new = vcorr - VP and its decayed copy
+    float it[NTW][4];
+    if (nh < NH) {
+      float vp[NTW][4];
 #pragma unroll
-    for (int a = 0; a < NT; ++a)
+      for (int a = 0; a < NTW; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    const int mt = warp & 3;
-    if (warp < 4)
-      warp_mma_tiles<NT, true, true>(acc, skc + mt * 16 * ldk, ldk, 1, S, kLdS, 1, 0, dk);
-    else
-      warp_mma_tiles<NT, false, true>(acc, sq + mt * 16 * ldkb, ldkb, 1, S, kLdS, 1, 0, dk);
-    if (warp < 4) {          // v_new = vcorr - VP   (in place in sV; each element has exactly one owner thread)
+        for (int b = 0; b < 4; ++b) vp[a][b] = it[a][b] = 0.f;
+      const float* A1 = skc + mt * 16 * ldk;
+      const __nv_bfloat16* A2 = sq + mt * 16 * ldkb;
+      const float* Bs = S + n0;
+      for (int k0 = 0; k0 < dk; k0 += 8) {
+        uint32_t ah[4], al[4], aq[4], dummy;
+        split_tf32(A1[g * ldk + k0 + t], ah[0], al[0]);
+        split_tf32(A1[(g + 8) * ldk + k0 + t], ah[1], al[1]);
+        split_tf32(A1[g * ldk + k0 + t + 4], ah[2], al[2]);
+        split_tf32(A1[(g + 8) * ldk + k0 + t + 4], ah[3], al[3]);
+        ld_tf32<false>(A2 + g * ldkb + k0 + t, aq[0], dummy);
+        ld_tf32<false>(A2 + (g + 8) * ldkb + k0 + t, aq[1], dummy);
+        ld_tf32<false>(A2 + g * ldkb + k0 + t + 4, aq[2], dummy);
+        ld_tf32<false>(A2 + (g + 8) * ldkb + k0 + t + 4, aq[3], dummy);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int r0 = mt * 16 + g, c0 = nt * 8 + 2 * t;
+        for (int nt = 0; nt < NTW; ++nt) {
+          uint32_t bh[2], bl[2];
+          split_tf32(Bs[(k0 + t) * kLdS + nt * 8 + g], bh[0], bl[0]);
+          split_tf32(Bs[(k0 + t + 4) * kLdS + nt * 8 + g], bh[1], bl[1]);
+          mma_tf32(vp[nt], al, bh);
+          mma_tf32(vp[nt], ah, bl);
+          mma_tf32(vp[nt], ah, bh);
+          mma_tf32(it[nt], aq, bl);
+          mma_tf32(it[nt], aq, bh);
+        }
+      }
+      const float gl = sg[kGC - 1];
+      const int r0 = mt * 16 + g;
+      const float d0 = expf(gl - sg[r0]), d1 = expf(gl - sg[r0 + 8]);
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        const int c0 = n0 + nt * 8 + 2 * t;
         float2 a = *reinterpret_cast<float2*>(sV + r0 * kLdS + c0), b = *reinterpret_cast<float2*>(sV + (r0 + 8) * kLdS + c0);
-        a.x -= acc[nt][0]; a.y -= acc[nt][1]; b.x -= acc[nt][2]; b.y -= acc[nt][3];
+        a.x -= vp[nt][0]; a.y -= vp[nt][1]; b.x -= vp[nt][2]; b.y -= vp[nt][3];
         *reinterpret_cast<float2*>(sV + r0 * kLdS + c0) = a;
         *reinterpret_cast<float2*>(sV + (r0 + 8) * kLdS + c0) = b;
+        *reinterpret_cast<float2*>(sO + r0 * kLdS + c0) = make_float2(d0 * a.x, d0 * a.y);
+        *reinterpret_cast<float2*>(sO + (r0 + 8) * kLdS + c0) = make_float2(d1 * b.x, d1 * b.y);
       }
     }
     __syncthreads();
-    // (2) out = exp(gcum_i) * IT + intra @ v_new : warps 4-7 keep IT in registers and add the (lower-triangular) product
-    if (warp >= 4) {
+    // (2) out = exp(gcum_i) * IT + intra @ v_new (lower-triangular: k < 16(mt+1))
+    if (nh < NH) {
       const float e0 = expf(sg[mt * 16 + g]), e1 = expf(sg[mt * 16 + g + 8]);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        acc[nt][0] *= e0; acc[nt][1] *= e0; acc[nt][2] *= e1; acc[nt][3] *= e1;
+      for (int nt = 0; nt < NTW; ++nt) {
+        it[nt][0] *= e0; it[nt][1] *= e0; it[nt][2] *= e1; it[nt][3] *= e1;
       }
-      warp_mma_tiles<NT, true, true>(acc, sI + mt * 16 * kLdA, kLdA, 1, sV, kLdS, 1, 0, (mt + 1) * 16);
+      warp_mma_tiles<NTW, true, true>(it, sI + mt * 16 * kLdA, kLdA, 1, sV + n0, kLdS, 1, 0, (mt + 1) * 16);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int r0 = mt * 16 + g, c0 = sl * kSV + nt * 8 + 2 * t;
+      for (int nt = 0; nt < NTW; ++nt) {
+        const int r0 = mt * 16 + g, c0 = sl * kSV + n0 + nt * 8 + 2 * t;
         const int ta = t0 + r0, tb = t0 + r0 + 8;
-        if (ta < M) *reinterpret_cast<float2*>(core_out + (long long)ta * vd + h * dv + c0) = make_float2(acc[nt][0], acc[nt][1]);
-        if (tb < M) *reinterpret_cast<float2*>(core_out + (long long)tb * vd + h * dv + c0) = make_float2(acc[nt][2], acc[nt][3]);
-      }
-    } else {                 // warps 0-3 meanwhile: decayed v_new for the state update
-      const float gl = sg[kGC - 1];
-      for (int idx = tid; idx < kGC * (kSV / 2); idx += 128) {
-        const int i = idx / (kSV / 2), c = (idx % (kSV / 2)) * 2;
-        const float e = expf(gl - sg[i]);
-        const float2 v = *reinterpret_cast<const float2*>(sV + i * kLdS + c);
-        *reinterpret_cast<float2*>(sO + i * kLdS + c) = make_float2(e * v.x, e * v.y);
+        if (ta < M) *reinterpret_cast<float2*>(core_out + (long long)ta * vd + h * dv + c0) = make_float2(it[nt][0], it[nt][1]);
+        if (tb < M) *reinterpret_cast<float2*>(core_out + (long long)tb * vd + h * dv + c0) = make_float2(it[nt][2], it[nt][3]);
       }
     }
-    __syncthreads();
-    // (3) S = S * exp(g_last) + K^T @ (decayed v_new): warp w owns state rows [16w, 16w+16) (dk = 128 -> 8 warps)
+    // (3) S = S * exp(g_last) + K^T @ (decayed v_new): warp w owns state rows [16w, 16w+16) (dk = 128 -> 8 warps).
+    //     Independent of (2): no barrier in between.
     {
       const float egl = expf(sg[kGC - 1]);
       for (int mt3 = warp; mt3 < dk / 16; mt3 += 8) {
@@ -573,10 +688,19 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
     cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     configured = true;
   }
-  gdn_prep_kernel<<<M, 256, sizeof(float) * C, s>>>(d, (const __nv_bfloat16*)qkvz, (const __nv_bfloat16*)ba,
-                                                    (const __nv_bfloat16*)conv_w, (const __nv_bfloat16*)conv_state, A_log,
-                                                    dt_bias, (__nv_bfloat16*)qn, (__nv_bfloat16*)kn, (__nv_bfloat16*)vc,
-                                                    beta, g, M);
+  if (d.dk == 128 && d.dv == 128 && d.K == 4) {
+    const int n_tiles = (M + 31) / 32;
+    const long long warps = (long long)n_tiles * (2 * d.nk + d.nv + 1);
+    gdn_prep_tiled_kernel<4, 4><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(
+        d, (const __nv_bfloat16*)qkvz, (const __nv_bfloat16*)ba, (const __nv_bfloat16*)conv_w,
+        (const __nv_bfloat16*)conv_state, A_log, dt_bias, (__nv_bfloat16*)qn, (__nv_bfloat16*)kn, (__nv_bfloat16*)vc, beta, g,
+        M, n_tiles);
+  } else {
+    gdn_prep_kernel<<<M, 256, sizeof(float) * C, s>>>(d, (const __nv_bfloat16*)qkvz, (const __nv_bfloat16*)ba,
+                                                      (const __nv_bfloat16*)conv_w, (const __nv_bfloat16*)conv_state, A_log,
+                                                      dt_bias, (__nv_bfloat16*)qn, (__nv_bfloat16*)kn, (__nv_bfloat16*)vc,
+                                                      beta, g, M);
+  }
   gdn_conv_state_kernel<<<(C + 255) / 256, 256, 0, s>>>(d, (const __nv_bfloat16*)qkvz, (__nv_bfloat16*)conv_state, M);
   gdn_chunk_prepare_kernel<<<dim3(n_chunks, d.nv), 256, gdn_prepare_smem(d), s>>>(
       d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, (const __nv_bfloat16*)vc, beta, g, M, n_chunks, vcorr, kcd,

@@ -96,6 +96,8 @@ def make_gguf_layer(rng, E, H, I, gate_up_type=G.GGML_Q4_K, down_type=G.GGML_Q8_
     def mk(t, rows, k):
         if t == G.GGML_Q8_0:   # realistic: quantise N(0, 0.02) floats
             return np.stack([G.quantize_q8_0(rng.normal(0, 0.02, (rows, k)).astype(np.float32)) for _ in range(E)])
+        if t == G.GGML_Q4_K:   # d, dmin sized so |w| ~ 0.1 and gate/up pre-activations are O(1), like a trained model
+            return np.stack([G.random_q4_k(rng, rows, k, d_range=(1e-4, 6e-4)) for _ in range(E)])
         return np.stack([G.random_blocks(rng, t, rows, k) for _ in range(E)])
     return GgufLayer(mk(gate_up_type, I, H), mk(gate_up_type, I, H), mk(down_type, H, I),
                      gate_up_type, down_type, H, I)
