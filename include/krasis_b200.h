@@ -272,6 +272,39 @@ KB2_API int kb2_gqa_forward(kb2_gqa* h, int layer, const void* hidden_dev, const
                             void* k_cache_layer_dev, void* v_cache_layer_dev, const int32_t* kv_indices_dev,
                             int32_t kv_len_after, void* out_dev, int32_t num_tokens, void* stream);
 
+/* ---- MLA prefill (python/krasis/attention.py:45-374, MLAAttention) ------------------------------------------------- */
+typedef struct kb2_mla kb2_mla;
+typedef struct kb2_mla_config {
+  int32_t hidden_size;
+  int32_t num_heads;        /* cfg.num_attention_heads */
+  int32_t qk_nope_head_dim; /* 128 */
+  int32_t qk_rope_head_dim; /* 64 */
+  int32_t v_head_dim;       /* 128 */
+  int32_t kv_lora_rank;     /* 512 */
+  int32_t q_lora_rank;      /* 0 = direct q_proj (V2-Lite); > 0 = q_a_proj -> layernorm -> q_b_proj (attention.py:248-259) */
+  float rms_norm_eps;
+  float sm_scale;           /* 1/sqrt(nope+rope) * yarn mscale^2 (attention.py:79-88) */
+  int32_t page_size;        /* 16 */
+  int32_t max_tokens;       /* rows of one forward call */
+  int32_t max_kv_len;       /* longest sequence (cached + new tokens) a call may attend over */
+  int32_t num_layers;
+  int32_t device;
+} kb2_mla_config;
+KB2_API int kb2_mla_create(const kb2_mla_config* cfg, kb2_mla** out);
+KB2_API void kb2_mla_destroy(kb2_mla* h);
+/* BF16 host weights (attention.py:90-107): q_proj [nh*(nope+rope)][H] when q_lora_rank == 0 (q_a_* NULL), else q_a_proj
+ * [q_lora][H], q_a_layernorm [q_lora], q_b_proj [nh*(nope+rope)][q_lora]; kv_a_proj_with_mqa [lora+rope][H];
+ * kv_a_layernorm [lora]; w_kc [nh][nope][lora]; w_vc [nh][dv][lora]; o_proj [H][nh*dv].
+ * rope_inv_freq: fp32 [rope/2] — the (YaRN-blended) inverse frequencies of attention.py:129-157. */
+KB2_API int kb2_mla_set_weights_host(kb2_mla* h, int layer, const void* q_proj_or_q_b_proj, const void* q_a_proj,
+                                     const void* q_a_layernorm, const void* kv_a_proj_with_mqa, const void* kv_a_layernorm,
+                                     const void* w_kc, const void* w_vc, const void* o_proj, const float* rope_inv_freq);
+/* hidden [M][H] bf16; positions [M] int32 = first_position .. first_position+M-1; latent caches of THIS layer:
+ * ckv [num_pages][16][lora], kpe [num_pages][16][rope] FP8-E4M3 (kv_cache.py:99-117); out [M][H] bf16. */
+KB2_API int kb2_mla_forward(kb2_mla* h, int layer, const void* hidden_dev, const int32_t* positions_dev, int32_t first_position,
+                            void* ckv_cache_layer_dev, void* kpe_cache_layer_dev, const int32_t* kv_indices_dev,
+                            int32_t kv_len_after, void* out_dev, int32_t num_tokens, void* stream);
+
 /* Per-kernel device timing with CUDA events recorded on the launching stream (the reference's
  * KRASIS_LAYER_TIMING / EP breakdown, python/krasis/model.py:2839-2860).  kb2_profile_collect synchronises the
  * device and returns, per kernel class, the summed milliseconds and the number of launches since enable. */

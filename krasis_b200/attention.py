@@ -233,3 +233,126 @@ class GQAAttention:
                                              seq_state.kv_indices(hidden.device).data_ptr(), seq_state.seq_len + M,
                                              out.data_ptr(), M, _stream(hidden.device)))
         return out
+
+
+# ------------------------------------------------------------------------------------------------ MLA
+
+class MLAPagedKVCache(PagedKVCache):
+    """MLA part of python/krasis/kv_cache.py:PagedKVCache (:99-117, split layout): FP8-E4M3 latent pools
+    ckv [num_layers, max_pages, 16, kv_lora_rank] and kpe [num_layers, max_pages, 16, qk_rope_head_dim]."""
+
+    def __init__(self, num_layers: int, kv_lora_rank: int, qk_rope_head_dim: int, device, max_pages: int,
+                 kv_dtype=torch.float8_e4m3fn, page_size: int = PAGE_SIZE):
+        if page_size != PAGE_SIZE or kv_dtype != torch.float8_e4m3fn:
+            raise ValueError("only page_size=16 and float8_e4m3fn are supported (the reference defaults)")
+        self.num_layers, self.ckv_dim, self.kpe_dim = num_layers, kv_lora_rank, qk_rope_head_dim
+        self.page_size, self.kv_dtype, self.max_pages = page_size, kv_dtype, max_pages
+        self.device = torch.device(device)
+        self.ckv_cache = torch.zeros((num_layers, max_pages, page_size, kv_lora_rank), dtype=kv_dtype, device=self.device)
+        self.kpe_cache = torch.zeros((num_layers, max_pages, page_size, qk_rope_head_dim), dtype=kv_dtype, device=self.device)
+        self._free = list(range(max_pages - 1, -1, -1))
+
+    def get_layer_caches(self, layer_offset: int):
+        return self.ckv_cache[layer_offset], self.kpe_cache[layer_offset]
+
+
+def mla_rope_inv_freq(qk_rope_dim: int, rope_theta: float, rope_scaling) -> "np.ndarray":
+    """Inverse frequencies of python/krasis/attention.py:_get_rope_cos_sin (:119-157), YaRN blend included, in fp32
+    with torch's own ops so the table the kernel multiplies positions with is the reference's, bit for bit."""
+    import math
+    dim = qk_rope_dim
+    freqs = 1.0 / (rope_theta ** (torch.arange(0, dim, 2).float() / dim))
+    cfg = rope_scaling or {}
+    factor = cfg.get("factor", 1.0)
+    if factor > 1.0:
+        original_max = cfg.get("original_max_position_embeddings", 4096)
+        beta_fast, beta_slow = cfg.get("beta_fast", 32.0), cfg.get("beta_slow", 1.0)
+        low = math.floor(dim * math.log(original_max / (beta_fast * 2 * math.pi)) / (2 * math.log(rope_theta)))
+        high = math.ceil(dim * math.log(original_max / (beta_slow * 2 * math.pi)) / (2 * math.log(rope_theta)))
+        low, high = max(low, 0), min(high, dim // 2 - 1)
+        ramp = torch.clamp((torch.arange(dim // 2).float() - low) / max(high - low, 0.001), 0, 1)
+        mask = 1.0 - ramp
+        freqs = (freqs / factor) * (1 - mask) + freqs * mask
+    return freqs.float().numpy()
+
+
+def mla_sm_scale(qk_nope_dim: int, qk_rope_dim: int, rope_scaling) -> float:
+    """attention.py:79-88: 1/sqrt(head_dim) * yarn mscale(mscale_all_dim)^2."""
+    import math
+    s = 1.0 / math.sqrt(qk_nope_dim + qk_rope_dim)
+    cfg = rope_scaling or {}
+    factor = cfg.get("factor", 1.0)
+    if factor > 1.0:
+        m = 0.1 * cfg.get("mscale_all_dim", 0) * math.log(factor) + 1.0
+        s *= m * m
+    return s
+
+
+class MLAAttention:
+    """Drop-in for python/krasis/attention.py:MLAAttention (prefill): forward(hidden, positions, kv_cache, seq_state,
+    layer_offset, num_new_tokens) -> [M, hidden] bf16.  `cfg` needs hidden_size, num_attention_heads, qk_nope_head_dim,
+    qk_rope_head_dim, v_head_dim, kv_lora_rank, q_lora_rank (None/0 = direct q_proj), rope_theta, rope_scaling,
+    rms_norm_eps.  weights as the reference (:90-107): q_proj | (q_a_proj, q_a_layernorm, q_b_proj), kv_a_proj_with_mqa,
+    kv_a_layernorm, w_kc [H,nope,lora], w_vc [H,v,lora], o_proj — BF16 tensors."""
+
+    _MAX_SHARED = 64
+
+    def __init__(self, cfg, layer_idx: int, weights: dict, device, max_tokens: int = 8192, max_kv_len: Optional[int] = None,
+                 share_scratch_with=None):
+        self.cfg, self.layer_idx, self.device = cfg, layer_idx, torch.device(device)
+        for k, v in weights.items():
+            if isinstance(v, tuple):
+                raise ValueError(f"{k}: INT8 attention weights are not supported (the reference disables them, config.py:209)")
+        self.q_lora_rank = int(getattr(cfg, "q_lora_rank", 0) or 0)
+        self.sm_scale = mla_sm_scale(cfg.qk_nope_head_dim, cfg.qk_rope_head_dim, getattr(cfg, "rope_scaling", None))
+        self._lib = capi.load()
+        if share_scratch_with is None:
+            c = capi.MlaConfig(cfg.hidden_size, cfg.num_attention_heads, cfg.qk_nope_head_dim, cfg.qk_rope_head_dim,
+                               cfg.v_head_dim, cfg.kv_lora_rank, self.q_lora_rank, float(cfg.rms_norm_eps), float(self.sm_scale),
+                               PAGE_SIZE, max_tokens, max_kv_len or max_tokens, self._MAX_SHARED, self.device.index or 0)
+            self._h = C.c_void_p()
+            capi.check(self._lib.kb2_mla_create(C.byref(c), C.byref(self._h)))
+            self._owner, self._slot, self._n_slots, self._c = None, 0, [1], c
+        else:
+            o = share_scratch_with
+            self._h, self._owner, self._c, self._n_slots = o._h, o, o._c, o._n_slots
+            self._slot = self._n_slots[0]
+            self._n_slots[0] += 1
+            if self._slot >= self._MAX_SHARED:
+                raise ValueError("too many layers share one MLA handle")
+        inv = np.ascontiguousarray(mla_rope_inv_freq(cfg.qk_rope_head_dim, float(cfg.rope_theta), getattr(cfg, "rope_scaling", None)),
+                                   dtype=np.float32)
+        h = lambda k: _bf16_host(weights[k])
+        if self.q_lora_rank:
+            q, qa, qan = h("q_b_proj"), h("q_a_proj"), h("q_a_layernorm")
+        else:
+            q, qa, qan = h("q_proj"), None, None
+        rest = [h(k) for k in ("kv_a_proj_with_mqa", "kv_a_layernorm", "w_kc", "w_vc", "o_proj")]
+        p = lambda a: a.ctypes.data if a is not None else None
+        capi.check(self._lib.kb2_mla_set_weights_host(self._h, self._slot, p(q), p(qa), p(qan), *[p(a) for a in rest], p(inv)))
+
+    def __del__(self):
+        try:
+            if self._owner is None and self._h:
+                self._lib.kb2_mla_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def forward(self, hidden: torch.Tensor, positions: torch.Tensor, kv_cache: MLAPagedKVCache, seq_state: SequenceKVState,
+                layer_offset: int, num_new_tokens: int = 0) -> torch.Tensor:
+        if not hidden.is_cuda or hidden.dtype != torch.bfloat16 or hidden.dim() != 2 or not hidden.is_contiguous() \
+                or hidden.shape[1] != self._c.hidden_size:
+            raise ValueError(f"hidden: expected contiguous CUDA bf16 [M, {self._c.hidden_size}]")
+        M = hidden.shape[0]
+        if num_new_tokens not in (0, M):
+            raise ValueError("num_new_tokens must equal the number of rows of hidden")
+        seq_state.ensure_capacity(M)
+        ckv_layer, kpe_layer = kv_cache.get_layer_caches(layer_offset)
+        pos = positions.to(device=hidden.device, dtype=torch.int32).contiguous()
+        out = torch.empty_like(hidden)
+        capi.check(self._lib.kb2_mla_forward(self._h, self._slot, hidden.data_ptr(), pos.data_ptr(), seq_state.seq_len,
+                                             ckv_layer.data_ptr(), kpe_layer.data_ptr(),
+                                             seq_state.kv_indices(hidden.device).data_ptr(), seq_state.seq_len + M,
+                                             out.data_ptr(), M, _stream(hidden.device)))
+        return out

@@ -36,6 +36,14 @@ class GqaConfig(C.Structure):
                 ("num_layers", C.c_int32), ("device", C.c_int32)]
 
 
+class MlaConfig(C.Structure):
+    _fields_ = [("hidden_size", C.c_int32), ("num_heads", C.c_int32), ("qk_nope_head_dim", C.c_int32),
+                ("qk_rope_head_dim", C.c_int32), ("v_head_dim", C.c_int32), ("kv_lora_rank", C.c_int32),
+                ("q_lora_rank", C.c_int32), ("rms_norm_eps", C.c_float), ("sm_scale", C.c_float),
+                ("page_size", C.c_int32), ("max_tokens", C.c_int32), ("max_kv_len", C.c_int32),
+                ("num_layers", C.c_int32), ("device", C.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/krasis_b200.h declares
 SIGNATURES = {
     "kb2_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -83,6 +91,11 @@ SIGNATURES = {
     "kb2_gqa_destroy": (None, [C.c_void_p]),
     "kb2_gqa_set_weights_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 6),
     "kb2_gqa_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "kb2_mla_create": (C.c_int, [C.POINTER(MlaConfig), C.POINTER(C.c_void_p)]),
+    "kb2_mla_destroy": (None, [C.c_void_p]),
+    "kb2_mla_set_weights_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9),
+    "kb2_mla_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "kb2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "kb2_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -34,6 +34,14 @@ struct GqaDims {
 cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_raw, const void* v_raw, const float* q_norm,
                             const float* k_norm, const int* positions, const int* kv_indices, void* q_rot, void* k_cache,
                             void* v_cache, void* attn_out, int M, int q_start, int kv_len, cudaStream_t s);
+struct MlaDims {
+  int H, nh, nope, rope, dv, lora;
+  float eps;
+};
+cudaError_t launch_mla_core(const MlaDims& m, void* q_full, const void* kv_a, const float* kv_norm_w, const float* inv_freq,
+                            const void* w_kv, const int* positions, const int* kv_indices, void* ckv_cache, void* kpe_cache,
+                            void* ckv_bf16, void* kpe_bf16, void* kv_up, void* attn_out, int M, int q_start, int kv_len,
+                            float sm_scale, int num_sms, cudaStream_t s);
 }  // namespace kb2
 using namespace kb2;
 
@@ -381,6 +389,132 @@ KB2_API int kb2_gqa_forward(kb2_gqa* h, int layer, const void* hidden_dev, const
   CUDA_TRY(launch_gqa_core(h->g, h->q_raw, h->k_raw, h->v_raw, L.q_norm, L.k_norm, positions_dev, kv_indices_dev, h->q_rot,
                            k_cache_layer_dev, v_cache_layer_dev, h->attn, M, first_position, kv_len_after, s));
   CUDA_TRY(launch_dense_gemm(h->attn, L.wo, out_dev, nullptr, M, H, qd, H, false, sms, s));
+  return KB2_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------- MLA
+struct MlaLayer {
+  void *wq = nullptr, *wqa = nullptr, *wkva = nullptr, *wkv = nullptr, *wo = nullptr;
+  float *qa_norm = nullptr, *kv_norm = nullptr, *inv_freq = nullptr;
+  bool loaded = false;
+};
+struct kb2_mla {
+  kb2_mla_config cfg{};
+  MlaDims m{};
+  std::vector<MlaLayer> layers;
+  void *q_full = nullptr, *q_a = nullptr, *kv_a = nullptr, *ckv_bf16 = nullptr, *kpe_bf16 = nullptr, *kv_up = nullptr, *attn = nullptr;
+};
+
+KB2_API int kb2_mla_create(const kb2_mla_config* c, kb2_mla** out) {
+  if (!c || !out) return failf(KB2_ERR_VALUE, "null argument");
+  if (c->qk_nope_head_dim != 128 || c->qk_rope_head_dim != 64 || c->v_head_dim != 128)
+    return failf(KB2_ERR_VALUE, "MLA head geometry must be nope 128 / rope 64 / v 128 (got %d/%d/%d)", c->qk_nope_head_dim,
+                 c->qk_rope_head_dim, c->v_head_dim);
+  if (c->kv_lora_rank < 64 || c->kv_lora_rank % 64) return failf(KB2_ERR_VALUE, "kv_lora_rank %% 64 == 0 required");
+  if (c->q_lora_rank < 0 || c->q_lora_rank % 64) return failf(KB2_ERR_VALUE, "q_lora_rank must be 0 or a multiple of 64");
+  if (c->num_heads < 1 || c->hidden_size % 64 || c->page_size != 16) return failf(KB2_ERR_VALUE, "hidden_size %% 64 == 0 and page_size == 16 required");
+  if (c->max_tokens < 1 || c->num_layers < 1 || c->max_kv_len < c->max_tokens) return failf(KB2_ERR_VALUE, "max_tokens, num_layers >= 1 and max_kv_len >= max_tokens required");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return failf(KB2_ERR_CUDA, "no CUDA device: krasis_b200 has no CPU fallback");
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  kb2_mla* h = new kb2_mla();
+  h->cfg = *c;
+  h->m = MlaDims{c->hidden_size, c->num_heads, c->qk_nope_head_dim, c->qk_rope_head_dim, c->v_head_dim, c->kv_lora_rank, c->rms_norm_eps};
+  h->layers.resize(c->num_layers);
+  const size_t M = c->max_tokens, T = c->max_kv_len, nh = c->num_heads;
+  CUDA_TRY(cudaMalloc(&h->q_full, M * nh * 192 * 2));
+  if (c->q_lora_rank) CUDA_TRY(cudaMalloc(&h->q_a, M * c->q_lora_rank * 2 * 2));     // raw + normed
+  CUDA_TRY(cudaMalloc(&h->kv_a, M * (c->kv_lora_rank + 64) * 2));
+  CUDA_TRY(cudaMalloc(&h->ckv_bf16, T * c->kv_lora_rank * 2));
+  CUDA_TRY(cudaMalloc(&h->kpe_bf16, T * 64 * 2));
+  CUDA_TRY(cudaMalloc(&h->kv_up, T * nh * 256 * 2));
+  CUDA_TRY(cudaMalloc(&h->attn, M * nh * 128 * 2));
+  *out = h;
+  return KB2_OK;
+}
+
+KB2_API void kb2_mla_destroy(kb2_mla* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (auto& L : h->layers) {
+    cudaFree(L.wq); cudaFree(L.wqa); cudaFree(L.wkva); cudaFree(L.wkv); cudaFree(L.wo);
+    cudaFree(L.qa_norm); cudaFree(L.kv_norm); cudaFree(L.inv_freq);
+  }
+  cudaFree(h->q_full); cudaFree(h->q_a); cudaFree(h->kv_a); cudaFree(h->ckv_bf16); cudaFree(h->kpe_bf16); cudaFree(h->kv_up); cudaFree(h->attn);
+  delete h;
+}
+
+KB2_API int kb2_mla_set_weights_host(kb2_mla* h, int layer, const void* q_proj_or_q_b_proj, const void* q_a_proj,
+                                     const void* q_a_layernorm, const void* kv_a_proj_with_mqa, const void* kv_a_layernorm,
+                                     const void* w_kc, const void* w_vc, const void* o_proj, const float* rope_inv_freq) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  if (layer < 0 || layer >= (int)h->layers.size()) return failf(KB2_ERR_VALUE, "layer %d out of range", layer);
+  const auto& c = h->cfg;
+  if (!q_proj_or_q_b_proj || !kv_a_proj_with_mqa || !kv_a_layernorm || !w_kc || !w_vc || !o_proj || !rope_inv_freq)
+    return failf(KB2_ERR_VALUE, "null weight pointer");
+  if ((c.q_lora_rank > 0) != (q_a_proj != nullptr && q_a_layernorm != nullptr))
+    return failf(KB2_ERR_VALUE, "q_a_proj / q_a_layernorm must be given exactly when q_lora_rank > 0");
+  CUDA_TRY(cudaSetDevice(c.device));
+  MlaLayer& L = h->layers[layer];
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!*dst) { cudaError_t e = cudaMalloc(dst, bytes); if (e != cudaSuccess) return e; }
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  const size_t H = c.hidden_size, nh = c.num_heads, lora = c.kv_lora_rank, qin = c.q_lora_rank ? c.q_lora_rank : H;
+  CUDA_TRY(up(&L.wq, q_proj_or_q_b_proj, nh * 192 * qin * 2));
+  if (c.q_lora_rank) {
+    CUDA_TRY(up(&L.wqa, q_a_proj, (size_t)c.q_lora_rank * H * 2));
+    auto v = bf16_to_f32_host(q_a_layernorm, c.q_lora_rank);
+    CUDA_TRY(up((void**)&L.qa_norm, v.data(), v.size() * 4));
+  }
+  CUDA_TRY(up(&L.wkva, kv_a_proj_with_mqa, (lora + 64) * H * 2));
+  {
+    auto v = bf16_to_f32_host(kv_a_layernorm, (int)lora);
+    CUDA_TRY(up((void**)&L.kv_norm, v.data(), v.size() * 4));
+  }
+  // [w_kc ; w_vc] as one [nh*256][lora] projection: rows [0, nh*128) = k_nope heads, rows [nh*128, nh*256) = v heads
+  if (!L.wkv) CUDA_TRY(cudaMalloc(&L.wkv, nh * 256 * lora * 2));
+  CUDA_TRY(cudaMemcpy(L.wkv, w_kc, nh * 128 * lora * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy((char*)L.wkv + nh * 128 * lora * 2, w_vc, nh * 128 * lora * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(up(&L.wo, o_proj, H * nh * 128 * 2));
+  CUDA_TRY(up((void**)&L.inv_freq, rope_inv_freq, 32 * 4));
+  L.loaded = true;
+  return KB2_OK;
+}
+
+KB2_API int kb2_mla_forward(kb2_mla* h, int layer, const void* hidden_dev, const int32_t* positions_dev, int32_t first_position,
+                            void* ckv_cache_layer_dev, void* kpe_cache_layer_dev, const int32_t* kv_indices_dev,
+                            int32_t kv_len_after, void* out_dev, int32_t M, void* stream) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  if (layer < 0 || layer >= (int)h->layers.size()) return failf(KB2_ERR_VALUE, "layer %d out of range", layer);
+  MlaLayer& L = h->layers[layer];
+  const auto& c = h->cfg;
+  if (M < 0 || M > c.max_tokens) return failf(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, c.max_tokens);
+  if (!L.loaded) return failf(KB2_ERR_STATE, "MLA weights not set for layer %d", layer);
+  if (M == 0) return KB2_OK;
+  if (!hidden_dev || !positions_dev || !ckv_cache_layer_dev || !kpe_cache_layer_dev || !kv_indices_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (first_position < 0 || kv_len_after != first_position + M) return failf(KB2_ERR_VALUE, "positions must be contiguous: kv_len_after (%d) != first_position (%d) + M (%d)", kv_len_after, first_position, M);
+  if (kv_len_after > c.max_kv_len) return failf(KB2_ERR_VALUE, "sequence length %d exceeds max_kv_len %d", kv_len_after, c.max_kv_len);
+  CUDA_TRY(cudaSetDevice(c.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = c.hidden_size, nh = c.num_heads, lora = c.kv_lora_rank, sms = device_sms(c.device);
+  CUDA_TRY(launch_dense_gemm(hidden_dev, L.wkva, h->kv_a, nullptr, M, lora + 64, H, lora + 64, false, sms, s));
+  if (c.q_lora_rank) {
+    void* q_a_normed = (char*)h->q_a + (size_t)c.max_tokens * c.q_lora_rank * 2;
+    CUDA_TRY(launch_dense_gemm(hidden_dev, L.wqa, h->q_a, nullptr, M, c.q_lora_rank, H, c.q_lora_rank, false, sms, s));
+    CUDA_TRY(launch_rmsnorm(h->q_a, nullptr, L.qa_norm, q_a_normed, M, c.q_lora_rank, c.rms_norm_eps, s));
+    CUDA_TRY(launch_dense_gemm(q_a_normed, L.wq, h->q_full, nullptr, M, nh * 192, c.q_lora_rank, nh * 192, false, sms, s));
+  } else {
+    CUDA_TRY(launch_dense_gemm(hidden_dev, L.wq, h->q_full, nullptr, M, nh * 192, H, nh * 192, false, sms, s));
+  }
+  CUDA_TRY(launch_mla_core(h->m, h->q_full, h->kv_a, L.kv_norm, L.inv_freq, L.wkv, positions_dev, kv_indices_dev,
+                           ckv_cache_layer_dev, kpe_cache_layer_dev, h->ckv_bf16, h->kpe_bf16, h->kv_up, h->attn, M,
+                           first_position, kv_len_after, c.sm_scale, sms, s));
+  CUDA_TRY(launch_dense_gemm(h->attn, L.wo, out_dev, nullptr, M, H, nh * 128, H, false, sms, s));
   return KB2_OK;
 }
 

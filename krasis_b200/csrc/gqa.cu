@@ -104,16 +104,18 @@ constexpr int kFK = 64;         // keys per KV tile
 constexpr int kFThreads = 384;
 constexpr int kFStages = 2;
 
-template <int D>
+template <int DQ, int DV>
 struct FmhaSmem {
-  static constexpr int kQBytes = kFQ * D * 2;
-  static constexpr int kKBytes = kFK * D * 2;
+  static constexpr int kQBytes = kFQ * DQ * 2;
+  static constexpr int kKBytes = kFK * DQ * 2;
+  static constexpr int kVBytes = kFK * DV * 2;
   static constexpr int kOffQ = 0;
   static constexpr int kOffK = kOffQ + kQBytes;
   static constexpr int kOffV = kOffK + kFStages * kKBytes;
-  static constexpr int kOffBar = kOffV + kFStages * kKBytes;
+  static constexpr int kOffBar = kOffV + kFStages * kVBytes;
   static constexpr int kTotal = kOffBar + 128;
   static_assert(kTotal <= 227 * 1024, "smem");
+  static_assert(kQBytes % 1024 == 0 && kKBytes % 1024 == 0 && kVBytes % 1024 == 0, "swizzle atoms");
 };
 
 __device__ __forceinline__ uint32_t umma_idesc_bf16_m128_bmn(uint32_t n) {   // B operand MN-major
@@ -140,15 +142,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
-template <int D>
+// DQ = q/k head dim, DV = v head dim.  SRC 0: K/V from the FP8 paged cache (GQA, DQ == DV).  SRC 1: dense BF16 rows
+// (MLA, non-absorbed): k = [k_cache as bf16 [T][kv_ld] at head*(DQ-64) | kpe [T][64] shared by all heads], v = v_cache as
+// bf16 [T][kv_ld] at head*DV.
+template <int DQ, int DV, int SRC>
 __global__ void __launch_bounds__(kFThreads, 1)
     gqa_fmha_kernel(const __grid_constant__ CUtensorMap tmap_q, GqaDims g, const uint8_t* __restrict__ k_cache,
                     const uint8_t* __restrict__ v_cache, const int* __restrict__ kv_indices,
-                    const __nv_bfloat16* __restrict__ q_raw,     // for the output gate
-                    __nv_bfloat16* __restrict__ out,             // [M][nh*D]
-                    int M, int q_start, int kv_len, float sm_scale_log2) {
-  using L = FmhaSmem<D>;
-  constexpr int NC = D / 64;                       // 64-wide d chunks
+                    const __nv_bfloat16* __restrict__ q_raw,     // for the output gate (SRC 0) | kpe rows (SRC 1)
+                    __nv_bfloat16* __restrict__ out,             // [M][nh*DV]
+                    int M, int q_start, int kv_len, float sm_scale_log2, int kv_ld) {
+  using L = FmhaSmem<DQ, DV>;
+  constexpr int D = DQ;
+  constexpr int NC = DQ / 64;                      // 64-wide d chunks of q/k
+  static_assert(SRC == 1 || DQ == DV, "paged FP8 source stores K and V with one head dim");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* q_full = bars;
@@ -198,10 +205,30 @@ __global__ void __launch_bounds__(kFThreads, 1)
       mbar_wait(&kv_empty[stage], phase ^ 1);
       const int key = it * kFK + j;
       const bool valid = key < kv_len;
-      const long long row = valid ? (((long long)kv_indices[key >> 4] * 16 + (key & 15)) * g.nkv + kvh) * D : 0;
       uint8_t* ks = smem + L::kOffK + stage * L::kKBytes;
-      uint8_t* vs = smem + L::kOffV + stage * L::kKBytes;
+      uint8_t* vs = smem + L::kOffV + stage * L::kVBytes;
       const uint32_t rowoff = (j >> 3) * 1024 + (j & 7) * 128;
+      if constexpr (SRC == 1) {
+        const __nv_bfloat16* kup = reinterpret_cast<const __nv_bfloat16*>(k_cache) + (long long)key * kv_ld + head * (DQ - 64);
+        const __nv_bfloat16* vup = reinterpret_cast<const __nv_bfloat16*>(v_cache) + (long long)key * kv_ld + head * DV;
+        const __nv_bfloat16* kpe = q_raw + (long long)key * 64;
+        constexpr int KP = DQ / 16, VP = DV / 16;        // 16-byte pieces per thread (two threads per key)
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+          const int dd = (half * KP + i) * 8, c = dd / 64, p = (dd % 64) / 8;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid) v = *reinterpret_cast<const uint4*>(dd < DQ - 64 ? kup + dd : kpe + (dd - (DQ - 64)));
+          *reinterpret_cast<uint4*>(ks + c * (kFK * 128) + rowoff + ((p ^ (j & 7)) << 4)) = v;
+        }
+#pragma unroll
+        for (int i = 0; i < VP; ++i) {
+          const int dd = (half * VP + i) * 8, c = dd / 64, p = (dd % 64) / 8;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid) v = *reinterpret_cast<const uint4*>(vup + dd);
+          *reinterpret_cast<uint4*>(vs + c * (kFK * 128) + rowoff + ((p ^ (j & 7)) << 4)) = v;
+        }
+      } else {
+      const long long row = valid ? (((long long)kv_indices[key >> 4] * 16 + (key & 15)) * g.nkv + kvh) * D : 0;
 #pragma unroll
       for (int c16 = 0; c16 < D / 32; ++c16) {          // 16 fp8 per step within this thread's half
         const int dd = half * (D / 2) + c16 * 16;        // first head-dim index of this step
@@ -234,6 +261,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
         *reinterpret_cast<uint4*>(vd + (((p) ^ (j & 7)) << 4)) = make_uint4(vo[0], vo[1], vo[2], vo[3]);
         *reinterpret_cast<uint4*>(vd + (((p + 1) ^ (j & 7)) << 4)) = make_uint4(vo[4], vo[5], vo[6], vo[7]);
       }
+      }
       fence_proxy_async_smem();
       mbar_arrive(&kv_full[stage]);
       if (++stage == kFStages) { stage = 0; phase ^= 1; }
@@ -242,13 +270,13 @@ __global__ void __launch_bounds__(kFThreads, 1)
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && n_tiles > 0) {
       const uint32_t id_s = umma_idesc_bf16_m128(kFK);
-      const uint32_t id_o = umma_idesc_bf16_m128_bmn(D);
+      const uint32_t id_o = umma_idesc_bf16_m128_bmn(DV);
       mbar_wait(q_full, 0);
       int stage = 0;
       uint32_t phase = 0, sc_phase = 0, pf_phase = 0;
       const uint32_t q_addr = smem_u32(smem + L::kOffQ);
       auto issue_pv = [&](int st, bool first) {
-        const uint32_t v_addr = smem_u32(smem + L::kOffV + st * L::kKBytes);
+        const uint32_t v_addr = smem_u32(smem + L::kOffV + st * L::kVBytes);
 #pragma unroll
         for (int k = 0; k < kFK / 16; ++k) {
           const uint64_t bd = umma_desc_mn_sw128(v_addr + k * 2048, kFK * 128, 1024);
@@ -356,14 +384,17 @@ __global__ void __launch_bounds__(kFThreads, 1)
         pv_phase ^= 1;
         tc_fence_after_sync();
       }
-      if (rescale) {
+      // tcgen05.ld/st are warp-collective (.sync.aligned): the decision must be warp-uniform; rows that keep their
+      // reference max multiply by 1
+      if (__any_sync(0xffffffffu, rescale)) {
+        const float sc = rescale ? scale_o : 1.f;
 #pragma unroll 2
-        for (int c0 = 0; c0 < D; c0 += 16) {
+        for (int c0 = 0; c0 < DV; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(lane_addr + kColO + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) r[jj] = __float_as_uint(__uint_as_float(r[jj]) * scale_o);
+          for (int jj = 0; jj < 16; ++jj) r[jj] = __float_as_uint(__uint_as_float(r[jj]) * sc);
           tmem_st16(lane_addr + kColO + c0, r);
         }
       }
@@ -386,17 +417,18 @@ __global__ void __launch_bounds__(kFThreads, 1)
       tc_fence_after_sync();
       const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
       const bool live = qi < M;
-      const long long obase = (long long)qi * g.nh * D + (long long)head * D;
+      const long long obase = (long long)qi * g.nh * DV + (long long)head * DV;
       const long long gbase = (long long)qi * g.nh * D * 2 + (long long)head * 2 * D + D;   // gate half of q_raw
+      const bool gated = SRC == 0 && g.gated;
 #pragma unroll 2
-      for (int c0 = 0; c0 < D; c0 += 16) {
+      for (int c0 = 0; c0 < DV; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(lane_addr + kColO + c0, r);
         tmem_ld_wait();
         if (live) {
           uint32_t o[8];
           uint4 gq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (g.gated) {
+          if (gated) {
             gq[0] = *reinterpret_cast<const uint4*>(q_raw + gbase + c0);
             gq[1] = *reinterpret_cast<const uint4*>(q_raw + gbase + c0 + 8);
           }
@@ -404,7 +436,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 2) {
             float a0 = bf16r_(__uint_as_float(r[jj]) * inv_l), a1 = bf16r_(__uint_as_float(r[jj + 1]) * inv_l);
-            if (g.gated) {
+            if (gated) {
               a0 *= bf16r_(1.0f / (1.0f + expf(-__bfloat162float(gp[jj]))));
               a1 *= bf16r_(1.0f / (1.0f + expf(-__bfloat162float(gp[jj + 1]))));
             }
@@ -431,8 +463,8 @@ cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_r
   if (g.d != 128 && g.d != 256) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gqa_fmha_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<128>::kTotal);
-    cudaFuncSetAttribute(gqa_fmha_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<256>::kTotal);
+    cudaFuncSetAttribute(gqa_fmha_kernel<128, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<128, 128>::kTotal);
+    cudaFuncSetAttribute(gqa_fmha_kernel<256, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<256, 256>::kTotal);
     configured = true;
   }
   gqa_prep_kernel<<<M, 256, 8 * g.d * sizeof(float), s>>>(g, (const __nv_bfloat16*)q_raw, (const __nv_bfloat16*)k_raw,
@@ -445,13 +477,162 @@ cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_r
   const float sl2 = (1.0f / sqrtf((float)g.d)) * 1.4426950408889634f;
   dim3 grid((M + kFQ - 1) / kFQ, g.nh);
   if (g.d == 256)
-    gqa_fmha_kernel<256><<<grid, kFThreads, FmhaSmem<256>::kTotal, s>>>(tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache,
-                                                                    kv_indices, (const __nv_bfloat16*)q_raw,
-                                                                    (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2);
+    gqa_fmha_kernel<256, 256, 0><<<grid, kFThreads, FmhaSmem<256, 256>::kTotal, s>>>(
+        tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache, kv_indices, (const __nv_bfloat16*)q_raw,
+        (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0);
   else
-    gqa_fmha_kernel<128><<<grid, kFThreads, FmhaSmem<128>::kTotal, s>>>(tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache,
-                                                                    kv_indices, (const __nv_bfloat16*)q_raw,
-                                                                    (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2);
+    gqa_fmha_kernel<128, 128, 0><<<grid, kFThreads, FmhaSmem<128, 128>::kTotal, s>>>(
+        tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache, kv_indices, (const __nv_bfloat16*)q_raw,
+        (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0);
+  return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// MLA (DeepSeek-V2 / Kimi) prefill — python/krasis/attention.py:213-374 (MLAAttention.forward)
+//   mla_prep_kernel    KV LayerNorm on the compressed latent (:243-246), de-interleave + RoPE (YaRN inv_freq table from the
+//                      host, :119-163,165-211) of k_pe and of every head's q_pe (in place in q_full), cast to FP8 and append
+//                      to the paged latent cache ckv [P][16][lora] / kpe [P][16][rope] (:282-309)
+//   mla_gather_kernel  FP8 pages of the whole sequence -> dense BF16 rows (the reference's per-call page upcast, :324-337)
+//   dense_gemm         k_nope | v = ckv @ [w_kc ; w_vc]^T  — the non-absorbed form: for prefill it needs (192+128)/(576+512)
+//                      of the attention FLOPs of the absorbed form the reference runs (:268-271,364-368); same math, the
+//                      BF16 rounding moves from q_nope_absorbed / attn_out to k_nope / v
+//   gqa_fmha_kernel<192,128,1>  causal softmax(q k^T * sm_scale) v, 16 heads, shared rope key
+// ------------------------------------------------------------------------------------------------
+struct MlaDims {
+  int H, nh, nope, rope, dv, lora;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) mla_prep_kernel(MlaDims m, const __nv_bfloat16* __restrict__ kv_a,   // [M][lora+rope]
+                                                       __nv_bfloat16* __restrict__ q_full,                 // [M][nh*(nope+rope)]
+                                                       const float* __restrict__ kv_norm_w,
+                                                       const float* __restrict__ inv_freq,                 // [rope/2]
+                                                       const int* __restrict__ positions,
+                                                       const int* __restrict__ kv_indices,
+                                                       uint8_t* __restrict__ ckv_cache, uint8_t* __restrict__ kpe_cache,
+                                                       int M) {
+  __shared__ float red[8];
+  const int t = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pos = positions[t];
+  const long long slot = (long long)kv_indices[pos >> 4] * 16 + (pos & 15);
+  const __nv_bfloat16* row = kv_a + (long long)t * (m.lora + m.rope);
+  // KV LayerNorm (flashinfer.norm.rmsnorm: fp32, output BF16) then the cache cast
+  float ss = 0.f;
+  for (int i = tid; i < m.lora; i += 256) {
+    const float v = __bfloat162float(row[i]);
+    ss += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss += red[i];
+  const float inv = rsqrtf(ss / m.lora + m.eps);
+  for (int i = tid; i < m.lora; i += 256) {
+    const float y = bf16r_(__bfloat162float(row[i]) * inv * kv_norm_w[i]);
+    ckv_cache[slot * m.lora + i] = (uint8_t)__nv_cvt_float_to_fp8(y, __NV_SATFINITE, __NV_E4M3);
+  }
+  // RoPE: interleaved (re, im) pairs -> half-split, BF16 tables, every product / sum rounded to BF16 (:190-211)
+  const int half = m.rope / 2, hd = m.nope + m.rope;
+  for (int u = warp; u < m.nh + 1; u += 8) {         // unit nh = the shared key
+    __nv_bfloat16* src = u < m.nh ? q_full + (long long)t * m.nh * hd + (long long)u * hd + m.nope : nullptr;
+    for (int i0 = 0; i0 < half; i0 += 32) {
+      const int i = i0 + lane;
+      float x1 = 0.f, x2 = 0.f;
+      if (i < half) {
+        x1 = __bfloat162float(u < m.nh ? src[2 * i] : row[m.lora + 2 * i]);
+        x2 = __bfloat162float(u < m.nh ? src[2 * i + 1] : row[m.lora + 2 * i + 1]);
+      }
+      __syncwarp();                                  // all lanes have read before anyone overwrites (in place for q)
+      if (i < half) {
+        const float ang = (float)pos * inv_freq[i];
+        const float c = bf16r_(cosf(ang)), sn = bf16r_(sinf(ang));
+        const float r1 = bf16r_(bf16r_(x1 * c) - bf16r_(x2 * sn));
+        const float r2 = bf16r_(bf16r_(x2 * c) + bf16r_(x1 * sn));
+        if (u < m.nh) {
+          src[i] = __float2bfloat16_rn(r1);
+          src[half + i] = __float2bfloat16_rn(r2);
+        } else {
+          kpe_cache[slot * m.rope + i] = (uint8_t)__nv_cvt_float_to_fp8(r1, __NV_SATFINITE, __NV_E4M3);
+          kpe_cache[slot * m.rope + half + i] = (uint8_t)__nv_cvt_float_to_fp8(r2, __NV_SATFINITE, __NV_E4M3);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void fp8x16_to_bf16(const uint4& q, uint4& lo, uint4& hi) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  uint32_t o[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp) {
+      const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * hp)) & 0xFFFF), __NV_E4M3);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+      __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);        // every E4M3 value is exact in BF16
+      o[i * 2 + hp] = *reinterpret_cast<uint32_t*>(&b);
+    }
+  }
+  lo = make_uint4(o[0], o[1], o[2], o[3]);
+  hi = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// one warp per key: ckv_bf16 [T][lora], kpe_bf16 [T][rope]   (lora % 16 == 0, rope % 16 == 0)
+__global__ void __launch_bounds__(256) mla_gather_kernel(const uint8_t* __restrict__ ckv_cache,
+                                                         const uint8_t* __restrict__ kpe_cache,
+                                                         const int* __restrict__ kv_indices, int lora, int rope, int T,
+                                                         __nv_bfloat16* __restrict__ ckv_out,
+                                                         __nv_bfloat16* __restrict__ kpe_out) {
+  const int key = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (key >= T) return;
+  const long long slot = (long long)kv_indices[key >> 4] * 16 + (key & 15);
+  for (int p = lane; p < (lora + rope) / 16; p += 32) {
+    const bool is_c = p < lora / 16;
+    const int off = is_c ? p * 16 : (p - lora / 16) * 16;
+    const uint4 q = *reinterpret_cast<const uint4*>(is_c ? ckv_cache + slot * lora + off : kpe_cache + slot * rope + off);
+    uint4 lo, hi;
+    fp8x16_to_bf16(q, lo, hi);
+    uint4* dst = reinterpret_cast<uint4*>(is_c ? ckv_out + (long long)key * lora + off : kpe_out + (long long)key * rope + off);
+    dst[0] = lo;
+    dst[1] = hi;
+  }
+}
+
+cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
+                              long long ldo, bool out_f32, int num_sms, cudaStream_t s);
+
+// q_full [M][nh*192] (q_proj output; rotated in place), kv_a [M][lora+rope]; w_kv [nh*(nope+dv)][lora] = [w_kc ; w_vc];
+// scratch: ckv_bf16 [T][lora], kpe_bf16 [T][rope], kv_up [T][nh*(nope+dv)]; attn_out [M][nh*dv]
+cudaError_t launch_mla_core(const MlaDims& m, void* q_full, const void* kv_a, const float* kv_norm_w, const float* inv_freq,
+                            const void* w_kv, const int* positions, const int* kv_indices, void* ckv_cache, void* kpe_cache,
+                            void* ckv_bf16, void* kpe_bf16, void* kv_up, void* attn_out, int M, int q_start, int kv_len,
+                            float sm_scale, int num_sms, cudaStream_t s) {
+  if (m.nope != 128 || m.rope != 64 || m.dv != 128 || m.lora % 64) return cudaErrorInvalidValue;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gqa_fmha_kernel<192, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<192, 128>::kTotal);
+    configured = true;
+  }
+  mla_prep_kernel<<<M, 256, 0, s>>>(m, (const __nv_bfloat16*)kv_a, (__nv_bfloat16*)q_full, kv_norm_w, inv_freq, positions,
+                                    kv_indices, (uint8_t*)ckv_cache, (uint8_t*)kpe_cache, M);
+  mla_gather_kernel<<<(kv_len + 7) / 8, 256, 0, s>>>((const uint8_t*)ckv_cache, (const uint8_t*)kpe_cache, kv_indices, m.lora,
+                                                     m.rope, kv_len, (__nv_bfloat16*)ckv_bf16, (__nv_bfloat16*)kpe_bf16);
+  const int up = m.nh * (m.nope + m.dv);
+  cudaError_t e = launch_dense_gemm(ckv_bf16, w_kv, kv_up, nullptr, kv_len, up, m.lora, up, false, num_sms, s);
+  if (e != cudaSuccess) return e;
+  alignas(64) CUtensorMap tq;
+  e = make_tmap_bf16_rows(&tq, q_full, M, (long long)m.nh * (m.nope + m.rope), kFQ);
+  if (e != cudaSuccess) return e;
+  GqaDims g{m.H, m.nh, m.nh, m.nope + m.rope, 0, 0, 0.f, m.eps};
+  const float sl2 = sm_scale * 1.4426950408889634f;
+  dim3 grid((M + kFQ - 1) / kFQ, m.nh);
+  gqa_fmha_kernel<192, 128, 1><<<grid, kFThreads, FmhaSmem<192, 128>::kTotal, s>>>(
+      tq, g, (const uint8_t*)kv_up, (const uint8_t*)((const __nv_bfloat16*)kv_up + (long long)m.nh * m.nope), kv_indices,
+      (const __nv_bfloat16*)kpe_bf16, (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, up);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,13 @@ GQA (Qwen3 / Qwen3-Next gated)   python/krasis/attention.py:496-687
   causal softmax(QK^T * d^-1/2) V             :596-642
   sigmoid output gate                          :665-666
 
+MLA (DeepSeek-V2 / Kimi)          python/krasis/attention.py:213-374 (absorbed form, as the reference runs it)
+  YaRN inverse frequencies + BF16 cos/sin tables   :119-163   (pinned: tests/golden/mla_rope_reference.npz holds
+  de-interleave + half-split rotation in BF16      :165-211    outputs of the reference's own _get_rope_cos_sin/_apply_rope)
+  w_kc absorb / w_vc un-absorb einsums in fp32     :268-271,364-368
+  attention core = FlashInfer MLA over the BF16 upcast of the FP8 latent pages (:324-361): third-party, absent from
+  the tree -> restated as fp32 softmax attention; parity of that core is unpinned beyond the reference's own cos>0.999 check
+
 tests/golden/make_attention_golden.py imports the REFERENCE's own linear_attention module (CPU, eager) to
 generate fixtures these functions are pinned against.
 """
@@ -220,3 +227,83 @@ def gqa_layer_prefill(hidden, w, cfg, positions, k_cache=None, v_cache=None, kv_
     if gated:
         flat = flat * torch.sigmoid(gate)
     return F.linear(flat.to(torch.bfloat16), w["o_proj"]), k_cache, v_cache
+
+
+# --------------------------------------------------------------------------------------------- MLA
+
+def mla_inv_freq(rope_dim, theta, rope_scaling=None):
+    """attention.py:129-157 (YaRN blend as HF DeepseekV2YarnRotaryEmbedding)."""
+    dim = rope_dim
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2).float() / dim))
+    cfg = rope_scaling or {}
+    factor = cfg.get("factor", 1.0)
+    if factor > 1.0:
+        original_max = cfg.get("original_max_position_embeddings", 4096)
+        beta_fast, beta_slow = cfg.get("beta_fast", 32.0), cfg.get("beta_slow", 1.0)
+        low = math.floor(dim * math.log(original_max / (beta_fast * 2 * math.pi)) / (2 * math.log(theta)))
+        high = math.ceil(dim * math.log(original_max / (beta_slow * 2 * math.pi)) / (2 * math.log(theta)))
+        low, high = max(low, 0), min(high, dim // 2 - 1)
+        ramp = torch.clamp((torch.arange(dim // 2).float() - low) / max(high - low, 0.001), 0, 1)
+        mask = 1.0 - ramp
+        freqs = (freqs / factor) * (1 - mask) + freqs * mask
+    return freqs
+
+
+def mla_rope_tables(max_len, rope_dim, theta, rope_scaling=None):
+    f = torch.outer(torch.arange(max_len, dtype=torch.float32), mla_inv_freq(rope_dim, theta, rope_scaling))
+    return f.cos().to(torch.bfloat16), f.sin().to(torch.bfloat16)
+
+
+def mla_deinterleave(x):
+    d = x.shape[-1]
+    return x.view(*x.shape[:-1], d // 2, 2).transpose(-1, -2).reshape(x.shape)
+
+
+def mla_apply_rope(x, cos, sin):
+    """x [M, heads, rope] bf16 interleaved -> de-interleaved and rotated, BF16 arithmetic (attention.py:165-211)."""
+    x = mla_deinterleave(x)
+    d2 = x.shape[-1] // 2
+    c, s = cos.unsqueeze(1), sin.unsqueeze(1)
+    x1, x2 = x[..., :d2], x[..., d2:]
+    return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1)
+
+
+def mla_sm_scale(nope, rope, rope_scaling=None):
+    s = 1.0 / math.sqrt(nope + rope)
+    cfg = rope_scaling or {}
+    if cfg.get("factor", 1.0) > 1.0:
+        m = 0.1 * cfg.get("mscale_all_dim", 0) * math.log(cfg["factor"]) + 1.0
+        s *= m * m
+    return s
+
+
+def mla_layer_prefill(hidden, w, cfg, positions, ckv_cache=None, kpe_cache=None, kv_dtype=torch.float8_e4m3fn):
+    """MLAAttention.forward (attention.py:213-374) for BF16 weights, absorbed form.  Returns (out [M,H] bf16, ckv_cache
+    [L,lora], kpe_cache [L,rope]) with the caches stored in kv_dtype."""
+    nh, nope, rope, dv, lora = cfg["nh"], cfg["nope"], cfg["rope"], cfg["dv"], cfg["lora"]
+    M = hidden.shape[0]
+    kv_out = F.linear(hidden, w["kv_a_proj_with_mqa"])
+    ckv = rmsnorm(kv_out[:, :lora], w["kv_a_layernorm"], cfg["eps"])
+    k_pe = kv_out[:, lora:]
+    if cfg.get("q_lora"):
+        q_c = rmsnorm(F.linear(hidden, w["q_a_proj"]), w["q_a_layernorm"], cfg["eps"])
+        q_full = F.linear(q_c, w["q_b_proj"])
+    else:
+        q_full = F.linear(hidden, w["q_proj"])
+    q_full = q_full.reshape(M, nh, nope + rope)
+    q_nope, q_pe = q_full[:, :, :nope], q_full[:, :, nope:]
+    cos, sin = mla_rope_tables(int(positions.max()) + 1, rope, cfg["theta"], cfg.get("rope_scaling"))
+    q_pe = mla_apply_rope(q_pe, cos[positions], sin[positions])
+    k_pe = mla_apply_rope(k_pe.unsqueeze(1), cos[positions], sin[positions]).squeeze(1)
+    q_abs = torch.einsum("mhi,hid->mhd", q_nope.float(), w["w_kc"].float()).to(torch.bfloat16)
+    ckv_new, kpe_new = ckv.to(kv_dtype), k_pe.to(kv_dtype)
+    ckv_cache = ckv_new if ckv_cache is None else torch.cat([ckv_cache, ckv_new], dim=0)
+    kpe_cache = kpe_new if kpe_cache is None else torch.cat([kpe_cache, kpe_new], dim=0)
+    cf, pf = ckv_cache.to(torch.bfloat16).float(), kpe_cache.to(torch.bfloat16).float()
+    s = (torch.einsum("mhd,ld->hml", q_abs.float(), cf) + torch.einsum("mhr,lr->hml", q_pe.float(), pf)) \
+        * mla_sm_scale(nope, rope, cfg.get("rope_scaling"))
+    L = cf.shape[0]
+    s = s.masked_fill((torch.arange(L)[None, :] > positions[:, None])[None], float("-inf"))
+    attn_out = torch.einsum("hml,ld->mhd", torch.softmax(s, dim=-1), cf).to(torch.bfloat16)
+    proj = torch.einsum("mhd,hod->mho", attn_out.float(), w["w_vc"].float()).to(torch.bfloat16)
+    return F.linear(proj.reshape(M, nh * dv), w["o_proj"]), ckv_cache, kpe_cache

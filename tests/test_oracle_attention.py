@@ -4,6 +4,7 @@ chunked form against the definitional recurrence."""
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import attention as A
@@ -75,3 +76,60 @@ def test_gqa_rope_and_cache_semantics():
     cos, sin = A.rope_tables(8, 8, 10000.0)
     r = A.apply_rope(q, cos[torch.tensor([0, 3, 7])], sin[torch.tensor([0, 3, 7])])
     assert torch.equal(r[..., 8:], q[..., 8:]) and torch.equal(r[0], q[0])
+
+
+# ------------------------------------------------------------------------------------------------ MLA
+
+MLA_G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mla_rope_reference.npz"))
+V2_LITE_ROPE = {"beta_fast": 32, "beta_slow": 1, "factor": 40, "mscale": 0.707, "mscale_all_dim": 0.707,
+                "original_max_position_embeddings": 4096, "type": "yarn"}
+
+
+@pytest.mark.parametrize("tag,scaling", [("yarn", V2_LITE_ROPE), ("plain", None)])
+def test_mla_rope_matches_reference_execution(tag, scaling):
+    """YaRN tables, de-interleave + BF16 rotation and sm_scale: bit-exact against outputs of the reference's own code."""
+    rows = torch.from_numpy(MLA_G[f"{tag}_rows"])
+    cos, sin = A.mla_rope_tables(5000, 64, 10000.0, scaling)
+    assert np.array_equal(cos[rows].float().numpy(), MLA_G[f"{tag}_cos"])
+    assert np.array_equal(sin[rows].float().numpy(), MLA_G[f"{tag}_sin"])
+    pos = torch.from_numpy(MLA_G[f"{tag}_pos"])
+    q = torch.from_numpy(MLA_G[f"{tag}_q_in"]).to(torch.bfloat16)
+    k = torch.from_numpy(MLA_G[f"{tag}_k_in"]).to(torch.bfloat16)
+    assert np.array_equal(A.mla_apply_rope(q, cos[pos], sin[pos]).float().numpy(), MLA_G[f"{tag}_q_out"])
+    assert np.array_equal(A.mla_apply_rope(k, cos[pos], sin[pos]).float().numpy(), MLA_G[f"{tag}_k_out"])
+    assert A.mla_sm_scale(128, 64, scaling) == float(MLA_G[f"{tag}_sm_scale"])
+
+
+def test_mla_absorbed_equals_explicit_heads():
+    """The absorbed form the reference runs == ordinary multi-head attention with k_nope = ckv W_kc^T, v = ckv W_vc^T
+    (what the B200 path computes), to BF16-rounding tolerance."""
+    torch.manual_seed(3)
+    nh, nope, rope, dv, lora, H, M = 4, 128, 64, 128, 512, 256, 70
+    bf = torch.bfloat16
+    w = dict(q_proj=(torch.randn(nh * (nope + rope), H) * 0.06).to(bf), kv_a_proj_with_mqa=(torch.randn(lora + rope, H) * 0.06).to(bf),
+             kv_a_layernorm=(1 + 0.1 * torch.randn(lora)).to(bf), w_kc=(torch.randn(nh, nope, lora) * 0.04).to(bf),
+             w_vc=(torch.randn(nh, dv, lora) * 0.04).to(bf), o_proj=(torch.randn(H, nh * dv) * 0.05).to(bf))
+    cfg = dict(nh=nh, nope=nope, rope=rope, dv=dv, lora=lora, theta=10000.0, eps=1e-6, rope_scaling=V2_LITE_ROPE)
+    x = torch.randn(M, H).to(bf)
+    pos = torch.arange(M)
+    out, ckv, kpe = A.mla_layer_prefill(x, w, cfg, pos)
+    # explicit heads from the same caches
+    cf, pf = ckv.to(bf).float(), kpe.to(bf).float()
+    k_nope = torch.einsum("ld,hid->lhi", cf, w["w_kc"].float())
+    v = torch.einsum("ld,hod->lho", cf, w["w_vc"].float())
+    q_full = torch.nn.functional.linear(x, w["q_proj"]).reshape(M, nh, nope + rope)
+    cos, sin = A.mla_rope_tables(M, rope, 10000.0, V2_LITE_ROPE)
+    q_pe = A.mla_apply_rope(q_full[:, :, nope:], cos[pos], sin[pos]).float()
+    s = (torch.einsum("mhi,lhi->hml", q_full[:, :, :nope].float(), k_nope) + torch.einsum("mhr,lr->hml", q_pe, pf)) \
+        * A.mla_sm_scale(nope, rope, V2_LITE_ROPE)
+    s = s.masked_fill((torch.arange(M)[None, :] > pos[:, None])[None], float("-inf"))
+    o = torch.einsum("hml,lho->mho", torch.softmax(s, -1), v).to(bf)
+    want = torch.nn.functional.linear(o.reshape(M, nh * dv), w["o_proj"]).float()
+    assert (out.float() - want).abs().max() <= 2 * 2 ** -7 * want.abs().max()
+
+
+def test_mla_product_inv_freq_is_the_oracles():
+    from krasis_b200.attention import mla_rope_inv_freq, mla_sm_scale
+    for sc in (V2_LITE_ROPE, None):
+        assert np.array_equal(mla_rope_inv_freq(64, 10000.0, sc), A.mla_inv_freq(64, 10000.0, sc).numpy())
+        assert mla_sm_scale(128, 64, sc) == A.mla_sm_scale(128, 64, sc)
