@@ -33,7 +33,8 @@ struct GqaDims {
 };
 cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_raw, const void* v_raw, const float* q_norm,
                             const float* k_norm, const int* positions, const int* kv_indices, void* q_rot, void* k_cache,
-                            void* v_cache, void* attn_out, int M, int q_start, int kv_len, cudaStream_t s);
+                            void* v_cache, void* k_bf, void* v_bf, void* attn_out, int M, int q_start, int kv_len,
+                            cudaStream_t s);
 struct MlaDims {
   int H, nh, nope, rope, dv, lora;
   float eps;
@@ -307,6 +308,8 @@ struct kb2_gqa {
   GqaDims g{};
   std::vector<GqaLayer> layers;
   void *q_raw = nullptr, *k_raw = nullptr, *v_raw = nullptr, *q_rot = nullptr, *attn = nullptr;
+  void *k_bf = nullptr, *v_bf = nullptr;     // dense BF16 upcast of the sequence's FP8 pages, [kv_cap][nkv*d] each
+  long long kv_cap = 0;
 };
 
 KB2_API int kb2_gqa_create(const kb2_gqa_config* c, kb2_gqa** out) {
@@ -341,6 +344,7 @@ KB2_API void kb2_gqa_destroy(kb2_gqa* h) {
   cudaSetDevice(h->cfg.device);
   for (auto& L : h->layers) { cudaFree(L.wq); cudaFree(L.wk); cudaFree(L.wv); cudaFree(L.wo); cudaFree(L.q_norm); cudaFree(L.k_norm); }
   cudaFree(h->q_raw); cudaFree(h->k_raw); cudaFree(h->v_raw); cudaFree(h->q_rot); cudaFree(h->attn);
+  cudaFree(h->k_bf); cudaFree(h->v_bf);
   delete h;
 }
 
@@ -386,8 +390,17 @@ KB2_API int kb2_gqa_forward(kb2_gqa* h, int layer, const void* hidden_dev, const
   CUDA_TRY(launch_dense_gemm(hidden_dev, L.wq, h->q_raw, nullptr, M, qw, H, qw, false, sms, s));
   CUDA_TRY(launch_dense_gemm(hidden_dev, L.wk, h->k_raw, nullptr, M, kvd, H, kvd, false, sms, s));
   CUDA_TRY(launch_dense_gemm(hidden_dev, L.wv, h->v_raw, nullptr, M, kvd, H, kvd, false, sms, s));
+  if (kv_len_after > h->kv_cap) {              // grow the upcast scratch (cudaFree synchronises: no kernel still reads it)
+    const long long cap = kv_len_after > 2 * h->kv_cap ? kv_len_after : 2 * h->kv_cap;
+    cudaFree(h->k_bf); cudaFree(h->v_bf);
+    h->k_bf = h->v_bf = nullptr;
+    h->kv_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->k_bf, (size_t)cap * kvd * 2));
+    CUDA_TRY(cudaMalloc(&h->v_bf, (size_t)cap * kvd * 2));
+    h->kv_cap = cap;
+  }
   CUDA_TRY(launch_gqa_core(h->g, h->q_raw, h->k_raw, h->v_raw, L.q_norm, L.k_norm, positions_dev, kv_indices_dev, h->q_rot,
-                           k_cache_layer_dev, v_cache_layer_dev, h->attn, M, first_position, kv_len_after, s));
+                           k_cache_layer_dev, v_cache_layer_dev, h->k_bf, h->v_bf, h->attn, M, first_position, kv_len_after, s));
   CUDA_TRY(launch_dense_gemm(h->attn, L.wo, out_dev, nullptr, M, H, qd, H, false, sms, s));
   return KB2_OK;
 }

@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256, 1) gdn_chunk_scan_kernel(GdnDims d, const
                                                                 const float* __restrict__ intra,
                                                                 const float* __restrict__ gcum, int M, int n_chunks,
                                                                 float* __restrict__ state,       // [nv][dk][dv] in/out
-                                                                float* __restrict__ core_out) {  // [M][nv][dv]
+                                                                __nv_bfloat16* __restrict__ core_out) {  // [M][nv][dv] (core_attn_out.to(bf16))
   extern __shared__ __align__(16) unsigned char smraw[];
   const int h = blockIdx.x, sl = blockIdx.y, r = d.nv / d.nk, kh = h / r;
   const int dk = d.dk, dv = d.dv, kd = d.nk * dk, vd = d.nv * dv;
@@ -602,8 +602,8 @@ __global__ void __launch_bounds__(256, 1) gdn_chunk_scan_kernel(GdnDims d, const
       for (int nt = 0; nt < NTW; ++nt) {
         const int r0 = mt * 16 + g, c0 = sl * kSV + n0 + nt * 8 + 2 * t;
         const int ta = t0 + r0, tb = t0 + r0 + 8;
-        if (ta < M) *reinterpret_cast<float2*>(core_out + (long long)ta * vd + h * dv + c0) = make_float2(it[nt][0], it[nt][1]);
-        if (tb < M) *reinterpret_cast<float2*>(core_out + (long long)tb * vd + h * dv + c0) = make_float2(it[nt][2], it[nt][3]);
+        if (ta < M) *reinterpret_cast<__nv_bfloat162*>(core_out + (long long)ta * vd + h * dv + c0) = __floats2bfloat162_rn(it[nt][0], it[nt][1]);
+        if (tb < M) *reinterpret_cast<__nv_bfloat162*>(core_out + (long long)tb * vd + h * dv + c0) = __floats2bfloat162_rn(it[nt][2], it[nt][3]);
       }
     }
     // (3) S = S * exp(g_last) + K^T @ (decayed v_new): warp w owns state rows [16w, 16w+16) (dk = 128 -> 8 warps).
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(256, 1) gdn_chunk_scan_kernel(GdnDims d, const
 }
 
 // gated RMSNorm: one warp per (token, head)
-__global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const float* __restrict__ core,
+__global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const __nv_bfloat16* __restrict__ core,
                                                        const __nv_bfloat16* __restrict__ qkvz,
                                                        const float* __restrict__ norm_w, int M,
                                                        __nv_bfloat16* __restrict__ out) {   // [M][nv*dv]
@@ -649,14 +649,14 @@ __global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const float* _
   const int zcol = (h / r) * G + 2 * d.dk + r * d.dv + (h % r) * d.dv;
   float ss = 0.f;
   for (int c = lane; c < d.dv; c += 32) {
-    const float x = bf16r(core[(long long)t * vd + h * d.dv + c]);          // core_attn_out.to(bf16)
+    const float x = __bfloat162float(core[(long long)t * vd + h * d.dv + c]);          // core_attn_out.to(bf16), done by the scan
     ss += x * x;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float inv = rsqrtf(ss / d.dv + d.eps);
   for (int c = lane; c < d.dv; c += 32) {
-    const float x = bf16r(core[(long long)t * vd + h * d.dv + c]);
+    const float x = __bfloat162float(core[(long long)t * vd + h * d.dv + c]);
     const float xn = bf16r(norm_w[c] * (x * inv));
     const float z = __bfloat162float(qkvz[(long long)t * ld + zcol + c]);
     const float sz = bf16r(z / (1.0f + expf(-z)));
@@ -709,11 +709,12 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
   const int sv = d.nv * (d.dv / 32) >= 96 ? 32 : (d.nv * (d.dv / 16) >= 96 ? 16 : 8);
 #define KB2_SCAN(SV)                                                                                                  \
   gdn_chunk_scan_kernel<SV><<<dim3(d.nv, d.dv / SV), 256, gdn_scan_smem(d), s>>>(                                      \
-      d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, vcorr, kcd, intra, gcum, M, n_chunks, rec_state, core)
+      d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, vcorr, kcd, intra, gcum, M, n_chunks, rec_state,       \
+      (__nv_bfloat16*)core)
   if (sv == 32) KB2_SCAN(32); else if (sv == 16) KB2_SCAN(16); else KB2_SCAN(8);
 #undef KB2_SCAN
   const long long nw = (long long)M * d.nv;
-  gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, core, (const __nv_bfloat16*)qkvz, norm_w, M,
+  gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, (const __nv_bfloat16*)core, (const __nv_bfloat16*)qkvz, norm_w, M,
                                                                   (__nv_bfloat16*)normed_out);
   return cudaGetLastError();
 }

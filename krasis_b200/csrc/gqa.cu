@@ -142,20 +142,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
-// DQ = q/k head dim, DV = v head dim.  SRC 0: K/V from the FP8 paged cache (GQA, DQ == DV).  SRC 1: dense BF16 rows
-// (MLA, non-absorbed): k = [k_cache as bf16 [T][kv_ld] at head*(DQ-64) | kpe [T][64] shared by all heads], v = v_cache as
-// bf16 [T][kv_ld] at head*DV.
-template <int DQ, int DV, int SRC>
+// DQ = q/k head dim, DV = v head dim.  K and V are dense BF16 rows (the FP8 pages of the sequence are upcast once per call
+// by *_gather_kernel, exactly like the reference's page upcast attention.py:324-337) and stream in by TMA:
+//   tmap_k   [kv_len][*]: this head's keys at column k_col0 + kvh * (PE ? DQ - 64 : DQ)
+//   tmap_kpe [kv_len][64] (PE only, MLA): the rope part of the key, shared by all heads, is the last 64-wide chunk
+//   tmap_v   [kv_len][*]: this head's values at column v_col0 + kvh * DV
+template <int DQ, int DV, bool PE>
 __global__ void __launch_bounds__(kFThreads, 1)
-    gqa_fmha_kernel(const __grid_constant__ CUtensorMap tmap_q, GqaDims g, const uint8_t* __restrict__ k_cache,
-                    const uint8_t* __restrict__ v_cache, const int* __restrict__ kv_indices,
-                    const __nv_bfloat16* __restrict__ q_raw,     // for the output gate (SRC 0) | kpe rows (SRC 1)
+    gqa_fmha_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_kpe, const __grid_constant__ CUtensorMap tmap_v, GqaDims g,
+                    const __nv_bfloat16* __restrict__ q_raw,     // for the output gate (g.gated)
                     __nv_bfloat16* __restrict__ out,             // [M][nh*DV]
-                    int M, int q_start, int kv_len, float sm_scale_log2, int kv_ld) {
+                    int M, int q_start, int kv_len, float sm_scale_log2, int k_col0, int v_col0) {
   using L = FmhaSmem<DQ, DV>;
   constexpr int D = DQ;
   constexpr int NC = DQ / 64;                      // 64-wide d chunks of q/k
-  static_assert(SRC == 1 || DQ == DV, "paged FP8 source stores K and V with one head dim");
+  constexpr int NKC = PE ? NC - 1 : NC;            // of which from tmap_k
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* q_full = bars;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 128);
+      mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
@@ -196,76 +198,25 @@ __global__ void __launch_bounds__(kFThreads, 1)
   constexpr uint32_t kColS = 0, kColP = 64, kColO = 128;
 
   if (warp < 4) {
-    // ------------------------------------------------------------ KV loaders
-    const int tid = threadIdx.x;           // 0..127
-    const int j = tid >> 1, half = tid & 1;    // key within tile, which half of the head dim
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int it = 0; it < n_tiles; ++it) {
-      mbar_wait(&kv_empty[stage], phase ^ 1);
-      const int key = it * kFK + j;
-      const bool valid = key < kv_len;
-      uint8_t* ks = smem + L::kOffK + stage * L::kKBytes;
-      uint8_t* vs = smem + L::kOffV + stage * L::kVBytes;
-      const uint32_t rowoff = (j >> 3) * 1024 + (j & 7) * 128;
-      if constexpr (SRC == 1) {
-        const __nv_bfloat16* kup = reinterpret_cast<const __nv_bfloat16*>(k_cache) + (long long)key * kv_ld + head * (DQ - 64);
-        const __nv_bfloat16* vup = reinterpret_cast<const __nv_bfloat16*>(v_cache) + (long long)key * kv_ld + head * DV;
-        const __nv_bfloat16* kpe = q_raw + (long long)key * 64;
-        constexpr int KP = DQ / 16, VP = DV / 16;        // 16-byte pieces per thread (two threads per key)
+    // ------------------------------------------------------------ KV producer: one thread issues the TMA boxes of a tile
+    if (warp == 0 && lane == 0) {
+      const int kx = k_col0 + kvh * (PE ? DQ - 64 : DQ), vx = v_col0 + kvh * DV;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_tiles; ++it) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* ks = smem + L::kOffK + stage * L::kKBytes;
+        uint8_t* vs = smem + L::kOffV + stage * L::kVBytes;
+        mbar_arrive_expect_tx(&kv_full[stage], L::kKBytes + L::kVBytes);
 #pragma unroll
-        for (int i = 0; i < KP; ++i) {
-          const int dd = (half * KP + i) * 8, c = dd / 64, p = (dd % 64) / 8;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid) v = *reinterpret_cast<const uint4*>(dd < DQ - 64 ? kup + dd : kpe + (dd - (DQ - 64)));
-          *reinterpret_cast<uint4*>(ks + c * (kFK * 128) + rowoff + ((p ^ (j & 7)) << 4)) = v;
-        }
+        for (int c = 0; c < NKC; ++c) tma_load_2d(ks + c * (kFK * 128), &tmap_k, kx + c * 64, it * kFK, &kv_full[stage]);
+        if constexpr (PE) tma_load_2d(ks + NKC * (kFK * 128), &tmap_kpe, 0, it * kFK, &kv_full[stage]);
 #pragma unroll
-        for (int i = 0; i < VP; ++i) {
-          const int dd = (half * VP + i) * 8, c = dd / 64, p = (dd % 64) / 8;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid) v = *reinterpret_cast<const uint4*>(vup + dd);
-          *reinterpret_cast<uint4*>(vs + c * (kFK * 128) + rowoff + ((p ^ (j & 7)) << 4)) = v;
-        }
-      } else {
-      const long long row = valid ? (((long long)kv_indices[key >> 4] * 16 + (key & 15)) * g.nkv + kvh) * D : 0;
-#pragma unroll
-      for (int c16 = 0; c16 < D / 32; ++c16) {          // 16 fp8 per step within this thread's half
-        const int dd = half * (D / 2) + c16 * 16;        // first head-dim index of this step
-        uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
-        if (valid) {
-          kq = *reinterpret_cast<const uint4*>(k_cache + row + dd);
-          vq = *reinterpret_cast<const uint4*>(v_cache + row + dd);
-        }
-        const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
-        uint32_t ko[8], vo[8];
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-#pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {
-            const __half2_raw hk = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((kw[w] >> (16 * hp)) & 0xFFFF), __NV_E4M3);
-            const __half2_raw hv = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((vw[w] >> (16 * hp)) & 0xFFFF), __NV_E4M3);
-            const float2 fk = __half22float2(*reinterpret_cast<const __half2*>(&hk));
-            const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&hv));
-            __nv_bfloat162 bk = __floats2bfloat162_rn(fk.x, fk.y), bv = __floats2bfloat162_rn(fv.x, fv.y);
-            ko[w * 2 + hp] = *reinterpret_cast<uint32_t*>(&bk);
-            vo[w * 2 + hp] = *reinterpret_cast<uint32_t*>(&bv);
-          }
-        }
-        // 16 bf16 = two 16-byte pieces p, p+1 of d-chunk c
-        const int c = dd / 64, p = (dd % 64) / 8;
-        uint8_t* kd = ks + c * (kFK * 128) + rowoff;
-        uint8_t* vd = vs + c * (kFK * 128) + rowoff;
-        *reinterpret_cast<uint4*>(kd + (((p) ^ (j & 7)) << 4)) = make_uint4(ko[0], ko[1], ko[2], ko[3]);
-        *reinterpret_cast<uint4*>(kd + (((p + 1) ^ (j & 7)) << 4)) = make_uint4(ko[4], ko[5], ko[6], ko[7]);
-        *reinterpret_cast<uint4*>(vd + (((p) ^ (j & 7)) << 4)) = make_uint4(vo[0], vo[1], vo[2], vo[3]);
-        *reinterpret_cast<uint4*>(vd + (((p + 1) ^ (j & 7)) << 4)) = make_uint4(vo[4], vo[5], vo[6], vo[7]);
+        for (int c = 0; c < DV / 64; ++c) tma_load_2d(vs + c * (kFK * 128), &tmap_v, vx + c * 64, it * kFK, &kv_full[stage]);
+        if (++stage == kFStages) { stage = 0; phase ^= 1; }
       }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&kv_full[stage]);
-      if (++stage == kFStages) { stage = 0; phase ^= 1; }
     }
+    __syncwarp();
   } else if (warp == 4) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && n_tiles > 0) {
@@ -419,7 +370,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
       const bool live = qi < M;
       const long long obase = (long long)qi * g.nh * DV + (long long)head * DV;
       const long long gbase = (long long)qi * g.nh * D * 2 + (long long)head * 2 * D + D;   // gate half of q_raw
-      const bool gated = SRC == 0 && g.gated;
+      const bool gated = g.gated != 0;
 #pragma unroll 2
       for (int c0 = 0; c0 < DV; c0 += 16) {
         uint32_t r[16];
@@ -455,38 +406,81 @@ __global__ void __launch_bounds__(kFThreads, 1)
   if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
+__device__ __forceinline__ void fp8x16_to_bf16(const uint4& q, uint4& lo, uint4& hi) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  uint32_t o[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp) {
+      const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * hp)) & 0xFFFF), __NV_E4M3);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+      __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);        // every E4M3 value is exact in BF16
+      o[i * 2 + hp] = *reinterpret_cast<uint32_t*>(&b);
+    }
+  }
+  lo = make_uint4(o[0], o[1], o[2], o[3]);
+  hi = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// FP8 pages of the sequence -> dense BF16 rows k_out/v_out [T][nkv*d] (every E4M3 value is exact in BF16)
+__global__ void __launch_bounds__(256) gqa_gather_kernel(const uint8_t* __restrict__ k_cache, const uint8_t* __restrict__ v_cache,
+                                                         const int* __restrict__ kv_indices, int row_bytes, int T,
+                                                         __nv_bfloat16* __restrict__ k_out, __nv_bfloat16* __restrict__ v_out) {
+  const int pieces = row_bytes / 16;                       // 16 fp8 per piece
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)T * pieces * 2) return;
+  const int which = (int)(idx / ((long long)T * pieces));  // 0 = K, 1 = V
+  const long long r = idx % ((long long)T * pieces);
+  const int key = (int)(r / pieces), p = (int)(r % pieces);
+  const long long slot = (long long)kv_indices[key >> 4] * 16 + (key & 15);
+  const uint4 q = *reinterpret_cast<const uint4*>((which ? v_cache : k_cache) + slot * row_bytes + p * 16);
+  uint4 lo, hi;
+  fp8x16_to_bf16(q, lo, hi);
+  uint4* dst = reinterpret_cast<uint4*>((which ? v_out : k_out) + (long long)key * row_bytes + p * 16);
+  dst[0] = lo;
+  dst[1] = hi;
+}
+
 cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
 
+// k_bf / v_bf: scratch [kv_len][nkv*d] bf16
 cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_raw, const void* v_raw, const float* q_norm,
                             const float* k_norm, const int* positions, const int* kv_indices, void* q_rot, void* k_cache,
-                            void* v_cache, void* attn_out, int M, int q_start, int kv_len, cudaStream_t s) {
+                            void* v_cache, void* k_bf, void* v_bf, void* attn_out, int M, int q_start, int kv_len,
+                            cudaStream_t s) {
   if (g.d != 128 && g.d != 256) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gqa_fmha_kernel<128, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<128, 128>::kTotal);
-    cudaFuncSetAttribute(gqa_fmha_kernel<256, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<256, 256>::kTotal);
+    cudaFuncSetAttribute(gqa_fmha_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<128, 128>::kTotal);
+    cudaFuncSetAttribute(gqa_fmha_kernel<256, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<256, 256>::kTotal);
     configured = true;
   }
   gqa_prep_kernel<<<M, 256, 8 * g.d * sizeof(float), s>>>(g, (const __nv_bfloat16*)q_raw, (const __nv_bfloat16*)k_raw,
                                                           (const __nv_bfloat16*)v_raw, q_norm, k_norm, positions,
                                                           kv_indices, (__nv_bfloat16*)q_rot, (uint8_t*)k_cache,
                                                           (uint8_t*)v_cache, M);
-  alignas(64) CUtensorMap tq;
+  const int row = g.nkv * g.d;
+  const long long n_thr = (long long)kv_len * (row / 16) * 2;
+  gqa_gather_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, s>>>((const uint8_t*)k_cache, (const uint8_t*)v_cache, kv_indices,
+                                                                    row, kv_len, (__nv_bfloat16*)k_bf, (__nv_bfloat16*)v_bf);
+  alignas(64) CUtensorMap tq, tk, tv;
   cudaError_t e = make_tmap_bf16_rows(&tq, q_rot, M, (long long)g.nh * g.d, kFQ);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tk, k_bf, kv_len, row, kFK);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tv, v_bf, kv_len, row, kFK);
   if (e != cudaSuccess) return e;
   const float sl2 = (1.0f / sqrtf((float)g.d)) * 1.4426950408889634f;
   dim3 grid((M + kFQ - 1) / kFQ, g.nh);
   if (g.d == 256)
-    gqa_fmha_kernel<256, 256, 0><<<grid, kFThreads, FmhaSmem<256, 256>::kTotal, s>>>(
-        tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache, kv_indices, (const __nv_bfloat16*)q_raw,
-        (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0);
+    gqa_fmha_kernel<256, 256, false><<<grid, kFThreads, FmhaSmem<256, 256>::kTotal, s>>>(
+        tq, tk, tk, tv, g, (const __nv_bfloat16*)q_raw, (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0, 0);
   else
-    gqa_fmha_kernel<128, 128, 0><<<grid, kFThreads, FmhaSmem<128, 128>::kTotal, s>>>(
-        tq, g, (const uint8_t*)k_cache, (const uint8_t*)v_cache, kv_indices, (const __nv_bfloat16*)q_raw,
-        (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0);
+    gqa_fmha_kernel<128, 128, false><<<grid, kFThreads, FmhaSmem<128, 128>::kTotal, s>>>(
+        tq, tk, tk, tv, g, (const __nv_bfloat16*)q_raw, (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0, 0);
   return cudaGetLastError();
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // MLA (DeepSeek-V2 / Kimi) prefill — python/krasis/attention.py:213-374 (MLAAttention.forward)
@@ -564,23 +558,6 @@ __global__ void __launch_bounds__(256) mla_prep_kernel(MlaDims m, const __nv_bfl
   }
 }
 
-__device__ __forceinline__ void fp8x16_to_bf16(const uint4& q, uint4& lo, uint4& hi) {
-  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-  uint32_t o[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int hp = 0; hp < 2; ++hp) {
-      const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * hp)) & 0xFFFF), __NV_E4M3);
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
-      __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);        // every E4M3 value is exact in BF16
-      o[i * 2 + hp] = *reinterpret_cast<uint32_t*>(&b);
-    }
-  }
-  lo = make_uint4(o[0], o[1], o[2], o[3]);
-  hi = make_uint4(o[4], o[5], o[6], o[7]);
-}
-
 // one warp per key: ckv_bf16 [T][lora], kpe_bf16 [T][rope]   (lora % 16 == 0, rope % 16 == 0)
 __global__ void __launch_bounds__(256) mla_gather_kernel(const uint8_t* __restrict__ ckv_cache,
                                                          const uint8_t* __restrict__ kpe_cache,
@@ -614,7 +591,7 @@ cudaError_t launch_mla_core(const MlaDims& m, void* q_full, const void* kv_a, co
   if (m.nope != 128 || m.rope != 64 || m.dv != 128 || m.lora % 64) return cudaErrorInvalidValue;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gqa_fmha_kernel<192, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<192, 128>::kTotal);
+    cudaFuncSetAttribute(gqa_fmha_kernel<192, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<192, 128>::kTotal);
     configured = true;
   }
   mla_prep_kernel<<<M, 256, 0, s>>>(m, (const __nv_bfloat16*)kv_a, (__nv_bfloat16*)q_full, kv_norm_w, inv_freq, positions,
@@ -624,15 +601,18 @@ cudaError_t launch_mla_core(const MlaDims& m, void* q_full, const void* kv_a, co
   const int up = m.nh * (m.nope + m.dv);
   cudaError_t e = launch_dense_gemm(ckv_bf16, w_kv, kv_up, nullptr, kv_len, up, m.lora, up, false, num_sms, s);
   if (e != cudaSuccess) return e;
-  alignas(64) CUtensorMap tq;
+  alignas(64) CUtensorMap tq, tk, tpe;
   e = make_tmap_bf16_rows(&tq, q_full, M, (long long)m.nh * (m.nope + m.rope), kFQ);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tk, kv_up, kv_len, up, kFK);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tpe, kpe_bf16, kv_len, m.rope, kFK);
   if (e != cudaSuccess) return e;
   GqaDims g{m.H, m.nh, m.nh, m.nope + m.rope, 0, 0, 0.f, m.eps};
   const float sl2 = sm_scale * 1.4426950408889634f;
   dim3 grid((M + kFQ - 1) / kFQ, m.nh);
-  gqa_fmha_kernel<192, 128, 1><<<grid, kFThreads, FmhaSmem<192, 128>::kTotal, s>>>(
-      tq, g, (const uint8_t*)kv_up, (const uint8_t*)((const __nv_bfloat16*)kv_up + (long long)m.nh * m.nope), kv_indices,
-      (const __nv_bfloat16*)kpe_bf16, (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, up);
+  gqa_fmha_kernel<192, 128, true><<<grid, kFThreads, FmhaSmem<192, 128>::kTotal, s>>>(
+      tq, tk, tpe, tk, g, nullptr, (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0, m.nh * m.nope);
   return cudaGetLastError();
 }
 
