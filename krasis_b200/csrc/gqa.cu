@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) gqa_prep_kernel(GqaDims g, const __nv_bfl
 // ------------------------------------------------------------------------------------------------
 constexpr int kFQ = 128;        // query rows per CTA
 constexpr int kFK = 64;         // keys per KV tile
-constexpr int kFThreads = 384;
+constexpr int kFThreads = 512;   // 16 warps: 0 KV TMA, 4 MMA, 5 Q TMA + TMEM, 8-15 softmax (two threads per query row)
 constexpr int kFStages = 2;
 
 template <int DQ, int DV>
@@ -113,7 +113,8 @@ struct FmhaSmem {
   static constexpr int kOffK = kOffQ + kQBytes;
   static constexpr int kOffV = kOffK + kFStages * kKBytes;
   static constexpr int kOffBar = kOffV + kFStages * kVBytes;
-  static constexpr int kTotal = kOffBar + 128;
+  static constexpr int kOffXchg = kOffBar + 128;          // float [2 tile parities][2 halves][128 rows]
+  static constexpr int kTotal = kOffXchg + 2 * 2 * kFQ * 4;
   static_assert(kTotal <= 227 * 1024, "smem");
   static_assert(kQBytes % 1024 == 0 && kKBytes % 1024 == 0 && kVBytes % 1024 == 0, "swizzle atoms");
 };
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_cons, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_cons, 256);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -278,36 +279,49 @@ __global__ void __launch_bounds__(kFThreads, 1)
     }
     __syncwarp();
   } else if (warp >= 8) {
-    // ------------------------------------------------------------ softmax + epilogue (thread = query row)
-    const int q = warp & 3;
+    // ------------------------------------------------------------ softmax + epilogue: two threads per query row.
+    // Warp w serves TMEM lane quarter q = w & 3; warps 8-11 take key columns [0,32) of each tile and the first half of
+    // the O columns, warps 12-15 the second halves.  The two threads of a row exchange their tile maxima through smem
+    // (one 64-thread named barrier per tile), make identical running-max decisions, and keep partial row sums that
+    // are added once at the end.
+    const int q = warp & 3, hf = (warp - 8) >> 2;
     const int row = q * 32 + lane;
     const int qi = q0 + row;                       // query index within this call
     const int q_pos = q_start + qi;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* xchg = reinterpret_cast<float*>(smem + L::kOffXchg);
+    constexpr int KH = kFK / 2, OH = DV / 2;
     float m_ref = -INFINITY, l_sum = 0.f;
     uint32_t sf_phase = 0, pv_phase = 0;
     for (int it = 0; it < n_tiles; ++it) {
       mbar_wait(s_full, sf_phase);
       sf_phase ^= 1;
       tc_fence_after_sync();
-      float s[kFK];
-#pragma unroll
-      for (int c0 = 0; c0 < kFK; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(lane_addr + kColS + c0, r);
+      float s[KH];
+      {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(lane_addr + kColS + hf * KH, r0);
+        tmem_ld16(lane_addr + kColS + hf * KH + 16, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) s[c0 + jj] = __uint_as_float(r[jj]) * sm_scale_log2;
+        for (int jj = 0; jj < 16; ++jj) {
+          s[jj] = __uint_as_float(r0[jj]) * sm_scale_log2;
+          s[16 + jj] = __uint_as_float(r1[jj]) * sm_scale_log2;
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(s_cons);                         // S may be overwritten by the next QK^T
-      const int key0 = it * kFK;
+      const int key0 = it * kFK + hf * KH;
       float m_tile = -INFINITY;
 #pragma unroll
-      for (int jj = 0; jj < kFK; ++jj) {
+      for (int jj = 0; jj < KH; ++jj) {
         if (key0 + jj > q_pos || key0 + jj >= kv_len) s[jj] = -INFINITY;
         m_tile = fmaxf(m_tile, s[jj]);
       }
+      float* xb = xchg + (it & 1) * (2 * kFQ);
+      xb[hf * kFQ + row] = m_tile;
+      named_bar_sync(1 + q, 64);
+      m_tile = fmaxf(m_tile, xb[(hf ^ 1) * kFQ + row]);
       // lazy rescale: keep the reference max until the true max exceeds it by 8 (p stays <= 2^8)
       float scale_o = 1.f;
       bool rescale = false;
@@ -320,9 +334,9 @@ __global__ void __launch_bounds__(kFThreads, 1)
         }
       }
       float psum = 0.f;
-      uint32_t pk[kFK / 2];
+      uint32_t pk[KH / 2];
 #pragma unroll
-      for (int jj = 0; jj < kFK; jj += 2) {
+      for (int jj = 0; jj < KH; jj += 2) {
         const float p0 = (m_ref == -INFINITY) ? 0.f : exp2f(s[jj] - m_ref);
         const float p1 = (m_ref == -INFINITY) ? 0.f : exp2f(s[jj + 1] - m_ref);
         __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
       if (__any_sync(0xffffffffu, rescale)) {
         const float sc = rescale ? scale_o : 1.f;
 #pragma unroll 2
-        for (int c0 = 0; c0 < DV; c0 += 16) {
+        for (int c0 = hf * OH; c0 < (hf + 1) * OH; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(lane_addr + kColO + c0, r);
           tmem_ld_wait();
@@ -349,21 +363,16 @@ __global__ void __launch_bounds__(kFThreads, 1)
           tmem_st16(lane_addr + kColO + c0, r);
         }
       }
-      {
-        uint32_t a[16], b[16];
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          a[jj] = pk[jj];
-          b[jj] = pk[16 + jj];
-        }
-        tmem_st16(lane_addr + kColP, a);
-        tmem_st16(lane_addr + kColP + 16, b);
-      }
+      tmem_st16(lane_addr + kColP + hf * (KH / 2), pk);
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(p_full);
     }
     if (n_tiles > 0) {
+      float* xb = xchg + (n_tiles & 1) * (2 * kFQ);   // the buffer the last tile did not use
+      xb[hf * kFQ + row] = l_sum;
+      named_bar_sync(1 + q, 64);
+      l_sum += xb[(hf ^ 1) * kFQ + row];
       mbar_wait(pv_done, pv_phase);
       tc_fence_after_sync();
       const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
       const long long gbase = (long long)qi * g.nh * D * 2 + (long long)head * 2 * D + D;   // gate half of q_raw
       const bool gated = g.gated != 0;
 #pragma unroll 2
-      for (int c0 = 0; c0 < DV; c0 += 16) {
+      for (int c0 = hf * OH; c0 < (hf + 1) * OH; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(lane_addr + kColO + c0, r);
         tmem_ld_wait();
