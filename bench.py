@@ -188,6 +188,7 @@ def workload_config(args, n):
 
 def run_full_model(args):
     """Whole-model prefill: embedding -> 48 x (norm, GDN|GQA, norm, router, routed experts, shared expert) -> norm -> lm_head."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     from krasis_b200.model import HybridMoEConfig, KrasisModel
@@ -278,8 +279,8 @@ def run_full_model(args):
     moe_ms = sum(v[0] for v in prof.values()) / args.steps
     n_gdn = sum(t == "linear_attention" for t in model.layer_types)
     n_gqa = args.layers - n_gdn
-    # kernels per step outside the MoE engine: GDN 3 GEMM + 5, GQA 4 GEMM + 2, 2 norms, shared expert 6, final norm + lm_head 3
-    other_launches = (n_gdn * 8 + n_gqa * 6 + args.layers * (2 + 6) + 3) * args.steps
+    # kernels per step outside the MoE engine: GDN 3 GEMM + 5, GQA 4 GEMM + 3, 2 norms, shared expert 6, final norm + lm_head 3
+    other_launches = (n_gdn * 8 + n_gqa * 7 + args.layers * (2 + 6) + 3) * args.steps
     roofline = {"kernel": "grouped_gemm_kernel<INT4, gate/up + SiLU*mul>", "bound": "tensor", "achieved": achieved,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": (achieved / pk["tf_sustained"]) if achieved else None,
                 "traffic": None, "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
@@ -287,6 +288,9 @@ def run_full_model(args):
                 "moe_kernel_ms_per_step": {kk: v[0] / args.steps for kk, v in prof.items()},
                 "moe_ms_per_step": moe_ms, "attention_dense_other_ms_per_step": ms_per_step - moe_ms,
                 "component_ms_per_step": comp}
+    cnt = eng.last_expert_counts().astype(np.float64)          # routing load of the last MoE layer of the last step
+    roofline["last_layer_tokens_per_expert"] = {"mean": float(cnt.mean()), "max": float(cnt.max()), "p50": float(np.median(cnt)),
+                                                "below_32": int((cnt < 32).sum()), "above_192": int((cnt > 192).sum())}
     cpu_b = None
     if not args.no_cpu_baseline:
         cpu_b, _, _ = cpu_sample(budget_s=args.cpu_budget)

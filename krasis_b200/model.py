@@ -19,6 +19,8 @@ from dataclasses import dataclass, field
 from types import SimpleNamespace
 from typing import List, Optional
 
+import math
+
 import torch
 
 from . import capi
@@ -136,6 +138,9 @@ class KrasisModel:
             self._kv_layer_offsets.append(off if t == "full_attention" else -1)
             off += t == "full_attention"
         self.layers = []
+        # GPT-2 / Megatron style init: projections that write into the residual stream are scaled by 1/sqrt(2 L), so the
+        # stream stays token-specific through 48 random layers and the router sees a realistic (not collapsed) load
+        res_scale = 1.0 / math.sqrt(2.0 * nl)
         ge = torch.Generator(device=dev).manual_seed(5000 + seed)   # global expert tensors, identical on every rank; each rank keeps its slice
         acfg = SimpleNamespace(hidden_size=H, num_attention_heads=cfg.num_attention_heads,
                                num_key_value_heads=cfg.num_key_value_heads, gqa_head_dim=cfg.gqa_head_dim,
@@ -162,7 +167,7 @@ class KrasisModel:
                 kd = cfg.linear_num_key_heads * cfg.linear_key_head_dim
                 vd = cfg.linear_num_value_heads * cfg.linear_value_head_dim
                 w = dict(in_proj_qkvz=rnd(2 * kd + 2 * vd, H), in_proj_ba=rnd(2 * cfg.linear_num_value_heads, H),
-                         out_proj=rnd(H, vd), conv1d_weight=rnd(2 * kd + vd, 1, cfg.linear_conv_kernel_dim, std=0.3),
+                         out_proj=rnd(H, vd, std=0.02 * res_scale), conv1d_weight=rnd(2 * kd + vd, 1, cfg.linear_conv_kernel_dim, std=0.3),
                          A_log=rnd(cfg.linear_num_value_heads, std=0.5), dt_bias=rnd(cfg.linear_num_value_heads, std=0.5),
                          norm_weight=(1 + 0.05 * torch.randn(cfg.linear_value_head_dim, device=dev, generator=g)).to(bf))
                 wl = shard_gdn_weights(w, cfg, rank, R) if R > 1 else w
@@ -172,7 +177,7 @@ class KrasisModel:
             else:
                 nh, nkv, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.gqa_head_dim
                 w = dict(q_proj=rnd(nh * d * (2 if cfg.gated_attention else 1), H), k_proj=rnd(nkv * d, H), v_proj=rnd(nkv * d, H),
-                         o_proj=rnd(H, nh * d), q_norm=(1 + 0.05 * torch.randn(d, device=dev, generator=g)).to(bf),
+                         o_proj=rnd(H, nh * d, std=0.02 * res_scale), q_norm=(1 + 0.05 * torch.randn(d, device=dev, generator=g)).to(bf),
                          k_norm=(1 + 0.05 * torch.randn(d, device=dev, generator=g)).to(bf))
                 if R > 1:
                     wl, nh_l, nkv_l = shard_gqa_weights(w, cfg, rank, R)
@@ -190,10 +195,15 @@ class KrasisModel:
                 n = self.engine.tiled_bytes(which)              # bytes of this rank's experts; tiles are [expert][...]
                 n_all, off = n // e_loc * e_all, n // e_loc * self.engine.expert_start
                 if which in (0, 2):
-                    full = torch.randint(0, 256, (n_all,), dtype=torch.uint8, device=dev, generator=ge)
+                    if cfg.expert_bits == 4:    # nibbles 1..15 = q in [-7, 7]: zero mean, the range the reference quantiser emits
+                        full = (torch.randint(1, 16, (n_all,), dtype=torch.uint8, device=dev, generator=ge) * 16
+                                + torch.randint(1, 16, (n_all,), dtype=torch.uint8, device=dev, generator=ge))
+                    else:
+                        full = torch.randint(0, 256, (n_all,), dtype=torch.uint8, device=dev, generator=ge)
                     ts.append(full[off:off + n].clone() if R > 1 else full)
-                else:
-                    full = (torch.rand(n_all // 2, device=dev, generator=ge) * 0.008 + 0.004).to(bf)
+                else:                           # group scales: |w| ~ 0.02; the down projection carries the residual-branch scale
+                    sc = 1.0 if which == 1 else res_scale
+                    full = ((torch.rand(n_all // 2, device=dev, generator=ge) * 0.004 + 0.002) * sc).to(bf)
                     ts.append(full[off // 2:(off + n) // 2].clone() if R > 1 else full)
                 del full
             self.engine.attach_tiled_layer(i, *ts)
@@ -203,7 +213,7 @@ class KrasisModel:
             lay.shared_expert = None
             if cfg.shared_expert_intermediate_size > 0:
                 Is = cfg.shared_expert_intermediate_size
-                sw = (rnd(2 * Is, H), rnd(H, Is), rnd(1, H, std=0.05) if cfg.shared_expert_gate else None)
+                sw = (rnd(2 * Is, H), rnd(H, Is, std=0.02 * res_scale), rnd(1, H, std=0.05) if cfg.shared_expert_gate else None)
                 lay.shared_expert = L.SharedExpert(*sw)
                 lay._shared_w = sw if keep_weights else None
             self.layers.append(lay)
