@@ -33,6 +33,55 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
+// one WARP per row, row kept in registers (H == 256 * VPL): no shared memory, no block barriers
+template <bool kAdd, int VPL>
+__global__ void __launch_bounds__(256) rmsnorm_warp_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
+                                                           const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                           int M, float eps) {
+  constexpr int H = 256 * VPL;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float f[VPL][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int v = lane + 32 * j;
+    const uint4 a = *reinterpret_cast<const uint4*>(x + row * H + v * 8);
+    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[j][i] = __bfloat162float(pa[i]);
+    if constexpr (kAdd) {
+      const uint4 r = *reinterpret_cast<const uint4*>(residual + row * H + v * 8);
+      const __nv_bfloat16* pr = reinterpret_cast<const __nv_bfloat16*>(&r);
+      uint4 o;
+      __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[j][i] += __bfloat162float(pr[i]);
+        po[i] = __float2bfloat16_rn(f[j][i]);
+      }
+      *reinterpret_cast<uint4*>(residual + row * H + v * 8) = o;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += f[j][i] * f[j][i];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = rsqrtf(ss / H + eps);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int v = lane + 32 * j;
+    const float4 w0 = *reinterpret_cast<const float4*>(w + v * 8), w1 = *reinterpret_cast<const float4*>(w + v * 8 + 4);
+    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    uint4 o;
+    __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) po[i] = __float2bfloat16_rn(f[j][i] * inv * ww[i]);
+    *reinterpret_cast<uint4*>(out + row * H + v * 8) = o;
+  }
+}
+
 // one CTA per row; H % 8 == 0; each thread owns 8-element vectors
 template <bool kAdd>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
@@ -117,19 +166,32 @@ __global__ void __launch_bounds__(256) silu_and_mul_kernel(const __nv_bfloat16* 
   *reinterpret_cast<uint4*>(out + r * N + v * 8) = o;
 }
 
-// y[m] *= bf16(sigmoid(bf16(dot(h[m], w)))) ; one CTA per row
+// y[m] *= bf16(sigmoid(bf16(dot(h[m], w)))) ; one warp per row, 16-byte vectors (H % 8 == 0, N % 8 == 0)
 __global__ void __launch_bounds__(256) sigmoid_gate_mul_kernel(const __nv_bfloat16* __restrict__ h,
                                                                const __nv_bfloat16* __restrict__ w,
-                                                               __nv_bfloat16* __restrict__ y, int H, int N) {
-  __shared__ float red[8];
-  const long long row = blockIdx.x;
+                                                               __nv_bfloat16* __restrict__ y, int M, int H, int N) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < H; i += blockDim.x) acc = fmaf(__bfloat162float(h[row * H + i]), __bfloat162float(w[i]), acc);
-  acc = block_sum(acc, red);
+  for (int v = lane; v < H / 8; v += 32) {
+    const uint4 a = *reinterpret_cast<const uint4*>(h + row * H + v * 8), b = *reinterpret_cast<const uint4*>(w + v * 8);
+    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+    const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc = fmaf(__bfloat162float(pa[i]), __bfloat162float(pb[i]), acc);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   const float lin = __bfloat162float(__float2bfloat16_rn(acc));
   const float gv = __bfloat162float(__float2bfloat16_rn(1.0f / (1.0f + expf(-lin))));
-  for (int i = threadIdx.x; i < N; i += blockDim.x)
-    y[row * N + i] = __float2bfloat16_rn(gv * __bfloat162float(y[row * N + i]));
+  for (int v = lane; v < N / 8; v += 32) {
+    uint4 a = *reinterpret_cast<const uint4*>(y + row * N + v * 8);
+    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(&a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pa[i] = __float2bfloat16_rn(gv * __bfloat162float(pa[i]));
+    *reinterpret_cast<uint4*>(y + row * N + v * 8) = a;
+  }
 }
 
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
@@ -154,6 +216,13 @@ cudaError_t launch_add_bf16(const void* a, const void* b, void* out, long long n
 
 cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, int M, int H, float eps, cudaStream_t s) {
   if (H % 8 || M <= 0) return cudaErrorInvalidValue;
+  if (H == 2048) {
+    if (residual)
+      rmsnorm_warp_kernel<true, 8><<<(M + 7) / 8, 256, 0, s>>>((__nv_bfloat16*)x, (__nv_bfloat16*)residual, w, (__nv_bfloat16*)out, M, eps);
+    else
+      rmsnorm_warp_kernel<false, 8><<<(M + 7) / 8, 256, 0, s>>>((__nv_bfloat16*)x, nullptr, w, (__nv_bfloat16*)out, M, eps);
+    return cudaGetLastError();
+  }
   if (residual)
     rmsnorm_kernel<true><<<M, 256, H * sizeof(float), s>>>((__nv_bfloat16*)x, (__nv_bfloat16*)residual, w, (__nv_bfloat16*)out, H, eps);
   else
@@ -172,8 +241,8 @@ cudaError_t launch_silu_and_mul(const void* x, void* out, int rows, int N, cudaS
   return cudaGetLastError();
 }
 cudaError_t launch_sigmoid_gate_mul(const void* h, const void* w, void* y, int M, int H, int N, cudaStream_t s) {
-  if (M <= 0) return cudaErrorInvalidValue;
-  sigmoid_gate_mul_kernel<<<M, 256, 0, s>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, H, N);
+  if (M <= 0 || H % 8 || N % 8) return cudaErrorInvalidValue;
+  sigmoid_gate_mul_kernel<<<(M + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, M, H, N);
   return cudaGetLastError();
 }
 

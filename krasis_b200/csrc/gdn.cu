@@ -647,6 +647,32 @@ __global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const __nv_bfl
   const int t = wid / d.nv, h = wid % d.nv, r = d.nv / d.nk;
   const int kd = d.nk * d.dk, vd = d.nv * d.dv, ld = 2 * kd + 2 * vd, G = 2 * d.dk + 2 * r * d.dv;
   const int zcol = (h / r) * G + 2 * d.dk + r * d.dv + (h % r) * d.dv;
+  if (d.dv == 128) {                      // 4 contiguous elements per lane: 8-byte loads / stores
+    const int c = lane * 4;
+    const uint2 xr = *reinterpret_cast<const uint2*>(core + (long long)t * vd + h * d.dv + c);
+    const uint2 zr = *reinterpret_cast<const uint2*>(qkvz + (long long)t * ld + zcol + c);
+    const float4 nw = *reinterpret_cast<const float4*>(norm_w + c);
+    const float x[4] = {__uint_as_float(xr.x << 16), __uint_as_float(xr.x & 0xFFFF0000u), __uint_as_float(xr.y << 16),
+                        __uint_as_float(xr.y & 0xFFFF0000u)};
+    const float z[4] = {__uint_as_float(zr.x << 16), __uint_as_float(zr.x & 0xFFFF0000u), __uint_as_float(zr.y << 16),
+                        __uint_as_float(zr.y & 0xFFFF0000u)};
+    const float wv[4] = {nw.x, nw.y, nw.z, nw.w};
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = rsqrtf(ss / d.dv + d.eps);
+    float o4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float xn = bf16r(wv[i] * (x[i] * inv));
+      const float sz = bf16r(z[i] / (1.0f + expf(-z[i])));
+      o4[i] = xn * sz;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(o4[0], o4[1]), hi = __floats2bfloat162_rn(o4[2], o4[3]);
+    *reinterpret_cast<uint2*>(out + (long long)t * vd + h * d.dv + c) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    return;
+  }
   float ss = 0.f;
   for (int c = lane; c < d.dv; c += 32) {
     const float x = __bfloat162float(core[(long long)t * vd + h * d.dv + c]);          // core_attn_out.to(bf16), done by the scan
