@@ -129,20 +129,37 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(__nv_bfloat16* __restrict_
 // one CTA per row of x [rows][K] bf16 -> q int8, scale (f32 and/or bf16)
 __global__ void __launch_bounds__(256) quant_rows_int8_kernel(const __nv_bfloat16* __restrict__ x, int8_t* __restrict__ q,
                                                               float* __restrict__ scale_f32,
-                                                              __nv_bfloat16* __restrict__ scale_bf16, int K) {
-  __shared__ float red[8];
-  const long long row = blockIdx.x;
+                                                              __nv_bfloat16* __restrict__ scale_bf16, int rows, int K) {
+  // one warp per row, 16-byte loads, 8-byte stores (K % 8 == 0); same arithmetic as the scalar form: max is order-free,
+  // x / scale is an IEEE division, rintf = round half to even
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
   float mx = 0.f;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) mx = fmaxf(mx, fabsf(__bfloat162float(x[row * K + i])));
-  mx = block_max(mx, red);
+  for (int v = lane; v < K / 8; v += 32) {
+    const uint4 a = *reinterpret_cast<const uint4*>(x + row * K + v * 8);
+    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(__bfloat162float(pa[i])));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   const float scale = fmaxf(mx, 1e-10f) / 127.0f;
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     if (scale_f32) scale_f32[row] = scale;
     if (scale_bf16) scale_bf16[row] = __float2bfloat16_rn(scale);
   }
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    const float v = rintf(__bfloat162float(x[row * K + i]) / scale);       // torch.round: half to even
-    q[row * K + i] = (int8_t)fminf(fmaxf(v, -128.f), 127.f);
+  for (int v = lane; v < K / 8; v += 32) {
+    const uint4 a = *reinterpret_cast<const uint4*>(x + row * K + v * 8);
+    const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+    uint32_t o[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r = rintf(__bfloat162float(pa[i]) / scale);               // torch.round: half to even
+      const int qi = (int)fminf(fmaxf(r, -128.f), 127.f);
+      o[i >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (i & 3));
+    }
+    *reinterpret_cast<uint2*>(q + row * K + v * 8) = make_uint2(o[0], o[1]);
   }
 }
 
@@ -230,8 +247,9 @@ cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, i
   return cudaGetLastError();
 }
 cudaError_t launch_quant_rows_int8(const void* x, void* q, float* scale_f32, void* scale_bf16, int rows, int K, cudaStream_t s) {
-  if (rows <= 0) return cudaErrorInvalidValue;
-  quant_rows_int8_kernel<<<rows, 256, 0, s>>>((const __nv_bfloat16*)x, (int8_t*)q, scale_f32, (__nv_bfloat16*)scale_bf16, K);
+  if (rows <= 0 || K % 8) return cudaErrorInvalidValue;
+  quant_rows_int8_kernel<<<(rows + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)x, (int8_t*)q, scale_f32, (__nv_bfloat16*)scale_bf16,
+                                                        rows, K);
   return cudaGetLastError();
 }
 cudaError_t launch_silu_and_mul(const void* x, void* out, int rows, int N, cudaStream_t s) {

@@ -221,3 +221,94 @@ def load_experts_from_gguf(engine, gguf_path: str, first_k_dense: int = 0):
     for moe_idx in range(engine.num_moe_layers()):
         gate, up, down, _, _ = gguf_expert_blocks(g, moe_idx + first_k_dense, engine.expert_start, engine.expert_end, H, I)
         engine.load_gguf_layer(moe_idx, gate, up, down)
+
+
+# --------------------------------------------------------------------------------------------- attention / norm weights
+# Load-time conventions that change numerics (SURVEY.md §8a last row; python/krasis/weight_loader.py).  All host-side
+# re-arrangement of BF16 tensors (torch on CPU): no arithmetic except the documented `+ 1.0` in BF16.
+
+def _st_bf16(tensors: Dict[str, SafetensorsFile], name: str):
+    import torch
+    return torch.from_numpy(np.array(tensors[name].tensor(name)).view(np.int16)).view(torch.bfloat16)
+
+
+def norm_plus_one(w):
+    """Qwen3-Next / Qwen3.5 RMSNorm weights are stored as `w - 1`: input / post-attention / final / q_norm / k_norm get
+    `w + 1.0` at load, computed in BF16 (weight_loader.py:168-169,259-265,286-289); the Gated-DeltaNet gated norm does NOT
+    (:421)."""
+    return w + 1.0
+
+
+def fuse_qwen35_linear_attn(qkv, z, b, a, nk: int, dk: int, nv: int, dv: int):
+    """Qwen3.5 stores in_proj_{qkv,z,b,a} separately (flat [Q_all, K_all, V_all]); the kernels consume Qwen3-Coder-Next's
+    fused per-key-head-group layout [q_i | k_i | v_i (r heads) | z_i (r heads)] and [b_i | a_i] (weight_loader.py:384-414)."""
+    import torch
+    r, kd = nv // nk, nk * dk
+    H = qkv.shape[1]
+    q = qkv[:kd].reshape(nk, dk, H)
+    k = qkv[kd:2 * kd].reshape(nk, dk, H)
+    v = qkv[2 * kd:].reshape(nk, r * dv, H)
+    zz = z.reshape(nk, r * dv, H)
+    qkvz = torch.cat([q, k, v, zz], dim=1).reshape(nk * (2 * dk + 2 * r * dv), H)
+    ba = torch.cat([b.reshape(nk, r, H), a.reshape(nk, r, H)], dim=1).reshape(2 * nv, H)
+    return qkvz.contiguous(), ba.contiguous()
+
+
+def split_kv_b_proj(kv_b, num_heads: int, qk_nope: int, v_head: int):
+    """kv_b_proj [heads*(nope+v), lora] -> w_kc [heads, nope, lora], w_vc [heads, v, lora] (weight_loader.py:223-230)."""
+    kv = kv_b.reshape(num_heads, qk_nope + v_head, kv_b.shape[1])
+    return kv[:, :qk_nope, :].contiguous(), kv[:, qk_nope:, :].contiguous()
+
+
+def load_linear_attention_weights(tensors, layers_prefix: str, layer: int, nk: int, dk: int, nv: int, dv: int) -> dict:
+    """weights dict for krasis_b200.attention.GatedDeltaNetAttention (weight_loader.py:376-425)."""
+    p = f"{layers_prefix}.layers.{layer}.linear_attn"
+    w = {}
+    if f"{p}.in_proj_qkvz.weight" in tensors:
+        w["in_proj_qkvz"] = _st_bf16(tensors, f"{p}.in_proj_qkvz.weight")
+        w["in_proj_ba"] = _st_bf16(tensors, f"{p}.in_proj_ba.weight")
+    else:
+        w["in_proj_qkvz"], w["in_proj_ba"] = fuse_qwen35_linear_attn(
+            *[_st_bf16(tensors, f"{p}.in_proj_{n}.weight") for n in ("qkv", "z", "b", "a")], nk, dk, nv, dv)
+    w["out_proj"] = _st_bf16(tensors, f"{p}.out_proj.weight")
+    w["conv1d_weight"] = _st_bf16(tensors, f"{p}.conv1d.weight")
+    w["A_log"], w["dt_bias"] = _st_bf16(tensors, f"{p}.A_log"), _st_bf16(tensors, f"{p}.dt_bias")
+    w["norm_weight"] = _st_bf16(tensors, f"{p}.norm.weight")            # not shifted
+    return w
+
+
+def load_gqa_weights(tensors, layers_prefix: str, layer: int, norm_bias_one: bool) -> dict:
+    """weights dict for krasis_b200.attention.GQAAttention (weight_loader.py:233-272)."""
+    p = f"{layers_prefix}.layers.{layer}.self_attn"
+    w = {k: _st_bf16(tensors, f"{p}.{k}.weight") for k in ("q_proj", "k_proj", "v_proj", "o_proj")}
+    for k in ("q_norm", "k_norm"):
+        if f"{p}.{k}.weight" in tensors:
+            t = _st_bf16(tensors, f"{p}.{k}.weight")
+            w[k] = norm_plus_one(t) if norm_bias_one else t
+    return w
+
+
+def load_mla_weights(tensors, layers_prefix: str, layer: int, num_heads: int, qk_nope: int, v_head: int, has_q_lora: bool) -> dict:
+    """weights dict for krasis_b200.attention.MLAAttention (weight_loader.py:199-231)."""
+    p = f"{layers_prefix}.layers.{layer}.self_attn"
+    names = ["q_a_proj", "q_b_proj", "q_a_layernorm"] if has_q_lora else ["q_proj"]
+    w = {k: _st_bf16(tensors, f"{p}.{k}.weight") for k in names + ["kv_a_proj_with_mqa", "o_proj", "kv_a_layernorm"]}
+    w["w_kc"], w["w_vc"] = split_kv_b_proj(_st_bf16(tensors, f"{p}.kv_b_proj.weight"), num_heads, qk_nope, v_head)
+    return w
+
+
+def load_layer_norms(tensors, layers_prefix: str, layer: int, norm_bias_one: bool) -> dict:
+    """input_layernorm / post_attention_layernorm (weight_loader.py:274-291)."""
+    p = f"{layers_prefix}.layers.{layer}"
+    out = {k: _st_bf16(tensors, f"{p}.{k}.weight") for k in ("input_layernorm", "post_attention_layernorm")}
+    return {k: norm_plus_one(v) for k, v in out.items()} if norm_bias_one else out
+
+
+def load_router(tensors, layers_prefix: str, layer: int):
+    """(gate [E,H] bf16, e_score_correction_bias or None) — `mlp.gate.*` or `mlp.router.*` (weight_loader.py:307-334)."""
+    for stem in ("mlp.gate", "mlp.router"):
+        name = f"{layers_prefix}.layers.{layer}.{stem}.weight"
+        if name in tensors:
+            bias = f"{layers_prefix}.layers.{layer}.{stem}.e_score_correction_bias"
+            return _st_bf16(tensors, name), (_st_bf16(tensors, bias) if bias in tensors else None)
+    raise KeyError(f"no router weight for layer {layer}")

@@ -72,3 +72,53 @@ def test_gguf_parser_and_merged_expert_slicing(tmp_path):
     # the bytes we hand to the GPU dequantise (oracle) to what gguf-py says
     ref = gguf.quants.dequantize(gate[2], Q.Q4_K)
     assert np.array_equal(G.dequantize(G.GGML_Q4_K, a[1].reshape(-1), I * H).reshape(I, H), ref)
+
+
+def test_attention_weight_conventions(tmp_path):
+    """Qwen3.5 separate in_proj_* -> fused per-group layout (loop restatement of weight_loader.py:384-414), kv_b_proj split,
+    norm +1 shift in BF16, router / norm naming."""
+    import torch
+    torch.manual_seed(0)
+    nk, dk, nv, dv, H = 4, 8, 8, 16, 32
+    r, kd, vd = nv // nk, nk * dk, nv * dv
+    bf = torch.bfloat16
+    qkv, z = torch.randn(2 * kd + vd, H).to(bf), torch.randn(vd, H).to(bf)
+    b, a = torch.randn(nv, H).to(bf), torch.randn(nv, H).to(bf)
+    parts, ba = [], []
+    for i in range(nk):                                       # the reference's loop, restated
+        parts += [qkv[i * dk:(i + 1) * dk], qkv[kd + i * dk:kd + (i + 1) * dk],
+                  qkv[2 * kd + i * r * dv:2 * kd + (i + 1) * r * dv], z[i * r * dv:(i + 1) * r * dv]]
+        ba += [b[i * r:(i + 1) * r], a[i * r:(i + 1) * r]]
+    got_qkvz, got_ba = Ld.fuse_qwen35_linear_attn(qkv, z, b, a, nk, dk, nv, dv)
+    assert torch.equal(got_qkvz, torch.cat(parts, 0)) and torch.equal(got_ba, torch.cat(ba, 0))
+    # and the oracle's un-interleave (linear_attention.py:337-391) undoes it
+    from oracle import attention as A
+    x = torch.randn(3, H).to(bf)
+    q_, k_, v_, z_, b_, a_ = A.gdn_unsplit(torch.nn.functional.linear(x, got_qkvz), torch.nn.functional.linear(x, got_ba), nk, nv, dk, dv)
+    assert torch.equal(q_.reshape(3, -1), torch.nn.functional.linear(x, qkv[:kd]))
+    assert torch.equal(z_.reshape(3, -1), torch.nn.functional.linear(x, z))
+    assert torch.equal(a_.reshape(3, -1), torch.nn.functional.linear(x, a))
+    kv_b = torch.randn(4 * (128 + 64), 16).to(bf)
+    w_kc, w_vc = Ld.split_kv_b_proj(kv_b, 4, 128, 64)
+    assert w_kc.shape == (4, 128, 16) and w_vc.shape == (4, 64, 16)
+    assert torch.equal(w_kc[1], kv_b[192:192 + 128]) and torch.equal(w_vc[3], kv_b[3 * 192 + 128:4 * 192])
+    w = torch.tensor([0.00390625, -0.5, 0.1]).to(bf)
+    assert torch.equal(Ld.norm_plus_one(w), (w.float() + 1.0).to(bf)) and Ld.norm_plus_one(w).dtype == bf
+    # file-level naming
+    u16 = lambda t: t.view(torch.int16).numpy().view(np.uint16)
+    t = {"model.layers.0.linear_attn.in_proj_qkv.weight": ("BF16", u16(qkv)), "model.layers.0.linear_attn.in_proj_z.weight": ("BF16", u16(z)),
+         "model.layers.0.linear_attn.in_proj_b.weight": ("BF16", u16(b)), "model.layers.0.linear_attn.in_proj_a.weight": ("BF16", u16(a)),
+         "model.layers.0.linear_attn.out_proj.weight": ("BF16", u16(torch.randn(H, vd).to(bf))),
+         "model.layers.0.linear_attn.conv1d.weight": ("BF16", u16(torch.randn(2 * kd + vd, 1, 4).to(bf))),
+         "model.layers.0.linear_attn.A_log": ("BF16", u16(torch.randn(nv).to(bf))), "model.layers.0.linear_attn.dt_bias": ("BF16", u16(torch.randn(nv).to(bf))),
+         "model.layers.0.linear_attn.norm.weight": ("BF16", u16(torch.randn(dv).to(bf))),
+         "model.layers.0.input_layernorm.weight": ("BF16", u16(w)), "model.layers.0.post_attention_layernorm.weight": ("BF16", u16(w)),
+         "model.layers.0.mlp.gate.weight": ("BF16", u16(torch.randn(6, H).to(bf)))}
+    _write_safetensors(tmp_path / "model.safetensors", t)
+    ts = Ld.open_model_safetensors(str(tmp_path))
+    la = Ld.load_linear_attention_weights(ts, "model", 0, nk, dk, nv, dv)
+    assert torch.equal(la["in_proj_qkvz"], got_qkvz) and la["conv1d_weight"].shape == (2 * kd + vd, 1, 4)
+    norms = Ld.load_layer_norms(ts, "model", 0, norm_bias_one=True)
+    assert torch.equal(norms["input_layernorm"], w + 1.0)
+    gate, bias = Ld.load_router(ts, "model", 0)
+    assert gate.shape == (6, H) and bias is None
