@@ -134,6 +134,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return dsc;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {       // 2^x, MUFU.EX2 (2 ulp); ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -167,8 +172,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
   uint64_t* s_full = bars + 5;
   uint64_t* s_cons = bars + 6;
   uint64_t* p_full = bars + 7;
-  uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* pv_done = bars + 8;      // [2]: PV(it) commits to pv_done[it & 1] (P is double-buffered)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;       // heavy (late) query tiles first
   const int head = blockIdx.y, kvh = head / (g.nh / g.nkv);
@@ -188,7 +193,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
     mbar_init(s_full, 1);
     mbar_init(s_cons, 256);
     mbar_init(p_full, 256);
-    mbar_init(pv_done, 1);
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc(tmem_ptr_smem, 512);
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColS = 0, kColP = 64, kColO = 128;
+  constexpr uint32_t kColS = 0, kColP = 64, kColO = 128;      // P: two buffers of 32 columns at 64 and 96
 
   if (warp < 4) {
     // ------------------------------------------------------------ KV producer: one thread issues the TMA boxes of a tile
@@ -227,12 +233,12 @@ __global__ void __launch_bounds__(kFThreads, 1)
       int stage = 0;
       uint32_t phase = 0, sc_phase = 0, pf_phase = 0;
       const uint32_t q_addr = smem_u32(smem + L::kOffQ);
-      auto issue_pv = [&](int st, bool first) {
+      auto issue_pv = [&](int st, bool first, int pbuf) {
         const uint32_t v_addr = smem_u32(smem + L::kOffV + st * L::kVBytes);
 #pragma unroll
         for (int k = 0; k < kFK / 16; ++k) {
           const uint64_t bd = umma_desc_mn_sw128(v_addr + k * 2048, kFK * 128, 1024);
-          umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + 8 * k, bd, id_o, (first && k == 0) ? 0u : 1u);
+          umma_bf16_ts(tmem_base + kColO, tmem_base + kColP + pbuf * 32 + 8 * k, bd, id_o, (first && k == 0) ? 0u : 1u);
         }
       };
       int prev_stage = 0;
@@ -256,8 +262,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
           mbar_wait(p_full, pf_phase);
           pf_phase ^= 1;
           tc_fence_after_sync();
-          issue_pv(prev_stage, it == 1);
-          umma_commit(pv_done);
+          issue_pv(prev_stage, it == 1, (it - 1) & 1);
+          umma_commit(&pv_done[(it - 1) & 1]);
           umma_commit(&kv_empty[prev_stage]);
         }
         prev_stage = stage;
@@ -265,8 +271,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
       }
       mbar_wait(p_full, pf_phase);
       tc_fence_after_sync();
-      issue_pv(prev_stage, n_tiles == 1);
-      umma_commit(pv_done);
+      issue_pv(prev_stage, n_tiles == 1, (n_tiles - 1) & 1);
+      umma_commit(&pv_done[(n_tiles - 1) & 1]);
       umma_commit(&kv_empty[prev_stage]);
     }
     __syncwarp();
@@ -292,12 +298,23 @@ __global__ void __launch_bounds__(kFThreads, 1)
     float* xchg = reinterpret_cast<float*>(smem + L::kOffXchg);
     constexpr int KH = kFK / 2, OH = DV / 2;
     float m_ref = -INFINITY, l_sum = 0.f;
-    uint32_t sf_phase = 0, pv_phase = 0;
+    uint32_t sf_phase = 0;
+    // PV completions observed so far on each of the two pv_done barriers.  P is double-buffered, so a tile only has to
+    // wait for PV(it-2) (its P buffer is free again) — and for PV(it-1) in the rare case it rescales O.  A thread never
+    // lags two completions behind on one barrier: the next PV on it cannot be issued before this thread's p_full arrive.
+    uint32_t pv_seen[2] = {0u, 0u};
+    auto pv_wait = [&](int b, uint32_t need) {
+      while (pv_seen[b] < need) {
+        mbar_wait(&pv_done[b], pv_seen[b] & 1);
+        ++pv_seen[b];
+      }
+      tc_fence_after_sync();
+    };
     for (int it = 0; it < n_tiles; ++it) {
       mbar_wait(s_full, sf_phase);
       sf_phase ^= 1;
       tc_fence_after_sync();
-      float s[KH];
+      float s[KH];                                   // raw scores (the softmax scale is folded into the exponent FMA)
       {
         uint32_t r0[16], r1[16];
         tmem_ld16(lane_addr + kColS + hf * KH, r0);
@@ -305,53 +322,53 @@ __global__ void __launch_bounds__(kFThreads, 1)
         tmem_ld_wait();
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          s[jj] = __uint_as_float(r0[jj]) * sm_scale_log2;
-          s[16 + jj] = __uint_as_float(r1[jj]) * sm_scale_log2;
+          s[jj] = __uint_as_float(r0[jj]);
+          s[16 + jj] = __uint_as_float(r1[jj]);
         }
       }
       tc_fence_before_sync();
       mbar_arrive(s_cons);                         // S may be overwritten by the next QK^T
       const int key0 = it * kFK + hf * KH;
+      // causal / length mask only where a key of this half-tile can be invisible to a row of this warp (warp-uniform)
+      if (key0 + KH - 1 > q_start + q0 + q * 32 || key0 + KH > kv_len) {
+#pragma unroll
+        for (int jj = 0; jj < KH; ++jj)
+          if (key0 + jj > q_pos || key0 + jj >= kv_len) s[jj] = -INFINITY;
+      }
       float m_tile = -INFINITY;
 #pragma unroll
-      for (int jj = 0; jj < KH; ++jj) {
-        if (key0 + jj > q_pos || key0 + jj >= kv_len) s[jj] = -INFINITY;
-        m_tile = fmaxf(m_tile, s[jj]);
-      }
+      for (int jj = 0; jj < KH; ++jj) m_tile = fmaxf(m_tile, s[jj]);
       float* xb = xchg + (it & 1) * (2 * kFQ);
       xb[hf * kFQ + row] = m_tile;
       named_bar_sync(1 + q, 64);
-      m_tile = fmaxf(m_tile, xb[(hf ^ 1) * kFQ + row]);
+      m_tile = fmaxf(m_tile, xb[(hf ^ 1) * kFQ + row]) * sm_scale_log2;      // sm_scale > 0: max commutes with the scale
       // lazy rescale: keep the reference max until the true max exceeds it by 8 (p stays <= 2^8)
       float scale_o = 1.f;
       bool rescale = false;
       if (m_tile > m_ref + 8.f || m_ref == -INFINITY) {
         const float m_new = fmaxf(m_tile, m_ref);
         if (m_new != -INFINITY) {
-          scale_o = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+          scale_o = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new);
           rescale = (m_ref != -INFINITY);
           m_ref = m_new;
         }
       }
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;   // row fully masked so far: every s is -inf -> p = 0
       float psum = 0.f;
       uint32_t pk[KH / 2];
 #pragma unroll
       for (int jj = 0; jj < KH; jj += 2) {
-        const float p0 = (m_ref == -INFINITY) ? 0.f : exp2f(s[jj] - m_ref);
-        const float p1 = (m_ref == -INFINITY) ? 0.f : exp2f(s[jj + 1] - m_ref);
+        const float p0 = ex2_approx(fmaf(s[jj], sm_scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(s[jj + 1], sm_scale_log2, neg_m));
         __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
         psum += __low2float(pb) + __high2float(pb);     // normalise with the values the MMA actually uses
         pk[jj / 2] = *reinterpret_cast<uint32_t*>(&pb);
       }
       l_sum = l_sum * scale_o + psum;
-      if (it > 0) {                                // O of the previous tile must be complete before we touch it / before PV(it)
-        mbar_wait(pv_done, pv_phase);
-        pv_phase ^= 1;
-        tc_fence_after_sync();
-      }
       // tcgen05.ld/st are warp-collective (.sync.aligned): the decision must be warp-uniform; rows that keep their
       // reference max multiply by 1
       if (__any_sync(0xffffffffu, rescale)) {
+        pv_wait((it - 1) & 1, (uint32_t)((it - 1) / 2 + 1));     // O must hold every PV up to tile it-1 (rescale => it >= 1)
         const float sc = rescale ? scale_o : 1.f;
 #pragma unroll 2
         for (int c0 = hf * OH; c0 < (hf + 1) * OH; c0 += 16) {
@@ -363,7 +380,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
           tmem_st16(lane_addr + kColO + c0, r);
         }
       }
-      tmem_st16(lane_addr + kColP + hf * (KH / 2), pk);
+      if (it >= 2) pv_wait(it & 1, (uint32_t)(it / 2));          // PV(it-2) has read this P buffer
+      tmem_st16(lane_addr + kColP + (it & 1) * 32 + hf * (KH / 2), pk);
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(p_full);
@@ -373,8 +391,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
       xb[hf * kFQ + row] = l_sum;
       named_bar_sync(1 + q, 64);
       l_sum += xb[(hf ^ 1) * kFQ + row];
-      mbar_wait(pv_done, pv_phase);
-      tc_fence_after_sync();
+      if (n_tiles >= 2) pv_wait((n_tiles - 2) & 1, (uint32_t)((n_tiles - 2) / 2 + 1));
+      pv_wait((n_tiles - 1) & 1, (uint32_t)((n_tiles - 1) / 2 + 1));
       const float inv_l = l_sum > 0.f ? 1.0f / l_sum : 0.f;
       const bool live = qi < M;
       const long long obase = (long long)qi * g.nh * DV + (long long)head * DV;

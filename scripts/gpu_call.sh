@@ -1,6 +1,6 @@
-timeout 400 python -m pytest tests/test_gpu_attention.py tests/test_gpu_model.py -x -q --timeout 120 --timeout-method=thread 2>&1 | grep -v "^  warn\|Warning" | tail -8
-timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_full8.json 2> gpurun_out/bench_full8.err; python - <<'PY'
+timeout 400 python -m pytest tests/test_gpu_attention.py tests/test_gpu_model.py -x -q --timeout 90 --timeout-method=thread 2>&1 | grep -v "^  warn\|Warning" | tail -8
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_full9.json 2> gpurun_out/bench_full9.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench_full8.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/bench_full9.json').read().strip().splitlines()[-1])
 print(d['value'], d['ms_per_step'], d['roofline']['component_ms_per_step'])
 PY
