@@ -186,6 +186,9 @@ def workload_config(args, n):
 
 # --------------------------------------------------------------------------------------------- GPU arm
 
+NCU_GEMM1_DRAM_BYTES = 966221312      # 889.42 MB read + 76.80 MB written (N=1, 8192 tokens)
+
+
 def run_full_model(args):
     """Whole-model prefill: embedding -> 48 x (norm, GDN|GQA, norm, router, routed experts, shared expert) -> norm -> lm_head."""
     import numpy as np
@@ -283,7 +286,10 @@ def run_full_model(args):
     other_launches = (n_gdn * 8 + n_gqa * 7 + args.layers * (2 + 6) + 3) * args.steps
     roofline = {"kernel": "grouped_gemm_kernel<INT4, gate/up + SiLU*mul>", "bound": "tensor", "achieved": achieved,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": (achieved / pk["tf_sustained"]) if achieved else None,
-                "traffic": None, "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                "traffic": NCU_GEMM1_DRAM_BYTES if world == 1 and M == TOKENS else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this command "
+                                  "(profiles/r01h_grouped_gemm_full_model_raw.csv); algorithmic minimum 528 MiB weights + 320 MiB tokens + 80 MiB act",
+                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                 "algorithmic": f"2*M*k*H*2I/ranks = {flops_per_launch:.3e} FLOP per launch", "avg_launch_ms": g1_ms / max(1, g1_n),
                 "moe_kernel_ms_per_step": {kk: v[0] / args.steps for kk, v in prof.items()},
                 "moe_ms_per_step": moe_ms, "attention_dense_other_ms_per_step": ms_per_step - moe_ms,
