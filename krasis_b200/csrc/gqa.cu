@@ -167,13 +167,15 @@ __global__ void __launch_bounds__(kFThreads, 1)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;      // [2]
-  uint64_t* kv_empty = bars + 3;     // [2]
+  uint64_t* k_full = bars + 1;       // [2]  K and V stages are filled and released separately: K(it) is free as soon as
+  uint64_t* k_empty = bars + 3;      // [2]  QK^T(it) has run, one PV earlier than V(it), so the next K tile's TMA starts
+  uint64_t* v_full = bars + 10;      // [2]  a whole tile period earlier (the 64 KB tile loads were the latency chain)
+  uint64_t* v_empty = bars + 12;     // [2]
   uint64_t* s_full = bars + 5;
   uint64_t* s_cons = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* pv_done = bars + 8;      // [2]: PV(it) commits to pv_done[it & 1] (P is double-buffered)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;       // heavy (late) query tiles first
   const int head = blockIdx.y, kvh = head / (g.nh / g.nkv);
@@ -187,8 +189,10 @@ __global__ void __launch_bounds__(kFThreads, 1)
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_cons, 256);
@@ -211,15 +215,17 @@ __global__ void __launch_bounds__(kFThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_tiles; ++it) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
         uint8_t* ks = smem + L::kOffK + stage * L::kKBytes;
         uint8_t* vs = smem + L::kOffV + stage * L::kVBytes;
-        mbar_arrive_expect_tx(&kv_full[stage], L::kKBytes + L::kVBytes);
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&k_full[stage], L::kKBytes);
 #pragma unroll
-        for (int c = 0; c < NKC; ++c) tma_load_2d(ks + c * (kFK * 128), &tmap_k, kx + c * 64, it * kFK, &kv_full[stage]);
-        if constexpr (PE) tma_load_2d(ks + NKC * (kFK * 128), &tmap_kpe, 0, it * kFK, &kv_full[stage]);
+        for (int c = 0; c < NKC; ++c) tma_load_2d(ks + c * (kFK * 128), &tmap_k, kx + c * 64, it * kFK, &k_full[stage]);
+        if constexpr (PE) tma_load_2d(ks + NKC * (kFK * 128), &tmap_kpe, 0, it * kFK, &k_full[stage]);
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&v_full[stage], L::kVBytes);
 #pragma unroll
-        for (int c = 0; c < DV / 64; ++c) tma_load_2d(vs + c * (kFK * 128), &tmap_v, vx + c * 64, it * kFK, &kv_full[stage]);
+        for (int c = 0; c < DV / 64; ++c) tma_load_2d(vs + c * (kFK * 128), &tmap_v, vx + c * 64, it * kFK, &v_full[stage]);
         if (++stage == kFStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -242,8 +248,9 @@ __global__ void __launch_bounds__(kFThreads, 1)
         }
       };
       int prev_stage = 0;
+      uint32_t prev_phase = 0;
       for (int it = 0; it < n_tiles; ++it) {
-        mbar_wait(&kv_full[stage], phase);
+        mbar_wait(&k_full[stage], phase);
         if (it > 0) {
           mbar_wait(s_cons, sc_phase);
           sc_phase ^= 1;
@@ -258,22 +265,26 @@ __global__ void __launch_bounds__(kFThreads, 1)
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS, ad + 2 * k, bd + 2 * k, id_s, (c > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(s_full);
+        umma_commit(&k_empty[stage]);              // K(it) is free once QK^T(it) has run
         if (it > 0) {
+          mbar_wait(&v_full[prev_stage], prev_phase);
           mbar_wait(p_full, pf_phase);
           pf_phase ^= 1;
           tc_fence_after_sync();
           issue_pv(prev_stage, it == 1, (it - 1) & 1);
           umma_commit(&pv_done[(it - 1) & 1]);
-          umma_commit(&kv_empty[prev_stage]);
+          umma_commit(&v_empty[prev_stage]);
         }
         prev_stage = stage;
+        prev_phase = phase;
         if (++stage == kFStages) { stage = 0; phase ^= 1; }
       }
+      mbar_wait(&v_full[prev_stage], prev_phase);
       mbar_wait(p_full, pf_phase);
       tc_fence_after_sync();
       issue_pv(prev_stage, n_tiles == 1, (n_tiles - 1) & 1);
       umma_commit(&pv_done[(n_tiles - 1) & 1]);
-      umma_commit(&kv_empty[prev_stage]);
+      umma_commit(&v_empty[prev_stage]);
     }
     __syncwarp();
   } else if (warp == 5) {
