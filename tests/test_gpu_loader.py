@@ -107,3 +107,31 @@ def test_gguf_file_to_moe_matches_oracle(tmp_path):
     wts = rng.uniform(0.1, 1, (M, k)).astype(np.float32)
     out = eng.moe_forward(0, bf16_t(x), torch.from_numpy(ids).cuda(), torch.from_numpy(wts).cuda(), routed_only=True)
     assert_close_bf16(to_np(out), OM.moe_forward_gpu_path(lay, x, ids, wts), ulps=3)
+
+
+def test_marlin_cache_to_moe_is_bit_identical_to_direct_load(tmp_path):
+    """Reference GPU cache file (Marlin order) -> reader -> tiles gives the same MoE output, bit for bit, as loading the
+    quantiser's arrays directly."""
+    import struct
+    from krasis_b200 import KrasisEngine, QuantizedExperts
+    from krasis_b200 import marlin_cache as MC
+    from tests.test_gpu_moe import bf16_t
+    rng = np.random.default_rng(21)
+    E, H, I, k, M, gs = 4, 256, 128, 2, 80, 128
+    lay = OM.make_int_layer(rng, E, H, I, 4)
+    body = []
+    for e in range(E):
+        for q, s in ((lay.w13_q[e], lay.w13_s[e]), (lay.w2_q[e], lay.w2_s[e])):
+            mp, ms = Q.marlin_repack_int4(q, s, gs)
+            body += [np.ascontiguousarray(mp).tobytes(), np.ascontiguousarray(ms).tobytes()]
+    path = tmp_path / "experts_marlin_int4_g128.bin"
+    path.write_bytes(b"KRAS" + struct.pack("<I", 3) + struct.pack("<7Q", H, I, E, 1, gs, MC.fnv1a(b"{}"), 0) + b"".join(body))
+    mk = lambda: KrasisEngine(hidden_size=H, moe_intermediate_size=I, n_routed_experts=E, num_experts_per_tok=k,
+                              num_moe_layers=1, num_bits=4, max_tokens=M)
+    a, b = mk(), mk()
+    MC.load_experts_from_marlin_cache(a, str(path), b"{}")
+    b.load_quantized_layer(0, QuantizedExperts(lay.w13_q, lay.w13_s, lay.w2_q, lay.w2_s))
+    x = bf16_t(B.round_bf16(rng.normal(0, 1, (M, H)).astype(np.float32)))
+    ids = torch.from_numpy(np.stack([rng.choice(E, k, replace=False) for _ in range(M)]).astype(np.int32)).cuda()
+    wts = torch.from_numpy(rng.uniform(0.1, 1, (M, k)).astype(np.float32)).cuda()
+    assert torch.equal(a.moe_forward(0, x, ids, wts, routed_only=True), b.moe_forward(0, x, ids, wts, routed_only=True))

@@ -122,3 +122,44 @@ def test_attention_weight_conventions(tmp_path):
     assert torch.equal(norms["input_layernorm"], w + 1.0)
     gate, bias = Ld.load_router(ts, "model", 0)
     assert gate.shape == (6, H) and bias is None
+
+
+def test_marlin_cache_file_round_trip(tmp_path):
+    """A cache file written the way the reference writes it (header :4117-4144, body :2462-2476, Marlin order produced by the
+    oracle's restatement of marlin_repack) reads back to exactly the quantiser's arrays; header validation errors."""
+    import struct
+    from krasis_b200 import marlin_cache as MC
+    from oracle import quant as Q, bf16 as B
+    assert MC.fnv1a(b"") == 0xCBF29CE484222325 and MC.fnv1a(b"a") == 0xAF63DC4C8601EC8C       # FNV-1a 64 test vectors
+    assert np.array_equal(MC._weight_perm_int4(), Q.marlin_weight_perm_int4())
+    rng = np.random.default_rng(3)
+    H, I, E, L, gs = 256, 128, 4, 2, 128
+    cfg_json = b'{"hidden_size": 256}'
+    body, ref = [], {}
+    for l in range(L):
+        for e in range(E):
+            w13 = B.f32_to_bf16_bits(rng.normal(0, 0.02, (2 * I, H)).astype(np.float32))
+            w2 = B.f32_to_bf16_bits(rng.normal(0, 0.02, (H, I)).astype(np.float32))
+            q13, s13 = Q.quantize_int4(w13)
+            q2, s2 = Q.quantize_int4(w2)
+            ref[(l, e)] = (q13, s13, q2, s2)
+            for q, s in ((q13, s13), (q2, s2)):
+                mp, ms = Q.marlin_repack_int4(q, s, gs)
+                body += [np.ascontiguousarray(mp).tobytes(), np.ascontiguousarray(ms).tobytes()]
+    hdr = b"KRAS" + struct.pack("<I", 3) + struct.pack("<7Q", H, I, E, L, gs, MC.fnv1a(cfg_json), 0)
+    assert len(hdr) == 64
+    path = tmp_path / "experts_marlin_int4_g128.bin"
+    path.write_bytes(hdr + b"".join(body))
+    c = MC.MarlinCacheFile(str(path), cfg_json)
+    assert (c.hidden_size, c.moe_intermediate_size, c.n_routed_experts, c.num_moe_layers, c.bits) == (H, I, E, L, 4)
+    q13, s13, q2, s2 = c.layer_quantiser_arrays(1, 1, 3)
+    for j, e in enumerate((1, 2)):
+        r = ref[(1, e)]
+        assert np.array_equal(q13[j], r[0]) and np.array_equal(s13[j].view(np.uint16), r[1].view(np.uint16))
+        assert np.array_equal(q2[j], r[2]) and np.array_equal(s2[j].view(np.uint16), r[3].view(np.uint16))
+    with pytest.raises(ValueError):
+        MC.MarlinCacheFile(str(path), b"other config")
+    (tmp_path / "experts_marlin_int4_g128.bin").write_bytes(hdr + b"".join(body)[:-4])
+    with pytest.raises(ValueError):
+        MC.MarlinCacheFile(str(path))
+    assert MC.marlin_expert_byte_sizes(2048, 512, 128, 4) == (1048576, 32768, 524288, 16384)      # SURVEY §8a: 1 MiB + 32 KiB + 0.5 MiB + 16 KiB
