@@ -313,11 +313,38 @@ class GpuPrefillManager:
         self.n_shared_experts = 0 if skip_shared_experts else n_shared_experts
         self.routed_scaling_factor = routed_scaling_factor
         self.num_bits = num_bits
+        self._max_tokens = max_tokens
+        self._shared_engine: Optional[KrasisEngine] = None
+        self._shared_loaded = set()
+
+    def load_shared_expert(self, moe_layer_idx: int, q: QuantizedExperts):
+        """Shared expert(s) of one layer in the manager's own INT4/INT8 format (gpu_prefill.py:4803-4840,
+        `get_shared_expert_weights`): q holds ONE fused expert, w13 [1, 2*n_shared*I, H/8|H], w2 [1, H, n_shared*I/8|...].
+        The reference runs it as a one-expert Marlin MoE with weight 1 (:4738-4801); so does this manager, through a second
+        engine with E = 1, k = 1 and intermediate size n_shared * I."""
+        if self.n_shared_experts <= 0:
+            raise RuntimeError("manager was built without shared experts")
+        if self._shared_engine is None:
+            self._shared_engine = KrasisEngine(hidden_size=self.hidden_size,
+                                               moe_intermediate_size=self.n_shared_experts * self.intermediate_size,
+                                               n_routed_experts=1, num_experts_per_tok=1,
+                                               num_moe_layers=self._engine.num_moe_layers(), num_bits=self.num_bits,
+                                               max_tokens=self._max_tokens, device=self.device.index or 0)
+        self._shared_engine.load_quantized_layer(moe_layer_idx, q)
+        self._shared_loaded.add(moe_layer_idx)
+
+    def _shared_expert_forward(self, moe_layer_idx: int, hidden_states: torch.Tensor) -> torch.Tensor:
+        M = hidden_states.shape[0]
+        ids = torch.zeros((M, 1), dtype=torch.int32, device=hidden_states.device)      # all tokens -> expert 0, weight 1
+        w = torch.ones((M, 1), dtype=torch.float32, device=hidden_states.device)
+        return self._shared_engine.moe_forward(moe_layer_idx, hidden_states, ids, w, routed_only=True)
 
     def forward(self, moe_layer_idx: int, hidden_states: torch.Tensor, topk_ids: torch.Tensor,
                 topk_weights: torch.Tensor, routed_only: bool = False, shared_output: Optional[torch.Tensor] = None):
         """gpu_prefill.py:4374-4484.  `shared_output` (optional, [M,H] bf16) is added after the rsf scaling,
         which is what the reference does with its own shared-expert result (gpu_prefill.py:4471-4480)."""
         torch.cuda.set_device(self.device)                     # gpu_prefill.py:4401
+        if not routed_only and shared_output is None and moe_layer_idx in self._shared_loaded:
+            shared_output = self._shared_expert_forward(moe_layer_idx, hidden_states)      # gpu_prefill.py:4471-4480
         return self._engine.moe_forward(moe_layer_idx, hidden_states, topk_ids, topk_weights,
                                         routed_only=routed_only, shared=shared_output)

@@ -359,3 +359,26 @@ def test_qcn_full_size_sampled_tokens_match_oracle():
     # determinism: a second run is bit-identical (slot order inside an expert may differ, results may not)
     out2 = eng.moe_forward(0, x, ids, w, routed_only=True)
     assert torch.equal(out, out2)
+
+
+def test_manager_owned_int4_shared_expert():
+    """Models without a shared-expert gate on one GPU (DeepSeek-V2-Lite): the manager runs the fused shared experts as a
+    one-expert INT4 MoE with weight 1 and returns bf16(rsf * routed) + shared (gpu_prefill.py:4738-4801,4471-4480)."""
+    from krasis_b200 import GpuPrefillManager, QuantizedExperts
+    rng = np.random.default_rng(31)
+    E, H, I, k, M, n_sh, rsf = 8, 256, 128, 2, 100, 2, 2.5
+    lay = omoe.make_int_layer(rng, E, H, I, 4)
+    sh = omoe.make_int_layer(rng, 1, H, n_sh * I, 4)
+    mgr = GpuPrefillManager(device="cuda:0", num_experts=E, hidden_size=H, intermediate_size=I, n_shared_experts=n_sh,
+                            routed_scaling_factor=rsf, num_bits=4, num_moe_layers=1, top_k=k, max_tokens=M)
+    mgr._engine.load_quantized_layer(0, QuantizedExperts(lay.w13_q, lay.w13_s, lay.w2_q, lay.w2_s))
+    mgr.load_shared_expert(0, QuantizedExperts(sh.w13_q, sh.w13_s, sh.w2_q, sh.w2_s))
+    x = round_bf16(rng.normal(0, 1, (M, H)).astype(np.float32))
+    ids = np.stack([rng.choice(E, k, replace=False) for _ in range(M)]).astype(np.int32)
+    w = rng.uniform(0.1, 1, (M, k)).astype(np.float32)
+    out = mgr.forward(0, bf16_t(x), torch.from_numpy(ids).cuda(), torch.from_numpy(w).cuda())
+    routed = omoe.moe_forward_gpu_path(lay, x, ids, w)
+    shared = omoe.moe_forward_gpu_path(sh, x, np.zeros((M, 1), np.int32), np.ones((M, 1), np.float32))
+    assert_close_bf16(to_np(out), omoe.finish_gpu_path(routed, rsf, shared), ulps=3)
+    ro = mgr.forward(0, bf16_t(x), torch.from_numpy(ids).cuda(), torch.from_numpy(w).cuda(), routed_only=True)
+    assert_close_bf16(to_np(ro), routed)
