@@ -73,10 +73,45 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_all_to_all_dispatch_roundtrip_gloo_world2():
-    world, port = 2, _free_port()
+@pytest.mark.parametrize("world", [2, 4])
+def test_all_to_all_dispatch_roundtrip_gloo(world):
+    port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert len(ret) == 2
+    assert len(ret) == world
     assert sum(v[0] for v in ret.values()) == sum(v[1] for v in ret.values())
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_head_parallel_shards_partition_the_layer(world):
+    """shard_gdn_weights / shard_gqa_weights: the ranks' slices tile the projections exactly once (KV heads are replicated
+    when there are fewer KV heads than ranks), for the Qwen3-Coder-Next geometry at 2, 4 and 8 ranks."""
+    from krasis_b200.model import HybridMoEConfig, shard_gdn_weights, shard_gqa_weights
+    cfg = HybridMoEConfig(hidden_size=64, num_hidden_layers=4, linear_key_head_dim=8, linear_value_head_dim=8, gqa_head_dim=8)
+    nk, nv, dk, dv = cfg.linear_num_key_heads, cfg.linear_num_value_heads, cfg.linear_key_head_dim, cfg.linear_value_head_dim
+    nh, nkv, d, H = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.gqa_head_dim, cfg.hidden_size
+    kd, vd = nk * dk, nv * dv
+    g = torch.Generator().manual_seed(0)
+    w = dict(in_proj_qkvz=torch.randn(2 * kd + 2 * vd, H, generator=g), in_proj_ba=torch.randn(2 * nv, H, generator=g),
+             out_proj=torch.randn(H, vd, generator=g), conv1d_weight=torch.randn(2 * kd + vd, 1, 4, generator=g),
+             A_log=torch.randn(nv, generator=g), dt_bias=torch.randn(nv, generator=g), norm_weight=torch.randn(dv, generator=g))
+    parts = [shard_gdn_weights(w, cfg, r, world) for r in range(world)]
+    assert torch.equal(torch.cat([p["in_proj_qkvz"] for p in parts]), w["in_proj_qkvz"])       # key-head groups are contiguous
+    assert torch.equal(torch.cat([p["in_proj_ba"] for p in parts]), w["in_proj_ba"])
+    assert torch.equal(torch.cat([p["out_proj"] for p in parts], dim=1), w["out_proj"])
+    assert torch.equal(torch.cat([p["A_log"] for p in parts]), w["A_log"])
+    assert sum(p["conv1d_weight"].shape[0] for p in parts) == 2 * kd + vd
+    qw = d * (2 if cfg.gated_attention else 1)
+    wq = dict(q_proj=torch.randn(nh * qw, H, generator=g), k_proj=torch.randn(nkv * d, H, generator=g),
+              v_proj=torch.randn(nkv * d, H, generator=g), o_proj=torch.randn(H, nh * d, generator=g))
+    grp = nh // nkv
+    seen_q = []
+    for r in range(world):
+        p, nh_l, nkv_l = shard_gqa_weights(wq, cfg, r, world)
+        assert nh_l == nh // world and p["q_proj"].shape[0] == nh_l * qw and p["k_proj"].shape[0] == nkv_l * d
+        h0 = r * nh // world
+        assert torch.equal(p["k_proj"], wq["k_proj"][(h0 // grp) * d:(h0 // grp + nkv_l) * d])  # the KV heads of this rank's groups
+        assert nh_l % nkv_l == 0                                                                 # local GQA grouping stays uniform
+        seen_q.append(p["q_proj"])
+    assert torch.equal(torch.cat(seen_q), wq["q_proj"])
