@@ -1,4 +1,4 @@
-"""Reader for the reference's on-disk GPU expert cache `~/.krasis/cache/<model>/experts_marlin_int{4}_g{gs}.bin`.
+"""Reader for the reference's on-disk GPU expert cache `~/.krasis/cache/<model>/experts_marlin_int{4,8}_g{gs}.bin`.
 
 Format (src/weights/mod.rs): 64-byte header :857-866,4117-4144 — magic "KRAS", version u32 (3 = Marlin), then u64 LE
 hidden_size, moe_intermediate_size, n_routed_experts, num_moe_layers, group_size, config_hash (FNV-1a of config.json,
@@ -53,6 +53,12 @@ def _weight_perm_int4() -> np.ndarray:
     return np.asarray(perm, np.int64).reshape(-1, 8)[:, [0, 2, 4, 6, 1, 3, 5, 7]].reshape(-1)
 
 
+def _weight_perm_int8() -> np.ndarray:
+    """Same base permutation, [0,2,1,3] interleave in groups of four (marlin.rs:586-625)."""
+    base = _weight_perm_int4().reshape(-1, 8)[:, [0, 4, 1, 5, 2, 6, 3, 7]].reshape(-1)     # undo the INT4 interleave
+    return base.reshape(-1, 4)[:, [0, 2, 1, 3]].reshape(-1)
+
+
 def _scale_perm(grouped: bool) -> np.ndarray:
     """marlin.rs:302-321: 64-entry permutation for group-wise scales, 32-entry for a single group."""
     if grouped:
@@ -80,6 +86,30 @@ def marlin_to_rowmajor_int4(mpacked: np.ndarray, mscales: np.ndarray, group_size
     sinv[..., p] = s
     scales = np.ascontiguousarray(np.swapaxes(sinv.reshape(lead + (k // group_size, n)), -1, -2))
     return packed, scales
+
+
+def _scales_to_rowmajor(mscales: np.ndarray, lead, k: int, n: int, group_size: int):
+    p = _scale_perm(group_size < k)
+    s = mscales.astype(np.uint16).reshape(lead + (-1, len(p)))
+    sinv = np.empty_like(s)
+    sinv[..., p] = s
+    return np.ascontiguousarray(np.swapaxes(sinv.reshape(lead + (k // group_size, n)), -1, -2))
+
+
+def marlin_to_rowmajor_int8(mpacked: np.ndarray, mscales: np.ndarray, group_size: int):
+    """([..., K/16, 4N] u32, [..., K/gs, N] u16) in Marlin INT8 order (q + 128, marlin.rs:639-760) -> ([..., N, K] i8, scales)."""
+    lead = mpacked.shape[:-2]
+    k16, n4 = mpacked.shape[-2:]
+    k, n = k16 * 16, n4 // 4
+    shifts = np.arange(4, dtype=np.uint32) * np.uint32(8)
+    b = ((mpacked.astype(np.uint32)[..., None] >> shifts) & np.uint32(0xFF)).astype(np.uint8)
+    b = b.reshape(lead + (k16, n * 16 // 1024, 1024))
+    src = np.empty_like(b)
+    src[..., _weight_perm_int8()] = b
+    t = src.reshape(lead + (k16, n // 16, 16, 16))
+    kn = np.moveaxis(t, -2, -3).reshape(lead + (k, n))
+    q = np.ascontiguousarray((np.swapaxes(kn, -1, -2).astype(np.int16) - 128).astype(np.int8))
+    return q, _scales_to_rowmajor(mscales, lead, k, n, group_size)
 
 
 class MarlinCacheFile:
@@ -115,17 +145,17 @@ class MarlinCacheFile:
         base = CACHE_HEADER_SIZE + (layer * self.n_routed_experts + e0) * per
         raw = np.frombuffer(self._mm, np.uint8, (e1 - e0) * per, base).reshape(e1 - e0, per)
         hw2 = marlin_w2_padded_n(h, m)
-        return (raw[:, :a].view(np.uint32).reshape(-1, h // 16, 2 * 2 * m), raw[:, a:a + b].view(np.uint16).reshape(-1, h // gs, 2 * m),
-                raw[:, a + b:a + b + c].view(np.uint32).reshape(-1, m // 16, 2 * hw2), raw[:, a + b + c:].view(np.uint16).reshape(-1, m // gs, hw2))
+        f = 2 if self.bits == 4 else 4                       # u32 words per (k-tile, n): [K/16, 2N] for INT4, [K/16, 4N] for INT8
+        return (raw[:, :a].view(np.uint32).reshape(-1, h // 16, f * 2 * m), raw[:, a:a + b].view(np.uint16).reshape(-1, h // gs, 2 * m),
+                raw[:, a + b:a + b + c].view(np.uint32).reshape(-1, m // 16, f * hw2), raw[:, a + b + c:].view(np.uint16).reshape(-1, m // gs, hw2))
 
     def layer_quantiser_arrays(self, layer: int, e0: int, e1: int):
         """(w13_q [E,2I,H/8] u32, w13_s [E,2I,H/gs] u16, w2_q [E,H,I/8] u32, w2_s [E,H,I/gs] u16): what quantize_int4 emitted."""
-        if self.bits != 4:
-            raise NotImplementedError("INT8 Marlin caches are not read yet")
         if marlin_w2_padded_n(self.hidden_size, self.moe_intermediate_size) != self.hidden_size:
             raise NotImplementedError("padded w2 (hidden == intermediate, not a multiple of 256)")
         p13, s13, p2, s2 = self.layer_marlin_arrays(layer, e0, e1)
-        return marlin_to_rowmajor_int4(p13, s13, self.group_size) + marlin_to_rowmajor_int4(p2, s2, self.group_size)
+        f = marlin_to_rowmajor_int4 if self.bits == 4 else marlin_to_rowmajor_int8
+        return f(p13, s13, self.group_size) + f(p2, s2, self.group_size)
 
 
 def load_experts_from_marlin_cache(engine, path: str, config_json: Optional[bytes] = None, start_layer: int = 0):

@@ -165,3 +165,36 @@ def marlin_unpack_int4(mpacked: np.ndarray, mscales: np.ndarray, group_size: int
     sinv[:, p] = s
     scales = np.ascontiguousarray(sinv.reshape(k // group_size, n).T)
     return packed, scales
+
+
+def marlin_weight_perm_int8() -> np.ndarray:
+    """marlin.rs:586-625 (== vLLM get_weight_perm(num_bits=8)): the INT4 base permutation with the [0,2,1,3] interleave."""
+    perm = []
+    for i in range(32):
+        col = i // 4
+        perm1 = []
+        for block in (0, 1):
+            for row in (2 * (i % 4), 2 * (i % 4) + 1, 2 * (i % 4 + 4), 2 * (i % 4 + 4) + 1):
+                perm1.append(16 * row + col + 8 * block)
+        for j in range(4):
+            perm.extend(p + 256 * j for p in perm1)
+    perm = np.asarray(perm, dtype=np.int64)
+    return perm.reshape(-1, 4)[:, [0, 2, 1, 3]].reshape(-1)
+
+
+def marlin_repack_int8(data: np.ndarray, scales: np.ndarray, group_size: int = GROUP_SIZE):
+    """marlin.rs:639-760.  ([N, K] i8, [N, K/gs] bf16) -> ([K/16, 4N] u32, [K/gs, N] bf16)."""
+    n, k = data.shape
+    assert k % 16 == 0 and n % 64 == 0
+    u = (data.astype(np.int16) + 128).astype(np.uint8)                 # [N, K] 0..255
+    t = u.T.reshape(k // 16, 16, n // 16, 16).transpose(0, 2, 1, 3).reshape(k // 16, n * 16)
+    t = t.reshape(k // 16, -1, 1024)[:, :, marlin_weight_perm_int8()].reshape(k // 16, n * 16)
+    v = t.reshape(k // 16, 4 * n, 4).astype(np.uint32)
+    shifts = np.arange(4, dtype=np.uint32) * np.uint32(8)
+    out = np.bitwise_or.reduce(v << shifts[None, None, :], axis=2).astype(np.uint32)
+    st = np.ascontiguousarray(np.asarray(scales, dtype=np.uint16).T)
+    sp, sp1 = marlin_scale_perms()
+    p = sp if group_size < k else sp1
+    st = st.reshape(-1, len(p))[:, p].reshape(k // group_size, n)
+    return out, st
+

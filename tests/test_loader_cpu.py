@@ -163,3 +163,30 @@ def test_marlin_cache_file_round_trip(tmp_path):
     with pytest.raises(ValueError):
         MC.MarlinCacheFile(str(path))
     assert MC.marlin_expert_byte_sizes(2048, 512, 128, 4) == (1048576, 32768, 524288, 16384)      # 1 MiB + 32 KiB + 0.5 MiB + 16 KiB
+
+
+def test_marlin_cache_int8_round_trip(tmp_path):
+    import struct
+    from krasis_b200 import marlin_cache as MC
+    from oracle import quant as Q, bf16 as B
+    assert np.array_equal(MC._weight_perm_int8(), Q.marlin_weight_perm_int8())
+    rng = np.random.default_rng(4)
+    H, I, E, gs = 256, 128, 3, 128
+    body, ref = [], []
+    for e in range(E):
+        qs = []
+        for shp in ((2 * I, H), (H, I)):
+            q, s = Q.quantize_int8(B.f32_to_bf16_bits(rng.normal(0, 0.02, shp).astype(np.float32)))
+            mp, ms = Q.marlin_repack_int8(q, s, gs)
+            body += [np.ascontiguousarray(mp).tobytes(), np.ascontiguousarray(ms).tobytes()]
+            qs += [q, s]
+        ref.append(qs)
+    path = tmp_path / "experts_marlin_int8_g128.bin"
+    path.write_bytes(b"KRAS" + struct.pack("<I", 3) + struct.pack("<7Q", H, I, E, 1, gs, 0, 0) + b"".join(body))
+    c = MC.MarlinCacheFile(str(path))
+    assert c.bits == 8
+    q13, s13, q2, s2 = c.layer_quantiser_arrays(0, 0, E)
+    for e in range(E):
+        assert np.array_equal(q13[e], ref[e][0]) and np.array_equal(s13[e].view(np.uint16), ref[e][1].view(np.uint16))
+        assert np.array_equal(q2[e], ref[e][2]) and np.array_equal(s2[e].view(np.uint16), ref[e][3].view(np.uint16))
+    assert MC.marlin_expert_byte_sizes(2048, 512, 128, 8) == (2097152, 32768, 1048576, 16384)
