@@ -9,7 +9,7 @@ Gated DeltaNet (Qwen3-Next linear attention)
   gated RMSNorm                  python/krasis/linear_attention.py:987-1004
 
 GQA (Qwen3 / Qwen3-Next gated)   python/krasis/attention.py:496-687
-  partial half-split RoPE, bf16 tables   :443-494
+  partial half-split RoPE, bf16 tables   :443-494   (pinned: reference execution, tests/golden/mla_rope_reference.npz)
   per-head RMSNorm (flashinfer.norm.rmsnorm)  :555-559
   KV cast to cache dtype (FP8 E4M3, unscaled) :582-583
   causal softmax(QK^T * d^-1/2) V             :596-642

@@ -1,6 +1,7 @@
 """Generates tests/golden/mla_rope_reference.npz by EXECUTING THE REFERENCE's own Python code on CPU:
 python/krasis/attention.py MLAAttention._get_rope_cos_sin (YaRN inverse frequencies + BF16 tables, :119-163),
-._deinterleave / ._apply_rope (:165-211) and the sm_scale arithmetic of __init__ (:79-88).
+._deinterleave / ._apply_rope (:165-211), the sm_scale arithmetic of __init__ (:79-88), and GQAAttention._get_rope_cos_sin /
+._apply_rope (:443-494, partial and full rotary).
 
 The attention core itself is FlashInfer (third-party, GPU only) and cannot be executed here; these are the parts of the
 MLA path that live in the reference tree.  flashinfer / krasis.config / kv_cache / timing / weight_loader are stubbed
@@ -64,6 +65,20 @@ def main():
                     f"{tag}_q_in": q_pe.float().numpy(), f"{tag}_k_in": k_pe.float().numpy(),
                     f"{tag}_q_out": q_r.float().numpy(), f"{tag}_k_out": k_r.float().numpy(),
                     f"{tag}_sm_scale": np.float64(sm)})
+    # GQAAttention._get_rope_cos_sin / _apply_rope (attention.py:443-494): partial (QCN: 64 of 256) and full (235B: 128) rotary
+    for tag, d, rot, theta in (("gqa_partial", 256, 64, 10000000.0), ("gqa_full", 128, 128, 1000000.0)):
+        obj = object.__new__(att.GQAAttention)
+        obj.device, obj.rotary_dim, obj.rope_theta, obj._rope_cos_sin = torch.device("cpu"), rot, theta, None
+        torch.manual_seed(9)
+        pos = torch.tensor([0, 1, 5, 100, 4095, 8191])
+        q = torch.randn(len(pos), 3, d).to(torch.bfloat16)
+        k = torch.randn(len(pos), 2, d).to(torch.bfloat16)
+        q_r, k_r = obj._apply_rope(q, k, pos)
+        cos, sin = obj._get_rope_cos_sin(8192)
+        out.update({f"{tag}_pos": pos.numpy(), f"{tag}_q_in": q.float().numpy(), f"{tag}_k_in": k.float().numpy(),
+                    f"{tag}_q_out": q_r.float().numpy(), f"{tag}_k_out": k_r.float().numpy(),
+                    f"{tag}_cos": cos[pos].float().numpy(), f"{tag}_sin": sin[pos].float().numpy(),
+                    f"{tag}_cfg": np.array([d, rot, theta], np.float64)})
     np.savez_compressed(os.path.join(HERE, "mla_rope_reference.npz"), **out)
     print("wrote mla_rope_reference.npz", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
 

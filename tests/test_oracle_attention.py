@@ -133,3 +133,17 @@ def test_mla_product_inv_freq_is_the_oracles():
     for sc in (V2_LITE_ROPE, None):
         assert np.array_equal(mla_rope_inv_freq(64, 10000.0, sc), A.mla_inv_freq(64, 10000.0, sc).numpy())
         assert mla_sm_scale(128, 64, sc) == A.mla_sm_scale(128, 64, sc)
+
+
+@pytest.mark.parametrize("tag", ["gqa_partial", "gqa_full"])
+def test_gqa_rope_matches_reference_execution(tag):
+    """GQA RoPE tables and (partial) half-split rotation in BF16: bit-exact against the reference's own
+    GQAAttention._get_rope_cos_sin/_apply_rope (tests/golden/make_mla_golden.py)."""
+    d, rot, theta = MLA_G[f"{tag}_cfg"]
+    pos = torch.from_numpy(MLA_G[f"{tag}_pos"])
+    cos, sin = A.rope_tables(8192, int(rot), float(theta))
+    assert np.array_equal(cos[pos].float().numpy(), MLA_G[f"{tag}_cos"])
+    assert np.array_equal(sin[pos].float().numpy(), MLA_G[f"{tag}_sin"])
+    for name in ("q", "k"):
+        x = torch.from_numpy(MLA_G[f"{tag}_{name}_in"]).to(torch.bfloat16)
+        assert np.array_equal(A.apply_rope(x, cos[pos], sin[pos]).float().numpy(), MLA_G[f"{tag}_{name}_out"])
