@@ -1,5 +1,8 @@
 """MoE router oracle (test infrastructure only).
 
+Pinned: tests/golden/router_reference.npz holds outputs of the reference's own compute_routing executed on CPU
+(tests/golden/make_router_golden.py); tests/test_oracle_kats.py checks this module against them.
+
 Restates python/krasis/layer.py:526-560 (TransformerLayer.compute_routing; the same
 code is inlined at layer.py:583-616) and the tie-break of the Rust twin
 src/moe.rs:3116-3128 (strict '>' scan => the LOWER expert index wins a tie;

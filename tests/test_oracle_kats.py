@@ -223,3 +223,35 @@ def test_gguf_cpu_path_close_to_dequant_path():
     h = c1[:256] / (1 + np.exp(-c1[:256])) * c1[256:]
     ref = w2 @ h
     assert np.abs(y - ref).max() < 2e-3 * np.abs(ref).max() + 1e-6
+
+
+# ------------------------------------------------------------------ router pinned on the reference's own compute_routing
+
+ROUTER_G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "router_reference.npz"))
+ROUTER_CASES = {   # name: (k, scoring, norm_topk_prob, gpt_oss)   — tests/golden/make_router_golden.py
+    "qwen_softmax_norm": (8, "softmax", True, False),
+    "deepseek_softmax": (6, "softmax", False, False),
+    "kimi_sigmoid_bias_norm": (8, "sigmoid", True, False),
+    "gptoss_topk_softmax": (4, "softmax", False, True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ROUTER_CASES))
+def test_router_oracle_matches_reference_execution(name):
+    """oracle.router vs outputs of python/krasis/layer.py:compute_routing executed on CPU: ids identical (order included)
+    wherever the selection is not a near-tie in fp32, weights to 3e-5 relative (fp32 matmul summation order)."""
+    from oracle import router as R
+    from oracle.bf16 import bf16_bits_to_f32
+    k, scoring, norm, gpt_oss = ROUTER_CASES[name]
+    hidden, gate = bf16_bits_to_f32(ROUTER_G[f"{name}_hidden"]), bf16_bits_to_f32(ROUTER_G[f"{name}_gate"])
+    gb = ROUTER_G[f"{name}_gate_bias"] if f"{name}_gate_bias" in ROUTER_G.files else None
+    cb = bf16_bits_to_f32(ROUTER_G[f"{name}_corr_bias"]) if f"{name}_corr_bias" in ROUTER_G.files else None
+    ids, w = R.compute_routing(hidden, gate, k, scoring_func=scoring, norm_topk_prob=norm, e_score_correction_bias=cb,
+                               gpt_oss=gpt_oss, gate_bias=gb)
+    want_ids, want_w = ROUTER_G[f"{name}_ids"], ROUTER_G[f"{name}_w"]
+    same = (ids == want_ids).all(axis=1)
+    assert same.mean() >= 0.97, same.mean()                   # near-ties may flip an order in a handful of rows
+    assert np.allclose(w[same], want_w[same], rtol=3e-5, atol=1e-7)
+    # rows that differ must differ only by a swap of (nearly) equal weights
+    for r in np.nonzero(~same)[0]:
+        assert sorted(ids[r]) == sorted(want_ids[r]) or np.abs(np.sort(w[r]) - np.sort(want_w[r])).max() < 1e-4
