@@ -255,3 +255,17 @@ def test_router_oracle_matches_reference_execution(name):
     # rows that differ must differ only by a swap of (nearly) equal weights
     for r in np.nonzero(~same)[0]:
         assert sorted(ids[r]) == sorted(want_ids[r]) or np.abs(np.sort(w[r]) - np.sort(want_w[r])).max() < 1e-4
+
+
+def test_int8_linear_oracle_matches_reference_execution():
+    """oracle.dense.quantize_to_int8 / int8_linear vs outputs of the reference's own weight_loader.py functions run on CPU
+    (tests/golden/make_int8_golden.py): integer work, bit-exact."""
+    import torch
+    from oracle import dense as D
+    Gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "int8_reference.npz"))
+    bf = lambda a: torch.from_numpy(a.view(np.int16)).view(torch.bfloat16)
+    x, w = bf(Gd["x"]), bf(Gd["w"])
+    wq, ws = D.quantize_to_int8(w)
+    assert np.array_equal(wq.numpy(), Gd["wq"]) and np.array_equal(ws.view(torch.int16).numpy().view(np.uint16), Gd["ws"])
+    y = D.int8_linear(x, wq, ws)
+    assert np.array_equal(y.view(torch.int16).numpy().view(np.uint16), Gd["y"])
