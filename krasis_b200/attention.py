@@ -127,13 +127,36 @@ class PagedKVCache:
         self.v_cache = torch.zeros(shape, dtype=kv_dtype, device=self.device)
         self._free = list(range(max_pages - 1, -1, -1))
 
+    @classmethod
+    def from_config(cls, cfg, num_layers: int, device, max_pages: Optional[int] = None, kv_dtype=torch.float8_e4m3fn,
+                    page_size: int = PAGE_SIZE, max_mb: Optional[int] = None):
+        """The reference constructor's signature and sizing rule (kv_cache.py:38-82): `max_pages` explicit, else
+        max(64, max_mb MiB // bytes_per_page) with max_mb defaulting to 2000."""
+        per_page = page_size * cfg.num_key_value_heads * cfg.gqa_head_dim * 2 * (1 if kv_dtype == torch.float8_e4m3fn else 2) * num_layers
+        if max_pages is None:
+            max_pages = max(64, (2000 if max_mb is None else max_mb) * 1024 * 1024 // per_page)
+        return cls(num_layers, cfg.num_key_value_heads, cfg.gqa_head_dim, device, max_pages, kv_dtype, page_size)
+
     def get_gqa_layer_caches(self, layer_offset: int):
         return self.k_cache[layer_offset], self.v_cache[layer_offset]
+
+    @property
+    def max_context_tokens(self) -> int:
+        return self.max_pages * self.page_size
+
+    @property
+    def free_page_count(self) -> int:
+        return len(self._free)
 
     def alloc_page(self) -> int:
         if not self._free:
             raise RuntimeError("KV cache out of pages")
         return self._free.pop()
+
+    def alloc_pages(self, n: int):
+        if n > len(self._free):
+            raise RuntimeError(f"KV cache exhausted: need {n} pages, have {len(self._free)}")      # kv_cache.py:149-156
+        return [self._free.pop() for _ in range(n)]
 
     def free_pages(self, pages):
         self._free.extend(pages)
@@ -160,9 +183,20 @@ class SequenceKVState:
             self._idx = torch.tensor(self.pages, dtype=torch.int32, device=device)
         return self._idx
 
+    def kv_indptr(self, device) -> torch.Tensor:
+        return torch.tensor([0, len(self.pages)], dtype=torch.int32, device=device)
+
+    def kv_len_arr(self, device) -> torch.Tensor:
+        return torch.tensor([self.seq_len], dtype=torch.int32, device=device)
+
     def last_page_len(self) -> int:
+        if self.seq_len == 0:                      # kv_cache.py:236-241
+            return 0
         r = self.seq_len % self.cache.page_size
         return r if r else self.cache.page_size
+
+    def last_page_len_tensor(self, device) -> torch.Tensor:
+        return torch.tensor([self.last_page_len()], dtype=torch.int32, device=device)
 
     def free(self):
         self.cache.free_pages(self.pages)

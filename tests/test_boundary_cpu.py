@@ -79,3 +79,36 @@ def test_product_never_imports_oracle_or_falls_back():
     eng = open(os.path.join(pkg, "engine.py")).read()
     for banned in ("torch.matmul", "torch.topk", "torch.softmax", "F.linear", "torch.mm", "@ "):
         assert banned not in eng, f"engine.py contains {banned!r}: arithmetic belongs in the CUDA library"
+
+
+def test_paged_kv_bookkeeping_matches_reference_execution():
+    """PagedKVCache / SequenceKVState host logic vs a trace produced by executing the reference's kv_cache.py on CPU
+    (tests/golden/make_kvcache_golden.py): sizing rule, pool shape/dtype, free-list order, page lists, kv_indices/indptr,
+    last_page_len after every step."""
+    import json
+    import types
+    import torch
+    from krasis_b200.attention import PagedKVCache, SequenceKVState
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kvcache_reference.json")))
+    cfg = types.SimpleNamespace(num_key_value_heads=2, gqa_head_dim=256)
+    sized = PagedKVCache.from_config(cfg, 12, "cpu", max_mb=3)
+    assert (sized.max_pages, sized.max_context_tokens) == (G["sized_pages"], G["sized_tokens"])
+    cache = PagedKVCache.from_config(cfg, 1, "cpu", max_pages=24)
+    assert list(cache.k_cache.shape) == G["k_cache_shape"] and str(cache.k_cache.dtype) == G["k_cache_dtype"]
+    seqs = {}
+    for op, want in zip(G["trace"], G["states"]):
+        if op[0] == "new":
+            seqs[op[1]] = SequenceKVState(cache, op[1])
+        elif op[0] == "ensure":
+            seqs[op[1]].ensure_capacity(op[2])
+        elif op[0] == "advance":
+            seqs[op[1]].advance(op[2])
+        else:
+            seqs[op[1]].free()
+        assert cache.free_page_count == want["free"]
+        for i, s in seqs.items():
+            w = want[str(i)]
+            assert s.pages == w["pages"] and s.seq_len == w["seq_len"] and s.last_page_len() == w["last_page_len"]
+            assert s.kv_indices("cpu").tolist() == w["kv_indices"] and s.kv_indptr("cpu").tolist() == w["kv_indptr"]
+    with pytest.raises(RuntimeError):
+        cache.alloc_pages(10 ** 6)
