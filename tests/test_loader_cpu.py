@@ -190,3 +190,22 @@ def test_marlin_cache_int8_round_trip(tmp_path):
         assert np.array_equal(q13[e], ref[e][0]) and np.array_equal(s13[e].view(np.uint16), ref[e][1].view(np.uint16))
         assert np.array_equal(q2[e], ref[e][2]) and np.array_equal(s2[e].view(np.uint16), ref[e][3].view(np.uint16))
     assert MC.marlin_expert_byte_sizes(2048, 512, 128, 8) == (2097152, 32768, 1048576, 16384)
+
+
+@pytest.mark.parametrize("tag", ["grouped", "single_group"])
+def test_marlin_inverse_matches_reference_execution(tag):
+    """krasis_b200.marlin_cache.marlin_to_rowmajor_int4 and the oracle's marlin_unpack_int4 / marlin_repack_int4 against
+    outputs of the reference's own inverse_marlin_repack / inverse_scale_permute (python/krasis/triton_moe.py:73-180)
+    executed on CPU (tests/golden/make_marlin_golden.py): bit-exact, both directions."""
+    from krasis_b200 import marlin_cache as MC
+    from oracle import quant as Q
+    Gm = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "marlin_inverse_reference.npz"))
+    K, N, gs = [int(v) for v in Gm[f"{tag}_cfg"]]
+    wm, sm, packed, scales = (Gm[f"{tag}_{k}"] for k in ("wm", "sm", "packed", "scales"))
+    p, s = MC.marlin_to_rowmajor_int4(wm, sm, gs)                     # batched (leading dim 2)
+    assert np.array_equal(p, packed) and np.array_equal(s, scales)
+    for b in range(wm.shape[0]):
+        po, so = Q.marlin_unpack_int4(wm[b], sm[b], gs)
+        assert np.array_equal(po, packed[b]) and np.array_equal(so.view(np.uint16), scales[b])
+        mp, ms = Q.marlin_repack_int4(packed[b], scales[b], gs)       # forward direction of the oracle
+        assert np.array_equal(mp, wm[b]) and np.array_equal(ms.view(np.uint16), sm[b])
