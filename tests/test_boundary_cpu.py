@@ -112,3 +112,16 @@ def test_paged_kv_bookkeeping_matches_reference_execution():
             assert s.kv_indices("cpu").tolist() == w["kv_indices"] and s.kv_indptr("cpu").tolist() == w["kv_indptr"]
     with pytest.raises(RuntimeError):
         cache.alloc_pages(10 ** 6)
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    """include/krasis_b200.h must be consumable by a C99 compiler (cgo / Rust bindgen / ctypes users) and by C++."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "krasis_b200.h"\nint main(void){ kb2_config c; kb2_mla_config m; kb2_gqa_config g; (void)c; (void)m; (void)g; return 0; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", f"-I{inc}", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{inc}", "-x", "c++", str(src)], check=True)
