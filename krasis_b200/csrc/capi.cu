@@ -116,6 +116,16 @@ struct ProfSpan {
   }
 };
 
+// device buffers that are freed on scope exit unless released (error paths of the loaders must not leak)
+struct DevBufs {
+  std::vector<void*> p;
+  explicit DevBufs(size_t n) : p(n, nullptr) {}
+  ~DevBufs() { for (void* q : p) if (q) cudaFree(q); }
+  void* release(size_t i) { void* q = p[i]; p[i] = nullptr; return q; }
+  DevBufs(const DevBufs&) = delete;
+  DevBufs& operator=(const DevBufs&) = delete;
+};
+
 static int fmt13(const kb2_engine* e) { return e->cfg.weight_format; }
 static int fmt2(const kb2_engine* e) { return e->cfg.w2_weight_format >= 0 ? e->cfg.w2_weight_format : e->cfg.weight_format; }
 
@@ -129,6 +139,7 @@ static size_t blob_bytes(int fmt) {
   }
   return 0;
 }
+static size_t gguf_row_bytes(int fmt, size_t k) { return fmt == KB2_FMT_GGUF_Q8_0 ? k / 32 * 34 : k / 256 * 144; }
 static bool has_scale_tiles(int fmt) { return fmt == KB2_FMT_INT4_G128 || fmt == KB2_FMT_INT8_G128; }
 
 static size_t tiled_bytes(const kb2_engine* e, int which) {
@@ -187,7 +198,15 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   e->layers.resize(c->num_moe_layers);
   const size_t MK = (size_t)c->max_tokens * c->num_experts_per_tok;
   const size_t max_chunks = c->n_routed_experts + MK / kMaxChunkTokens + 1;
-#define ALLOC(ptr, bytes) CUDA_TRY(cudaMalloc((void**)&(ptr), (bytes)))
+  // a failed allocation must not leak the engine or the buffers made so far: kb2_destroy frees whatever exists
+#define ALLOC(ptr, bytes)                                                                               \
+  do {                                                                                                  \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                               \
+    if (_e != cudaSuccess) {                                                                            \
+      kb2_destroy(e);                                                                                   \
+      return fail(KB2_ERR_CUDA, "cudaMalloc(%s, %zu bytes): %s", #ptr, (size_t)(bytes), cudaGetErrorString(_e)); \
+    }                                                                                                   \
+  } while (0)
   ALLOC(e->counts, sizeof(int) * c->n_routed_experts);
   ALLOC(e->offsets, sizeof(int) * (c->n_routed_experts + 1));
   ALLOC(e->cursor, sizeof(int) * c->n_routed_experts);
@@ -204,8 +223,12 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   ALLOC(e->x_tmp, (size_t)c->max_tokens * c->hidden_size * 2);
   ALLOC(e->out_tmp, (size_t)c->max_tokens * c->hidden_size * 2);
 #undef ALLOC
-  CUDA_TRY(make_tmap_bf16_rows(e->tmap_x, e->x_sorted, (long long)MK, c->hidden_size, gemm_b_box_rows()));
-  CUDA_TRY(make_tmap_bf16_rows(e->tmap_act, e->act, (long long)MK, c->moe_intermediate_size, gemm_b_box_rows()));
+  cudaError_t te = make_tmap_bf16_rows(e->tmap_x, e->x_sorted, (long long)MK, c->hidden_size, gemm_b_box_rows());
+  if (te == cudaSuccess) te = make_tmap_bf16_rows(e->tmap_act, e->act, (long long)MK, c->moe_intermediate_size, gemm_b_box_rows());
+  if (te != cudaSuccess) {
+    kb2_destroy(e);
+    return fail(KB2_ERR_CUDA, "tensor map creation failed: %s", cudaGetErrorString(te));
+  }
   *out = e;
   return KB2_OK;
 }
@@ -268,29 +291,27 @@ KB2_API int kb2_load_experts_host(kb2_engine* e, int layer, const void* w13_q, c
                           const void* w2_s) {
   if (int r = check_layer(e, layer)) return r;
   if (!w13_q || !w13_s || !w2_q || !w2_s) return fail(KB2_ERR_VALUE, "null weight pointer");
-  CUDA_TRY(cudaSetDevice(e->cfg.device));
-  LayerWeights& L = e->layers[layer];
-  free_layer(L);
-  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, fmt = e->cfg.weight_format;
-  if (!has_scale_tiles(fmt13(e)) || !has_scale_tiles(fmt2(e)) || fmt13(e) != fmt2(e))
+  if (!has_scale_tiles(fmt13(e)) || !has_scale_tiles(fmt2(e)) || fmt13(e) != fmt2(e))   // validate BEFORE touching the layer
     return fail(KB2_ERR_STATE, "kb2_load_experts_host takes the INT4/INT8 group-quantised layout; this engine was created for GGUF blocks");
-  void* dst[4];
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, fmt = e->cfg.weight_format;
+  DevBufs dst(4), tmp(4);
   const void* src[4] = {w13_q, w13_s, w2_q, w2_s};
-  void* tmp[4];
   for (int i = 0; i < 4; ++i) {
     const size_t b = tiled_bytes(e, i);   // the re-tiling is a permutation: same byte counts
-    CUDA_TRY(cudaMalloc(&dst[i], b));
-    CUDA_TRY(cudaMalloc(&tmp[i], b));
-    CUDA_TRY(cudaMemcpy(tmp[i], src[i], b, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&dst.p[i], b));
+    CUDA_TRY(cudaMalloc(&tmp.p[i], b));
+    CUDA_TRY(cudaMemcpy(tmp.p[i], src[i], b, cudaMemcpyHostToDevice));
   }
-  cudaError_t r1 = launch_repack(fmt, tmp[0], tmp[1], dst[0], dst[1], e->e_local, 2 * I, H, 0);
-  cudaError_t r2 = launch_repack(fmt, tmp[2], tmp[3], dst[2], dst[3], e->e_local, H, I, 0);
+  cudaError_t r1 = launch_repack(fmt, tmp.p[0], tmp.p[1], dst.p[0], dst.p[1], e->e_local, 2 * I, H, 0);
+  cudaError_t r2 = launch_repack(fmt, tmp.p[2], tmp.p[3], dst.p[2], dst.p[3], e->e_local, H, I, 0);
   e->launches += 4;
   CUDA_TRY(cudaDeviceSynchronize());
-  for (int i = 0; i < 4; ++i) cudaFree(tmp[i]);
   if (r1 != cudaSuccess || r2 != cudaSuccess) return fail(KB2_ERR_CUDA, "retile failed");
-  L.w13_q = (const uint8_t*)dst[0]; L.w13_s = (const uint8_t*)dst[1];
-  L.w2_q = (const uint8_t*)dst[2]; L.w2_s = (const uint8_t*)dst[3];
+  LayerWeights& L = e->layers[layer];
+  free_layer(L);                          // the old weights go only after the new ones exist
+  L.w13_q = (const uint8_t*)dst.release(0); L.w13_s = (const uint8_t*)dst.release(1);
+  L.w2_q = (const uint8_t*)dst.release(2); L.w2_s = (const uint8_t*)dst.release(3);
   L.owned = true;
   return KB2_OK;
 }
@@ -311,17 +332,17 @@ KB2_API int kb2_load_experts_dev(kb2_engine* e, int layer, const void* w13_q_dev
   if (!w13_q_dev || !w13_s_dev || !w2_q_dev || !w2_s_dev) return fail(KB2_ERR_VALUE, "null weight pointer");
   if (!has_scale_tiles(fmt13(e)) || fmt13(e) != fmt2(e)) return fail(KB2_ERR_STATE, "engine was created for GGUF blocks");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
+  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, fmt = e->cfg.weight_format;
+  DevBufs dst(4);
+  for (int i = 0; i < 4; ++i) CUDA_TRY(cudaMalloc(&dst.p[i], tiled_bytes(e, i)));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(launch_repack(fmt, w13_q_dev, w13_s_dev, dst.p[0], dst.p[1], e->e_local, 2 * I, H, s));
+  CUDA_TRY(launch_repack(fmt, w2_q_dev, w2_s_dev, dst.p[2], dst.p[3], e->e_local, H, I, s));
+  e->launches += 4;
   LayerWeights& L = e->layers[layer];
   free_layer(L);
-  const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, fmt = e->cfg.weight_format;
-  void* dst[4];
-  for (int i = 0; i < 4; ++i) CUDA_TRY(cudaMalloc(&dst[i], tiled_bytes(e, i)));
-  cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(launch_repack(fmt, w13_q_dev, w13_s_dev, dst[0], dst[1], e->e_local, 2 * I, H, s));
-  CUDA_TRY(launch_repack(fmt, w2_q_dev, w2_s_dev, dst[2], dst[3], e->e_local, H, I, s));
-  e->launches += 4;
-  L.w13_q = (const uint8_t*)dst[0]; L.w13_s = (const uint8_t*)dst[1];
-  L.w2_q = (const uint8_t*)dst[2]; L.w2_s = (const uint8_t*)dst[3];
+  L.w13_q = (const uint8_t*)dst.release(0); L.w13_s = (const uint8_t*)dst.release(1);
+  L.w2_q = (const uint8_t*)dst.release(2); L.w2_s = (const uint8_t*)dst.release(3);
   L.owned = true;
   return KB2_OK;
 }
@@ -332,24 +353,22 @@ KB2_API int kb2_load_experts_gguf_host(kb2_engine* e, int layer, const void* gat
   const int f13 = fmt13(e), f2 = fmt2(e);
   if (has_scale_tiles(f13) || has_scale_tiles(f2)) return fail(KB2_ERR_STATE, "this engine was not created for GGUF block formats");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
-  LayerWeights& L = e->layers[layer];
-  free_layer(L);
   const size_t H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size, E = e->e_local;
-  auto row_bytes = [](int fmt, size_t k) { return fmt == KB2_FMT_GGUF_Q8_0 ? k / 32 * 34 : k / 256 * 144; };
-  const size_t gu_bytes = E * I * row_bytes(f13, H), dn_bytes = E * H * row_bytes(f2, I);
-  void *dg = nullptr, *du = nullptr, *dd = nullptr, *t13 = nullptr, *t2 = nullptr;
-  CUDA_TRY(cudaMalloc(&dg, gu_bytes)); CUDA_TRY(cudaMalloc(&du, gu_bytes)); CUDA_TRY(cudaMalloc(&dd, dn_bytes));
-  CUDA_TRY(cudaMemcpy(dg, gate_host, gu_bytes, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(du, up_host, gu_bytes, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(dd, down_host, dn_bytes, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&t13, tiled_bytes(e, 0))); CUDA_TRY(cudaMalloc(&t2, tiled_bytes(e, 2)));
-  cudaError_t r1 = launch_retile_gguf(f13, dg, du, (int)I, t13, (int)E, (int)(2 * I), (int)H, 0);
-  cudaError_t r2 = launch_retile_gguf(f2, dd, dd, (int)H, t2, (int)E, (int)H, (int)I, 0);
+  const size_t gu_bytes = E * I * gguf_row_bytes(f13, H), dn_bytes = E * H * gguf_row_bytes(f2, I);
+  DevBufs src(3), til(2);      // raw blocks (freed on return), tiles (kept on success)
+  CUDA_TRY(cudaMalloc(&src.p[0], gu_bytes)); CUDA_TRY(cudaMalloc(&src.p[1], gu_bytes)); CUDA_TRY(cudaMalloc(&src.p[2], dn_bytes));
+  CUDA_TRY(cudaMemcpy(src.p[0], gate_host, gu_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(src.p[1], up_host, gu_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(src.p[2], down_host, dn_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&til.p[0], tiled_bytes(e, 0))); CUDA_TRY(cudaMalloc(&til.p[1], tiled_bytes(e, 2)));
+  cudaError_t r1 = launch_retile_gguf(f13, src.p[0], src.p[1], (int)I, til.p[0], (int)E, (int)(2 * I), (int)H, 0);
+  cudaError_t r2 = launch_retile_gguf(f2, src.p[2], src.p[2], (int)H, til.p[1], (int)E, (int)H, (int)I, 0);
   e->launches += 2;
   CUDA_TRY(cudaDeviceSynchronize());
-  cudaFree(dg); cudaFree(du); cudaFree(dd);
-  if (r1 != cudaSuccess || r2 != cudaSuccess) { cudaFree(t13); cudaFree(t2); return fail(KB2_ERR_CUDA, "GGUF re-tiling failed"); }
-  L.w13_q = (const uint8_t*)t13; L.w2_q = (const uint8_t*)t2; L.w13_s = nullptr; L.w2_s = nullptr;
+  if (r1 != cudaSuccess || r2 != cudaSuccess) return fail(KB2_ERR_CUDA, "GGUF re-tiling failed");
+  LayerWeights& L = e->layers[layer];
+  free_layer(L);
+  L.w13_q = (const uint8_t*)til.release(0); L.w2_q = (const uint8_t*)til.release(1); L.w13_s = nullptr; L.w2_s = nullptr;
   L.owned = true;
   return KB2_OK;
 }

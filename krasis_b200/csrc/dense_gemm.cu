@@ -173,15 +173,16 @@ cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows
 cudaError_t make_tmap_u8_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
 
 static cudaError_t dense_configure() {
-  static bool configured = false;
-  if (configured) return cudaSuccess;
+  static PerDeviceOnce once;
+  const int dev = once.pending();
+  if (dev < 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(dense_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(dense_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(dense_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem);
   if (e != cudaSuccess) return e;
-  configured = true;
+  once.mark(dev);
   return cudaSuccess;
 }
 

@@ -705,14 +705,14 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
   if (d.dv % kSVMax || d.dk > 128 || d.dk % 16 || d.dv > 128 || d.K > 8) return cudaErrorInvalidValue;
   const int C = 2 * d.nk * d.dk + d.nv * d.dv;
   const int n_chunks = (M + kGC - 1) / kGC;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (const int dev = once.pending(); dev >= 0) {
     cudaFuncSetAttribute(gdn_chunk_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     cudaFuncSetAttribute(gdn_chunk_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gdn_chunk_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gdn_chunk_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    configured = true;
+    once.mark(dev);
   }
   if (d.dk == 128 && d.dv == 128 && d.K == 4) {
     const int n_tiles = (M + 31) / 32;

@@ -488,11 +488,13 @@ cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_r
                             void* v_cache, void* k_bf, void* v_bf, void* attn_out, int M, int q_start, int kv_len,
                             cudaStream_t s) {
   if (g.d != 128 && g.d != 256) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(gqa_fmha_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<128, 128>::kTotal);
-    cudaFuncSetAttribute(gqa_fmha_kernel<256, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<256, 256>::kTotal);
-    configured = true;
+  static PerDeviceOnce once;
+  if (const int dev = once.pending(); dev >= 0) {
+    cudaError_t e = cudaFuncSetAttribute(gqa_fmha_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<128, 128>::kTotal);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gqa_fmha_kernel<256, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<256, 256>::kTotal);
+    if (e != cudaSuccess) return e;
+    once.mark(dev);
   }
   gqa_prep_kernel<<<M, 256, 8 * g.d * sizeof(float), s>>>(g, (const __nv_bfloat16*)q_raw, (const __nv_bfloat16*)k_raw,
                                                           (const __nv_bfloat16*)v_raw, q_norm, k_norm, positions,
@@ -627,10 +629,11 @@ cudaError_t launch_mla_core(const MlaDims& m, void* q_full, const void* kv_a, co
                             void* ckv_bf16, void* kpe_bf16, void* kv_up, void* attn_out, int M, int q_start, int kv_len,
                             float sm_scale, int num_sms, cudaStream_t s) {
   if (m.nope != 128 || m.rope != 64 || m.dv != 128 || m.lora % 64) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(gqa_fmha_kernel<192, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<192, 128>::kTotal);
-    configured = true;
+  static PerDeviceOnce once;
+  if (const int dev = once.pending(); dev >= 0) {
+    cudaError_t e0 = cudaFuncSetAttribute(gqa_fmha_kernel<192, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<192, 128>::kTotal);
+    if (e0 != cudaSuccess) return e0;
+    once.mark(dev);
   }
   mla_prep_kernel<<<M, 256, 0, s>>>(m, (const __nv_bfloat16*)kv_a, (__nv_bfloat16*)q_full, kv_norm_w, inv_freq, positions,
                                     kv_indices, (uint8_t*)ckv_cache, (uint8_t*)kpe_cache, M);

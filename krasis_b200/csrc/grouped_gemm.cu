@@ -482,11 +482,11 @@ template <int FMT, bool kGemm1>
 static cudaError_t launch_one(const GemmParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {
   auto kern = grouped_gemm_kernel<FMT, kGemm1>;
   constexpr int smem = SmemLayout<FMT, kGemm1>::kTotal;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (const int dev = once.pending(); dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.mark(dev);
   }
   kern<<<num_sms, kNumThreads, smem, stream>>>(p, tmap);
   return cudaGetLastError();

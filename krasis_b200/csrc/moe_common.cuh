@@ -4,7 +4,24 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 namespace kb2 {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: one process may drive several GPUs (the
+// reference's EP layout, python/krasis/model.py:1496-1523), so the opt-in is remembered per device ordinal, not per
+// process.  Thread-safe (atomic flags; setting the attribute twice is harmless).
+struct PerDeviceOnce {
+  std::atomic<bool> done[64];
+  PerDeviceOnce() { for (auto& d : done) d.store(false); }
+  // returns the current device ordinal if its opt-in is still pending, else -1
+  int pending() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;   // unknown device: always (re)configure
+    return done[dev].load(std::memory_order_acquire) ? -1 : dev;
+  }
+  void mark(int dev) { if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release); }
+};
 
 // ---------------------------------------------------------------------------------------------
 // B200 expert-weight layout ("KB2 tiles").  The reference's quantiser emits, per expert and matrix,

@@ -137,11 +137,11 @@ cudaError_t launch_router_gemm(const void* x, const void* tmap_g, const float* b
   alignas(64) CUtensorMap tx;
   cudaError_t e = make_tmap_bf16_rows(&tx, x, M, H, 128);
   if (e != cudaSuccess) return e;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (const int dev = once.pending(); dev >= 0) {
     e = cudaFuncSetAttribute(router_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.mark(dev);
   }
   router_gemm_kernel<<<(M + 127) / 128, kRThreads, kRSmem, s>>>(tx, *reinterpret_cast<const CUtensorMap*>(tmap_g), bias,
                                                                logits, M, E, H);

@@ -120,6 +120,23 @@ class KrasisEngine:
             arrs.append(a)
         capi.check(self._lib.kb2_load_experts_host(self._h, moe_layer_idx, *[a.ctypes.data for a in arrs]))
 
+    def load_quantized_layer_dev(self, moe_layer_idx: int, w13_q: torch.Tensor, w13_s: torch.Tensor,
+                                 w2_q: torch.Tensor, w2_s: torch.Tensor):
+        """`load_quantized_layer` for arrays that already live on the device (same reference-quantiser layout and
+        shapes; int32 words for INT4, int8 for INT8, int16 raw-BF16 scales): re-tiled on the device, no host copy."""
+        E = self.expert_end - self.expert_start
+        H, I = self._cfg.hidden_size, self._cfg.moe_intermediate_size
+        shapes = ({4: (E, 2 * I, H // 8), 8: (E, 2 * I, H)}[self._num_bits], (E, 2 * I, H // 128),
+                  {4: (E, H, I // 8), 8: (E, H, I)}[self._num_bits], (E, H, I // 128))
+        qdt = torch.int32 if self._num_bits == 4 else torch.int8
+        for name, t, shp, dt in zip(("w13_q", "w13_s", "w2_q", "w2_s"), (w13_q, w13_s, w2_q, w2_s), shapes,
+                                    (qdt, torch.int16, qdt, torch.int16)):
+            if tuple(t.shape) != shp or t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"{name}: expected contiguous CUDA {dt} {shp}, got {t.dtype} {tuple(t.shape)}")
+        capi.check(self._lib.kb2_load_experts_dev(self._h, moe_layer_idx, w13_q.data_ptr(), w13_s.data_ptr(),
+                                                  w2_q.data_ptr(), w2_s.data_ptr(), _stream_ptr(self.device)))
+        torch.cuda.synchronize(self.device)
+
     def quantize_group(self, w_bf16: torch.Tensor, num_bits: Optional[int] = None):
         """Krasis symmetric g128 quantiser on the device (src/weights/marlin.rs:145-207 / :65-114), bit-exact.
         w [..., K] bf16 -> (q [..., K/8] int32 | [..., K] int8, scales [..., K/128] raw-bf16 int16)."""

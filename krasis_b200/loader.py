@@ -77,19 +77,28 @@ def expert_prefix(names) -> str:
     raise ValueError("no expert tensors found")
 
 
+def _expert_tensor_bf16(tensors: Dict[str, SafetensorsFile], name: str) -> np.ndarray:
+    """Raw BF16 bits of an expert tensor.  The quantiser's input contract is BF16 (src/weights/mod.rs:5023-5046 reads
+    `&[u16]`); any other storage dtype is refused instead of being reinterpreted."""
+    dt = tensors[name].header[name]["dtype"]
+    if dt != "BF16":
+        raise ValueError(f"{name}: expert tensors must be BF16 (found {dt}); pre-quantised / FP16 / FP32 checkpoints are out of scope")
+    return tensors[name].tensor(name)
+
+
 def read_layer_experts_bf16(tensors: Dict[str, SafetensorsFile], prefix: str, layer: int, e0: int, e1: int):
     """Returns (w13 [E, 2I, H] uint16 bf16 with gate rows first, w2 [E, H, I]) for experts [e0, e1)."""
     stacked = f"{prefix}.layers.{layer}.mlp.experts.gate_up_proj"
     if stacked in tensors:                                                  # Qwen3.5: mod.rs:4670-4677,5095-5168
-        w13 = tensors[stacked].tensor(stacked)[e0:e1]
+        w13 = _expert_tensor_bf16(tensors, stacked)[e0:e1]
         dn = f"{prefix}.layers.{layer}.mlp.experts.down_proj"
-        return np.ascontiguousarray(w13), np.ascontiguousarray(tensors[dn].tensor(dn)[e0:e1])
+        return np.ascontiguousarray(w13), np.ascontiguousarray(_expert_tensor_bf16(tensors, dn)[e0:e1])
     w13, w2 = [], []
     for e in range(e0, e1):                                                 # mod.rs:5023-5046
         base = f"{prefix}.layers.{layer}.mlp.experts.{e}."
-        g = tensors[base + "gate_proj.weight"].tensor(base + "gate_proj.weight")
-        u = tensors[base + "up_proj.weight"].tensor(base + "up_proj.weight")
-        d = tensors[base + "down_proj.weight"].tensor(base + "down_proj.weight")
+        g = _expert_tensor_bf16(tensors, base + "gate_proj.weight")
+        u = _expert_tensor_bf16(tensors, base + "up_proj.weight")
+        d = _expert_tensor_bf16(tensors, base + "down_proj.weight")
         w13.append(np.concatenate([g, u], axis=0))                         # w13 = [gate ; up] (mod.rs:346-349)
         w2.append(d)
     return np.stack(w13), np.stack(w2)
@@ -228,8 +237,17 @@ def load_experts_from_gguf(engine, gguf_path: str, first_k_dense: int = 0):
 # re-arrangement of BF16 tensors (torch on CPU): no arithmetic except the documented `+ 1.0` in BF16.
 
 def _st_bf16(tensors: Dict[str, SafetensorsFile], name: str):
+    """The reference's `_load_bf16` = `_read_tensor(name).to(torch.bfloat16)` (weight_loader.py:147-166): BF16 storage is
+    taken as is; F32 / F16 storage (A_log, dt_bias, e_score_correction_bias, some norm weights in real checkpoints) is
+    CONVERTED (round to nearest even, like torch); any other dtype is an error rather than a reinterpretation."""
     import torch
-    return torch.from_numpy(np.array(tensors[name].tensor(name)).view(np.int16)).view(torch.bfloat16)
+    dt = tensors[name].header[name]["dtype"]
+    raw = np.array(tensors[name].tensor(name))
+    if dt == "BF16":
+        return torch.from_numpy(raw.view(np.int16)).view(torch.bfloat16)
+    if dt in ("F32", "F16"):
+        return torch.from_numpy(raw).to(torch.bfloat16)
+    raise ValueError(f"{name}: dtype {dt} cannot be loaded as a BF16 weight")
 
 
 def norm_plus_one(w):

@@ -198,9 +198,12 @@ def gqa_core(q, k_cache, v_cache, q_pos, sm_scale):
     return torch.einsum("hml,lhd->mhd", p, vf).to(torch.bfloat16)
 
 
-def gqa_layer_prefill(hidden, w, cfg, positions, k_cache=None, v_cache=None, kv_dtype=torch.float8_e4m3fn):
+def gqa_layer_prefill(hidden, w, cfg, positions, k_cache=None, v_cache=None, kv_dtype=torch.float8_e4m3fn, rows=None):
     """GQAAttention.forward (attention.py:496-687) for BF16 weights: returns (out [M,H] bf16, k_cache, v_cache)
-    with the caches holding values already rounded through kv_dtype (stored as that dtype)."""
+    with the caches holding values already rounded through kv_dtype (stored as that dtype).
+    rows (optional LongTensor): evaluate the attention core and the output projection only for these query rows of
+    `hidden` (the projections, norms, RoPE and the cache append still cover every token) -> out [len(rows), H]; this is
+    how the 8K-token parity tests stay within seconds of CPU time."""
     nh, nkv, d = cfg["nh"], cfg["nkv"], cfg["d"]
     M = hidden.shape[0]
     q_raw = F.linear(hidden, w["q_proj"])
@@ -222,6 +225,10 @@ def gqa_layer_prefill(hidden, w, cfg, positions, k_cache=None, v_cache=None, kv_
     k_new, v_new = k.to(kv_dtype), v.to(kv_dtype)
     k_cache = k_new if k_cache is None else torch.cat([k_cache, k_new], dim=0)
     v_cache = v_new if v_cache is None else torch.cat([v_cache, v_new], dim=0)
+    if rows is not None:
+        q, positions, M = q[rows], positions[rows], len(rows)
+        if gated:
+            gate = gate[rows]
     attn = gqa_core(q.to(torch.bfloat16), k_cache, v_cache, positions, 1.0 / math.sqrt(d))
     flat = attn.reshape(M, nh * d)
     if gated:
