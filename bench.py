@@ -1,25 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — prefill throughput of the B200-native MoE hot path (driver contract: one JSON line).
+"""bench.py — prefill throughput of the B200-native Krasis hot path (driver contract: one JSON line on stdout).
 
-  python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--config qcn|qwen35|v2lite|q235b]
 
-Workload (BASELINE.json configs[3], the config the metric is quoted on): Qwen3-Coder-Next geometry —
-H=2048, I=512, E=512 routed experts, top-10, INT4 g128 experts, 48 MoE layers, one 8192-token prompt.
-A "step" = one prefill pass of the 8192 tokens through the 48 MoE blocks (router -> top-k -> binning ->
-grouped gate/up GEMM + SiLU*mul -> grouped down GEMM -> weighted combine) with synthetic weights
-(random INT4 nibbles + BF16 group scales) and a synthetic RMS-normalised hidden state.  Attention blocks
-are NOT in this round's step (DESIGN.md "scope this round"); the workload name says so.
+Workload (default = BASELINE.json configs[3], the configuration the metric is quoted on): the WHOLE Qwen3-Coder-Next
+prefill — embedding gather -> 48 x (RMSNorm, Gated DeltaNet or gated GQA attention with an FP8 paged KV cache, fused
+add + RMSNorm, router, 512-expert top-10 INT4 g128 MoE, INT8 gated shared expert) -> final norm -> INT8 lm_head — of one
+8192-token prompt, with synthetic weights of the real shapes (krasis_b200.model.SyntheticWeights; no checkpoints exist in
+this environment).  --config selects the other BASELINE configurations (DeepSeek-V2-Lite: MLA + first dense layer + INT4
+shared experts; Qwen3.5-35B-A3B; Qwen3-235B at 4096 tokens).  A "step" is one such prefill.
 
-  value     tokens/s with the hidden state resident in HBM (device-timed, CUDA events, max over ranks)
-  e2e       tokens/s through the C-ABI host entry point: H2D of the pinned hidden state, all layers, D2H
-  roofline  dominant kernel = grouped gate/up expert GEMM (tensor-bound; algorithmic FLOPs / event time)
-  cpu_baseline  the reference's CPU expert path (C/AVX2 port, oracle/cpu_moe.c) on a bounded token sample
+  value     tokens/s, inputs resident in HBM, device-timed with CUDA events around K steps, max over ranks.  Per-kernel
+            and per-component profiling is OFF inside this region.
+  e2e       the same prefill through the public API (KrasisModel.forward) with HOST buffers: pinned token ids copied in,
+            last-token logits copied out, every step, wall clock, max over ranks.
+  roofline  for the kernel class with the LARGEST measured share of the step; the per-kernel table comes from a separate
+            profiled pass (CUDA events around every launch, kb2_kernel_profile_*) that is not part of `value`.
+  cpu_baseline / --impl reference   the reference's CPU expert path (C/AVX2 port, oracle/cpu_moe.c) on the host cores.
 
-N>1 (torchrun, one rank per GPU): expert-parallel.  Experts are sliced like the reference
-(python/krasis/gpu_prefill.py:353-359: rank r owns E/N contiguous experts of every layer); unlike the reference
-(tokens replicated through pinned host memory, partial sums added on GPU0, python/krasis/model.py:3086-3211) the
-8192 tokens are SHARDED over the ranks and only routed rows travel: NCCL all-to-all dispatch -> grouped expert
-GEMMs on the owner -> all-to-all back -> weighted combine at home (krasis_b200/parallel.py).  scaling = "strong".
+N > 1 (torchrun, one rank per GPU): the residual stream is token-sharded, attention head-parallel (all-gather in,
+reduce-scatter out), experts sliced by rank like the reference (python/krasis/gpu_prefill.py:353-359) with an all-gather of
+the routed rows and a reduce-scatter of the partial sums — NCCL over NVLink behind the C ABI (kb2_comm_*).  One prompt is
+split over the GPUs: scaling = "strong".
 """
 import argparse
 import json
@@ -32,10 +34,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-QCN = dict(hidden_size=2048, moe_intermediate_size=512, n_routed_experts=512, num_experts_per_tok=10,
-           num_moe_layers=48, num_bits=4, norm_topk_prob=True, routed_scaling_factor=1.0)
-TOKENS = 8192
 METRIC = "prefill tokens/sec @8K ctx, Qwen3-Coder-Next Q4"
+DEFAULT_TOKENS = {"qcn": 8192, "qwen35": 8192, "v2lite": 8192, "q235b": 4096}
+BASELINE_CONFIG = {"qcn": "configs[3] Qwen3-Coder-Next int4gpu", "qwen35": "configs[2] Qwen3.5-35B-A3B int4gpu",
+                   "v2lite": "configs[1] DeepSeek-V2-Lite int4gpu", "q235b": "configs[4] Qwen3-235B-A22B int4gpu (prefill half)"}
 
 
 def peaks():
@@ -95,16 +97,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def preset(args):
+    from dataclasses import replace
+    from krasis_b200.model import PRESETS
+    cfg = PRESETS[args.config]
+    if args.layers:
+        cfg = replace(cfg, num_hidden_layers=args.layers)
+    return cfg
+
+
 # --------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_sample(budget_s=15.0, n_weight_sets=2, threads=0):
-    """Time the C/AVX2 port of the reference's CPU expert path on a bounded token sample of the SAME
-    workload (QCN geometry, 48 layer passes per token).  Weights: n_weight_sets layers of random packed
-    INT4 (0.8 GB each) cycled over the 48 passes; routing: uniform without replacement + Dirichlet(1)
-    weights (tests/bench_engine_isolated.py:88-92)."""
+def cpu_sample(cfg, budget_s=15.0, n_weight_sets=2, threads=0):
+    """Time the C/AVX2 port of the reference's CPU expert path (moe_forward_unified, src/moe.rs:572-715) on a bounded
+    token sample of the SAME workload geometry (one pass per MoE layer per token).  Weights: n_weight_sets layers of random
+    packed INT4 cycled over the layer passes; routing: uniform without replacement + Dirichlet(1) weights
+    (tests/bench_engine_isolated.py:88-92)."""
     import numpy as np
     from oracle import cpu_ref
-    H, I, E, k, L = QCN["hidden_size"], QCN["moe_intermediate_size"], QCN["n_routed_experts"], QCN["num_experts_per_tok"], QCN["num_moe_layers"]
+    H, I, E, k, L = cfg.hidden_size, cfg.moe_intermediate_size, cfg.n_routed_experts, cfg.num_experts_per_tok, cfg.num_moe_layers
     rng = np.random.default_rng(0xDEADBEEF)
     sets = []
     for _ in range(n_weight_sets):
@@ -126,9 +137,8 @@ def cpu_sample(budget_s=15.0, n_weight_sets=2, threads=0):
             cpu_ref.moe_forward_int4(*sets[l % n_weight_sets], xb, ids, w, nthreads=nthreads)
         return time.perf_counter() - t0
 
-    # "all the host threads it can use": the flattened dispatch has 40-80 work items per phase
-    # (src/moe.rs:727-740), so more threads than that only add barrier cost; pick the fastest of a few
-    # thread counts on a 2-token probe and say which.
+    # "all the host threads it can use": the flattened dispatch has k*H/.. work items per phase (src/moe.rs:727-740), so more
+    # threads than that only add barrier cost; pick the fastest of a few thread counts on a 2-token probe and say which.
     nthreads = threads or avail
     run(1)                                                # warms the thread pool, first-touches the weights
     if not threads:
@@ -143,18 +153,20 @@ def cpu_sample(budget_s=15.0, n_weight_sets=2, threads=0):
     n_tok = int(max(2, min(4096, budget_s / max(t1, 1e-4))))
     dt = run(n_tok)
     return dict(value=n_tok / dt, unit="tokens/s", cores=nthreads, host_threads_available=avail, kind="port",
-                sample=f"{n_tok} tokens x {L} MoE layer passes, QCN geometry, {n_weight_sets} random weight sets cycled; "
-                       f"C/AVX2 port of src/moe.rs:572-715 + src/kernel/avx2.rs:1066-1206 ({dt:.1f}s)"), n_tok, dt
+                sample=f"{n_tok} tokens x {L} MoE layer passes, {cfg.name} expert geometry (H{H} I{I} E{E} top-{k}), {n_weight_sets} random "
+                       f"weight sets cycled; C/AVX2 port of src/moe.rs:572-715 + src/kernel/avx2.rs:1066-1206 ({dt:.1f}s); routed-expert "
+                       f"MoE blocks only (the reference's CPU expert path) — attention is not in the CPU sample"), n_tok, dt
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = preset(args)
     per_step = max(3.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     vals = []
     for i in range(args.warmup + args.steps):
-        r, n_tok, dt = cpu_sample(budget_s=per_step)
+        r, n_tok, dt = cpu_sample(cfg, budget_s=per_step)
         if i >= args.warmup:
             vals.append((r, n_tok, dt))
     tot_tok = sum(v[1] for v in vals)
@@ -164,48 +176,120 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": tot_tok / tot_t, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16xint4->f32",
-            "data": "synthetic", "config": workload_config(args, 1),
+            "data": "synthetic", "config": workload_config(args, cfg, 1),
             "cpu_baseline": cb,
             "e2e": {"value": tot_tok / tot_t, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(args, n):
-    if args.workload == "moe_stack":
-        return {"workload": f"qcn_moe_stack: {args.layers} MoE layers x {args.tokens} tokens, H2048 I512 E512 top-10, INT4 g128",
-                "tokens": args.tokens, "layers": args.layers, "parallelism": f"ep{n}-{args.ep_mode}" if n > 1 else "single",
-                "l2_policy": "inputs larger than L2: 792 MiB of expert weights streamed per layer",
-                "attention": "not in this workload"}
-    return {"workload": f"qcn_full_prefill: Qwen3-Coder-Next architecture, {args.layers} layers (3 Gated-DeltaNet : 1 gated GQA 16/2/256), "
-                        f"512-expert top-10 INT4 g128 MoE + INT8 shared expert per layer, final norm + INT8 lm_head, {args.tokens}-token prompt",
-            "tokens": args.tokens, "layers": args.layers,
-            "parallelism": f"ep{n}-replicate (attention replicated, experts sliced, partial sums all-reduced)" if n > 1 else "single",
-            "l2_policy": "inputs larger than L2: ~0.9 GB of weights streamed per layer",
+def workload_config(args, cfg, n):
+    n_lin = sum(cfg.layer_type(i) == "linear_attention" for i in range(cfg.num_hidden_layers))
+    att = ("MLA (FP8 latent cache)" if cfg.is_mla else f"gated GQA {cfg.num_attention_heads}/{cfg.num_key_value_heads}/{cfg.gqa_head_dim}"
+           if cfg.gated_attention else f"GQA {cfg.num_attention_heads}/{cfg.num_key_value_heads}/{cfg.gqa_head_dim}")
+    if not cfg.shared_width:
+        shared = "no shared expert"
+    elif cfg.shared_expert_gate:
+        shared = "INT8 gated shared expert"
+    else:
+        shared = "INT4 fused shared experts (manager-owned)" if n == 1 else "INT8 shared experts"
+    return {"workload": f"{args.config}_full_prefill: {cfg.name} architecture, {cfg.num_hidden_layers} layers ({n_lin} Gated-DeltaNet, "
+                        f"{cfg.num_hidden_layers - n_lin} {att}, {cfg.first_k_dense_replace} dense-MLP), {cfg.n_routed_experts}-expert "
+                        f"top-{cfg.num_experts_per_tok} INT4 g128 MoE (H{cfg.hidden_size} I{cfg.moe_intermediate_size}) + {shared}, final norm + "
+                        f"INT8 lm_head, {args.tokens}-token prompt",
+            "baseline_config": BASELINE_CONFIG[args.config],
+            "tokens": args.tokens, "layers": cfg.num_hidden_layers,
+            "parallelism": (f"tp{n}+ep{n}: token-sharded residual stream, head-parallel attention (all-gather / reduce-scatter), "
+                            f"experts sliced by rank (all-gather rows, reduce-scatter partial sums), NCCL behind the C ABI") if n > 1 else "single",
+            "l2_policy": "inputs larger than L2: every layer streams its own expert weights (0.3-1.2 GB per layer) from HBM",
             "kv_cache": "FP8 E4M3 paged (16 tokens/page)"}
+
+
+# --------------------------------------------------------------------------------------------- roofline bookkeeping
+
+def algorithmic_work(cfg, M, R):
+    """Algorithmic FLOPs (tensor-bound classes) or bytes (HBM-bound classes) per STEP of each kernel class, on one rank
+    (DESIGN.md §4 states the per-unit figures).  Returns {class: (bound, work_per_step)}."""
+    H, I, k, E = cfg.hidden_size, cfg.moe_intermediate_size, cfg.num_experts_per_tok, cfg.n_routed_experts
+    L = cfg.num_hidden_layers
+    n_moe = cfg.num_moe_layers
+    types = [cfg.layer_type(i) for i in range(L)]
+    n_gdn, n_mla = types.count("linear_attention"), types.count("mla")
+    n_gqa = L - n_gdn - n_mla
+    nk, nv, dk, dv = cfg.linear_num_key_heads // R, cfg.linear_num_value_heads // R, cfg.linear_key_head_dim, cfg.linear_value_head_dim
+    kd, vd = nk * dk, nv * dv
+    nh, d = cfg.num_attention_heads // R, cfg.gqa_head_dim
+    nkv = max(1, cfg.num_key_value_heads // R)
+    nch = (M + 63) // 64
+    Ml = M // R
+    w = {}
+    w["grouped_gemm<gate_up+silu_mul>"] = ("tensor", n_moe * 2.0 * M * k * H * 2 * I / R)
+    w["grouped_gemm<down>"] = ("tensor", n_moe * 2.0 * M * k * I * H / R)
+    if cfg.shared_width and not cfg.shared_expert_gate and R == 1:      # manager-owned INT4 shared experts run the same kernels
+        w["grouped_gemm<gate_up+silu_mul>"] = ("tensor", w["grouped_gemm<gate_up+silu_mul>"][1] + n_moe * 2.0 * M * H * 2 * cfg.shared_width)
+        w["grouped_gemm<down>"] = ("tensor", w["grouped_gemm<down>"][1] + n_moe * 2.0 * M * cfg.shared_width * H)
+    w["router_gemm"] = ("tensor", n_moe * 2.0 * Ml * H * E)
+    # Gated DeltaNet, per (head, 64-token chunk): kcd.S, q.S, k^T.v (2*64*dk*dv each) + intra.v (2*64*64*dv); prepare: k.k^T,
+    # q.k^T (2*64*64*dk each) + the unit-lower-triangular solve with dk+dv right-hand sides (64*64*(dk+dv))
+    w["gdn_chunk_scan"] = ("tensor", n_gdn * nv * nch * (3 * 2.0 * 64 * dk * dv + 2.0 * 64 * 64 * dv))
+    w["gdn_chunk_prepare"] = ("tensor", n_gdn * nv * nch * (2 * 2.0 * 64 * 64 * dk + 64.0 * 64 * (dk + dv)))
+    w["gdn_prep(conv+l2norm+gates)"] = ("hbm", n_gdn * M * 2.0 * ((2 * kd + 2 * vd) + (2 * kd + vd)))         # read qkvz, write q,k,v
+    w["gdn_post(gated_rmsnorm)"] = ("hbm", n_gdn * M * 2.0 * 3 * vd)                                           # core + z in, normed out
+    if cfg.is_mla:
+        qd = cfg.qk_nope_head_dim + cfg.qk_rope_head_dim
+        w["fmha"] = ("tensor", n_mla * 2.0 * M * M / 2 * nh * (qd + cfg.v_head_dim))
+    else:
+        w["fmha"] = ("tensor", n_gqa * 4.0 * M * M / 2 * nh * d)
+    dense = n_gdn * (2.0 * M * H * (2 * kd + 2 * vd) + 2.0 * M * H * 2 * nv + 2.0 * M * vd * H)
+    if cfg.is_mla:
+        lora, qd = cfg.kv_lora_rank, cfg.qk_nope_head_dim + cfg.qk_rope_head_dim
+        dense += n_mla * (2.0 * M * H * (lora + cfg.qk_rope_head_dim) + 2.0 * M * H * nh * qd + 2.0 * M * lora * nh * 256 + 2.0 * M * nh * 128 * H)
+    else:
+        dense += n_gqa * (2.0 * M * H * nh * d * (2 if cfg.gated_attention else 1) + 2 * 2.0 * M * H * nkv * d + 2.0 * M * nh * d * H)
+    w["dense_gemm<bf16>"] = ("tensor", dense)
+    i8 = 2.0 * H * cfg.vocab_size                                                                               # lm_head on the last token
+    if cfg.shared_width and (cfg.shared_expert_gate or R > 1):
+        i8 += n_moe * 2.0 * Ml * H * 3 * cfg.shared_width
+    i8 += cfg.first_k_dense_replace * 2.0 * Ml * H * 3 * cfg.intermediate_size
+    w["dense_gemm<int8>"] = ("tensor", i8)
+    w["combine"] = ("hbm", n_moe * (M * k * H * 2.0 / R * 1.0 + M * H * 2.0 * 2))
+    w["binning(count+scan+scatter)"] = ("hbm", n_moe * (M * H * 2.0 + M * k * H * 2.0 / R))
+    w["rmsnorm"] = ("hbm", (2 * L + 1) * Ml * H * 2.0 * 4)                                                      # x, residual in; x, residual out
+    w["kv_gather(fp8->bf16)"] = ("hbm", (n_gqa * M * nkv * d * 2 * 3.0) if not cfg.is_mla else n_mla * M * (cfg.kv_lora_rank + 64) * 3.0)
+    return w
+
+
+def load_traffic():
+    """ncu DRAM bytes per launch, per kernel class, from the committed capture summary (profiles/kernel_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
 
-NCU_GEMM1_DRAM_BYTES = 966221312      # 889.42 MB read + 76.80 MB written (N=1, 8192 tokens)
-
-
 def run_full_model(args):
-    """Whole-model prefill: embedding -> 48 x (norm, GDN|GQA, norm, router, routed experts, shared expert) -> norm -> lm_head."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from krasis_b200.model import HybridMoEConfig, KrasisModel
+    from krasis_b200 import capi
+    from krasis_b200.model import KrasisModel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    comm = None
     if world > 1:
+        from krasis_b200.parallel import Communicator
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        torch.cuda.set_device(local)
+        comm = Communicator.from_torch_distributed(local)       # NCCL behind the C ABI; torch.distributed only carried the id
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    cfg = HybridMoEConfig(num_hidden_layers=args.layers)
+    cfg = preset(args)
     M = args.tokens
-    model = KrasisModel(cfg, device=local, max_tokens=M, rank=rank, num_ranks=world)
+    model = KrasisModel(cfg, device=local, max_tokens=M, rank=rank, num_ranks=world, comm=comm)
     eng = model.engine
     g = torch.Generator().manual_seed(42)
     tok_host = torch.randint(0, cfg.vocab_size, (M,), generator=g, dtype=torch.int32).pin_memory()
@@ -221,15 +305,21 @@ def run_full_model(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     for _ in range(args.warmup):
         step()
     barrier()
+    # ---- timed region: no per-kernel events, no component spans
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    eng.profile(True)
-    model.timing_start()
-    l0 = eng.launch_count()
+    l0 = capi.total_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -237,20 +327,13 @@ def run_full_model(args):
         step()
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    moe_launches = eng.launch_count() - l0
-    prof = eng.profile_collect()
-    comp = {kk: v / args.steps for kk, v in model.timing_collect().items()}
-    eng.profile(False)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = capi.total_launches() - l0
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_per_step = ms / args.steps
     value = M / (ms_per_step * 1e-3)
 
-    # end to end: pinned host token ids -> device, forward, last-token logits -> pinned host, every step
+    # ---- end to end: pinned host token ids -> device, forward, last-token logits -> pinned host, every step
     def e2e_step():
         tk = tok_host.to(dev, non_blocking=True)
         lg = model.forward(tk, pos, model.new_sequence())
@@ -263,184 +346,68 @@ def run_full_model(args):
     for _ in range(args.steps):
         e2e_step()
     barrier()
-    dt = (time.perf_counter() - t0) / args.steps
-    if world > 1:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dt = max_over_ranks((time.perf_counter() - t0) / args.steps)
     e2e = {"value": M / dt, "unit": "tokens/s", "h2d_bytes_per_step": M * 4, "d2h_bytes_per_step": cfg.vocab_size * 4,
            "ms_per_step": dt * 1e3, "entry": "KrasisModel.forward(token_ids, positions, seq_states): pinned host token ids in, last-token logits out"}
+
+    # ---- separate profiled pass (not part of `value`): CUDA events around every kernel launch + per-component spans
+    prof_steps = max(1, min(2, args.steps))
+    capi.kernel_profile(True)
+    model.timing_start()
+    barrier()
+    for _ in range(prof_steps):
+        step()
+    kprof = {n: (t / prof_steps, c // prof_steps) for n, (t, c) in capi.kernel_profile_collect().items()}
+    comp = {kk: v / prof_steps for kk, v in model.timing_collect().items()}
+    capi.kernel_profile(False)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
-    k, H, I = cfg.num_experts_per_tok, cfg.hidden_size, cfg.moe_intermediate_size
-    g1_ms, g1_n = prof["gemm1_gate_up_silu"]
-    flops_per_launch = 2.0 * M * k * H * (2 * I) / world
-    achieved = flops_per_launch / (g1_ms / max(1, g1_n) * 1e-3) / 1e12 if g1_n else None
-    moe_ms = sum(v[0] for v in prof.values()) / args.steps
-    n_gdn = sum(t == "linear_attention" for t in model.layer_types)
-    n_gqa = args.layers - n_gdn
-    # kernels per step outside the MoE engine: GDN 3 GEMM + 5, GQA 4 GEMM + 3, 2 norms, shared expert 6, final norm + lm_head 3
-    other_launches = (n_gdn * 8 + n_gqa * 7 + args.layers * (2 + 6) + 3) * args.steps
-    roofline = {"kernel": "grouped_gemm_kernel<INT4, gate/up + SiLU*mul>", "bound": "tensor", "achieved": achieved,
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": (achieved / pk["tf_sustained"]) if achieved else None,
-                "traffic": NCU_GEMM1_DRAM_BYTES if world == 1 and M == TOKENS else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this command "
-                                  "(profiles/r01h_grouped_gemm_full_model_raw.csv); algorithmic minimum 528 MiB weights + 320 MiB tokens + 80 MiB act",
-                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
-                "algorithmic": f"2*M*k*H*2I/ranks = {flops_per_launch:.3e} FLOP per launch", "avg_launch_ms": g1_ms / max(1, g1_n),
-                "moe_kernel_ms_per_step": {kk: v[0] / args.steps for kk, v in prof.items()},
-                "moe_ms_per_step": moe_ms, "attention_dense_other_ms_per_step": ms_per_step - moe_ms,
-                "component_ms_per_step": comp}
+    work = algorithmic_work(cfg, M, world)
+    traffic = load_traffic()
+    table = {}
+    for name, (t_ms, n) in sorted(kprof.items(), key=lambda kv: -kv[1][0]):
+        row = {"ms_per_step": t_ms, "launches_per_step": n}
+        if name in work and t_ms > 0:
+            bound, amount = work[name]
+            row["bound"] = bound
+            if bound == "tensor":
+                row["achieved_tflops"] = amount / (t_ms * 1e-3) / 1e12
+                row["frac_of_peak"] = row["achieved_tflops"] / pk["tf_sustained"]
+            else:
+                row["achieved_gbs"] = amount / (t_ms * 1e-3) / 1e9
+                row["frac_of_peak"] = row["achieved_gbs"] / pk["hbm_gbs"]
+        table[name] = row
+    top = next(iter(table)) if table else None
+    roofline = None
+    if top:
+        r = table[top]
+        tensor = r.get("bound", "tensor") == "tensor"
+        ach = r.get("achieved_tflops" if tensor else "achieved_gbs")
+        roofline = {"kernel": top, "bound": "tensor" if tensor else "hbm", "achieved": ach,
+                    "peak": pk["tf_sustained"] if tensor else pk["hbm_gbs"], "unit": "TFLOP/s" if tensor else "GB/s",
+                    "frac": r.get("frac_of_peak"),
+                    "traffic": traffic.get(top, {}).get("dram_bytes_per_launch") if world == 1 and M == DEFAULT_TOKENS[args.config] else None,
+                    "traffic_source": traffic.get(top, {}).get("source"),
+                    "peak_source": pk["source"] + (", sustained figure (kernel timed inside a long step)" if tensor else ""),
+                    "selection": "kernel class with the largest summed device time in the profiled pass",
+                    "share_of_profiled_step": r["ms_per_step"] / max(1e-9, sum(x["ms_per_step"] for x in table.values())),
+                    "avg_launch_ms": r["ms_per_step"] / max(1, r["launches_per_step"]),
+                    "algorithmic_per_step": work.get(top, (None, None))[1],
+                    "per_kernel": table, "component_ms_per_step": comp}
     cnt = eng.last_expert_counts().astype(np.float64)          # routing load of the last MoE layer of the last step
-    roofline["last_layer_tokens_per_expert"] = {"mean": float(cnt.mean()), "max": float(cnt.max()), "p50": float(np.median(cnt)),
-                                                "below_32": int((cnt < 32).sum()), "above_192": int((cnt > 192).sum())}
+    if roofline:
+        roofline["last_layer_tokens_per_expert"] = {"mean": float(cnt.mean()), "max": float(cnt.max()), "p50": float(np.median(cnt)),
+                                                    "below_32": int((cnt < 32).sum()), "above_192": int((cnt > 192).sum())}
     cpu_b = None
     if not args.no_cpu_baseline:
-        cpu_b, _, _ = cpu_sample(budget_s=args.cpu_budget)
-        cpu_b["sample"] += " — routed-expert MoE blocks only (the reference's CPU expert path); attention is not in the CPU sample"
+        cpu_b, _, _ = cpu_sample(cfg, budget_s=args.cpu_budget)
     line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int4 experts x bf16 activations (fp32 acc), bf16 attention, fp8 KV, int8 shared expert / lm_head",
-            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(moe_launches + other_launches), "roofline": roofline, "cpu_baseline": cpu_b}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from krasis_b200 import KrasisEngine
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    cfg = dict(QCN)
-    cfg["num_moe_layers"] = args.layers
-    M = args.tokens
-    eng = KrasisEngine(**cfg, rank=rank, num_ranks=world, max_tokens=M, device=local)
-
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)   # expert weights differ per rank (different experts)
-    weights = []
-    for l in range(args.layers):
-        ts = []
-        for which in range(4):
-            n = eng.tiled_bytes(which)
-            if which in (0, 2):
-                ts.append(torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g))
-            else:
-                ts.append((torch.rand(n // 2, device=dev, generator=g) * 0.008 + 0.004).to(torch.bfloat16))
-        eng.attach_tiled_layer(l, *ts)
-        weights.append(ts)
-        gate = (torch.randn(cfg["n_routed_experts"], cfg["hidden_size"], device=dev,
-                            generator=torch.Generator(device=dev).manual_seed(77 + l)) * 0.02).to(torch.bfloat16)
-        eng.set_routing_weights(l, gate)
-    gx = torch.Generator(device=dev).manual_seed(42)   # identical on every rank
-    x = torch.randn(M, cfg["hidden_size"], device=dev, generator=gx)
-    x = (x / x.pow(2).mean(-1, keepdim=True).sqrt()).to(torch.bfloat16)
-    x_host = x.cpu().pin_memory()
-    out_host = torch.empty_like(x_host).pin_memory()
-
-    ep = None
-    if world > 1:
-        from krasis_b200.parallel import ExpertParallelMoE
-        ep = ExpertParallelMoE(eng)
-        lo, hi = rank * M // world, (rank + 1) * M // world
-        x_local = x[lo:hi].contiguous()            # token shard of this rank (same global x on every rank: seed 42)
-
-    def step():
-        out = None
-        for l in range(args.layers):
-            if world > 1 and args.ep_mode == "a2a":
-                out = ep.forward(l, x_local)       # route -> all-to-all dispatch -> experts -> all-to-all -> combine
-            elif world > 1:
-                # reference semantics (model.py:3086-3211) on NVLink: tokens replicated, partial sums all-reduced
-                ids, w = eng.compute_routing(l, x)
-                out = eng.moe_forward(l, x, ids, w, routed_only=True)
-                dist.all_reduce(out)
-            else:
-                ids, w = eng.compute_routing(l, x)
-                out = eng.moe_forward(l, x, ids, w)
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    eng.profile(True)
-    l0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - l0
-    prof = eng.profile_collect()
-    eng.profile(False)
-    clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = M / (ms_per_step * 1e-3)
-
-    # end-to-end through the C-ABI host entry point (single GPU engine semantics; EP ranks each copy in)
-    e2e = None
-    if world == 1:
-        for _ in range(2):
-            eng.prefill_moe_stack_host(x_host, out_host)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            eng.prefill_moe_stack_host(x_host, out_host)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.steps
-        nbytes = M * cfg["hidden_size"] * 2
-        e2e = {"value": M / dt, "unit": "tokens/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": dt * 1e3, "entry": "kb2_prefill_moe_stack_host (pinned host hidden state in, last-layer output out)"}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    pk = peaks()
-    k, H, I = cfg["num_experts_per_tok"], cfg["hidden_size"], cfg["moe_intermediate_size"]
-    g1_ms, g1_n = prof["gemm1_gate_up_silu"]
-    flops_per_launch = 2.0 * M * k * H * (2 * I) / world          # routed slots are split over EP ranks on average
-    achieved = flops_per_launch / (g1_ms / max(1, g1_n) * 1e-3) / 1e12 if g1_n else None
-    roofline = {"kernel": "grouped_gemm_kernel<INT4, gate/up + SiLU*mul>", "bound": "tensor",
-                "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": (achieved / pk["tf_sustained"]) if achieved else None, "traffic": None,
-                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
-                "algorithmic": f"2*M*k*H*2I = {flops_per_launch:.3e} FLOP per launch",
-                "avg_launch_ms": g1_ms / max(1, g1_n),
-                "kernel_share_ms_per_step": {kk: v[0] / args.steps for kk, v in prof.items()}}
-    cpu_b = None
-    if not args.no_cpu_baseline:
-        cpu_b, _, _ = cpu_sample(budget_s=args.cpu_budget)
-    line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "int4 weights x bf16 activations, fp32 accumulate (tcgen05)",
-            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
+            "data": "synthetic", "config": workload_config(args, cfg, world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_b}
     print(json.dumps(line))
     if world > 1:
@@ -453,21 +420,18 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layers", type=int, default=QCN["num_moe_layers"])
-    ap.add_argument("--tokens", type=int, default=TOKENS)
+    ap.add_argument("--config", default="qcn", choices=["qcn", "qwen35", "v2lite", "q235b"],
+                    help="BASELINE configuration: qcn (default, the one the metric is quoted on), qwen35, v2lite, q235b")
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (profiling runs)")
+    ap.add_argument("--tokens", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="full", choices=["full", "moe_stack"],
-                    help="full = whole Qwen3-Coder-Next prefill (default); moe_stack = the 48 MoE blocks only")
-    ap.add_argument("--ep-mode", default="replicate", choices=["a2a", "replicate"],
-                    help="N>1: replicate = tokens on every rank, partial sums all-reduced over NVLink (default; moves ~k x fewer bytes at top-10); a2a = all-to-all dispatch of routed rows")
     args = ap.parse_args()
+    args.tokens = args.tokens or DEFAULT_TOKENS[args.config]
     if args.impl == "reference":
         run_reference_arm(args)
-    elif args.workload == "full":
-        run_full_model(args)
     else:
-        run_ours(args)
+        run_full_model(args)
 
 
 if __name__ == "__main__":

@@ -156,6 +156,11 @@ KB2_API int kb2_moe_forward_rows(kb2_engine* e, int moe_layer_idx, const void* r
 KB2_API int kb2_ep_combine_rows(kb2_engine* e, const void* rows_sorted_dev, const int32_t* slot_of_dev, int32_t num_tokens,
                                 int32_t routed_only, const void* shared_dev, void* out_dev, void* stream);
 
+/* The tail of GpuPrefillManager.forward applied to an already reduced routed sum (EP: after the reduce-scatter of the
+ * partial sums): out = bf16(rsf * routed) (+ shared_dev) — python/krasis/gpu_prefill.py:4467-4482.  out may alias routed. */
+KB2_API int kb2_finish_routed(kb2_engine* e, const void* routed_dev, const void* shared_dev, void* out_dev, int32_t num_tokens,
+                              void* stream);
+
 /* Host-buffer variant of route + forward for callers that hold activations in (pinned) host memory —
  * the shape of KrasisEngine.submit_forward/sync_forward (src/moe.rs:2722,2809: bytes in, bytes out).
  * If topk_ids_host is NULL the engine routes with its own router weights.  Copies H2D, computes,
@@ -305,6 +310,26 @@ KB2_API int kb2_mla_forward(kb2_mla* h, int layer, const void* hidden_dev, const
                             void* ckv_cache_layer_dev, void* kpe_cache_layer_dev, const int32_t* kv_indices_dev,
                             int32_t kv_len_after, void* out_dev, int32_t num_tokens, void* stream);
 
+/* ================================================================================================
+ * Multi-GPU: the expert-parallel communicator.  One process per GPU; replaces the reference's replicated-token EP loop
+ * with a pinned-host bounce and a GPU0 reduction (python/krasis/model.py:3086-3211, KrasisEngine.reduce_sum_bf16
+ * src/moe.rs:2505) by NCCL collectives over NVLink owned by THIS library (bound with dlopen at first use: no link-time
+ * dependency).  The host moves only the 128-byte unique id between its processes.  Token-sharded schedule of one layer:
+ *   norm (M/R rows) -> kb2_comm_all_gather -> head-parallel attention -> kb2_comm_reduce_scatter_bf16 -> add+norm, router,
+ *   shared expert (M/R rows) -> kb2_comm_all_gather (rows, ids, weights) -> kb2_moe_forward(routed_only) on the local
+ *   expert slice -> kb2_comm_reduce_scatter_bf16 -> rsf * routed + shared.
+ * ================================================================================================ */
+typedef struct kb2_comm kb2_comm;
+KB2_API int kb2_comm_unique_id(void* out128);                                   /* rank 0: ncclGetUniqueId */
+KB2_API int kb2_comm_init(const void* unique_id128, int32_t rank, int32_t num_ranks, int32_t device, kb2_comm** out);
+KB2_API void kb2_comm_destroy(kb2_comm* c);
+/* recv [R][bytes_per_rank] <- every rank's send [bytes_per_rank]; stream-ordered */
+KB2_API int kb2_comm_all_gather(kb2_comm* c, const void* send_dev, void* recv_dev, size_t bytes_per_rank, void* stream);
+/* recv [elems_per_rank] = sum over ranks of send[rank_slice]; send holds R * elems_per_rank BF16 */
+KB2_API int kb2_comm_reduce_scatter_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems_per_rank, void* stream);
+KB2_API int kb2_comm_all_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems, void* stream);
+KB2_API int kb2_comm_broadcast(kb2_comm* c, void* buf_dev, size_t bytes, int32_t root, void* stream);
+
 /* Per-kernel device timing with CUDA events recorded on the launching stream (the reference's
  * KRASIS_LAYER_TIMING / EP breakdown, python/krasis/model.py:2839-2860).  kb2_profile_collect synchronises the
  * device and returns, per kernel class, the summed milliseconds and the number of launches since enable. */
@@ -317,6 +342,15 @@ KB2_API int kb2_mla_forward(kb2_mla* h, int layer, const void* hidden_dev, const
 #define KB2_PROF_NUM 6
 KB2_API int kb2_profile_enable(kb2_engine* e, int on);
 KB2_API int kb2_profile_collect(kb2_engine* e, double* total_ms, int64_t* n_spans);
+
+/* Process-wide kernel accounting: every kernel this library launches is counted (kb2_total_launches) and, while
+ * kb2_kernel_profile_enable(1) is in effect, timed with CUDA events on its launching stream.  kb2_kernel_profile_collect
+ * synchronises the device and fills total_ms[k] / n_spans[k] for k < kb2_kernel_profile_num(), then clears the record. */
+KB2_API int64_t kb2_total_launches(void);
+KB2_API int kb2_kernel_profile_num(void);
+KB2_API const char* kb2_kernel_profile_name(int id);
+KB2_API int kb2_kernel_profile_enable(int on);
+KB2_API int kb2_kernel_profile_collect(double* total_ms, int64_t* n_spans);
 
 #ifdef __cplusplus
 }

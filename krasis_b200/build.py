@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libkrasis_b200.so")
-SOURCES = ["grouped_gemm.cu", "router_gemm.cu", "dense_gemm.cu", "gdn.cu", "gqa.cu", "elementwise.cu", "moe_kernels.cu", "capi.cu", "capi_attn.cu"]
+SOURCES = ["grouped_gemm.cu", "router_gemm.cu", "dense_gemm.cu", "gdn.cu", "gdn_tc.cu", "gqa.cu", "elementwise.cu", "moe_kernels.cu", "capi.cu", "capi_attn.cu", "capi_comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(obj + ".ptxas.txt", "w") as f:
             f.write(r.stderr)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

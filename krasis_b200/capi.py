@@ -68,6 +68,7 @@ SIGNATURES = {
     "kb2_moe_forward_rows": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
     "kb2_ep_combine_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
+    "kb2_finish_routed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "kb2_moe_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_void_p]),
     "kb2_prefill_moe_stack_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -97,6 +98,18 @@ SIGNATURES = {
     "kb2_mla_set_weights_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9),
     "kb2_mla_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "kb2_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "kb2_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "kb2_comm_destroy": (None, [C.c_void_p]),
+    "kb2_comm_all_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kb2_comm_reduce_scatter_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kb2_comm_all_reduce_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kb2_comm_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
+    "kb2_total_launches": (C.c_int64, []),
+    "kb2_kernel_profile_num": (C.c_int, []),
+    "kb2_kernel_profile_name": (C.c_char_p, [C.c_int]),
+    "kb2_kernel_profile_enable": (C.c_int, [C.c_int]),
+    "kb2_kernel_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "kb2_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "kb2_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
@@ -119,6 +132,23 @@ def load():
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib
+
+
+def kernel_profile(on: bool):
+    check(load().kb2_kernel_profile_enable(int(bool(on))))
+
+
+def kernel_profile_collect():
+    """{kernel class: (total_ms, launches)} of every kernel timed since kernel_profile(True); synchronises the device."""
+    lib = load()
+    n = lib.kb2_kernel_profile_num()
+    ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+    check(lib.kb2_kernel_profile_collect(ms, cnt))
+    return {lib.kb2_kernel_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
+
+
+def total_launches() -> int:
+    return int(load().kb2_total_launches())
 
 
 class Kb2Error(RuntimeError):

@@ -10,6 +10,9 @@
 
 #include "../../include/krasis_b200.h"
 #include "moe_common.cuh"
+#include "prof.cuh"
+#include <atomic>
+#include <mutex>
 
 namespace kb2 {
 cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, const void* tmap_b, int num_sms,
@@ -36,6 +39,40 @@ cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* d
 }  // namespace kb2
 
 using namespace kb2;
+
+// ---- process-wide kernel accounting (prof.cuh) --------------------------------------------------------------------------
+namespace {
+std::atomic<long long> g_launches{0};
+std::atomic<bool> g_kprof_on{false};
+std::mutex g_kprof_mu;
+std::vector<cudaEvent_t> g_kev;                                   // event pool, reused across collects
+size_t g_kev_used = 0;
+std::vector<std::pair<int, int>> g_kspans[K_NUM];                 // (begin, end) event indices per kernel class
+const char* const kKernelNames[K_NUM] = {
+    "router_gemm", "router_topk", "binning(count+scan+scatter)", "grouped_gemm<gate_up+silu_mul>", "grouped_gemm<down>", "combine",
+    "dense_gemm<bf16>", "dense_gemm<int8>", "gdn_prep(conv+l2norm+gates)", "gdn_conv_state", "gdn_chunk_prepare", "gdn_chunk_scan",
+    "gdn_post(gated_rmsnorm)", "gqa_prep(norm+rope+fp8_append)", "kv_gather(fp8->bf16)", "fmha", "mla_prep", "rmsnorm", "quant_rows_int8",
+    "silu_and_mul", "sigmoid_gate_mul", "add_bf16", "quantize_group", "retile"};
+}  // namespace
+
+namespace kb2 {
+void kernel_span_begin(int id, cudaStream_t s, int n_launches, int* slot) {
+  g_launches.fetch_add(n_launches, std::memory_order_relaxed);
+  *slot = -1;
+  if (!g_kprof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_kprof_mu);
+  if (g_kev_used + 2 > g_kev.size())
+    for (int i = 0; i < 512; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); g_kev.push_back(ev); }
+  *slot = (int)g_kev_used;
+  g_kev_used += 2;
+  cudaEventRecord(g_kev[*slot], s);
+}
+void kernel_span_end(int id, cudaStream_t s, int slot) {
+  std::lock_guard<std::mutex> lk(g_kprof_mu);
+  cudaEventRecord(g_kev[slot + 1], s);
+  g_kspans[id].push_back({slot, slot + 1});
+}
+}  // namespace kb2
 
 static thread_local std::string g_err;
 
@@ -530,6 +567,19 @@ KB2_API int kb2_ep_combine_rows(kb2_engine* e, const void* rows_sorted, const in
   return KB2_OK;
 }
 
+KB2_API int kb2_finish_routed(kb2_engine* e, const void* routed, const void* shared, void* out, int32_t M, void* stream) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (M == 0) return KB2_OK;
+  if (!routed || !out) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfSpan ps(e, KB2_PROF_COMBINE, s);
+  CUDA_TRY(launch_combine(routed, nullptr, M, e->cfg.hidden_size, 1, e->cfg.routed_scaling_factor, 1, shared, out, s));
+  e->launches += 1;
+  return KB2_OK;
+}
+
 KB2_API int kb2_moe_forward_host(kb2_engine* e, int layer, const void* x_host, const int32_t* ids_host, const float* w_host,
                          void* out_host, int32_t M, int32_t routed_only, void* stream) {
   if (int r = check_layer(e, layer)) return r;
@@ -578,6 +628,34 @@ KB2_API int kb2_last_expert_counts(kb2_engine* e, int32_t* counts_host, void* st
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   CUDA_TRY(cudaMemcpyAsync(counts_host, e->counts, sizeof(int) * e->e_local, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int64_t kb2_total_launches(void) { return (int64_t)g_launches.load(); }
+KB2_API int kb2_kernel_profile_num(void) { return K_NUM; }
+KB2_API const char* kb2_kernel_profile_name(int id) { return id >= 0 && id < K_NUM ? kKernelNames[id] : ""; }
+KB2_API int kb2_kernel_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_kprof_mu);
+  g_kprof_on.store(on != 0);
+  g_kev_used = 0;
+  for (auto& v : g_kspans) v.clear();
+  return KB2_OK;
+}
+KB2_API int kb2_kernel_profile_collect(double* total_ms, int64_t* n_spans) {
+  if (!total_ms || !n_spans) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_kprof_mu);
+  for (int k = 0; k < K_NUM; ++k) {
+    double t = 0;
+    for (auto& sp : g_kspans[k]) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, g_kev[sp.first], g_kev[sp.second]) == cudaSuccess) t += ms;
+    }
+    total_ms[k] = t;
+    n_spans[k] = (int64_t)g_kspans[k].size();
+    g_kspans[k].clear();
+  }
+  g_kev_used = 0;
   return KB2_OK;
 }
 

@@ -192,7 +192,7 @@ KB2_API int kb2_gdn_create(const kb2_gdn_config* c, kb2_gdn** out) {
   ALLOC(h->normed, M * vd * 2);
   ALLOC(h->beta, M * nv * 4);
   ALLOC(h->g, M * nv * 4);
-  ALLOC(h->vcorr, nv * nch * 64 * c->v_head_dim * 4);
+  ALLOC(h->vcorr, nv * nch * 64 * c->v_head_dim * 4 * 9 / 8);   // tcgen05 scan: rows padded 32 -> 36 floats per dv slice
   ALLOC(h->kcd, nv * nch * 64 * c->k_head_dim * 4);
   ALLOC(h->intra, nv * nch * 64 * 64 * 4);
   ALLOC(h->gcum, nv * nch * 64 * 4);

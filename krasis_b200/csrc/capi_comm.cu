@@ -1,0 +1,142 @@
+// C-ABI for the expert-parallel communicator (include/krasis_b200.h, "multi-GPU" section).
+//
+// The reference's EP exchange is Python: every GPU gets all tokens through a pinned-host bounce and GPU0 adds the partial
+// sums (python/krasis/model.py:3086-3211, KrasisEngine.reduce_sum_bf16 src/moe.rs:2505).  Here one process drives one GPU
+// and the exchange is NCCL over NVLink, owned by this library so a Rust / C host needs no torch: the host only moves the
+// 128-byte NCCL unique id between its processes (any side channel), everything else is behind these calls.
+// NCCL is bound at run time (dlopen of libnccl.so.2 — the copy already loaded by the host process if there is one), so the
+// library itself has no link-time dependency and single-GPU users never touch it.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+
+#include <cuda_runtime.h>
+
+#include "../../include/krasis_b200.h"
+
+extern "C" int kb2_set_error_(int code, const char* msg);   // capi.cu
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+enum { kNcclUint8 = 1, kNcclBfloat16 = 9 };
+enum { kNcclSum = 0 };
+
+struct NcclApi {
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the host's copy (e.g. torch's bundled NCCL) if loaded
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+#define KB2_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
+    KB2_SYM(GetUniqueId, "ncclGetUniqueId");
+    KB2_SYM(CommInitRank, "ncclCommInitRank");
+    KB2_SYM(CommDestroy, "ncclCommDestroy");
+    KB2_SYM(AllGather, "ncclAllGather");
+    KB2_SYM(ReduceScatter, "ncclReduceScatter");
+    KB2_SYM(AllReduce, "ncclAllReduce");
+    KB2_SYM(Broadcast, "ncclBroadcast");
+    KB2_SYM(GetErrorString, "ncclGetErrorString");
+#undef KB2_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.ReduceScatter && api.AllReduce &&
+             api.Broadcast && api.GetErrorString;
+  });
+  return api;
+}
+
+int failf(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return kb2_set_error_(code, buf);
+}
+
+}  // namespace
+
+struct kb2_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1, device = 0;
+};
+
+#define NCCL_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    int _r = (expr);                                                                                     \
+    if (_r != 0) return failf(KB2_ERR_CUDA, "%s: %s", #expr, nccl().GetErrorString(_r));                  \
+  } while (0)
+
+extern "C" {
+
+KB2_API int kb2_comm_unique_id(void* out128) {
+  if (!out128) return failf(KB2_ERR_VALUE, "null argument");
+  if (!nccl().ok) return failf(KB2_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+  NcclUniqueId id;
+  NCCL_TRY(nccl().GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  return KB2_OK;
+}
+
+KB2_API int kb2_comm_init(const void* unique_id128, int32_t rank, int32_t num_ranks, int32_t device, kb2_comm** out) {
+  if (!unique_id128 || !out) return failf(KB2_ERR_VALUE, "null argument");
+  if (num_ranks < 1 || rank < 0 || rank >= num_ranks) return failf(KB2_ERR_VALUE, "bad rank %d/%d", rank, num_ranks);
+  if (!nccl().ok) return failf(KB2_ERR_STATE, "NCCL (libnccl.so.2) could not be loaded");
+  if (cudaSetDevice(device) != cudaSuccess) return failf(KB2_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  NcclUniqueId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  kb2_comm* c = new kb2_comm();
+  c->rank = rank; c->nranks = num_ranks; c->device = device;
+  int r = nccl().CommInitRank(&c->comm, num_ranks, id, rank);
+  if (r != 0) { delete c; return failf(KB2_ERR_CUDA, "ncclCommInitRank: %s", nccl().GetErrorString(r)); }
+  *out = c;
+  return KB2_OK;
+}
+
+KB2_API void kb2_comm_destroy(kb2_comm* c) {
+  if (!c) return;
+  if (c->comm) nccl().CommDestroy(c->comm);
+  delete c;
+}
+
+KB2_API int kb2_comm_all_gather(kb2_comm* c, const void* send_dev, void* recv_dev, size_t bytes_per_rank, void* stream) {
+  if (!c || !send_dev || !recv_dev) return failf(KB2_ERR_VALUE, "null argument");
+  NCCL_TRY(nccl().AllGather(send_dev, recv_dev, bytes_per_rank, kNcclUint8, c->comm, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_comm_reduce_scatter_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems_per_rank, void* stream) {
+  if (!c || !send_dev || !recv_dev) return failf(KB2_ERR_VALUE, "null argument");
+  NCCL_TRY(nccl().ReduceScatter(send_dev, recv_dev, elems_per_rank, kNcclBfloat16, kNcclSum, c->comm, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_comm_all_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems, void* stream) {
+  if (!c || !send_dev || !recv_dev) return failf(KB2_ERR_VALUE, "null argument");
+  NCCL_TRY(nccl().AllReduce(send_dev, recv_dev, elems, kNcclBfloat16, kNcclSum, c->comm, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_comm_broadcast(kb2_comm* c, void* buf_dev, size_t bytes, int32_t root, void* stream) {
+  if (!c || !buf_dev) return failf(KB2_ERR_VALUE, "null argument");
+  NCCL_TRY(nccl().Broadcast(buf_dev, buf_dev, bytes, kNcclUint8, root, c->comm, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+}  // extern "C"

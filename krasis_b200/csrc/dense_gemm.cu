@@ -9,6 +9,7 @@
 #include <cuda.h>
 
 #include "moe_common.cuh"
+#include "prof.cuh"
 #include "ptx.cuh"
 
 namespace kb2 {
@@ -189,6 +190,7 @@ static cudaError_t dense_configure() {
 // X [M][K] bf16 row-major, W [N][K] bf16 row-major, out [M][ldo] (bf16 or f32).  K % 64 == 0, N % 16 == 0.
 cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
                               long long ldo, bool out_f32, int num_sms, cudaStream_t s) {
+  KernelSpan ks(K_DENSE_BF16, s);
   if (K % kBlockK || N % 16 || M <= 0) return cudaErrorInvalidValue;
   alignas(64) CUtensorMap tx, tw;
   cudaError_t e = make_tmap_bf16_rows(&tx, x, M, K, 128);
@@ -209,6 +211,7 @@ cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const flo
 // W8A8: xq [M][K] int8, x_scale [M] f32, wq [N][K] int8, w_scale [N] bf16 -> out [M][ldo] bf16.  K % 128 == 0, N % 16 == 0.
 cudaError_t launch_dense_gemm_i8(const void* xq, const float* x_scale, const void* wq, const void* w_scale, void* out,
                                  int M, int N, int K, long long ldo, int num_sms, cudaStream_t s) {
+  KernelSpan ks(K_DENSE_I8, s);
   if (K % 128 || N % 16 || M <= 0) return cudaErrorInvalidValue;
   alignas(64) CUtensorMap tx, tw;
   cudaError_t e = make_tmap_u8_rows(&tx, xq, M, K, 128);

@@ -7,6 +7,7 @@
 //   silu_and_mul                  flashinfer.activation.silu_and_mul (layer.py:512): bf16(silu(x[:N]) * x[N:]) in fp32
 //   sigmoid_gate_mul              layer.py:518-522: out *= sigmoid(F.linear(hidden, w[1,H])) with BF16 rounding at every tensor op
 #include "moe_common.cuh"
+#include "prof.cuh"
 
 namespace kb2 {
 
@@ -225,6 +226,7 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
   reinterpret_cast<uint4*>(out)[i] = o;
 }
 cudaError_t launch_add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t s) {
+  KernelSpan ks(K_ADD, s);
   if (n % 8 || n <= 0) return cudaErrorInvalidValue;
   add_bf16_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
                                                                  (__nv_bfloat16*)out, n / 8);
@@ -232,6 +234,7 @@ cudaError_t launch_add_bf16(const void* a, const void* b, void* out, long long n
 }
 
 cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, int M, int H, float eps, cudaStream_t s) {
+  KernelSpan ks(K_RMSNORM, s);
   if (H % 8 || M <= 0) return cudaErrorInvalidValue;
   if (H == 2048) {
     if (residual)
@@ -247,18 +250,21 @@ cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, i
   return cudaGetLastError();
 }
 cudaError_t launch_quant_rows_int8(const void* x, void* q, float* scale_f32, void* scale_bf16, int rows, int K, cudaStream_t s) {
+  KernelSpan ks(K_QUANT_ROWS, s);
   if (rows <= 0 || K % 8) return cudaErrorInvalidValue;
   quant_rows_int8_kernel<<<(rows + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)x, (int8_t*)q, scale_f32, (__nv_bfloat16*)scale_bf16,
                                                         rows, K);
   return cudaGetLastError();
 }
 cudaError_t launch_silu_and_mul(const void* x, void* out, int rows, int N, cudaStream_t s) {
+  KernelSpan ks(K_SILU_MUL, s);
   if (N % 8 || rows <= 0) return cudaErrorInvalidValue;
   const long long total = (long long)rows * (N / 8);
   silu_and_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, N);
   return cudaGetLastError();
 }
 cudaError_t launch_sigmoid_gate_mul(const void* h, const void* w, void* y, int M, int H, int N, cudaStream_t s) {
+  KernelSpan ks(K_SIGMOID_GATE, s);
   if (M <= 0 || H % 8 || N % 8) return cudaErrorInvalidValue;
   sigmoid_gate_mul_kernel<<<(M + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, M, H, N);
   return cudaGetLastError();

@@ -11,7 +11,10 @@
 //   gdn_chunk_scan         sequential pass over chunks per (head, 32-wide slice of dv): the _chunk_step recurrence (:43-60)
 //   gdn_post_kernel        gated RMSNorm (:987-1004)
 // The in/out projections are dense_gemm_kernel (tcgen05).  All delta-rule math is fp32 like the reference.
+#include <cstdlib>
+
 #include "moe_common.cuh"
+#include "prof.cuh"
 #include "ptx.cuh"
 
 namespace kb2 {
@@ -273,6 +276,22 @@ __device__ __forceinline__ void warp_mma_tiles(float (&c)[NT][4], const TA* __re
 // ------------------------------------------------------------------------------------------------
 constexpr int kLdA = kGC + 4;   // [row][k] fp32 operands: row stride = 4 mod 32 words -> conflict-free A fragments
 
+// TC = true (dk == dv == 128): outputs in the operand layouts of gdn_scan_tc_kernel (gdn_tc.cu):
+//   vcorr  [hc][dv/32][64][36] fp32 (one padded 9 KB slice per scan CTA)
+//   kcd    [hc][hi c0 | hi c1 | lo c0 | lo c1] BF16 hi/lo pair, each an 8 KB K-major 128B-swizzled UMMA image (64 rows x 64 k)
+//   intra  [hc][hi | lo] same image format (64 x 64)
+__device__ __forceinline__ uint32_t prep_sw128_off(int row, int k) {       // element (row, k) of a 64-row K-major SW128 image pair
+  const int kk = k & 63;
+  return (uint32_t)((k >> 6) * 8192 + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1)));
+}
+__device__ __forceinline__ void prep_split_bf16(float x, unsigned short& hi, unsigned short& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = *reinterpret_cast<const unsigned short*>(&h);
+  lo = *reinterpret_cast<const unsigned short*>(&l);
+}
+
+template <bool TC>
 __global__ void __launch_bounds__(256, 2) gdn_chunk_prepare_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qn,
                                                                    const __nv_bfloat16* __restrict__ kn,
                                                                    const __nv_bfloat16* __restrict__ vc,
@@ -344,6 +363,14 @@ __global__ void __launch_bounds__(256, 2) gdn_chunk_prepare_kernel(GdnDims d, co
           const float bi = sb[i];
           *reinterpret_cast<float2*>(sA + i * kLdA + j) =
               make_float2(j < i ? -(a0 * bi) * d0 : 0.f, j + 1 < i ? -(a1 * bi) * d1 : 0.f);
+        } else if (TC) {
+          unsigned short h0, l0, h1, l1;
+          prep_split_bf16(j <= i ? a0 * d0 : 0.f, h0, l0);
+          prep_split_bf16(j + 1 <= i ? a1 * d1 : 0.f, h1, l1);
+          unsigned char* img = reinterpret_cast<unsigned char*>(intra) + hc * 16384;
+          const uint32_t off = prep_sw128_off(i, j);
+          *reinterpret_cast<uint32_t*>(img + off) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          *reinterpret_cast<uint32_t*>(img + 8192 + off) = (uint32_t)l0 | ((uint32_t)l1 << 16);
         } else {
           *reinterpret_cast<float2*>(o_intra + i * kGC + j) = make_float2(j <= i ? a0 * d0 : 0.f, j + 1 <= i ? a1 * d1 : 0.f);
         }
@@ -434,6 +461,20 @@ __global__ void __launch_bounds__(256, 2) gdn_chunk_prepare_kernel(GdnDims d, co
     for (int idx = tid; idx < kGC * cpr; idx += 256) {
       const int i = idx / cpr, c = (idx % cpr) * 4;
       const float4 v = *reinterpret_cast<const float4*>(sB + i * ldb + c);
+      if (TC) {
+        if (c < dv) {
+          *reinterpret_cast<float4*>(vcorr + ((hc * (dv / 32) + (c >> 5)) * kGC + i) * 36 + (c & 31)) = v;
+        } else {
+          unsigned short h[4], l[4];
+          prep_split_bf16(v.x, h[0], l[0]); prep_split_bf16(v.y, h[1], l[1]);
+          prep_split_bf16(v.z, h[2], l[2]); prep_split_bf16(v.w, h[3], l[3]);
+          unsigned char* img = reinterpret_cast<unsigned char*>(kcd) + hc * 32768;
+          const uint32_t off = prep_sw128_off(i, c - dv);
+          *reinterpret_cast<uint2*>(img + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+          *reinterpret_cast<uint2*>(img + 16384 + off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+        }
+        continue;
+      }
       if (c < dv) *reinterpret_cast<float4*>(vcorr + hc * kGC * dv + i * dv + c) = v;
       else *reinterpret_cast<float4*>(kcd + hc * kGC * dk + i * dk + (c - dv)) = v;
     }
@@ -698,6 +739,16 @@ size_t gdn_scan_smem(const GdnDims& d) {   // same for every slice width
   return sizeof(float) * (d.dk * kLdS + kGC * kLdS) + 2 * (size_t)scan_stage(d.dk).bytes;
 }
 
+cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_img, const void* intra_img, const float* vcorr,
+                               const float* gcum, float* state, void* core_out, int M, int n_chunks, int nk, int nv,
+                               cudaStream_t s);
+
+// KB2_GDN_LEGACY=1 keeps the mma.sync scan for dk == dv == 128 too (A/B comparison in tests; never set in production)
+static bool gdn_use_tc(const GdnDims& d) {
+  const char* e = getenv("KB2_GDN_LEGACY");            // read per call so one test process can run both paths
+  return !(e && e[0] == '1') && d.dk == 128 && d.dv == 128;
+}
+
 cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, const void* conv_w, void* conv_state,
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
                             void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
@@ -707,13 +758,15 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
   const int n_chunks = (M + kGC - 1) / kGC;
   static PerDeviceOnce once;
   if (const int dev = once.pending(); dev >= 0) {
-    cudaFuncSetAttribute(gdn_chunk_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_prepare_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaFuncSetAttribute(gdn_chunk_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     cudaFuncSetAttribute(gdn_chunk_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gdn_chunk_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gdn_chunk_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     once.mark(dev);
   }
+  { KernelSpan ks(K_GDN_PREP, s);
   if (d.dk == 128 && d.dv == 128 && d.K == 4) {
     const int n_tiles = (M + 31) / 32;
     const long long warps = (long long)n_tiles * (2 * d.nk + d.nv + 1);
@@ -726,20 +779,37 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
                                                       (const __nv_bfloat16*)conv_w, (const __nv_bfloat16*)conv_state, A_log,
                                                       dt_bias, (__nv_bfloat16*)qn, (__nv_bfloat16*)kn, (__nv_bfloat16*)vc,
                                                       beta, g, M);
+  } }
+  { KernelSpan ks(K_GDN_CONV_STATE, s);
+  gdn_conv_state_kernel<<<(C + 255) / 256, 256, 0, s>>>(d, (const __nv_bfloat16*)qkvz, (__nv_bfloat16*)conv_state, M); }
+  const long long nw = (long long)M * d.nv;
+  if (gdn_use_tc(d)) {
+    { KernelSpan ks(K_GDN_PREPARE, s);
+    gdn_chunk_prepare_kernel<true><<<dim3(n_chunks, d.nv), 256, gdn_prepare_smem(d), s>>>(
+        d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, (const __nv_bfloat16*)vc, beta, g, M, n_chunks, vcorr, kcd,
+        intra, gcum); }
+    { KernelSpan ks(K_GDN_SCAN, s);
+    cudaError_t e = launch_gdn_scan_tc(qn, kn, kcd, intra, vcorr, gcum, rec_state, core, M, n_chunks, d.nk, d.nv, s);
+    if (e != cudaSuccess) return e; }
+    KernelSpan ks(K_GDN_POST, s);
+    gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, (const __nv_bfloat16*)core, (const __nv_bfloat16*)qkvz, norm_w, M,
+                                                                    (__nv_bfloat16*)normed_out);
+    return cudaGetLastError();
   }
-  gdn_conv_state_kernel<<<(C + 255) / 256, 256, 0, s>>>(d, (const __nv_bfloat16*)qkvz, (__nv_bfloat16*)conv_state, M);
-  gdn_chunk_prepare_kernel<<<dim3(n_chunks, d.nv), 256, gdn_prepare_smem(d), s>>>(
+  { KernelSpan ks(K_GDN_PREPARE, s);
+  gdn_chunk_prepare_kernel<false><<<dim3(n_chunks, d.nv), 256, gdn_prepare_smem(d), s>>>(
       d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, (const __nv_bfloat16*)vc, beta, g, M, n_chunks, vcorr, kcd,
-      intra, gcum);
+      intra, gcum); }
   // slice width: keep >= ~128 CTAs in flight (one per SM) when a rank holds only a few heads
   const int sv = d.nv * (d.dv / 32) >= 96 ? 32 : (d.nv * (d.dv / 16) >= 96 ? 16 : 8);
 #define KB2_SCAN(SV)                                                                                                  \
   gdn_chunk_scan_kernel<SV><<<dim3(d.nv, d.dv / SV), 256, gdn_scan_smem(d), s>>>(                                      \
       d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, vcorr, kcd, intra, gcum, M, n_chunks, rec_state,       \
       (__nv_bfloat16*)core)
-  if (sv == 32) KB2_SCAN(32); else if (sv == 16) KB2_SCAN(16); else KB2_SCAN(8);
+  { KernelSpan ks(K_GDN_SCAN, s);
+  if (sv == 32) KB2_SCAN(32); else if (sv == 16) KB2_SCAN(16); else KB2_SCAN(8); }
 #undef KB2_SCAN
-  const long long nw = (long long)M * d.nv;
+  KernelSpan ks(K_GDN_POST, s);
   gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, (const __nv_bfloat16*)core, (const __nv_bfloat16*)qkvz, norm_w, M,
                                                                   (__nv_bfloat16*)normed_out);
   return cudaGetLastError();

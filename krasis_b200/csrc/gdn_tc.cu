@@ -1,0 +1,391 @@
+// Gated DeltaNet chunk scan on tcgen05 (dk == dv == 128): the sequential pass of python/krasis/linear_attention.py:43-60
+// (_chunk_step) over the chunks of one (value head, 32-wide dv slice) per CTA.
+//
+//   per chunk c (64 tokens):   VP  = kcd_c  S_c                       (64 x 32)      \  one M=128 tile: rows 0-63 = kcd, rows
+//                              IT  = q_c    S_c                       (64 x 32)      /  64-127 = q          [G1]
+//                              v   = vcorr_c - VP                                       CUDA cores
+//                              dS  = k_c^T (v . e^{g_last - gcum_j})  (128 x 32)      [G2]
+//                              O2  = intra_c v                        (64 x 32)       [G3]
+//                              S_{c+1} = e^{g_last} S_c + dS                            CUDA cores (S row per thread, fp32 registers)
+//                              out = e^{gcum_i} IT + O2  -> BF16
+//
+// All contractions run as tcgen05.mma kind::f16 (BF16 inputs, fp32 accumulation in TMEM).  fp32 operands (kcd, intra, S, v)
+// are carried as a BF16 pair hi + lo (hi = bf16(x), lo = bf16(x - hi), |x - hi - lo| <= 2^-17 |x|) and every product is the
+// three-term sum hi*hi + hi*lo + lo*hi, which keeps the recurrence at fp32-grade accuracy like the reference (it runs these
+// matmuls in fp32, linear_attention.py:776-779); q and k hold BF16 values and are exact single operands.
+//
+// Operand staging: q, k tiles by 2-D TMA (128 B swizzle) straight from the prep kernel's outputs (k is consumed MN-major as the
+// A operand of G2, so no transposed copy exists); kcd / intra arrive as ready-made 128B-swizzled K-major images written by
+// gdn_chunk_prepare_kernel<true> and move with 1-D bulk copies; S and v B-operands are written by the CUDA cores in the same
+// swizzled K-major layout.  64-row A operands are issued as M=128 MMAs whose rows 64-127 read whatever follows in shared
+// memory: those rows only produce accumulator lanes 64-127 of a column range nobody reads.
+//
+// Warps 0-3: CUDA-core work, one thread per TMEM lane; warp 4: TMA producer; warp 5: MMA issuer.  2-stage operand ring.
+#include <cuda.h>
+
+#include "moe_common.cuh"
+#include "ptx.cuh"
+
+namespace kb2 {
+
+cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows, long long cols, int box_rows);
+
+constexpr int kTC = 64;            // chunk length (linear_attention.py:702)
+constexpr int kTSV = 32;           // dv slice per CTA
+constexpr int kTD = 128;           // dk == dv
+constexpr int kTThreads = 192;
+constexpr int kVcLd = 36;          // padded row of the vcorr slice (floats): conflict-free float4 rows
+
+// per-stage byte offsets
+constexpr int kOffA1 = 0;                  // [kcd_hi c0 8K][q c0 8K][kcd_hi c1 8K][q c1 8K]
+constexpr int kOffA1L = 32768;             // [kcd_lo c0 8K][kcd_lo c1 8K]   (rows 64-127 of the M=128 reads run into A3: ignored lanes)
+constexpr int kOffA3 = 49152;              // [intra_hi 8K][intra_lo 8K]     a true 128-row tile: lanes 0-63 = hi part, 64-127 = lo part
+constexpr int kOffA2 = 65536;              // k tile, MN-major: [dk 0-63: 64 tokens x 128 B][dk 64-127]
+constexpr int kOffVC = 81920;              // vcorr slice fp32 [64][36]
+constexpr int kOffG = kOffVC + kTC * kVcLd * 4;   // gcum fp32 [64]
+constexpr int kStageBytes = 92160;         // 90 KB (1 KB multiple: every tile base stays 1024-aligned)
+static_assert(kOffG + kTC * 4 <= kStageBytes, "stage layout");
+constexpr int kTxBytes = 16384 * 5 + kTC * kVcLd * 4 + kTC * 4;
+// static region
+constexpr int kOffSH = 2 * kStageBytes;    // S hi: [c0: 32 rows x 128 B][c1]
+constexpr int kOffSL = kOffSH + 8192;
+constexpr int kOffVH = kOffSL + 8192;      // v hi   [32 rows (dv) x 64 tokens]
+constexpr int kOffVL = kOffVH + 4096;
+constexpr int kOffVDH = kOffVL + 4096;     // decayed v hi
+constexpr int kOffVDL = kOffVDH + 4096;
+constexpr int kOffX = kOffVDL + 4096;      // epilogue exchange fp32 [64][36]
+constexpr int kOffBar = kOffX + kTC * kVcLd * 4;
+constexpr int kTcSmem = kOffBar + 128;
+static_assert(kTcSmem <= 227 * 1024, "smem");
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// MN-major operand, SWIZZLE_128B: 64-element (128 B) rows along MN, 8 K-rows per 1024 B atom
+__device__ __forceinline__ uint64_t tc_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// byte offset of element (row, k) in a K-major SW128 tile whose 64-element K chunks are `chunk_stride` bytes apart
+__device__ __forceinline__ uint32_t sw128_off(int row, int k, int chunk_stride) {
+  const int kk = k & 63;
+  return (uint32_t)((k >> 6) * chunk_stride + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1)));
+}
+
+__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = *reinterpret_cast<const unsigned short*>(&h);
+  lo = *reinterpret_cast<const unsigned short*>(&l);
+}
+
+struct GdnTcParams {
+  const uint8_t* kcd_img;    // [nv][n_chunks][hi c0 | hi c1 | lo c0 | lo c1] 8 KB each
+  const uint8_t* intra_img;  // [nv][n_chunks][hi | lo] 8 KB each
+  const float* vcorr;        // [nv][n_chunks][dv/32][64][36]
+  const float* gcum;         // [nv][n_chunks][64]
+  float* state;              // [nv][dk][dv] in/out
+  __nv_bfloat16* core_out;   // [M][nv*dv]
+  int M, n_chunks, nv, nk;
+};
+
+__global__ void __launch_bounds__(kTThreads, 1)
+    gdn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* full = bars;           // [2]
+  uint64_t* empty = bars + 2;      // [2]
+  uint64_t* s_ready = bars + 4;
+  uint64_t* g1_done = bars + 5;
+  uint64_t* v_ready = bars + 6;
+  uint64_t* g2_done = bars + 7;
+  uint64_t* g3_done = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, sl = blockIdx.y;
+  const int kh = h / (p.nv / p.nk);
+  const int n_chunks = p.n_chunks;
+  const int vd = p.nv * kTD;
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_init(s_ready, 128);
+    mbar_init(g1_done, 1);
+    mbar_init(v_ready, 128);
+    mbar_init(g2_done, 1);
+    mbar_init(g3_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr_smem, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kColD1 = 0, kColD1b = 32, kColD2 = 64, kColD3 = 96;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ producer
+    if (tid == 128) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      const long long hc0 = (long long)h * n_chunks;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
+        uint8_t* sb = smem + st * kStageBytes;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], kTxBytes);
+        const long long hc = hc0 + c;
+        const uint8_t* kimg = p.kcd_img + hc * 32768;
+        bulk_g2s(sb + kOffA1, kimg, 8192, &full[st]);                       // kcd_hi c0
+        bulk_g2s(sb + kOffA1 + 16384, kimg + 8192, 8192, &full[st]);        // kcd_hi c1
+        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);             // kcd_lo c0, c1
+        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);  // intra hi, lo
+        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
+        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
+        tma_load_2d(sb + kOffA1 + 8192, &tmap_q, kh * kTD, c * kTC, &full[st]);
+        tma_load_2d(sb + kOffA1 + 16384 + 8192, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
+        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
+        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (tid == 160) {
+      const uint32_t id_k = umma_idesc_bf16_m128(kTSV);                     // A, B K-major
+      const uint32_t id_amn = umma_idesc_bf16_m128(kTSV) | (1u << 15);      // A MN-major (k tile), B K-major
+      const uint32_t sh = smem_u32(smem + kOffSH), slo = smem_u32(smem + kOffSL);
+      const uint32_t vh = smem_u32(smem + kOffVH), vl = smem_u32(smem + kOffVL);
+      const uint32_t vdh = smem_u32(smem + kOffVDH), vdl = smem_u32(smem + kOffVDL);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
+        const uint32_t sb = smem_u32(smem + st * kStageBytes);
+        mbar_wait(&full[st], ph);
+        mbar_wait(s_ready, cp);
+        tc_fence_after_sync();
+        // G1: [kcd_hi ; q] (S_hi + S_lo) -> D1 ;  [kcd_lo ; *] S_hi -> D1b
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a0 = sb + (pass < 2 ? kOffA1 : kOffA1L);
+          const uint32_t a_chunk = pass < 2 ? 16384u : 8192u;
+          const uint32_t b0 = pass == 1 ? slo : sh;
+          const uint32_t dcol = pass < 2 ? kColD1 : kColD1b;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const uint64_t ad = umma_desc_k_sw128(a0 + ch * a_chunk);
+            const uint64_t bd = umma_desc_k_sw128(b0 + ch * 4096);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(tmem_base + dcol, ad + 2 * ks, bd + 2 * ks, id_k, (pass == 1 || ch > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(g1_done);
+        mbar_wait(v_ready, cp);
+        tc_fence_after_sync();
+        // G2: dS = k^T (vdec_hi + vdec_lo)
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const uint64_t bd = umma_desc_k_sw128(pass ? vdl : vdh);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
+            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn, (pass > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(g2_done);
+        // G3: [intra_hi ; intra_lo] (v_hi + v_lo)
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const uint64_t ad = umma_desc_k_sw128(sb + kOffA3);
+          const uint64_t bd = umma_desc_k_sw128(pass ? vl : vh);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + kColD3, ad + 2 * ks, bd + 2 * ks, id_k, (pass > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(g3_done);
+        umma_commit(&empty[st]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ CUDA-core warps: thread = TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float s[kTSV];                                  // state row k = tid, columns of this dv slice
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
+#pragma unroll
+      for (int j4 = 0; j4 < kTSV / 4; ++j4) {
+        const float4 v = src[j4];
+        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
+      }
+    }
+    auto write_s_tiles = [&]() {
+#pragma unroll
+      for (int j = 0; j < kTSV; ++j) {
+        unsigned short hi, lo;
+        split_bf16(s[j], hi, lo);
+        const uint32_t off = sw128_off(j, tid, 4096);
+        *reinterpret_cast<unsigned short*>(smem + kOffSH + off) = hi;
+        *reinterpret_cast<unsigned short*>(smem + kOffSL + off) = lo;
+      }
+    };
+    write_s_tiles();
+    fence_proxy_async_smem();
+    mbar_arrive(s_ready);
+    float* xch = reinterpret_cast<float*>(smem + kOffX);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int st = c & 1;
+      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
+      const uint8_t* sb = smem + st * kStageBytes;
+      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
+      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
+      mbar_wait(&full[st], ph);                     // this chunk's gcum / vcorr are in shared memory
+      const int i = tid & 63;                        // token row of this thread in G1 / G3
+      const float g_last = sg[kTC - 1], g_i = sg[i];
+      const float d_last = expf(g_last);
+      float it[kTSV];
+#pragma unroll
+      for (int j = 0; j < kTSV; ++j) it[j] = 0.f;
+      mbar_wait(g1_done, cp);
+      tc_fence_after_sync();
+      if (tid < 64) {
+        uint32_t a[32], b[32];
+        tmem_ld32(lane_addr + kColD1, a);
+        tmem_ld32(lane_addr + kColD1b, b);
+        tmem_ld_wait();
+        const float dec = expf(g_last - g_i);
+#pragma unroll
+        for (int j4 = 0; j4 < kTSV / 4; ++j4) {
+          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + 4 * j4);
+          const float vcv[4] = {vc4.x, vc4.y, vc4.z, vc4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * j4 + e;
+            const float v = vcv[e] - (__uint_as_float(a[j]) + __uint_as_float(b[j]));
+            unsigned short hi, lo, dhi, dlo;
+            split_bf16(v, hi, lo);
+            split_bf16(v * dec, dhi, dlo);
+            const uint32_t off = sw128_off(j, i, 0);
+            *reinterpret_cast<unsigned short*>(smem + kOffVH + off) = hi;
+            *reinterpret_cast<unsigned short*>(smem + kOffVL + off) = lo;
+            *reinterpret_cast<unsigned short*>(smem + kOffVDH + off) = dhi;
+            *reinterpret_cast<unsigned short*>(smem + kOffVDL + off) = dlo;
+          }
+        }
+      } else {
+        uint32_t a[32];
+        tmem_ld32(lane_addr + kColD1, a);
+        tmem_ld_wait();
+        const float eg = expf(g_i);
+#pragma unroll
+        for (int j = 0; j < kTSV; ++j) it[j] = eg * __uint_as_float(a[j]);
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(v_ready);
+      // state update: S = e^{g_last} S + dS
+      mbar_wait(g2_done, cp);
+      tc_fence_after_sync();
+      {
+        uint32_t a[32];
+        tmem_ld32(lane_addr + kColD2, a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < kTSV; ++j) s[j] = fmaf(d_last, s[j], __uint_as_float(a[j]));
+      }
+      if (c + 1 < n_chunks) {
+        write_s_tiles();
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(s_ready);
+      }
+      // output rows of this chunk
+      mbar_wait(g3_done, cp);
+      tc_fence_after_sync();
+      {
+        uint32_t a[32];
+        tmem_ld32(lane_addr + kColD3, a);
+        tmem_ld_wait();
+        if (tid < 64) {
+#pragma unroll
+          for (int j4 = 0; j4 < kTSV / 4; ++j4)
+            *reinterpret_cast<float4*>(xch + i * kVcLd + 4 * j4) =
+                make_float4(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1]), __uint_as_float(a[4 * j4 + 2]),
+                            __uint_as_float(a[4 * j4 + 3]));
+        }
+        named_bar_sync(1, 128);
+        if (tid >= 64) {
+          const int t = c * kTC + i;
+          uint32_t o[kTSV / 2];
+#pragma unroll
+          for (int j4 = 0; j4 < kTSV / 4; ++j4) {
+            const float4 x = *reinterpret_cast<const float4*>(xch + i * kVcLd + 4 * j4);
+            const float r0 = it[4 * j4] + x.x + __uint_as_float(a[4 * j4]);
+            const float r1 = it[4 * j4 + 1] + x.y + __uint_as_float(a[4 * j4 + 1]);
+            const float r2 = it[4 * j4 + 2] + x.z + __uint_as_float(a[4 * j4 + 2]);
+            const float r3 = it[4 * j4 + 3] + x.w + __uint_as_float(a[4 * j4 + 3]);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(r0, r1), p1 = __floats2bfloat162_rn(r2, r3);
+            o[2 * j4] = *reinterpret_cast<uint32_t*>(&p0);
+            o[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p1);
+          }
+          if (t < p.M) {
+            uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV);
+#pragma unroll
+            for (int q = 0; q < kTSV / 8; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+    }
+    {
+      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
+#pragma unroll
+      for (int j4 = 0; j4 < kTSV / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
+}
+
+// qn, kn: [M][nk*128] bf16 (prep kernel outputs).  The prepared operands are in the layouts documented in GdnTcParams.
+cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_img, const void* intra_img, const float* vcorr,
+                               const float* gcum, float* state, void* core_out, int M, int n_chunks, int nk, int nv,
+                               cudaStream_t s) {
+  static PerDeviceOnce once;
+  if (const int dev = once.pending(); dev >= 0) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    if (e != cudaSuccess) return e;
+    once.mark(dev);
+  }
+  alignas(64) CUtensorMap tq, tk;
+  cudaError_t e = make_tmap_bf16_rows(&tq, qn, M, (long long)nk * kTD, kTC);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tk, kn, M, (long long)nk * kTD, kTC);
+  if (e != cudaSuccess) return e;
+  GdnTcParams p{(const uint8_t*)kcd_img, (const uint8_t*)intra_img, vcorr, gcum, state, (__nv_bfloat16*)core_out, M, n_chunks, nv, nk};
+  gdn_scan_tc_kernel<<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
+  return cudaGetLastError();
+}
+
+}  // namespace kb2

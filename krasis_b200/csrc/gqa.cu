@@ -19,6 +19,7 @@
 #include <cuda_fp8.h>
 
 #include "moe_common.cuh"
+#include "prof.cuh"
 #include "ptx.cuh"
 
 namespace kb2 {
@@ -496,14 +497,16 @@ cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_r
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
+  { KernelSpan ks(K_GQA_PREP, s);
   gqa_prep_kernel<<<M, 256, 8 * g.d * sizeof(float), s>>>(g, (const __nv_bfloat16*)q_raw, (const __nv_bfloat16*)k_raw,
                                                           (const __nv_bfloat16*)v_raw, q_norm, k_norm, positions,
                                                           kv_indices, (__nv_bfloat16*)q_rot, (uint8_t*)k_cache,
-                                                          (uint8_t*)v_cache, M);
+                                                          (uint8_t*)v_cache, M); }
   const int row = g.nkv * g.d;
   const long long n_thr = (long long)kv_len * (row / 16) * 2;
+  { KernelSpan ks(K_KV_GATHER, s);
   gqa_gather_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, s>>>((const uint8_t*)k_cache, (const uint8_t*)v_cache, kv_indices,
-                                                                    row, kv_len, (__nv_bfloat16*)k_bf, (__nv_bfloat16*)v_bf);
+                                                                    row, kv_len, (__nv_bfloat16*)k_bf, (__nv_bfloat16*)v_bf); }
   alignas(64) CUtensorMap tq, tk, tv;
   cudaError_t e = make_tmap_bf16_rows(&tq, q_rot, M, (long long)g.nh * g.d, kFQ);
   if (e != cudaSuccess) return e;
@@ -513,6 +516,7 @@ cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_r
   if (e != cudaSuccess) return e;
   const float sl2 = (1.0f / sqrtf((float)g.d)) * 1.4426950408889634f;
   dim3 grid((M + kFQ - 1) / kFQ, g.nh);
+  KernelSpan ks(K_FMHA, s);
   if (g.d == 256)
     gqa_fmha_kernel<256, 256, false><<<grid, kFThreads, FmhaSmem<256, 256>::kTotal, s>>>(
         tq, tk, tk, tv, g, (const __nv_bfloat16*)q_raw, (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0, 0);
@@ -635,10 +639,12 @@ cudaError_t launch_mla_core(const MlaDims& m, void* q_full, const void* kv_a, co
     if (e0 != cudaSuccess) return e0;
     once.mark(dev);
   }
+  { KernelSpan ks(K_MLA_PREP, s);
   mla_prep_kernel<<<M, 256, 0, s>>>(m, (const __nv_bfloat16*)kv_a, (__nv_bfloat16*)q_full, kv_norm_w, inv_freq, positions,
-                                    kv_indices, (uint8_t*)ckv_cache, (uint8_t*)kpe_cache, M);
+                                    kv_indices, (uint8_t*)ckv_cache, (uint8_t*)kpe_cache, M); }
+  { KernelSpan ks(K_KV_GATHER, s);
   mla_gather_kernel<<<(kv_len + 7) / 8, 256, 0, s>>>((const uint8_t*)ckv_cache, (const uint8_t*)kpe_cache, kv_indices, m.lora,
-                                                     m.rope, kv_len, (__nv_bfloat16*)ckv_bf16, (__nv_bfloat16*)kpe_bf16);
+                                                     m.rope, kv_len, (__nv_bfloat16*)ckv_bf16, (__nv_bfloat16*)kpe_bf16); }
   const int up = m.nh * (m.nope + m.dv);
   cudaError_t e = launch_dense_gemm(ckv_bf16, w_kv, kv_up, nullptr, kv_len, up, m.lora, up, false, num_sms, s);
   if (e != cudaSuccess) return e;
@@ -652,6 +658,7 @@ cudaError_t launch_mla_core(const MlaDims& m, void* q_full, const void* kv_a, co
   GqaDims g{m.H, m.nh, m.nh, m.nope + m.rope, 0, 0, 0.f, m.eps};
   const float sl2 = sm_scale * 1.4426950408889634f;
   dim3 grid((M + kFQ - 1) / kFQ, m.nh);
+  KernelSpan ks(K_FMHA, s);
   gqa_fmha_kernel<192, 128, true><<<grid, kFThreads, FmhaSmem<192, 128>::kTotal, s>>>(
       tq, tk, tpe, tk, g, nullptr, (__nv_bfloat16*)attn_out, M, q_start, kv_len, sl2, 0, m.nh * m.nope);
   return cudaGetLastError();

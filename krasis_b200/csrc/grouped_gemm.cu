@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include "moe_common.cuh"
+#include "prof.cuh"
 #include "ptx.cuh"
 
 namespace kb2 {
@@ -488,6 +489,7 @@ static cudaError_t launch_one(const GemmParams& p, const CUtensorMap& tmap, int 
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
+  KernelSpan ks(kGemm1 ? K_GEMM1_GATE_UP : K_GEMM2_DOWN, stream);
   kern<<<num_sms, kNumThreads, smem, stream>>>(p, tmap);
   return cudaGetLastError();
 }

@@ -9,6 +9,7 @@
 //   combine_kernel                             moe_sum_reduce (gpu_prefill.py:238) + rsf*out + shared
 //                                              (gpu_prefill.py:4471-4482)
 #include "moe_common.cuh"
+#include "prof.cuh"
 
 namespace kb2 {
 
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const __nv_bfloat16* __res
   const int m = (int)(idx / vec_per_row), v = (int)(idx % vec_per_row);
   float acc[8] = {};
   for (int j = 0; j < top_k; ++j) {
-    const int slot = slot_of[(long long)m * top_k + j];
+    const int slot = slot_of ? slot_of[(long long)m * top_k + j] : m * top_k + j;     // no table: rows already in token order
     if (slot < 0) continue;
     const uint4 x = *reinterpret_cast<const uint4*>(c3 + (long long)slot * H + v * 8);
     const __nv_bfloat16* px = reinterpret_cast<const __nv_bfloat16*>(&x);
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(256) quantize_group_kernel(const __nv_bfloat16
 }
 
 cudaError_t launch_quantize_group(const void* w, int bits, void* q_out, void* scales, long long rows, int K, cudaStream_t s) {
+  KernelSpan ks(K_QUANTIZE_GROUP, s);
   if ((bits != 4 && bits != 8) || K % kGroup || rows <= 0) return cudaErrorInvalidValue;
   const long long warps = rows * (K / kGroup);
   quantize_group_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)w, bits, q_out,
@@ -469,6 +471,7 @@ __global__ void retile_gguf_kernel(int fmt, const uint8_t* __restrict__ a, const
 
 cudaError_t launch_retile_gguf(int fmt, const void* a, const void* b, int n_a, void* dst, int E, int N, int K,
                                cudaStream_t s) {
+  KernelSpan ks(K_RETILE, s);
   if (N % kTileRows || K % kBlockK || (fmt == kFmtQ4_K && K % 256) || (fmt != kFmtQ4_K && fmt != kFmtQ8_0)) return cudaErrorInvalidValue;
   const long long total = (long long)E * (N / kTileRows) * (K / kBlockK) * kTileRows;
   retile_gguf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(fmt, (const uint8_t*)a, (const uint8_t*)b, n_a,
@@ -481,6 +484,7 @@ cudaError_t launch_retile_gguf(int fmt, const void* a, const void* b, int n_a, v
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_router_logits(const void* h, const void* gate, const float* bias, float* logits, int M, int E,
                                  int H, cudaStream_t s) {
+  KernelSpan ks(K_ROUTER_GEMM, s);
   dim3 grid((E + RT - 1) / RT, (M + RT - 1) / RT);
   router_logits_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)h, (const __nv_bfloat16*)gate, bias, logits, M, E, H);
   return cudaGetLastError();
@@ -488,6 +492,7 @@ cudaError_t launch_router_logits(const void* h, const void* gate, const float* b
 
 cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int M, int E, int top_k, int scoring,
                                int renorm, int* ids, float* wts, cudaStream_t s) {
+  KernelSpan ks(K_ROUTER_TOPK, s);
   const int warps = 4;
   dim3 grid((M + warps - 1) / warps);
   if (top_k > 32 || E > 1024) return cudaErrorInvalidValue;
@@ -507,6 +512,7 @@ cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int 
 cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
                            int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
                            int* sorted_ids, const void* x, void* x_sorted, int H, cudaStream_t s) {
+  KernelSpan ks(K_BINNING, s, 3);
   const int n = M * top_k, E = e_end - e_start;
   if (E > 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * E, s);
@@ -521,6 +527,7 @@ cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, i
 
 cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
                            const void* shared, void* out, cudaStream_t s) {
+  KernelSpan ks(K_COMBINE, s);
   const long long total = (long long)M * (H / 8);
   if (total == 0) return cudaSuccess;
   combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)c3, slot_of, M, H, top_k, rsf,
@@ -531,6 +538,7 @@ cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int
 
 cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,
                           cudaStream_t s) {
+  KernelSpan ks(K_RETILE, s, 2);
   if (N % kTileRows || K % kGroup) return cudaErrorInvalidValue;
   if (fmt == kFmtInt4G128) {
     const long long total = (long long)E * N * (K / 8);

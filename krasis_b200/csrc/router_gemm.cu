@@ -12,6 +12,7 @@
 #include <cuda.h>
 
 #include "moe_common.cuh"
+#include "prof.cuh"
 #include "ptx.cuh"
 
 namespace kb2 {
@@ -134,6 +135,7 @@ bool router_gemm_supported(int E, int H) { return E >= 16 && E <= 512 && E % 64 
 // tmap_g: tensor map over gate [E][H] with box rows 64 (built once per layer); x: [M][H] bf16
 cudaError_t launch_router_gemm(const void* x, const void* tmap_g, const float* bias, float* logits, int M, int E,
                                int H, cudaStream_t s) {
+  KernelSpan ks(K_ROUTER_GEMM, s);
   alignas(64) CUtensorMap tx;
   cudaError_t e = make_tmap_bf16_rows(&tx, x, M, H, 128);
   if (e != cudaSuccess) return e;

@@ -253,6 +253,15 @@ class KrasisEngine:
                                              _stream_ptr(hidden_states.device)))
         return out
 
+    def finish(self, routed: torch.Tensor, shared: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bf16(rsf * routed) + shared, in place on `routed` (the tail of gpu_prefill.py:4467-4482 after an EP reduction)."""
+        self._check_act(routed, "routed")
+        if shared is not None:
+            self._check_act(shared, "shared")
+        capi.check(self._lib.kb2_finish_routed(self._h, routed.data_ptr(), shared.data_ptr() if shared is not None else None,
+                                               routed.data_ptr(), routed.shape[0], _stream_ptr(routed.device)))
+        return routed
+
     def moe_forward_host(self, moe_layer_idx, x_host: torch.Tensor, topk_ids=None, topk_weights=None,
                          routed_only=False, out_host: Optional[torch.Tensor] = None):
         """Host-buffer entry (bytes in / bytes out like submit_forward+sync_forward, src/moe.rs:2722,2809)."""

@@ -65,6 +65,77 @@ def splits_from_count_matrix(count_matrix: List[List[int]], rank: int):
     return send, recv
 
 
+class Communicator:
+    """The expert-parallel communicator behind the C ABI (kb2_comm_*, include/krasis_b200.h): NCCL over NVLink owned by
+    libkrasis_b200.  torch.distributed (any backend) is used ONCE, to hand rank 0's 128-byte unique id to the other ranks —
+    the only thing a Rust / C host would have to move between its processes."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        self._lib = capi.load()
+        self.rank, self.world, self.device = rank, world, torch.device("cuda", device)
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        capi.check(self._lib.kb2_comm_init(buf, rank, world, device, C.byref(self._h)))
+
+    @staticmethod
+    def new_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        capi.check(capi.load().kb2_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int, group=None):
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.new_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(box[0], rank, world, device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kb2_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """[rows, ...] on every rank -> [world * rows, ...] in rank order."""
+        x = x.contiguous()
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        capi.check(self._lib.kb2_comm_all_gather(self._h, x.data_ptr(), out.data_ptr(), x.numel() * x.element_size(), self._stream()))
+        return out
+
+    def reduce_scatter_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """BF16 [world * rows, H] partial sums -> this rank's [rows, H] slice of the sum over ranks."""
+        if x.dtype != torch.bfloat16 or x.shape[0] % self.world or not x.is_contiguous():
+            raise ValueError("reduce_scatter_rows: contiguous bf16 [world * rows, ...] expected")
+        out = torch.empty((x.shape[0] // self.world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        capi.check(self._lib.kb2_comm_reduce_scatter_bf16(self._h, x.data_ptr(), out.data_ptr(), out.numel(), self._stream()))
+        return out
+
+    def all_reduce(self, x: torch.Tensor) -> torch.Tensor:
+        capi.check(self._lib.kb2_comm_all_reduce_bf16(self._h, x.data_ptr(), x.data_ptr(), x.numel(), self._stream()))
+        return x
+
+    def broadcast(self, x: torch.Tensor, root: int) -> torch.Tensor:
+        capi.check(self._lib.kb2_comm_broadcast(self._h, x.data_ptr(), x.numel() * x.element_size(), root, self._stream()))
+        return x
+
+
+def token_shard(num_tokens: int, rank: int, world: int):
+    """Rows [lo, hi) of the residual stream owned by `rank` (token-sharded prefill); num_tokens % world == 0."""
+    if num_tokens % world:
+        raise ValueError(f"{num_tokens} tokens do not divide over {world} ranks")
+    per = num_tokens // world
+    return rank * per, (rank + 1) * per
+
+
 class ExpertParallelMoE:
     """Prefill MoE forward for a token shard, experts sharded over the ranks of `group`."""
 
@@ -104,10 +175,14 @@ class ExpertParallelMoE:
                                        self._xs.data_ptr(), self._ws_buf().data_ptr(), self._is_buf().data_ptr(),
                                        self._slot.data_ptr(), self._counts.data_ptr(), stream))
         dist.all_gather_into_tensor(self._all_counts.view(-1), self._counts, group=self.group)
-        send, recv = splits_from_count_matrix(self._all_counts.cpu().tolist(), self.rank)   # the one host sync per layer
+        cm = self._all_counts.cpu().tolist()                                                 # the one host sync per layer
+        send, recv = splits_from_count_matrix(cm, self.rank)
         n_send, n_recv = sum(send), sum(recv)
-        if n_recv > self.cap:
-            raise ValueError(f"received {n_recv} rows > capacity {self.cap}; raise max_tokens")
+        # every rank holds the whole count matrix: check EVERY rank's receive total so that all ranks raise together
+        # (a rank that raised alone would leave the others blocked inside the all-to-all)
+        worst = max(sum(splits_from_count_matrix(cm, r)[1]) for r in range(self.world))
+        if worst > self.cap:
+            raise ValueError(f"a rank would receive {worst} rows > capacity {self.cap}; raise max_tokens")
         rows, ids, wts = self._rows[:n_recv], self._rid_buf()[:n_recv], self._rw_buf()[:n_recv]
         dist.all_to_all_single(rows, self._xs[:n_send], output_split_sizes=recv, input_split_sizes=send, group=self.group)
         dist.all_to_all_single(ids, self._is_buf()[:n_send], output_split_sizes=recv, input_split_sizes=send, group=self.group)

@@ -92,7 +92,9 @@ def _model_worker(rank, world, port, ret):
                               linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=32, linear_value_head_dim=32,
                               synthetic_router_std=1.0)   # decisive router: near-ties (legitimately implementation-dependent) become rare
         M = 150
-        model = KrasisModel(cfg, device=rank, max_tokens=M, rank=rank, num_ranks=world)
+        from krasis_b200.parallel import Communicator
+        comm = Communicator.from_torch_distributed(rank) if world > 1 else None      # NCCL behind the C ABI (kb2_comm_*)
+        model = KrasisModel(cfg, device=rank, max_tokens=M, rank=rank, num_ranks=world, comm=comm)
         tok = torch.randint(0, cfg.vocab_size, (M,), generator=torch.Generator().manual_seed(9)).cuda(rank)
         logits = model.forward(tok, torch.arange(M).cuda(rank), model.new_sequence(), return_all_logits=True)
         torch.cuda.synchronize()
@@ -102,8 +104,8 @@ def _model_worker(rank, world, port, ret):
 
 
 def test_whole_model_two_ranks_matches_one_rank():
-    """Head-parallel attention + expert-parallel MoE on 2 GPUs == the single-GPU forward (up to BF16 partial-sum
-    rounding and the router near-ties it can flip)."""
+    """Token-sharded residual stream + head-parallel attention + expert-parallel MoE on 2 GPUs (all-gather / reduce-scatter
+    through kb2_comm_*) == the single-GPU forward (up to BF16 partial-sum rounding and the router near-ties it can flip)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()

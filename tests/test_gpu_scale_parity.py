@@ -216,3 +216,36 @@ def test_router_mismatches_are_near_ties_at_benchmark_size(E, k, H):
     rel = np.abs(w.cpu().numpy()[ok] - w_o[ok]) / w_o[ok]
     assert rel.max() < 3e-5
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 scan vs mma.sync scan
+
+@pytest.mark.parametrize("M", [200, 1024])
+def test_gdn_tcgen05_scan_matches_the_mma_sync_scan(M, monkeypatch):
+    """Same layer, same inputs, two state carries: the tcgen05 chunk scan (BF16 hi/lo pairs, fp32 accumulate) against the
+    3xTF32 mma.sync scan kept for other head sizes.  Both are fp32-grade: the carried state must agree to 1e-4 relative,
+    the BF16 outputs to one BF16 ulp of the output maximum (rare rounding flips)."""
+    from krasis_b200.attention import GatedDeltaNetAttention
+    torch.manual_seed(21)
+    nk, nv, dk, dv, H, K = 2, 4, 128, 128, 256, 4
+    kd, vd = nk * dk, nv * dv
+    bf = torch.bfloat16
+    w = dict(in_proj_qkvz=(torch.randn(2 * kd + 2 * vd, H) * 0.15).to(bf), in_proj_ba=(torch.randn(2 * nv, H) * 0.15).to(bf),
+             out_proj=(torch.randn(H, vd) * 0.05).to(bf), conv1d_weight=(torch.randn(2 * kd + vd, 1, K) * 0.5).to(bf),
+             A_log=(torch.randn(nv) * 0.5).to(bf), dt_bias=(torch.randn(nv) * 0.5).to(bf),
+             norm_weight=(1 + 0.1 * torch.randn(dv)).to(bf))
+    cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_value_heads=nv, linear_key_head_dim=dk,
+                                linear_value_head_dim=dv, linear_conv_kernel_dim=K, rms_norm_eps=1e-6)
+    x1, x2 = torch.randn(M, H).to(bf).cuda(), torch.randn(M // 2 + 3, H).to(bf).cuda()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KB2_GDN_LEGACY", mode)
+        lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
+        y1 = lay.forward(x1, is_decode=False).float().cpu()
+        y2 = lay.forward(x2, is_decode=False).float().cpu()          # state carried into a second call
+        _, rec = lay.state()
+        res[mode] = (y1, y2, rec)
+    for a, b in zip(res["0"][:2], res["1"][:2]):
+        assert (a - b).abs().max().item() <= 2 ** -8 * b.abs().max().item()
+        assert (a == b).float().mean().item() > 0.97
+    assert np.abs(res["0"][2] - res["1"][2]).max() <= 1e-4 * np.abs(res["1"][2]).max()

@@ -115,3 +115,59 @@ def test_head_parallel_shards_partition_the_layer(world):
         assert nh_l % nkv_l == 0                                                                 # local GQA grouping stays uniform
         seen_q.append(p["q_proj"])
     assert torch.equal(torch.cat(seen_q), wq["q_proj"])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_token_shards_and_mla_head_shards_partition(world):
+    """Token-sharded prefill: the ranks' row ranges tile [0, M); MLA head shards tile q / w_kc / w_vc / o_proj exactly once
+    (DeepSeek-V2-Lite geometry, 16 heads)."""
+    from krasis_b200.model import DEEPSEEK_V2_LITE as cfg, shard_mla_weights
+    M = 8192
+    spans = [P.token_shard(M, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == M and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    with pytest.raises(ValueError):
+        P.token_shard(M + 1, 0, world)
+    nh, qd, dv, lora, H = cfg.num_attention_heads, cfg.qk_nope_head_dim + cfg.qk_rope_head_dim, cfg.v_head_dim, 64, 32
+    g = torch.Generator().manual_seed(0)
+    w = dict(q_proj=torch.randn(nh * qd, H, generator=g), kv_a_proj_with_mqa=torch.randn(lora + 64, H, generator=g),
+             kv_a_layernorm=torch.randn(lora, generator=g), w_kc=torch.randn(nh, 128, lora, generator=g),
+             w_vc=torch.randn(nh, dv, lora, generator=g), o_proj=torch.randn(H, nh * dv, generator=g))
+    parts = [shard_mla_weights(w, cfg, r, world) for r in range(world)]
+    assert all(n == nh // world for _, n in parts)
+    assert torch.equal(torch.cat([p["q_proj"] for p, _ in parts]), w["q_proj"])
+    assert torch.equal(torch.cat([p["w_kc"] for p, _ in parts]), w["w_kc"]) and torch.equal(torch.cat([p["w_vc"] for p, _ in parts]), w["w_vc"])
+    assert torch.equal(torch.cat([p["o_proj"] for p, _ in parts], dim=1), w["o_proj"])
+    assert all(torch.equal(p["kv_a_proj_with_mqa"], w["kv_a_proj_with_mqa"]) for p, _ in parts)      # latent projection replicated
+
+
+def _sharded_schedule_worker(rank, world, port, ret):
+    """The token-sharded layer schedule with gloo collectives standing in for kb2_comm_*: all-gather rows -> per-rank
+    partial of a column-sharded linear map -> reduce-scatter == the unsharded map on this rank's rows."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        M, H, N = 8 * world, 16, 4 * world
+        g = torch.Generator().manual_seed(5)
+        x, w = torch.randn(M, H, generator=g), torch.randn(N, H, generator=g)
+        wo = torch.randn(H, N, generator=g)
+        lo, hi = P.token_shard(M, rank, world)
+        parts = [torch.empty(hi - lo, H) for _ in range(world)]
+        dist.all_gather(parts, x[lo:hi].contiguous())
+        full = torch.cat(parts)
+        assert torch.equal(full, x)                                   # rank order == token order
+        n0, n1 = rank * N // world, (rank + 1) * N // world           # "heads" of this rank
+        partial = (full @ w[n0:n1].T) @ wo[:, n0:n1].T                 # [M, H] partial output of the head-parallel block
+        out = torch.empty(hi - lo, H)
+        dist.reduce_scatter(out, list(partial.split(M // world)))
+        want = ((x @ w.T) @ wo.T)[lo:hi]
+        ret[rank] = float((out - want).abs().max() / want.abs().max())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_token_sharded_schedule_gloo(world):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_schedule_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world and max(ret.values()) < 1e-5
