@@ -112,6 +112,15 @@ KB2_API int kb2_load_experts_gguf_host(kb2_engine* e, int moe_layer_idx, const v
 KB2_API int kb2_attach_experts_tiled_dev(kb2_engine* e, int moe_layer_idx, const void* w13_q_dev, const void* w13_s_dev,
                                  const void* w2_q_dev, const void* w2_s_dev);
 
+/* B200-layout expert cache (krasis_b200/tile_cache.py; the counterpart of the reference's Marlin cache file,
+ * src/weights/mod.rs:857-893,2462-2476,4117-4144): the four tiled buffers of one layer's LOCAL experts, host side.
+ * kb2_export_experts_tiled_host copies buffer `which` (sizes = kb2_tiled_bytes; a size mismatch is KB2_ERR_VALUE like
+ * write_experts_*_into, src/moe.rs:2285-2300) to host memory and synchronises; kb2_load_experts_tiled_host uploads four such
+ * buffers and owns the device copies — no quantisation or re-tiling happens on this path. */
+KB2_API int kb2_export_experts_tiled_host(kb2_engine* e, int moe_layer_idx, int which, void* dst_host, size_t dst_bytes);
+KB2_API int kb2_load_experts_tiled_host(kb2_engine* e, int moe_layer_idx, const void* w13_q_host, const void* w13_s_host,
+                                        const void* w2_q_host, const void* w2_s_host);
+
 /* Re-tile on the device without attaching (exposed so tests can check the layout transform). */
 KB2_API int kb2_retile_dev(kb2_engine* e, int weight_format, const void* src_q_dev, const void* src_s_dev, void* dst_q_dev,
                    void* dst_s_dev, int n_experts, int n_rows, int k_cols, void* stream);

@@ -58,6 +58,8 @@ SIGNATURES = {
                                          C.c_void_p]),
     "kb2_load_experts_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5),
     "kb2_load_experts_gguf_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 3),
+    "kb2_export_experts_tiled_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "kb2_load_experts_tiled_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
     "kb2_attach_experts_tiled_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4),
     "kb2_retile_dev": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
     "kb2_set_router_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -410,6 +410,41 @@ KB2_API int kb2_load_experts_gguf_host(kb2_engine* e, int layer, const void* gat
   return KB2_OK;
 }
 
+KB2_API int kb2_load_experts_tiled_host(kb2_engine* e, int layer, const void* w13_q, const void* w13_s, const void* w2_q,
+                                        const void* w2_s) {
+  if (int r = check_layer(e, layer)) return r;
+  if (!w13_q || !w2_q || (has_scale_tiles(fmt13(e)) && !w13_s) || (has_scale_tiles(fmt2(e)) && !w2_s)) return fail(KB2_ERR_VALUE, "null weight pointer");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  DevBufs dst(4);
+  const void* src[4] = {w13_q, w13_s, w2_q, w2_s};
+  for (int i = 0; i < 4; ++i) {
+    const size_t b = tiled_bytes(e, i);
+    if (!b) continue;
+    CUDA_TRY(cudaMalloc(&dst.p[i], b));
+    CUDA_TRY(cudaMemcpy(dst.p[i], src[i], b, cudaMemcpyHostToDevice));
+  }
+  LayerWeights& L = e->layers[layer];
+  free_layer(L);
+  L.w13_q = (const uint8_t*)dst.release(0); L.w13_s = (const uint8_t*)dst.release(1);
+  L.w2_q = (const uint8_t*)dst.release(2); L.w2_s = (const uint8_t*)dst.release(3);
+  L.owned = true;
+  return KB2_OK;
+}
+
+KB2_API int kb2_export_experts_tiled_host(kb2_engine* e, int layer, int which, void* dst_host, size_t dst_bytes) {
+  if (int r = check_layer(e, layer)) return r;
+  if (which < 0 || which > 3 || !dst_host) return fail(KB2_ERR_VALUE, "bad argument");
+  LayerWeights& L = e->layers[layer];
+  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
+  const size_t b = tiled_bytes(e, which);
+  if (dst_bytes != b) return fail(KB2_ERR_VALUE, "buffer %d: expected %zu bytes, got %zu", which, b, dst_bytes);   // moe.rs:2285-2300
+  const void* src[4] = {L.w13_q, L.w13_s, L.w2_q, L.w2_s};
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (b) CUDA_TRY(cudaMemcpy(dst_host, src[which], b, cudaMemcpyDeviceToHost));
+  return KB2_OK;
+}
+
 KB2_API int kb2_attach_experts_tiled_dev(kb2_engine* e, int layer, const void* w13_q, const void* w13_s, const void* w2_q,
                                  const void* w2_s) {
   if (int r = check_layer(e, layer)) return r;

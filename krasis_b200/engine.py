@@ -46,18 +46,39 @@ class KrasisEngine:
     kb2_config) and weights arrive either as the quantiser's arrays (`load_quantized_layer`) or as
     device-resident tiles (`attach_tiled_layer`)."""
 
-    def __init__(self, *, hidden_size: int, moe_intermediate_size: int, n_routed_experts: int,
-                 num_experts_per_tok: int, num_moe_layers: int, num_bits: int = 4, group_size: int = 128,
+    def __init__(self, parallel: bool = True, num_threads: Optional[int] = None, skip_shared_experts: bool = False, *,
+                 hidden_size: Optional[int] = None, moe_intermediate_size: int = 0, n_routed_experts: int = 0,
+                 num_experts_per_tok: int = 0, num_moe_layers: int = 0, num_bits: int = 4, group_size: int = 128,
                  gguf_gate_up_type: Optional[str] = None, gguf_down_type: Optional[str] = None,
                  rank: int = 0, num_ranks: int = 1, scoring_func: str = "softmax", norm_topk_prob: bool = False,
                  routed_scaling_factor: float = 1.0, max_tokens: int = 8192, device: int = 0):
+        """Two ways in, both kept:
+          * the reference's: `KrasisEngine(parallel=True, num_threads=None, skip_shared_experts=False)` then
+            `load(model_dir, ...)` (src/moe.rs:1482,1538) — geometry comes from config.json;
+          * explicit geometry keywords (what kb2_config takes), weights through load_quantized_layer / load_bf16_layer /
+            load_gguf_layer / attach_tiled_layer.
+        `parallel` / `num_threads` size the reference's rayon pool (moe.rs:1497-1500); the GPU engine has no host worker
+        threads, so they are accepted and recorded only."""
+        self._parallel, self._num_threads, self._skip_shared = bool(parallel), num_threads, bool(skip_shared_experts)
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        self._keep = {}          # device tensors attached by the caller (kept alive)
+        self._export_cache = None
+        self._model_dir = None
+        if hidden_size is not None:
+            self._create(hidden_size, moe_intermediate_size, n_routed_experts, num_experts_per_tok, num_moe_layers, num_bits,
+                         group_size, gguf_gate_up_type, gguf_down_type, rank, num_ranks, scoring_func, norm_topk_prob,
+                         routed_scaling_factor, max_tokens, device)
+
+    def _create(self, hidden_size, moe_intermediate_size, n_routed_experts, num_experts_per_tok, num_moe_layers, num_bits,
+                group_size, gguf_gate_up_type, gguf_down_type, rank, num_ranks, scoring_func, norm_topk_prob,
+                routed_scaling_factor, max_tokens, device):
         if num_bits not in (4, 8):
             raise ValueError(f"num_bits must be 4 or 8, got {num_bits}")           # gpu_prefill.py:259
         if group_size != 128:
             raise ValueError("only group_size=128 is supported (src/weights/marlin.rs:12)")
         if scoring_func not in _SCORING:
             raise ValueError(f"unknown scoring_func {scoring_func!r}")
-        self._lib = capi.load()
         gg = {"Q8_0": capi.FMT_GGUF_Q8_0, "Q4_K": capi.FMT_GGUF_Q4_K}
         if gguf_gate_up_type is not None:        # gguf_native=True in KrasisEngine.load (src/moe.rs:1538): keep GGUF blocks
             if gguf_gate_up_type not in gg or (gguf_down_type or gguf_gate_up_type) not in gg:
@@ -72,11 +93,70 @@ class KrasisEngine:
         self._h = C.c_void_p()
         capi.check(self._lib.kb2_create(C.byref(self._cfg), C.byref(self._h)))
         self._num_bits, self._group_size = num_bits, group_size
-        self._keep = {}          # device tensors attached by the caller (kept alive)
         self.device = torch.device("cuda", device)
         s, t = C.c_int32(), C.c_int32()
         capi.check(self._lib.kb2_expert_range(self._h, C.byref(s), C.byref(t)))
         self.expert_start, self.expert_end = s.value, t.value
+
+    def _loaded(self):
+        if not self._h:
+            raise RuntimeError("Model not loaded")                                  # PyRuntimeError, src/moe.rs:1790-1803
+
+    def load(self, model_dir: str, group_size: Optional[int] = None, max_layers: Optional[int] = None,
+             start_layer: Optional[int] = None, num_bits: Optional[int] = None, cpu_num_bits: Optional[int] = None,
+             gpu_num_bits: Optional[int] = None, gguf_path: Optional[str] = None, gguf_native: bool = False, *,
+             device: int = 0, max_tokens: int = 8192, rank: int = 0, num_ranks: int = 1, use_cache: bool = True,
+             cache_dir: Optional[str] = None):
+        """KrasisEngine.load (src/moe.rs:1538; python/krasis/model.py:1428-1440): config.json -> geometry, then the routed
+        experts of MoE layers [start_layer, start_layer + max_layers) — from the KB2 tile cache if a valid one exists
+        (`~/.krasis/cache/<model>/experts_kb2_int{b}_g128.bin`, header / hash / size checked like mod.rs:2382-2423), else from
+        the BF16 safetensors through the device quantiser (and the cache is then written, single rank only), or, with
+        gguf_path + gguf_native, native GGUF expert blocks.  cpu_num_bits is accepted for signature parity (no CPU experts)."""
+        import json
+        import os
+        from . import loader, tile_cache
+        from .model import HybridMoEConfig
+        if self._h:
+            raise RuntimeError("engine is already loaded")
+        raw_bytes = open(os.path.join(model_dir, "config.json"), "rb").read()
+        cfg = HybridMoEConfig.from_hf_config(json.loads(raw_bytes))
+        bits = gpu_num_bits or num_bits or 4
+        s0 = start_layer or 0
+        n_layers = cfg.num_moe_layers - s0
+        if max_layers is not None:
+            n_layers = min(n_layers, max_layers)
+        if n_layers < 1:
+            raise ValueError("no MoE layers in the requested range")
+        gg = {}
+        g = None
+        if gguf_path is not None and gguf_native:
+            g = loader.GgufFile(gguf_path)
+            _, _, _, t13, t2 = loader.gguf_expert_blocks(g, cfg.first_k_dense_replace + s0, 0, 1, cfg.hidden_size, cfg.moe_intermediate_size)
+            gg = dict(gguf_gate_up_type=t13, gguf_down_type=t2)
+        self._create(cfg.hidden_size, cfg.moe_intermediate_size, cfg.n_routed_experts, cfg.num_experts_per_tok, n_layers, bits,
+                     group_size or 128, gg.get("gguf_gate_up_type"), gg.get("gguf_down_type"), rank, num_ranks, cfg.scoring_func,
+                     cfg.norm_topk_prob, cfg.routed_scaling_factor, max_tokens, device)
+        self._model_dir = model_dir
+        first = cfg.first_k_dense_replace + s0
+        if g is not None:
+            for m in range(n_layers):
+                gate, up, down, _, _ = loader.gguf_expert_blocks(g, first + m, self.expert_start, self.expert_end, cfg.hidden_size,
+                                                                 cfg.moe_intermediate_size)
+                self.load_gguf_layer(m, gate, up, down)
+            return
+        cdir = cache_dir or os.path.join(os.path.expanduser("~"), ".krasis", "cache", os.path.basename(os.path.normpath(model_dir)))
+        cpath = os.path.join(cdir, tile_cache.cache_file_name(bits))
+        whole = s0 == 0 and n_layers == cfg.num_moe_layers              # the cache always describes the whole model
+        if use_cache and whole and os.path.exists(cpath):
+            try:
+                tile_cache.load_tile_cache(self, cpath, raw_bytes)
+                return
+            except ValueError:
+                pass                                                    # stale / foreign cache: rebuild (mod.rs:2417-2423)
+        loader.load_experts_from_safetensors(self, model_dir, first_k_dense=first, num_bits=bits)
+        if use_cache and whole and num_ranks == 1:
+            os.makedirs(cdir, exist_ok=True)
+            tile_cache.write_tile_cache(self, cpath, raw_bytes, n_shared_experts=cfg.n_shared_experts)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -90,15 +170,17 @@ class KrasisEngine:
             pass
 
     # ---- introspection: all METHODS, as in the reference (src/moe.rs:1874-1965)
-    def num_moe_layers(self): return self._cfg.num_moe_layers
-    def hidden_size(self): return self._cfg.hidden_size
-    def intermediate_size(self): return self._cfg.moe_intermediate_size
-    def num_experts(self): return self._cfg.n_routed_experts
-    def top_k(self): return self._cfg.num_experts_per_tok
-    def group_size(self): return self._group_size
-    def gpu_num_bits(self): return self._num_bits
-    def cpu_num_bits(self): return self._num_bits
-    def is_parallel(self): return True
+    def num_moe_layers(self): self._loaded(); return self._cfg.num_moe_layers
+    def hidden_size(self): self._loaded(); return self._cfg.hidden_size
+    def intermediate_size(self): self._loaded(); return self._cfg.moe_intermediate_size
+    def num_experts(self): self._loaded(); return self._cfg.n_routed_experts
+    def top_k(self): self._loaded(); return self._cfg.num_experts_per_tok
+    def group_size(self): self._loaded(); return self._group_size
+    def gpu_num_bits(self): self._loaded(); return self._num_bits
+    def cpu_num_bits(self): self._loaded(); return self._num_bits
+    def is_parallel(self): return self._parallel
+    def has_unified(self): return False            # no CPU-format experts are kept (src/moe.rs:1930)
+    def has_gguf(self): return bool(self._h) and self._gguf
     def is_marlin_format(self): return True       # gpu_prefill.py:851 reads this without calling it: keep truthy
     def marlin_w2_padded_n(self): return self._cfg.hidden_size
     def launch_count(self): return int(self._lib.kb2_launch_count(self._h))
@@ -195,6 +277,62 @@ class KrasisEngine:
                 raise ValueError(f"tiled buffer {i}: expected {self.tiled_bytes(i)} bytes, got {t.numel() * t.element_size()}")
         capi.check(self._lib.kb2_attach_experts_tiled_dev(self._h, moe_layer_idx, *[t.data_ptr() for t in ts]))
         self._keep[moe_layer_idx] = ts
+
+    # ---- GPU-weight hand-off in the reference's own (Marlin) byte order — src/moe.rs:1972-2097,2431
+    def _marlin_layer(self, moe_layer_idx: int):
+        """The four Marlin-order arrays of every LOCAL expert of one layer, rebuilt from the device tiles: export -> host
+        untile (krasis_b200/tiles.py) -> marlin_repack (krasis_b200/marlin_cache.py).  Cached per layer: the reference's
+        callers ask for the four buffers one after the other (gpu_prefill.py:1059-1062)."""
+        self._loaded()
+        if self._gguf:
+            raise RuntimeError("GPU weights not available: this engine holds native GGUF blocks")       # moe.rs:1978
+        if self._export_cache is not None and self._export_cache[0] == moe_layer_idx:
+            return self._export_cache[1]
+        from . import marlin_cache as mc, tiles
+        E = self.expert_end - self.expert_start
+        H, I = self._cfg.hidden_size, self._cfg.moe_intermediate_size
+        bufs = []
+        for which in range(4):
+            a = np.empty(self.tiled_bytes(which), np.uint8)
+            capi.check(self._lib.kb2_export_experts_tiled_host(self._h, moe_layer_idx, which, a.ctypes.data, a.size))
+            bufs.append(a)
+        un = tiles.untile_int4 if self._num_bits == 4 else tiles.untile_int8
+        fw = mc.rowmajor_to_marlin_int4 if self._num_bits == 4 else mc.rowmajor_to_marlin_int8
+        q13, s13 = un(bufs[0], bufs[1], E, 2 * I, H)
+        q2, s2 = un(bufs[2], bufs[3], E, H, I)
+        out = fw(q13, s13, self._group_size) + fw(q2, s2, self._group_size)
+        self._export_cache = (moe_layer_idx, out)
+        return out
+
+    def _marlin_slice(self, moe_layer_idx: int, which: int, start, end) -> np.ndarray:
+        self._loaded()
+        s = self.expert_start if start is None else start
+        e = self.expert_end if end is None else end
+        if not (self.expert_start <= s <= e <= self.expert_end):
+            raise ValueError(f"expert range [{s}, {e}) outside this engine's experts [{self.expert_start}, {self.expert_end})")
+        return np.ascontiguousarray(self._marlin_layer(moe_layer_idx)[which][s - self.expert_start:e - self.expert_start])
+
+    def get_expert_w13_packed(self, moe_layer_idx: int, start=None, end=None) -> bytes:
+        return self._marlin_slice(moe_layer_idx, 0, start, end).tobytes()
+
+    def get_expert_w13_scales(self, moe_layer_idx: int, start=None, end=None) -> bytes:
+        return self._marlin_slice(moe_layer_idx, 1, start, end).tobytes()
+
+    def get_expert_w2_packed(self, moe_layer_idx: int, start=None, end=None) -> bytes:
+        return self._marlin_slice(moe_layer_idx, 2, start, end).tobytes()
+
+    def get_expert_w2_scales(self, moe_layer_idx: int, start=None, end=None) -> bytes:
+        return self._marlin_slice(moe_layer_idx, 3, start, end).tobytes()
+
+    def write_experts_range_into_pinned(self, moe_layer_idx: int, start: int, end: int, w13p_ptr: int, w13p_len: int,
+                                        w13s_ptr: int, w13s_len: int, w2p_ptr: int, w2p_len: int, w2s_ptr: int, w2s_len: int):
+        """src/moe.rs:2431: raw (address, length) pairs of caller-owned (pinned) buffers; lengths must match exactly
+        (PyValueError otherwise, :2285-2300)."""
+        for which, (ptr, ln) in enumerate(((w13p_ptr, w13p_len), (w13s_ptr, w13s_len), (w2p_ptr, w2p_len), (w2s_ptr, w2s_len))):
+            a = self._marlin_slice(moe_layer_idx, which, start, end)
+            if a.nbytes != ln:
+                raise ValueError(f"buffer {which}: expected {a.nbytes} bytes, got {ln}")
+            C.memmove(ptr, a.ctypes.data, ln)
 
     # ---- routing (src/moe.rs:2959-3050 set_routing_config / set_routing_weights)
     def set_routing_weights(self, moe_layer_idx: int, gate_bf16, bias_f32=None, e_score_correction_bias=None):

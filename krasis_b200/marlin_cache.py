@@ -112,6 +112,42 @@ def marlin_to_rowmajor_int8(mpacked: np.ndarray, mscales: np.ndarray, group_size
     return q, _scales_to_rowmajor(mscales, lead, k, n, group_size)
 
 
+def rowmajor_to_marlin_int4(packed: np.ndarray, scales: np.ndarray, group_size: int):
+    """The forward direction (marlin.rs:330-491 `marlin_repack`): ([..., N, K/8] u32, [..., N, K/gs] u16) as the quantiser
+    emits them -> ([..., K/16, 2N] u32, [..., K/gs, N] u16) in the Marlin GPU order.  Exact inverse of marlin_to_rowmajor_int4;
+    used to serve the reference's get_expert_* hand-off (src/moe.rs:1972-2097) from this engine."""
+    lead = packed.shape[:-2]
+    n, k8 = packed.shape[-2:]
+    k = k8 * 8
+    shifts = np.arange(8, dtype=np.uint32) * np.uint32(4)
+    nib = ((packed.astype(np.uint32)[..., None] >> shifts) & np.uint32(0xF)).astype(np.uint8).reshape(lead + (n, k))
+    kn = np.swapaxes(nib, -1, -2)                                              # [K][N]
+    t = np.moveaxis(kn.reshape(lead + (k // 16, 16, n // 16, 16)), -3, -2)     # [K/16][N/16][k 16][n 16]
+    blk = t.reshape(lead + (k // 16, n * 16 // 1024, 1024))[..., _weight_perm_int4()]
+    u = blk.reshape(lead + (k // 16, 2 * n, 8)).astype(np.uint32)
+    mpacked = np.bitwise_or.reduce(u << shifts, axis=-1).astype(np.uint32)
+    return mpacked, _scales_to_marlin(scales, lead, k, n, group_size)
+
+
+def _scales_to_marlin(scales: np.ndarray, lead, k: int, n: int, group_size: int):
+    p = _scale_perm(group_size < k)
+    s = np.swapaxes(scales.astype(np.uint16), -1, -2).reshape(lead + (-1, len(p)))
+    return np.ascontiguousarray(s[..., p].reshape(lead + (k // group_size, n)))
+
+
+def rowmajor_to_marlin_int8(q: np.ndarray, scales: np.ndarray, group_size: int):
+    """([..., N, K] i8, scales) -> ([..., K/16, 4N] u32 holding q + 128, Marlin scales) (marlin.rs:582-626,639-760)."""
+    lead = q.shape[:-2]
+    n, k = q.shape[-2:]
+    b = (q.astype(np.int16) + 128).astype(np.uint8)
+    kn = np.swapaxes(b, -1, -2)
+    t = np.moveaxis(kn.reshape(lead + (k // 16, 16, n // 16, 16)), -3, -2)
+    blk = t.reshape(lead + (k // 16, n * 16 // 1024, 1024))[..., _weight_perm_int8()]
+    u = blk.reshape(lead + (k // 16, 4 * n, 4)).astype(np.uint32)
+    shifts = np.arange(4, dtype=np.uint32) * np.uint32(8)
+    return np.bitwise_or.reduce(u << shifts, axis=-1).astype(np.uint32), _scales_to_marlin(scales, lead, k, n, group_size)
+
+
 class MarlinCacheFile:
     def __init__(self, path: str, config_json: Optional[bytes] = None):
         self.path = path

@@ -1,5 +1,6 @@
 """Device quantiser (bit-exact vs the oracle's restatement of marlin.rs) and the safetensors / GGUF load paths."""
 import json
+import os
 import struct
 
 import numpy as np
@@ -135,3 +136,89 @@ def test_marlin_cache_to_moe_is_bit_identical_to_direct_load(tmp_path):
     ids = torch.from_numpy(np.stack([rng.choice(E, k, replace=False) for _ in range(M)]).astype(np.int32)).cuda()
     wts = torch.from_numpy(rng.uniform(0.1, 1, (M, k)).astype(np.float32)).cuda()
     assert torch.equal(a.moe_forward(0, x, ids, wts, routed_only=True), b.moe_forward(0, x, ids, wts, routed_only=True))
+
+
+def test_tile_cache_round_trip_is_bit_identical(tmp_path):
+    """Quantise + re-tile once, write the KB2 tile cache, load it into a fresh engine (and into the two ranks of an EP pair):
+    the tiles and the MoE output are bit-identical and nothing is re-quantised; a wrong config hash / geometry / size is refused."""
+    from krasis_b200 import KrasisEngine, tile_cache as T
+    rng = np.random.default_rng(5)
+    E, H, I, k, M, L = 8, 256, 128, 2, 64, 2
+    kw = dict(hidden_size=H, moe_intermediate_size=I, n_routed_experts=E, num_experts_per_tok=k, num_moe_layers=L, max_tokens=M)
+    a = KrasisEngine(**kw)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for l in range(L):
+        a.load_bf16_layer(l, (torch.randn(E, 2 * I, H, device="cuda", generator=g) * 0.05).to(torch.bfloat16),
+                          (torch.randn(E, H, I, device="cuda", generator=g) * 0.05).to(torch.bfloat16))
+    cfg_json = b'{"hidden_size": 256}'
+    path = str(tmp_path / T.cache_file_name(4))
+    size = T.write_tile_cache(a, path, cfg_json, n_shared_experts=0)
+    assert size == T.expected_size(a) == os.path.getsize(path)
+    x = torch.randn(M, H, device="cuda", generator=g).to(torch.bfloat16)
+    ids = torch.from_numpy(np.stack([rng.choice(E, k, replace=False) for _ in range(M)]).astype(np.int32)).cuda()
+    w = torch.from_numpy(rng.dirichlet(np.ones(k), M).astype(np.float32)).cuda()
+    b = KrasisEngine(**kw)
+    T.load_tile_cache(b, path, cfg_json)
+    for l in range(L):
+        assert torch.equal(a.moe_forward(l, x, ids, w), b.moe_forward(l, x, ids, w))
+    parts = []
+    for r in range(2):                                           # an EP rank reads only its expert slice
+        e = KrasisEngine(**kw, rank=r, num_ranks=2)
+        T.load_tile_cache(e, path, cfg_json)
+        parts.append(e.moe_forward(1, x, ids, w, routed_only=True).float())
+    full = a.moe_forward(1, x, ids, w, routed_only=True).float()
+    assert (parts[0] + parts[1] - full).abs().max().item() <= 2 ** -7 * full.abs().max().item()
+    with pytest.raises(ValueError):
+        T.load_tile_cache(b, path, b'{"hidden_size": 257}')      # config.json changed
+    c = KrasisEngine(**{**kw, "num_moe_layers": 3})
+    with pytest.raises(ValueError):
+        T.load_tile_cache(c, path, cfg_json)                      # geometry mismatch
+    with open(path, "ab") as f:
+        f.write(b"\0")
+    with pytest.raises(ValueError):
+        T.load_tile_cache(b, path, cfg_json)                      # size mismatch
+
+
+def test_reference_engine_load_and_marlin_getters(tmp_path):
+    """The reference's two-step start-up — KrasisEngine() then load(model_dir, ...) (src/moe.rs:1482,1538) — on a real-format
+    checkpoint directory, the KB2 tile cache it leaves behind, and the Marlin-order hand-off (get_expert_*, src/moe.rs:1972-2097):
+    the returned bytes are the oracle's quantiser output pushed through the oracle's marlin_repack, bit for bit."""
+    from krasis_b200 import KrasisEngine, tile_cache as T
+    from tests.test_gpu_pretrained import build_v2lite_checkpoint
+    from tests.test_loader_cpu import _write_safetensors
+    hf, t, W = build_v2lite_checkpoint()
+    json.dump(hf, open(tmp_path / "config.json", "w"))
+    _write_safetensors(tmp_path / "model.safetensors", t)
+    cdir = str(tmp_path / "cache")
+    eng = KrasisEngine(parallel=True, num_threads=None, skip_shared_experts=False)
+    eng.load(str(tmp_path), max_tokens=64, cache_dir=cdir)
+    E, I, H = hf["n_routed_experts"], hf["moe_intermediate_size"], hf["hidden_size"]
+    assert (eng.hidden_size(), eng.intermediate_size(), eng.num_experts(), eng.top_k(), eng.num_moe_layers()) == (H, I, E, 2, 2)
+    assert os.path.exists(os.path.join(cdir, T.cache_file_name(4)))
+    w13, w2 = W["layers"][2]["experts"]                          # absolute layer 2 = moe layer 1 (first_k_dense_replace = 1)
+    for e in (0, E - 1):
+        q, s = Q.quantize_int4(w13[e].view(torch.int16).numpy().view(np.uint16))
+        mp, ms = Q.marlin_repack_int4(q, s)
+        assert eng.get_expert_w13_packed(1, e, e + 1) == mp.tobytes()
+        assert eng.get_expert_w13_scales(1, e, e + 1) == np.ascontiguousarray(ms).view(np.uint16).tobytes()
+        q, s = Q.quantize_int4(w2[e].view(torch.int16).numpy().view(np.uint16))
+        mp, ms = Q.marlin_repack_int4(q, s)
+        assert eng.get_expert_w2_packed(1, e, e + 1) == mp.tobytes()
+        assert eng.get_expert_w2_scales(1, e, e + 1) == np.ascontiguousarray(ms).view(np.uint16).tobytes()
+    assert len(eng.get_expert_w13_packed(0)) == E * (H // 16) * (2 * 2 * I) * 4          # [K/16, 2N] u32 per expert (mod.rs:955-970)
+    buf = [np.zeros(len(eng.get_expert_w13_packed(1, 2, 5)), np.uint8), np.zeros(len(eng.get_expert_w13_scales(1, 2, 5)), np.uint8),
+           np.zeros(len(eng.get_expert_w2_packed(1, 2, 5)), np.uint8), np.zeros(len(eng.get_expert_w2_scales(1, 2, 5)), np.uint8)]
+    args = [v for b in buf for v in (b.ctypes.data, b.size)]
+    eng.write_experts_range_into_pinned(1, 2, 5, *args)
+    assert buf[0].tobytes() == eng.get_expert_w13_packed(1, 2, 5) and buf[3].tobytes() == eng.get_expert_w2_scales(1, 2, 5)
+    with pytest.raises(ValueError):
+        eng.write_experts_range_into_pinned(1, 2, 5, buf[0].ctypes.data, buf[0].size - 4, *args[2:])
+    # second start: the cache is used (same tiles, bit-identical MoE output) and a stale cache is rebuilt, not trusted
+    eng2 = KrasisEngine()
+    eng2.load(str(tmp_path), max_tokens=64, cache_dir=cdir)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(64, H, device="cuda", generator=g).to(torch.bfloat16)
+    ids = torch.randint(0, E, (64, 2), device="cuda", generator=g, dtype=torch.int32)
+    ids[:, 1] = (ids[:, 0] + 1) % E
+    w = torch.rand(64, 2, device="cuda", generator=g)
+    assert torch.equal(eng.moe_forward(1, x, ids, w), eng2.moe_forward(1, x, ids, w))

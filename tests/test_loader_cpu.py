@@ -209,3 +209,61 @@ def test_marlin_inverse_matches_reference_execution(tag):
         assert np.array_equal(po, packed[b]) and np.array_equal(so.view(np.uint16), scales[b])
         mp, ms = Q.marlin_repack_int4(packed[b], scales[b], gs)       # forward direction of the oracle
         assert np.array_equal(mp, wm[b]) and np.array_equal(ms.view(np.uint16), sm[b])
+    fp, fs = MC.rowmajor_to_marlin_int4(packed, scales, gs)           # forward direction of the PRODUCT (get_expert_* hand-off)
+    assert np.array_equal(fp, wm) and np.array_equal(fs, sm)
+
+
+def test_marlin_forward_int8_and_host_untile_round_trips():
+    """rowmajor_to_marlin_int8 is the exact inverse of the INT8 cache reader; the host untile of the KB2 tile layout is the
+    exact inverse of the numpy statement of the device re-tiling (tests/test_gpu_moe.py checks that against the kernel)."""
+    from krasis_b200 import marlin_cache as MC, tiles
+    rng = np.random.default_rng(3)
+    for N, K in ((128, 256), (256, 128)):
+        q = rng.integers(-128, 128, (2, N, K)).astype(np.int8)
+        s = rng.integers(0, 2 ** 16, (2, N, K // 128), dtype=np.uint32).astype(np.uint16)
+        mq, ms = MC.rowmajor_to_marlin_int8(q, s, 128)
+        q2, s2 = MC.marlin_to_rowmajor_int8(mq, ms, 128)
+        assert np.array_equal(q, q2) and np.array_equal(s, s2)
+        # INT4 tile layout: tile (numpy statement used by the GPU tests) then untile (product)
+        packed = rng.integers(0, 2 ** 32, (2, N, K // 8), dtype=np.uint64).astype(np.uint32)
+        nib = (packed[..., None] >> (np.arange(8, dtype=np.uint32) * 4)) & 0xF
+        w = np.bitwise_or.reduce(nib[..., [0, 2, 4, 6, 1, 3, 5, 7]] << (np.arange(8, dtype=np.uint32) * 4), axis=-1).astype(np.uint32)
+        wq = np.ascontiguousarray(w.reshape(2, N // 128, 128, K // 64, 2, 4).transpose(0, 1, 3, 4, 2, 5)).reshape(-1)
+        ws = np.ascontiguousarray(s.reshape(2, N // 128, 128, K // 128).transpose(0, 1, 3, 2)).reshape(-1)
+        p2, s3 = tiles.untile_int4(wq.view(np.uint8), ws.view(np.uint8), 2, N, K)
+        assert np.array_equal(p2, packed) and np.array_equal(s3, s)
+        t8 = np.ascontiguousarray(q.reshape(2, N // 128, 128, K // 64, 4, 16).transpose(0, 1, 3, 4, 2, 5)).reshape(-1)
+        q3, s4 = tiles.untile_int8(t8.view(np.uint8), ws.view(np.uint8), 2, N, K)
+        assert np.array_equal(q3, q) and np.array_equal(s4, s)
+
+
+def test_reference_style_engine_surface_without_a_model():
+    """KrasisEngine(parallel, num_threads, skip_shared_experts) constructs unloaded; every accessor then raises the
+    reference's PyRuntimeError text (src/moe.rs:1790-1803); is_marlin_format stays truthy unbound (gpu_prefill.py:851)."""
+    from krasis_b200 import KrasisEngine
+    e = KrasisEngine(parallel=True, num_threads=8, skip_shared_experts=False)
+    assert e.is_parallel() and e.is_marlin_format and not e.has_unified()
+    for fn in (e.hidden_size, e.num_experts, e.top_k, e.num_moe_layers, e.gpu_num_bits, e.group_size):
+        with pytest.raises(RuntimeError, match="Model not loaded"):
+            fn()
+    with pytest.raises(RuntimeError, match="Model not loaded"):
+        e.get_expert_w13_packed(0)
+
+
+def test_tile_cache_header_discipline():
+    """KB2 tile cache header: reference field order / magic, own version, num_bits, and rejection of foreign files."""
+    from krasis_b200 import tile_cache as T
+    from krasis_b200.marlin_cache import CACHE_MAGIC, fnv1a
+    h = T.pack_header(2048, 512, 512, 48, 128, fnv1a(b'{"a": 1}'), 1, 4)
+    assert len(h) == 64 and h[:4] == CACHE_MAGIC
+    d = T.unpack_header(h)
+    assert d == dict(hidden=2048, inter=512, n_experts=512, n_layers=48, group_size=128, config_hash=fnv1a(b'{"a": 1}'),
+                     n_shared=1, num_bits=4)
+    with pytest.raises(ValueError):
+        T.unpack_header(b"XXXX" + h[4:])                       # bad magic
+    marlin = struct.pack("<4sI7Q", CACHE_MAGIC, 3, 2048, 512, 512, 48, 128, 0, 1)     # the reference's Marlin cache (version 3)
+    with pytest.raises(ValueError):
+        T.unpack_header(marlin)
+    with pytest.raises(ValueError):
+        T.unpack_header(h[:40])
+    assert T.cache_file_name(4) == "experts_kb2_int4_g128.bin"
