@@ -108,7 +108,50 @@ def preset(args):
 
 # --------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_sample(cfg, budget_s=15.0, n_weight_sets=2, threads=0):
+def cpu_sample_gguf(cfg, budget_s=15.0, threads=0):
+    """BASELINE configs[0]: the reference's CPU path on native GGUF blocks (moe_forward_gguf, src/moe.rs:990-1110): Q4_K
+    gate/up and — because K = moe_intermediate_size = 1408 is not a multiple of 256 for DeepSeek-V2-Lite — Q8_0 down
+    (SURVEY.md §8d C1), random blocks with sane fp16 scales, one weight set cycled over the MoE layer passes."""
+    import numpy as np
+    from oracle import cpu_ref, gguf_blocks as G
+    H, I, E, k, L = cfg.hidden_size, cfg.moe_intermediate_size, cfg.n_routed_experts, cfg.num_experts_per_tok, cfg.num_moe_layers
+    rng = np.random.default_rng(0xDEADBEEF)
+    t13 = G.GGML_Q4_K
+    t2 = G.GGML_Q4_K if I % 256 == 0 else G.GGML_Q8_0
+    gate = G.random_blocks(rng, t13, E * I, H).reshape(E, I, -1)
+    up = G.random_blocks(rng, t13, E * I, H).reshape(E, I, -1)
+    down = G.random_blocks(rng, t2, E * H, I).reshape(E, H, -1)
+    avail = host_threads()
+    nthreads = threads or min(avail, 64)
+
+    def run(n_tok):
+        x = rng.normal(0, 1, (n_tok, H)).astype(np.float32)
+        x /= np.sqrt((x ** 2).mean(axis=1, keepdims=True))
+        xb = ((x.view(np.uint32) + 0x8000) >> 16).astype(np.uint16)
+        ids = np.stack([rng.choice(E, k, replace=False) for _ in range(n_tok)]).astype(np.int32)
+        w = rng.dirichlet(np.ones(k), n_tok).astype(np.float32)
+        t0 = time.perf_counter()
+        for _ in range(L):
+            cpu_ref.moe_forward_gguf(gate, up, down, t13, t2, H, I, xb, ids, w, nthreads=nthreads)
+        return time.perf_counter() - t0
+
+    run(1)
+    t1 = run(4) / 4
+    n_tok = int(max(2, min(2048, budget_s / max(t1, 1e-4))))
+    dt = run(n_tok)
+    return dict(value=n_tok / dt, unit="tokens/s", cores=nthreads, host_threads_available=avail, kind="port",
+                sample=f"{n_tok} tokens x {L} MoE layer passes, {cfg.name} expert geometry (H{H} I{I} E{E} top-{k}), native GGUF blocks "
+                       f"({G.NAMES[t13]} gate/up, {G.NAMES[t2]} down), one random weight set cycled; C/AVX2 port of moe_forward_gguf "
+                       f"(src/moe.rs:990-1110, src/gguf_kernels.rs:271-425,690-756) ({dt:.1f}s); routed-expert blocks only"), n_tok, dt
+
+
+def cpu_sample(cfg, budget_s=15.0, n_weight_sets=2, threads=0, fmt="int4"):
+    if fmt == "gguf":
+        return cpu_sample_gguf(cfg, budget_s=budget_s, threads=threads)
+    return _cpu_sample_int4(cfg, budget_s, n_weight_sets, threads)
+
+
+def _cpu_sample_int4(cfg, budget_s=15.0, n_weight_sets=2, threads=0):
     """Time the C/AVX2 port of the reference's CPU expert path (moe_forward_unified, src/moe.rs:572-715) on a bounded
     token sample of the SAME workload geometry (one pass per MoE layer per token).  Weights: n_weight_sets layers of random
     packed INT4 cycled over the layer passes; routing: uniform without replacement + Dirichlet(1) weights
@@ -166,7 +209,7 @@ def run_reference_arm(args):
     per_step = max(3.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     vals = []
     for i in range(args.warmup + args.steps):
-        r, n_tok, dt = cpu_sample(cfg, budget_s=per_step)
+        r, n_tok, dt = cpu_sample(cfg, budget_s=per_step, fmt=args.cpu_format)
         if i >= args.warmup:
             vals.append((r, n_tok, dt))
     tot_tok = sum(v[1] for v in vals)
@@ -403,7 +446,7 @@ def run_full_model(args):
                                                     "below_32": int((cnt < 32).sum()), "above_192": int((cnt > 192).sum())}
     cpu_b = None
     if not args.no_cpu_baseline:
-        cpu_b, _, _ = cpu_sample(cfg, budget_s=args.cpu_budget)
+        cpu_b, _, _ = cpu_sample(cfg, budget_s=args.cpu_budget, fmt=args.cpu_format)
     line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int4 experts x bf16 activations (fp32 acc), bf16 attention, fp8 KV, int8 shared expert / lm_head",
@@ -426,6 +469,9 @@ def main():
     ap.add_argument("--tokens", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-format", default="int4", choices=["int4", "gguf"],
+                    help="CPU arm: int4 = moe_forward_unified on INT4 g128 (default); gguf = moe_forward_gguf on native Q4_K/Q8_0 blocks "
+                         "(BASELINE configs[0]: --config v2lite --impl reference --cpu-format gguf --tokens 2048)")
     args = ap.parse_args()
     args.tokens = args.tokens or DEFAULT_TOKENS[args.config]
     if args.impl == "reference":

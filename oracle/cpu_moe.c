@@ -201,6 +201,166 @@ int kcpu_moe_forward_int4(const uint32_t* w13, const uint16_t* s13, const uint32
   return 0;
 }
 
+/* ====================================================================================================================
+ * Native-GGUF CPU expert path: moe_forward_gguf (src/moe.rs:990-1110, non-NUMA parallel branch: one expert per task, then the
+ * weighted sum in expert order) over expert_forward_gguf (src/gguf_kernels.rs:690-756) with the INT16 activation path:
+ *   quantize_{bf16,f32}_to_int16   src/gguf_kernels.rs:108-172  (groups of 32, scale = amax/32767, round half away, group sums)
+ *   matvec_q4_k_avx2               src/gguf_kernels.rs:271-370  (madd_epi16 on zero-extended nibbles; fp32 lane accumulation;
+ *                                   dmin*mn*ascale*sum correction subtracted once per row)
+ *   matvec_q8_0_avx2               src/gguf_kernels.rs:376-425
+ *   SiLU in plain f32 (g / (1 + exp(-g)))  :727-731
+ * Types: 8 = Q8_0 (34 B / 32), 12 = Q4_K (144 B / 256)  (src/gguf.rs:15-31,56-85).
+ * ==================================================================================================================== */
+static inline float f16_to_f32(const uint8_t* p) {
+  uint16_t h;
+  memcpy(&h, p, 2);
+  return _cvtsh_ss(h);
+}
+
+static void quant_act_i16_g32(const float* x, int k, int16_t* q, float* scales, int32_t* sums) {
+  for (int g = 0; g < k / 32; ++g) {
+    float mx = 0.f;
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fabsf(x[g * 32 + i]));
+    const float scale = mx > 0.f ? mx / 32767.0f : 1.0f, inv = mx > 0.f ? 32767.0f / mx : 0.0f;
+    scales[g] = scale;
+    int32_t sum = 0;
+    for (int i = 0; i < 32; ++i) {
+      int v = (int)roundf(x[g * 32 + i] * inv);
+      if (v > 32767) v = 32767;
+      if (v < -32768) v = -32768;
+      q[g * 32 + i] = (int16_t)v;
+      sum += v;
+    }
+    sums[g] = sum;
+  }
+}
+
+static inline float hsum_avx(__m256 v) {        /* same reduction order as gguf_kernels.rs:hsum_avx */
+  const __m128 s = _mm_add_ps(_mm256_castps256_ps128(v), _mm256_extractf128_ps(v, 1));
+  const __m128 s64 = _mm_add_ps(s, _mm_movehdup_ps(s));
+  return _mm_cvtss_f32(_mm_add_ss(s64, _mm_movehl_ps(s64, s64)));
+}
+
+static inline void scale_min_k4(int j, const uint8_t* sc, uint8_t* s, uint8_t* m) {   /* src/gguf_kernels.rs:640-648 */
+  if (j < 4) { *s = sc[j] & 63; *m = sc[j + 4] & 63; }
+  else { *s = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4); *m = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4); }
+}
+
+static void matvec_q4_k(const uint8_t* w, const int16_t* a, const float* as, const int32_t* asum, int n, int k, float* out) {
+  const int bpr = k / 256, row_bytes = bpr * 144;
+  const __m128i m0f = _mm_set1_epi8(0x0F);
+  for (int row = 0; row < n; ++row) {
+    const uint8_t* rd = w + (size_t)row * row_bytes;
+    __m256 facc = _mm256_setzero_ps();
+    float corr = 0.f;
+    for (int b = 0; b < bpr; ++b) {
+      const uint8_t* blk = rd + b * 144;
+      const float d = f16_to_f32(blk), dmin = f16_to_f32(blk + 2);
+      for (int j = 0; j < 4; ++j) {
+        uint8_t scl, mnl, sch, mnh;
+        scale_min_k4(2 * j, blk + 4, &scl, &mnl);
+        scale_min_k4(2 * j + 1, blk + 4, &sch, &mnh);
+        const uint8_t* qs = blk + 16 + j * 32;
+        const int gl = b * 8 + 2 * j, gh = gl + 1, ab = b * 256 + j * 64;
+        const __m128i r0 = _mm_loadu_si128((const __m128i*)qs), r1 = _mm_loadu_si128((const __m128i*)(qs + 16));
+        const __m128i l0 = _mm_and_si128(r0, m0f), l1 = _mm_and_si128(r1, m0f);
+        const __m128i h0 = _mm_and_si128(_mm_srli_epi16(r0, 4), m0f), h1 = _mm_and_si128(_mm_srli_epi16(r1, 4), m0f);
+        __m256i il = _mm256_madd_epi16(_mm256_cvtepu8_epi16(l0), _mm256_loadu_si256((const __m256i*)(a + ab)));
+        il = _mm256_add_epi32(il, _mm256_madd_epi16(_mm256_cvtepu8_epi16(l1), _mm256_loadu_si256((const __m256i*)(a + ab + 16))));
+        facc = _mm256_fmadd_ps(_mm256_cvtepi32_ps(il), _mm256_set1_ps(d * (float)scl * as[gl]), facc);
+        corr += dmin * (float)mnl * as[gl] * (float)asum[gl];
+        __m256i ih = _mm256_madd_epi16(_mm256_cvtepu8_epi16(h0), _mm256_loadu_si256((const __m256i*)(a + ab + 32)));
+        ih = _mm256_add_epi32(ih, _mm256_madd_epi16(_mm256_cvtepu8_epi16(h1), _mm256_loadu_si256((const __m256i*)(a + ab + 48))));
+        facc = _mm256_fmadd_ps(_mm256_cvtepi32_ps(ih), _mm256_set1_ps(d * (float)sch * as[gh]), facc);
+        corr += dmin * (float)mnh * as[gh] * (float)asum[gh];
+      }
+    }
+    out[row] = hsum_avx(facc) - corr;
+  }
+}
+
+static void matvec_q8_0(const uint8_t* w, const int16_t* a, const float* as, int n, int k, float* out) {
+  const int bpr = k / 32, row_bytes = bpr * 34;
+  for (int row = 0; row < n; ++row) {
+    const uint8_t* rd = w + (size_t)row * row_bytes;
+    __m256 facc = _mm256_setzero_ps();
+    for (int b = 0; b < bpr; ++b) {
+      const uint8_t* blk = rd + b * 34;
+      const float comb = f16_to_f32(blk) * as[b];
+      __m256i ia = _mm256_madd_epi16(_mm256_cvtepi8_epi16(_mm_loadu_si128((const __m128i*)(blk + 2))),
+                                     _mm256_loadu_si256((const __m256i*)(a + b * 32)));
+      ia = _mm256_add_epi32(ia, _mm256_madd_epi16(_mm256_cvtepi8_epi16(_mm_loadu_si128((const __m128i*)(blk + 18))),
+                                                  _mm256_loadu_si256((const __m256i*)(a + b * 32 + 16))));
+      facc = _mm256_fmadd_ps(_mm256_cvtepi32_ps(ia), _mm256_set1_ps(comb), facc);
+    }
+    out[row] = hsum_avx(facc);
+  }
+}
+
+static int gguf_row_bytes(int type, int k) { return type == 8 ? k / 32 * 34 : (type == 12 ? k / 256 * 144 : -1); }
+
+static void gguf_matvec(int type, const uint8_t* w, const int16_t* a, const float* as, const int32_t* asum, int n, int k, float* out) {
+  if (type == 8) matvec_q8_0(w, a, as, n, k, out);
+  else matvec_q4_k(w, a, as, asum, n, k, out);
+}
+
+/*
+ * gate/up: [E][I][row_bytes(t13, H)], down: [E][H][row_bytes(t2, I)] raw GGUF blocks.  Tokens sequentially; per token the
+ * selected experts run in parallel (one task each, rayon par_iter in the reference), then out = sum_i w_i * expert_i in
+ * expert order.  ids < 0 skipped.  Returns 0, or -1 for an unsupported type.
+ */
+int kcpu_moe_forward_gguf(const uint8_t* gate, const uint8_t* up, const uint8_t* down, int t13, int t2, int E, int H, int I,
+                          const uint16_t* x_bf16, const int32_t* ids, const float* wts, int M, int topk, float* out,
+                          int nthreads) {
+  (void)E;
+  const int rb13 = gguf_row_bytes(t13, H), rb2 = gguf_row_bytes(t2, I);
+  if (rb13 < 0 || rb2 < 0 || H % 32 || I % 32) return -1;
+  const size_t gu_e = (size_t)I * rb13, dn_e = (size_t)H * rb2;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  float* xf = (float*)malloc(sizeof(float) * H);
+  int16_t* xa = (int16_t*)malloc(sizeof(int16_t) * H);
+  float* xs = (float*)malloc(sizeof(float) * (H / 32));
+  int32_t* xsum = (int32_t*)malloc(sizeof(int32_t) * (H / 32));
+  float* go = (float*)malloc(sizeof(float) * (size_t)topk * 2 * I);       /* gate_out | up_out -> hidden (in place) */
+  int16_t* ha = (int16_t*)malloc(sizeof(int16_t) * (size_t)topk * I);
+  float* hs = (float*)malloc(sizeof(float) * (size_t)topk * (I / 32));
+  int32_t* hsum = (int32_t*)malloc(sizeof(int32_t) * (size_t)topk * (I / 32));
+  float* eo = (float*)malloc(sizeof(float) * (size_t)topk * H);
+#pragma omp parallel
+  for (int m = 0; m < M; ++m) {
+#pragma omp single
+    {
+      for (int i = 0; i < H; ++i) xf[i] = bf16_to_f32(x_bf16[(size_t)m * H + i]);
+      quant_act_i16_g32(xf, H, xa, xs, xsum);
+    }
+    const int32_t* id = ids + (size_t)m * topk;
+#pragma omp for schedule(dynamic, 1)
+    for (int j = 0; j < topk; ++j) {
+      const int e = id[j];
+      if (e < 0) continue;
+      float* g = go + (size_t)j * 2 * I;
+      float* u = g + I;
+      gguf_matvec(t13, gate + e * gu_e, xa, xs, xsum, I, H, g);
+      gguf_matvec(t13, up + e * gu_e, xa, xs, xsum, I, H, u);
+      for (int i = 0; i < I; ++i) g[i] = g[i] / (1.0f + expf(-g[i])) * u[i];
+      quant_act_i16_g32(g, I, ha + (size_t)j * I, hs + (size_t)j * (I / 32), hsum + (size_t)j * (I / 32));
+      gguf_matvec(t2, down + e * dn_e, ha + (size_t)j * I, hs + (size_t)j * (I / 32), hsum + (size_t)j * (I / 32), H, I,
+                  eo + (size_t)j * H);
+    }
+#pragma omp for schedule(static)
+    for (int h = 0; h < H; ++h) {
+      float s = 0.f;
+      for (int j = 0; j < topk; ++j)
+        if (id[j] >= 0) s += wts[(size_t)m * topk + j] * eo[(size_t)j * H + h];
+      out[(size_t)m * H + h] = s;
+    }
+  }
+  free(xf); free(xa); free(xs); free(xsum); free(go); free(ha); free(hs); free(hsum); free(eo);
+  return 0;
+}
+
 int kcpu_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
