@@ -43,6 +43,13 @@ extern "C" {
 #define KB2_FMT_INT8_G128 1 /* Krasis symmetric INT8, group 128 (src/weights/marlin.rs:65-114)  */
 #define KB2_FMT_GGUF_Q8_0 2 /* native GGUF Q8_0 blocks (src/gguf.rs:574-593), losslessly re-tiled */
 #define KB2_FMT_GGUF_Q4_K 3 /* native GGUF Q4_K super-blocks (src/gguf.rs:681-738), losslessly re-tiled */
+/* The remaining expert types of real GGUF files (Q4_K_M pairs Q4_K gate/up with Q6_K down; 32-element fallbacks when K is not
+ * a multiple of 256).  Decoded at load time — losslessly: same values, same single f32 rounding as
+ * src/gguf.rs — into int8 codes + one (a, b) f32 pair per 16 elements, w = fma(a, code, -b) inside the grouped GEMM. */
+#define KB2_FMT_GGUF_Q6_K 4 /* src/gguf.rs:813-866 (scale index as in src/gguf_kernels.rs:594-635 / ggml) */
+#define KB2_FMT_GGUF_Q5_K 5 /* src/gguf.rs:740-811 */
+#define KB2_FMT_GGUF_Q5_0 6 /* src/gguf.rs:599-633 */
+#define KB2_FMT_GGUF_Q4_0 7 /* src/gguf.rs:635-664 */
 
 typedef struct kb2_engine kb2_engine;
 

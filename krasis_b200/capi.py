@@ -10,6 +10,11 @@ LIB_PATH = os.path.join(HERE, "_lib", "libkrasis_b200.so")
 KB2_OK, KB2_ERR_STATE, KB2_ERR_VALUE, KB2_ERR_CUDA = 0, 1, 2, 3
 SCORE_SOFTMAX, SCORE_SIGMOID, SCORE_TOPK_SOFTMAX = 0, 1, 2
 FMT_INT4_G128, FMT_INT8_G128, FMT_GGUF_Q8_0, FMT_GGUF_Q4_K = 0, 1, 2, 3
+FMT_GGUF_Q6_K, FMT_GGUF_Q5_K, FMT_GGUF_Q5_0, FMT_GGUF_Q4_0 = 4, 5, 6, 7
+GGUF_FORMATS = {"Q8_0": FMT_GGUF_Q8_0, "Q4_K": FMT_GGUF_Q4_K, "Q6_K": FMT_GGUF_Q6_K, "Q5_K": FMT_GGUF_Q5_K, "Q5_0": FMT_GGUF_Q5_0,
+                "Q4_0": FMT_GGUF_Q4_0}
+GGUF_ROW_BYTES = {FMT_GGUF_Q8_0: lambda k: k // 32 * 34, FMT_GGUF_Q4_K: lambda k: k // 256 * 144, FMT_GGUF_Q6_K: lambda k: k // 256 * 210,
+                  FMT_GGUF_Q5_K: lambda k: k // 256 * 176, FMT_GGUF_Q5_0: lambda k: k // 32 * 22, FMT_GGUF_Q4_0: lambda k: k // 32 * 18}
 
 
 class Config(C.Structure):

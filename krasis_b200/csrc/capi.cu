@@ -173,10 +173,22 @@ static size_t blob_bytes(int fmt) {
     case KB2_FMT_INT8_G128: return kInt8TileBytes;
     case KB2_FMT_GGUF_Q8_0: return kQ8_0TileBytes;
     case KB2_FMT_GGUF_Q4_K: return kQ4KTileBytes;
+    case KB2_FMT_GGUF_Q6_K: case KB2_FMT_GGUF_Q5_K: case KB2_FMT_GGUF_Q5_0: case KB2_FMT_GGUF_Q4_0: return kAffine8TileBytes;
   }
   return 0;
 }
-static size_t gguf_row_bytes(int fmt, size_t k) { return fmt == KB2_FMT_GGUF_Q8_0 ? k / 32 * 34 : k / 256 * 144; }
+static size_t gguf_row_bytes(int fmt, size_t k) {      // src/gguf.rs:56-85
+  switch (fmt) {
+    case KB2_FMT_GGUF_Q8_0: return k / 32 * 34;
+    case KB2_FMT_GGUF_Q4_K: return k / 256 * 144;
+    case KB2_FMT_GGUF_Q6_K: return k / 256 * 210;
+    case KB2_FMT_GGUF_Q5_K: return k / 256 * 176;
+    case KB2_FMT_GGUF_Q5_0: return k / 32 * 22;
+    case KB2_FMT_GGUF_Q4_0: return k / 32 * 18;
+  }
+  return 0;
+}
+static bool gguf_needs_k256(int fmt) { return fmt == KB2_FMT_GGUF_Q4_K || fmt == KB2_FMT_GGUF_Q6_K || fmt == KB2_FMT_GGUF_Q5_K; }
 static bool has_scale_tiles(int fmt) { return fmt == KB2_FMT_INT4_G128 || fmt == KB2_FMT_INT8_G128; }
 
 static size_t tiled_bytes(const kb2_engine* e, int which) {
@@ -204,13 +216,13 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   if (c->num_ranks < 1 || c->rank < 0 || c->rank >= c->num_ranks) return fail(KB2_ERR_VALUE, "bad rank %d/%d", c->rank, c->num_ranks);
   if (c->n_routed_experts < c->num_ranks) return fail(KB2_ERR_VALUE, "fewer experts than ranks");
   if (c->num_experts_per_tok < 1 || c->num_experts_per_tok > 32) return fail(KB2_ERR_VALUE, "top-k must be in [1,32]");
-  if (c->weight_format < KB2_FMT_INT4_G128 || c->weight_format > KB2_FMT_GGUF_Q4_K)
+  if (c->weight_format < KB2_FMT_INT4_G128 || c->weight_format > KB2_FMT_GGUF_Q4_0)
     return fail(KB2_ERR_VALUE, "unknown weight_format %d", c->weight_format);
-  if (c->w2_weight_format > KB2_FMT_GGUF_Q4_K) return fail(KB2_ERR_VALUE, "unknown w2_weight_format %d", c->w2_weight_format);
+  if (c->w2_weight_format > KB2_FMT_GGUF_Q4_0) return fail(KB2_ERR_VALUE, "unknown w2_weight_format %d", c->w2_weight_format);
   {
     const int f2 = c->w2_weight_format >= 0 ? c->w2_weight_format : c->weight_format;
-    if (c->weight_format == KB2_FMT_GGUF_Q4_K && c->hidden_size % 256) return fail(KB2_ERR_VALUE, "Q4_K gate/up needs hidden_size %% 256 == 0");
-    if (f2 == KB2_FMT_GGUF_Q4_K && c->moe_intermediate_size % 256) return fail(KB2_ERR_VALUE, "Q4_K down needs moe_intermediate_size %% 256 == 0");
+    if (gguf_needs_k256(c->weight_format) && c->hidden_size % 256) return fail(KB2_ERR_VALUE, "K-quant gate/up needs hidden_size %% 256 == 0");
+    if (gguf_needs_k256(f2) && c->moe_intermediate_size % 256) return fail(KB2_ERR_VALUE, "K-quant down needs moe_intermediate_size %% 256 == 0 (use a 32-element type: Q8_0 / Q5_0 / Q4_0)");
   }
   if (c->max_tokens < 1 || c->num_moe_layers < 1) return fail(KB2_ERR_VALUE, "max_tokens and num_moe_layers must be >= 1");
   int ndev = 0;

@@ -72,6 +72,11 @@ struct Fmt<kFmtQ4_K> {
   static constexpr int kTileBytes = kQ4KTileBytes;
   static constexpr int kStagesW = 3;
 };
+template <>
+struct Fmt<kFmtAffine8> {
+  static constexpr int kTileBytes = kAffine8TileBytes;
+  static constexpr int kStagesW = 2;
+};
 template <int FMT>
 constexpr bool kHasScaleTiles = (FMT == kFmtInt4G128 || FMT == kFmtInt8G128);
 
@@ -277,6 +282,25 @@ __global__ void __launch_bounds__(kNumThreads, 1)
               const int b0 = (int)(int8_t)((word >> ((e & 1) * 16)) & 0xFF);
               const int b1 = (int)(int8_t)((word >> ((e & 1) * 16 + 8)) & 0xFF);
               __nv_bfloat162 v = __floats2bfloat162_rn((float)b0 * sf, (float)b1 * sf);
+              o[q * 8 + e] = *reinterpret_cast<uint32_t*>(&v);
+            }
+          }
+        } else if constexpr (FMT == kFmtAffine8) {
+          // GGUF Q6_K / Q5_K / Q5_0 / Q4_0 decoded at load time into int8 codes + (a, b) per 16 elements:
+          // w = bf16(fma(a, code, -b)) — a, b and a*code are exact in f32, so this is the reference's single f32 rounding
+          const float4 p0 = *reinterpret_cast<const float4*>(wsrc + tile * TB + kTileRows * kBlockK + t * 32);
+          const float4 p1 = *reinterpret_cast<const float4*>(wsrc + tile * TB + kTileRows * kBlockK + t * 32 + 16);
+          const float av[4] = {p0.x, p0.z, p1.x, p1.z}, bv[4] = {p0.y, p0.w, p1.y, p1.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w = *reinterpret_cast<const uint4*>(wsrc + tile * TB + q * 2048 + t * 16);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t word = ww[e >> 1];
+              const int b0 = (int)(int8_t)((word >> ((e & 1) * 16)) & 0xFF);
+              const int b1 = (int)(int8_t)((word >> ((e & 1) * 16 + 8)) & 0xFF);
+              __nv_bfloat162 v = __floats2bfloat162_rn(fmaf(av[q], (float)b0, -bv[q]), fmaf(av[q], (float)b1, -bv[q]));
               o[q * 8 + e] = *reinterpret_cast<uint32_t*>(&v);
             }
           }
@@ -510,6 +534,9 @@ cudaError_t launch_grouped_gemm(int fmt, bool gemm1, const GemmParams& p, const 
   }
   if (fmt == kFmtQ4_K) {
     return gemm1 ? launch_one<kFmtQ4_K, true>(p, tm, num_sms, stream) : launch_one<kFmtQ4_K, false>(p, tm, num_sms, stream);
+  }
+  if (fmt >= kFmtAffine8 && fmt <= kFmtQ4_0) {      // Q6_K / Q5_K / Q5_0 / Q4_0 share the decoded-affine tile kernel
+    return gemm1 ? launch_one<kFmtAffine8, true>(p, tm, num_sms, stream) : launch_one<kFmtAffine8, false>(p, tm, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

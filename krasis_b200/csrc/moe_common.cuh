@@ -50,7 +50,14 @@ enum WeightFormat : int {
   kFmtInt8G128 = 1,   // Krasis symmetric INT8, group 128
   kFmtQ8_0 = 2,       // GGUF Q8_0 blocks (fp16 d + 32 x i8), re-tiled losslessly
   kFmtQ4_K = 3,       // GGUF Q4_K super-blocks (fp16 d, dmin, 6-bit scales/mins, 4-bit quants), re-tiled losslessly
+  kFmtAffine8 = 4,    // kernel-side form of the GGUF types below: int8 codes + per-16-element (a, b) f32, w = fma(a, code, -b)
+  // API-level ids of the GGUF types decoded into kFmtAffine8 tiles at load time (lossless: same values, same single f32 rounding)
+  kFmtQ6_K = 4,       // 210 B / 256: w = (d*sc)*(q-32), sc per 16 elements            (src/gguf.rs:813-866, gguf_kernels.rs:594-635)
+  kFmtQ5_K = 5,       // 176 B / 256: w = (d*sc)*q - dmin*mn, 5-bit q                   (src/gguf.rs:740-811)
+  kFmtQ5_0 = 6,       // 22 B / 32:   w = d*(q-16)                                      (src/gguf.rs:599-633)
+  kFmtQ4_0 = 7,       // 18 B / 32:   w = d*(q-8)                                       (src/gguf.rs:635-664)
 };
+__host__ __device__ constexpr int kernel_format(int fmt) { return fmt >= kFmtAffine8 ? kFmtAffine8 : fmt; }
 
 // GGUF tile blobs are self-contained (block scales travel with the quants):
 //   Q8_0 (128 rows x 64 K): [quarter 0..3][row][16 B] int8 (8192 B) | [row][2] fp16 d of the two 32-element blocks (512 B)
@@ -59,6 +66,8 @@ enum WeightFormat : int {
 //        | [row][8 B] = fp16 d, fp16 dmin, u8 sc_lo, mn_lo, sc_hi, mn_hi (get_scale_min_k4 already applied) (1024 B)
 constexpr int kQ8_0TileBytes = kTileRows * kBlockK + kTileRows * 4;   // 8704
 constexpr int kQ4KTileBytes = kTileRows * kBlockK / 2 + kTileRows * 8; // 5120
+//   Affine8 (128 rows x 64 K): [quarter 0..3][row][16 B] int8 codes (8192 B) | [row][4 x (a f32, b f32)] one pair per 16 elements (4096 B)
+constexpr int kAffine8TileBytes = kTileRows * kBlockK + kTileRows * 32;  // 12288
 
 // One unit of grouped-GEMM work along the token axis: a run of <= kMaxChunkTokens sorted slots of one expert.
 struct ChunkDesc {

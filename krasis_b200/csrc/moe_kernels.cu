@@ -453,6 +453,55 @@ __global__ void retile_gguf_kernel(int fmt, const uint8_t* __restrict__ a, const
         blob[(k / 16) * 2048 + row * 16 + (k % 16)] = sb[2 + l];
       }
     }
+  } else if (fmt >= kFmtAffine8) {
+    // Decode one row's 64 elements of this k-block into int8 codes + (a, b) per 16 elements.  d*sc, dmin*mn are exact in
+    // f32 (fp16 x small integer), so w = fma(a, code, -b) in the GEMM reproduces the reference's single rounding.
+    uint8_t* blob = dst + (((long long)e * ntile + tile) * nkb + kb) * kAffine8TileBytes;
+    float* prm = reinterpret_cast<float*>(blob + kTileRows * kBlockK + row * 32);
+    const uint8_t* rows = from_a ? a : b;
+    auto put = [&](int k, int code) { blob[(k / 16) * 2048 + row * 16 + (k % 16)] = (uint8_t)(int8_t)code; };
+    auto f16 = [](const uint8_t* p) { return __half2float(__ushort_as_half((unsigned short)(p[0] | (p[1] << 8)))); };
+    if (fmt == kFmtQ6_K) {
+      const uint8_t* sb = rows + ((long long)e * rows_src + n_src) * ((long long)K / 256 * 210) + (long long)(kb / 4) * 210;
+      const float d = f16(sb + 208);
+      const int8_t* sc = reinterpret_cast<const int8_t*>(sb + 192);
+      for (int k = 0; k < 64; ++k) {
+        const int el = (kb % 4) * 64 + k, half = el / 128, r = el % 128, sub = r / 32, l = r % 32;
+        const uint8_t qlb = sb[half * 64 + (sub & 1) * 32 + l];
+        const int q4 = sub < 2 ? (qlb & 0xF) : (qlb >> 4);
+        const int q = q4 | (((sb[128 + half * 32 + l] >> (2 * sub)) & 3) << 4);
+        put(k, q - 32);
+        if (k % 16 == 0) { prm[(k / 16) * 2] = d * (float)sc[half * 8 + l / 16 + 2 * sub]; prm[(k / 16) * 2 + 1] = 0.f; }
+      }
+    } else if (fmt == kFmtQ5_K) {
+      const uint8_t* sb = rows + ((long long)e * rows_src + n_src) * ((long long)K / 256 * 176) + (long long)(kb / 4) * 176;
+      const float d = f16(sb), dmin = f16(sb + 2);
+      const int c = kb % 4;
+      for (int h = 0; h < 2; ++h) {
+        uint8_t sj, mj;
+        k4_scale_min(2 * c + h, sb + 4, sj, mj);
+        for (int l = 0; l < 32; ++l) {
+          const uint8_t qb = sb[48 + c * 32 + l];
+          const int q4 = h ? (qb >> 4) : (qb & 0xF);
+          put(h * 32 + l, q4 + 16 * ((sb[16 + l] >> (2 * c + h)) & 1));
+        }
+        for (int g = 0; g < 2; ++g) { prm[(h * 2 + g) * 2] = d * (float)sj; prm[(h * 2 + g) * 2 + 1] = dmin * (float)mj; }
+      }
+    } else {   // Q5_0 / Q4_0: two 32-element blocks per k-block
+      const int bb = fmt == kFmtQ5_0 ? 22 : 18;
+      const uint8_t* src = rows + ((long long)e * rows_src + n_src) * ((long long)K / 32 * bb) + (long long)kb * 2 * bb;
+      for (int blk = 0; blk < 2; ++blk) {
+        const uint8_t* sb = src + blk * bb;
+        const float d = f16(sb);
+        const uint8_t* qs = sb + (fmt == kFmtQ5_0 ? 6 : 2);
+        const uint32_t qh = fmt == kFmtQ5_0 ? (uint32_t)sb[2] | ((uint32_t)sb[3] << 8) | ((uint32_t)sb[4] << 16) | ((uint32_t)sb[5] << 24) : 0u;
+        for (int l = 0; l < 32; ++l) {
+          const int q4 = l < 16 ? (qs[l] & 0xF) : (qs[l - 16] >> 4);
+          put(blk * 32 + l, fmt == kFmtQ5_0 ? ((q4 | (int)(((qh >> l) & 1u) << 4)) - 16) : (q4 - 8));
+        }
+        for (int g = 0; g < 2; ++g) { prm[(blk * 2 + g) * 2] = d; prm[(blk * 2 + g) * 2 + 1] = 0.f; }
+      }
+    }
   } else {   // Q4_K
     const long long row_bytes = (long long)K / 256 * 144;
     const uint8_t* sb = (from_a ? a : b) + ((long long)e * rows_src + n_src) * row_bytes + (long long)(kb / 4) * 144;
@@ -472,7 +521,8 @@ __global__ void retile_gguf_kernel(int fmt, const uint8_t* __restrict__ a, const
 cudaError_t launch_retile_gguf(int fmt, const void* a, const void* b, int n_a, void* dst, int E, int N, int K,
                                cudaStream_t s) {
   KernelSpan ks(K_RETILE, s);
-  if (N % kTileRows || K % kBlockK || (fmt == kFmtQ4_K && K % 256) || (fmt != kFmtQ4_K && fmt != kFmtQ8_0)) return cudaErrorInvalidValue;
+  const bool k256 = fmt == kFmtQ4_K || fmt == kFmtQ6_K || fmt == kFmtQ5_K;
+  if (N % kTileRows || K % kBlockK || (k256 && K % 256) || fmt < kFmtQ8_0 || fmt > kFmtQ4_0) return cudaErrorInvalidValue;
   const long long total = (long long)E * (N / kTileRows) * (K / kBlockK) * kTileRows;
   retile_gguf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(fmt, (const uint8_t*)a, (const uint8_t*)b, n_a,
                                                                     (uint8_t*)dst, E, N, K);

@@ -79,10 +79,10 @@ class KrasisEngine:
             raise ValueError("only group_size=128 is supported (src/weights/marlin.rs:12)")
         if scoring_func not in _SCORING:
             raise ValueError(f"unknown scoring_func {scoring_func!r}")
-        gg = {"Q8_0": capi.FMT_GGUF_Q8_0, "Q4_K": capi.FMT_GGUF_Q4_K}
+        gg = capi.GGUF_FORMATS
         if gguf_gate_up_type is not None:        # gguf_native=True in KrasisEngine.load (src/moe.rs:1538): keep GGUF blocks
             if gguf_gate_up_type not in gg or (gguf_down_type or gguf_gate_up_type) not in gg:
-                raise ValueError("GGUF expert types supported on the GPU path: Q4_K, Q8_0")
+                raise ValueError(f"GGUF expert types supported on the GPU path: {sorted(gg)}")
             f13, f2 = gg[gguf_gate_up_type], gg[gguf_down_type or gguf_gate_up_type]
         else:
             f13, f2 = (capi.FMT_INT4_G128 if num_bits == 4 else capi.FMT_INT8_G128), -1
@@ -255,7 +255,7 @@ class KrasisEngine:
             raise capi.Kb2Error("engine was not created with gguf_gate_up_type")
         E = self.expert_end - self.expert_start
         H, I = self._cfg.hidden_size, self._cfg.moe_intermediate_size
-        rb = {capi.FMT_GGUF_Q8_0: lambda k: k // 32 * 34, capi.FMT_GGUF_Q4_K: lambda k: k // 256 * 144}
+        rb = capi.GGUF_ROW_BYTES
         f13 = self._cfg.weight_format
         f2 = self._cfg.w2_weight_format if self._cfg.w2_weight_format >= 0 else f13
         want = ((E, I, rb[f13](H)), (E, I, rb[f13](H)), (E, H, rb[f2](I)))

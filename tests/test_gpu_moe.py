@@ -169,13 +169,16 @@ def test_moe_forward_matches_oracle(bits, E, H, I, k, M, skew):
     assert_close_bf16(to_np(out), want)
 
 
-@pytest.mark.parametrize("gu,dn", [("Q4_K", "Q8_0"), ("Q8_0", "Q8_0"), ("Q4_K", "Q4_K")])
+@pytest.mark.parametrize("gu,dn", [("Q4_K", "Q8_0"), ("Q8_0", "Q8_0"), ("Q4_K", "Q4_K"),
+                                   ("Q4_K", "Q6_K"),      # the Q4_K_M pairing (src/weights/mod.rs:646-647)
+                                   ("Q5_K", "Q5_0"), ("Q4_0", "Q4_0"), ("Q6_K", "Q5_K")])
 def test_moe_forward_native_gguf_blocks(gu, dn):
-    """GGUF expert tensors consumed as native blocks on the GPU (north_star: Q4_K / Q8_0).  The re-tiling is lossless and
-    the in-kernel dequant is bit-exact w.r.t. src/gguf.rs (W = bf16(dequant)), so the usual MoE tolerance applies."""
+    """GGUF expert tensors consumed as native blocks on the GPU (north_star: Q4_K / Q8_0; Q6_K / Q5_K / Q5_0 / Q4_0 are decoded
+    losslessly into int8 codes + per-16 affine pairs at load time).  The in-kernel dequant reproduces src/gguf.rs's single f32
+    rounding (W = bf16(dequant)), so the usual MoE tolerance applies."""
     from krasis_b200 import KrasisEngine
     from oracle import gguf_blocks as G
-    T = {"Q4_K": G.GGML_Q4_K, "Q8_0": G.GGML_Q8_0}
+    T = {"Q4_K": G.GGML_Q4_K, "Q8_0": G.GGML_Q8_0, "Q6_K": G.GGML_Q6_K, "Q5_K": G.GGML_Q5_K, "Q5_0": G.GGML_Q5_0, "Q4_0": G.GGML_Q4_0}
     rng = np.random.default_rng(31)
     E, H, I, k, M = 6, 512, 256, 2, 230
     lay = omoe.make_gguf_layer(rng, E, H, I, gate_up_type=T[gu], down_type=T[dn])
