@@ -188,6 +188,106 @@ __global__ void __launch_bounds__(256) gdn_prep_tiled_kernel(GdnDims d, const __
   }
 }
 
+
+// Vectorised variant (dk == dv == 128, conv width 4): one warp per (token tile, head); every lane owns FOUR CONSECUTIVE
+// channels of the head, so a token row is one 8-byte load / store per lane (the kernel above issues four 2-byte ones) and
+// the conv window lives in registers.  SiLU uses ex2-based __expf / __fdividef: the f32 result differs from expf by <= 2 ulp,
+// which moves a BF16 rounding only when the value sits within 2^-22 of a rounding boundary (p ~ 6e-5 per element).
+// Rounding points are those of gdn_prep_kernel; the l2norm partial sums are grouped per lane differently (f32 addition order).
+template <int TT>
+__global__ void __launch_bounds__(256) gdn_prep_vec_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qkvz,
+                                                           const __nv_bfloat16* __restrict__ ba,
+                                                           const __nv_bfloat16* __restrict__ conv_w,
+                                                           const __nv_bfloat16* __restrict__ conv_state,
+                                                           const float* __restrict__ A_log, const float* __restrict__ dt_bias,
+                                                           __nv_bfloat16* __restrict__ qn, __nv_bfloat16* __restrict__ kn,
+                                                           __nv_bfloat16* __restrict__ vc, float* __restrict__ beta,
+                                                           float* __restrict__ g, int M, int n_tiles) {
+  constexpr int KW = 4;
+  const int lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n_units = 2 * d.nk + d.nv + 1;
+  const int tile = (int)(wg / n_units), u = (int)(wg % n_units);
+  if (tile >= n_tiles) return;
+  const int t_begin = tile * TT, t_end = min(M, t_begin + TT);
+  const int kd = d.nk * d.dk, vd = d.nv * d.dv, ld = 2 * kd + 2 * vd, r = d.nv / d.nk;
+  if (u == 2 * d.nk + d.nv) {             // gates for this token tile
+    for (int t = t_begin; t < t_end; ++t)
+      for (int h = lane; h < d.nv; h += 32) {
+        const int kh = h / r, j = h % r;
+        const float b = __bfloat162float(ba[(long long)t * d.ba_ld + kh * 2 * r + j]);
+        const float a = __bfloat162float(ba[(long long)t * d.ba_ld + kh * 2 * r + r + j]);
+        beta[(long long)t * d.nv + h] = bf16r(1.0f / (1.0f + expf(-b)));
+        const float x = a + dt_bias[h];
+        const float sp = x > 20.f ? x : log1pf(expf(x));
+        g[(long long)t * d.nv + h] = -expf(A_log[h]) * sp;
+      }
+    return;
+  }
+  const bool is_q = u < d.nk, is_k = !is_q && u < 2 * d.nk;
+  const int c0 = (is_q ? u * d.dk : (is_k ? kd + (u - d.nk) * d.dk : 2 * kd + (u - 2 * d.nk) * d.dv)) + lane * 4;   // conv channel
+  const int col0 = qkvz_col(d, c0);                                 // the 4 channels are consecutive columns of qkvz
+  float w[4][KW], hist[4][KW - 1];
+  {
+    const uint4 w01 = *reinterpret_cast<const uint4*>(conv_w + (long long)c0 * KW);          // 16 bf16 = 4 channels x 4 taps
+    const uint4 w23 = *reinterpret_cast<const uint4*>(conv_w + (long long)c0 * KW + 8);
+    const uint32_t ww[8] = {w01.x, w01.y, w01.z, w01.w, w23.x, w23.y, w23.z, w23.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      w[e][0] = __uint_as_float(ww[2 * e] << 16); w[e][1] = __uint_as_float(ww[2 * e] & 0xFFFF0000u);
+      w[e][2] = __uint_as_float(ww[2 * e + 1] << 16); w[e][3] = __uint_as_float(ww[2 * e + 1] & 0xFFFF0000u);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KW - 1; ++j) {
+    const int tt = t_begin - (KW - 1) + j;
+    if (tt >= 0) {
+      const uint2 x = *reinterpret_cast<const uint2*>(qkvz + (long long)tt * ld + col0);
+      hist[0][j] = __uint_as_float(x.x << 16); hist[1][j] = __uint_as_float(x.x & 0xFFFF0000u);
+      hist[2][j] = __uint_as_float(x.y << 16); hist[3][j] = __uint_as_float(x.y & 0xFFFF0000u);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hist[e][j] = __bfloat162float(conv_state[(long long)(c0 + e) * KW + (KW + tt)]);
+    }
+  }
+  __nv_bfloat16* dst = is_q ? qn + (long long)u * d.dk : (is_k ? kn + (long long)(u - d.nk) * d.dk : vc + (long long)(u - 2 * d.nk) * d.dv);
+  const int dst_ld = (is_q || is_k) ? kd : vd;
+  uint2 nxt = *reinterpret_cast<const uint2*>(qkvz + (long long)t_begin * ld + col0);
+  for (int t = t_begin; t < t_end; ++t) {
+    const uint2 cur = nxt;
+    if (t + 1 < t_end) nxt = *reinterpret_cast<const uint2*>(qkvz + (long long)(t + 1) * ld + col0);      // next row in flight
+    const float x[4] = {__uint_as_float(cur.x << 16), __uint_as_float(cur.x & 0xFFFF0000u), __uint_as_float(cur.y << 16),
+                        __uint_as_float(cur.y & 0xFFFF0000u)};
+    float sv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < KW - 1; ++j) acc = fmaf(w[e][j], hist[e][j], acc);
+      acc = fmaf(w[e][KW - 1], x[e], acc);
+#pragma unroll
+      for (int j = 0; j < KW - 2; ++j) hist[e][j] = hist[e][j + 1];
+      hist[e][KW - 2] = x[e];
+      const float y = bf16r(acc);
+      sv[e] = bf16r(__fdividef(y, 1.0f + __expf(-y)));
+    }
+    if (is_q || is_k) {
+      float ss = (bf16r(sv[0] * sv[0]) + bf16r(sv[1] * sv[1])) + (bf16r(sv[2] * sv[2]) + bf16r(sv[3] * sv[3]));
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = bf16r(rsqrtf(bf16r(bf16r(ss) + 1e-6f)));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sv[e] = bf16r(sv[e] * inv);
+        if (is_q) sv[e] = bf16r(sv[e] * d.scale);
+      }
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(sv[0], sv[1]), hi = __floats2bfloat162_rn(sv[2], sv[3]);
+    *reinterpret_cast<uint2*>(dst + (long long)t * dst_ld + lane * 4) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
 // new conv state = last K pre-conv inputs (older entries come from the previous state when M < K)
 __global__ void gdn_conv_state_kernel(GdnDims d, const __nv_bfloat16* __restrict__ qkvz,
                                       __nv_bfloat16* __restrict__ conv_state, int M) {
@@ -678,7 +778,50 @@ __global__ void __launch_bounds__(256, 1) gdn_chunk_scan_kernel(GdnDims d, const
   }
 }
 
-// gated RMSNorm: one warp per (token, head)
+// gated RMSNorm: one warp per (token, head) — or, for dv == 128, per (token, HP heads) with all loads issued up front
+template <int HP>
+__global__ void __launch_bounds__(256) gdn_post128_kernel(GdnDims d, const __nv_bfloat16* __restrict__ core,
+                                                          const __nv_bfloat16* __restrict__ qkvz,
+                                                          const float* __restrict__ norm_w, int M,
+                                                          __nv_bfloat16* __restrict__ out) {   // [M][nv*128]
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, groups = d.nv / HP;
+  if (wid >= (long long)M * groups) return;
+  const int t = (int)(wid / groups), h0 = (int)(wid % groups) * HP, r = d.nv / d.nk;
+  const int kd = d.nk * d.dk, vd = d.nv * 128, ld = 2 * kd + 2 * vd, G = 2 * d.dk + 2 * r * 128;
+  const int c = lane * 4;
+  uint2 xr[HP], zr[HP];
+#pragma unroll
+  for (int i = 0; i < HP; ++i) {
+    const int h = h0 + i;
+    xr[i] = *reinterpret_cast<const uint2*>(core + (long long)t * vd + h * 128 + c);
+    zr[i] = *reinterpret_cast<const uint2*>(qkvz + (long long)t * ld + (h / r) * G + 2 * d.dk + r * 128 + (h % r) * 128 + c);
+  }
+  const float4 nw = *reinterpret_cast<const float4*>(norm_w + c);
+  const float wv[4] = {nw.x, nw.y, nw.z, nw.w};
+#pragma unroll
+  for (int i = 0; i < HP; ++i) {
+    const float x[4] = {__uint_as_float(xr[i].x << 16), __uint_as_float(xr[i].x & 0xFFFF0000u), __uint_as_float(xr[i].y << 16),
+                        __uint_as_float(xr[i].y & 0xFFFF0000u)};
+    const float z[4] = {__uint_as_float(zr[i].x << 16), __uint_as_float(zr[i].x & 0xFFFF0000u), __uint_as_float(zr[i].y << 16),
+                        __uint_as_float(zr[i].y & 0xFFFF0000u)};
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = rsqrtf(ss / 128.f + d.eps);
+    float o4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xn = bf16r(wv[j] * (x[j] * inv));
+      const float sz = bf16r(__fdividef(z[j], 1.0f + __expf(-z[j])));
+      o4[j] = xn * sz;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(o4[0], o4[1]), hi = __floats2bfloat162_rn(o4[2], o4[3]);
+    *reinterpret_cast<uint2*>(out + (long long)t * vd + (h0 + i) * 128 + c) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
 __global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const __nv_bfloat16* __restrict__ core,
                                                        const __nv_bfloat16* __restrict__ qkvz,
                                                        const float* __restrict__ norm_w, int M,
@@ -688,32 +831,6 @@ __global__ void __launch_bounds__(256) gdn_post_kernel(GdnDims d, const __nv_bfl
   const int t = wid / d.nv, h = wid % d.nv, r = d.nv / d.nk;
   const int kd = d.nk * d.dk, vd = d.nv * d.dv, ld = 2 * kd + 2 * vd, G = 2 * d.dk + 2 * r * d.dv;
   const int zcol = (h / r) * G + 2 * d.dk + r * d.dv + (h % r) * d.dv;
-  if (d.dv == 128) {                      // 4 contiguous elements per lane: 8-byte loads / stores
-    const int c = lane * 4;
-    const uint2 xr = *reinterpret_cast<const uint2*>(core + (long long)t * vd + h * d.dv + c);
-    const uint2 zr = *reinterpret_cast<const uint2*>(qkvz + (long long)t * ld + zcol + c);
-    const float4 nw = *reinterpret_cast<const float4*>(norm_w + c);
-    const float x[4] = {__uint_as_float(xr.x << 16), __uint_as_float(xr.x & 0xFFFF0000u), __uint_as_float(xr.y << 16),
-                        __uint_as_float(xr.y & 0xFFFF0000u)};
-    const float z[4] = {__uint_as_float(zr.x << 16), __uint_as_float(zr.x & 0xFFFF0000u), __uint_as_float(zr.y << 16),
-                        __uint_as_float(zr.y & 0xFFFF0000u)};
-    const float wv[4] = {nw.x, nw.y, nw.z, nw.w};
-    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = rsqrtf(ss / d.dv + d.eps);
-    float o4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float xn = bf16r(wv[i] * (x[i] * inv));
-      const float sz = bf16r(z[i] / (1.0f + expf(-z[i])));
-      o4[i] = xn * sz;
-    }
-    __nv_bfloat162 lo = __floats2bfloat162_rn(o4[0], o4[1]), hi = __floats2bfloat162_rn(o4[2], o4[3]);
-    *reinterpret_cast<uint2*>(out + (long long)t * vd + h * d.dv + c) =
-        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-    return;
-  }
   float ss = 0.f;
   for (int c = lane; c < d.dv; c += 32) {
     const float x = __bfloat162float(core[(long long)t * vd + h * d.dv + c]);          // core_attn_out.to(bf16), done by the scan
@@ -744,10 +861,24 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
                                cudaStream_t s);
 
 // KB2_GDN_LEGACY=1 keeps the mma.sync scan for dk == dv == 128 too (A/B comparison in tests; never set in production)
-static bool gdn_use_tc(const GdnDims& d) {
-  const char* e = getenv("KB2_GDN_LEGACY");            // read per call so one test process can run both paths
-  return !(e && e[0] == '1') && d.dk == 128 && d.dv == 128;
+static void launch_gdn_post(const GdnDims& d, const void* core, const void* qkvz, const float* norm_w, int M, void* out,
+                            cudaStream_t s) {
+  if (d.dv == 128 && d.nv % 4 == 0) {
+    const long long nw = (long long)M * (d.nv / 4);
+    gdn_post128_kernel<4><<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, (const __nv_bfloat16*)core, (const __nv_bfloat16*)qkvz,
+                                                                           norm_w, M, (__nv_bfloat16*)out);
+    return;
+  }
+  const long long nw = (long long)M * d.nv;
+  gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, (const __nv_bfloat16*)core, (const __nv_bfloat16*)qkvz, norm_w, M,
+                                                                  (__nv_bfloat16*)out);
 }
+
+static bool gdn_legacy_env() {
+  const char* e = getenv("KB2_GDN_LEGACY");            // read per call so one test process can run both paths
+  return e && e[0] == '1';
+}
+static bool gdn_use_tc(const GdnDims& d) { return !gdn_legacy_env() && d.dk == 128 && d.dv == 128; }
 
 cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, const void* conv_w, void* conv_state,
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
@@ -767,7 +898,15 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
     once.mark(dev);
   }
   { KernelSpan ks(K_GDN_PREP, s);
-  if (d.dk == 128 && d.dv == 128 && d.K == 4) {
+  if (d.dk == 128 && d.dv == 128 && d.K == 4 && !gdn_legacy_env()) {
+    constexpr int TT = 64;
+    const int n_tiles = (M + TT - 1) / TT;
+    const long long warps = (long long)n_tiles * (2 * d.nk + d.nv + 1);
+    gdn_prep_vec_kernel<TT><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(
+        d, (const __nv_bfloat16*)qkvz, (const __nv_bfloat16*)ba, (const __nv_bfloat16*)conv_w,
+        (const __nv_bfloat16*)conv_state, A_log, dt_bias, (__nv_bfloat16*)qn, (__nv_bfloat16*)kn, (__nv_bfloat16*)vc, beta, g,
+        M, n_tiles);
+  } else if (d.dk == 128 && d.dv == 128 && d.K == 4) {
     const int n_tiles = (M + 31) / 32;
     const long long warps = (long long)n_tiles * (2 * d.nk + d.nv + 1);
     gdn_prep_tiled_kernel<4, 4><<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(
@@ -792,8 +931,7 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
     cudaError_t e = launch_gdn_scan_tc(qn, kn, kcd, intra, vcorr, gcum, rec_state, core, M, n_chunks, d.nk, d.nv, s);
     if (e != cudaSuccess) return e; }
     KernelSpan ks(K_GDN_POST, s);
-    gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, (const __nv_bfloat16*)core, (const __nv_bfloat16*)qkvz, norm_w, M,
-                                                                    (__nv_bfloat16*)normed_out);
+    launch_gdn_post(d, core, qkvz, norm_w, M, normed_out, s);
     return cudaGetLastError();
   }
   { KernelSpan ks(K_GDN_PREPARE, s);
@@ -810,8 +948,7 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
   if (sv == 32) KB2_SCAN(32); else if (sv == 16) KB2_SCAN(16); else KB2_SCAN(8); }
 #undef KB2_SCAN
   KernelSpan ks(K_GDN_POST, s);
-  gdn_post_kernel<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, s>>>(d, (const __nv_bfloat16*)core, (const __nv_bfloat16*)qkvz, norm_w, M,
-                                                                  (__nv_bfloat16*)normed_out);
+  launch_gdn_post(d, core, qkvz, norm_w, M, normed_out, s);
   return cudaGetLastError();
 }
 

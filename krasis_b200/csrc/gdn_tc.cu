@@ -23,6 +23,8 @@
 // Warps 0-3: CUDA-core work, one thread per TMEM lane; warp 4: TMA producer; warp 5: MMA issuer.  2-stage operand ring.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "moe_common.cuh"
 #include "ptx.cuh"
 
@@ -34,6 +36,7 @@ constexpr int kTC = 64;            // chunk length (linear_attention.py:702)
 constexpr int kTSV = 32;           // dv slice per CTA
 constexpr int kTD = 128;           // dk == dv
 constexpr int kTThreads = 192;
+constexpr bool kDefaultSplit = false;   // chained accumulators (measured r02a); flip after comparing with KB2_GDN_SCAN_SPLIT=1
 constexpr int kVcLd = 36;          // padded row of the vcorr slice (floats): conflict-free float4 rows
 
 // per-stage byte offsets
@@ -103,8 +106,12 @@ struct GdnTcParams {
   float* state;              // [nv][dk][dv] in/out
   __nv_bfloat16* core_out;   // [M][nv*dv]
   int M, n_chunks, nv, nk;
+  long long* trace;          // optional (tests / tuning): clock64 stamps of CTA (0,0), chunks [8, 16): [chunk][16]
 };
 
+// SPLIT: every pass of a hi/lo product accumulates into its OWN TMEM columns (the CUDA cores add the partial results when
+// they read them back) instead of chaining all passes on one accumulator: shorter dependent tcgen05.mma chains, more LDTM.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kTThreads, 1)
     gdn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,12 +141,17 @@ __global__ void __launch_bounds__(kTThreads, 1)
     mbar_init(g3_done, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_ptr_smem, 128);
+  if (warp == 4) tmem_alloc(tmem_ptr_smem, SPLIT ? 256 : 128);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
   constexpr uint32_t kColD1 = 0, kColD1b = 32, kColD2 = 64, kColD3 = 96;
+  constexpr uint32_t kColD1c = 128, kColD2b = 160, kColD3b = 192;       // SPLIT: second-pass accumulators
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  auto stamp = [&](int c, int slot) {
+    if (tracing && c >= 8 && c < 16) p.trace[(c - 8) * 16 + slot] = clock64();
+  };
 
   if (warp == 4) {
     // ------------------------------------------------------------------ producer
@@ -183,25 +195,28 @@ __global__ void __launch_bounds__(kTThreads, 1)
         mbar_wait(&full[st], ph);
         mbar_wait(s_ready, cp);
         tc_fence_after_sync();
+        stamp(c, 0);
         // G1: [kcd_hi ; q] (S_hi + S_lo) -> D1 ;  [kcd_lo ; *] S_hi -> D1b
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a0 = sb + (pass < 2 ? kOffA1 : kOffA1L);
           const uint32_t a_chunk = pass < 2 ? 16384u : 8192u;
           const uint32_t b0 = pass == 1 ? slo : sh;
-          const uint32_t dcol = pass < 2 ? kColD1 : kColD1b;
+          const uint32_t dcol = pass == 2 ? kColD1b : ((SPLIT && pass == 1) ? kColD1c : kColD1);
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
             const uint64_t ad = umma_desc_k_sw128(a0 + ch * a_chunk);
             const uint64_t bd = umma_desc_k_sw128(b0 + ch * 4096);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(tmem_base + dcol, ad + 2 * ks, bd + 2 * ks, id_k, (pass == 1 || ch > 0 || ks > 0) ? 1u : 0u);
+              umma_bf16(tmem_base + dcol, ad + 2 * ks, bd + 2 * ks, id_k, ((!SPLIT && pass == 1) || ch > 0 || ks > 0) ? 1u : 0u);
           }
         }
         umma_commit(g1_done);
+        stamp(c, 1);
         mbar_wait(v_ready, cp);
         tc_fence_after_sync();
+        stamp(c, 2);
         // G2: dS = k^T (vdec_hi + vdec_lo)
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
@@ -209,7 +224,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
-            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn, (pass > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(tmem_base + ((SPLIT && pass) ? kColD2b : kColD2), ad, bd + 2 * ks, id_amn, ((!SPLIT && pass > 0) || ks > 0) ? 1u : 0u);
           }
         }
         umma_commit(g2_done);
@@ -220,10 +235,11 @@ __global__ void __launch_bounds__(kTThreads, 1)
           const uint64_t bd = umma_desc_k_sw128(pass ? vl : vh);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem_base + kColD3, ad + 2 * ks, bd + 2 * ks, id_k, (pass > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16(tmem_base + ((SPLIT && pass) ? kColD3b : kColD3), ad + 2 * ks, bd + 2 * ks, id_k, ((!SPLIT && pass > 0) || ks > 0) ? 1u : 0u);
         }
         umma_commit(g3_done);
         umma_commit(&empty[st]);
+        stamp(c, 3);
       }
     }
     __syncwarp();
@@ -268,10 +284,18 @@ __global__ void __launch_bounds__(kTThreads, 1)
       for (int j = 0; j < kTSV; ++j) it[j] = 0.f;
       mbar_wait(g1_done, cp);
       tc_fence_after_sync();
+      if (tid == 0) stamp(c, 4);
       if (tid < 64) {
         uint32_t a[32], b[32];
         tmem_ld32(lane_addr + kColD1, a);
         tmem_ld32(lane_addr + kColD1b, b);
+        if constexpr (SPLIT) {
+          uint32_t cc[32];
+          tmem_ld32(lane_addr + kColD1c, cc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
+        }
         tmem_ld_wait();
         const float dec = expf(g_last - g_i);
 #pragma unroll
@@ -295,6 +319,13 @@ __global__ void __launch_bounds__(kTThreads, 1)
       } else {
         uint32_t a[32];
         tmem_ld32(lane_addr + kColD1, a);
+        if constexpr (SPLIT) {
+          uint32_t cc[32];
+          tmem_ld32(lane_addr + kColD1c, cc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
+        }
         tmem_ld_wait();
         const float eg = expf(g_i);
 #pragma unroll
@@ -303,12 +334,21 @@ __global__ void __launch_bounds__(kTThreads, 1)
       tc_fence_before_sync();
       fence_proxy_async_smem();
       mbar_arrive(v_ready);
+      if (tid == 0) stamp(c, 5);
       // state update: S = e^{g_last} S + dS
       mbar_wait(g2_done, cp);
       tc_fence_after_sync();
+      if (tid == 0) stamp(c, 6);
       {
         uint32_t a[32];
         tmem_ld32(lane_addr + kColD2, a);
+        if constexpr (SPLIT) {
+          uint32_t cc[32];
+          tmem_ld32(lane_addr + kColD2b, cc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < kTSV; ++j) s[j] = fmaf(d_last, s[j], __uint_as_float(a[j]));
@@ -319,12 +359,21 @@ __global__ void __launch_bounds__(kTThreads, 1)
         fence_proxy_async_smem();
         mbar_arrive(s_ready);
       }
+      if (tid == 0) stamp(c, 7);
       // output rows of this chunk
       mbar_wait(g3_done, cp);
       tc_fence_after_sync();
+      if (tid == 0) stamp(c, 8);
       {
         uint32_t a[32];
         tmem_ld32(lane_addr + kColD3, a);
+        if constexpr (SPLIT) {
+          uint32_t cc[32];
+          tmem_ld32(lane_addr + kColD3b, cc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
+        }
         tmem_ld_wait();
         if (tid < 64) {
 #pragma unroll
@@ -356,6 +405,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         }
       }
       tc_fence_before_sync();
+      if (tid == 0) stamp(c, 9);
     }
     {
       float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
@@ -365,7 +415,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 128);
+  if (warp == 4) tmem_dealloc(tmem_base, SPLIT ? 256 : 128);
 }
 
 // qn, kn: [M][nk*128] bf16 (prep kernel outputs).  The prepared operands are in the layouts documented in GdnTcParams.
@@ -374,17 +424,25 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
                                cudaStream_t s) {
   static PerDeviceOnce once;
   if (const int dev = once.pending(); dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    cudaError_t e = cudaFuncSetAttribute(gdn_scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
+  // tuning knobs read per call (tests / profiling only): KB2_GDN_SCAN_SPLIT=0|1 picks the accumulator scheme,
+  // KB2_GDN_SCAN_TRACE=<device pointer> receives clock64 stamps of CTA (0,0)
+  const char* ev = getenv("KB2_GDN_SCAN_SPLIT");
+  const bool split = ev ? ev[0] == '1' : kDefaultSplit;
+  const char* tv = getenv("KB2_GDN_SCAN_TRACE");
+  long long* trace = tv ? reinterpret_cast<long long*>(strtoull(tv, nullptr, 0)) : nullptr;
   alignas(64) CUtensorMap tq, tk;
   cudaError_t e = make_tmap_bf16_rows(&tq, qn, M, (long long)nk * kTD, kTC);
   if (e != cudaSuccess) return e;
   e = make_tmap_bf16_rows(&tk, kn, M, (long long)nk * kTD, kTC);
   if (e != cudaSuccess) return e;
-  GdnTcParams p{(const uint8_t*)kcd_img, (const uint8_t*)intra_img, vcorr, gcum, state, (__nv_bfloat16*)core_out, M, n_chunks, nv, nk};
-  gdn_scan_tc_kernel<<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
+  GdnTcParams p{(const uint8_t*)kcd_img, (const uint8_t*)intra_img, vcorr, gcum, state, (__nv_bfloat16*)core_out, M, n_chunks, nv, nk, trace};
+  if (split) gdn_scan_tc_kernel<true><<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
+  else gdn_scan_tc_kernel<false><<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
   return cudaGetLastError();
 }
 

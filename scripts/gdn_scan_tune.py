@@ -1,0 +1,52 @@
+"""Tuning harness for the tcgen05 GDN chunk scan (GPU): per-kernel times of one QCN-geometry GDN layer at 8192 tokens for
+the accumulator schemes (KB2_GDN_SCAN_SPLIT=0/1) and a clock64 timeline of one CTA (KB2_GDN_SCAN_TRACE).
+Slots: MMA thread 0 s_ready seen, 1 G1 issued, 2 v_ready seen, 3 G2+G3 issued; core thread 0: 4 g1_done seen, 5 v tiles written,
+6 g2_done seen, 7 S tiles written, 8 g3_done seen, 9 epilogue done."""
+import os
+import sys
+import types
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from krasis_b200 import capi  # noqa: E402
+from krasis_b200.attention import GatedDeltaNetAttention  # noqa: E402
+
+torch.manual_seed(0)
+nk, nv, dk, dv, H, K, M = 16, 32, 128, 128, 256, 4, 8192
+kd, vd = nk * dk, nv * dv
+bf = torch.bfloat16
+w = dict(in_proj_qkvz=(torch.randn(2 * kd + 2 * vd, H) * 0.15).to(bf), in_proj_ba=(torch.randn(2 * nv, H) * 0.15).to(bf),
+         out_proj=(torch.randn(H, vd) * 0.05).to(bf), conv1d_weight=(torch.randn(2 * kd + vd, 1, K) * 0.5).to(bf),
+         A_log=(torch.randn(nv) * 0.5).to(bf), dt_bias=(torch.randn(nv) * 0.5).to(bf), norm_weight=(1 + 0.1 * torch.randn(dv)).to(bf))
+cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_value_heads=nv, linear_key_head_dim=dk,
+                            linear_value_head_dim=dv, linear_conv_kernel_dim=K, rms_norm_eps=1e-6)
+lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
+x = torch.randn(M, H).to(bf).cuda()
+outs = {}
+for split in ("0", "1"):
+    os.environ["KB2_GDN_SCAN_SPLIT"] = split
+    for _ in range(3):
+        lay.reset_state()
+        lay.forward(x)
+    capi.kernel_profile(True)
+    for _ in range(5):
+        lay.reset_state()
+        y = lay.forward(x)
+    prof = capi.kernel_profile_collect()
+    capi.kernel_profile(False)
+    outs[split] = y.float()
+    print(f"split={split}: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]) if n.startswith("gdn")))
+    trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
+    os.environ["KB2_GDN_SCAN_TRACE"] = str(trace.data_ptr())
+    lay.reset_state()
+    lay.forward(x)
+    torch.cuda.synchronize()
+    del os.environ["KB2_GDN_SCAN_TRACE"]
+    t = trace.cpu().view(8, 16)[:, :10]
+    base = t[:, 0:1]
+    print("  timeline (cycles since the MMA thread saw s_ready), chunks 8..15:")
+    for r in (t - base).tolist():
+        print("   ", r)
+    print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
+print("max |split0 - split1| / max:", ((outs["0"] - outs["1"]).abs().max() / outs["0"].abs().max()).item())
