@@ -37,7 +37,7 @@ def test_create_validates_shapes_like_the_reference(lib):
     bad = capi.Config(2000, 512, 64, 6, 1, 0, 0, 1, 0, 0, 1.0, 16, 0, -1)    # H not a multiple of 256
     assert lib.kb2_create(C.byref(bad), C.byref(h)) == capi.KB2_ERR_VALUE
     assert b"hidden_size" in lib.kb2_last_error()
-    bad = capi.Config(2048, 512, 64, 6, 1, 7, 0, 1, 0, 0, 1.0, 16, 0, -1)    # unknown weight format
+    bad = capi.Config(2048, 512, 64, 6, 1, 8, 0, 1, 0, 0, 1.0, 16, 0, -1)    # unknown weight format (0..7 are defined)
     assert lib.kb2_create(C.byref(bad), C.byref(h)) == capi.KB2_ERR_VALUE
     bad = capi.Config(2048, 512, 64, 6, 1, 0, 3, 2, 0, 0, 1.0, 16, 0, -1)    # rank >= num_ranks
     assert lib.kb2_create(C.byref(bad), C.byref(h)) == capi.KB2_ERR_VALUE
