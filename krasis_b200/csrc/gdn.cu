@@ -880,6 +880,20 @@ static bool gdn_legacy_env() {
 }
 static bool gdn_use_tc(const GdnDims& d) { return !gdn_legacy_env() && d.dk == 128 && d.dv == 128; }
 
+cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc, const float* beta, const float* g,
+                                  void* kcd_img, void* intra_img, float* vcorr, float* gcum, int M, int n_chunks, int nk, int nv,
+                                  int num_sms, cudaStream_t s);
+// KB2_GDN_PREPARE_MMA_SYNC=1 keeps the mma.sync chunk-prepare in front of the tcgen05 scan (A/B tests only)
+static bool gdn_prepare_mma_sync_env() {
+  const char* e = getenv("KB2_GDN_PREPARE_MMA_SYNC");
+  return e && e[0] == '1';
+}
+static int gdn_num_sms() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
 cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, const void* conv_w, void* conv_state,
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
                             void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
@@ -924,9 +938,15 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
   const long long nw = (long long)M * d.nv;
   if (gdn_use_tc(d)) {
     { KernelSpan ks(K_GDN_PREPARE, s);
-    gdn_chunk_prepare_kernel<true><<<dim3(n_chunks, d.nv), 256, gdn_prepare_smem(d), s>>>(
-        d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, (const __nv_bfloat16*)vc, beta, g, M, n_chunks, vcorr, kcd,
-        intra, gcum); }
+    if (gdn_prepare_mma_sync_env()) {
+      gdn_chunk_prepare_kernel<true><<<dim3(n_chunks, d.nv), 256, gdn_prepare_smem(d), s>>>(
+          d, (const __nv_bfloat16*)qn, (const __nv_bfloat16*)kn, (const __nv_bfloat16*)vc, beta, g, M, n_chunks, vcorr, kcd,
+          intra, gcum);
+    } else {
+      static int sms = gdn_num_sms();
+      cudaError_t e = launch_gdn_prepare_tc(qn, kn, vc, beta, g, kcd, intra, vcorr, gcum, M, n_chunks, d.nk, d.nv, sms, s);
+      if (e != cudaSuccess) return e;
+    } }
     { KernelSpan ks(K_GDN_SCAN, s);
     cudaError_t e = launch_gdn_scan_tc(qn, kn, kcd, intra, vcorr, gcum, rec_state, core, M, n_chunks, d.nk, d.nv, s);
     if (e != cudaSuccess) return e; }

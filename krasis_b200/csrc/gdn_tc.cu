@@ -418,6 +418,357 @@ __global__ void __launch_bounds__(kTThreads, 1)
   if (warp == 4) tmem_dealloc(tmem_base, SPLIT ? 256 : 128);
 }
 
+
+// ====================================================================================================================
+// Chunk prepare on tcgen05 (dk == dv == 128): everything of linear_attention.py:593-646 that does not depend on the carried
+// state, for one (value head, 64-token chunk) per loop iteration of a persistent CTA:
+//   MMA-A   [k ; q] k^T  (M=128 stacked, N=64, K=128; BF16 operands, exact products)  -> k k^T (lanes 0-63), q k^T (lanes 64-127)
+//   cores   A = -(beta_i k_i.k_j) e^{g_i-g_j} (j<i);  intra = (q_i.k_j) e^{g_i-g_j} (j<=i) -> hi/lo images to global
+//   cores   T = (I - A)^-1 by substitution on T^T (thread c owns ROW c of T, A^T rows are broadcast float4 loads)
+//   MMA-B   vcorr = [T'_hi ; T'_lo] v,  T' = T diag(beta)            (v exact BF16, consumed MN-major straight from the prep output)
+//   MMA-C   kcd   = [T''_hi ; T''_lo] k, T'' = T diag(beta e^{g})     (k tile reused MN-major)
+//   cores   hi-part lanes + lo-part lanes summed through shared memory; vcorr slices / kcd hi-lo images / gcum to global
+// The reference solves with the right-hand sides (solve_triangular); forming T explicitly and multiplying is the same linear
+// map evaluated in fp32-grade arithmetic (BF16 hi/lo pairs of T, exact BF16 v and k).
+// Warps 0-3 CUDA cores (thread = TMEM lane), warp 4 TMA producer, warp 5 MMA issuer; 2-stage input ring.
+// ====================================================================================================================
+constexpr int kPStage = 49152;                       // [k c0 8K][q c0 8K][k c1 8K][q c1 8K][v dv0-63 8K][v dv64-127 8K]
+constexpr int kPOffV = 32768;
+constexpr int kPOffAT = 2 * kPStage;                 // A^T fp32 [64][68]
+constexpr int kPLdAT = 68;
+constexpr int kPOffImg1 = kPOffAT + 64 * kPLdAT * 4; // [T'_hi 8K][T'_lo 8K]
+static_assert(kPOffImg1 % 1024 == 0, "image alignment");
+constexpr int kPOffImg2 = kPOffImg1 + 16384;         // [T''_hi][T''_lo]
+constexpr int kPLdX = 132;
+constexpr int kPOffXB = kPOffImg2 + 16384;           // exchange: lo part of vcorr rows   fp32 [64][132]
+constexpr int kPOffXC = kPOffXB + 64 * kPLdX * 4;    // exchange: hi part of kcd rows
+constexpr int kPOffSc = kPOffXC + 64 * kPLdX * 4;    // gcum[64] | beta[64] | beta*e^gcum[64] | scan scratch[4]
+constexpr int kPOffBar = kPOffSc + 1024;
+constexpr int kPSmem = kPOffBar + 128;
+static_assert(kPSmem <= 227 * 1024, "smem");
+
+struct GdnPrepParams {
+  const float* beta;         // [M][nv]
+  const float* g;            // [M][nv]
+  uint8_t* kcd_img;
+  uint8_t* intra_img;
+  float* vcorr;
+  float* gcum;
+  int M, n_chunks, nv, nk;
+};
+
+__global__ void __launch_bounds__(kTThreads, 1)
+    gdn_prepare_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                          const __grid_constant__ CUtensorMap tmap_v, GdnPrepParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPOffBar);
+  uint64_t* full = bars;           // [2]
+  uint64_t* empty = bars + 2;      // [2]
+  uint64_t* a_done = bars + 4;
+  uint64_t* img_ready = bars + 5;
+  uint64_t* bc_done = bars + 6;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_units = p.nv * p.n_chunks, r = p.nv / p.nk;
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_init(a_done, 1);
+    mbar_init(img_ready, 64);
+    mbar_init(bc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kColA = 0, kColB = 128, kColC = 256;
+
+  if (warp == 4) {
+    if (tid == 128) {
+      prefetch_tmap(&tmap_q); prefetch_tmap(&tmap_k); prefetch_tmap(&tmap_v);
+      int it = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        const int h = u / p.n_chunks, ch = u % p.n_chunks, kh = h / r;
+        uint8_t* sb = smem + st * kPStage;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], kPStage);
+        tma_load_2d(sb, &tmap_k, kh * kTD, ch * kTC, &full[st]);
+        tma_load_2d(sb + 8192, &tmap_q, kh * kTD, ch * kTC, &full[st]);
+        tma_load_2d(sb + 16384, &tmap_k, kh * kTD + 64, ch * kTC, &full[st]);
+        tma_load_2d(sb + 24576, &tmap_q, kh * kTD + 64, ch * kTC, &full[st]);
+        tma_load_2d(sb + kPOffV, &tmap_v, h * kTD, ch * kTC, &full[st]);
+        tma_load_2d(sb + kPOffV + 8192, &tmap_v, h * kTD + 64, ch * kTC, &full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (tid == 160) {
+      const uint32_t id_a = umma_idesc_bf16_m128(64);                       // A, B K-major, N = 64
+      const uint32_t id_bc = umma_idesc_bf16_m128(128) | (1u << 16);        // B MN-major, N = 128
+      const uint32_t img1 = smem_u32(smem + kPOffImg1), img2 = smem_u32(smem + kPOffImg2);
+      int it = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u, up = (uint32_t)it & 1u;
+        const uint32_t sb = smem_u32(smem + st * kPStage);
+        mbar_wait(&full[st], ph);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int chn = 0; chn < 2; ++chn) {
+          const uint64_t ad = umma_desc_k_sw128(sb + chn * 16384);          // rows 0-63 k, rows 64-127 q
+          const uint64_t bd = umma_desc_k_sw128(sb + chn * 16384);          // N = 64: the k rows only
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColA, ad + 2 * ks, bd + 2 * ks, id_a, (chn > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(a_done);
+        mbar_wait(img_ready, up);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t a1 = umma_desc_k_sw128(img1) + 2 * ks, a2 = umma_desc_k_sw128(img2) + 2 * ks;
+          umma_bf16(tmem_base + kColB, a1, tc_desc_mn_sw128(sb + kPOffV + ks * 2048, 8192, 1024), id_bc, ks > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + kColC, a2, tc_desc_mn_sw128(sb + ks * 2048, 16384, 1024), id_bc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bc_done);
+        umma_commit(&empty[st]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int i = tid & 63, lane = tid & 31;
+    float* sAT = reinterpret_cast<float*>(smem + kPOffAT);
+    float* sXB = reinterpret_cast<float*>(smem + kPOffXB);
+    float* sXC = reinterpret_cast<float*>(smem + kPOffXC);
+    float* sg = reinterpret_cast<float*>(smem + kPOffSc);
+    float* sbeta = sg + 64;
+    float* secol = sg + 128;
+    float* sscan = sg + 192;
+    auto load_gate = [&](int u, float& b, float& gg) {
+      b = 0.f; gg = 0.f;
+      if (u < n_units && tid < 64) {
+        const int h = u / p.n_chunks, t = (u % p.n_chunks) * kTC + i;
+        if (t < p.M) { b = p.beta[(long long)t * p.nv + h]; gg = p.g[(long long)t * p.nv + h]; }
+      }
+    };
+    float b_nxt, g_nxt;
+    load_gate(blockIdx.x, b_nxt, g_nxt);
+    int it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t up = (uint32_t)it & 1u;
+      const int h = u / p.n_chunks, ch = u % p.n_chunks;
+      const long long hc = (long long)h * p.n_chunks + ch;
+      const float b_i = b_nxt, g_in = g_nxt;
+      load_gate(u + gridDim.x, b_nxt, g_nxt);                      // next unit's gates are in flight during this one
+      // inclusive scan of g over the 64 tokens (warps 0, 1)
+      float gc = g_in;
+      if (tid < 64) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float v = __shfl_up_sync(0xffffffffu, gc, o);
+          if (lane >= o) gc += v;
+        }
+        if (tid == 31) sscan[0] = gc;
+      }
+      named_bar_sync(2, 128);
+      if (tid >= 32 && tid < 64) gc += sscan[0];
+      if (tid < 64) {
+        sg[i] = gc;
+        sbeta[i] = b_i;
+        secol[i] = b_i * expf(gc);
+      }
+      named_bar_sync(2, 128);
+      mbar_wait(a_done, up);
+      tc_fence_after_sync();
+      const float g_i = sg[i];
+      if (tid < 64) {                         // k k^T row i  ->  A^T
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t a[32];
+          tmem_ld32(lane_addr + kColA + half * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = half * 32 + jj;
+            if (j < i) sAT[j * kPLdAT + i] = -(__uint_as_float(a[jj]) * b_i) * expf(g_i - sg[j]);
+          }
+        }
+      } else {                                // q k^T row i  ->  intra hi/lo images (global)
+        uint8_t* img = p.intra_img + hc * 16384 + i * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t a[32];
+          tmem_ld32(lane_addr + kColA + half * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = half * 32 + q8 * 8 + 2 * e;
+              const float v0 = j <= i ? __uint_as_float(a[q8 * 8 + 2 * e]) * expf(g_i - sg[j]) : 0.f;
+              const float v1 = j + 1 <= i ? __uint_as_float(a[q8 * 8 + 2 * e + 1]) * expf(g_i - sg[j + 1]) : 0.f;
+              unsigned short h0, l0, h1, l1;
+              split_bf16(v0, h0, l0);
+              split_bf16(v1, h1, l1);
+              hw[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              lw[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            const int chunk = ((half * 4 + q8) ^ (i & 7)) << 4;
+            *reinterpret_cast<uint4*>(img + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(img + 8192 + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      named_bar_sync(2, 128);                 // A^T complete; D_A fully read
+      if (tid < 64) {
+        // row c of T = column c of X = T^T, (I - A^T) X = I by back substitution; A^T row i is read as broadcast float4
+        const int c = tid;
+        float x[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) x[j] = (j == c) ? 1.f : 0.f;
+#pragma unroll
+        for (int ii = 62; ii >= 0; --ii) {
+          float acc = x[ii];                 // 1 on the diagonal, else 0; rows ii > c stay 0 because x[j > c] = 0 ... but
+          const float* arow = sAT + ii * kPLdAT;   // A^T[ii][j] is only defined for j > ii (strictly lower part of A)
+#pragma unroll
+          for (int j4 = (ii + 1) / 4; j4 < 16; ++j4) {
+            const float4 av = *reinterpret_cast<const float4*>(arow + 4 * j4);
+            if (4 * j4 + 0 > ii) acc = fmaf(av.x, x[4 * j4 + 0], acc);
+            if (4 * j4 + 1 > ii) acc = fmaf(av.y, x[4 * j4 + 1], acc);
+            if (4 * j4 + 2 > ii) acc = fmaf(av.z, x[4 * j4 + 2], acc);
+            if (4 * j4 + 3 > ii) acc = fmaf(av.w, x[4 * j4 + 3], acc);
+          }
+          x[ii] = (ii > c) ? 0.f : acc;
+        }
+        // T' = T diag(beta), T'' = T diag(beta e^gcum) as hi/lo K-major SW128 rows
+        uint8_t* i1 = smem + kPOffImg1 + c * 128;
+        uint8_t* i2 = smem + kPOffImg2 + c * 128;
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) {
+          uint32_t h1[4], l1[4], h2[4], l2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = q8 * 8 + 2 * e;
+            unsigned short a0, b0, a1, b1;
+            split_bf16(x[j] * sbeta[j], a0, b0);
+            split_bf16(x[j + 1] * sbeta[j + 1], a1, b1);
+            h1[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
+            l1[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
+            split_bf16(x[j] * secol[j], a0, b0);
+            split_bf16(x[j + 1] * secol[j + 1], a1, b1);
+            h2[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
+            l2[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
+          }
+          const int chunk = (q8 ^ (c & 7)) << 4;
+          *reinterpret_cast<uint4*>(i1 + chunk) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+          *reinterpret_cast<uint4*>(i1 + 8192 + chunk) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+          *reinterpret_cast<uint4*>(i2 + chunk) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+          *reinterpret_cast<uint4*>(i2 + 8192 + chunk) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(img_ready);
+        p.gcum[hc * kTC + i] = g_i;
+      }
+      mbar_wait(bc_done, up);
+      tc_fence_after_sync();
+      // hand the partner its missing part: lanes 0-63 hold the hi parts, lanes 64-127 the lo parts
+      {
+        float* xdst = (tid < 64 ? sXC : sXB) + i * kPLdX;
+        const uint32_t col = tid < 64 ? kColC : kColB;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t a[32];
+          tmem_ld32(lane_addr + col + q * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(xdst + q * 32 + 4 * j4) =
+                make_float4(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1]), __uint_as_float(a[4 * j4 + 2]), __uint_as_float(a[4 * j4 + 3]));
+        }
+      }
+      named_bar_sync(2, 128);
+      if (tid < 64) {                         // vcorr row i = hi part (own lane) + lo part (partner) -> [slice][i][36]
+        const float* xsrc = sXB + i * kPLdX;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t a[32];
+          tmem_ld32(lane_addr + kColB + q * 32, a);
+          tmem_ld_wait();
+          float* dst = p.vcorr + ((hc * (kTD / kTSV) + q) * kTC + i) * kVcLd;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 o = *reinterpret_cast<const float4*>(xsrc + q * 32 + 4 * j4);
+            *reinterpret_cast<float4*>(dst + 4 * j4) =
+                make_float4(__uint_as_float(a[4 * j4]) + o.x, __uint_as_float(a[4 * j4 + 1]) + o.y, __uint_as_float(a[4 * j4 + 2]) + o.z,
+                            __uint_as_float(a[4 * j4 + 3]) + o.w);
+          }
+        }
+      } else {                                // kcd row i = hi part (partner) + lo part (own lane) -> hi/lo images
+        const float* xsrc = sXC + i * kPLdX;
+        uint8_t* img = p.kcd_img + hc * 32768 + i * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t a[32];
+          tmem_ld32(lane_addr + kColC + q * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int jj = q8 * 8 + 2 * e;
+              const float v0 = __uint_as_float(a[jj]) + xsrc[q * 32 + jj], v1 = __uint_as_float(a[jj + 1]) + xsrc[q * 32 + jj + 1];
+              unsigned short h0, l0, h1, l1;
+              split_bf16(v0, h0, l0);
+              split_bf16(v1, h1, l1);
+              hw[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              lw[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            const int k8 = q * 4 + q8;          // 8-element group along dk: chunk c = k8 / 8, 16-byte slot k8 % 8
+            const int off = (k8 >> 3) * 8192 + (((k8 & 7) ^ (i & 7)) << 4);
+            *reinterpret_cast<uint4*>(img + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(img + 16384 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc, const float* beta, const float* g,
+                                  void* kcd_img, void* intra_img, float* vcorr, float* gcum, int M, int n_chunks, int nk, int nv,
+                                  int num_sms, cudaStream_t s) {
+  static PerDeviceOnce once;
+  if (const int dev = once.pending(); dev >= 0) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_prepare_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
+    if (e != cudaSuccess) return e;
+    once.mark(dev);
+  }
+  alignas(64) CUtensorMap tq, tk, tv;
+  cudaError_t e = make_tmap_bf16_rows(&tq, qn, M, (long long)nk * kTD, kTC);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tk, kn, M, (long long)nk * kTD, kTC);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_rows(&tv, vc, M, (long long)nv * kTD, kTC);
+  if (e != cudaSuccess) return e;
+  GdnPrepParams p{beta, g, (uint8_t*)kcd_img, (uint8_t*)intra_img, vcorr, gcum, M, n_chunks, nv, nk};
+  const int n_units = nv * n_chunks;
+  gdn_prepare_tc_kernel<<<n_units < num_sms ? n_units : num_sms, kTThreads, kPSmem, s>>>(tq, tk, tv, p);
+  return cudaGetLastError();
+}
+
 // qn, kn: [M][nk*128] bf16 (prep kernel outputs).  The prepared operands are in the layouts documented in GdnTcParams.
 cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_img, const void* intra_img, const float* vcorr,
                                const float* gcum, float* state, void* core_out, int M, int n_chunks, int nk, int nv,

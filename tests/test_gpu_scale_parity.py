@@ -249,3 +249,35 @@ def test_gdn_tcgen05_scan_matches_the_mma_sync_scan(M, monkeypatch):
         assert (a - b).abs().max().item() <= 2 ** -8 * b.abs().max().item()
         assert (a == b).float().mean().item() > 0.97
     assert np.abs(res["0"][2] - res["1"][2]).max() <= 1e-4 * np.abs(res["1"][2]).max()
+
+
+@pytest.mark.parametrize("M", [200, 1500])
+def test_gdn_tcgen05_prepare_matches_the_mma_sync_prepare(M, monkeypatch):
+    """tcgen05 chunk-prepare (explicit T = (I - A)^-1, BF16 hi/lo pairs of T times exact BF16 v / k) against the mma.sync
+    prepare (blocked forward substitution on the right-hand sides), both feeding the same tcgen05 scan: fp32-grade both,
+    so the carried state agrees to 1e-4 relative and the BF16 outputs to one ulp of the maximum."""
+    from krasis_b200.attention import GatedDeltaNetAttention
+    torch.manual_seed(22)
+    nk, nv, dk, dv, H, K = 2, 4, 128, 128, 256, 4
+    kd, vd = nk * dk, nv * dv
+    bf = torch.bfloat16
+    w = dict(in_proj_qkvz=(torch.randn(2 * kd + 2 * vd, H) * 0.15).to(bf), in_proj_ba=(torch.randn(2 * nv, H) * 0.15).to(bf),
+             out_proj=(torch.randn(H, vd) * 0.05).to(bf), conv1d_weight=(torch.randn(2 * kd + vd, 1, K) * 0.5).to(bf),
+             A_log=(torch.randn(nv) * 0.5).to(bf), dt_bias=(torch.randn(nv) * 0.5).to(bf),
+             norm_weight=(1 + 0.1 * torch.randn(dv)).to(bf))
+    cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_value_heads=nv, linear_key_head_dim=dk,
+                                linear_value_head_dim=dv, linear_conv_kernel_dim=K, rms_norm_eps=1e-6)
+    x1, x2 = torch.randn(M, H).to(bf).cuda(), torch.randn(M // 2 + 3, H).to(bf).cuda()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KB2_GDN_PREPARE_MMA_SYNC", mode)
+        lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
+        y1 = lay.forward(x1, is_decode=False).float().cpu()
+        y2 = lay.forward(x2, is_decode=False).float().cpu()
+        _, rec = lay.state()
+        res[mode] = (y1, y2, rec)
+    for a, b in zip(res["0"][:2], res["1"][:2]):
+        assert torch.isfinite(a).all()
+        assert (a - b).abs().max().item() <= 2 ** -8 * b.abs().max().item()
+        assert (a == b).float().mean().item() > 0.97
+    assert np.abs(res["0"][2] - res["1"][2]).max() <= 1e-4 * np.abs(res["1"][2]).max()
