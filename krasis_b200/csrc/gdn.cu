@@ -883,10 +883,13 @@ static bool gdn_use_tc(const GdnDims& d) { return !gdn_legacy_env() && d.dk == 1
 cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc, const float* beta, const float* g,
                                   void* kcd_img, void* intra_img, float* vcorr, float* gcum, int M, int n_chunks, int nk, int nv,
                                   int num_sms, cudaStream_t s);
-// KB2_GDN_PREPARE_MMA_SYNC=1 keeps the mma.sync chunk-prepare in front of the tcgen05 scan (A/B tests only)
+// Which chunk-prepare feeds the tcgen05 scan.  Measured r02c (QCN layer, 8192 tokens): mma.sync 310 us, tcgen05 460 us — the
+// tcgen05 kernel is latency-bound on its per-unit phases; it stays selectable while it is being tuned:
+// KB2_GDN_PREPARE_MMA_SYNC=0 picks tcgen05, =1 mma.sync; unset -> kDefaultPrepareTc.
+constexpr bool kDefaultPrepareTc = false;
 static bool gdn_prepare_mma_sync_env() {
   const char* e = getenv("KB2_GDN_PREPARE_MMA_SYNC");
-  return e && e[0] == '1';
+  return e ? e[0] == '1' : !kDefaultPrepareTc;
 }
 static int gdn_num_sms() {
   int dev = 0, n = 148;

@@ -448,6 +448,7 @@ constexpr int kPSmem = kPOffBar + 128;
 static_assert(kPSmem <= 227 * 1024, "smem");
 
 struct GdnPrepParams {
+  long long* trace;          // optional clock64 stamps of CTA 0, loop iterations [2, 10): [iteration][16]
   const float* beta;         // [M][nv]
   const float* g;            // [M][nv]
   uint8_t* kcd_img;
@@ -485,6 +486,10 @@ __global__ void __launch_bounds__(kTThreads, 1)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
   constexpr uint32_t kColA = 0, kColB = 128, kColC = 256;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int it, int slot) {
+    if (tracing && it >= 2 && it < 10) p.trace[(it - 2) * 16 + slot] = clock64();
+  };
 
   if (warp == 4) {
     if (tid == 128) {
@@ -518,6 +523,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         const uint32_t sb = smem_u32(smem + st * kPStage);
         mbar_wait(&full[st], ph);
         tc_fence_after_sync();
+        stamp(it, 0);
 #pragma unroll
         for (int chn = 0; chn < 2; ++chn) {
           const uint64_t ad = umma_desc_k_sw128(sb + chn * 16384);          // rows 0-63 k, rows 64-127 q
@@ -526,8 +532,10 @@ __global__ void __launch_bounds__(kTThreads, 1)
           for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColA, ad + 2 * ks, bd + 2 * ks, id_a, (chn > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(a_done);
+        stamp(it, 1);
         mbar_wait(img_ready, up);
         tc_fence_after_sync();
+        stamp(it, 2);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t a1 = umma_desc_k_sw128(img1) + 2 * ks, a2 = umma_desc_k_sw128(img2) + 2 * ks;
@@ -536,6 +544,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         }
         umma_commit(bc_done);
         umma_commit(&empty[st]);
+        stamp(it, 3);
       }
     }
     __syncwarp();
@@ -584,8 +593,10 @@ __global__ void __launch_bounds__(kTThreads, 1)
         secol[i] = b_i * expf(gc);
       }
       named_bar_sync(2, 128);
+      if (tid == 0) stamp(it, 4);
       mbar_wait(a_done, up);
       tc_fence_after_sync();
+      if (tid == 0) stamp(it, 5);
       const float g_i = sg[i];
       if (tid < 64) {                         // k k^T row i  ->  A^T
 #pragma unroll
@@ -596,7 +607,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
             const int j = half * 32 + jj;
-            if (j < i) sAT[j * kPLdAT + i] = -(__uint_as_float(a[jj]) * b_i) * expf(g_i - sg[j]);
+            if (j < i) sAT[j * kPLdAT + i] = -(__uint_as_float(a[jj]) * b_i) * __expf(g_i - sg[j]);
           }
         }
       } else {                                // q k^T row i  ->  intra hi/lo images (global)
@@ -612,8 +623,8 @@ __global__ void __launch_bounds__(kTThreads, 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = half * 32 + q8 * 8 + 2 * e;
-              const float v0 = j <= i ? __uint_as_float(a[q8 * 8 + 2 * e]) * expf(g_i - sg[j]) : 0.f;
-              const float v1 = j + 1 <= i ? __uint_as_float(a[q8 * 8 + 2 * e + 1]) * expf(g_i - sg[j + 1]) : 0.f;
+              const float v0 = j <= i ? __uint_as_float(a[q8 * 8 + 2 * e]) * __expf(g_i - sg[j]) : 0.f;
+              const float v1 = j + 1 <= i ? __uint_as_float(a[q8 * 8 + 2 * e + 1]) * __expf(g_i - sg[j + 1]) : 0.f;
               unsigned short h0, l0, h1, l1;
               split_bf16(v0, h0, l0);
               split_bf16(v1, h1, l1);
@@ -628,6 +639,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
       }
       tc_fence_before_sync();
       named_bar_sync(2, 128);                 // A^T complete; D_A fully read
+      if (tid == 0) stamp(it, 6);
       if (tid < 64) {
         // row c of T = column c of X = T^T, (I - A^T) X = I by back substitution; A^T row i is read as broadcast float4
         const int c = tid;
@@ -636,18 +648,21 @@ __global__ void __launch_bounds__(kTThreads, 1)
         for (int j = 0; j < 64; ++j) x[j] = (j == c) ? 1.f : 0.f;
 #pragma unroll
         for (int ii = 62; ii >= 0; --ii) {
-          float acc = x[ii];                 // 1 on the diagonal, else 0; rows ii > c stay 0 because x[j > c] = 0 ... but
-          const float* arow = sAT + ii * kPLdAT;   // A^T[ii][j] is only defined for j > ii (strictly lower part of A)
+          // x[ii] starts as the identity entry; A^T[ii][j] is only defined for j > ii (strictly lower part of A).  Four
+          // independent partial sums: the row's FMA chain would otherwise be up to 63 dependent operations long.
+          float a0 = x[ii], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          const float* arow = sAT + ii * kPLdAT;
 #pragma unroll
           for (int j4 = (ii + 1) / 4; j4 < 16; ++j4) {
             const float4 av = *reinterpret_cast<const float4*>(arow + 4 * j4);
-            if (4 * j4 + 0 > ii) acc = fmaf(av.x, x[4 * j4 + 0], acc);
-            if (4 * j4 + 1 > ii) acc = fmaf(av.y, x[4 * j4 + 1], acc);
-            if (4 * j4 + 2 > ii) acc = fmaf(av.z, x[4 * j4 + 2], acc);
-            if (4 * j4 + 3 > ii) acc = fmaf(av.w, x[4 * j4 + 3], acc);
+            if (4 * j4 + 0 > ii) a0 = fmaf(av.x, x[4 * j4 + 0], a0);
+            if (4 * j4 + 1 > ii) a1 = fmaf(av.y, x[4 * j4 + 1], a1);
+            if (4 * j4 + 2 > ii) a2 = fmaf(av.z, x[4 * j4 + 2], a2);
+            if (4 * j4 + 3 > ii) a3 = fmaf(av.w, x[4 * j4 + 3], a3);
           }
-          x[ii] = (ii > c) ? 0.f : acc;
+          x[ii] = (ii > c) ? 0.f : (a0 + a1) + (a2 + a3);
         }
+        if (tid == 0) stamp(it, 7);
         // T' = T diag(beta), T'' = T diag(beta e^gcum) as hi/lo K-major SW128 rows
         uint8_t* i1 = smem + kPOffImg1 + c * 128;
         uint8_t* i2 = smem + kPOffImg2 + c * 128;
@@ -676,9 +691,11 @@ __global__ void __launch_bounds__(kTThreads, 1)
         fence_proxy_async_smem();
         mbar_arrive(img_ready);
         p.gcum[hc * kTC + i] = g_i;
+        if (tid == 0) stamp(it, 8);
       }
       mbar_wait(bc_done, up);
       tc_fence_after_sync();
+      if (tid == 0) stamp(it, 9);
       // hand the partner its missing part: lanes 0-63 hold the hi parts, lanes 64-127 the lo parts
       {
         float* xdst = (tid < 64 ? sXC : sXB) + i * kPLdX;
@@ -740,6 +757,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         }
       }
       tc_fence_before_sync();
+      if (tid == 0) stamp(it, 10);
     }
   }
   tc_fence_before_sync();
@@ -763,7 +781,9 @@ cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc
   if (e != cudaSuccess) return e;
   e = make_tmap_bf16_rows(&tv, vc, M, (long long)nv * kTD, kTC);
   if (e != cudaSuccess) return e;
-  GdnPrepParams p{beta, g, (uint8_t*)kcd_img, (uint8_t*)intra_img, vcorr, gcum, M, n_chunks, nv, nk};
+  const char* trv = getenv("KB2_GDN_PREPARE_TRACE");
+  long long* trace = trv ? reinterpret_cast<long long*>(strtoull(trv, nullptr, 0)) : nullptr;
+  GdnPrepParams p{trace, beta, g, (uint8_t*)kcd_img, (uint8_t*)intra_img, vcorr, gcum, M, n_chunks, nv, nk};
   const int n_units = nv * n_chunks;
   gdn_prepare_tc_kernel<<<n_units < num_sms ? n_units : num_sms, kTThreads, kPSmem, s>>>(tq, tk, tv, p);
   return cudaGetLastError();

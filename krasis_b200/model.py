@@ -526,6 +526,7 @@ class KrasisModel:
                     del sw
             self.layers.append(lay)
         self._ones = self._zero_ids = None
+        self._side_stream = None
 
     # ------------------------------------------------------------------------------------------- real checkpoints
     @classmethod
@@ -573,8 +574,23 @@ class KrasisModel:
     def _moe(self, lay, h, M_loc):
         """Router + shared expert + routed experts of one MoE layer on this rank's token rows h [M_loc, H]."""
         tm, m, R = self._timer, lay.moe_idx, self.num_ranks
+        if R > 1:
+            # the gather of this rank's rows runs on a side stream while the router and the shared expert (which need only the
+            # local rows) run on the main stream; ids / weights follow as soon as the router has produced them
+            main = torch.cuda.current_stream(self.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(self.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                h_all = self.comm.all_gather_rows(h)
         with tm("router"):
             ids, w = self.engine.compute_routing(m, h)
+        if R > 1:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ids_all = self.comm.all_gather_rows(ids)
+                w_all = self.comm.all_gather_rows(w)
         shared = None
         with tm("shared_expert"):
             if lay.shared_expert is not None:
@@ -588,9 +604,9 @@ class KrasisModel:
             with tm("routed_experts"):
                 return self.engine.moe_forward(m, h, ids, w, shared=shared)
         with tm("ep_all_gather"):
-            h_all = self.comm.all_gather_rows(h)
-            ids_all = self.comm.all_gather_rows(ids)
-            w_all = self.comm.all_gather_rows(w)
+            main.wait_stream(side)                                          # gathered rows / ids / weights are in place
+            for t in (h_all, ids_all, w_all):
+                t.record_stream(main)
         with tm("routed_experts"):
             part = self.engine.moe_forward(m, h_all, ids_all, w_all, routed_only=True)       # local expert slice, all tokens
         with tm("ep_reduce_scatter"):

@@ -50,3 +50,31 @@ for split in ("0", "1"):
         print("   ", r)
     print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
 print("max |split0 - split1| / max:", ((outs["0"] - outs["1"]).abs().max() / outs["0"].abs().max()).item())
+
+# ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,
+# 3 MMA-B/C issued; core thread 0: 4 gates scanned, 5 k.k^T seen, 6 A^T built, 7 T solved, 8 images written, 9 vcorr/kcd products seen,
+# 10 outputs stored)
+os.environ.pop("KB2_GDN_SCAN_SPLIT", None)
+for mode in ("1", "0"):
+    os.environ["KB2_GDN_PREPARE_MMA_SYNC"] = mode
+    for _ in range(2):
+        lay.reset_state()
+        lay.forward(x)
+    capi.kernel_profile(True)
+    for _ in range(5):
+        lay.reset_state()
+        lay.forward(x)
+    prof = capi.kernel_profile_collect()
+    capi.kernel_profile(False)
+    print(("mma.sync" if mode == "1" else "tcgen05") + " prepare: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in prof.items() if "prepare" in n))
+trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
+os.environ["KB2_GDN_PREPARE_TRACE"] = str(trace.data_ptr())
+lay.reset_state()
+lay.forward(x)
+torch.cuda.synchronize()
+del os.environ["KB2_GDN_PREPARE_TRACE"]
+t = trace.cpu().view(8, 16)[:, :11]
+print("  prepare timeline (cycles since inputs landed), loop iterations 2..9:")
+for r in (t - t[:, 0:1]).tolist():
+    print("   ", r)
+print("  unit period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
