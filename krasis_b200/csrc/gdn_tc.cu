@@ -36,6 +36,7 @@ constexpr int kTC = 64;            // chunk length (linear_attention.py:702)
 constexpr int kTSV = 32;           // dv slice per CTA
 constexpr int kTD = 128;           // dk == dv
 constexpr int kTThreads = 192;
+constexpr int kDefaultLayout = 1;      // flip to 2 once measured faster (KB2_GDN_SCAN_LAYOUT overrides per call)
 constexpr bool kDefaultSplit = false;   // chained accumulators (measured r02a); flip after comparing with KB2_GDN_SCAN_SPLIT=1
 constexpr int kVcLd = 36;          // padded row of the vcorr slice (floats): conflict-free float4 rows
 
@@ -419,6 +420,285 @@ __global__ void __launch_bounds__(kTThreads, 1)
 }
 
 
+
+// --------------------------------------------------------------------------------------------------------------------
+// Scan, second layout (measured motivation, profiles/r02c_gdn_scan_timeline.txt: of 4400 cycles per chunk, 1530 were two
+// warps writing the v operand tiles while the other two idled, and the epilogue needed a cross-lane exchange).  Differences:
+//   * G1 stacks [q ; kcd_hi]: IT lands on lanes 0-63, VP on lanes 64-127; the kcd_lo tile is addressed 8 KB early so that
+//     its product lands on lanes 64-127 too.
+//   * warps 2-3 form v = vcorr - VP in fp32 and park it in shared memory; after one 128-thread barrier ALL four warps split
+//     and store the operand tiles (16 columns each).
+//   * G3 uses two 64-row tiles (intra_hi, intra_lo) accumulating on lanes 0-63, where IT already is: the epilogue is local
+//     to warps 0-1, no exchange buffer.
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kOffXV = kOffX;                // fp32 [64][36] v rows (the exchange buffer of the first layout)
+
+__global__ void __launch_bounds__(kTThreads, 1)
+    gdn_scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* full = bars;           // [2]
+  uint64_t* empty = bars + 2;      // [2]
+  uint64_t* s_ready = bars + 4;
+  uint64_t* g1_done = bars + 5;
+  uint64_t* v_ready = bars + 6;
+  uint64_t* g2_done = bars + 7;
+  uint64_t* g3_done = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, sl = blockIdx.y;
+  const int kh = h / (p.nv / p.nk);
+  const int n_chunks = p.n_chunks;
+  const int vd = p.nv * kTD;
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_init(s_ready, 128);
+    mbar_init(g1_done, 1);
+    mbar_init(v_ready, 128);
+    mbar_init(g2_done, 1);
+    mbar_init(g3_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr_smem, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kColD1 = 0, kColD1b = 32, kColD2 = 64, kColD3 = 96;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  auto stamp = [&](int c, int slot) {
+    if (tracing && c >= 8 && c < 16) p.trace[(c - 8) * 16 + slot] = clock64();
+  };
+
+  if (warp == 4) {
+    if (tid == 128) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      const long long hc0 = (long long)h * n_chunks;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
+        uint8_t* sb = smem + st * kStageBytes;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[st], kTxBytes);
+        const long long hc = hc0 + c;
+        const uint8_t* kimg = p.kcd_img + hc * 32768;
+        // A1 = [q c0 | kcd_hi c0 | q c1 | kcd_hi c1], A1L = [kcd_lo c0 | kcd_lo c1]
+        tma_load_2d(sb + kOffA1, &tmap_q, kh * kTD, c * kTC, &full[st]);
+        bulk_g2s(sb + kOffA1 + 8192, kimg, 8192, &full[st]);
+        tma_load_2d(sb + kOffA1 + 16384, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
+        bulk_g2s(sb + kOffA1 + 24576, kimg + 8192, 8192, &full[st]);
+        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);
+        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);
+        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
+        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
+        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
+        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (tid == 160) {
+      const uint32_t id_k = umma_idesc_bf16_m128(kTSV);
+      const uint32_t id_amn = umma_idesc_bf16_m128(kTSV) | (1u << 15);
+      const uint32_t sh = smem_u32(smem + kOffSH), slo = smem_u32(smem + kOffSL);
+      const uint32_t vh = smem_u32(smem + kOffVH), vl = smem_u32(smem + kOffVL);
+      const uint32_t vdh = smem_u32(smem + kOffVDH), vdl = smem_u32(smem + kOffVDL);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
+        const uint32_t sb = smem_u32(smem + st * kStageBytes);
+        mbar_wait(&full[st], ph);
+        mbar_wait(s_ready, cp);
+        tc_fence_after_sync();
+        stamp(c, 0);
+        // G1: [q ; kcd_hi] (S_hi + S_lo) -> D1 (IT lanes 0-63, VP lanes 64-127);  [* ; kcd_lo] S_hi -> D1b (lanes 64-127)
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t b0 = pass == 1 ? slo : sh;
+          const uint32_t dcol = pass < 2 ? kColD1 : kColD1b;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            // kcd_lo chunk ch sits at A1L + 8K*ch; starting 8 KB earlier puts it on rows 64-127
+            const uint32_t a_addr = pass < 2 ? sb + kOffA1 + ch * 16384 : sb + kOffA1L + ch * 8192 - 8192;
+            const uint64_t ad = umma_desc_k_sw128(a_addr);
+            const uint64_t bd = umma_desc_k_sw128(b0 + ch * 4096);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(tmem_base + dcol, ad + 2 * ks, bd + 2 * ks, id_k, (pass == 1 || ch > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(g1_done);
+        stamp(c, 1);
+        mbar_wait(v_ready, cp);
+        tc_fence_after_sync();
+        stamp(c, 2);
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {          // G2: dS = k^T (vdec_hi + vdec_lo)
+          const uint64_t bd = umma_desc_k_sw128(pass ? vdl : vdh);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
+            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn, (pass > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(g2_done);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {          // G3 (lanes 0-63): intra_hi (v_hi + v_lo) + intra_lo v_hi
+          const uint64_t ad = umma_desc_k_sw128(sb + kOffA3 + (pass == 2 ? 8192 : 0));
+          const uint64_t bd = umma_desc_k_sw128(pass == 1 ? vl : vh);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(tmem_base + kColD3, ad + 2 * ks, bd + 2 * ks, id_k, (pass > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(g3_done);
+        umma_commit(&empty[st]);
+        stamp(c, 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float s[kTSV];
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
+#pragma unroll
+      for (int j4 = 0; j4 < kTSV / 4; ++j4) {
+        const float4 v = src[j4];
+        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
+      }
+    }
+    auto write_s_tiles = [&]() {
+#pragma unroll
+      for (int j = 0; j < kTSV; ++j) {
+        unsigned short hi, lo;
+        split_bf16(s[j], hi, lo);
+        const uint32_t off = sw128_off(j, tid, 4096);
+        *reinterpret_cast<unsigned short*>(smem + kOffSH + off) = hi;
+        *reinterpret_cast<unsigned short*>(smem + kOffSL + off) = lo;
+      }
+    };
+    write_s_tiles();
+    fence_proxy_async_smem();
+    mbar_arrive(s_ready);
+    float* xv = reinterpret_cast<float*>(smem + kOffXV);
+    const int i = tid & 63, half = tid >> 6;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int st = c & 1;
+      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
+      const uint8_t* sb = smem + st * kStageBytes;
+      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
+      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
+      mbar_wait(&full[st], ph);
+      const float g_last = sg[kTC - 1], g_i = sg[i];
+      const float d_last = expf(g_last);
+      const float dec = expf(g_last - g_i);
+      float it[kTSV];
+#pragma unroll
+      for (int j = 0; j < kTSV; ++j) it[j] = 0.f;
+      mbar_wait(g1_done, cp);
+      tc_fence_after_sync();
+      if (tid == 0) stamp(c, 4);
+      if (tid >= 64) {                         // VP rows (lanes 64-127): v = vcorr - VP, parked as fp32
+        uint32_t a[32], b[32];
+        tmem_ld32(lane_addr + kColD1, a);
+        tmem_ld32(lane_addr + kColD1b, b);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < kTSV / 4; ++j4) {
+          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + 4 * j4);
+          *reinterpret_cast<float4*>(xv + i * kVcLd + 4 * j4) =
+              make_float4(vc4.x - (__uint_as_float(a[4 * j4]) + __uint_as_float(b[4 * j4])),
+                          vc4.y - (__uint_as_float(a[4 * j4 + 1]) + __uint_as_float(b[4 * j4 + 1])),
+                          vc4.z - (__uint_as_float(a[4 * j4 + 2]) + __uint_as_float(b[4 * j4 + 2])),
+                          vc4.w - (__uint_as_float(a[4 * j4 + 3]) + __uint_as_float(b[4 * j4 + 3])));
+        }
+      } else {                                 // IT rows (lanes 0-63)
+        uint32_t a[32];
+        tmem_ld32(lane_addr + kColD1, a);
+        tmem_ld_wait();
+        const float eg = expf(g_i);
+#pragma unroll
+        for (int j = 0; j < kTSV; ++j) it[j] = eg * __uint_as_float(a[j]);
+      }
+      tc_fence_before_sync();
+      named_bar_sync(1, 128);
+      {                                        // all four warps: token i, 16 of the 32 columns -> hi/lo operand tiles
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(xv + i * kVcLd + half * 16 + 4 * j4);
+          const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = half * 16 + 4 * j4 + e;
+            unsigned short hi, lo, dhi, dlo;
+            split_bf16(vv[e], hi, lo);
+            split_bf16(vv[e] * dec, dhi, dlo);
+            const uint32_t off = sw128_off(j, i, 0);
+            *reinterpret_cast<unsigned short*>(smem + kOffVH + off) = hi;
+            *reinterpret_cast<unsigned short*>(smem + kOffVL + off) = lo;
+            *reinterpret_cast<unsigned short*>(smem + kOffVDH + off) = dhi;
+            *reinterpret_cast<unsigned short*>(smem + kOffVDL + off) = dlo;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(v_ready);
+      if (tid == 0) stamp(c, 5);
+      mbar_wait(g2_done, cp);
+      tc_fence_after_sync();
+      if (tid == 0) stamp(c, 6);
+      {
+        uint32_t a[32];
+        tmem_ld32(lane_addr + kColD2, a);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < kTSV; ++j) s[j] = fmaf(d_last, s[j], __uint_as_float(a[j]));
+      }
+      if (c + 1 < n_chunks) {
+        write_s_tiles();
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(s_ready);
+      }
+      if (tid == 0) stamp(c, 7);
+      if (tid < 64) {                          // output rows: IT and intra.v share lanes 0-63
+        mbar_wait(g3_done, cp);
+        tc_fence_after_sync();
+        if (tid == 0) stamp(c, 8);
+        uint32_t a[32];
+        tmem_ld32(lane_addr + kColD3, a);
+        tmem_ld_wait();
+        const int t = c * kTC + i;
+        if (t < p.M) {
+          uint32_t o[kTSV / 2];
+#pragma unroll
+          for (int j2 = 0; j2 < kTSV / 2; ++j2) {
+            __nv_bfloat162 pr = __floats2bfloat162_rn(it[2 * j2] + __uint_as_float(a[2 * j2]), it[2 * j2 + 1] + __uint_as_float(a[2 * j2 + 1]));
+            o[j2] = *reinterpret_cast<uint32_t*>(&pr);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV);
+#pragma unroll
+          for (int q = 0; q < kTSV / 8; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+        tc_fence_before_sync();
+        if (tid == 0) stamp(c, 9);
+      }
+    }
+    {
+      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
+#pragma unroll
+      for (int j4 = 0; j4 < kTSV / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
+}
+
 // ====================================================================================================================
 // Chunk prepare on tcgen05 (dk == dv == 128): everything of linear_attention.py:593-646 that does not depend on the carried
 // state, for one (value head, 64-token chunk) per loop iteration of a persistent CTA:
@@ -797,6 +1077,7 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
   if (const int dev = once.pending(); dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(gdn_scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
@@ -812,7 +1093,10 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
   e = make_tmap_bf16_rows(&tk, kn, M, (long long)nk * kTD, kTC);
   if (e != cudaSuccess) return e;
   GdnTcParams p{(const uint8_t*)kcd_img, (const uint8_t*)intra_img, vcorr, gcum, state, (__nv_bfloat16*)core_out, M, n_chunks, nv, nk, trace};
-  if (split) gdn_scan_tc_kernel<true><<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
+  const char* vv = getenv("KB2_GDN_SCAN_LAYOUT");          // 1 = first layout, 2 = second layout (see above); unset -> kDefaultLayout
+  const int layout = vv ? atoi(vv) : kDefaultLayout;
+  if (layout == 2) gdn_scan_tc2_kernel<<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
+  else if (split) gdn_scan_tc_kernel<true><<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
   else gdn_scan_tc_kernel<false><<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
   return cudaGetLastError();
 }

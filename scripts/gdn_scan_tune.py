@@ -24,8 +24,9 @@ cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_v
 lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
 x = torch.randn(M, H).to(bf).cuda()
 outs = {}
-for split in ("0", "1"):
-    os.environ["KB2_GDN_SCAN_SPLIT"] = split
+for split in ("0", "2"):                                   # "0": first layout, chained accumulators; "2": second layout
+    os.environ["KB2_GDN_SCAN_SPLIT"] = "0"
+    os.environ["KB2_GDN_SCAN_LAYOUT"] = "2" if split == "2" else "1"
     for _ in range(3):
         lay.reset_state()
         lay.forward(x)
@@ -49,7 +50,8 @@ for split in ("0", "1"):
     for r in (t - base).tolist():
         print("   ", r)
     print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
-print("max |split0 - split1| / max:", ((outs["0"] - outs["1"]).abs().max() / outs["0"].abs().max()).item())
+print("max |layout1 - layout2| / max:", ((outs["0"] - outs["2"]).abs().max() / outs["0"].abs().max()).item())
+os.environ.pop("KB2_GDN_SCAN_LAYOUT", None)
 
 # ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,
 # 3 MMA-B/C issued; core thread 0: 4 gates scanned, 5 k.k^T seen, 6 A^T built, 7 T solved, 8 images written, 9 vcorr/kcd products seen,
