@@ -3,6 +3,7 @@
 // (`GpuPrefillManager`, python/krasis/gpu_prefill.py:326-4484); here it is C++ behind a C boundary.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -29,6 +30,10 @@ cudaError_t launch_router_topk(const float* logits, const float* corr_bias, int 
 cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
                            int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
                            int* sorted_ids, const void* x, void* x_sorted, int H, cudaStream_t s);
+cudaError_t launch_binning_index(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
+                                 int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
+                                 int* sorted_tok, cudaStream_t s);
+cudaError_t make_tmap_bf16_gather(void* out_tmap, const void* base, long long rows, long long cols);
 cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
                            const void* shared, void* out, cudaStream_t s);
 cudaError_t launch_quantize_group(const void* w, int bits, void* q_out, void* scales, long long rows, int K, cudaStream_t s);
@@ -73,6 +78,8 @@ void kernel_span_end(int id, cudaStream_t s, int slot) {
   g_kspans[id].push_back({slot, slot + 1});
 }
 }  // namespace kb2
+
+constexpr bool kDefaultMoeGather = false;   // flip after the gather4 path is measured (KB2_MOE_GATHER overrides per call)
 
 static thread_local std::string g_err;
 
@@ -119,6 +126,7 @@ struct kb2_engine {
   int *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *n_chunks = nullptr;
   ChunkDesc* chunks = nullptr;
   int* slot_of = nullptr;
+  int* sorted_tok = nullptr;                       // gather mode: token row of every sorted slot (+ kMaxChunkTokens of padding)
   void* x_sorted = nullptr;                        // [max_tokens*k][H] bf16: per-expert contiguous token tiles
   alignas(64) unsigned char tmap_x[128];           // CUtensorMap over x_sorted (GEMM1 B operand)
   alignas(64) unsigned char tmap_act[128];         // CUtensorMap over act      (GEMM2 B operand)
@@ -263,6 +271,8 @@ KB2_API int kb2_create(const kb2_config* c, kb2_engine** out) {
   ALLOC(e->chunks, sizeof(ChunkDesc) * max_chunks);
   ALLOC(e->x_sorted, MK * c->hidden_size * 2);
   ALLOC(e->slot_of, sizeof(int) * MK);
+  ALLOC(e->sorted_tok, sizeof(int) * (MK + kMaxChunkTokens));
+  if (cudaMemset(e->sorted_tok, 0, sizeof(int) * (MK + kMaxChunkTokens)) != cudaSuccess) { kb2_destroy(e); return fail(KB2_ERR_CUDA, "cudaMemset failed"); }
   ALLOC(e->sorted_w, sizeof(float) * MK);
   ALLOC(e->act, MK * c->moe_intermediate_size * 2);
   ALLOC(e->c3, MK * c->hidden_size * 2);
@@ -298,7 +308,7 @@ KB2_API void kb2_destroy(kb2_engine* e) {
     cudaFree(L.gate); cudaFree(L.gate_bias); cudaFree(L.corr_bias);
   }
   cudaFree(e->counts); cudaFree(e->offsets); cudaFree(e->cursor); cudaFree(e->n_chunks); cudaFree(e->chunks);
-  cudaFree(e->x_sorted); cudaFree(e->slot_of); cudaFree(e->sorted_w); cudaFree(e->act); cudaFree(e->c3);
+  cudaFree(e->x_sorted); cudaFree(e->slot_of); cudaFree(e->sorted_tok); cudaFree(e->sorted_w); cudaFree(e->act); cudaFree(e->c3);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   cudaFree(e->logits); cudaFree(e->ids_tmp); cudaFree(e->w_tmp); cudaFree(e->x_tmp); cudaFree(e->out_tmp);
   delete e;
@@ -523,9 +533,19 @@ static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32
   const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size;
   const int f13 = fmt13(e), f2 = fmt2(e);
 
+  // KB2_MOE_GATHER=1: the gate/up GEMM fetches token rows from x itself with TMA gather4; no x_sorted copy is made
+  const char* gev = getenv("KB2_MOE_GATHER");
+  const bool gather = gev ? gev[0] == '1' : kDefaultMoeGather;
+  alignas(64) unsigned char tmap_gather[128];
   { ProfSpan ps(e, KB2_PROF_BINNING, s);
-    CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
-                            e->n_chunks, e->sorted_w, e->slot_of, nullptr, x, e->x_sorted, H, s)); }
+    if (gather) {
+      CUDA_TRY(launch_binning_index(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
+                                    e->n_chunks, e->sorted_w, e->slot_of, e->sorted_tok, s));
+      CUDA_TRY(make_tmap_bf16_gather(tmap_gather, x, M, H));
+    } else {
+      CUDA_TRY(launch_binning(ids, wts, M, K, e->e_start, e->e_end, e->counts, e->offsets, e->cursor, e->chunks,
+                              e->n_chunks, e->sorted_w, e->slot_of, nullptr, x, e->x_sorted, H, s));
+    } }
   e->launches += 3;
 
   GemmParams g1{};
@@ -536,8 +556,9 @@ static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32
   g1.items_per_chunk = I / kTileRows; g1.tile1_offset = I / kTileRows; g1.tile0_mul = 1;
   g1.chunks = e->chunks; g1.n_chunks = e->n_chunks;
   g1.out = (__nv_bfloat16*)e->act; g1.out_ld = I; g1.slot_weight = nullptr;
+  g1.gather_rows = gather ? e->sorted_tok : nullptr;
   { ProfSpan ps(e, KB2_PROF_GEMM1, s);
-    CUDA_TRY(launch_grouped_gemm(f13, true, g1, e->tmap_x, e->num_sms, s)); }
+    CUDA_TRY(launch_grouped_gemm(f13, true, g1, gather ? tmap_gather : e->tmap_x, e->num_sms, s)); }
 
   GemmParams g2{};
   g2.wq = L.w2_q; g2.ws = L.w2_s;

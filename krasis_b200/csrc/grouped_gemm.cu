@@ -234,7 +234,40 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     __syncwarp();
   } else if (warp == 2) {
     // ------------------------------------------------------------ token (B operand) producer: 2-D TMA
-    if (lane == 0) {
+    if (p.gather_rows != nullptr) {
+      // gather mode: the whole warp keeps the chunk's row indices in registers (6 per lane cover 192 slots); lane 0 issues
+      // one gather4 per 4 token rows and k-block.  Slots past n_tok (padding up to a multiple of 16) read whatever valid
+      // row index follows in the table: those accumulator columns are never stored.
+      Ring rb;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
+        const int n_pad = (cd.n_tok + 15) & ~15;
+        int idx[kMaxChunkTokens / 32];
+#pragma unroll
+        for (int q = 0; q < kMaxChunkTokens / 32; ++q) idx[q] = (q * 32 + lane < n_pad) ? p.gather_rows[cd.slot_begin + q * 32 + lane] : 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (lane == 0) {
+            mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
+            mbar_arrive_expect_tx(&b_full[rb.stage], n_pad * kBlockK * 2);
+          }
+          __syncwarp();
+          uint8_t* dst = smem + L::kOffB + rb.stage * kBStageBytes;
+#pragma unroll
+          for (int q = 0; q < kMaxChunkTokens / 32; ++q) {
+            if (q * 32 < n_pad) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const int r0 = __shfl_sync(0xffffffffu, idx[q], 4 * g), r1 = __shfl_sync(0xffffffffu, idx[q], 4 * g + 1);
+                const int r2 = __shfl_sync(0xffffffffu, idx[q], 4 * g + 2), r3 = __shfl_sync(0xffffffffu, idx[q], 4 * g + 3);
+                if (lane == 0 && q * 32 + 4 * g < n_pad)
+                  tma_gather4_2d(dst + (q * 32 + 4 * g) * (kBlockK * 2), &tmap_b, kb * kBlockK, r0, r1, r2, r3, &b_full[rb.stage]);
+              }
+            }
+          }
+          rb.advance(kStagesB);
+        }
+      }
+    } else if (lane == 0) {
       Ring rb;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
@@ -502,6 +535,11 @@ cudaError_t make_tmap_u8_rows(void* out_tmap, const void* base, long long rows, 
 }
 
 int gemm_b_box_rows() { return kBBoxRows; }
+
+// rows x cols BF16 row-major matrix for TMA gather4: box = 1 row x 64 columns, 128 B swizzle
+cudaError_t make_tmap_bf16_gather(void* out_tmap, const void* base, long long rows, long long cols) {
+  return make_tmap_bf16_rows(out_tmap, base, rows, cols, 1);
+}
 
 template <int FMT, bool kGemm1>
 static cudaError_t launch_one(const GemmParams& p, const CUtensorMap& tmap, int num_sms, cudaStream_t stream) {

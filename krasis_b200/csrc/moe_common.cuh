@@ -93,6 +93,8 @@ struct GemmParams {
   __nv_bfloat16* out;         // GEMM1: act[slot][I]   GEMM2: c3[slot][H]
   long long out_ld;
   const float* slot_weight;   // GEMM2: routing weight per sorted slot
+  const int* gather_rows;     // GEMM1, gather mode: token row of every sorted slot (the B operand is fetched from the caller's
+                              // activation matrix with TMA gather4 instead of a pre-sorted copy); nullptr = B rows are contiguous
 };
 
 }  // namespace kb2

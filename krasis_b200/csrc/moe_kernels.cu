@@ -256,6 +256,25 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int* __restrict__ id
   if (lane == 0) slot_of[i] = slot;
 }
 
+// Gather mode: no row copy — one THREAD per routing entry records which token row sits in which sorted slot; the grouped
+// GEMM then fetches the rows from the caller's activation matrix with TMA gather4.
+__global__ void __launch_bounds__(256) scatter_index_kernel(const int* __restrict__ ids, const float* __restrict__ wts, int n,
+                                                            int top_k, int e_start, int e_end, const int* __restrict__ offsets,
+                                                            int* __restrict__ cursor, float* __restrict__ sorted_w,
+                                                            int* __restrict__ slot_of, int* __restrict__ sorted_tok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = ids[i];
+  int slot = -1;
+  if (e >= e_start && e < e_end) {
+    const int le = e - e_start;
+    slot = offsets[le] + atomicAdd(&cursor[le], 1);
+    sorted_w[slot] = wts[i];
+    sorted_tok[slot] = i / top_k;
+  }
+  slot_of[i] = slot;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Combine: out[m] = bf16( sum_j f32(c3[slot_of[m][j]]) ) in j order; then bf16(rsf*out) (+ shared)
 // one thread = 8 consecutive h (16 B)
@@ -572,6 +591,22 @@ cudaError_t launch_binning(const int* ids, const float* wts, int M, int top_k, i
   if (n > 0)
     scatter_kernel<<<(n + 7) / 8, 256, 0, s>>>(ids, wts, n, top_k, e_start, e_end, offsets, cursor, sorted_w, slot_of,
                                                sorted_ids, (const uint4*)x, (uint4*)x_sorted, H / 8);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_binning_index(const int* ids, const float* wts, int M, int top_k, int e_start, int e_end, int* counts,
+                                 int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
+                                 int* sorted_tok, cudaStream_t s) {
+  KernelSpan ks(K_BINNING, s, 3);
+  const int n = M * top_k, E = e_end - e_start;
+  if (E > 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * E, s);
+  if (e != cudaSuccess) return e;
+  if (n > 0) count_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, n, e_start, e_end, counts);
+  scan_kernel<<<1, 1024, 0, s>>>(counts, E, offsets, cursor, chunks, n_chunks);
+  if (n > 0)
+    scatter_index_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, wts, n, top_k, e_start, e_end, offsets, cursor, sorted_w, slot_of,
+                                                         sorted_tok);
   return cudaGetLastError();
 }
 

@@ -71,6 +71,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, in
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA gather4: four rows (r0..r3, arbitrary row indices) x one box of columns starting at c0 -> four consecutive
+// 128-byte rows of shared memory (hardware swizzle from the tensor map).  The tensor map's box must be {cols, 1 row}.
+__device__ __forceinline__ void tma_gather4_2d(void* dst_smem, const void* tmap, int c0, int r0, int r1, int r2, int r3,
+                                               uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
