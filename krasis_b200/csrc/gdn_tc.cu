@@ -92,11 +92,14 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k, int chunk_stride) 
   return (uint32_t)((k >> 6) * chunk_stride + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1)));
 }
 
+// x = hi + lo with hi = bf16_rne(x) and lo = bf16_trunc(x - hi): |x - hi - lo| <= 2^-17 |x|.  Integer rounding on purpose:
+// F2F.BF16.F32 runs on a quarter-rate unit and 64-128 conversions per thread and chunk were the largest single cost of the
+// CUDA-core phases (profiles/r02a_gdn_scan_tc_stalls.txt).
 __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-  hi = *reinterpret_cast<const unsigned short*>(&h);
-  lo = *reinterpret_cast<const unsigned short*>(&l);
+  const uint32_t u = __float_as_uint(x);
+  const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+  hi = (unsigned short)(r >> 16);
+  lo = (unsigned short)(__float_as_uint(x - __uint_as_float(r & 0xFFFF0000u)) >> 16);
 }
 
 struct GdnTcParams {
