@@ -717,14 +717,20 @@ __global__ void __launch_bounds__(kTThreads, 1)
 // ====================================================================================================================
 constexpr int kPStage = 49152;                       // [k c0 8K][q c0 8K][k c1 8K][q c1 8K][v dv0-63 8K][v dv64-127 8K]
 constexpr int kPOffV = 32768;
-constexpr int kPOffAT = 2 * kPStage;                 // A^T fp32 [64][68]
-constexpr int kPLdAT = 68;
-constexpr int kPOffImg1 = kPOffAT + 64 * kPLdAT * 4; // [T'_hi 8K][T'_lo 8K]
+constexpr int kPLdAT = 68;                           // row stride (floats) of the fp32 A and T matrices
+constexpr int kPOffImg1 = 2 * kPStage;               // [T'_hi 8K][T'_lo 8K]
 static_assert(kPOffImg1 % 1024 == 0, "image alignment");
 constexpr int kPOffImg2 = kPOffImg1 + 16384;         // [T''_hi][T''_lo]
 constexpr int kPLdX = 132;
 constexpr int kPOffXB = kPOffImg2 + 16384;           // exchange: lo part of vcorr rows   fp32 [64][132]
 constexpr int kPOffXC = kPOffXB + 64 * kPLdX * 4;    // exchange: hi part of kcd rows
+// A (fp32 [64][68]) lives in the XB region, T (fp32 [64][68]) and the product scratch P (fp32 [32][36]) in the XC region:
+// both matrices are dead once the operand images exist, long before the epilogue uses the exchange buffers.
+constexpr int kPOffA = kPOffXB;
+constexpr int kPOffT = kPOffXC;
+constexpr int kPOffP = kPOffXC + 64 * kPLdAT * 4;
+constexpr int kPLdP = 36;
+static_assert(64 * kPLdAT * 4 <= 64 * kPLdX * 4 && 64 * kPLdAT * 4 + 32 * kPLdP * 4 <= 64 * kPLdX * 4, "A / T / P fit the exchange buffers");
 constexpr int kPOffSc = kPOffXC + 64 * kPLdX * 4;    // gcum[64] | beta[64] | beta*e^gcum[64] | scan scratch[4]
 constexpr int kPOffBar = kPOffSc + 1024;
 constexpr int kPSmem = kPOffBar + 128;
@@ -759,7 +765,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
     mbar_init(&full[0], 1); mbar_init(&full[1], 1);
     mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
     mbar_init(a_done, 1);
-    mbar_init(img_ready, 64);
+    mbar_init(img_ready, 128);
     mbar_init(bc_done, 1);
     fence_mbar_init();
   }
@@ -834,7 +840,9 @@ __global__ void __launch_bounds__(kTThreads, 1)
   } else {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int i = tid & 63, lane = tid & 31;
-    float* sAT = reinterpret_cast<float*>(smem + kPOffAT);
+    float* sA = reinterpret_cast<float*>(smem + kPOffA);
+    float* sT = reinterpret_cast<float*>(smem + kPOffT);
+    float* sP = reinterpret_cast<float*>(smem + kPOffP);
     float* sXB = reinterpret_cast<float*>(smem + kPOffXB);
     float* sXC = reinterpret_cast<float*>(smem + kPOffXC);
     float* sg = reinterpret_cast<float*>(smem + kPOffSc);
@@ -888,9 +896,14 @@ __global__ void __launch_bounds__(kTThreads, 1)
           tmem_ld32(lane_addr + kColA + half * 32, a);
           tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const int j = half * 32 + jj;
-            if (j < i) sAT[j * kPLdAT + i] = -(__uint_as_float(a[jj]) * b_i) * __expf(g_i - sg[j]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = half * 32 + 4 * j4 + e;
+              v[e] = j < i ? -(__uint_as_float(a[4 * j4 + e]) * b_i) * __expf(g_i - sg[j]) : 0.f;
+            }
+            *reinterpret_cast<float4*>(sA + i * kPLdAT + half * 32 + 4 * j4) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
       } else {                                // q k^T row i  ->  intra hi/lo images (global)
@@ -923,49 +936,110 @@ __global__ void __launch_bounds__(kTThreads, 1)
       tc_fence_before_sync();
       named_bar_sync(2, 128);                 // A^T complete; D_A fully read
       if (tid == 0) stamp(it, 6);
+      // ---- T = (I - A)^-1 for the unit-lower-triangular 64x64 system, blocked 16 -> 32 -> 64, all 128 threads, fp32:
+      //   level 0  the four diagonal blocks D_b = (I - A_bb)^-1 by forward substitution (thread = one column of one block)
+      //   level 1  T[1][0] = D_1 (A_10 D_0),  T[3][2] = D_3 (A_32 D_2)                      (16x16x16 products)
+      //   level 2  T[2:4][0:2] = T_hi (A_lo T_lo)                                           (32x32x32 products)
+      for (int idx = tid; idx < 64 * (kPLdAT / 4); idx += 128) reinterpret_cast<float4*>(sT)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      named_bar_sync(2, 128);
       if (tid < 64) {
-        // row c of T = column c of X = T^T, (I - A^T) X = I by back substitution; A^T row i is read as broadcast float4
-        const int c = tid;
-        float x[64];
+        const int b = tid >> 4, cc = tid & 15;
+        const float* Ab = sA + (16 * b) * kPLdAT + 16 * b;
+        float x[16];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) x[j] = (j == c) ? 1.f : 0.f;
+        for (int r = 0; r < 16; ++r) {
+          float a0 = (r == cc) ? 1.f : 0.f, a1 = 0.f;
 #pragma unroll
-        for (int ii = 62; ii >= 0; --ii) {
-          // x[ii] starts as the identity entry; A^T[ii][j] is only defined for j > ii (strictly lower part of A).  Four
-          // independent partial sums: the row's FMA chain would otherwise be up to 63 dependent operations long.
-          float a0 = x[ii], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-          const float* arow = sAT + ii * kPLdAT;
-#pragma unroll
-          for (int j4 = (ii + 1) / 4; j4 < 16; ++j4) {
-            const float4 av = *reinterpret_cast<const float4*>(arow + 4 * j4);
-            if (4 * j4 + 0 > ii) a0 = fmaf(av.x, x[4 * j4 + 0], a0);
-            if (4 * j4 + 1 > ii) a1 = fmaf(av.y, x[4 * j4 + 1], a1);
-            if (4 * j4 + 2 > ii) a2 = fmaf(av.z, x[4 * j4 + 2], a2);
-            if (4 * j4 + 3 > ii) a3 = fmaf(av.w, x[4 * j4 + 3], a3);
+          for (int j = 0; j < r; ++j) {
+            if (j & 1) a1 = fmaf(Ab[r * kPLdAT + j], x[j], a1);
+            else a0 = fmaf(Ab[r * kPLdAT + j], x[j], a0);
           }
-          x[ii] = (ii > c) ? 0.f : (a0 + a1) + (a2 + a3);
+          x[r] = a0 + a1;
+          sT[(16 * b + r) * kPLdAT + 16 * b + cc] = x[r];
         }
-        if (tid == 0) stamp(it, 7);
-        // T' = T diag(beta), T'' = T diag(beta e^gcum) as hi/lo K-major SW128 rows
+      }
+      named_bar_sync(2, 128);
+      {                                       // level 1, stage 1: P_p = A[2p+1][2p] D_2p ; stage 2: T[2p+1][2p] = D_2p+1 P_p
+        const int pp = tid >> 6, r = (tid & 63) >> 2, c0 = (tid & 3) * 4;
+        const float* Ar = sA + (32 * pp + 16 + r) * kPLdAT + 32 * pp;
+        const float* Dl = sT + (32 * pp) * kPLdAT + 32 * pp + c0;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float av = Ar[k];
+          const float4 dv = *reinterpret_cast<const float4*>(Dl + k * kPLdAT);
+          acc[0] = fmaf(av, dv.x, acc[0]); acc[1] = fmaf(av, dv.y, acc[1]); acc[2] = fmaf(av, dv.z, acc[2]); acc[3] = fmaf(av, dv.w, acc[3]);
+        }
+        *reinterpret_cast<float4*>(sP + (16 * pp + r) * kPLdP + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        named_bar_sync(2, 128);
+        const float* Dr = sT + (32 * pp + 16 + r) * kPLdAT + 32 * pp + 16;
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float dv = Dr[k];
+          const float4 pv = *reinterpret_cast<const float4*>(sP + (16 * pp + k) * kPLdP + c0);
+          out[0] = fmaf(dv, pv.x, out[0]); out[1] = fmaf(dv, pv.y, out[1]); out[2] = fmaf(dv, pv.z, out[2]); out[3] = fmaf(dv, pv.w, out[3]);
+        }
+        named_bar_sync(2, 128);               // every thread has read D / P before T[2p+1][2p] is written next to D
+        *reinterpret_cast<float4*>(sT + (32 * pp + 16 + r) * kPLdAT + 32 * pp + c0) = make_float4(out[0], out[1], out[2], out[3]);
+      }
+      named_bar_sync(2, 128);
+      {                                       // level 2: P = A[32:64][0:32] T[0:32][0:32] ; T[32:64][0:32] = T[32:64][32:64] P
+        const int r = tid >> 2, c0 = (tid & 3) * 8;
+        const float* Ar = sA + (32 + r) * kPLdAT;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+          const float av = Ar[k];
+          const float4 t0 = *reinterpret_cast<const float4*>(sT + k * kPLdAT + c0), t1 = *reinterpret_cast<const float4*>(sT + k * kPLdAT + c0 + 4);
+          acc[0] = fmaf(av, t0.x, acc[0]); acc[1] = fmaf(av, t0.y, acc[1]); acc[2] = fmaf(av, t0.z, acc[2]); acc[3] = fmaf(av, t0.w, acc[3]);
+          acc[4] = fmaf(av, t1.x, acc[4]); acc[5] = fmaf(av, t1.y, acc[5]); acc[6] = fmaf(av, t1.z, acc[6]); acc[7] = fmaf(av, t1.w, acc[7]);
+        }
+        *reinterpret_cast<float4*>(sP + r * kPLdP + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(sP + r * kPLdP + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        named_bar_sync(2, 128);
+        const float* Tr = sT + (32 + r) * kPLdAT + 32;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+          const float tv = Tr[k];
+          const float4 p0 = *reinterpret_cast<const float4*>(sP + k * kPLdP + c0), p1 = *reinterpret_cast<const float4*>(sP + k * kPLdP + c0 + 4);
+          acc[0] = fmaf(tv, p0.x, acc[0]); acc[1] = fmaf(tv, p0.y, acc[1]); acc[2] = fmaf(tv, p0.z, acc[2]); acc[3] = fmaf(tv, p0.w, acc[3]);
+          acc[4] = fmaf(tv, p1.x, acc[4]); acc[5] = fmaf(tv, p1.y, acc[5]); acc[6] = fmaf(tv, p1.z, acc[6]); acc[7] = fmaf(tv, p1.w, acc[7]);
+        }
+        *reinterpret_cast<float4*>(sT + (32 + r) * kPLdAT + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(sT + (32 + r) * kPLdAT + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      named_bar_sync(2, 128);
+      if (tid == 0) stamp(it, 7);
+      {
+        // T' = T diag(beta), T'' = T diag(beta e^gcum) as hi/lo K-major SW128 rows: thread (row c = tid & 63, column half tid >> 6)
+        const int c = tid & 63, hf = tid >> 6;
+        const float* trow = sT + c * kPLdAT + hf * 32;
         uint8_t* i1 = smem + kPOffImg1 + c * 128;
         uint8_t* i2 = smem + kPOffImg2 + c * 128;
 #pragma unroll
-        for (int q8 = 0; q8 < 8; ++q8) {
+        for (int q8 = 0; q8 < 4; ++q8) {
+          const float4 ta = *reinterpret_cast<const float4*>(trow + q8 * 8), tb = *reinterpret_cast<const float4*>(trow + q8 * 8 + 4);
+          const float tx[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
           uint32_t h1[4], l1[4], h2[4], l2[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = q8 * 8 + 2 * e;
+            const int j = hf * 32 + q8 * 8 + 2 * e;
             unsigned short a0, b0, a1, b1;
-            split_bf16(x[j] * sbeta[j], a0, b0);
-            split_bf16(x[j + 1] * sbeta[j + 1], a1, b1);
+            split_bf16(tx[2 * e] * sbeta[j], a0, b0);
+            split_bf16(tx[2 * e + 1] * sbeta[j + 1], a1, b1);
             h1[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
             l1[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
-            split_bf16(x[j] * secol[j], a0, b0);
-            split_bf16(x[j + 1] * secol[j + 1], a1, b1);
+            split_bf16(tx[2 * e] * secol[j], a0, b0);
+            split_bf16(tx[2 * e + 1] * secol[j + 1], a1, b1);
             h2[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
             l2[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
           }
-          const int chunk = (q8 ^ (c & 7)) << 4;
+          const int chunk = ((hf * 4 + q8) ^ (c & 7)) << 4;
           *reinterpret_cast<uint4*>(i1 + chunk) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
           *reinterpret_cast<uint4*>(i1 + 8192 + chunk) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
           *reinterpret_cast<uint4*>(i2 + chunk) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
@@ -973,7 +1047,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         }
         fence_proxy_async_smem();
         mbar_arrive(img_ready);
-        p.gcum[hc * kTC + i] = g_i;
+        if (tid < 64) p.gcum[hc * kTC + i] = g_i;
         if (tid == 0) stamp(it, 8);
       }
       mbar_wait(bc_done, up);
