@@ -565,7 +565,7 @@ static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32
   g2.wq_expert_stride = (long long)(tiled_bytes(e, 2) / e->e_local);
   g2.ws_expert_stride = (long long)(tiled_bytes(e, 3) / e->e_local);
   g2.n_kblocks = I / kBlockK;
-  g2.items_per_chunk = H / kTileRows; g2.tile1_offset = 0; g2.tile0_mul = 1;   // one 128-row tile per item (double-buffered accumulator)
+  g2.items_per_chunk = H / (2 * kTileRows); g2.tile1_offset = 1; g2.tile0_mul = 2;
   g2.chunks = e->chunks; g2.n_chunks = e->n_chunks;
   g2.out = (__nv_bfloat16*)e->c3; g2.out_ld = H; g2.slot_weight = e->sorted_w;
   { ProfSpan ps(e, KB2_PROF_GEMM2, s);

@@ -92,14 +92,13 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k, int chunk_stride) 
   return (uint32_t)((k >> 6) * chunk_stride + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1)));
 }
 
-// x = hi + lo with hi = bf16_rne(x) and lo = bf16_trunc(x - hi): |x - hi - lo| <= 2^-17 |x|.  Integer rounding on purpose:
-// F2F.BF16.F32 runs on a quarter-rate unit and 64-128 conversions per thread and chunk were the largest single cost of the
-// CUDA-core phases (profiles/r02a_gdn_scan_tc_stalls.txt).
+// x = hi + lo with hi = bf16_rne(x), lo = bf16_rne(x - hi): |x - hi - lo| <= 2^-17 |x|.  (An integer-arithmetic variant with a
+// truncated lo was measured slower — 340 vs 318 us per scan — so the conversions are not what bounds the CUDA-core phases.)
 __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
-  const uint32_t u = __float_as_uint(x);
-  const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
-  hi = (unsigned short)(r >> 16);
-  lo = (unsigned short)(__float_as_uint(x - __uint_as_float(r & 0xFFFF0000u)) >> 16);
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = *reinterpret_cast<const unsigned short*>(&h);
+  lo = *reinterpret_cast<const unsigned short*>(&l);
 }
 
 struct GdnTcParams {
@@ -610,6 +609,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         tmem_ld32(lane_addr + kColD1, a);
         tmem_ld32(lane_addr + kColD1b, b);
         tmem_ld_wait();
+        if (tid == 64) stamp(c, 10);
 #pragma unroll
         for (int j4 = 0; j4 < kTSV / 4; ++j4) {
           const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + 4 * j4);
@@ -627,8 +627,10 @@ __global__ void __launch_bounds__(kTThreads, 1)
 #pragma unroll
         for (int j = 0; j < kTSV; ++j) it[j] = eg * __uint_as_float(a[j]);
       }
+      if (tid == 64) stamp(c, 11);
       tc_fence_before_sync();
       named_bar_sync(1, 128);
+      if (tid == 0) stamp(c, 12);
       {                                        // all four warps: token i, 16 of the 32 columns -> hi/lo operand tiles
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
@@ -648,7 +650,9 @@ __global__ void __launch_bounds__(kTThreads, 1)
           }
         }
       }
+      if (tid == 0) stamp(c, 13);
       fence_proxy_async_smem();
+      if (tid == 0) stamp(c, 14);
       mbar_arrive(v_ready);
       if (tid == 0) stamp(c, 5);
       mbar_wait(g2_done, cp);
@@ -661,6 +665,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
 #pragma unroll
         for (int j = 0; j < kTSV; ++j) s[j] = fmaf(d_last, s[j], __uint_as_float(a[j]));
       }
+      if (tid == 0) stamp(c, 15);
       if (c + 1 < n_chunks) {
         write_s_tiles();
         tc_fence_before_sync();

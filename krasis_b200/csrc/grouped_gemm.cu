@@ -39,8 +39,7 @@ namespace kb2 {
 
 constexpr int kNumThreads = 512;
 constexpr int kStagesA = 2;                                     // A operand stages in TMEM
-constexpr int kStagesB1 = 3;                                    // token (B operand) ring in smem, gate/up GEMM
-constexpr int kStagesB2 = 4;                                    // down GEMM (consumes two B stages per weight stage)
+constexpr int kStagesB = 3;                                     // token (B operand) ring in smem
 constexpr int kBStageBytes = kMaxChunkTokens * kBlockK * 2;     // 24 KB
 constexpr int kBBoxRows = 32;                                   // TMA box = 32 token rows x 64 K
 constexpr int kBBoxBytes = kBBoxRows * kBlockK * 2;             // 4 KB
@@ -85,14 +84,12 @@ template <int FMT, bool kGemm1>
 struct SmemLayout {
   static constexpr int kStagesW = Fmt<FMT>::kStagesW;
   static constexpr int kWStageBytes = 2 * Fmt<FMT>::kTileBytes + (kHasScaleTiles<FMT> ? 2 * kScaleTileBytes : 0);
-  static constexpr int kStagesB = kGemm1 ? kStagesB1 : kStagesB2;
-  // epilogue staging: gate/up = 512 B per token (gate tile | up tile); down = 256 B per token (one 128-row tile)
-  static constexpr int kStageRowBytes = (kGemm1 ? 2 : 1) * kTileRows * 2;
+  static constexpr int kStageRowBytes = 2 * kTileRows * 2;   // epilogue staging: 512 B per token (gate|up or two down tiles)
   static constexpr int kOffB = 0;                                               // 1024-aligned (swizzle atoms)
   static constexpr int kOffStage = kOffB + kStagesB * kBStageBytes;
   static constexpr int kOffW = kOffStage + kMaxChunkTokens * kStageRowBytes;
   static constexpr int kOffBar = kOffW + kStagesW * kWStageBytes;
-  static constexpr int kNumBars = 2 * kStagesW + 2 * kStagesA + 2 * kStagesB + 4;
+  static constexpr int kNumBars = 2 * kStagesW + 2 * kStagesA + 2 * kStagesB + 2;
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
   static_assert(kTotal <= 227 * 1024, "CTA shared memory exceeds the 227 KB sm_100 limit");
@@ -129,7 +126,6 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     grouped_gemm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_b) {
   using L = SmemLayout<FMT, kGemm1>;
   constexpr int kStagesW = L::kStagesW;
-  constexpr int kStagesB = L::kStagesB;
   constexpr int TB = Fmt<FMT>::kTileBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
@@ -139,8 +135,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   uint64_t* a_empty = a_full + kStagesA;
   uint64_t* b_full = a_empty + kStagesA;
   uint64_t* b_empty = b_full + kStagesB;
-  uint64_t* tmem_full = b_empty + kStagesB;      // [2]: the down GEMM double-buffers its accumulator (gate/up uses [0])
-  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint64_t* tmem_full = b_empty + kStagesB;
+  uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
 
   const int warp = threadIdx.x >> 5;
@@ -160,10 +156,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kNumEpiThreads);
-    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kNumEpiThreads);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_ptr_smem, kTmemCols);
@@ -176,10 +170,6 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   const int n_chunks = *p.n_chunks;
   const int n_items = n_chunks * p.items_per_chunk;
   const int nkb = p.n_kblocks;
-  // Weight stages per item.  gate/up: one per k-block, holding the gate tile and the up tile (two accumulators).  down: one
-  // per PAIR of k-blocks of a single 128-row tile (one accumulator, double-buffered across items): the two dequant groups
-  // still work in parallel, the accumulator drain of item i overlaps the MMAs of item i+1.
-  const int n_wst = kGemm1 ? nkb : nkb / 2;
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight-tile producer (bulk TMA)
@@ -192,28 +182,17 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         const uint8_t* wq_e = p.wq + (long long)cd.expert * p.wq_expert_stride;
         const uint8_t* ws_e = p.ws + (long long)cd.expert * p.ws_expert_stride;
         const int ngroups = nkb / 2;
-        for (int ws = 0; ws < n_wst; ++ws) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&w_empty[rw.stage], rw.phase ^ 1);
           uint8_t* dst = smem + L::kOffW + rw.stage * L::kWStageBytes;
           mbar_arrive_expect_tx(&w_full[rw.stage], L::kWStageBytes);
-          if constexpr (kGemm1) {
-            const int kb = ws;
-            bulk_g2s(dst, wq_e + ((long long)t0 * nkb + kb) * TB, TB, &w_full[rw.stage]);
-            bulk_g2s(dst + TB, wq_e + ((long long)t1 * nkb + kb) * TB, TB, &w_full[rw.stage]);
-            if constexpr (kHasScaleTiles<FMT>) {
-              bulk_g2s(dst + 2 * TB, ws_e + ((long long)t0 * ngroups + (kb >> 1)) * kScaleTileBytes, kScaleTileBytes,
-                       &w_full[rw.stage]);
-              bulk_g2s(dst + 2 * TB + kScaleTileBytes, ws_e + ((long long)t1 * ngroups + (kb >> 1)) * kScaleTileBytes,
-                       kScaleTileBytes, &w_full[rw.stage]);
-            }
-          } else {
-            // k-blocks 2ws, 2ws+1 of tile rt are adjacent blobs; both belong to scale group ws (128 columns)
-            bulk_g2s(dst, wq_e + ((long long)rt * nkb + 2 * ws) * TB, 2 * TB, &w_full[rw.stage]);
-            if constexpr (kHasScaleTiles<FMT>) {
-              const uint8_t* sc = ws_e + ((long long)rt * ngroups + ws) * kScaleTileBytes;
-              bulk_g2s(dst + 2 * TB, sc, kScaleTileBytes, &w_full[rw.stage]);
-              bulk_g2s(dst + 2 * TB + kScaleTileBytes, sc, kScaleTileBytes, &w_full[rw.stage]);
-            }
+          bulk_g2s(dst, wq_e + ((long long)t0 * nkb + kb) * TB, TB, &w_full[rw.stage]);
+          bulk_g2s(dst + TB, wq_e + ((long long)t1 * nkb + kb) * TB, TB, &w_full[rw.stage]);
+          if constexpr (kHasScaleTiles<FMT>) {
+            bulk_g2s(dst + 2 * TB, ws_e + ((long long)t0 * ngroups + (kb >> 1)) * kScaleTileBytes, kScaleTileBytes,
+                     &w_full[rw.stage]);
+            bulk_g2s(dst + 2 * TB + kScaleTileBytes, ws_e + ((long long)t1 * ngroups + (kb >> 1)) * kScaleTileBytes,
+                     kScaleTileBytes, &w_full[rw.stage]);
           }
           rw.advance(kStagesW);
         }
@@ -225,58 +204,31 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     if (lane == 0) {
       Ring ra, rb;
       uint32_t tphase = 0;
-      int acc_it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
         const uint32_t n_pad = (uint32_t)((cd.n_tok + 15) & ~15);
         const uint32_t idesc = umma_idesc_bf16_m128(n_pad);
-        if constexpr (kGemm1) {
-          mbar_wait(&tmem_empty[0], tphase ^ 1);
+        mbar_wait(tmem_empty, tphase ^ 1);
+        tc_fence_after_sync();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&a_full[ra.stage], ra.phase);
+          mbar_wait(&b_full[rb.stage], rb.phase);
           tc_fence_after_sync();
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&a_full[ra.stage], ra.phase);
-            mbar_wait(&b_full[rb.stage], rb.phase);
-            tc_fence_after_sync();
-            const uint32_t a_t = tmem_base + kATmemCol + ra.stage * 2 * kATileCols;
-            const uint64_t b0 = umma_desc_k_sw128(smem_u32(smem + L::kOffB + rb.stage * kBStageBytes));
+          const uint32_t a_t = tmem_base + kATmemCol + ra.stage * 2 * kATileCols;
+          const uint64_t b0 = umma_desc_k_sw128(smem_u32(smem + L::kOffB + rb.stage * kBStageBytes));
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-              umma_bf16_ts(tmem_base, a_t + 8 * k, b0 + 2 * k, idesc, acc);
-              umma_bf16_ts(tmem_base + kAcc1Col, a_t + kATileCols + 8 * k, b0 + 2 * k, idesc, acc);
-            }
-            umma_commit(&a_empty[ra.stage]);
-            umma_commit(&b_empty[rb.stage]);
-            ra.advance(kStagesA);
-            rb.advance(kStagesB);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_bf16_ts(tmem_base, a_t + 8 * k, b0 + 2 * k, idesc, acc);
+            umma_bf16_ts(tmem_base + kAcc1Col, a_t + kATileCols + 8 * k, b0 + 2 * k, idesc, acc);
           }
-          umma_commit(&tmem_full[0]);
-          tphase ^= 1;
-        } else {
-          const int set = acc_it & 1;
-          mbar_wait(&tmem_empty[set], (((uint32_t)acc_it >> 1) & 1u) ^ 1u);
-          tc_fence_after_sync();
-          const uint32_t d_t = tmem_base + set * kAcc1Col;
-          for (int ws = 0; ws < n_wst; ++ws) {
-            mbar_wait(&a_full[ra.stage], ra.phase);
-            const uint32_t a_t = tmem_base + kATmemCol + ra.stage * 2 * kATileCols;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {               // A tile `half` of the stage = k-block 2ws + half
-              mbar_wait(&b_full[rb.stage], rb.phase);
-              tc_fence_after_sync();
-              const uint64_t b0 = umma_desc_k_sw128(smem_u32(smem + L::kOffB + rb.stage * kBStageBytes));
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16_ts(d_t, a_t + half * kATileCols + 8 * k, b0 + 2 * k, idesc, (ws > 0 || half > 0 || k > 0) ? 1u : 0u);
-              umma_commit(&b_empty[rb.stage]);
-              rb.advance(kStagesB);
-            }
-            umma_commit(&a_empty[ra.stage]);
-            ra.advance(kStagesA);
-          }
-          umma_commit(&tmem_full[set]);
-          ++acc_it;
+          umma_commit(&a_empty[ra.stage]);
+          umma_commit(&b_empty[rb.stage]);
+          ra.advance(kStagesA);
+          rb.advance(kStagesB);
         }
+        umma_commit(tmem_full);
+        tphase ^= 1;
       }
     }
     __syncwarp();
@@ -341,7 +293,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     Ring rw, ra;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kATmemCol + tile * kATileCols;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      for (int ws = 0; ws < n_wst; ++ws) {
+      for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&w_full[rw.stage], rw.phase);
         const uint8_t* wsrc = smem + L::kOffW + rw.stage * L::kWStageBytes;
         __nv_bfloat16 s = __float2bfloat16_rn(0.f);
@@ -467,49 +419,36 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     uint8_t* stage = smem + L::kOffStage;
     constexpr int kRowB = L::kStageRowBytes;   // 512
     uint32_t tphase = 0;
-    int acc_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
       const int rt = item % p.items_per_chunk;
       const int n_pad = (cd.n_tok + 15) & ~15;
+      mbar_wait(tmem_full, tphase);
+      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      if constexpr (kGemm1) {
-        mbar_wait(&tmem_full[0], tphase);
-        tc_fence_after_sync();
-        for (int c0 = 0; c0 < n_pad; c0 += 16) {
-          uint32_t r0v[16], r1v[16];
-          tmem_ld16(taddr + c0, r0v);
-          tmem_ld16(taddr + kAcc1Col + c0, r1v);
-          tmem_ld_wait();
+      for (int c0 = 0; c0 < n_pad; c0 += 16) {
+        uint32_t r0v[16], r1v[16];
+        tmem_ld16(taddr + c0, r0v);
+        tmem_ld16(taddr + kAcc1Col + c0, r1v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + (c0 + j) * kRowB);
-            srow[row] = __float2bfloat16_rn(__uint_as_float(r0v[j]));
-            srow[kTileRows + row] = __float2bfloat16_rn(__uint_as_float(r1v[j]));
-          }
-        }
-        tc_fence_before_sync();
-        mbar_arrive(&tmem_empty[0]);             // accumulators drained: the next tile's MMAs may start
-        tphase ^= 1;
-      } else {
-        const int set = acc_it & 1;
-        mbar_wait(&tmem_full[set], ((uint32_t)acc_it >> 1) & 1u);
-        tc_fence_after_sync();
-        for (int c0 = 0; c0 < n_pad; c0 += 16) {
-          uint32_t r0v[16];
-          tmem_ld16(taddr + set * kAcc1Col + c0, r0v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int tok = c0 + j;
+        for (int j = 0; j < 16; ++j) {
+          const int tok = c0 + j;
+          float v0 = __uint_as_float(r0v[j]);
+          float v1 = __uint_as_float(r1v[j]);
+          if constexpr (!kGemm1) {
             const float wgt = (tok < cd.n_tok) ? p.slot_weight[cd.slot_begin + tok] : 0.f;
-            reinterpret_cast<__nv_bfloat16*>(stage + tok * kRowB)[row] = __float2bfloat16_rn(__uint_as_float(r0v[j]) * wgt);
+            v0 *= wgt;
+            v1 *= wgt;
           }
+          __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + tok * kRowB);
+          srow[row] = __float2bfloat16_rn(v0);
+          srow[kTileRows + row] = __float2bfloat16_rn(v1);
         }
-        tc_fence_before_sync();
-        mbar_arrive(&tmem_empty[set]);           // this accumulator is free; the other one is already being filled
-        ++acc_it;
       }
+      tc_fence_before_sync();
+      mbar_arrive(tmem_empty);                 // accumulators drained: the next tile's MMAs may start
+      tphase ^= 1;
       named_bar_sync(1, kNumEpiThreads);       // staging tile complete
       if constexpr (kGemm1) {
         // 16 outputs per step: gate chunk v and up chunk v of one token -> 8 activations (16 B store)
@@ -531,12 +470,12 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           *reinterpret_cast<uint4*>(p.out + (long long)(cd.slot_begin + tok) * p.out_ld + (long long)rt * kTileRows + v * 8) = o4;
         }
       } else {
-        constexpr int kVecPerRow = kTileRows / 8;          // 16
+        constexpr int kVecPerRow = 2 * kTileRows / 8;      // 32
         const int n_vec = cd.n_tok * kVecPerRow;
         for (int idx = et; idx < n_vec; idx += kNumEpiThreads) {
           const int tok = idx / kVecPerRow, v = idx % kVecPerRow;
           const uint4 val = *reinterpret_cast<const uint4*>(stage + tok * kRowB + v * 16);
-          *reinterpret_cast<uint4*>(p.out + (long long)(cd.slot_begin + tok) * p.out_ld + (long long)rt * kTileRows + v * 8) = val;
+          *reinterpret_cast<uint4*>(p.out + (long long)(cd.slot_begin + tok) * p.out_ld + (long long)rt * 2 * kTileRows + v * 8) = val;
         }
       }
       named_bar_sync(1, kNumEpiThreads);       // staging free again

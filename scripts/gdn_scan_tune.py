@@ -1,7 +1,8 @@
 """Tuning harness for the tcgen05 GDN chunk scan (GPU): per-kernel times of one QCN-geometry GDN layer at 8192 tokens for
 the accumulator schemes (KB2_GDN_SCAN_SPLIT=0/1) and a clock64 timeline of one CTA (KB2_GDN_SCAN_TRACE).
 Slots: MMA thread 0 s_ready seen, 1 G1 issued, 2 v_ready seen, 3 G2+G3 issued; core thread 0: 4 g1_done seen, 5 v tiles written,
-6 g2_done seen, 7 S tiles written, 8 g3_done seen, 9 epilogue done."""
+6 g2_done seen, 7 S tiles written, 8 g3_done seen, 9 epilogue done; layout 2 only: 10 VP loaded (thread 64), 11 v parked, 12 after the
+128-thread barrier, 13 tiles stored, 14 after fence.proxy.async, 15 state row updated."""
 import os
 import sys
 import types
@@ -44,7 +45,7 @@ for split in ("0", "2"):                                   # "0": first layout, 
     lay.forward(x)
     torch.cuda.synchronize()
     del os.environ["KB2_GDN_SCAN_TRACE"]
-    t = trace.cpu().view(8, 16)[:, :10]
+    t = trace.cpu().view(8, 16)
     base = t[:, 0:1]
     print("  timeline (cycles since the MMA thread saw s_ready), chunks 8..15:")
     for r in (t - base).tolist():
