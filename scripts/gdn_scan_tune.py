@@ -25,9 +25,9 @@ cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_v
 lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
 x = torch.randn(M, H).to(bf).cuda()
 outs = {}
-for split in ("0", "2"):                                   # "0": first layout, chained accumulators; "2": second layout
+for split in ("1", "2", "3"):                              # operand / warp layouts of the tcgen05 scan (gdn_tc.cu)
     os.environ["KB2_GDN_SCAN_SPLIT"] = "0"
-    os.environ["KB2_GDN_SCAN_LAYOUT"] = "2" if split == "2" else "1"
+    os.environ["KB2_GDN_SCAN_LAYOUT"] = split
     for _ in range(3):
         lay.reset_state()
         lay.forward(x)
@@ -38,7 +38,7 @@ for split in ("0", "2"):                                   # "0": first layout, 
     prof = capi.kernel_profile_collect()
     capi.kernel_profile(False)
     outs[split] = y.float()
-    print(f"split={split}: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]) if n.startswith("gdn")))
+    print(f"layout={split}: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]) if n.startswith("gdn")))
     trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
     os.environ["KB2_GDN_SCAN_TRACE"] = str(trace.data_ptr())
     lay.reset_state()
@@ -51,7 +51,7 @@ for split in ("0", "2"):                                   # "0": first layout, 
     for r in (t - base).tolist():
         print("   ", r)
     print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
-print("max |layout1 - layout2| / max:", ((outs["0"] - outs["2"]).abs().max() / outs["0"].abs().max()).item())
+print("max |layout1 - layout3| / max:", ((outs["1"] - outs["3"]).abs().max() / outs["1"].abs().max()).item())
 os.environ.pop("KB2_GDN_SCAN_LAYOUT", None)
 
 # ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,
