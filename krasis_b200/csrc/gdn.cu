@@ -27,7 +27,7 @@ struct GdnDims {
   int ba_ld;                  // row stride of the ba projection output (2*nv rounded up to 16)
 };
 
-__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf16r(float x) { return bf16_round_rn(x); }
 
 // column of mixed_qkvz (per key-head group [q dk | k dk | v r*dv | z r*dv]) holding conv channel c
 __device__ __forceinline__ int qkvz_col(const GdnDims& d, int c) {
@@ -385,10 +385,10 @@ __device__ __forceinline__ uint32_t prep_sw128_off(int row, int k) {       // el
   return (uint32_t)((k >> 6) * 8192 + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1)));
 }
 __device__ __forceinline__ void prep_split_bf16(float x, unsigned short& hi, unsigned short& lo) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-  hi = *reinterpret_cast<const unsigned short*>(&h);
-  lo = *reinterpret_cast<const unsigned short*>(&l);
+  const uint32_t h = bf16_bits_rn(x);                                     // packed converter, not the quarter-rate F2F (ptx.cuh)
+  const uint32_t l = bf16_bits_rn(x - __uint_as_float(h << 16));
+  hi = (unsigned short)h;
+  lo = (unsigned short)l;
 }
 
 template <bool TC>

@@ -92,13 +92,14 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k, int chunk_stride) 
   return (uint32_t)((k >> 6) * chunk_stride + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1)));
 }
 
-// x = hi + lo with hi = bf16_rne(x), lo = bf16_rne(x - hi): |x - hi - lo| <= 2^-17 |x|.  (An integer-arithmetic variant with a
-// truncated lo was measured slower — 340 vs 318 us per scan — so the conversions are not what bounds the CUDA-core phases.)
+// x = hi + lo with hi = bf16_rne(x), lo = bf16_rne(x - hi): |x - hi - lo| <= 2^-17 |x|.  Both conversions go through the packed
+// converter (bf16_bits_rn, ptx.cuh): the F2F.BF16.F32 nvcc emitted for the hi half issues at quarter rate and was the bound of the
+// tile-writing phases.  (An integer-arithmetic variant with a truncated lo was measured slower, 340 vs 318 us per scan.)
 __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-  hi = *reinterpret_cast<const unsigned short*>(&h);
-  lo = *reinterpret_cast<const unsigned short*>(&l);
+  const uint32_t h = bf16_bits_rn(x);
+  const uint32_t l = bf16_bits_rn(x - __uint_as_float(h << 16));
+  hi = (unsigned short)h;
+  lo = (unsigned short)l;
 }
 
 struct GdnTcParams {

@@ -29,7 +29,7 @@ struct GqaDims {
   float theta, eps;
 };
 
-__device__ __forceinline__ float bf16r_(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf16r_(float x) { return bf16_round_rn(x); }
 
 // ------------------------------------------------------------------------------------------------
 // prep: one CTA per token, one warp per head (q heads then k heads then v heads)

@@ -31,6 +31,8 @@
 // fp32 accumulation in TMEM, BF16 rounding at C1, A and C3.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "moe_common.cuh"
 #include "prof.cuh"
 #include "ptx.cuh"
@@ -88,7 +90,8 @@ struct SmemLayout {
   static constexpr int kOffB = 0;                                               // 1024-aligned (swizzle atoms)
   static constexpr int kOffStage = kOffB + kStagesB * kBStageBytes;
   static constexpr int kOffW = kOffStage + kMaxChunkTokens * kStageRowBytes;
-  static constexpr int kOffBar = kOffW + kStagesW * kWStageBytes;
+  static constexpr int kOffSlotW = kOffW + kStagesW * kWStageBytes;             // GEMM2: routing weight of the chunk's token slots (f32)
+  static constexpr int kOffBar = kOffSlotW + kMaxChunkTokens * 4;
   static constexpr int kNumBars = 2 * kStagesW + 2 * kStagesA + 2 * kStagesB + 2;
   static constexpr int kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
@@ -170,6 +173,11 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   const int n_chunks = *p.n_chunks;
   const int n_items = n_chunks * p.items_per_chunk;
   const int nkb = p.n_kblocks;
+  // tuning aid: per work item of CTA 0, slot = clock64 stamp or accumulated wait cycles (see scripts/gemm_trace.py)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int it, int slot, long long v) {
+    if (tracing && it < 16) p.trace[it * 16 + slot] = v;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight-tile producer (bulk TMA)
@@ -182,8 +190,11 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         const uint8_t* wq_e = p.wq + (long long)cd.expert * p.wq_expert_stride;
         const uint8_t* ws_e = p.ws + (long long)cd.expert * p.ws_expert_stride;
         const int ngroups = nkb / 2;
+        long long wacc = 0;
         for (int kb = 0; kb < nkb; ++kb) {
+          const long long c0 = tracing ? clock64() : 0;
           mbar_wait(&w_empty[rw.stage], rw.phase ^ 1);
+          if (tracing) wacc += clock64() - c0;
           uint8_t* dst = smem + L::kOffW + rw.stage * L::kWStageBytes;
           mbar_arrive_expect_tx(&w_full[rw.stage], L::kWStageBytes);
           bulk_g2s(dst, wq_e + ((long long)t0 * nkb + kb) * TB, TB, &w_full[rw.stage]);
@@ -196,6 +207,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           }
           rw.advance(kStagesW);
         }
+        stamp(item / (int)gridDim.x, 12, wacc);
       }
     }
     __syncwarp();
@@ -208,11 +220,18 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
         const uint32_t n_pad = (uint32_t)((cd.n_tok + 15) & ~15);
         const uint32_t idesc = umma_idesc_bf16_m128(n_pad);
+        const int ti = item / (int)gridDim.x;
+        stamp(ti, 0, tracing ? clock64() : 0);
         mbar_wait(tmem_empty, tphase ^ 1);
         tc_fence_after_sync();
+        stamp(ti, 1, tracing ? clock64() : 0);
+        long long wa = 0, wb = 0;
         for (int kb = 0; kb < nkb; ++kb) {
+          const long long c0 = tracing ? clock64() : 0;
           mbar_wait(&a_full[ra.stage], ra.phase);
+          const long long c1 = tracing ? clock64() : 0;
           mbar_wait(&b_full[rb.stage], rb.phase);
+          if (tracing) { wa += c1 - c0; wb += clock64() - c1; }
           tc_fence_after_sync();
           const uint32_t a_t = tmem_base + kATmemCol + ra.stage * 2 * kATileCols;
           const uint64_t b0 = umma_desc_k_sw128(smem_u32(smem + L::kOffB + rb.stage * kBStageBytes));
@@ -228,6 +247,10 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           rb.advance(kStagesB);
         }
         umma_commit(tmem_full);
+        stamp(ti, 2, tracing ? clock64() : 0);
+        stamp(ti, 3, wa);
+        stamp(ti, 4, wb);
+        stamp(ti, 14, (long long)cd.n_tok);
         tphase ^= 1;
       }
     }
@@ -273,14 +296,18 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
         const int n_pad = (cd.n_tok + 15) & ~15;
         const int n_box = (n_pad + kBBoxRows - 1) / kBBoxRows;
+        long long bacc = 0;
         for (int kb = 0; kb < nkb; ++kb) {
+          const long long c0 = tracing ? clock64() : 0;
           mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
+          if (tracing) bacc += clock64() - c0;
           uint8_t* dst = smem + L::kOffB + rb.stage * kBStageBytes;
           mbar_arrive_expect_tx(&b_full[rb.stage], n_box * kBBoxBytes);
           for (int b = 0; b < n_box; ++b)
             tma_load_2d(dst + b * kBBoxBytes, &tmap_b, kb * kBlockK, cd.slot_begin + b * kBBoxRows, &b_full[rb.stage]);
           rb.advance(kStagesB);
         }
+        stamp(item / (int)gridDim.x, 13, bacc);
       }
     }
     __syncwarp();
@@ -292,9 +319,13 @@ __global__ void __launch_bounds__(kNumThreads, 1)
     const int t = (warp & 3) * 32 + lane;                // weight row within the tile == TMEM lane
     Ring rw, ra;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kATmemCol + tile * kATileCols;
+    const bool dtr = tracing && threadIdx.x == 128;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      long long ww_ = 0, wae = 0, wst = 0;
       for (int kb = 0; kb < nkb; ++kb) {
+        const long long c0 = dtr ? clock64() : 0;
         mbar_wait(&w_full[rw.stage], rw.phase);
+        if (dtr) ww_ += clock64() - c0;
         const uint8_t* wsrc = smem + L::kOffW + rw.stage * L::kWStageBytes;
         __nv_bfloat16 s = __float2bfloat16_rn(0.f);
         if constexpr (kHasScaleTiles<FMT>) s = reinterpret_cast<const __nv_bfloat16*>(wsrc + 2 * TB)[tile * kTileRows + t];
@@ -398,14 +429,21 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           }
         }
         mbar_arrive(&w_empty[rw.stage]);     // packed words are now in registers
+        const long long c1 = dtr ? clock64() : 0;
         mbar_wait(&a_empty[ra.stage], ra.phase ^ 1);
+        const long long c2 = dtr ? clock64() : 0;
         tc_fence_after_sync();
         tmem_st32(lane_base + ra.stage * 2 * kATileCols, o);
         tmem_st_wait();
         tc_fence_before_sync();
         mbar_arrive(&a_full[ra.stage]);
+        if (dtr) { wae += c2 - c1; wst += clock64() - c2; }
         rw.advance(kStagesW);
         ra.advance(kStagesA);
+      }
+      if (dtr) {
+        const int ti = item / (int)gridDim.x;
+        stamp(ti, 8, ww_); stamp(ti, 9, wae); stamp(ti, 10, wst); stamp(ti, 11, clock64());
       }
     }
   } else {
@@ -423,8 +461,18 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
       const int rt = item % p.items_per_chunk;
       const int n_pad = (cd.n_tok + 15) & ~15;
+      if constexpr (!kGemm1) {
+        // routing weights of this chunk -> shared memory while the MMAs run (a global load per accumulator column inside the
+        // drain loop made phase 1 of the down projection 3x longer than the gate/up one: profiles/r02h_gemm_item_timeline.txt)
+        float* sw = reinterpret_cast<float*>(smem + L::kOffSlotW);
+        for (int i = et; i < n_pad; i += kNumEpiThreads) sw[i] = (i < cd.n_tok) ? p.slot_weight[cd.slot_begin + i] : 0.f;
+        named_bar_sync(1, kNumEpiThreads);
+      }
       mbar_wait(tmem_full, tphase);
       tc_fence_after_sync();
+      const bool etr = tracing && et == 0;
+      const int ti = item / (int)gridDim.x;
+      if (etr) stamp(ti, 5, clock64());
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < n_pad; c0 += 16) {
         uint32_t r0v[16], r1v[16];
@@ -437,7 +485,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           float v0 = __uint_as_float(r0v[j]);
           float v1 = __uint_as_float(r1v[j]);
           if constexpr (!kGemm1) {
-            const float wgt = (tok < cd.n_tok) ? p.slot_weight[cd.slot_begin + tok] : 0.f;
+            const float wgt = reinterpret_cast<const float*>(smem + L::kOffSlotW)[tok];
             v0 *= wgt;
             v1 *= wgt;
           }
@@ -448,6 +496,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       }
       tc_fence_before_sync();
       mbar_arrive(tmem_empty);                 // accumulators drained: the next tile's MMAs may start
+      if (etr) stamp(ti, 6, clock64());
       tphase ^= 1;
       named_bar_sync(1, kNumEpiThreads);       // staging tile complete
       if constexpr (kGemm1) {
@@ -479,6 +528,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         }
       }
       named_bar_sync(1, kNumEpiThreads);       // staging free again
+      if (etr) stamp(ti, 7, clock64());
     }
   }
 
@@ -552,7 +602,10 @@ static cudaError_t launch_one(const GemmParams& p, const CUtensorMap& tmap, int 
     once.mark(dev);
   }
   KernelSpan ks(kGemm1 ? K_GEMM1_GATE_UP : K_GEMM2_DOWN, stream);
-  kern<<<num_sms, kNumThreads, smem, stream>>>(p, tmap);
+  GemmParams pp = p;
+  const char* tv = getenv(kGemm1 ? "KB2_GEMM1_TRACE" : "KB2_GEMM2_TRACE");      // tuning only: device pointer to [16][16] int64
+  pp.trace = tv ? reinterpret_cast<long long*>(strtoull(tv, nullptr, 0)) : nullptr;
+  kern<<<num_sms, kNumThreads, smem, stream>>>(pp, tmap);
   return cudaGetLastError();
 }
 

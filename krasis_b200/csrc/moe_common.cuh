@@ -95,6 +95,7 @@ struct GemmParams {
   const float* slot_weight;   // GEMM2: routing weight per sorted slot
   const int* gather_rows;     // GEMM1, gather mode: token row of every sorted slot (the B operand is fetched from the caller's
                               // activation matrix with TMA gather4 instead of a pre-sorted copy); nullptr = B rows are contiguous
+  long long* trace;           // optional (tuning only, KB2_GEMM_TRACE=<device pointer>): clock64 stamps of CTA 0, [item < 16][16]
 };
 
 }  // namespace kb2

@@ -10,6 +10,7 @@
 //                                              (gpu_prefill.py:4471-4482)
 #include "moe_common.cuh"
 #include "prof.cuh"
+#include "ptx.cuh"
 
 namespace kb2 {
 
@@ -304,10 +305,10 @@ __global__ void __launch_bounds__(256) combine_kernel(const __nv_bfloat16* __res
   __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    __nv_bfloat16 r = __float2bfloat16_rn(acc[i]);
-    if (apply_rsf) r = __float2bfloat16_rn(rsf * __bfloat162float(r));
-    if (shared) r = __float2bfloat16_rn(__bfloat162float(r) + __bfloat162float(ps[i]));
-    po[i] = r;
+    float r = bf16_round_rn(acc[i]);                       // every stage rounds to BF16 like the reference's tensor ops
+    if (apply_rsf) r = bf16_round_rn(rsf * r);
+    if (shared) r = bf16_round_rn(r + __bfloat162float(ps[i]));
+    po[i] = __ushort_as_bfloat16((unsigned short)(__float_as_uint(r) >> 16));
   }
   *reinterpret_cast<uint4*>(out + (long long)m * H + v * 8) = o;
 }

@@ -120,6 +120,24 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 }
 // Instruction descriptor for kind::f16, A=B=BF16, D=F32, both K-major, M=128, N=n
 // (cute::UMMA::InstrDescriptor: c_format [4,6)=1 | a_format [7,10)=1 | b_format [10,13)=1 | n>>3 [17,23) | m>>4 [24,29)).
+// bf16 RNE of one float, result in the LOW 16 bits (high bits zero), through the PACKED converter (F2FP.BF16.F32.PACK_AB, full
+// rate).  When the converted value is reused as an integer nvcc picks the single-value F2F.BF16.F32 for __float2bfloat16_rn, which
+// issues on the quarter-rate conversion pipe: 8 issue cycles per warp instruction bounded the CUDA-core phases of the tcgen05
+// Gated-DeltaNet kernels (profiles/r02g_*).
+__device__ __forceinline__ uint32_t bf16_bits_rn(float x) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  return r;
+}
+// round to bf16 and back (the "bf16r" of the numerics contracts) without the quarter-rate F2F
+__device__ __forceinline__ float bf16_round_rn(float x) { return __uint_as_float(bf16_bits_rn(x) << 16); }
+// two floats -> packed bf16x2 {low half = bf16(lo), high half = bf16(hi)}
+__device__ __forceinline__ uint32_t bf16x2_bits_rn(float hi, float lo) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
