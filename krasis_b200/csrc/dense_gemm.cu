@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(kDThreads, 1)
   uint64_t* acc_full = empty + kDStages;     // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle so that the role branches are provably warp-uniform: the single-thread instructions (TMA, tcgen05.mma,
+  // commit) then take their operands from uniform registers instead of an ELECT + R2UR.BROADCAST loop per instruction
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_tiles = (N + kDTileN - 1) / kDTileN, m_tiles = (M + kDTileM - 1) / kDTileM;
   const int total = n_tiles * m_tiles;
   const int nkb = K / kElemsPerBlock;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -74,17 +76,20 @@ __global__ void __launch_bounds__(kDThreads, 1)
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = smem + stage * kDStage;
-          mbar_arrive_expect_tx(&full[stage], kDStage);
-          tma_load_2d(a, &tmap_x, kb * kElemsPerBlock, m0, &full[stage]);
-          tma_load_2d(a + kDABytes, &tmap_w, kb * kElemsPerBlock, n0, &full[stage]);               // rows n0..n0+127
-          tma_load_2d(a + kDABytes + kDABytes, &tmap_w, kb * kElemsPerBlock, n0 + 128, &full[stage]); // rows n0+128..+255
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], kDStage);
+            tma_load_2d(a, &tmap_x, kb * kElemsPerBlock, m0, &full[stage]);
+            tma_load_2d(a + kDABytes, &tmap_w, kb * kElemsPerBlock, n0, &full[stage]);               // rows n0..n0+127
+            tma_load_2d(a + kDABytes + kDABytes, &tmap_w, kb * kElemsPerBlock, n0 + 128, &full[stage]); // rows n0+128..+255
+          }
+          __syncwarp();
           if (++stage == kDStages) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t aphase[2] = {0, 0};
@@ -103,17 +108,21 @@ __global__ void __launch_bounds__(kDThreads, 1)
           const uint32_t a_addr = smem_u32(smem + stage * kDStage);
           const uint64_t ad = umma_desc_k_sw128(a_addr);
           const uint64_t bd = umma_desc_k_sw128(a_addr + kDABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {          // 4 x 32 B of K per 128 B row (K=16 bf16 or K=32 int8 per MMA)
-            if constexpr (MODE == 2)
-              umma_i8(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else
-              umma_bf16(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {          // 4 x 32 B of K per 128 B row (K=16 bf16 or K=32 int8 per MMA)
+              if constexpr (MODE == 2)
+                umma_i8(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(tmem_base + b * kDTileN, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == kDStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[b]);
+        if (elect_one()) umma_commit(&acc_full[b]);
+        __syncwarp();
       }
     }
     __syncwarp();

@@ -36,7 +36,7 @@ constexpr int kTC = 64;            // chunk length (linear_attention.py:702)
 constexpr int kTSV = 32;           // dv slice per CTA
 constexpr int kTD = 128;           // dk == dv
 constexpr int kTThreads = 192;
-constexpr int kDefaultLayout = 3;      // flip to 2 once measured faster (KB2_GDN_SCAN_LAYOUT overrides per call)
+constexpr int kDefaultLayout = 4;      // flip to 2 once measured faster (KB2_GDN_SCAN_LAYOUT overrides per call)
 constexpr bool kDefaultSplit = false;   // chained accumulators (measured r02a); flip after comparing with KB2_GDN_SCAN_SPLIT=1
 constexpr int kVcLd = 36;          // padded row of the vcorr slice (floats): conflict-free float4 rows
 
@@ -1004,7 +1004,9 @@ __global__ void __launch_bounds__(kT3Threads, 1)
   uint64_t* g2_done = bars + 7;
   uint64_t* g3_done = bars + 8;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // warp index through a shuffle: the role branches are then provably warp-uniform and the operands of tcgen05.mma / commit / TMA
+  // stay in uniform registers (from a divergent `tid == 288` branch every MMA paid an ELECT + R2UR.BROADCAST loop, ~50 cycles)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int h = blockIdx.x, sl = blockIdx.y;
   const int kh = h / (p.nv / p.nk);
   const int n_chunks = p.n_chunks;
@@ -1030,22 +1032,25 @@ __global__ void __launch_bounds__(kT3Threads, 1)
   constexpr uint32_t kColD1 = 0, kColD1b = 64, kColD2 = 96, kColD3 = 160;     // D1, D2, D3: 64 columns (hi-part | lo-part)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   auto stamp = [&](int c, int slot) {
-    if (tracing && c >= 8 && c < 16) p.trace[(c - 8) * 16 + slot] = clock64();
+    if (tracing && c >= 8 && c < 16 && ((tid & 31) == 0 || tid == 64)) p.trace[(c - 8) * 16 + slot] = clock64();
   };
 
   if (warp == 8) {
-    if (tid == 256) {
-      prefetch_tmap(&tmap_q);
-      prefetch_tmap(&tmap_k);
+    {
+      if (elect_one()) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_k);
+      }
       const long long hc0 = (long long)h * n_chunks;
       for (int c = 0; c < n_chunks; ++c) {
         const int st = c & 1;
         const uint32_t ph = (uint32_t)(c >> 1) & 1u;
         uint8_t* sb = smem + st * kStageBytes;
         mbar_wait(&empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[st], kTxBytes);
         const long long hc = hc0 + c;
         const uint8_t* kimg = p.kcd_img + hc * 32768;
+        if (elect_one()) {
+        mbar_arrive_expect_tx(&full[st], kTxBytes);
         tma_load_2d(sb + kOffA1, &tmap_q, kh * kTD, c * kTC, &full[st]);
         bulk_g2s(sb + kOffA1 + 8192, kimg, 8192, &full[st]);
         tma_load_2d(sb + kOffA1 + 16384, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
@@ -1056,11 +1061,13 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
         tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
         tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == 9) {
-    if (tid == 288) {
+    {
       const uint32_t id_k = umma_idesc_bf16_m128(kTSV), id_k2 = umma_idesc_bf16_m128(2 * kTSV);
       const uint32_t id_amn2 = umma_idesc_bf16_m128(2 * kTSV) | (1u << 15);
       const uint32_t sS = smem_u32(smem + kOffSH);                 // per K chunk: [S_hi 32 rows | S_lo 32 rows] = one N=64 tile
@@ -1074,6 +1081,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         tc_fence_after_sync();
         stamp(c, 0);
         // G1: [q ; kcd_hi] [S_hi ; S_lo]^T -> D1 (64 columns);  [* ; kcd_lo] S_hi^T -> D1b (32 columns, lanes 64-127)
+        if (elect_one()) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const uint64_t ad = umma_desc_k_sw128(sb + kOffA1 + ch * 16384);
@@ -1089,10 +1097,13 @@ __global__ void __launch_bounds__(kT3Threads, 1)
           for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD1b, ad + 2 * ks, bd + 2 * ks, id_k, (ch > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(g1_done);
+        }
+        __syncwarp();
         stamp(c, 1);
         mbar_wait(v_ready, cp);
         tc_fence_after_sync();
         stamp(c, 2);
+        if (elect_one()) {
         {                                                 // G2: dS = k^T [vdec_hi ; vdec_lo]^T  (64 columns)
           const uint64_t bd = umma_desc_k_sw128(vdh);
 #pragma unroll
@@ -1112,6 +1123,8 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         }
         umma_commit(g3_done);
         umma_commit(&empty[st]);
+        }
+        __syncwarp();
         stamp(c, 3);
       }
     }
@@ -1318,7 +1331,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
   uint64_t* img_ready = bars + 5;
   uint64_t* bc_done = bars + 6;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role branches
   const int n_units = p.nv * p.n_chunks, r = p.nv / p.nk;
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -1337,12 +1350,12 @@ __global__ void __launch_bounds__(kTThreads, 1)
   constexpr uint32_t kColA = 0, kColB = 128, kColC = 256;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   auto stamp = [&](int it, int slot) {
-    if (tracing && it >= 2 && it < 10) p.trace[(it - 2) * 16 + slot] = clock64();
+    if (tracing && it >= 2 && it < 10 && (tid & 31) == 0) p.trace[(it - 2) * 16 + slot] = clock64();
   };
 
   if (warp == 4) {
-    if (tid == 128) {
-      prefetch_tmap(&tmap_q); prefetch_tmap(&tmap_k); prefetch_tmap(&tmap_v);
+    {
+      if (elect_one()) { prefetch_tmap(&tmap_q); prefetch_tmap(&tmap_k); prefetch_tmap(&tmap_v); }
       int it = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
         const int st = it & 1;
@@ -1350,6 +1363,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         const int h = u / p.n_chunks, ch = u % p.n_chunks, kh = h / r;
         uint8_t* sb = smem + st * kPStage;
         mbar_wait(&empty[st], ph ^ 1u);
+        if (elect_one()) {
         mbar_arrive_expect_tx(&full[st], kPStage);
         tma_load_2d(sb, &tmap_k, kh * kTD, ch * kTC, &full[st]);
         tma_load_2d(sb + 8192, &tmap_q, kh * kTD, ch * kTC, &full[st]);
@@ -1357,11 +1371,13 @@ __global__ void __launch_bounds__(kTThreads, 1)
         tma_load_2d(sb + 24576, &tmap_q, kh * kTD + 64, ch * kTC, &full[st]);
         tma_load_2d(sb + kPOffV, &tmap_v, h * kTD, ch * kTC, &full[st]);
         tma_load_2d(sb + kPOffV + 8192, &tmap_v, h * kTD + 64, ch * kTC, &full[st]);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (tid == 160) {
+    {
       const uint32_t id_a = umma_idesc_bf16_m128(64);                       // A, B K-major, N = 64
       const uint32_t id_bc = umma_idesc_bf16_m128(128) | (1u << 16);        // B MN-major, N = 128
       const uint32_t img1 = smem_u32(smem + kPOffImg1), img2 = smem_u32(smem + kPOffImg2);
@@ -1373,6 +1389,7 @@ __global__ void __launch_bounds__(kTThreads, 1)
         mbar_wait(&full[st], ph);
         tc_fence_after_sync();
         stamp(it, 0);
+        if (elect_one()) {
 #pragma unroll
         for (int chn = 0; chn < 2; ++chn) {
           const uint64_t ad = umma_desc_k_sw128(sb + chn * 16384);          // rows 0-63 k, rows 64-127 q
@@ -1381,10 +1398,13 @@ __global__ void __launch_bounds__(kTThreads, 1)
           for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColA, ad + 2 * ks, bd + 2 * ks, id_a, (chn > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(a_done);
+        }
+        __syncwarp();
         stamp(it, 1);
         mbar_wait(img_ready, up);
         tc_fence_after_sync();
         stamp(it, 2);
+        if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t a1 = umma_desc_k_sw128(img1) + 2 * ks, a2 = umma_desc_k_sw128(img2) + 2 * ks;
@@ -1393,6 +1413,8 @@ __global__ void __launch_bounds__(kTThreads, 1)
         }
         umma_commit(bc_done);
         umma_commit(&empty[st]);
+        }
+        __syncwarp();
         stamp(it, 3);
       }
     }

@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(kFThreads, 1)
   uint64_t* p_full = bars + 7;
   uint64_t* pv_done = bars + 8;      // [2]: PV(it) commits to pv_done[it & 1] (P is double-buffered)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shuffle-broadcast warp index: role branches provably warp-uniform -> TMA / tcgen05 operands stay in uniform registers (issued
+  // from a divergent `lane == 0` branch each tcgen05.mma pays an ELECT + R2UR.BROADCAST loop of ~50 cycles, more than an N=64 MMA runs)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;       // heavy (late) query tiles first
   const int head = blockIdx.y, kvh = head / (g.nh / g.nkv);
   const int q0 = qt * kFQ;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 
   if (warp < 4) {
     // ------------------------------------------------------------ KV producer: one thread issues the TMA boxes of a tile
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       const int kx = k_col0 + kvh * (PE ? DQ - 64 : DQ), vx = v_col0 + kvh * DV;
       int stage = 0;
       uint32_t phase = 0;
@@ -219,21 +221,27 @@ __global__ void __launch_bounds__(kFThreads, 1)
         uint8_t* ks = smem + L::kOffK + stage * L::kKBytes;
         uint8_t* vs = smem + L::kOffV + stage * L::kVBytes;
         mbar_wait(&k_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&k_full[stage], L::kKBytes);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&k_full[stage], L::kKBytes);
 #pragma unroll
-        for (int c = 0; c < NKC; ++c) tma_load_2d(ks + c * (kFK * 128), &tmap_k, kx + c * 64, it * kFK, &k_full[stage]);
-        if constexpr (PE) tma_load_2d(ks + NKC * (kFK * 128), &tmap_kpe, 0, it * kFK, &k_full[stage]);
+          for (int c = 0; c < NKC; ++c) tma_load_2d(ks + c * (kFK * 128), &tmap_k, kx + c * 64, it * kFK, &k_full[stage]);
+          if constexpr (PE) tma_load_2d(ks + NKC * (kFK * 128), &tmap_kpe, 0, it * kFK, &k_full[stage]);
+        }
+        __syncwarp();
         mbar_wait(&v_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&v_full[stage], L::kVBytes);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&v_full[stage], L::kVBytes);
 #pragma unroll
-        for (int c = 0; c < DV / 64; ++c) tma_load_2d(vs + c * (kFK * 128), &tmap_v, vx + c * 64, it * kFK, &v_full[stage]);
+          for (int c = 0; c < DV / 64; ++c) tma_load_2d(vs + c * (kFK * 128), &tmap_v, vx + c * 64, it * kFK, &v_full[stage]);
+        }
+        __syncwarp();
         if (++stage == kFStages) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 4) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && n_tiles > 0) {
+    if (n_tiles > 0) {
       const uint32_t id_s = umma_idesc_bf16_m128(kFK);
       const uint32_t id_o = umma_idesc_bf16_m128_bmn(DV);
       mbar_wait(q_full, 0);
@@ -258,23 +266,29 @@ __global__ void __launch_bounds__(kFThreads, 1)
         }
         tc_fence_after_sync();
         const uint32_t k_addr = smem_u32(smem + L::kOffK + stage * L::kKBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const uint64_t ad = umma_desc_k_sw128(q_addr + c * (kFQ * 128));
-          const uint64_t bd = umma_desc_k_sw128(k_addr + c * (kFK * 128));
+          for (int c = 0; c < NC; ++c) {
+            const uint64_t ad = umma_desc_k_sw128(q_addr + c * (kFQ * 128));
+            const uint64_t bd = umma_desc_k_sw128(k_addr + c * (kFK * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS, ad + 2 * k, bd + 2 * k, id_s, (c > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + kColS, ad + 2 * k, bd + 2 * k, id_s, (c > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(s_full);
+          umma_commit(&k_empty[stage]);              // K(it) is free once QK^T(it) has run
         }
-        umma_commit(s_full);
-        umma_commit(&k_empty[stage]);              // K(it) is free once QK^T(it) has run
+        __syncwarp();
         if (it > 0) {
           mbar_wait(&v_full[prev_stage], prev_phase);
           mbar_wait(p_full, pf_phase);
           pf_phase ^= 1;
           tc_fence_after_sync();
-          issue_pv(prev_stage, it == 1, (it - 1) & 1);
-          umma_commit(&pv_done[(it - 1) & 1]);
-          umma_commit(&v_empty[prev_stage]);
+          if (elect_one()) {
+            issue_pv(prev_stage, it == 1, (it - 1) & 1);
+            umma_commit(&pv_done[(it - 1) & 1]);
+            umma_commit(&v_empty[prev_stage]);
+          }
+          __syncwarp();
         }
         prev_stage = stage;
         prev_phase = phase;
@@ -283,13 +297,16 @@ __global__ void __launch_bounds__(kFThreads, 1)
       mbar_wait(&v_full[prev_stage], prev_phase);
       mbar_wait(p_full, pf_phase);
       tc_fence_after_sync();
-      issue_pv(prev_stage, n_tiles == 1, (n_tiles - 1) & 1);
-      umma_commit(&pv_done[(n_tiles - 1) & 1]);
-      umma_commit(&v_empty[prev_stage]);
+      if (elect_one()) {
+        issue_pv(prev_stage, n_tiles == 1, (n_tiles - 1) & 1);
+        umma_commit(&pv_done[(n_tiles - 1) & 1]);
+        umma_commit(&v_empty[prev_stage]);
+      }
+      __syncwarp();
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0 && n_tiles > 0) {
+    if (n_tiles > 0 && elect_one()) {
       mbar_arrive_expect_tx(q_full, L::kQBytes);
 #pragma unroll
       for (int c = 0; c < NC; ++c)

@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + L::kOffTmemPtr);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then KNOWS the role branches below are warp-uniform and keeps the operands of the
+  // single-thread instructions (tcgen05.mma / commit, TMA) in uniform registers.  Issued from a divergent `lane == 0` branch every
+  // tcgen05.mma was wrapped in an ELECT + 5 x R2UR.BROADCAST loop: ~50 cycles of issue per MMA, which made the K loop issue-bound
+  // (135 cycles per N=160 MMA in situ against 80 of execution: profiles/r02h_gemm_item_timeline.txt, r02h_mma_uniform_ubench.txt).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 32) {
@@ -176,12 +180,12 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   // tuning aid: per work item of CTA 0, slot = clock64 stamp or accumulated wait cycles (see scripts/gemm_trace.py)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   auto stamp = [&](int it, int slot, long long v) {
-    if (tracing && it < 16) p.trace[it * 16 + slot] = v;
+    if (tracing && it < 16 && (lane == 0 || threadIdx.x == 256)) p.trace[it * 16 + slot] = v;
   };
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight-tile producer (bulk TMA)
-    if (lane == 0) {
+    {
       Ring rw;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
@@ -196,24 +200,26 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           mbar_wait(&w_empty[rw.stage], rw.phase ^ 1);
           if (tracing) wacc += clock64() - c0;
           uint8_t* dst = smem + L::kOffW + rw.stage * L::kWStageBytes;
-          mbar_arrive_expect_tx(&w_full[rw.stage], L::kWStageBytes);
-          bulk_g2s(dst, wq_e + ((long long)t0 * nkb + kb) * TB, TB, &w_full[rw.stage]);
-          bulk_g2s(dst + TB, wq_e + ((long long)t1 * nkb + kb) * TB, TB, &w_full[rw.stage]);
-          if constexpr (kHasScaleTiles<FMT>) {
-            bulk_g2s(dst + 2 * TB, ws_e + ((long long)t0 * ngroups + (kb >> 1)) * kScaleTileBytes, kScaleTileBytes,
-                     &w_full[rw.stage]);
-            bulk_g2s(dst + 2 * TB + kScaleTileBytes, ws_e + ((long long)t1 * ngroups + (kb >> 1)) * kScaleTileBytes,
-                     kScaleTileBytes, &w_full[rw.stage]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&w_full[rw.stage], L::kWStageBytes);
+            bulk_g2s(dst, wq_e + ((long long)t0 * nkb + kb) * TB, TB, &w_full[rw.stage]);
+            bulk_g2s(dst + TB, wq_e + ((long long)t1 * nkb + kb) * TB, TB, &w_full[rw.stage]);
+            if constexpr (kHasScaleTiles<FMT>) {
+              bulk_g2s(dst + 2 * TB, ws_e + ((long long)t0 * ngroups + (kb >> 1)) * kScaleTileBytes, kScaleTileBytes,
+                       &w_full[rw.stage]);
+              bulk_g2s(dst + 2 * TB + kScaleTileBytes, ws_e + ((long long)t1 * ngroups + (kb >> 1)) * kScaleTileBytes,
+                       kScaleTileBytes, &w_full[rw.stage]);
+            }
           }
+          __syncwarp();
           rw.advance(kStagesW);
         }
         stamp(item / (int)gridDim.x, 12, wacc);
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp runs the loop, one elected lane issues)
+    {
       Ring ra, rb;
       uint32_t tphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -235,18 +241,22 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           tc_fence_after_sync();
           const uint32_t a_t = tmem_base + kATmemCol + ra.stage * 2 * kATileCols;
           const uint64_t b0 = umma_desc_k_sw128(smem_u32(smem + L::kOffB + rb.stage * kBStageBytes));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-            umma_bf16_ts(tmem_base, a_t + 8 * k, b0 + 2 * k, idesc, acc);
-            umma_bf16_ts(tmem_base + kAcc1Col, a_t + kATileCols + 8 * k, b0 + 2 * k, idesc, acc);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              umma_bf16_ts(tmem_base, a_t + 8 * k, b0 + 2 * k, idesc, acc);
+              umma_bf16_ts(tmem_base + kAcc1Col, a_t + kATileCols + 8 * k, b0 + 2 * k, idesc, acc);
+            }
+            umma_commit(&a_empty[ra.stage]);
+            umma_commit(&b_empty[rb.stage]);
           }
-          umma_commit(&a_empty[ra.stage]);
-          umma_commit(&b_empty[rb.stage]);
+          __syncwarp();
           ra.advance(kStagesA);
           rb.advance(kStagesB);
         }
-        umma_commit(tmem_full);
+        if (elect_one()) umma_commit(tmem_full);
+        __syncwarp();
         stamp(ti, 2, tracing ? clock64() : 0);
         stamp(ti, 3, wa);
         stamp(ti, 4, wb);
@@ -254,7 +264,6 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         tphase ^= 1;
       }
     }
-    __syncwarp();
   } else if (warp == 2) {
     // ------------------------------------------------------------ token (B operand) producer: 2-D TMA
     if (p.gather_rows != nullptr) {
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           rb.advance(kStagesB);
         }
       }
-    } else if (lane == 0) {
+    } else {
       Ring rb;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const ChunkDesc cd = p.chunks[item / p.items_per_chunk];
@@ -302,9 +311,12 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           mbar_wait(&b_empty[rb.stage], rb.phase ^ 1);
           if (tracing) bacc += clock64() - c0;
           uint8_t* dst = smem + L::kOffB + rb.stage * kBStageBytes;
-          mbar_arrive_expect_tx(&b_full[rb.stage], n_box * kBBoxBytes);
-          for (int b = 0; b < n_box; ++b)
-            tma_load_2d(dst + b * kBBoxBytes, &tmap_b, kb * kBlockK, cd.slot_begin + b * kBBoxRows, &b_full[rb.stage]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&b_full[rb.stage], n_box * kBBoxBytes);
+            for (int b = 0; b < n_box; ++b)
+              tma_load_2d(dst + b * kBBoxBytes, &tmap_b, kb * kBlockK, cd.slot_begin + b * kBBoxRows, &b_full[rb.stage]);
+          }
+          __syncwarp();
           rb.advance(kStagesB);
         }
         stamp(item / (int)gridDim.x, 13, bacc);

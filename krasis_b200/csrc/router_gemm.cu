@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(kRThreads, 1)
   uint64_t* empty = full + kRStages;
   uint64_t* done = empty + kRStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shuffle-broadcast warp index: role branches provably warp-uniform -> TMA / tcgen05 operands stay in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
   const int nkb = H / kBlockK;
   const int n0 = E > 256 ? 256 : E;          // columns of accumulator 0
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(kRThreads, 1)
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t bytes = kRATile + (uint32_t)E * kBlockK * 2;
@@ -67,15 +68,18 @@ __global__ void __launch_bounds__(kRThreads, 1)
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* a = smem + stage * kRStage;
         uint8_t* b = a + kRATile;
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        tma_load_2d(a, &tmap_x, kb * kBlockK, m0, &full[stage]);                 // 128 token rows (OOB rows -> 0)
-        for (int r = 0; r < E; r += 64) tma_load_2d(b + r * 128, &tmap_g, kb * kBlockK, r, &full[stage]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[stage], bytes);
+          tma_load_2d(a, &tmap_x, kb * kBlockK, m0, &full[stage]);                 // 128 token rows (OOB rows -> 0)
+          for (int r = 0; r < E; r += 64) tma_load_2d(b + r * 128, &tmap_g, kb * kBlockK, r, &full[stage]);
+        }
+        __syncwarp();
         if (++stage == kRStages) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t id0 = umma_idesc_bf16_m128((uint32_t)n0);
@@ -87,16 +91,20 @@ __global__ void __launch_bounds__(kRThreads, 1)
         const uint64_t ad = umma_desc_k_sw128(a_addr);
         const uint64_t bd0 = umma_desc_k_sw128(a_addr + kRATile);
         const uint64_t bd1 = umma_desc_k_sw128(a_addr + kRATile + 256 * 128);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, ad + 2 * k, bd0 + 2 * k, id0, acc);
-          if (n1 > 0) umma_bf16(tmem_base + 256, ad + 2 * k, bd1 + 2 * k, id1, acc);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_base, ad + 2 * k, bd0 + 2 * k, id0, acc);
+            if (n1 > 0) umma_bf16(tmem_base + 256, ad + 2 * k, bd1 + 2 * k, id1, acc);
+          }
+          umma_commit(&empty[stage]);
         }
-        umma_commit(&empty[stage]);
+        __syncwarp();
         if (++stage == kRStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done);
+      if (elect_one()) umma_commit(done);
+      __syncwarp();
     }
     __syncwarp();
   } else if (warp >= 4) {
