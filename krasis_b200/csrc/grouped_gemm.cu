@@ -41,7 +41,6 @@ namespace kb2 {
 
 constexpr int kNumThreads = 512;
 constexpr int kStagesA = 2;                                     // A operand stages in TMEM
-constexpr int kStagesB = 3;                                     // token (B operand) ring in smem
 constexpr int kBStageBytes = kMaxChunkTokens * kBlockK * 2;     // 24 KB
 constexpr int kBBoxRows = 32;                                   // TMA box = 32 token rows x 64 K
 constexpr int kBBoxBytes = kBBoxRows * kBlockK * 2;             // 4 KB
@@ -85,6 +84,9 @@ constexpr bool kHasScaleTiles = (FMT == kFmtInt4G128 || FMT == kFmtInt8G128);
 template <int FMT, bool kGemm1>
 struct SmemLayout {
   static constexpr int kStagesW = Fmt<FMT>::kStagesW;
+  // token (B operand) ring: 4 stages wherever they fit the 227 KB (everything but the 12 KB Affine8 tiles).  With tcgen05.mma issued
+  // at full rate the K loop waited ~200 cycles per k-block on token rows with 3 stages (profiles/r02i_gemm_item_timeline_*).
+  static constexpr int kStagesB = (FMT == kFmtAffine8) ? 3 : 4;
   static constexpr int kWStageBytes = 2 * Fmt<FMT>::kTileBytes + (kHasScaleTiles<FMT> ? 2 * kScaleTileBytes : 0);
   static constexpr int kStageRowBytes = 2 * kTileRows * 2;   // epilogue staging: 512 B per token (gate|up or two down tiles)
   static constexpr int kOffB = 0;                                               // 1024-aligned (swizzle atoms)
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
   uint64_t* a_full = w_empty + kStagesW;
   uint64_t* a_empty = a_full + kStagesA;
   uint64_t* b_full = a_empty + kStagesA;
+  constexpr int kStagesB = L::kStagesB;
   uint64_t* b_empty = b_full + kStagesB;
   uint64_t* tmem_full = b_empty + kStagesB;
   uint64_t* tmem_empty = tmem_full + 1;
@@ -490,6 +493,17 @@ __global__ void __launch_bounds__(kNumThreads, 1)
         uint32_t r0v[16], r1v[16];
         tmem_ld16(taddr + c0, r0v);
         tmem_ld16(taddr + kAcc1Col + c0, r1v);
+        float wv[16];
+        if constexpr (!kGemm1) {
+          // the 16 routing weights of this column group, loaded BEFORE the staging stores: the compiler cannot move a shared-memory
+          // load across the stores (possible alias), and one exposed load latency per column was 2/3 of this phase
+          const float4* sw4 = reinterpret_cast<const float4*>(smem + L::kOffSlotW) + (c0 >> 2);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 w4 = sw4[q4];
+            wv[4 * q4] = w4.x; wv[4 * q4 + 1] = w4.y; wv[4 * q4 + 2] = w4.z; wv[4 * q4 + 3] = w4.w;
+          }
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -497,9 +511,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
           float v0 = __uint_as_float(r0v[j]);
           float v1 = __uint_as_float(r1v[j]);
           if constexpr (!kGemm1) {
-            const float wgt = reinterpret_cast<const float*>(smem + L::kOffSlotW)[tok];
-            v0 *= wgt;
-            v1 *= wgt;
+            v0 *= wv[j];
+            v1 *= wv[j];
           }
           __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + tok * kRowB);
           srow[row] = __float2bfloat16_rn(v0);
