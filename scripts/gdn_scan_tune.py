@@ -25,7 +25,7 @@ cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_v
 lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
 x = torch.randn(M, H).to(bf).cuda()
 outs = {}
-for split in ("1", "4", "5"):                              # operand / warp layouts of the tcgen05 scan (gdn_tc.cu)
+for split in ("4", "5"):                              # operand / warp layouts of the tcgen05 scan (gdn_tc.cu)
     os.environ["KB2_GDN_SCAN_SPLIT"] = "0"
     os.environ["KB2_GDN_SCAN_LAYOUT"] = split
     for _ in range(3):
@@ -51,15 +51,16 @@ for split in ("1", "4", "5"):                              # operand / warp layo
     for r in (t - base).tolist():
         print("   ", r)
     print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
-print("max |layout1 - layout5| / max:", ((outs["1"] - outs["5"]).abs().max() / outs["1"].abs().max()).item())
+print("max |layout4 - layout5| / max:", ((outs["4"] - outs["5"]).abs().max() / outs["4"].abs().max()).item())
 os.environ.pop("KB2_GDN_SCAN_LAYOUT", None)
 
 # ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,
 # 3 MMA-B/C issued; core thread 0: 4 gates scanned, 5 k.k^T seen, 6 A^T built, 7 T solved, 8 images written, 9 vcorr/kcd products seen,
 # 10 outputs stored)
 os.environ.pop("KB2_GDN_SCAN_SPLIT", None)
-for mode in ("1", "0"):
+for mode, version in (("1", "1"), ("0", "1"), ("0", "2")):
     os.environ["KB2_GDN_PREPARE_MMA_SYNC"] = mode
+    os.environ["KB2_GDN_PREPARE_VERSION"] = version
     for _ in range(2):
         lay.reset_state()
         lay.forward(x)
@@ -69,15 +70,17 @@ for mode in ("1", "0"):
         lay.forward(x)
     prof = capi.kernel_profile_collect()
     capi.kernel_profile(False)
-    print(("mma.sync" if mode == "1" else "tcgen05") + " prepare: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in prof.items() if "prepare" in n))
-trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
-os.environ["KB2_GDN_PREPARE_TRACE"] = str(trace.data_ptr())
-lay.reset_state()
-lay.forward(x)
-torch.cuda.synchronize()
-del os.environ["KB2_GDN_PREPARE_TRACE"]
-t = trace.cpu().view(8, 16)[:, :11]
-print("  prepare timeline (cycles since inputs landed), loop iterations 2..9:")
-for r in (t - t[:, 0:1]).tolist():
-    print("   ", r)
-print("  unit period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
+    print(("mma.sync" if mode == "1" else f"tcgen05 v{version}") + " prepare: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in prof.items() if "prepare" in n))
+    if mode == "1":
+        continue
+    trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
+    os.environ["KB2_GDN_PREPARE_TRACE"] = str(trace.data_ptr())
+    lay.reset_state()
+    lay.forward(x)
+    torch.cuda.synchronize()
+    del os.environ["KB2_GDN_PREPARE_TRACE"]
+    t = trace.cpu().view(8, 16)[:, :11]
+    print("  prepare timeline (cycles since inputs landed), loop iterations 2..9:")
+    for r in (t - t[:, 0:1]).tolist()[:4]:
+        print("   ", r)
+    print("  unit period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
