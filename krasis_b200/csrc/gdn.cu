@@ -886,7 +886,7 @@ cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc
 // Which chunk-prepare feeds the tcgen05 scan.  Measured r02c (QCN layer, 8192 tokens): mma.sync 310 us, tcgen05 460 us — the
 // tcgen05 kernel is latency-bound on its per-unit phases; it stays selectable while it is being tuned:
 // KB2_GDN_PREPARE_MMA_SYNC=0 picks tcgen05, =1 mma.sync; unset -> kDefaultPrepareTc.
-constexpr bool kDefaultPrepareTc = false;
+constexpr bool kDefaultPrepareTc = true;
 static bool gdn_prepare_mma_sync_env() {
   const char* e = getenv("KB2_GDN_PREPARE_MMA_SYNC");
   return e ? e[0] == '1' : !kDefaultPrepareTc;

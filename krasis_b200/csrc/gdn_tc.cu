@@ -37,7 +37,7 @@ constexpr int kTSV = 32;           // dv slice per CTA
 constexpr int kTD = 128;           // dk == dv
 constexpr int kTThreads = 192;
 constexpr int kDefaultPrepareVersion = 2;
-constexpr int kDefaultLayout = 4;      // flip to 2 once measured faster (KB2_GDN_SCAN_LAYOUT overrides per call)
+constexpr int kDefaultLayout = 5;      // flip to 2 once measured faster (KB2_GDN_SCAN_LAYOUT overrides per call)
 constexpr bool kDefaultSplit = false;   // chained accumulators (measured r02a); flip after comparing with KB2_GDN_SCAN_SPLIT=1
 constexpr int kVcLd = 36;          // padded row of the vcorr slice (floats): conflict-free float4 rows
 
@@ -2194,7 +2194,8 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = part * 32 + 4 * j4 + e;
-            v[e] = j < i ? -(__uint_as_float(a[4 * j4 + e]) * b_row) * __expf(g_i - sg[j]) : 0.f;
+            const float dec = exp_fast_nobranch(g_i - sg[j]);             // unconditional (select below): see ptx.cuh
+            v[e] = j < i ? -(__uint_as_float(a[4 * j4 + e]) * b_row) * dec : 0.f;
           }
           *reinterpret_cast<float4*>(sA + i * kPLdAT + part * 32 + 4 * j4) = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -2209,8 +2210,9 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = part * 32 + q8 * 8 + 2 * e;
-            const float v0 = j <= i ? __uint_as_float(a[q8 * 8 + 2 * e]) * __expf(g_i - sg[j]) : 0.f;
-            const float v1 = j + 1 <= i ? __uint_as_float(a[q8 * 8 + 2 * e + 1]) * __expf(g_i - sg[j + 1]) : 0.f;
+            const float d0 = exp_fast_nobranch(g_i - sg[j]), d1 = exp_fast_nobranch(g_i - sg[j + 1]);
+            const float v0 = j <= i ? __uint_as_float(a[q8 * 8 + 2 * e]) * d0 : 0.f;
+            const float v1 = j + 1 <= i ? __uint_as_float(a[q8 * 8 + 2 * e + 1]) * d1 : 0.f;
             unsigned short h0, l0, h1, l1;
             split_bf16(v0, h0, l0);
             split_bf16(v1, h1, l1);

@@ -489,14 +489,16 @@ __global__ void __launch_bounds__(kNumThreads, 1)
       const int ti = item / (int)gridDim.x;
       if (etr) stamp(ti, 5, clock64());
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < n_pad; c0 += 16) {
-        uint32_t r0v[16], r1v[16];
-        tmem_ld16(taddr + c0, r0v);
-        tmem_ld16(taddr + kAcc1Col + c0, r1v);
-        float wv[16];
+      // 16 accumulator columns (tokens) per step, software-pipelined over two register sets: the tcgen05.ld of the next step is in
+      // flight while this step is rounded to BF16 and staged (the exposed TMEM load latency was ~1/3 of this phase, which holds TMEM)
+      auto load_cols = [&](int c0, uint32_t (&a)[16], uint32_t (&b)[16]) {
+        tmem_ld16(taddr + c0, a);
+        tmem_ld16(taddr + kAcc1Col + c0, b);
+      };
+      auto load_weights = [&](int c0, float (&wv)[16]) {
         if constexpr (!kGemm1) {
-          // the 16 routing weights of this column group, loaded BEFORE the staging stores: the compiler cannot move a shared-memory
-          // load across the stores (possible alias), and one exposed load latency per column was 2/3 of this phase
+          // routing weights of the column group, loaded BEFORE the staging stores of the step (a shared-memory load cannot be moved
+          // across those stores by the compiler: possible alias)
           const float4* sw4 = reinterpret_cast<const float4*>(smem + L::kOffSlotW) + (c0 >> 2);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -504,19 +506,37 @@ __global__ void __launch_bounds__(kNumThreads, 1)
             wv[4 * q4] = w4.x; wv[4 * q4 + 1] = w4.y; wv[4 * q4 + 2] = w4.z; wv[4 * q4 + 3] = w4.w;
           }
         }
-        tmem_ld_wait();
+      };
+      auto stage_cols = [&](int c0, const uint32_t (&a)[16], const uint32_t (&b)[16], const float (&wv)[16]) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int tok = c0 + j;
-          float v0 = __uint_as_float(r0v[j]);
-          float v1 = __uint_as_float(r1v[j]);
+          float v0 = __uint_as_float(a[j]);
+          float v1 = __uint_as_float(b[j]);
           if constexpr (!kGemm1) {
             v0 *= wv[j];
             v1 *= wv[j];
           }
-          __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + tok * kRowB);
+          __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(stage + (c0 + j) * kRowB);
           srow[row] = __float2bfloat16_rn(v0);
           srow[kTileRows + row] = __float2bfloat16_rn(v1);
+        }
+      };
+      {
+        uint32_t a0[16], b0[16], a1[16], b1[16];
+        float w0[16], w1[16];
+        load_cols(0, a0, b0);
+        for (int c0 = 0; c0 < n_pad; c0 += 32) {
+          const bool second = c0 + 16 < n_pad;
+          load_weights(c0, w0);
+          if (second) load_weights(c0 + 16, w1);
+          tmem_ld_wait();                                      // set 0 is in registers
+          if (second) load_cols(c0 + 16, a1, b1);
+          stage_cols(c0, a0, b0, w0);
+          if (second) {
+            tmem_ld_wait();                                    // set 1 is in registers
+            if (c0 + 32 < n_pad) load_cols(c0 + 32, a0, b0);
+            stage_cols(c0 + 16, a1, b1, w1);
+          }
         }
       }
       tc_fence_before_sync();

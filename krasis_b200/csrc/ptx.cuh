@@ -120,6 +120,15 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 }
 // Instruction descriptor for kind::f16, A=B=BF16, D=F32, both K-major, M=128, N=n
 // (cute::UMMA::InstrDescriptor: c_format [4,6)=1 | a_format [7,10)=1 | b_format [10,13)=1 | n>>3 [17,23) | m>>4 [24,29)).
+// e^x through one MUFU.EX2, executed unconditionally: written as `cond ? acc * __expf(x) : 0.f` nvcc branches around the exponential,
+// and one divergent basic block per element (with the MUFU latency exposed in each) made the masked decay matrices of the GDN
+// chunk-prepare latency-bound.  Compute first, select afterwards.
+__device__ __forceinline__ float exp_fast_nobranch(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 // bf16 RNE of one float, result in the LOW 16 bits (high bits zero), through the PACKED converter (F2FP.BF16.F32.PACK_AB, full
 // rate).  When the converted value is reused as an integer nvcc picks the single-value F2F.BF16.F32 for __float2bfloat16_rn, which
 // issues on the quarter-rate conversion pipe: 8 issue cycles per warp instruction bounded the CUDA-core phases of the tcgen05
