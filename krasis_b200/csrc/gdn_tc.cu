@@ -60,7 +60,8 @@ constexpr int kOffVDH = kOffVL + 4096;     // decayed v hi
 constexpr int kOffVDL = kOffVDH + 4096;
 constexpr int kOffX = kOffVDL + 4096;      // epilogue exchange fp32 [64][36]
 constexpr int kOffBar = kOffX + kTC * kVcLd * 4;
-constexpr int kTcSmem = kOffBar + 128;
+constexpr int kOffDec = kOffBar + 128;      // e^(g_last - g_t) per token of the running chunk (layout 6)
+constexpr int kTcSmem = kOffDec + kTC * 4;
 static_assert(kTcSmem <= 227 * 1024, "smem");
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -1590,6 +1591,330 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 
 
 
+// --------------------------------------------------------------------------------------------------------------------
+// Scan, sixth layout = the fifth one with the v tiles written TRANSPOSED: after the parking barrier thread (column n = lane, token
+// octet = warp) reads 8 tokens of one column, converts token PAIRS with one cvt.rn.bf16x2 each (the packed word is already the
+// K-contiguous memory order) and writes each of the four tiles with ONE 16-byte store: ~75 instructions per thread instead of ~170
+// (8 columns x (2 splits + 4 two-byte stores)).
+// (Fifth layout:) the fourth one with the v tiles written by ALL eight core warps: the VP threads (lanes 64-127, i.e. only
+// two of the four schedulers) park v as fp32 in shared memory, one 256-thread barrier, then every thread splits and stores 8 columns
+// of one token (the hi/lo split + four 2-byte stores per element are what the v phase costs: ~17 instructions per element).
+// (Fourth layout:) the third one with the hi and lo halves of every B operand STACKED ALONG N.  Measured motivation
+// (profiles/r02d_mma_issue_ubench.txt): a tcgen05.mma costs ~44 cycles to issue whether N is 32 or 64, so
+// A.[S_hi ; S_lo] as ONE N=64 instruction stream replaces two N=32 streams: G1 24 -> 16 MMAs, G2 8 -> 4, G3 12 -> 8; the
+// CUDA cores add the two 32-column halves when they read the accumulators back.
+// (Third layout:) the second one with EIGHT CUDA-core warps.  Measured motivation (profiles/r02f_gdn_timelines_fine.txt):
+// with four core warps there is one warp per scheduler, every dependent instruction pays its full latency, and the tile
+// writing phases ran at IPC ~0.3 (1170 + 500 cycles per chunk).  Warps w and w + 4 share TMEM lane quadrant w & 3 and take
+// 16 of the 32 columns each: the VP threads (lanes 64-127) split and store their own 16 columns of v (no parking, no
+// exchange), every thread owns 16 columns of one state row.  Warp 8 = TMA producer, warp 9 = MMA issuer.
+// --------------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kT3Threads, 1)
+    gdn_scan_tc6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* full = bars;           // [2]
+  uint64_t* empty = bars + 2;      // [2]
+  uint64_t* s_ready = bars + 4;
+  uint64_t* g1_done = bars + 5;
+  uint64_t* v_ready = bars + 6;
+  uint64_t* g2_done = bars + 7;
+  uint64_t* g3_done = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  // warp index through a shuffle: the role branches are then provably warp-uniform and the operands of tcgen05.mma / commit / TMA
+  // stay in uniform registers (from a divergent `tid == 288` branch every MMA paid an ELECT + R2UR.BROADCAST loop, ~50 cycles)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int h = blockIdx.x, sl = blockIdx.y;
+  const int kh = h / (p.nv / p.nk);
+  const int n_chunks = p.n_chunks;
+  const int vd = p.nv * kTD;
+  constexpr int kHC = kTSV / 2;      // columns per thread
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_init(s_ready, 256);
+    mbar_init(g1_done, 1);
+    mbar_init(v_ready, 256);
+    mbar_init(g2_done, 1);
+    mbar_init(g3_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_ptr_smem, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kColD1 = 0, kColD1b = 64, kColD2 = 96, kColD3 = 160;     // D1, D2, D3: 64 columns (hi-part | lo-part)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  auto stamp = [&](int c, int slot) {
+    if (tracing && c >= 8 && c < 16 && ((tid & 31) == 0 || tid == 64)) p.trace[(c - 8) * 16 + slot] = clock64();
+  };
+
+  if (warp == 8) {
+    {
+      if (elect_one()) {
+        prefetch_tmap(&tmap_q);
+        prefetch_tmap(&tmap_k);
+      }
+      const long long hc0 = (long long)h * n_chunks;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
+        uint8_t* sb = smem + st * kStageBytes;
+        mbar_wait(&empty[st], ph ^ 1u);
+        const long long hc = hc0 + c;
+        const uint8_t* kimg = p.kcd_img + hc * 32768;
+        if (elect_one()) {
+        mbar_arrive_expect_tx(&full[st], kTxBytes);
+        tma_load_2d(sb + kOffA1, &tmap_q, kh * kTD, c * kTC, &full[st]);
+        bulk_g2s(sb + kOffA1 + 8192, kimg, 8192, &full[st]);
+        tma_load_2d(sb + kOffA1 + 16384, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
+        bulk_g2s(sb + kOffA1 + 24576, kimg + 8192, 8192, &full[st]);
+        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);
+        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);
+        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
+        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
+        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
+        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    {
+      const uint32_t id_k = umma_idesc_bf16_m128(kTSV), id_k2 = umma_idesc_bf16_m128(2 * kTSV);
+      const uint32_t id_amn2 = umma_idesc_bf16_m128(2 * kTSV) | (1u << 15);
+      const uint32_t sS = smem_u32(smem + kOffSH);                 // per K chunk: [S_hi 32 rows | S_lo 32 rows] = one N=64 tile
+      const uint32_t vh = smem_u32(smem + kOffVH), vdh = smem_u32(smem + kOffVDH);   // [v_hi | v_lo], [vdec_hi | vdec_lo]
+      for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
+        const uint32_t sb = smem_u32(smem + st * kStageBytes);
+        mbar_wait(&full[st], ph);
+        mbar_wait(s_ready, cp);
+        tc_fence_after_sync();
+        stamp(c, 0);
+        // G1: [q ; kcd_hi] [S_hi ; S_lo]^T -> D1 (64 columns);  [* ; kcd_lo] S_hi^T -> D1b (32 columns, lanes 64-127)
+        if (elect_one()) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const uint64_t ad = umma_desc_k_sw128(sb + kOffA1 + ch * 16384);
+          const uint64_t bd = umma_desc_k_sw128(sS + ch * 8192);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD1, ad + 2 * ks, bd + 2 * ks, id_k2, (ch > 0 || ks > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const uint64_t ad = umma_desc_k_sw128(sb + kOffA1L + ch * 8192 - 8192);
+          const uint64_t bd = umma_desc_k_sw128(sS + ch * 8192);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD1b, ad + 2 * ks, bd + 2 * ks, id_k, (ch > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(g1_done);
+        }
+        __syncwarp();
+        stamp(c, 1);
+        mbar_wait(v_ready, cp);
+        tc_fence_after_sync();
+        stamp(c, 2);
+        if (elect_one()) {
+        {                                                 // G2: dS = k^T [vdec_hi ; vdec_lo]^T  (64 columns)
+          const uint64_t bd = umma_desc_k_sw128(vdh);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
+            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn2, ks > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(g2_done);
+        {                                                 // G3 (lanes 0-63): intra_hi [v_hi ; v_lo]^T, then intra_lo v_hi^T onto the hi half
+          const uint64_t ah = umma_desc_k_sw128(sb + kOffA3), al = umma_desc_k_sw128(sb + kOffA3 + 8192);
+          const uint64_t bd = umma_desc_k_sw128(vh);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD3, ah + 2 * ks, bd + 2 * ks, id_k2, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD3, al + 2 * ks, bd + 2 * ks, id_k, 1u);
+        }
+        umma_commit(g3_done);
+        umma_commit(&empty[st]);
+        }
+        __syncwarp();
+        stamp(c, 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int L = (warp & 3) * 32 + (tid & 31);        // TMEM lane of this thread
+    const int hcol = warp >> 2;                        // which 16 of the 32 columns
+    const int j0 = hcol * kHC;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + j0;
+    float s[kHC];                                      // state row L, columns j0 .. j0+15
+    {
+      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
+#pragma unroll
+      for (int j4 = 0; j4 < kHC / 4; ++j4) {
+        const float4 v = src[j4];
+        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
+      }
+    }
+    // operand tile addressing: row n = j0 + jj (j0 is a multiple of 8, so (n & 7) == (jj & 7)), k = L or token index
+    uint8_t* s_hi = smem + kOffSH + j0 * 128;                       // K chunk (L >> 6): [S_hi rows 0-31 | S_lo rows 0-31]
+    uint8_t* s_lo = s_hi + 4096;
+    const uint32_t k_off_s = (uint32_t)((L >> 6) * 8192 + ((L & 7) << 1));
+    const int kc_s = (L & 63) >> 3;
+    auto write_s_tiles = [&]() {
+#pragma unroll
+      for (int jj = 0; jj < kHC; ++jj) {
+        unsigned short hi, lo;
+        split_bf16(s[jj], hi, lo);
+        const uint32_t off = k_off_s + jj * 128 + ((kc_s ^ (jj & 7)) << 4);
+        *reinterpret_cast<unsigned short*>(s_hi + off) = hi;
+        *reinterpret_cast<unsigned short*>(s_lo + off) = lo;
+      }
+    };
+    write_s_tiles();
+    fence_proxy_async_smem();
+    mbar_arrive(s_ready);
+    const int i = L & 63;                              // token row (IT for L < 64, VP for L >= 64)
+    const int kc_v = i >> 3;
+    const uint32_t k_off_v = (uint32_t)(j0 * 128 + ((i & 7) << 1));
+    for (int c = 0; c < n_chunks; ++c) {
+      const int st = c & 1;
+      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
+      const uint8_t* sb = smem + st * kStageBytes;
+      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
+      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
+      mbar_wait(&full[st], ph);
+      const float g_last = sg[kTC - 1], g_i = sg[i];
+      const float d_last = expf(g_last);
+      float it[kHC];
+#pragma unroll
+      for (int jj = 0; jj < kHC; ++jj) it[jj] = 0.f;
+      mbar_wait(g1_done, cp);
+      tc_fence_after_sync();
+      if (tid == 0) stamp(c, 4);
+      float* xv = reinterpret_cast<float*>(smem + kOffX);            // parked v: fp32 [64 tokens][36]
+      if (L >= 64) {                           // VP rows: v = vcorr - VP for this thread's 16 columns, parked as fp32
+        uint32_t a[16], a2[16], b[16];
+        tmem_ld16(lane_addr + kColD1, a);
+        tmem_ld16(lane_addr + kColD1 + kTSV, a2);
+        tmem_ld16(lane_addr + kColD1b, b);
+        tmem_ld_wait();
+        if (tid == 64) stamp(c, 10);
+#pragma unroll
+        for (int j4 = 0; j4 < kHC / 4; ++j4) {
+          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + j0 + 4 * j4);
+          float4 o;
+          o.x = vc4.x - ((__uint_as_float(a[4 * j4]) + __uint_as_float(a2[4 * j4])) + __uint_as_float(b[4 * j4]));
+          o.y = vc4.y - ((__uint_as_float(a[4 * j4 + 1]) + __uint_as_float(a2[4 * j4 + 1])) + __uint_as_float(b[4 * j4 + 1]));
+          o.z = vc4.z - ((__uint_as_float(a[4 * j4 + 2]) + __uint_as_float(a2[4 * j4 + 2])) + __uint_as_float(b[4 * j4 + 2]));
+          o.w = vc4.w - ((__uint_as_float(a[4 * j4 + 3]) + __uint_as_float(a2[4 * j4 + 3])) + __uint_as_float(b[4 * j4 + 3]));
+          *reinterpret_cast<float4*>(xv + i * kVcLd + j0 + 4 * j4) = o;
+        }
+        if (hcol == 0) reinterpret_cast<float*>(smem + kOffDec)[i] = expf(g_last - g_i);
+      } else {                                 // IT rows
+        uint32_t a[16], a2[16];
+        tmem_ld16(lane_addr + kColD1, a);
+        tmem_ld16(lane_addr + kColD1 + kTSV, a2);
+        tmem_ld_wait();
+        const float eg = expf(g_i);
+#pragma unroll
+        for (int jj = 0; jj < kHC; ++jj) it[jj] = eg * (__uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
+      }
+      if (tid == 64) stamp(c, 11);
+      named_bar_sync(1, 256);
+      if (tid == 64) stamp(c, 12);
+      {                                        // every thread: column n, tokens 8 t8 .. 8 t8 + 7 of v -> one 16-byte store per tile
+        const int n = tid & 31, t8 = tid >> 5;
+        const float* sdec = reinterpret_cast<const float*>(smem + kOffDec);
+        const float4 d0 = *reinterpret_cast<const float4*>(sdec + 8 * t8), d1 = *reinterpret_cast<const float4*>(sdec + 8 * t8 + 4);
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = xv[(8 * t8 + e) * kVcLd + n];
+        uint32_t vh[4], vl[4], dh[4], dl[4];
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+          const float x0 = x[2 * pr], x1 = x[2 * pr + 1];
+          vh[pr] = bf16x2_bits_rn(x1, x0);
+          vl[pr] = bf16x2_bits_rn(x1 - __uint_as_float(vh[pr] & 0xFFFF0000u), x0 - __uint_as_float(vh[pr] << 16));
+          const float y0 = x0 * dv[2 * pr], y1 = x1 * dv[2 * pr + 1];
+          dh[pr] = bf16x2_bits_rn(y1, y0);
+          dl[pr] = bf16x2_bits_rn(y1 - __uint_as_float(dh[pr] & 0xFFFF0000u), y0 - __uint_as_float(dh[pr] << 16));
+        }
+        const uint32_t off = (uint32_t)(n * 128 + ((t8 ^ (n & 7)) << 4));
+        *reinterpret_cast<uint4*>(smem + kOffVH + off) = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+        *reinterpret_cast<uint4*>(smem + kOffVL + off) = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+        *reinterpret_cast<uint4*>(smem + kOffVDH + off) = make_uint4(dh[0], dh[1], dh[2], dh[3]);
+        *reinterpret_cast<uint4*>(smem + kOffVDL + off) = make_uint4(dl[0], dl[1], dl[2], dl[3]);
+      }
+      if (tid == 64) stamp(c, 13);
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(v_ready);
+      if (tid == 64) stamp(c, 5);
+      mbar_wait(g2_done, cp);
+      tc_fence_after_sync();
+      if (tid == 0) stamp(c, 6);
+      {
+        uint32_t a[16], a2[16];
+        tmem_ld16(lane_addr + kColD2, a);
+        tmem_ld16(lane_addr + kColD2 + kTSV, a2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < kHC; ++jj) s[jj] = fmaf(d_last, s[jj], __uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
+      }
+      if (c + 1 < n_chunks) {
+        write_s_tiles();
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(s_ready);
+      }
+      if (tid == 0) stamp(c, 7);
+      if (L < 64) {                            // output rows (IT and intra.v share lanes 0-63)
+        mbar_wait(g3_done, cp);
+        tc_fence_after_sync();
+        if (tid == 0) stamp(c, 8);
+        uint32_t a[16], a2[16];
+        tmem_ld16(lane_addr + kColD3, a);
+        tmem_ld16(lane_addr + kColD3 + kTSV, a2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < kHC; ++jj) a[jj] = __float_as_uint(__uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
+        const int t = c * kTC + i;
+        if (t < p.M) {
+          uint32_t o[kHC / 2];
+#pragma unroll
+          for (int j2 = 0; j2 < kHC / 2; ++j2) {
+            __nv_bfloat162 pr = __floats2bfloat162_rn(it[2 * j2] + __uint_as_float(a[2 * j2]), it[2 * j2 + 1] + __uint_as_float(a[2 * j2 + 1]));
+            o[j2] = *reinterpret_cast<uint32_t*>(&pr);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV + j0);
+          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        tc_fence_before_sync();
+        if (tid == 0) stamp(c, 9);
+      }
+    }
+    {
+      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
+#pragma unroll
+      for (int j4 = 0; j4 < kHC / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
+}
+
+
+
+
 // ====================================================================================================================
 // Chunk prepare on tcgen05 (dk == dv == 128): everything of linear_attention.py:593-646 that does not depend on the carried
 // state, for one (value head, 64-token chunk) per loop iteration of a persistent CTA:
@@ -2430,6 +2755,7 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
@@ -2447,7 +2773,8 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
   GdnTcParams p{(const uint8_t*)kcd_img, (const uint8_t*)intra_img, vcorr, gcum, state, (__nv_bfloat16*)core_out, M, n_chunks, nv, nk, trace};
   const char* vv = getenv("KB2_GDN_SCAN_LAYOUT");          // 1 = first layout, 2 = second layout (see above); unset -> kDefaultLayout
   const int layout = vv ? atoi(vv) : kDefaultLayout;
-  if (layout == 5) gdn_scan_tc5_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
+  if (layout == 6) gdn_scan_tc6_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
+  else if (layout == 5) gdn_scan_tc5_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
   else if (layout == 4) gdn_scan_tc4_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
   else if (layout == 3) gdn_scan_tc3_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
   else if (layout == 2) gdn_scan_tc2_kernel<<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);

@@ -25,7 +25,7 @@ cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_v
 lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
 x = torch.randn(M, H).to(bf).cuda()
 outs = {}
-for split in ("4", "5"):                              # operand / warp layouts of the tcgen05 scan (gdn_tc.cu)
+for split in ("5", "6"):                              # operand / warp layouts of the tcgen05 scan (gdn_tc.cu)
     os.environ["KB2_GDN_SCAN_SPLIT"] = "0"
     os.environ["KB2_GDN_SCAN_LAYOUT"] = split
     for _ in range(3):
@@ -51,7 +51,7 @@ for split in ("4", "5"):                              # operand / warp layouts o
     for r in (t - base).tolist():
         print("   ", r)
     print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
-print("max |layout4 - layout5| / max:", ((outs["4"] - outs["5"]).abs().max() / outs["4"].abs().max()).item())
+print("max |layout5 - layout6| / max:", ((outs["5"] - outs["6"]).abs().max() / outs["5"].abs().max()).item())
 os.environ.pop("KB2_GDN_SCAN_LAYOUT", None)
 
 # ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,

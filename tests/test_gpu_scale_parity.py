@@ -220,7 +220,7 @@ def test_router_mismatches_are_near_ties_at_benchmark_size(E, k, H):
 
 # ------------------------------------------------------------------------------------------------ tcgen05 scan vs mma.sync scan
 
-@pytest.mark.parametrize("layout", ["1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("layout", ["1", "2", "3", "4", "5", "6"])
 @pytest.mark.parametrize("M", [200, 1024])
 def test_gdn_tcgen05_scan_matches_the_mma_sync_scan(M, layout, monkeypatch):
     """Same layer, same inputs, two state carries: the tcgen05 chunk scan (BF16 hi/lo pairs, fp32 accumulate) against the
