@@ -20,7 +20,7 @@
 // swizzled K-major layout.  64-row A operands are issued as M=128 MMAs whose rows 64-127 read whatever follows in shared
 // memory: those rows only produce accumulator lanes 64-127 of a column range nobody reads.
 //
-// Warps 0-3: CUDA-core work, one thread per TMEM lane; warp 4: TMA producer; warp 5: MMA issuer.  2-stage operand ring.
+// 2-stage operand ring; warp roles and the TMEM map are described at the kernel below.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -37,8 +37,6 @@ constexpr int kTSV = 32;           // dv slice per CTA
 constexpr int kTD = 128;           // dk == dv
 constexpr int kTThreads = 192;
 constexpr int kDefaultPrepareVersion = 2;
-constexpr int kDefaultLayout = 5;      // flip to 2 once measured faster (KB2_GDN_SCAN_LAYOUT overrides per call)
-constexpr bool kDefaultSplit = false;   // chained accumulators (measured r02a); flip after comparing with KB2_GDN_SCAN_SPLIT=1
 constexpr int kVcLd = 36;          // padded row of the vcorr slice (floats): conflict-free float4 rows
 
 // per-stage byte offsets
@@ -115,1503 +113,24 @@ struct GdnTcParams {
   long long* trace;          // optional (tests / tuning): clock64 stamps of CTA (0,0), chunks [8, 16): [chunk][16]
 };
 
-// SPLIT: every pass of a hi/lo product accumulates into its OWN TMEM columns (the CUDA cores add the partial results when
-// they read them back) instead of chaining all passes on one accumulator: shorter dependent tcgen05.mma chains, more LDTM.
-template <bool SPLIT>
-__global__ void __launch_bounds__(kTThreads, 1)
-    gdn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* full = bars;           // [2]
-  uint64_t* empty = bars + 2;      // [2]
-  uint64_t* s_ready = bars + 4;
-  uint64_t* g1_done = bars + 5;
-  uint64_t* v_ready = bars + 6;
-  uint64_t* g2_done = bars + 7;
-  uint64_t* g3_done = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int h = blockIdx.x, sl = blockIdx.y;
-  const int kh = h / (p.nv / p.nk);
-  const int n_chunks = p.n_chunks;
-  const int vd = p.nv * kTD;
-
-  if (tid == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(s_ready, 128);
-    mbar_init(g1_done, 1);
-    mbar_init(v_ready, 128);
-    mbar_init(g2_done, 1);
-    mbar_init(g3_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 4) tmem_alloc(tmem_ptr_smem, SPLIT ? 256 : 128);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColD1 = 0, kColD1b = 32, kColD2 = 64, kColD3 = 96;
-  constexpr uint32_t kColD1c = 128, kColD2b = 160, kColD3b = 192;       // SPLIT: second-pass accumulators
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-  auto stamp = [&](int c, int slot) {
-    if (tracing && c >= 8 && c < 16) p.trace[(c - 8) * 16 + slot] = clock64();
-  };
-
-  if (warp == 4) {
-    // ------------------------------------------------------------------ producer
-    if (tid == 128) {
-      prefetch_tmap(&tmap_q);
-      prefetch_tmap(&tmap_k);
-      const long long hc0 = (long long)h * n_chunks;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
-        uint8_t* sb = smem + st * kStageBytes;
-        mbar_wait(&empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[st], kTxBytes);
-        const long long hc = hc0 + c;
-        const uint8_t* kimg = p.kcd_img + hc * 32768;
-        bulk_g2s(sb + kOffA1, kimg, 8192, &full[st]);                       // kcd_hi c0
-        bulk_g2s(sb + kOffA1 + 16384, kimg + 8192, 8192, &full[st]);        // kcd_hi c1
-        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);             // kcd_lo c0, c1
-        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);  // intra hi, lo
-        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
-        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
-        tma_load_2d(sb + kOffA1 + 8192, &tmap_q, kh * kTD, c * kTC, &full[st]);
-        tma_load_2d(sb + kOffA1 + 16384 + 8192, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
-        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
-        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (tid == 160) {
-      const uint32_t id_k = umma_idesc_bf16_m128(kTSV);                     // A, B K-major
-      const uint32_t id_amn = umma_idesc_bf16_m128(kTSV) | (1u << 15);      // A MN-major (k tile), B K-major
-      const uint32_t sh = smem_u32(smem + kOffSH), slo = smem_u32(smem + kOffSL);
-      const uint32_t vh = smem_u32(smem + kOffVH), vl = smem_u32(smem + kOffVL);
-      const uint32_t vdh = smem_u32(smem + kOffVDH), vdl = smem_u32(smem + kOffVDL);
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-        const uint32_t sb = smem_u32(smem + st * kStageBytes);
-        mbar_wait(&full[st], ph);
-        mbar_wait(s_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 0);
-        // G1: [kcd_hi ; q] (S_hi + S_lo) -> D1 ;  [kcd_lo ; *] S_hi -> D1b
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = sb + (pass < 2 ? kOffA1 : kOffA1L);
-          const uint32_t a_chunk = pass < 2 ? 16384u : 8192u;
-          const uint32_t b0 = pass == 1 ? slo : sh;
-          const uint32_t dcol = pass == 2 ? kColD1b : ((SPLIT && pass == 1) ? kColD1c : kColD1);
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            const uint64_t ad = umma_desc_k_sw128(a0 + ch * a_chunk);
-            const uint64_t bd = umma_desc_k_sw128(b0 + ch * 4096);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(tmem_base + dcol, ad + 2 * ks, bd + 2 * ks, id_k, ((!SPLIT && pass == 1) || ch > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(g1_done);
-        stamp(c, 1);
-        mbar_wait(v_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 2);
-        // G2: dS = k^T (vdec_hi + vdec_lo)
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const uint64_t bd = umma_desc_k_sw128(pass ? vdl : vdh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
-            umma_bf16(tmem_base + ((SPLIT && pass) ? kColD2b : kColD2), ad, bd + 2 * ks, id_amn, ((!SPLIT && pass > 0) || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(g2_done);
-        // G3: [intra_hi ; intra_lo] (v_hi + v_lo)
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const uint64_t ad = umma_desc_k_sw128(sb + kOffA3);
-          const uint64_t bd = umma_desc_k_sw128(pass ? vl : vh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem_base + ((SPLIT && pass) ? kColD3b : kColD3), ad + 2 * ks, bd + 2 * ks, id_k, ((!SPLIT && pass > 0) || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(g3_done);
-        umma_commit(&empty[st]);
-        stamp(c, 3);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ CUDA-core warps: thread = TMEM lane
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float s[kTSV];                                  // state row k = tid, columns of this dv slice
-    {
-      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
-#pragma unroll
-      for (int j4 = 0; j4 < kTSV / 4; ++j4) {
-        const float4 v = src[j4];
-        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
-      }
-    }
-    auto write_s_tiles = [&]() {
-#pragma unroll
-      for (int j = 0; j < kTSV; ++j) {
-        unsigned short hi, lo;
-        split_bf16(s[j], hi, lo);
-        const uint32_t off = sw128_off(j, tid, 4096);
-        *reinterpret_cast<unsigned short*>(smem + kOffSH + off) = hi;
-        *reinterpret_cast<unsigned short*>(smem + kOffSL + off) = lo;
-      }
-    };
-    write_s_tiles();
-    fence_proxy_async_smem();
-    mbar_arrive(s_ready);
-    float* xch = reinterpret_cast<float*>(smem + kOffX);
-    for (int c = 0; c < n_chunks; ++c) {
-      const int st = c & 1;
-      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-      const uint8_t* sb = smem + st * kStageBytes;
-      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
-      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
-      mbar_wait(&full[st], ph);                     // this chunk's gcum / vcorr are in shared memory
-      const int i = tid & 63;                        // token row of this thread in G1 / G3
-      const float g_last = sg[kTC - 1], g_i = sg[i];
-      const float d_last = expf(g_last);
-      float it[kTSV];
-#pragma unroll
-      for (int j = 0; j < kTSV; ++j) it[j] = 0.f;
-      mbar_wait(g1_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 4);
-      if (tid < 64) {
-        uint32_t a[32], b[32];
-        tmem_ld32(lane_addr + kColD1, a);
-        tmem_ld32(lane_addr + kColD1b, b);
-        if constexpr (SPLIT) {
-          uint32_t cc[32];
-          tmem_ld32(lane_addr + kColD1c, cc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
-        }
-        tmem_ld_wait();
-        const float dec = expf(g_last - g_i);
-#pragma unroll
-        for (int j4 = 0; j4 < kTSV / 4; ++j4) {
-          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + 4 * j4);
-          const float vcv[4] = {vc4.x, vc4.y, vc4.z, vc4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = 4 * j4 + e;
-            const float v = vcv[e] - (__uint_as_float(a[j]) + __uint_as_float(b[j]));
-            unsigned short hi, lo, dhi, dlo;
-            split_bf16(v, hi, lo);
-            split_bf16(v * dec, dhi, dlo);
-            const uint32_t off = sw128_off(j, i, 0);
-            *reinterpret_cast<unsigned short*>(smem + kOffVH + off) = hi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVL + off) = lo;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDH + off) = dhi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDL + off) = dlo;
-          }
-        }
-      } else {
-        uint32_t a[32];
-        tmem_ld32(lane_addr + kColD1, a);
-        if constexpr (SPLIT) {
-          uint32_t cc[32];
-          tmem_ld32(lane_addr + kColD1c, cc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
-        }
-        tmem_ld_wait();
-        const float eg = expf(g_i);
-#pragma unroll
-        for (int j = 0; j < kTSV; ++j) it[j] = eg * __uint_as_float(a[j]);
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(v_ready);
-      if (tid == 0) stamp(c, 5);
-      // state update: S = e^{g_last} S + dS
-      mbar_wait(g2_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 6);
-      {
-        uint32_t a[32];
-        tmem_ld32(lane_addr + kColD2, a);
-        if constexpr (SPLIT) {
-          uint32_t cc[32];
-          tmem_ld32(lane_addr + kColD2b, cc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < kTSV; ++j) s[j] = fmaf(d_last, s[j], __uint_as_float(a[j]));
-      }
-      if (c + 1 < n_chunks) {
-        write_s_tiles();
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        mbar_arrive(s_ready);
-      }
-      if (tid == 0) stamp(c, 7);
-      // output rows of this chunk
-      mbar_wait(g3_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 8);
-      {
-        uint32_t a[32];
-        tmem_ld32(lane_addr + kColD3, a);
-        if constexpr (SPLIT) {
-          uint32_t cc[32];
-          tmem_ld32(lane_addr + kColD3b, cc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < kTSV; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(cc[j]));
-        }
-        tmem_ld_wait();
-        if (tid < 64) {
-#pragma unroll
-          for (int j4 = 0; j4 < kTSV / 4; ++j4)
-            *reinterpret_cast<float4*>(xch + i * kVcLd + 4 * j4) =
-                make_float4(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1]), __uint_as_float(a[4 * j4 + 2]),
-                            __uint_as_float(a[4 * j4 + 3]));
-        }
-        named_bar_sync(1, 128);
-        if (tid >= 64) {
-          const int t = c * kTC + i;
-          uint32_t o[kTSV / 2];
-#pragma unroll
-          for (int j4 = 0; j4 < kTSV / 4; ++j4) {
-            const float4 x = *reinterpret_cast<const float4*>(xch + i * kVcLd + 4 * j4);
-            const float r0 = it[4 * j4] + x.x + __uint_as_float(a[4 * j4]);
-            const float r1 = it[4 * j4 + 1] + x.y + __uint_as_float(a[4 * j4 + 1]);
-            const float r2 = it[4 * j4 + 2] + x.z + __uint_as_float(a[4 * j4 + 2]);
-            const float r3 = it[4 * j4 + 3] + x.w + __uint_as_float(a[4 * j4 + 3]);
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(r0, r1), p1 = __floats2bfloat162_rn(r2, r3);
-            o[2 * j4] = *reinterpret_cast<uint32_t*>(&p0);
-            o[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&p1);
-          }
-          if (t < p.M) {
-            uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV);
-#pragma unroll
-            for (int q = 0; q < kTSV / 8; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-          }
-        }
-      }
-      tc_fence_before_sync();
-      if (tid == 0) stamp(c, 9);
-    }
-    {
-      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
-#pragma unroll
-      for (int j4 = 0; j4 < kTSV / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, SPLIT ? 256 : 128);
-}
-
-
-
 // --------------------------------------------------------------------------------------------------------------------
-// Scan, second layout (measured motivation, profiles/r02c_gdn_scan_timeline.txt: of 4400 cycles per chunk, 1530 were two
-// warps writing the v operand tiles while the other two idled, and the epilogue needed a cross-lane exchange).  Differences:
-//   * G1 stacks [q ; kcd_hi]: IT lands on lanes 0-63, VP on lanes 64-127; the kcd_lo tile is addressed 8 KB early so that
-//     its product lands on lanes 64-127 too.
-//   * warps 2-3 form v = vcorr - VP in fp32 and park it in shared memory; after one 128-thread barrier ALL four warps split
-//     and store the operand tiles (16 columns each).
-//   * G3 uses two 64-row tiles (intra_hi, intra_lo) accumulating on lanes 0-63, where IT already is: the epilogue is local
-//     to warps 0-1, no exchange buffer.
-// --------------------------------------------------------------------------------------------------------------------
-constexpr int kOffXV = kOffX;                // fp32 [64][36] v rows (the exchange buffer of the first layout)
-
-__global__ void __launch_bounds__(kTThreads, 1)
-    gdn_scan_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* full = bars;           // [2]
-  uint64_t* empty = bars + 2;      // [2]
-  uint64_t* s_ready = bars + 4;
-  uint64_t* g1_done = bars + 5;
-  uint64_t* v_ready = bars + 6;
-  uint64_t* g2_done = bars + 7;
-  uint64_t* g3_done = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int h = blockIdx.x, sl = blockIdx.y;
-  const int kh = h / (p.nv / p.nk);
-  const int n_chunks = p.n_chunks;
-  const int vd = p.nv * kTD;
-
-  if (tid == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(s_ready, 128);
-    mbar_init(g1_done, 1);
-    mbar_init(v_ready, 128);
-    mbar_init(g2_done, 1);
-    mbar_init(g3_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 4) tmem_alloc(tmem_ptr_smem, 128);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColD1 = 0, kColD1b = 32, kColD2 = 64, kColD3 = 96;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-  auto stamp = [&](int c, int slot) {
-    if (tracing && c >= 8 && c < 16) p.trace[(c - 8) * 16 + slot] = clock64();
-  };
-
-  if (warp == 4) {
-    if (tid == 128) {
-      prefetch_tmap(&tmap_q);
-      prefetch_tmap(&tmap_k);
-      const long long hc0 = (long long)h * n_chunks;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
-        uint8_t* sb = smem + st * kStageBytes;
-        mbar_wait(&empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[st], kTxBytes);
-        const long long hc = hc0 + c;
-        const uint8_t* kimg = p.kcd_img + hc * 32768;
-        // A1 = [q c0 | kcd_hi c0 | q c1 | kcd_hi c1], A1L = [kcd_lo c0 | kcd_lo c1]
-        tma_load_2d(sb + kOffA1, &tmap_q, kh * kTD, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 8192, kimg, 8192, &full[st]);
-        tma_load_2d(sb + kOffA1 + 16384, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 24576, kimg + 8192, 8192, &full[st]);
-        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
-        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
-        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
-        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 5) {
-    if (tid == 160) {
-      const uint32_t id_k = umma_idesc_bf16_m128(kTSV);
-      const uint32_t id_amn = umma_idesc_bf16_m128(kTSV) | (1u << 15);
-      const uint32_t sh = smem_u32(smem + kOffSH), slo = smem_u32(smem + kOffSL);
-      const uint32_t vh = smem_u32(smem + kOffVH), vl = smem_u32(smem + kOffVL);
-      const uint32_t vdh = smem_u32(smem + kOffVDH), vdl = smem_u32(smem + kOffVDL);
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-        const uint32_t sb = smem_u32(smem + st * kStageBytes);
-        mbar_wait(&full[st], ph);
-        mbar_wait(s_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 0);
-        // G1: [q ; kcd_hi] (S_hi + S_lo) -> D1 (IT lanes 0-63, VP lanes 64-127);  [* ; kcd_lo] S_hi -> D1b (lanes 64-127)
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t b0 = pass == 1 ? slo : sh;
-          const uint32_t dcol = pass < 2 ? kColD1 : kColD1b;
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            // kcd_lo chunk ch sits at A1L + 8K*ch; starting 8 KB earlier puts it on rows 64-127
-            const uint32_t a_addr = pass < 2 ? sb + kOffA1 + ch * 16384 : sb + kOffA1L + ch * 8192 - 8192;
-            const uint64_t ad = umma_desc_k_sw128(a_addr);
-            const uint64_t bd = umma_desc_k_sw128(b0 + ch * 4096);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(tmem_base + dcol, ad + 2 * ks, bd + 2 * ks, id_k, (pass == 1 || ch > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(g1_done);
-        stamp(c, 1);
-        mbar_wait(v_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 2);
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {          // G2: dS = k^T (vdec_hi + vdec_lo)
-          const uint64_t bd = umma_desc_k_sw128(pass ? vdl : vdh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
-            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn, (pass > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(g2_done);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {          // G3 (lanes 0-63): intra_hi (v_hi + v_lo) + intra_lo v_hi
-          const uint64_t ad = umma_desc_k_sw128(sb + kOffA3 + (pass == 2 ? 8192 : 0));
-          const uint64_t bd = umma_desc_k_sw128(pass == 1 ? vl : vh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem_base + kColD3, ad + 2 * ks, bd + 2 * ks, id_k, (pass > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(g3_done);
-        umma_commit(&empty[st]);
-        stamp(c, 3);
-      }
-    }
-    __syncwarp();
-  } else {
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float s[kTSV];
-    {
-      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
-#pragma unroll
-      for (int j4 = 0; j4 < kTSV / 4; ++j4) {
-        const float4 v = src[j4];
-        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
-      }
-    }
-    auto write_s_tiles = [&]() {
-#pragma unroll
-      for (int j = 0; j < kTSV; ++j) {
-        unsigned short hi, lo;
-        split_bf16(s[j], hi, lo);
-        const uint32_t off = sw128_off(j, tid, 4096);
-        *reinterpret_cast<unsigned short*>(smem + kOffSH + off) = hi;
-        *reinterpret_cast<unsigned short*>(smem + kOffSL + off) = lo;
-      }
-    };
-    write_s_tiles();
-    fence_proxy_async_smem();
-    mbar_arrive(s_ready);
-    float* xv = reinterpret_cast<float*>(smem + kOffXV);
-    const int i = tid & 63, half = tid >> 6;
-    for (int c = 0; c < n_chunks; ++c) {
-      const int st = c & 1;
-      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-      const uint8_t* sb = smem + st * kStageBytes;
-      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
-      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
-      mbar_wait(&full[st], ph);
-      const float g_last = sg[kTC - 1], g_i = sg[i];
-      const float d_last = expf(g_last);
-      const float dec = expf(g_last - g_i);
-      float it[kTSV];
-#pragma unroll
-      for (int j = 0; j < kTSV; ++j) it[j] = 0.f;
-      mbar_wait(g1_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 4);
-      if (tid >= 64) {                         // VP rows (lanes 64-127): v = vcorr - VP, parked as fp32
-        uint32_t a[32], b[32];
-        tmem_ld32(lane_addr + kColD1, a);
-        tmem_ld32(lane_addr + kColD1b, b);
-        tmem_ld_wait();
-        if (tid == 64) stamp(c, 10);
-#pragma unroll
-        for (int j4 = 0; j4 < kTSV / 4; ++j4) {
-          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + 4 * j4);
-          *reinterpret_cast<float4*>(xv + i * kVcLd + 4 * j4) =
-              make_float4(vc4.x - (__uint_as_float(a[4 * j4]) + __uint_as_float(b[4 * j4])),
-                          vc4.y - (__uint_as_float(a[4 * j4 + 1]) + __uint_as_float(b[4 * j4 + 1])),
-                          vc4.z - (__uint_as_float(a[4 * j4 + 2]) + __uint_as_float(b[4 * j4 + 2])),
-                          vc4.w - (__uint_as_float(a[4 * j4 + 3]) + __uint_as_float(b[4 * j4 + 3])));
-        }
-      } else {                                 // IT rows (lanes 0-63)
-        uint32_t a[32];
-        tmem_ld32(lane_addr + kColD1, a);
-        tmem_ld_wait();
-        const float eg = expf(g_i);
-#pragma unroll
-        for (int j = 0; j < kTSV; ++j) it[j] = eg * __uint_as_float(a[j]);
-      }
-      if (tid == 64) stamp(c, 11);
-      tc_fence_before_sync();
-      named_bar_sync(1, 128);
-      if (tid == 0) stamp(c, 12);
-      {                                        // all four warps: token i, 16 of the 32 columns -> hi/lo operand tiles
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 v4 = *reinterpret_cast<const float4*>(xv + i * kVcLd + half * 16 + 4 * j4);
-          const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int jj = 4 * j4 + e;             // row n = half * 16 + jj; (n & 7) == (jj & 7): the swizzle term is compile-time
-            unsigned short hi, lo, dhi, dlo;
-            split_bf16(vv[e], hi, lo);
-            split_bf16(vv[e] * dec, dhi, dlo);
-            const uint32_t off = (uint32_t)(half * 2048 + jj * 128 + ((((i >> 3) ^ (jj & 7)) << 4) | ((i & 7) << 1)));
-            *reinterpret_cast<unsigned short*>(smem + kOffVH + off) = hi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVL + off) = lo;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDH + off) = dhi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDL + off) = dlo;
-          }
-        }
-      }
-      if (tid == 0) stamp(c, 13);
-      fence_proxy_async_smem();
-      if (tid == 0) stamp(c, 14);
-      mbar_arrive(v_ready);
-      if (tid == 0) stamp(c, 5);
-      mbar_wait(g2_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 6);
-      {
-        uint32_t a[32];
-        tmem_ld32(lane_addr + kColD2, a);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < kTSV; ++j) s[j] = fmaf(d_last, s[j], __uint_as_float(a[j]));
-      }
-      if (tid == 0) stamp(c, 15);
-      if (c + 1 < n_chunks) {
-        write_s_tiles();
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        mbar_arrive(s_ready);
-      }
-      if (tid == 0) stamp(c, 7);
-      if (tid < 64) {                          // output rows: IT and intra.v share lanes 0-63
-        mbar_wait(g3_done, cp);
-        tc_fence_after_sync();
-        if (tid == 0) stamp(c, 8);
-        uint32_t a[32];
-        tmem_ld32(lane_addr + kColD3, a);
-        tmem_ld_wait();
-        const int t = c * kTC + i;
-        if (t < p.M) {
-          uint32_t o[kTSV / 2];
-#pragma unroll
-          for (int j2 = 0; j2 < kTSV / 2; ++j2) {
-            __nv_bfloat162 pr = __floats2bfloat162_rn(it[2 * j2] + __uint_as_float(a[2 * j2]), it[2 * j2 + 1] + __uint_as_float(a[2 * j2 + 1]));
-            o[j2] = *reinterpret_cast<uint32_t*>(&pr);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV);
-#pragma unroll
-          for (int q = 0; q < kTSV / 8; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        }
-        tc_fence_before_sync();
-        if (tid == 0) stamp(c, 9);
-      }
-    }
-    {
-      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + tid) * kTD + sl * kTSV);
-#pragma unroll
-      for (int j4 = 0; j4 < kTSV / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 128);
-}
-
-
-// --------------------------------------------------------------------------------------------------------------------
-// Scan, third layout = the second one with EIGHT CUDA-core warps.  Measured motivation (profiles/r02f_gdn_timelines_fine.txt):
-// with four core warps there is one warp per scheduler, every dependent instruction pays its full latency, and the tile
-// writing phases ran at IPC ~0.3 (1170 + 500 cycles per chunk).  Warps w and w + 4 share TMEM lane quadrant w & 3 and take
-// 16 of the 32 columns each: the VP threads (lanes 64-127) split and store their own 16 columns of v (no parking, no
-// exchange), every thread owns 16 columns of one state row.  Warp 8 = TMA producer, warp 9 = MMA issuer.
+// The scan kernel.  320 threads: warps 0-7 CUDA cores, warp 8 TMA producer, warp 9 MMA issuer (whole warp runs the role loop, one
+// elected lane issues: see ptx.cuh / ENGINEERING_NOTES.md on warp-uniform issue).  Core thread = (TMEM lane L, column half): warps w
+// and w + 4 share lane quadrant w & 3 and take 16 of the slice's 32 columns each, so every scheduler has two core warps.
+//   TMEM columns   D1 [0,64)  = [q ; kcd_hi] [S_hi | S_lo]   (lanes 0-63 = IT parts, 64-127 = VP parts; the two 32-column halves are
+//                  D1b [64,96) = [* ; kcd_lo] S_hi             added by the cores: hi/lo halves of a B operand are STACKED ALONG N, one
+//                  D2 [96,160) = k^T [vdec_hi | vdec_lo]       N = 64 instruction stream instead of two N = 32 ones: 16 + 4 + 8 MMAs
+//                  D3 [160,224) = intra_hi [v_hi | v_lo] (+ intra_lo v_hi on the first half)                      per chunk, not 24 + 8 + 12)
+//   per chunk      G1 -> cores: IT rows keep e^g (IT) in registers; VP rows park v = vcorr - VP as fp32 in shared memory
+//                  barrier -> every thread (column n = lane, token octet = warp) converts 8 tokens of one column pairwise
+//                  (cvt.rn.bf16x2: the packed word is the K-contiguous memory order) and writes v_hi / v_lo / vdec_hi / vdec_lo with
+//                  one 16-byte store each -> G2, G3 -> S = e^{g_last} S + dS in registers, new S_hi / S_lo tiles -> epilogue (local).
+// History of the layout with the measurements that drove each step: profiles/README.md (r02a ... r02l), ENGINEERING_NOTES.md.
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int kT3Threads = 320;
 
 __global__ void __launch_bounds__(kT3Threads, 1)
-    gdn_scan_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* full = bars;           // [2]
-  uint64_t* empty = bars + 2;      // [2]
-  uint64_t* s_ready = bars + 4;
-  uint64_t* g1_done = bars + 5;
-  uint64_t* v_ready = bars + 6;
-  uint64_t* g2_done = bars + 7;
-  uint64_t* g3_done = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int h = blockIdx.x, sl = blockIdx.y;
-  const int kh = h / (p.nv / p.nk);
-  const int n_chunks = p.n_chunks;
-  const int vd = p.nv * kTD;
-  constexpr int kHC = kTSV / 2;      // columns per thread
-
-  if (tid == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(s_ready, 256);
-    mbar_init(g1_done, 1);
-    mbar_init(v_ready, 256);
-    mbar_init(g2_done, 1);
-    mbar_init(g3_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 8) tmem_alloc(tmem_ptr_smem, 128);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColD1 = 0, kColD1b = 32, kColD2 = 64, kColD3 = 96;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-  auto stamp = [&](int c, int slot) {
-    if (tracing && c >= 8 && c < 16) p.trace[(c - 8) * 16 + slot] = clock64();
-  };
-
-  if (warp == 8) {
-    if (tid == 256) {
-      prefetch_tmap(&tmap_q);
-      prefetch_tmap(&tmap_k);
-      const long long hc0 = (long long)h * n_chunks;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
-        uint8_t* sb = smem + st * kStageBytes;
-        mbar_wait(&empty[st], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[st], kTxBytes);
-        const long long hc = hc0 + c;
-        const uint8_t* kimg = p.kcd_img + hc * 32768;
-        tma_load_2d(sb + kOffA1, &tmap_q, kh * kTD, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 8192, kimg, 8192, &full[st]);
-        tma_load_2d(sb + kOffA1 + 16384, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 24576, kimg + 8192, 8192, &full[st]);
-        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
-        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
-        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
-        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    if (tid == 288) {
-      const uint32_t id_k = umma_idesc_bf16_m128(kTSV);
-      const uint32_t id_amn = umma_idesc_bf16_m128(kTSV) | (1u << 15);
-      const uint32_t sh = smem_u32(smem + kOffSH), slo = smem_u32(smem + kOffSL);
-      const uint32_t vh = smem_u32(smem + kOffVH), vl = smem_u32(smem + kOffVL);
-      const uint32_t vdh = smem_u32(smem + kOffVDH), vdl = smem_u32(smem + kOffVDL);
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-        const uint32_t sb = smem_u32(smem + st * kStageBytes);
-        mbar_wait(&full[st], ph);
-        mbar_wait(s_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 0);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {          // G1, see gdn_scan_tc2_kernel
-          const uint32_t b0 = pass == 1 ? slo : sh;
-          const uint32_t dcol = pass < 2 ? kColD1 : kColD1b;
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            const uint32_t a_addr = pass < 2 ? sb + kOffA1 + ch * 16384 : sb + kOffA1L + ch * 8192 - 8192;
-            const uint64_t ad = umma_desc_k_sw128(a_addr);
-            const uint64_t bd = umma_desc_k_sw128(b0 + ch * 4096);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(tmem_base + dcol, ad + 2 * ks, bd + 2 * ks, id_k, (pass == 1 || ch > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(g1_done);
-        stamp(c, 1);
-        mbar_wait(v_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 2);
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const uint64_t bd = umma_desc_k_sw128(pass ? vdl : vdh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
-            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn, (pass > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(g2_done);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint64_t ad = umma_desc_k_sw128(sb + kOffA3 + (pass == 2 ? 8192 : 0));
-          const uint64_t bd = umma_desc_k_sw128(pass == 1 ? vl : vh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16(tmem_base + kColD3, ad + 2 * ks, bd + 2 * ks, id_k, (pass > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(g3_done);
-        umma_commit(&empty[st]);
-        stamp(c, 3);
-      }
-    }
-    __syncwarp();
-  } else {
-    const int L = (warp & 3) * 32 + (tid & 31);        // TMEM lane of this thread
-    const int hcol = warp >> 2;                        // which 16 of the 32 columns
-    const int j0 = hcol * kHC;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + j0;
-    float s[kHC];                                      // state row L, columns j0 .. j0+15
-    {
-      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
-#pragma unroll
-      for (int j4 = 0; j4 < kHC / 4; ++j4) {
-        const float4 v = src[j4];
-        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
-      }
-    }
-    // operand tile addressing: row n = j0 + jj (j0 is a multiple of 8, so (n & 7) == (jj & 7)), k = L or token index
-    uint8_t* s_hi = smem + kOffSH + j0 * 128;
-    uint8_t* s_lo = smem + kOffSL + j0 * 128;
-    const uint32_t k_off_s = (uint32_t)((L >> 6) * 4096 + ((L & 7) << 1));
-    const int kc_s = (L & 63) >> 3;
-    auto write_s_tiles = [&]() {
-#pragma unroll
-      for (int jj = 0; jj < kHC; ++jj) {
-        unsigned short hi, lo;
-        split_bf16(s[jj], hi, lo);
-        const uint32_t off = k_off_s + jj * 128 + ((kc_s ^ (jj & 7)) << 4);
-        *reinterpret_cast<unsigned short*>(s_hi + off) = hi;
-        *reinterpret_cast<unsigned short*>(s_lo + off) = lo;
-      }
-    };
-    write_s_tiles();
-    fence_proxy_async_smem();
-    mbar_arrive(s_ready);
-    const int i = L & 63;                              // token row (IT for L < 64, VP for L >= 64)
-    const int kc_v = i >> 3;
-    const uint32_t k_off_v = (uint32_t)(j0 * 128 + ((i & 7) << 1));
-    for (int c = 0; c < n_chunks; ++c) {
-      const int st = c & 1;
-      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-      const uint8_t* sb = smem + st * kStageBytes;
-      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
-      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
-      mbar_wait(&full[st], ph);
-      const float g_last = sg[kTC - 1], g_i = sg[i];
-      const float d_last = expf(g_last);
-      float it[kHC];
-#pragma unroll
-      for (int jj = 0; jj < kHC; ++jj) it[jj] = 0.f;
-      mbar_wait(g1_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 4);
-      if (L >= 64) {                           // VP rows: v = vcorr - VP for this thread's 16 columns -> hi/lo operand tiles
-        uint32_t a[16], b[16];
-        tmem_ld16(lane_addr + kColD1, a);
-        tmem_ld16(lane_addr + kColD1b, b);
-        tmem_ld_wait();
-        const float dec = expf(g_last - g_i);
-#pragma unroll
-        for (int j4 = 0; j4 < kHC / 4; ++j4) {
-          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + j0 + 4 * j4);
-          const float vcv[4] = {vc4.x, vc4.y, vc4.z, vc4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int jj = 4 * j4 + e;
-            const float v = vcv[e] - (__uint_as_float(a[jj]) + __uint_as_float(b[jj]));
-            unsigned short hi, lo, dhi, dlo;
-            split_bf16(v, hi, lo);
-            split_bf16(v * dec, dhi, dlo);
-            const uint32_t off = k_off_v + jj * 128 + ((kc_v ^ (jj & 7)) << 4);
-            *reinterpret_cast<unsigned short*>(smem + kOffVH + off) = hi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVL + off) = lo;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDH + off) = dhi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDL + off) = dlo;
-          }
-        }
-      } else {                                 // IT rows
-        uint32_t a[16];
-        tmem_ld16(lane_addr + kColD1, a);
-        tmem_ld_wait();
-        const float eg = expf(g_i);
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) it[jj] = eg * __uint_as_float(a[jj]);
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(v_ready);
-      if (tid == 64) stamp(c, 5);
-      mbar_wait(g2_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 6);
-      {
-        uint32_t a[16];
-        tmem_ld16(lane_addr + kColD2, a);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) s[jj] = fmaf(d_last, s[jj], __uint_as_float(a[jj]));
-      }
-      if (c + 1 < n_chunks) {
-        write_s_tiles();
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        mbar_arrive(s_ready);
-      }
-      if (tid == 0) stamp(c, 7);
-      if (L < 64) {                            // output rows (IT and intra.v share lanes 0-63)
-        mbar_wait(g3_done, cp);
-        tc_fence_after_sync();
-        if (tid == 0) stamp(c, 8);
-        uint32_t a[16];
-        tmem_ld16(lane_addr + kColD3, a);
-        tmem_ld_wait();
-        const int t = c * kTC + i;
-        if (t < p.M) {
-          uint32_t o[kHC / 2];
-#pragma unroll
-          for (int j2 = 0; j2 < kHC / 2; ++j2) {
-            __nv_bfloat162 pr = __floats2bfloat162_rn(it[2 * j2] + __uint_as_float(a[2 * j2]), it[2 * j2 + 1] + __uint_as_float(a[2 * j2 + 1]));
-            o[j2] = *reinterpret_cast<uint32_t*>(&pr);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV + j0);
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-        tc_fence_before_sync();
-        if (tid == 0) stamp(c, 9);
-      }
-    }
-    {
-      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
-#pragma unroll
-      for (int j4 = 0; j4 < kHC / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 128);
-}
-
-// --------------------------------------------------------------------------------------------------------------------
-// Scan, fourth layout = the third one with the hi and lo halves of every B operand STACKED ALONG N.  Measured motivation
-// (profiles/r02d_mma_issue_ubench.txt): a tcgen05.mma costs ~44 cycles to issue whether N is 32 or 64, so
-// A.[S_hi ; S_lo] as ONE N=64 instruction stream replaces two N=32 streams: G1 24 -> 16 MMAs, G2 8 -> 4, G3 12 -> 8; the
-// CUDA cores add the two 32-column halves when they read the accumulators back.
-// (Third layout:) the second one with EIGHT CUDA-core warps.  Measured motivation (profiles/r02f_gdn_timelines_fine.txt):
-// with four core warps there is one warp per scheduler, every dependent instruction pays its full latency, and the tile
-// writing phases ran at IPC ~0.3 (1170 + 500 cycles per chunk).  Warps w and w + 4 share TMEM lane quadrant w & 3 and take
-// 16 of the 32 columns each: the VP threads (lanes 64-127) split and store their own 16 columns of v (no parking, no
-// exchange), every thread owns 16 columns of one state row.  Warp 8 = TMA producer, warp 9 = MMA issuer.
-// --------------------------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(kT3Threads, 1)
-    gdn_scan_tc4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* full = bars;           // [2]
-  uint64_t* empty = bars + 2;      // [2]
-  uint64_t* s_ready = bars + 4;
-  uint64_t* g1_done = bars + 5;
-  uint64_t* v_ready = bars + 6;
-  uint64_t* g2_done = bars + 7;
-  uint64_t* g3_done = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
-  // warp index through a shuffle: the role branches are then provably warp-uniform and the operands of tcgen05.mma / commit / TMA
-  // stay in uniform registers (from a divergent `tid == 288` branch every MMA paid an ELECT + R2UR.BROADCAST loop, ~50 cycles)
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  const int h = blockIdx.x, sl = blockIdx.y;
-  const int kh = h / (p.nv / p.nk);
-  const int n_chunks = p.n_chunks;
-  const int vd = p.nv * kTD;
-  constexpr int kHC = kTSV / 2;      // columns per thread
-
-  if (tid == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(s_ready, 256);
-    mbar_init(g1_done, 1);
-    mbar_init(v_ready, 256);
-    mbar_init(g2_done, 1);
-    mbar_init(g3_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 8) tmem_alloc(tmem_ptr_smem, 256);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColD1 = 0, kColD1b = 64, kColD2 = 96, kColD3 = 160;     // D1, D2, D3: 64 columns (hi-part | lo-part)
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-  auto stamp = [&](int c, int slot) {
-    if (tracing && c >= 8 && c < 16 && ((tid & 31) == 0 || tid == 64)) p.trace[(c - 8) * 16 + slot] = clock64();
-  };
-
-  if (warp == 8) {
-    {
-      if (elect_one()) {
-        prefetch_tmap(&tmap_q);
-        prefetch_tmap(&tmap_k);
-      }
-      const long long hc0 = (long long)h * n_chunks;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
-        uint8_t* sb = smem + st * kStageBytes;
-        mbar_wait(&empty[st], ph ^ 1u);
-        const long long hc = hc0 + c;
-        const uint8_t* kimg = p.kcd_img + hc * 32768;
-        if (elect_one()) {
-        mbar_arrive_expect_tx(&full[st], kTxBytes);
-        tma_load_2d(sb + kOffA1, &tmap_q, kh * kTD, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 8192, kimg, 8192, &full[st]);
-        tma_load_2d(sb + kOffA1 + 16384, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 24576, kimg + 8192, 8192, &full[st]);
-        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
-        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
-        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
-        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
-        }
-        __syncwarp();
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    {
-      const uint32_t id_k = umma_idesc_bf16_m128(kTSV), id_k2 = umma_idesc_bf16_m128(2 * kTSV);
-      const uint32_t id_amn2 = umma_idesc_bf16_m128(2 * kTSV) | (1u << 15);
-      const uint32_t sS = smem_u32(smem + kOffSH);                 // per K chunk: [S_hi 32 rows | S_lo 32 rows] = one N=64 tile
-      const uint32_t vh = smem_u32(smem + kOffVH), vdh = smem_u32(smem + kOffVDH);   // [v_hi | v_lo], [vdec_hi | vdec_lo]
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-        const uint32_t sb = smem_u32(smem + st * kStageBytes);
-        mbar_wait(&full[st], ph);
-        mbar_wait(s_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 0);
-        // G1: [q ; kcd_hi] [S_hi ; S_lo]^T -> D1 (64 columns);  [* ; kcd_lo] S_hi^T -> D1b (32 columns, lanes 64-127)
-        if (elect_one()) {
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const uint64_t ad = umma_desc_k_sw128(sb + kOffA1 + ch * 16384);
-          const uint64_t bd = umma_desc_k_sw128(sS + ch * 8192);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD1, ad + 2 * ks, bd + 2 * ks, id_k2, (ch > 0 || ks > 0) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const uint64_t ad = umma_desc_k_sw128(sb + kOffA1L + ch * 8192 - 8192);
-          const uint64_t bd = umma_desc_k_sw128(sS + ch * 8192);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD1b, ad + 2 * ks, bd + 2 * ks, id_k, (ch > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(g1_done);
-        }
-        __syncwarp();
-        stamp(c, 1);
-        mbar_wait(v_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 2);
-        if (elect_one()) {
-        {                                                 // G2: dS = k^T [vdec_hi ; vdec_lo]^T  (64 columns)
-          const uint64_t bd = umma_desc_k_sw128(vdh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
-            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn2, ks > 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(g2_done);
-        {                                                 // G3 (lanes 0-63): intra_hi [v_hi ; v_lo]^T, then intra_lo v_hi^T onto the hi half
-          const uint64_t ah = umma_desc_k_sw128(sb + kOffA3), al = umma_desc_k_sw128(sb + kOffA3 + 8192);
-          const uint64_t bd = umma_desc_k_sw128(vh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD3, ah + 2 * ks, bd + 2 * ks, id_k2, ks > 0 ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD3, al + 2 * ks, bd + 2 * ks, id_k, 1u);
-        }
-        umma_commit(g3_done);
-        umma_commit(&empty[st]);
-        }
-        __syncwarp();
-        stamp(c, 3);
-      }
-    }
-    __syncwarp();
-  } else {
-    const int L = (warp & 3) * 32 + (tid & 31);        // TMEM lane of this thread
-    const int hcol = warp >> 2;                        // which 16 of the 32 columns
-    const int j0 = hcol * kHC;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + j0;
-    float s[kHC];                                      // state row L, columns j0 .. j0+15
-    {
-      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
-#pragma unroll
-      for (int j4 = 0; j4 < kHC / 4; ++j4) {
-        const float4 v = src[j4];
-        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
-      }
-    }
-    // operand tile addressing: row n = j0 + jj (j0 is a multiple of 8, so (n & 7) == (jj & 7)), k = L or token index
-    uint8_t* s_hi = smem + kOffSH + j0 * 128;                       // K chunk (L >> 6): [S_hi rows 0-31 | S_lo rows 0-31]
-    uint8_t* s_lo = s_hi + 4096;
-    const uint32_t k_off_s = (uint32_t)((L >> 6) * 8192 + ((L & 7) << 1));
-    const int kc_s = (L & 63) >> 3;
-    auto write_s_tiles = [&]() {
-#pragma unroll
-      for (int jj = 0; jj < kHC; ++jj) {
-        unsigned short hi, lo;
-        split_bf16(s[jj], hi, lo);
-        const uint32_t off = k_off_s + jj * 128 + ((kc_s ^ (jj & 7)) << 4);
-        *reinterpret_cast<unsigned short*>(s_hi + off) = hi;
-        *reinterpret_cast<unsigned short*>(s_lo + off) = lo;
-      }
-    };
-    write_s_tiles();
-    fence_proxy_async_smem();
-    mbar_arrive(s_ready);
-    const int i = L & 63;                              // token row (IT for L < 64, VP for L >= 64)
-    const int kc_v = i >> 3;
-    const uint32_t k_off_v = (uint32_t)(j0 * 128 + ((i & 7) << 1));
-    for (int c = 0; c < n_chunks; ++c) {
-      const int st = c & 1;
-      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-      const uint8_t* sb = smem + st * kStageBytes;
-      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
-      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
-      mbar_wait(&full[st], ph);
-      const float g_last = sg[kTC - 1], g_i = sg[i];
-      const float d_last = expf(g_last);
-      float it[kHC];
-#pragma unroll
-      for (int jj = 0; jj < kHC; ++jj) it[jj] = 0.f;
-      mbar_wait(g1_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 4);
-      if (L >= 64) {                           // VP rows: v = vcorr - VP for this thread's 16 columns -> hi/lo operand tiles
-        uint32_t a[16], a2[16], b[16];
-        tmem_ld16(lane_addr + kColD1, a);
-        tmem_ld16(lane_addr + kColD1 + kTSV, a2);
-        tmem_ld16(lane_addr + kColD1b, b);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) a[jj] = __float_as_uint(__uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
-        const float dec = expf(g_last - g_i);
-#pragma unroll
-        for (int j4 = 0; j4 < kHC / 4; ++j4) {
-          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + j0 + 4 * j4);
-          const float vcv[4] = {vc4.x, vc4.y, vc4.z, vc4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int jj = 4 * j4 + e;
-            const float v = vcv[e] - (__uint_as_float(a[jj]) + __uint_as_float(b[jj]));
-            unsigned short hi, lo, dhi, dlo;
-            split_bf16(v, hi, lo);
-            split_bf16(v * dec, dhi, dlo);
-            const uint32_t off = k_off_v + jj * 128 + ((kc_v ^ (jj & 7)) << 4);
-            *reinterpret_cast<unsigned short*>(smem + kOffVH + off) = hi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVL + off) = lo;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDH + off) = dhi;
-            *reinterpret_cast<unsigned short*>(smem + kOffVDL + off) = dlo;
-          }
-        }
-      } else {                                 // IT rows
-        uint32_t a[16], a2[16];
-        tmem_ld16(lane_addr + kColD1, a);
-        tmem_ld16(lane_addr + kColD1 + kTSV, a2);
-        tmem_ld_wait();
-        const float eg = expf(g_i);
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) it[jj] = eg * (__uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(v_ready);
-      if (tid == 64) stamp(c, 5);
-      mbar_wait(g2_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 6);
-      {
-        uint32_t a[16], a2[16];
-        tmem_ld16(lane_addr + kColD2, a);
-        tmem_ld16(lane_addr + kColD2 + kTSV, a2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) s[jj] = fmaf(d_last, s[jj], __uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
-      }
-      if (c + 1 < n_chunks) {
-        write_s_tiles();
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        mbar_arrive(s_ready);
-      }
-      if (tid == 0) stamp(c, 7);
-      if (L < 64) {                            // output rows (IT and intra.v share lanes 0-63)
-        mbar_wait(g3_done, cp);
-        tc_fence_after_sync();
-        if (tid == 0) stamp(c, 8);
-        uint32_t a[16], a2[16];
-        tmem_ld16(lane_addr + kColD3, a);
-        tmem_ld16(lane_addr + kColD3 + kTSV, a2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) a[jj] = __float_as_uint(__uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
-        const int t = c * kTC + i;
-        if (t < p.M) {
-          uint32_t o[kHC / 2];
-#pragma unroll
-          for (int j2 = 0; j2 < kHC / 2; ++j2) {
-            __nv_bfloat162 pr = __floats2bfloat162_rn(it[2 * j2] + __uint_as_float(a[2 * j2]), it[2 * j2 + 1] + __uint_as_float(a[2 * j2 + 1]));
-            o[j2] = *reinterpret_cast<uint32_t*>(&pr);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV + j0);
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-        tc_fence_before_sync();
-        if (tid == 0) stamp(c, 9);
-      }
-    }
-    {
-      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
-#pragma unroll
-      for (int j4 = 0; j4 < kHC / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 256);
-}
-
-
-// --------------------------------------------------------------------------------------------------------------------
-// Scan, fifth layout = the fourth one with the v tiles written by ALL eight core warps: the VP threads (lanes 64-127, i.e. only
-// two of the four schedulers) park v as fp32 in shared memory, one 256-thread barrier, then every thread splits and stores 8 columns
-// of one token (the hi/lo split + four 2-byte stores per element are what the v phase costs: ~17 instructions per element).
-// (Fourth layout:) the third one with the hi and lo halves of every B operand STACKED ALONG N.  Measured motivation
-// (profiles/r02d_mma_issue_ubench.txt): a tcgen05.mma costs ~44 cycles to issue whether N is 32 or 64, so
-// A.[S_hi ; S_lo] as ONE N=64 instruction stream replaces two N=32 streams: G1 24 -> 16 MMAs, G2 8 -> 4, G3 12 -> 8; the
-// CUDA cores add the two 32-column halves when they read the accumulators back.
-// (Third layout:) the second one with EIGHT CUDA-core warps.  Measured motivation (profiles/r02f_gdn_timelines_fine.txt):
-// with four core warps there is one warp per scheduler, every dependent instruction pays its full latency, and the tile
-// writing phases ran at IPC ~0.3 (1170 + 500 cycles per chunk).  Warps w and w + 4 share TMEM lane quadrant w & 3 and take
-// 16 of the 32 columns each: the VP threads (lanes 64-127) split and store their own 16 columns of v (no parking, no
-// exchange), every thread owns 16 columns of one state row.  Warp 8 = TMA producer, warp 9 = MMA issuer.
-// --------------------------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(kT3Threads, 1)
-    gdn_scan_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* full = bars;           // [2]
-  uint64_t* empty = bars + 2;      // [2]
-  uint64_t* s_ready = bars + 4;
-  uint64_t* g1_done = bars + 5;
-  uint64_t* v_ready = bars + 6;
-  uint64_t* g2_done = bars + 7;
-  uint64_t* g3_done = bars + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
-  // warp index through a shuffle: the role branches are then provably warp-uniform and the operands of tcgen05.mma / commit / TMA
-  // stay in uniform registers (from a divergent `tid == 288` branch every MMA paid an ELECT + R2UR.BROADCAST loop, ~50 cycles)
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  const int h = blockIdx.x, sl = blockIdx.y;
-  const int kh = h / (p.nv / p.nk);
-  const int n_chunks = p.n_chunks;
-  const int vd = p.nv * kTD;
-  constexpr int kHC = kTSV / 2;      // columns per thread
-
-  if (tid == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(s_ready, 256);
-    mbar_init(g1_done, 1);
-    mbar_init(v_ready, 256);
-    mbar_init(g2_done, 1);
-    mbar_init(g3_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 8) tmem_alloc(tmem_ptr_smem, 256);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColD1 = 0, kColD1b = 64, kColD2 = 96, kColD3 = 160;     // D1, D2, D3: 64 columns (hi-part | lo-part)
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-  auto stamp = [&](int c, int slot) {
-    if (tracing && c >= 8 && c < 16 && ((tid & 31) == 0 || tid == 64)) p.trace[(c - 8) * 16 + slot] = clock64();
-  };
-
-  if (warp == 8) {
-    {
-      if (elect_one()) {
-        prefetch_tmap(&tmap_q);
-        prefetch_tmap(&tmap_k);
-      }
-      const long long hc0 = (long long)h * n_chunks;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u;
-        uint8_t* sb = smem + st * kStageBytes;
-        mbar_wait(&empty[st], ph ^ 1u);
-        const long long hc = hc0 + c;
-        const uint8_t* kimg = p.kcd_img + hc * 32768;
-        if (elect_one()) {
-        mbar_arrive_expect_tx(&full[st], kTxBytes);
-        tma_load_2d(sb + kOffA1, &tmap_q, kh * kTD, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 8192, kimg, 8192, &full[st]);
-        tma_load_2d(sb + kOffA1 + 16384, &tmap_q, kh * kTD + 64, c * kTC, &full[st]);
-        bulk_g2s(sb + kOffA1 + 24576, kimg + 8192, 8192, &full[st]);
-        bulk_g2s(sb + kOffA1L, kimg + 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffA3, p.intra_img + hc * 16384, 16384, &full[st]);
-        bulk_g2s(sb + kOffVC, p.vcorr + ((hc * (kTD / kTSV) + sl) * kTC) * kVcLd, kTC * kVcLd * 4, &full[st]);
-        bulk_g2s(sb + kOffG, p.gcum + hc * kTC, kTC * 4, &full[st]);
-        tma_load_2d(sb + kOffA2, &tmap_k, kh * kTD, c * kTC, &full[st]);
-        tma_load_2d(sb + kOffA2 + 8192, &tmap_k, kh * kTD + 64, c * kTC, &full[st]);
-        }
-        __syncwarp();
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    {
-      const uint32_t id_k = umma_idesc_bf16_m128(kTSV), id_k2 = umma_idesc_bf16_m128(2 * kTSV);
-      const uint32_t id_amn2 = umma_idesc_bf16_m128(2 * kTSV) | (1u << 15);
-      const uint32_t sS = smem_u32(smem + kOffSH);                 // per K chunk: [S_hi 32 rows | S_lo 32 rows] = one N=64 tile
-      const uint32_t vh = smem_u32(smem + kOffVH), vdh = smem_u32(smem + kOffVDH);   // [v_hi | v_lo], [vdec_hi | vdec_lo]
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c & 1;
-        const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-        const uint32_t sb = smem_u32(smem + st * kStageBytes);
-        mbar_wait(&full[st], ph);
-        mbar_wait(s_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 0);
-        // G1: [q ; kcd_hi] [S_hi ; S_lo]^T -> D1 (64 columns);  [* ; kcd_lo] S_hi^T -> D1b (32 columns, lanes 64-127)
-        if (elect_one()) {
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const uint64_t ad = umma_desc_k_sw128(sb + kOffA1 + ch * 16384);
-          const uint64_t bd = umma_desc_k_sw128(sS + ch * 8192);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD1, ad + 2 * ks, bd + 2 * ks, id_k2, (ch > 0 || ks > 0) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const uint64_t ad = umma_desc_k_sw128(sb + kOffA1L + ch * 8192 - 8192);
-          const uint64_t bd = umma_desc_k_sw128(sS + ch * 8192);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD1b, ad + 2 * ks, bd + 2 * ks, id_k, (ch > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(g1_done);
-        }
-        __syncwarp();
-        stamp(c, 1);
-        mbar_wait(v_ready, cp);
-        tc_fence_after_sync();
-        stamp(c, 2);
-        if (elect_one()) {
-        {                                                 // G2: dS = k^T [vdec_hi ; vdec_lo]^T  (64 columns)
-          const uint64_t bd = umma_desc_k_sw128(vdh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = tc_desc_mn_sw128(sb + kOffA2 + ks * 2048, 8192, 1024);
-            umma_bf16(tmem_base + kColD2, ad, bd + 2 * ks, id_amn2, ks > 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(g2_done);
-        {                                                 // G3 (lanes 0-63): intra_hi [v_hi ; v_lo]^T, then intra_lo v_hi^T onto the hi half
-          const uint64_t ah = umma_desc_k_sw128(sb + kOffA3), al = umma_desc_k_sw128(sb + kOffA3 + 8192);
-          const uint64_t bd = umma_desc_k_sw128(vh);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD3, ah + 2 * ks, bd + 2 * ks, id_k2, ks > 0 ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColD3, al + 2 * ks, bd + 2 * ks, id_k, 1u);
-        }
-        umma_commit(g3_done);
-        umma_commit(&empty[st]);
-        }
-        __syncwarp();
-        stamp(c, 3);
-      }
-    }
-    __syncwarp();
-  } else {
-    const int L = (warp & 3) * 32 + (tid & 31);        // TMEM lane of this thread
-    const int hcol = warp >> 2;                        // which 16 of the 32 columns
-    const int j0 = hcol * kHC;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + j0;
-    float s[kHC];                                      // state row L, columns j0 .. j0+15
-    {
-      const float4* src = reinterpret_cast<const float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
-#pragma unroll
-      for (int j4 = 0; j4 < kHC / 4; ++j4) {
-        const float4 v = src[j4];
-        s[4 * j4] = v.x; s[4 * j4 + 1] = v.y; s[4 * j4 + 2] = v.z; s[4 * j4 + 3] = v.w;
-      }
-    }
-    // operand tile addressing: row n = j0 + jj (j0 is a multiple of 8, so (n & 7) == (jj & 7)), k = L or token index
-    uint8_t* s_hi = smem + kOffSH + j0 * 128;                       // K chunk (L >> 6): [S_hi rows 0-31 | S_lo rows 0-31]
-    uint8_t* s_lo = s_hi + 4096;
-    const uint32_t k_off_s = (uint32_t)((L >> 6) * 8192 + ((L & 7) << 1));
-    const int kc_s = (L & 63) >> 3;
-    auto write_s_tiles = [&]() {
-#pragma unroll
-      for (int jj = 0; jj < kHC; ++jj) {
-        unsigned short hi, lo;
-        split_bf16(s[jj], hi, lo);
-        const uint32_t off = k_off_s + jj * 128 + ((kc_s ^ (jj & 7)) << 4);
-        *reinterpret_cast<unsigned short*>(s_hi + off) = hi;
-        *reinterpret_cast<unsigned short*>(s_lo + off) = lo;
-      }
-    };
-    write_s_tiles();
-    fence_proxy_async_smem();
-    mbar_arrive(s_ready);
-    const int i = L & 63;                              // token row (IT for L < 64, VP for L >= 64)
-    const int kc_v = i >> 3;
-    const uint32_t k_off_v = (uint32_t)(j0 * 128 + ((i & 7) << 1));
-    for (int c = 0; c < n_chunks; ++c) {
-      const int st = c & 1;
-      const uint32_t ph = (uint32_t)(c >> 1) & 1u, cp = (uint32_t)c & 1u;
-      const uint8_t* sb = smem + st * kStageBytes;
-      const float* sg = reinterpret_cast<const float*>(sb + kOffG);
-      const float* svc = reinterpret_cast<const float*>(sb + kOffVC);
-      mbar_wait(&full[st], ph);
-      const float g_last = sg[kTC - 1], g_i = sg[i];
-      const float d_last = expf(g_last);
-      float it[kHC];
-#pragma unroll
-      for (int jj = 0; jj < kHC; ++jj) it[jj] = 0.f;
-      mbar_wait(g1_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 4);
-      float* xv = reinterpret_cast<float*>(smem + kOffX);            // parked v: fp32 [64 tokens][36]
-      if (L >= 64) {                           // VP rows: v = vcorr - VP for this thread's 16 columns, parked as fp32
-        uint32_t a[16], a2[16], b[16];
-        tmem_ld16(lane_addr + kColD1, a);
-        tmem_ld16(lane_addr + kColD1 + kTSV, a2);
-        tmem_ld16(lane_addr + kColD1b, b);
-        tmem_ld_wait();
-        if (tid == 64) stamp(c, 10);
-#pragma unroll
-        for (int j4 = 0; j4 < kHC / 4; ++j4) {
-          const float4 vc4 = *reinterpret_cast<const float4*>(svc + i * kVcLd + j0 + 4 * j4);
-          float4 o;
-          o.x = vc4.x - ((__uint_as_float(a[4 * j4]) + __uint_as_float(a2[4 * j4])) + __uint_as_float(b[4 * j4]));
-          o.y = vc4.y - ((__uint_as_float(a[4 * j4 + 1]) + __uint_as_float(a2[4 * j4 + 1])) + __uint_as_float(b[4 * j4 + 1]));
-          o.z = vc4.z - ((__uint_as_float(a[4 * j4 + 2]) + __uint_as_float(a2[4 * j4 + 2])) + __uint_as_float(b[4 * j4 + 2]));
-          o.w = vc4.w - ((__uint_as_float(a[4 * j4 + 3]) + __uint_as_float(a2[4 * j4 + 3])) + __uint_as_float(b[4 * j4 + 3]));
-          *reinterpret_cast<float4*>(xv + i * kVcLd + j0 + 4 * j4) = o;
-        }
-      } else {                                 // IT rows
-        uint32_t a[16], a2[16];
-        tmem_ld16(lane_addr + kColD1, a);
-        tmem_ld16(lane_addr + kColD1 + kTSV, a2);
-        tmem_ld_wait();
-        const float eg = expf(g_i);
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) it[jj] = eg * (__uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
-      }
-      if (tid == 64) stamp(c, 11);
-      named_bar_sync(1, 256);
-      if (tid == 64) stamp(c, 12);
-      {                                        // every thread: token ti, columns cg*8 .. cg*8+7 of v -> hi/lo tiles of v and v.e^(g_last-g)
-        const int ti = tid & 63, cg = tid >> 6;
-        const float dec = expf(g_last - sg[ti]);
-        const float4 x0 = *reinterpret_cast<const float4*>(xv + ti * kVcLd + cg * 8);
-        const float4 x1 = *reinterpret_cast<const float4*>(xv + ti * kVcLd + cg * 8 + 4);
-        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        const uint32_t kb_off = (uint32_t)(cg * 8 * 128 + ((ti & 7) << 1));
-        const int kc_t = ti >> 3;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          unsigned short hi, lo, dhi, dlo;
-          split_bf16(xs[jj], hi, lo);
-          split_bf16(xs[jj] * dec, dhi, dlo);
-          const uint32_t off = kb_off + jj * 128 + ((kc_t ^ jj) << 4);
-          *reinterpret_cast<unsigned short*>(smem + kOffVH + off) = hi;
-          *reinterpret_cast<unsigned short*>(smem + kOffVL + off) = lo;
-          *reinterpret_cast<unsigned short*>(smem + kOffVDH + off) = dhi;
-          *reinterpret_cast<unsigned short*>(smem + kOffVDL + off) = dlo;
-        }
-      }
-      if (tid == 64) stamp(c, 13);
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      mbar_arrive(v_ready);
-      if (tid == 64) stamp(c, 5);
-      mbar_wait(g2_done, cp);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(c, 6);
-      {
-        uint32_t a[16], a2[16];
-        tmem_ld16(lane_addr + kColD2, a);
-        tmem_ld16(lane_addr + kColD2 + kTSV, a2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) s[jj] = fmaf(d_last, s[jj], __uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
-      }
-      if (c + 1 < n_chunks) {
-        write_s_tiles();
-        tc_fence_before_sync();
-        fence_proxy_async_smem();
-        mbar_arrive(s_ready);
-      }
-      if (tid == 0) stamp(c, 7);
-      if (L < 64) {                            // output rows (IT and intra.v share lanes 0-63)
-        mbar_wait(g3_done, cp);
-        tc_fence_after_sync();
-        if (tid == 0) stamp(c, 8);
-        uint32_t a[16], a2[16];
-        tmem_ld16(lane_addr + kColD3, a);
-        tmem_ld16(lane_addr + kColD3 + kTSV, a2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < kHC; ++jj) a[jj] = __float_as_uint(__uint_as_float(a[jj]) + __uint_as_float(a2[jj]));
-        const int t = c * kTC + i;
-        if (t < p.M) {
-          uint32_t o[kHC / 2];
-#pragma unroll
-          for (int j2 = 0; j2 < kHC / 2; ++j2) {
-            __nv_bfloat162 pr = __floats2bfloat162_rn(it[2 * j2] + __uint_as_float(a[2 * j2]), it[2 * j2 + 1] + __uint_as_float(a[2 * j2 + 1]));
-            o[j2] = *reinterpret_cast<uint32_t*>(&pr);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(p.core_out + (long long)t * vd + h * kTD + sl * kTSV + j0);
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-        tc_fence_before_sync();
-        if (tid == 0) stamp(c, 9);
-      }
-    }
-    {
-      float4* dst = reinterpret_cast<float4*>(p.state + ((long long)h * kTD + L) * kTD + sl * kTSV + j0);
-#pragma unroll
-      for (int j4 = 0; j4 < kHC / 4; ++j4) dst[j4] = make_float4(s[4 * j4], s[4 * j4 + 1], s[4 * j4 + 2], s[4 * j4 + 3]);
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 256);
-}
-
-
-
-// --------------------------------------------------------------------------------------------------------------------
-// Scan, sixth layout = the fifth one with the v tiles written TRANSPOSED: after the parking barrier thread (column n = lane, token
-// octet = warp) reads 8 tokens of one column, converts token PAIRS with one cvt.rn.bf16x2 each (the packed word is already the
-// K-contiguous memory order) and writes each of the four tiles with ONE 16-byte store: ~75 instructions per thread instead of ~170
-// (8 columns x (2 splits + 4 two-byte stores)).
-// (Fifth layout:) the fourth one with the v tiles written by ALL eight core warps: the VP threads (lanes 64-127, i.e. only
-// two of the four schedulers) park v as fp32 in shared memory, one 256-thread barrier, then every thread splits and stores 8 columns
-// of one token (the hi/lo split + four 2-byte stores per element are what the v phase costs: ~17 instructions per element).
-// (Fourth layout:) the third one with the hi and lo halves of every B operand STACKED ALONG N.  Measured motivation
-// (profiles/r02d_mma_issue_ubench.txt): a tcgen05.mma costs ~44 cycles to issue whether N is 32 or 64, so
-// A.[S_hi ; S_lo] as ONE N=64 instruction stream replaces two N=32 streams: G1 24 -> 16 MMAs, G2 8 -> 4, G3 12 -> 8; the
-// CUDA cores add the two 32-column halves when they read the accumulators back.
-// (Third layout:) the second one with EIGHT CUDA-core warps.  Measured motivation (profiles/r02f_gdn_timelines_fine.txt):
-// with four core warps there is one warp per scheduler, every dependent instruction pays its full latency, and the tile
-// writing phases ran at IPC ~0.3 (1170 + 500 cycles per chunk).  Warps w and w + 4 share TMEM lane quadrant w & 3 and take
-// 16 of the 32 columns each: the VP threads (lanes 64-127) split and store their own 16 columns of v (no parking, no
-// exchange), every thread owns 16 columns of one state row.  Warp 8 = TMA producer, warp 9 = MMA issuer.
-// --------------------------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(kT3Threads, 1)
-    gdn_scan_tc6_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
+    gdn_scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, GdnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* full = bars;           // [2]
@@ -1947,6 +466,16 @@ static_assert(64 * kPLdAT * 4 <= 64 * kPLdX * 4 && 64 * kPLdAT * 4 + 32 * kPLdP 
 constexpr int kPOffSc = kPOffXC + 64 * kPLdX * 4;    // gcum[64] | beta[64] | beta*e^gcum[64] | scan scratch[4]
 constexpr int kPOffBar = kPOffSc + 1024;
 constexpr int kPSmem = kPOffBar + 128;
+// version 2: outputs are staged in shared memory and leave by bulk copies (per-lane 16-byte global stores touch 32 different 128 B
+// lines per warp instruction: the output phase was 4 K cycles of LSU wavefronts).  vcorr + kcd staging alias A / T / P (dead by then).
+constexpr int kP2OffOutV = kPOffXB;                         // fp32 [4 slices][64][36] = 36,864 B, the global layout
+constexpr int kP2OffOutK = kP2OffOutV + 4 * kTC * kVcLd * 4;  // [hi c0 | hi c1 | lo c0 | lo c1] 32 KB, the global layout
+constexpr int kP2OffSc = kP2OffOutK + 32768;
+static_assert(kP2OffSc >= kPOffP + 32 * 36 * 4, "A / T / P stay inside the aliased region");
+constexpr int kP2OffBar = kP2OffSc + 1024;
+constexpr int kP2OffIntra = kP2OffBar + 128;                // intra [hi 8K | lo 8K]
+constexpr int kP2Smem = kP2OffIntra + 16384;
+static_assert(kP2Smem <= 227 * 1024 && kP2OffOutK % 16 == 0 && kP2OffIntra % 16 == 0, "smem");
 static_assert(kPSmem <= 227 * 1024, "smem");
 
 struct GdnPrepParams {
@@ -2355,7 +884,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
     gdn_prepare_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, GdnPrepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPOffBar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kP2OffBar);
   uint64_t* full = bars;           // [2]
   uint64_t* empty = bars + 2;      // [2]
   uint64_t* a_done = bars + 4;
@@ -2464,7 +993,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
     float* sP = reinterpret_cast<float*>(smem + kPOffP);
     float* sXB = reinterpret_cast<float*>(smem + kPOffXB);
     float* sXC = reinterpret_cast<float*>(smem + kPOffXC);
-    float* sg = reinterpret_cast<float*>(smem + kPOffSc);
+    float* sg = reinterpret_cast<float*>(smem + kP2OffSc);
     float* sbeta = sg + 64;
     float* secol = sg + 128;
     float* sscan = sg + 192;
@@ -2496,6 +1025,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         if (tid == 31) sscan[0] = gc;
       }
       named_bar_sync(2, 256);
+      if (tid == 0) bulk_wait_group_read0();          // the previous unit's output copies have read their staging buffers
       if (tid >= 32 && tid < 64) gc += sscan[0];
       if (tid < 64) {
         sg[i] = gc;
@@ -2525,7 +1055,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
           *reinterpret_cast<float4*>(sA + i * kPLdAT + part * 32 + 4 * j4) = make_float4(v[0], v[1], v[2], v[3]);
         }
       } else {                                // q k^T row i, columns [32 part, 32 part + 32)  ->  intra hi/lo images (global)
-        uint8_t* img = p.intra_img + hc * 16384 + i * 128;
+        uint8_t* img = smem + kP2OffIntra + i * 128;          // staged: [hi 8K | lo 8K], leaves by one bulk copy
         uint32_t a[32];
         tmem_ld32(lane_addr + kColA + part * 32, a);
         tmem_ld_wait();
@@ -2550,7 +1080,12 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         }
       }
       tc_fence_before_sync();
+      fence_proxy_async_smem();               // intra image: generic-proxy stores -> visible to the bulk copy
       named_bar_sync(2, 256);                 // A^T complete; D_A fully read
+      if (tid == 0) {
+        bulk_s2g(p.intra_img + hc * 16384, smem + kP2OffIntra, 16384);
+        bulk_commit_group();
+      }
       if (tid == 0) stamp(it, 6);
       // ---- T = (I - A)^-1 for the unit-lower-triangular 64x64 system, blocked 16 -> 32 -> 64, all 128 threads, fp32:
       //   level 0  the four diagonal blocks D_b = (I - A_bb)^-1 by forward substitution (thread = one column of one block)
@@ -2672,14 +1207,14 @@ __global__ void __launch_bounds__(kT3Threads, 1)
           uint32_t a[32];
           tmem_ld32(lane_addr + kColB + q * 32, a);
           tmem_ld_wait();
-          float* dst = p.vcorr + ((hc * (kTD / kTSV) + q) * kTC + i) * kVcLd;
+          float* dst = reinterpret_cast<float*>(smem + kP2OffOutV) + (q * kTC + i) * kVcLd;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4)
             *reinterpret_cast<float4*>(dst + 4 * j4) =
                 make_float4(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1]), __uint_as_float(a[4 * j4 + 2]), __uint_as_float(a[4 * j4 + 3]));
         }
       } else {
-        uint8_t* img = p.kcd_img + hc * 32768 + i * 128;
+        uint8_t* img = smem + kP2OffOutK + i * 128;
 #pragma unroll
         for (int qq = 0; qq < 2; ++qq) {
           const int q = part * 2 + qq;
@@ -2706,9 +1241,17 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         }
       }
       tc_fence_before_sync();
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);                 // staged outputs complete
+      if (tid == 0) {
+        bulk_s2g(p.vcorr + hc * (kTD / kTSV) * kTC * kVcLd, smem + kP2OffOutV, 4 * kTC * kVcLd * 4);
+        bulk_s2g(p.kcd_img + hc * 32768, smem + kP2OffOutK, 32768);
+        bulk_commit_group();
+      }
       if (tid == 0) stamp(it, 10);
     }
   }
+  if (tid == 0) bulk_wait_group0();           // every output copy has completed before the CTA (and its shared memory) goes away
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, 512);
@@ -2721,7 +1264,7 @@ cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc
   static PerDeviceOnce once;
   if (const int dev = once.pending(); dev >= 0) {
     cudaError_t e = cudaFuncSetAttribute(gdn_prepare_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_prepare_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_prepare_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Smem);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
@@ -2739,7 +1282,7 @@ cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc
   const char* pv = getenv("KB2_GDN_PREPARE_VERSION");        // 1 = four core warps + exchange, 2 = eight core warps (default)
   const int version = pv ? atoi(pv) : kDefaultPrepareVersion;
   if (version == 1) gdn_prepare_tc_kernel<<<n_units < num_sms ? n_units : num_sms, kTThreads, kPSmem, s>>>(tq, tk, tv, p);
-  else gdn_prepare_tc2_kernel<<<n_units < num_sms ? n_units : num_sms, kT3Threads, kPSmem, s>>>(tq, tk, tv, p);
+  else gdn_prepare_tc2_kernel<<<n_units < num_sms ? n_units : num_sms, kT3Threads, kP2Smem, s>>>(tq, tk, tv, p);
   return cudaGetLastError();
 }
 
@@ -2749,20 +1292,11 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
                                cudaStream_t s) {
   static PerDeviceOnce once;
   if (const int dev = once.pending(); dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_scan_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_scan_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    cudaError_t e = cudaFuncSetAttribute(gdn_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
-  // tuning knobs read per call (tests / profiling only): KB2_GDN_SCAN_SPLIT=0|1 picks the accumulator scheme,
-  // KB2_GDN_SCAN_TRACE=<device pointer> receives clock64 stamps of CTA (0,0)
-  const char* ev = getenv("KB2_GDN_SCAN_SPLIT");
-  const bool split = ev ? ev[0] == '1' : kDefaultSplit;
+  // tuning only: KB2_GDN_SCAN_TRACE=<device pointer> receives clock64 stamps of CTA (0,0) (scripts/gdn_scan_tune.py)
   const char* tv = getenv("KB2_GDN_SCAN_TRACE");
   long long* trace = tv ? reinterpret_cast<long long*>(strtoull(tv, nullptr, 0)) : nullptr;
   alignas(64) CUtensorMap tq, tk;
@@ -2771,15 +1305,7 @@ cudaError_t launch_gdn_scan_tc(const void* qn, const void* kn, const void* kcd_i
   e = make_tmap_bf16_rows(&tk, kn, M, (long long)nk * kTD, kTC);
   if (e != cudaSuccess) return e;
   GdnTcParams p{(const uint8_t*)kcd_img, (const uint8_t*)intra_img, vcorr, gcum, state, (__nv_bfloat16*)core_out, M, n_chunks, nv, nk, trace};
-  const char* vv = getenv("KB2_GDN_SCAN_LAYOUT");          // 1 = first layout, 2 = second layout (see above); unset -> kDefaultLayout
-  const int layout = vv ? atoi(vv) : kDefaultLayout;
-  if (layout == 6) gdn_scan_tc6_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
-  else if (layout == 5) gdn_scan_tc5_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
-  else if (layout == 4) gdn_scan_tc4_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
-  else if (layout == 3) gdn_scan_tc3_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
-  else if (layout == 2) gdn_scan_tc2_kernel<<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
-  else if (split) gdn_scan_tc_kernel<true><<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
-  else gdn_scan_tc_kernel<false><<<dim3(nv, kTD / kTSV), kTThreads, kTcSmem, s>>>(tq, tk, p);
+  gdn_scan_tc_kernel<<<dim3(nv, kTD / kTSV), kT3Threads, kTcSmem, s>>>(tq, tk, p);
   return cudaGetLastError();
 }
 

@@ -62,6 +62,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// 1-D bulk TMA store (smem -> global), bulk-group completion.  Writers make their generic-proxy smem stores visible to the async
+// proxy (fence_proxy_async_smem) and synchronise; ONE thread issues the copy + commit; the same thread waits `.read` before the
+// source buffer is reused.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ 2-D tiled TMA (global -> smem, hardware swizzle)
 // c0 = innermost (element) coordinate, c1 = row coordinate of the box origin.
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {

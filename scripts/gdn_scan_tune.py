@@ -1,8 +1,8 @@
 """Tuning harness for the tcgen05 GDN chunk scan (GPU): per-kernel times of one QCN-geometry GDN layer at 8192 tokens for
-the accumulator schemes (KB2_GDN_SCAN_SPLIT=0/1) and a clock64 timeline of one CTA (KB2_GDN_SCAN_TRACE).
-Slots: MMA thread 0 s_ready seen, 1 G1 issued, 2 v_ready seen, 3 G2+G3 issued; core thread 0: 4 g1_done seen, 5 v tiles written,
-6 g2_done seen, 7 S tiles written, 8 g3_done seen, 9 epilogue done; layout 2 only: 10 VP loaded (thread 64), 11 v parked, 12 after the
-128-thread barrier, 13 tiles stored, 14 after fence.proxy.async, 15 state row updated."""
+a clock64 timeline of one CTA (KB2_GDN_SCAN_TRACE) and of the chunk-prepare kernels (KB2_GDN_PREPARE_TRACE).
+Scan slots: MMA warp 0 s_ready seen, 1 G1 issued, 2 v_ready seen, 3 G2+G3 issued; core thread 0: 4 g1_done seen, 6 g2_done seen,
+7 S tiles written, 8 g3_done seen, 9 epilogue done; thread 64 (a VP row): 10 accumulators loaded, 11 v parked, 12 after the
+256-thread barrier, 13 v tiles stored, 5 v_ready arrive done."""
 import os
 import sys
 import types
@@ -24,40 +24,32 @@ cfg = types.SimpleNamespace(hidden_size=H, linear_num_key_heads=nk, linear_num_v
                             linear_value_head_dim=dv, linear_conv_kernel_dim=K, rms_norm_eps=1e-6)
 lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
 x = torch.randn(M, H).to(bf).cuda()
-outs = {}
-for split in ("5", "6"):                              # operand / warp layouts of the tcgen05 scan (gdn_tc.cu)
-    os.environ["KB2_GDN_SCAN_SPLIT"] = "0"
-    os.environ["KB2_GDN_SCAN_LAYOUT"] = split
-    for _ in range(3):
-        lay.reset_state()
-        lay.forward(x)
-    capi.kernel_profile(True)
-    for _ in range(5):
-        lay.reset_state()
-        y = lay.forward(x)
-    prof = capi.kernel_profile_collect()
-    capi.kernel_profile(False)
-    outs[split] = y.float()
-    print(f"layout={split}: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]) if n.startswith("gdn")))
-    trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
-    os.environ["KB2_GDN_SCAN_TRACE"] = str(trace.data_ptr())
+for _ in range(3):
     lay.reset_state()
     lay.forward(x)
-    torch.cuda.synchronize()
-    del os.environ["KB2_GDN_SCAN_TRACE"]
-    t = trace.cpu().view(8, 16)
-    base = t[:, 0:1]
-    print("  timeline (cycles since the MMA thread saw s_ready), chunks 8..15:")
-    for r in (t - base).tolist():
-        print("   ", r)
-    print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
-print("max |layout5 - layout6| / max:", ((outs["5"] - outs["6"]).abs().max() / outs["5"].abs().max()).item())
-os.environ.pop("KB2_GDN_SCAN_LAYOUT", None)
+capi.kernel_profile(True)
+for _ in range(5):
+    lay.reset_state()
+    y = lay.forward(x)
+prof = capi.kernel_profile_collect()
+capi.kernel_profile(False)
+print("GDN layer: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]) if n.startswith("gdn")))
+trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")
+os.environ["KB2_GDN_SCAN_TRACE"] = str(trace.data_ptr())
+lay.reset_state()
+lay.forward(x)
+torch.cuda.synchronize()
+del os.environ["KB2_GDN_SCAN_TRACE"]
+t = trace.cpu().view(8, 16)
+base = t[:, 0:1]
+print("  scan timeline (cycles since the MMA thread saw s_ready), chunks 8..15:")
+for r in (t - base).tolist():
+    print("   ", r[:14])
+print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
 
 # ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,
 # 3 MMA-B/C issued; core thread 0: 4 gates scanned, 5 k.k^T seen, 6 A^T built, 7 T solved, 8 images written, 9 vcorr/kcd products seen,
 # 10 outputs stored)
-os.environ.pop("KB2_GDN_SCAN_SPLIT", None)
 for mode, version in (("1", "1"), ("0", "1"), ("0", "2")):
     os.environ["KB2_GDN_PREPARE_MMA_SYNC"] = mode
     os.environ["KB2_GDN_PREPARE_VERSION"] = version

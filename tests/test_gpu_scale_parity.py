@@ -220,9 +220,8 @@ def test_router_mismatches_are_near_ties_at_benchmark_size(E, k, H):
 
 # ------------------------------------------------------------------------------------------------ tcgen05 scan vs mma.sync scan
 
-@pytest.mark.parametrize("layout", ["1", "2", "3", "4", "5", "6"])
-@pytest.mark.parametrize("M", [200, 1024])
-def test_gdn_tcgen05_scan_matches_the_mma_sync_scan(M, layout, monkeypatch):
+@pytest.mark.parametrize("M", [200, 1024, 3000])
+def test_gdn_tcgen05_scan_matches_the_mma_sync_scan(M, monkeypatch):
     """Same layer, same inputs, two state carries: the tcgen05 chunk scan (BF16 hi/lo pairs, fp32 accumulate) against the
     3xTF32 mma.sync scan kept for other head sizes.  Both are fp32-grade: the carried state must agree to 1e-4 relative,
     the BF16 outputs to one BF16 ulp of the output maximum's binade (2^-7 relative; rare rounding flips)."""
@@ -239,7 +238,6 @@ def test_gdn_tcgen05_scan_matches_the_mma_sync_scan(M, layout, monkeypatch):
                                 linear_value_head_dim=dv, linear_conv_kernel_dim=K, rms_norm_eps=1e-6)
     x1, x2 = torch.randn(M, H).to(bf).cuda(), torch.randn(M // 2 + 3, H).to(bf).cuda()
     res = {}
-    monkeypatch.setenv("KB2_GDN_SCAN_LAYOUT", layout)       # both operand layouts of the tcgen05 scan (gdn_tc.cu)
     for mode in ("1", "0"):
         monkeypatch.setenv("KB2_GDN_LEGACY", mode)
         lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
