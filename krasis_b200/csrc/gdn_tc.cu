@@ -1025,7 +1025,9 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         if (tid == 31) sscan[0] = gc;
       }
       named_bar_sync(2, 256);
-      if (tid == 0) bulk_wait_group_read0();          // the previous unit's output copies have read their staging buffers
+      // bulk groups of this thread, oldest first: intra(u-1), vcorr(u-1), kcd(u-1).  The A matrix and the intra staging written next
+      // alias / reuse only the first two; the kcd copy may still be draining (it is waited for before T is zeroed)
+      if (tid == 0) bulk_wait_group_read1();
       if (tid >= 32 && tid < 64) gc += sscan[0];
       if (tid < 64) {
         sg[i] = gc;
@@ -1085,7 +1087,9 @@ __global__ void __launch_bounds__(kT3Threads, 1)
       if (tid == 0) {
         bulk_s2g(p.intra_img + hc * 16384, smem + kP2OffIntra, 16384);
         bulk_commit_group();
+        bulk_wait_group_read1();              // everything older than this intra copy (i.e. kcd(u-1)) has left its staging buffer
       }
+      named_bar_sync(2, 256);                 // ... which T / P alias
       if (tid == 0) stamp(it, 6);
       // ---- T = (I - A)^-1 for the unit-lower-triangular 64x64 system, blocked 16 -> 32 -> 64, all 128 threads, fp32:
       //   level 0  the four diagonal blocks D_b = (I - A_bb)^-1 by forward substitution (thread = one column of one block)
@@ -1213,6 +1217,12 @@ __global__ void __launch_bounds__(kT3Threads, 1)
             *reinterpret_cast<float4*>(dst + 4 * j4) =
                 make_float4(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1]), __uint_as_float(a[4 * j4 + 2]), __uint_as_float(a[4 * j4 + 3]));
         }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);                 // the four vcorr warps (0, 1, 4, 5): their half leaves without waiting for the kcd splits
+        if (tid == 0) {
+          bulk_s2g(p.vcorr + hc * (kTD / kTSV) * kTC * kVcLd, smem + kP2OffOutV, 4 * kTC * kVcLd * 4);
+          bulk_commit_group();
+        }
       } else {
         uint8_t* img = smem + kP2OffOutK + i * 128;
 #pragma unroll
@@ -1244,7 +1254,6 @@ __global__ void __launch_bounds__(kT3Threads, 1)
       fence_proxy_async_smem();
       named_bar_sync(2, 256);                 // staged outputs complete
       if (tid == 0) {
-        bulk_s2g(p.vcorr + hc * (kTD / kTSV) * kTC * kVcLd, smem + kP2OffOutV, 4 * kTC * kVcLd * 4);
         bulk_s2g(p.kcd_img + hc * 32768, smem + kP2OffOutK, 32768);
         bulk_commit_group();
       }
