@@ -252,10 +252,20 @@ __global__ void __launch_bounds__(256) gdn_prep_vec_kernel(GdnDims d, const __nv
   }
   __nv_bfloat16* dst = is_q ? qn + (long long)u * d.dk : (is_k ? kn + (long long)(u - d.nk) * d.dk : vc + (long long)(u - 2 * d.nk) * d.dv);
   const int dst_ld = (is_q || is_k) ? kd : vd;
-  uint2 nxt = *reinterpret_cast<const uint2*>(qkvz + (long long)t_begin * ld + col0);
-  for (int t = t_begin; t < t_end; ++t) {
-    const uint2 cur = nxt;
-    if (t + 1 < t_end) nxt = *reinterpret_cast<const uint2*>(qkvz + (long long)(t + 1) * ld + col0);      // next row in flight
+  // rows are consumed strictly in order (the convolution history lives in registers), so the only memory-level parallelism a warp
+  // has is how far ahead it loads: four rows (1 KB per warp) in flight instead of one took this kernel off the latency bound
+  constexpr int kAhead = 4;
+  uint2 ring[kAhead];
+#pragma unroll
+  for (int j = 0; j < kAhead; ++j)
+    ring[j] = t_begin + j < t_end ? *reinterpret_cast<const uint2*>(qkvz + (long long)(t_begin + j) * ld + col0) : make_uint2(0u, 0u);
+  for (int t0 = t_begin; t0 < t_end; t0 += kAhead) {
+#pragma unroll
+   for (int jr = 0; jr < kAhead; ++jr) {
+    const int t = t0 + jr;
+    if (t >= t_end) break;                                   // warp-uniform
+    const uint2 cur = ring[jr];
+    if (t + kAhead < t_end) ring[jr] = *reinterpret_cast<const uint2*>(qkvz + (long long)(t + kAhead) * ld + col0);
     const float x[4] = {__uint_as_float(cur.x << 16), __uint_as_float(cur.x & 0xFFFF0000u), __uint_as_float(cur.y << 16),
                         __uint_as_float(cur.y & 0xFFFF0000u)};
     float sv[4];
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(256) gdn_prep_vec_kernel(GdnDims d, const __nv
     __nv_bfloat162 lo = __floats2bfloat162_rn(sv[0], sv[1]), hi = __floats2bfloat162_rn(sv[2], sv[3]);
     *reinterpret_cast<uint2*>(dst + (long long)t * dst_ld + lane * 4) =
         make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+   }
   }
 }
 
