@@ -345,6 +345,9 @@ KB2_API int kb2_comm_all_gather(kb2_comm* c, const void* send_dev, void* recv_de
 KB2_API int kb2_comm_reduce_scatter_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems_per_rank, void* stream);
 KB2_API int kb2_comm_all_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems, void* stream);
 KB2_API int kb2_comm_broadcast(kb2_comm* c, void* buf_dev, size_t bytes, int32_t root, void* stream);
+/* BF16 sum over ranks delivered to `root` only (recv_dev may be NULL elsewhere): one chunk of a pipelined reduce-scatter whose
+ * chunk j is rank j's token shard (krasis_b200/model.py: attention over chunk j+1 runs while chunk j's partial outputs are reduced). */
+KB2_API int kb2_comm_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems, int32_t root, void* stream);
 
 /* Per-kernel device timing with CUDA events recorded on the launching stream (the reference's
  * KRASIS_LAYER_TIMING / EP breakdown, python/krasis/model.py:2839-2860).  kb2_profile_collect synchronises the

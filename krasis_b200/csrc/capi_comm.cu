@@ -33,6 +33,7 @@ struct NcclApi {
   int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -53,10 +54,11 @@ NcclApi& nccl() {
     KB2_SYM(ReduceScatter, "ncclReduceScatter");
     KB2_SYM(AllReduce, "ncclAllReduce");
     KB2_SYM(Broadcast, "ncclBroadcast");
+    KB2_SYM(Reduce, "ncclReduce");
     KB2_SYM(GetErrorString, "ncclGetErrorString");
 #undef KB2_SYM
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.ReduceScatter && api.AllReduce &&
-             api.Broadcast && api.GetErrorString;
+             api.Broadcast && api.Reduce && api.GetErrorString;
   });
   return api;
 }
@@ -136,6 +138,14 @@ KB2_API int kb2_comm_all_reduce_bf16(kb2_comm* c, const void* send_dev, void* re
 KB2_API int kb2_comm_broadcast(kb2_comm* c, void* buf_dev, size_t bytes, int32_t root, void* stream) {
   if (!c || !buf_dev) return failf(KB2_ERR_VALUE, "null argument");
   NCCL_TRY(nccl().Broadcast(buf_dev, buf_dev, bytes, kNcclUint8, root, c->comm, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_comm_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems, int32_t root, void* stream) {
+  if (!c || !send_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (root < 0 || root >= c->nranks) return failf(KB2_ERR_VALUE, "reduce: root %d outside [0, %d)", root, c->nranks);
+  if (c->rank == root && !recv_dev) return failf(KB2_ERR_VALUE, "reduce: the root needs a receive buffer");
+  NCCL_TRY(nccl().Reduce(send_dev, recv_dev, elems, kNcclBfloat16, kNcclSum, root, c->comm, (cudaStream_t)stream));
   return KB2_OK;
 }
 

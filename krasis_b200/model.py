@@ -406,6 +406,24 @@ class DenseMLP:
         return L.int8_linear(act, *self.down)
 
 
+class _ChunkKVState:
+    """View of a SequenceKVState `offset` tokens ahead: what a layer sees while it processes a later token chunk of the same prefill
+    call (the real state is advanced once per model forward, after the last layer)."""
+
+    def __init__(self, state, offset: int):
+        self._st, self._off = state, offset
+
+    @property
+    def seq_len(self):
+        return self._st.seq_len + self._off
+
+    def ensure_capacity(self, num_new_tokens: int):
+        self._st.ensure_capacity(self._off + num_new_tokens)
+
+    def kv_indices(self, device):
+        return self._st.kv_indices(device)
+
+
 class KrasisModel:
     """Prefill forward of a MoE transformer: synthetic weights of the real architecture (`KrasisModel(cfg, ...)`) or a real
     checkpoint (`KrasisModel.from_pretrained(model_dir, ...)`)."""
@@ -527,6 +545,9 @@ class KrasisModel:
             self.layers.append(lay)
         self._ones = self._zero_ids = None
         self._side_stream = None
+        # chunk-pipelined attention collectives under token sharding (KB2_PIPELINE_ATTENTION=0 falls back to one all-gather + one
+        # reduce-scatter per layer)
+        self.pipeline_attention = os.environ.get("KB2_PIPELINE_ATTENTION", "1") != "0"
 
     # ------------------------------------------------------------------------------------------- real checkpoints
     @classmethod
@@ -614,6 +635,48 @@ class KrasisModel:
         with tm("routed_experts"):
             return self.engine.finish(routed, shared)                                        # bf16(rsf * routed) + shared
 
+    def _attention_pipelined(self, lay, i, hidden, positions, st, M):
+        """Head-parallel attention with the all-gather and the reduce-scatter cut into one chunk per rank (chunk j = rank j's token
+        shard) and pipelined against the attention itself: broadcast_j brings rank j's normed rows to everyone, every rank runs its
+        heads over chunk j as one step of a chunked prefill (conv / recurrent state and the KV cache carry over exactly like two
+        prefill calls of the reference), reduce_j sums the partial o_proj outputs on rank j while chunk j + 1 is being computed.
+        Exposed communication: the first broadcast and the last reduce, 1/R of each collective."""
+        R, rows, tm = self.num_ranks, M // self.num_ranks, self._timer
+        main = torch.cuda.current_stream(self.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+        side = self._side_stream
+        full = torch.empty((M, hidden.shape[1]), dtype=hidden.dtype, device=hidden.device)
+        full[self.rank * rows:(self.rank + 1) * rows].copy_(hidden)
+        ev_in = [torch.cuda.Event() for _ in range(R)]
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for j in range(R):
+                self.comm.broadcast(full[j * rows:(j + 1) * rows], root=j)
+                ev_in[j].record(side)
+        full.record_stream(side)
+        own = torch.empty((rows, hidden.shape[1]), dtype=hidden.dtype, device=hidden.device)
+        own.record_stream(side)
+        name = "gdn_attention" if lay.layer_type == "linear_attention" else ("mla_attention" if lay.layer_type == "mla" else "gqa_attention")
+        for j in range(R):
+            main.wait_event(ev_in[j])
+            x = full[j * rows:(j + 1) * rows]
+            with tm(name):
+                if lay.layer_type == "linear_attention":
+                    part = lay.attention.forward(x, is_decode=False)
+                else:
+                    part = lay.attention.forward(x, positions[j * rows:(j + 1) * rows], self.kv_cache, _ChunkKVState(st, j * rows),
+                                                 self._kv_layer_offsets[i], num_new_tokens=rows)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            part.record_stream(side)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                self.comm.reduce_rows(part, root=j, out=own if j == self.rank else None)
+        with tm("attention_reduce_scatter"):
+            main.wait_stream(side)
+        return own
+
     def forward(self, token_ids: torch.Tensor, positions: torch.Tensor, seq_states: List[SequenceKVState],
                 return_all_logits: bool = False) -> torch.Tensor:
         """model.py:2167: token_ids [M] int64/int32 on the device, positions [M]; returns logits [1, V] (last token)
@@ -637,18 +700,21 @@ class KrasisModel:
                     hidden = L.rmsnorm(hidden, lay.input_norm, eps)
                 else:
                     L.fused_add_rmsnorm(hidden, residual, lay.input_norm, eps)
-            if R > 1:
-                with tm("attention_all_gather"):
-                    hidden = self.comm.all_gather_rows(hidden)             # head-parallel attention sees every token
-            if lay.layer_type == "linear_attention":
-                with tm("gdn_attention"):
-                    attn = lay.attention.forward(hidden, is_decode=False)
+            if R > 1 and self.pipeline_attention:
+                attn = self._attention_pipelined(lay, i, hidden, positions, st, M)
             else:
-                with tm("mla_attention" if lay.layer_type == "mla" else "gqa_attention"):
-                    attn = lay.attention.forward(hidden, positions, self.kv_cache, st, self._kv_layer_offsets[i], num_new_tokens=M)
-            if R > 1:
-                with tm("attention_reduce_scatter"):
-                    attn = self.comm.reduce_scatter_rows(attn)             # sum of the partial o_proj outputs, this rank's rows
+                if R > 1:
+                    with tm("attention_all_gather"):
+                        hidden = self.comm.all_gather_rows(hidden)             # head-parallel attention sees every token
+                if lay.layer_type == "linear_attention":
+                    with tm("gdn_attention"):
+                        attn = lay.attention.forward(hidden, is_decode=False)
+                else:
+                    with tm("mla_attention" if lay.layer_type == "mla" else "gqa_attention"):
+                        attn = lay.attention.forward(hidden, positions, self.kv_cache, st, self._kv_layer_offsets[i], num_new_tokens=M)
+                if R > 1:
+                    with tm("attention_reduce_scatter"):
+                        attn = self.comm.reduce_scatter_rows(attn)             # sum of the partial o_proj outputs, this rank's rows
             with tm("norms"):
                 L.fused_add_rmsnorm(attn, residual, lay.post_attn_norm, eps)   # layer.py:305-309
             if lay.dense is not None:

@@ -123,6 +123,16 @@ class Communicator:
         capi.check(self._lib.kb2_comm_all_reduce_bf16(self._h, x.data_ptr(), x.data_ptr(), x.numel(), self._stream()))
         return x
 
+    def reduce_rows(self, x: torch.Tensor, root: int, out: torch.Tensor = None) -> torch.Tensor:
+        """BF16 sum over ranks of `x`, delivered to `root` (returns `out` there, None elsewhere)."""
+        if x.dtype != torch.bfloat16 or not x.is_contiguous():
+            raise ValueError("reduce_rows: contiguous bf16 tensor expected")
+        if self.rank == root and out is None:
+            out = torch.empty_like(x)
+        capi.check(self._lib.kb2_comm_reduce_bf16(self._h, x.data_ptr(), out.data_ptr() if self.rank == root else None, x.numel(), root,
+                                                  self._stream()))
+        return out if self.rank == root else None
+
     def broadcast(self, x: torch.Tensor, root: int) -> torch.Tensor:
         capi.check(self._lib.kb2_comm_broadcast(self._h, x.data_ptr(), x.numel() * x.element_size(), root, self._stream()))
         return x
