@@ -32,7 +32,9 @@ struct GqaDims {
 __device__ __forceinline__ float bf16r_(float x) { return bf16_round_rn(x); }
 
 // ------------------------------------------------------------------------------------------------
-// prep: one CTA per token, one warp per head (q heads then k heads then v heads)
+// prep: one CTA per token, one warp per head (q heads then k heads then v heads).  The BF16 cos / sin of the token's position are
+// computed once per CTA (powf + cosf + sinf per (head, pair) was most of this kernel: 20 heads recomputed the same 32 angles at QCN
+// geometry, 72 heads the same 64 at Qwen3-235B); rows move as BF16 pairs / FP8 pairs.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gqa_prep_kernel(GqaDims g, const __nv_bfloat16* __restrict__ q_raw,   // [M][nh*d*(1+gated)]
                                                        const __nv_bfloat16* __restrict__ k_raw,             // [M][nkv*d]
@@ -46,23 +48,37 @@ __global__ void __launch_bounds__(256) gqa_prep_kernel(GqaDims g, const __nv_bfl
   const int d = g.d, d2 = g.rotary_dim / 2;
   const int pos = positions[t];
   const long long slot = ((long long)kv_indices[pos >> 4] * 16 + (pos & 15)) * g.nkv;
-  extern __shared__ float sx[];              // [nw][d]
+  extern __shared__ float sx[];              // [nw][d] rows | cos[d2] | sin[d2]
   float* x = sx + warp * d;
+  float* s_cos = sx + nw * d;
+  float* s_sin = s_cos + d2;
+  for (int i = threadIdx.x; i < d2; i += blockDim.x) {
+    const float freq = 1.0f / powf(g.theta, (float)(2 * i) / (float)g.rotary_dim);
+    const float ang = (float)pos * freq;
+    s_cos[i] = bf16r_(cosf(ang));
+    s_sin[i] = bf16r_(sinf(ang));
+  }
+  __syncthreads();
   for (int hh = warp; hh < g.nh + 2 * g.nkv; hh += nw) {
     const bool is_q = hh < g.nh, is_k = !is_q && hh < g.nh + g.nkv;
     const int h = is_q ? hh : (is_k ? hh - g.nh : hh - g.nh - g.nkv);
     const __nv_bfloat16* src = is_q ? q_raw + (long long)t * g.nh * d * (1 + g.gated) + (long long)h * d * (1 + g.gated)
                                     : (is_k ? k_raw : v_raw) + (long long)t * g.nkv * d + (long long)h * d;
     float ss = 0.f;
-    for (int i = lane; i < d; i += 32) {
-      const float v = __bfloat162float(src[i]);
-      x[i] = v;
-      ss += v * v;
+    for (int i = 2 * lane; i < d; i += 64) {                        // d is even, rows are 4-byte aligned (d % 8 == 0)
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + i));
+      x[i] = v.x;
+      x[i + 1] = v.y;
+      ss += v.x * v.x;
+      ss += v.y * v.y;
     }
     if (!is_q && !is_k) {                    // V: plain cast to FP8
       __syncwarp();
-      for (int i = lane; i < d; i += 32)
-        v_cache[(slot + h) * d + i] = (uint8_t)__nv_cvt_float_to_fp8(x[i], __NV_SATFINITE, __NV_E4M3);
+      for (int i = 2 * lane; i < d; i += 64) {
+        const uint8_t b0 = (uint8_t)__nv_cvt_float_to_fp8(x[i], __NV_SATFINITE, __NV_E4M3);
+        const uint8_t b1 = (uint8_t)__nv_cvt_float_to_fp8(x[i + 1], __NV_SATFINITE, __NV_E4M3);
+        *reinterpret_cast<uchar2*>(v_cache + (slot + h) * d + i) = make_uchar2(b0, b1);
+      }
       __syncwarp();
       continue;
     }
@@ -77,9 +93,7 @@ __global__ void __launch_bounds__(256) gqa_prep_kernel(GqaDims g, const __nv_bfl
     __syncwarp();
     // RoPE on the first rotary_dim dims: (x1, x2) = (x[i], x[i + d2]); BF16 tables, every product / sum rounded to BF16
     for (int i = lane; i < d2; i += 32) {
-      const float freq = 1.0f / powf(g.theta, (float)(2 * i) / (float)g.rotary_dim);
-      const float ang = (float)pos * freq;
-      const float c = bf16r_(cosf(ang)), s = bf16r_(sinf(ang));
+      const float c = s_cos[i], s = s_sin[i];
       const float x1 = x[i], x2 = x[i + d2];
       const float r1 = bf16r_(bf16r_(x1 * c) - bf16r_(x2 * s));
       const float r2 = bf16r_(bf16r_(x2 * c) + bf16r_(x1 * s));
@@ -88,10 +102,14 @@ __global__ void __launch_bounds__(256) gqa_prep_kernel(GqaDims g, const __nv_bfl
     }
     __syncwarp();
     if (is_q) {
-      for (int i = lane; i < d; i += 32) q_out[(long long)t * g.nh * d + (long long)h * d + i] = __float2bfloat16_rn(x[i]);
+      __nv_bfloat16* dst = q_out + (long long)t * g.nh * d + (long long)h * d;
+      for (int i = 2 * lane; i < d; i += 64) *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(x[i], x[i + 1]);
     } else {
-      for (int i = lane; i < d; i += 32)
-        k_cache[(slot + h) * d + i] = (uint8_t)__nv_cvt_float_to_fp8(x[i], __NV_SATFINITE, __NV_E4M3);
+      for (int i = 2 * lane; i < d; i += 64) {
+        const uint8_t b0 = (uint8_t)__nv_cvt_float_to_fp8(x[i], __NV_SATFINITE, __NV_E4M3);
+        const uint8_t b1 = (uint8_t)__nv_cvt_float_to_fp8(x[i + 1], __NV_SATFINITE, __NV_E4M3);
+        *reinterpret_cast<uchar2*>(k_cache + (slot + h) * d + i) = make_uchar2(b0, b1);
+      }
     }
     __syncwarp();
   }
@@ -515,7 +533,7 @@ cudaError_t launch_gqa_core(const GqaDims& g, const void* q_raw, const void* k_r
     once.mark(dev);
   }
   { KernelSpan ks(K_GQA_PREP, s);
-  gqa_prep_kernel<<<M, 256, 8 * g.d * sizeof(float), s>>>(g, (const __nv_bfloat16*)q_raw, (const __nv_bfloat16*)k_raw,
+  gqa_prep_kernel<<<M, 256, (8 * g.d + g.rotary_dim) * sizeof(float), s>>>(g, (const __nv_bfloat16*)q_raw, (const __nv_bfloat16*)k_raw,
                                                           (const __nv_bfloat16*)v_raw, q_norm, k_norm, positions,
                                                           kv_indices, (__nv_bfloat16*)q_rot, (uint8_t*)k_cache,
                                                           (uint8_t*)v_cache, M); }

@@ -545,9 +545,11 @@ class KrasisModel:
             self.layers.append(lay)
         self._ones = self._zero_ids = None
         self._side_stream = None
-        # chunk-pipelined attention collectives under token sharding (KB2_PIPELINE_ATTENTION=0 falls back to one all-gather + one
-        # reduce-scatter per layer)
-        self.pipeline_attention = os.environ.get("KB2_PIPELINE_ATTENTION", "1") != "0"
+        # chunk-pipelined attention collectives under token sharding: OFF by default.  Measured on 2 GPUs (profiles/r02p_*): 70.0 ms per
+        # step against 65.1 ms with one all-gather + one reduce-scatter per layer — the NCCL kernels that now run next to the attention
+        # hold SMs that the persistent one-CTA-per-SM GEMM / scan kernels are sized for (Gated DeltaNet 24.8 -> 32.0 ms), which costs
+        # more than the 2 x 1 ms of hidden communication.  KB2_PIPELINE_ATTENTION=1 enables it.
+        self.pipeline_attention = os.environ.get("KB2_PIPELINE_ATTENTION", "0") == "1"
 
     # ------------------------------------------------------------------------------------------- real checkpoints
     @classmethod
