@@ -223,6 +223,18 @@ KB2_API int kb2_quantize_rows_int8(const void* x_dev, void* q_dev, float* scale_
 KB2_API int kb2_int8_linear(const void* x_dev, const void* wq_dev, const void* w_scale_bf16_dev, void* out_dev, void* xq_scratch_dev,
                             float* xs_scratch_dev, int32_t M, int32_t N, int32_t K, int32_t device, void* stream);
 /* flashinfer.activation.silu_and_mul (layer.py:512): x [rows][2N] -> out [rows][N] bf16. */
+/* Fused forms of the shared expert's W8A8 chain (layer.py:508-524 + weight_loader.py:46-99), bit-identical to the unfused calls:
+ *   kb2_rmsnorm_q8            kb2_rmsnorm that also emits the INT8 row quantisation (q [M][H] int8, q_scale [M] f32) of its output
+ *   kb2_int8_linear_q8        kb2_int8_linear on an already quantised activation
+ *   kb2_silu_mul_int8_linear  out = int8_linear(silu(gate) * up, W): the activation is quantised straight from the [M][2K] gate|up rows
+ *                             (act_scratch [M][K] bf16 is only touched for K outside {256, 512, 1024, 2048}) */
+KB2_API int kb2_rmsnorm_q8(void* x_dev, void* residual_dev, const float* weight_dev, void* out_dev, void* q_dev, float* q_scale_dev,
+                           int32_t M, int32_t H, float eps, int32_t device, void* stream);
+KB2_API int kb2_int8_linear_q8(const void* xq_dev, const float* xs_dev, const void* wq_dev, const void* w_scale_bf16_dev, void* out_dev,
+                               int32_t M, int32_t N, int32_t K, int32_t device, void* stream);
+KB2_API int kb2_silu_mul_int8_linear(const void* gate_up_dev, const void* wq_dev, const void* w_scale_bf16_dev, void* out_dev,
+                                     void* act_scratch_dev, void* xq_scratch_dev, float* xs_scratch_dev, int32_t M, int32_t N, int32_t K,
+                                     int32_t device, void* stream);
 KB2_API int kb2_silu_and_mul(const void* x_dev, void* out_dev, int32_t rows, int32_t N, int32_t device, void* stream);
 /* Qwen3-Next shared-expert gate (layer.py:518-522): y[m][:] *= sigmoid(hidden[m] . gate_w), y [M][N], gate_w [H] bf16. */
 KB2_API int kb2_sigmoid_gate_mul(const void* hidden_dev, const void* gate_w_dev, void* y_dev, int32_t M, int32_t H, int32_t N,

@@ -87,6 +87,9 @@ SIGNATURES = {
     "kb2_quantize_rows_int8": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
     "kb2_int8_linear": (C.c_int, [C.c_void_p] * 6 + [C.c_int32] * 4 + [C.c_void_p]),
     "kb2_silu_and_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "kb2_rmsnorm_q8": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "kb2_int8_linear_q8": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
+    "kb2_silu_mul_int8_linear": (C.c_int, [C.c_void_p] * 7 + [C.c_int32] * 4 + [C.c_void_p]),
     "kb2_sigmoid_gate_mul": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]),
     "kb2_add_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "kb2_gdn_create": (C.c_int, [C.POINTER(GdnConfig), C.POINTER(C.c_void_p)]),

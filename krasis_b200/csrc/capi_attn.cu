@@ -24,6 +24,10 @@ cudaError_t launch_dense_gemm_i8(const void* xq, const float* x_scale, const voi
                                  int M, int N, int K, long long ldo, int num_sms, cudaStream_t s);
 cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, int M, int H, float eps, cudaStream_t s);
 cudaError_t launch_quant_rows_int8(const void* x, void* q, float* scale_f32, void* scale_bf16, int rows, int K, cudaStream_t s);
+bool rmsnorm_q8_supported(int H);
+cudaError_t launch_rmsnorm_q8(void* x, void* residual, const float* w, void* out, void* q, float* q_scale, int M, int H, float eps, cudaStream_t s);
+bool silu_mul_quant_supported(int N);
+cudaError_t launch_silu_mul_quant(const void* x, void* q, float* scale_f32, int rows, int N, cudaStream_t s);
 cudaError_t launch_silu_and_mul(const void* x, void* out, int rows, int N, cudaStream_t s);
 cudaError_t launch_sigmoid_gate_mul(const void* h, const void* w, void* y, int M, int H, int N, cudaStream_t s);
 cudaError_t launch_add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t s);
@@ -133,6 +137,48 @@ KB2_API int kb2_int8_linear(const void* x_dev, const void* wq_dev, const void* w
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(launch_quant_rows_int8(x_dev, xq_scratch_dev, xs_scratch_dev, nullptr, M, K, s));
+  CUDA_TRY(launch_dense_gemm_i8(xq_scratch_dev, xs_scratch_dev, wq_dev, w_scale_bf16_dev, out_dev, M, N, K, N, device_sms(device), s));
+  return KB2_OK;
+}
+
+KB2_API int kb2_rmsnorm_q8(void* x_dev, void* residual_dev, const float* weight_dev, void* out_dev, void* q_dev, float* q_scale_dev,
+                           int32_t M, int32_t H, float eps, int32_t device, void* stream) {
+  if (!x_dev || !weight_dev || !out_dev || !q_dev || !q_scale_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (M <= 0 || H <= 0 || H % 8) return failf(KB2_ERR_VALUE, "rmsnorm: need M > 0 and H %% 8 == 0");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rmsnorm_q8_supported(H)) {
+    CUDA_TRY(launch_rmsnorm_q8(x_dev, residual_dev, weight_dev, out_dev, q_dev, q_scale_dev, M, H, eps, s));
+  } else {                                   // same results, two passes
+    CUDA_TRY(launch_rmsnorm(x_dev, residual_dev, weight_dev, out_dev, M, H, eps, s));
+    CUDA_TRY(launch_quant_rows_int8(out_dev, q_dev, q_scale_dev, nullptr, M, H, s));
+  }
+  return KB2_OK;
+}
+
+KB2_API int kb2_int8_linear_q8(const void* xq_dev, const float* xs_dev, const void* wq_dev, const void* w_scale_bf16_dev, void* out_dev,
+                               int32_t M, int32_t N, int32_t K, int32_t device, void* stream) {
+  if (!xq_dev || !xs_dev || !wq_dev || !w_scale_bf16_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (M <= 0 || K % 128 || N % 16) return failf(KB2_ERR_VALUE, "int8_linear: need M > 0, K %% 128 == 0, N %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_dense_gemm_i8(xq_dev, xs_dev, wq_dev, w_scale_bf16_dev, out_dev, M, N, K, N, device_sms(device), (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+KB2_API int kb2_silu_mul_int8_linear(const void* gate_up_dev, const void* wq_dev, const void* w_scale_bf16_dev, void* out_dev,
+                                     void* act_scratch_dev, void* xq_scratch_dev, float* xs_scratch_dev, int32_t M, int32_t N, int32_t K,
+                                     int32_t device, void* stream) {
+  if (!gate_up_dev || !wq_dev || !w_scale_bf16_dev || !out_dev || !xq_scratch_dev || !xs_scratch_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (M <= 0 || K % 128 || N % 16) return failf(KB2_ERR_VALUE, "int8_linear: need M > 0, K %% 128 == 0, N %% 16 == 0 (M=%d N=%d K=%d)", M, N, K);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (silu_mul_quant_supported(K)) {
+    CUDA_TRY(launch_silu_mul_quant(gate_up_dev, xq_scratch_dev, xs_scratch_dev, M, K, s));
+  } else {                                   // same results through the BF16 activation
+    if (!act_scratch_dev) return failf(KB2_ERR_VALUE, "silu_mul_int8_linear: K=%d needs the BF16 activation scratch", K);
+    CUDA_TRY(launch_silu_and_mul(gate_up_dev, act_scratch_dev, M, K, s));
+    CUDA_TRY(launch_quant_rows_int8(act_scratch_dev, xq_scratch_dev, xs_scratch_dev, nullptr, M, K, s));
+  }
   CUDA_TRY(launch_dense_gemm_i8(xq_scratch_dev, xs_scratch_dev, wq_dev, w_scale_bf16_dev, out_dev, M, N, K, N, device_sms(device), s));
   return KB2_OK;
 }

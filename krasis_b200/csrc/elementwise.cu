@@ -35,10 +35,14 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 // one WARP per row, row kept in registers (H == 256 * VPL): no shared memory, no block barriers
-template <bool kAdd, int VPL>
+// kQuant: additionally emits the row-quantised INT8 copy of the OUTPUT row (the activation quantisation of int8_linear,
+// weight_loader.py:46-99: scale = max(|y|, 1e-10) / 127, q = clamp(round_half_even(y / scale))) — the row is already in registers,
+// so the shared expert's first W8A8 GEMM needs no separate quantisation pass over the normed activations.
+template <bool kAdd, int VPL, bool kQuant = false>
 __global__ void __launch_bounds__(256) rmsnorm_warp_kernel(__nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ residual,
                                                            const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                           int M, float eps) {
+                                                           int M, float eps, int8_t* __restrict__ q_out = nullptr,
+                                                           float* __restrict__ q_scale = nullptr) {
   constexpr int H = 256 * VPL;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -78,8 +82,33 @@ __global__ void __launch_bounds__(256) rmsnorm_warp_kernel(__nv_bfloat16* __rest
     uint4 o;
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(&o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) po[i] = __float2bfloat16_rn(f[j][i] * inv * ww[i]);
+    for (int i = 0; i < 8; ++i) {
+      po[i] = __float2bfloat16_rn(f[j][i] * inv * ww[i]);
+      if constexpr (kQuant) f[j][i] = __bfloat162float(po[i]);
+    }
     *reinterpret_cast<uint4*>(out + row * H + v * 8) = o;
+  }
+  if constexpr (kQuant) {
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, fabsf(f[j][i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float scale = fmaxf(mx, 1e-10f) / 127.0f;
+    if (lane == 0) q_scale[row] = scale;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      uint32_t o[2] = {0u, 0u};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float r = rintf(f[j][i] / scale);
+        const int qi = (int)fminf(fmaxf(r, -128.f), 127.f);
+        o[i >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (i & 3));
+      }
+      *reinterpret_cast<uint2*>(q_out + row * H + (lane + 32 * j) * 8) = make_uint2(o[0], o[1]);
+    }
   }
 }
 
@@ -184,6 +213,48 @@ __global__ void __launch_bounds__(256) silu_and_mul_kernel(const __nv_bfloat16* 
   *reinterpret_cast<uint4*>(out + r * N + v * 8) = o;
 }
 
+// act = bf16(silu(gate) * up) exactly as silu_and_mul_kernel, quantised per row exactly as quant_rows_int8_kernel, without writing the
+// BF16 activation: one warp per row, N == 256 * VPL, row kept in registers
+template <int VPL>
+__global__ void __launch_bounds__(256) silu_mul_quant_kernel(const __nv_bfloat16* __restrict__ x, int8_t* __restrict__ q,
+                                                             float* __restrict__ scale_f32, int rows) {
+  constexpr int N = 256 * VPL;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float f[VPL][8];
+  float mx = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int v = lane + 32 * j;
+    const uint4 g4 = *reinterpret_cast<const uint4*>(x + row * 2 * N + v * 8);
+    const uint4 u4 = *reinterpret_cast<const uint4*>(x + row * 2 * N + N + v * 8);
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&g4);
+    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(&u4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gv = __bfloat162float(g[i]);
+      f[j][i] = __bfloat162float(__float2bfloat16_rn(gv / (1.0f + __expf(-gv)) * __bfloat162float(u[i])));
+      mx = fmaxf(mx, fabsf(f[j][i]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float scale = fmaxf(mx, 1e-10f) / 127.0f;
+  if (lane == 0) scale_f32[row] = scale;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    uint32_t o[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r = rintf(f[j][i] / scale);
+      const int qi = (int)fminf(fmaxf(r, -128.f), 127.f);
+      o[i >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (i & 3));
+    }
+    *reinterpret_cast<uint2*>(q + row * N + (lane + 32 * j) * 8) = make_uint2(o[0], o[1]);
+  }
+}
+
 // y[m] *= bf16(sigmoid(bf16(dot(h[m], w)))) ; one warp per row, 16-byte vectors (H % 8 == 0, N % 8 == 0)
 __global__ void __launch_bounds__(256) sigmoid_gate_mul_kernel(const __nv_bfloat16* __restrict__ h,
                                                                const __nv_bfloat16* __restrict__ w,
@@ -247,6 +318,33 @@ cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, i
     rmsnorm_kernel<true><<<M, 256, H * sizeof(float), s>>>((__nv_bfloat16*)x, (__nv_bfloat16*)residual, w, (__nv_bfloat16*)out, H, eps);
   else
     rmsnorm_kernel<false><<<M, 256, H * sizeof(float), s>>>((__nv_bfloat16*)x, nullptr, w, (__nv_bfloat16*)out, H, eps);
+  return cudaGetLastError();
+}
+// rmsnorm (+ residual add) that also emits the INT8 row quantisation of its output; false = geometry not covered by the fused kernel
+bool rmsnorm_q8_supported(int H) { return H == 2048; }
+cudaError_t launch_rmsnorm_q8(void* x, void* residual, const float* w, void* out, void* q, float* q_scale, int M, int H, float eps,
+                              cudaStream_t s) {
+  KernelSpan ks(K_RMSNORM, s);
+  if (!rmsnorm_q8_supported(H) || M <= 0) return cudaErrorInvalidValue;
+  if (residual)
+    rmsnorm_warp_kernel<true, 8, true><<<(M + 7) / 8, 256, 0, s>>>((__nv_bfloat16*)x, (__nv_bfloat16*)residual, w, (__nv_bfloat16*)out, M,
+                                                                   eps, (int8_t*)q, q_scale);
+  else
+    rmsnorm_warp_kernel<false, 8, true><<<(M + 7) / 8, 256, 0, s>>>((__nv_bfloat16*)x, nullptr, w, (__nv_bfloat16*)out, M, eps, (int8_t*)q,
+                                                                    q_scale);
+  return cudaGetLastError();
+}
+bool silu_mul_quant_supported(int N) { return N == 256 || N == 512 || N == 1024 || N == 2048; }
+cudaError_t launch_silu_mul_quant(const void* x, void* q, float* scale_f32, int rows, int N, cudaStream_t s) {
+  KernelSpan ks(K_SILU_MUL, s);
+  if (rows <= 0) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  if (N == 256) silu_mul_quant_kernel<1><<<grid, 256, 0, s>>>(xb, (int8_t*)q, scale_f32, rows);
+  else if (N == 512) silu_mul_quant_kernel<2><<<grid, 256, 0, s>>>(xb, (int8_t*)q, scale_f32, rows);
+  else if (N == 1024) silu_mul_quant_kernel<4><<<grid, 256, 0, s>>>(xb, (int8_t*)q, scale_f32, rows);
+  else if (N == 2048) silu_mul_quant_kernel<8><<<grid, 256, 0, s>>>(xb, (int8_t*)q, scale_f32, rows);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 cudaError_t launch_quant_rows_int8(const void* x, void* q, float* scale_f32, void* scale_bf16, int rows, int K, cudaStream_t s) {

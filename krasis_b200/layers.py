@@ -38,6 +38,18 @@ def fused_add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, weight_f32: torch
                                        x.shape[1], float(eps), _dev(x), _s(x)))
 
 
+def fused_add_rmsnorm_q8(x: torch.Tensor, residual: torch.Tensor, weight_f32: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fused_add_rmsnorm that also returns the INT8 row quantisation (q int8 [M,H], scale f32 [M]) of the normed rows — exactly what
+    int8_linear (weight_loader.py:46-99) would compute from them, so the shared expert's first GEMM skips its quantisation pass."""
+    _chk_bf16(x, "x")
+    _chk_bf16(residual, "residual")
+    q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    qs = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    capi.check(capi.load().kb2_rmsnorm_q8(x.data_ptr(), residual.data_ptr(), weight_f32.data_ptr(), x.data_ptr(), q.data_ptr(), qs.data_ptr(),
+                                          x.shape[0], x.shape[1], float(eps), _dev(x), _s(x)))
+    return q, qs
+
+
 def quantize_to_int8(weight_bf16: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """weight_loader.py:25-43: per-row symmetric INT8; returns (int8 [N,K], scale bf16 [N])."""
     _chk_bf16(weight_bf16, "weight")
@@ -62,6 +74,32 @@ def int8_linear(x: torch.Tensor, weight_int8: torch.Tensor, scale: torch.Tensor)
     return out
 
 
+def int8_linear_q8(xq: torch.Tensor, xs: torch.Tensor, weight_int8: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """int8_linear on an activation that is already row-quantised (xq int8 [M,K], xs f32 [M])."""
+    m, k = xq.shape
+    n = weight_int8.shape[0]
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=xq.device)
+    capi.check(capi.load().kb2_int8_linear_q8(xq.data_ptr(), xs.data_ptr(), weight_int8.data_ptr(), scale.data_ptr(), out.data_ptr(),
+                                              m, n, k, _dev(xq), _s(xq)))
+    return out
+
+
+def silu_mul_int8_linear(gate_up: torch.Tensor, weight_int8: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """int8_linear(silu(gate) * up, W) with the activation quantised straight from the [M, 2K] gate|up rows (bit-identical to
+    silu_and_mul followed by int8_linear)."""
+    _chk_bf16(gate_up, "gate_up")
+    m, k = gate_up.shape[0], gate_up.shape[1] // 2
+    n = weight_int8.shape[0]
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=gate_up.device)
+    xq = torch.empty((m, k), dtype=torch.int8, device=gate_up.device)
+    xs = torch.empty(m, dtype=torch.float32, device=gate_up.device)
+    act = None if k in (256, 512, 1024, 2048) else torch.empty((m, k), dtype=torch.bfloat16, device=gate_up.device)
+    capi.check(capi.load().kb2_silu_mul_int8_linear(gate_up.data_ptr(), weight_int8.data_ptr(), scale.data_ptr(), out.data_ptr(),
+                                                    act.data_ptr() if act is not None else None, xq.data_ptr(), xs.data_ptr(), m, n, k,
+                                                    _dev(gate_up), _s(gate_up)))
+    return out
+
+
 def silu_and_mul(x: torch.Tensor) -> torch.Tensor:
     _chk_bf16(x, "x")
     out = torch.empty((x.shape[0], x.shape[1] // 2), dtype=torch.bfloat16, device=x.device)
@@ -77,9 +115,10 @@ class SharedExpert:
         self.down = quantize_to_int8(down_proj_bf16.contiguous())
         self.gate = shared_expert_gate.reshape(-1).contiguous() if shared_expert_gate is not None else None
 
-    def forward(self, hidden: torch.Tensor) -> torch.Tensor:
-        act = silu_and_mul(int8_linear(hidden, *self.gate_up))
-        out = int8_linear(act, *self.down)
+    def forward(self, hidden: torch.Tensor, hidden_q8=None) -> torch.Tensor:
+        """hidden_q8 = (q, scale) from fused_add_rmsnorm_q8 when the caller's norm already quantised these rows."""
+        gu = int8_linear_q8(hidden_q8[0], hidden_q8[1], *self.gate_up) if hidden_q8 is not None else int8_linear(hidden, *self.gate_up)
+        out = silu_mul_int8_linear(gu, *self.down)
         if self.gate is not None:
             capi.check(capi.load().kb2_sigmoid_gate_mul(hidden.data_ptr(), self.gate.data_ptr(), out.data_ptr(), hidden.shape[0],
                                                          hidden.shape[1], out.shape[1], _dev(hidden), _s(hidden)))

@@ -594,7 +594,7 @@ class KrasisModel:
         return self._live_seqs
 
     # ------------------------------------------------------------------------------------------- forward
-    def _moe(self, lay, h, M_loc):
+    def _moe(self, lay, h, M_loc, h_q8=None):
         """Router + shared expert + routed experts of one MoE layer on this rank's token rows h [M_loc, H]."""
         tm, m, R = self._timer, lay.moe_idx, self.num_ranks
         if R > 1:
@@ -617,7 +617,7 @@ class KrasisModel:
         shared = None
         with tm("shared_expert"):
             if lay.shared_expert is not None:
-                shared = lay.shared_expert.forward(h)
+                shared = lay.shared_expert.forward(h, h_q8) if h_q8 is not None else lay.shared_expert.forward(h)
             elif self.shared_mode == "int4_manager":                        # gpu_prefill.py:4738-4801: one-expert MoE, weight 1
                 if self._ones is None or self._ones.shape[0] < h.shape[0]:
                     self._zero_ids = torch.zeros((self.max_tokens, 1), dtype=torch.int32, device=self.device)
@@ -717,13 +717,17 @@ class KrasisModel:
                 if R > 1:
                     with tm("attention_reduce_scatter"):
                         attn = self.comm.reduce_scatter_rows(attn)             # sum of the partial o_proj outputs, this rank's rows
+            h_q8 = None
             with tm("norms"):
-                L.fused_add_rmsnorm(attn, residual, lay.post_attn_norm, eps)   # layer.py:305-309
+                if lay.dense is None and isinstance(lay.shared_expert, L.SharedExpert):
+                    h_q8 = L.fused_add_rmsnorm_q8(attn, residual, lay.post_attn_norm, eps)   # + the shared expert's activation quantisation
+                else:
+                    L.fused_add_rmsnorm(attn, residual, lay.post_attn_norm, eps)   # layer.py:305-309
             if lay.dense is not None:
                 with tm("dense_mlp"):
                     hidden = lay.dense.forward(attn)
             else:
-                hidden = self._moe(lay, attn, hi - lo)
+                hidden = self._moe(lay, attn, hi - lo, h_q8)
         st.advance(M)
         with tm("final_norm_lm_head"):
             L.fused_add_rmsnorm(hidden, residual, self.final_norm, eps)    # model.py:3380-3386
