@@ -176,6 +176,15 @@ KB2_API int kb2_ep_combine_rows(kb2_engine* e, const void* rows_sorted_dev, cons
  * partial sums): out = bf16(rsf * routed) (+ shared_dev) — python/krasis/gpu_prefill.py:4467-4482.  out may alias routed. */
 KB2_API int kb2_finish_routed(kb2_engine* e, const void* routed_dev, const void* shared_dev, void* out_dev, int32_t num_tokens,
                               void* stream);
+/* Expert parallelism with the reduce-scatter fused into the combine kernel (replaces kb2_moe_forward(routed_only=1) +
+ * kb2_comm_reduce_scatter_bf16 + kb2_finish_routed; reference semantics: python/krasis/model.py:3086-3211).
+ * peer_recv_host[r] = rank r's receive buffer as seen from this rank (kb2_comm_peer_alloc), layout [M / num_ranks][num_ranks][H] bf16.
+ * Every rank: kb2_moe_forward_scatter(all M tokens, local expert slice) -> kb2_comm_barrier -> kb2_finish_routed_slots(own buffer). */
+KB2_API int kb2_moe_forward_scatter(kb2_engine* e, int moe_layer_idx, const void* hidden_dev, const int32_t* topk_ids_dev,
+                                    const float* topk_weights_dev, void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank,
+                                    int32_t num_tokens, void* stream);
+KB2_API int kb2_finish_routed_slots(kb2_engine* e, const void* slots_dev, int32_t num_ranks, const void* shared_dev, void* out_dev,
+                                    int32_t rows, void* stream);
 
 /* Host-buffer variant of route + forward for callers that hold activations in (pinned) host memory —
  * the shape of KrasisEngine.submit_forward/sync_forward (src/moe.rs:2722,2809: bytes in, bytes out).
@@ -357,6 +366,15 @@ KB2_API int kb2_comm_all_gather(kb2_comm* c, const void* send_dev, void* recv_de
 KB2_API int kb2_comm_reduce_scatter_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems_per_rank, void* stream);
 KB2_API int kb2_comm_all_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems, void* stream);
 KB2_API int kb2_comm_broadcast(kb2_comm* c, void* buf_dev, size_t bytes, int32_t root, void* stream);
+/* Peer memory + barrier for collectives fused into compute kernels (one process per GPU, one node, NVLink / NVSwitch):
+ *   kb2_comm_peer_alloc   collective: cudaMalloc(bytes) on every rank, CUDA IPC handles exchanged by all-gather;
+ *                         ptrs_out_host[r] = pointer through which THIS rank loads / stores rank r's buffer (r == rank: local)
+ *   kb2_comm_barrier      4-byte all-reduce on `stream`: a rank leaves only after every peer's stream has reached it
+ *   kb2_moe_forward_scatter + kb2_finish_routed_slots (below, engine section) use them for the expert-parallel reduce-scatter:
+ *   the combine kernel of every rank stores its partial rows straight into the token owner's receive buffer. */
+KB2_API int kb2_comm_peer_alloc(kb2_comm* c, size_t bytes, void** ptrs_out_host);
+KB2_API int kb2_comm_peer_free(kb2_comm* c, void** ptrs_host);
+KB2_API int kb2_comm_barrier(kb2_comm* c, void* stream);
 /* BF16 sum over ranks delivered to `root` only (recv_dev may be NULL elsewhere): one chunk of a pipelined reduce-scatter whose
  * chunk j is rank j's token shard (krasis_b200/model.py: attention over chunk j+1 runs while chunk j's partial outputs are reduced). */
 KB2_API int kb2_comm_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_dev, size_t elems, int32_t root, void* stream);

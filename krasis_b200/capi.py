@@ -115,6 +115,12 @@ SIGNATURES = {
     "kb2_comm_reduce_scatter_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kb2_comm_all_reduce_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kb2_comm_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
+    "kb2_comm_peer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "kb2_comm_peer_free": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "kb2_comm_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kb2_moe_forward_scatter": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_void_p]),
+    "kb2_finish_routed_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "kb2_comm_reduce_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
     "kb2_total_launches": (C.c_int64, []),
     "kb2_kernel_profile_num": (C.c_int, []),

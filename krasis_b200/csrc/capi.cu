@@ -34,6 +34,8 @@ cudaError_t launch_binning_index(const int* ids, const float* wts, int M, int to
                                  int* offsets, int* cursor, ChunkDesc* chunks, int* n_chunks, float* sorted_w, int* slot_of,
                                  int* sorted_tok, cudaStream_t s);
 cudaError_t make_tmap_bf16_gather(void* out_tmap, const void* base, long long rows, long long cols);
+cudaError_t launch_combine_scatter(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
+                                   const void* shared, void* out, const CombineScatter& sc, cudaStream_t s);
 cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
                            const void* shared, void* out, cudaStream_t s);
 cudaError_t launch_quantize_group(const void* w, int bits, void* q_out, void* scales, long long rows, int K, cudaStream_t s);
@@ -528,7 +530,7 @@ KB2_API int kb2_route(kb2_engine* e, int layer, const void* hidden, int32_t M, i
 
 // Shared implementation: `n_rows` activation rows, `K` routing entries per row.
 static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32_t* ids, const float* wts, void* out,
-                            int M, int K, int apply_rsf, const void* shared, cudaStream_t s) {
+                            int M, int K, int apply_rsf, const void* shared, cudaStream_t s, const CombineScatter* scatter = nullptr) {
   LayerWeights& L = e->layers[layer];
   const int H = e->cfg.hidden_size, I = e->cfg.moe_intermediate_size;
   const int f13 = fmt13(e), f2 = fmt2(e);
@@ -572,7 +574,8 @@ static int moe_forward_impl(kb2_engine* e, int layer, const void* x, const int32
     CUDA_TRY(launch_grouped_gemm(f2, false, g2, e->tmap_act, e->num_sms, s)); }
 
   { ProfSpan ps(e, KB2_PROF_COMBINE, s);
-    CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply_rsf, shared, out, s)); }
+    if (scatter) CUDA_TRY(launch_combine_scatter(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, 0, nullptr, nullptr, *scatter, s));
+    else CUDA_TRY(launch_combine(e->c3, e->slot_of, M, H, K, e->cfg.routed_scaling_factor, apply_rsf, shared, out, s)); }
   e->launches += 3;
   return KB2_OK;
 }
@@ -588,6 +591,46 @@ KB2_API int kb2_moe_forward(kb2_engine* e, int layer, const void* x, const int32
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   return moe_forward_impl(e, layer, x, ids, wts, out, M, e->cfg.num_experts_per_tok, routed_only ? 0 : 1,
                           routed_only ? nullptr : shared, (cudaStream_t)stream);
+}
+
+// Expert-parallel forward with the reduce-scatter fused into the combine kernel: this rank's partial sums (local expert slice, ALL
+// M = num_ranks * rows_per_rank tokens) are written straight into the receive buffers of the token owners (peer-mapped memory from
+// kb2_comm_peer_alloc, layout [rows_per_rank][num_ranks][H] bf16, slot = source rank).  After kb2_comm_barrier the owner calls
+// kb2_finish_routed_slots.  Replaces kb2_moe_forward(routed_only) + kb2_comm_reduce_scatter_bf16 + kb2_finish_routed.
+KB2_API int kb2_moe_forward_scatter(kb2_engine* e, int layer, const void* x, const int32_t* ids, const float* wts,
+                                    void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank, int32_t M, void* stream) {
+  if (int r = check_layer(e, layer)) return r;
+  LayerWeights& L = e->layers[layer];
+  if (M < 0 || M > e->cfg.max_tokens) return fail(KB2_ERR_VALUE, "num_tokens %d outside [0, max_tokens=%d]", M, e->cfg.max_tokens);
+  if (num_ranks < 1 || num_ranks > kMaxPeers || src_rank < 0 || src_rank >= num_ranks || M % num_ranks)
+    return fail(KB2_ERR_VALUE, "scatter: need 1 <= num_ranks <= %d, 0 <= src_rank < num_ranks, num_tokens %% num_ranks == 0", kMaxPeers);
+  if (!L.w13_q) return fail(KB2_ERR_STATE, "GPU weights not available for layer %d", layer);
+  if (M == 0) return KB2_OK;
+  if (!x || !ids || !wts || !peer_recv_host) return fail(KB2_ERR_VALUE, "null argument");
+  CombineScatter sc;
+  for (int r = 0; r < num_ranks; ++r) {
+    if (!peer_recv_host[r]) return fail(KB2_ERR_VALUE, "scatter: null receive buffer for rank %d", r);
+    sc.peer_out[r] = (__nv_bfloat16*)peer_recv_host[r];
+  }
+  sc.rows_per_rank = M / num_ranks; sc.src_rank = src_rank; sc.n_ranks = num_ranks;
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  return moe_forward_impl(e, layer, x, ids, wts, nullptr, M, e->cfg.num_experts_per_tok, 0, nullptr, (cudaStream_t)stream, &sc);
+}
+
+// out[m] = bf16(rsf * bf16(sum_r f32(slots[m][r]))) + shared[m]: the consumer side of the fused reduce-scatter (fp32 sum of the
+// num_ranks BF16 partials, one rounding — NCCL's ring rounds to BF16 at every hop).
+KB2_API int kb2_finish_routed_slots(kb2_engine* e, const void* slots, int32_t num_ranks, const void* shared, void* out, int32_t rows,
+                                    void* stream) {
+  if (!e) return fail(KB2_ERR_VALUE, "null engine");
+  if (rows < 0 || rows > e->cfg.max_tokens || num_ranks < 1 || num_ranks > kMaxPeers) return fail(KB2_ERR_VALUE, "bad rows / num_ranks");
+  if (rows == 0) return KB2_OK;
+  if (!slots || !out) return fail(KB2_ERR_VALUE, "null argument");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfSpan ps(e, KB2_PROF_COMBINE, s);
+  CUDA_TRY(launch_combine(slots, nullptr, rows, e->cfg.hidden_size, num_ranks, e->cfg.routed_scaling_factor, 1, shared, out, s));
+  e->launches += 1;
+  return KB2_OK;
 }
 
 // ---- expert-parallel building blocks (all-to-all dispatch / combine) -------------------------

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <mutex>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -77,6 +78,7 @@ int failf(int code, const char* fmt, ...) {
 struct kb2_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1, device = 0;
+  int* barrier_word = nullptr;        // 4-byte device buffer of kb2_comm_barrier
 };
 
 #define NCCL_TRY(expr)                                                                                   \
@@ -113,6 +115,7 @@ KB2_API int kb2_comm_init(const void* unique_id128, int32_t rank, int32_t num_ra
 
 KB2_API void kb2_comm_destroy(kb2_comm* c) {
   if (!c) return;
+  if (c->barrier_word) cudaFree(c->barrier_word);
   if (c->comm) nccl().CommDestroy(c->comm);
   delete c;
 }
@@ -146,6 +149,64 @@ KB2_API int kb2_comm_reduce_bf16(kb2_comm* c, const void* send_dev, void* recv_d
   if (root < 0 || root >= c->nranks) return failf(KB2_ERR_VALUE, "reduce: root %d outside [0, %d)", root, c->nranks);
   if (c->rank == root && !recv_dev) return failf(KB2_ERR_VALUE, "reduce: the root needs a receive buffer");
   NCCL_TRY(nccl().Reduce(send_dev, recv_dev, elems, kNcclBfloat16, kNcclSum, root, c->comm, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+// Cross-rank barrier on `stream`: a 4-byte all-reduce.  A rank leaves it only after every rank's stream has reached it, i.e. after
+// every kernel the peers enqueued before it (and its peer-memory stores) has completed.
+KB2_API int kb2_comm_barrier(kb2_comm* c, void* stream) {
+  if (!c) return failf(KB2_ERR_VALUE, "null argument");
+  if (!c->barrier_word) {
+    if (cudaMalloc(&c->barrier_word, 64) != cudaSuccess) return failf(KB2_ERR_CUDA, "cudaMalloc failed (barrier word)");
+    cudaMemset(c->barrier_word, 0, 64);
+  }
+  NCCL_TRY(nccl().AllReduce(c->barrier_word, c->barrier_word, 1, kNcclUint8, kNcclSum, c->comm, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
+// Collective: every rank allocates `bytes` of device memory (cudaMalloc, zero-filled), the CUDA IPC handles travel by all-gather, and
+// ptrs_out_host[r] receives a pointer through which THIS rank can load / store rank r's buffer (ptrs_out_host[rank] = the local one).
+// One process per GPU on one node (NVLink / NVSwitch peer access).  Free with kb2_comm_peer_free on every rank.
+KB2_API int kb2_comm_peer_alloc(kb2_comm* c, size_t bytes, void** ptrs_out_host) {
+  if (!c || !ptrs_out_host || bytes == 0) return failf(KB2_ERR_VALUE, "null argument");
+  if (cudaSetDevice(c->device) != cudaSuccess) return failf(KB2_ERR_CUDA, "cudaSetDevice failed");
+  void* local = nullptr;
+  if (cudaMalloc(&local, bytes) != cudaSuccess) return failf(KB2_ERR_CUDA, "cudaMalloc(%zu) failed (peer buffer)", bytes);
+  cudaMemset(local, 0, bytes);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, local) != cudaSuccess) { cudaFree(local); return failf(KB2_ERR_CUDA, "cudaIpcGetMemHandle failed"); }
+  const size_t hs = sizeof(cudaIpcMemHandle_t);
+  unsigned char* dbuf = nullptr;
+  if (cudaMalloc(&dbuf, hs * c->nranks) != cudaSuccess) { cudaFree(local); return failf(KB2_ERR_CUDA, "cudaMalloc failed (handle exchange)"); }
+  cudaMemcpy(dbuf + hs * c->rank, &mine, hs, cudaMemcpyHostToDevice);
+  int rc = nccl().AllGather(dbuf + hs * c->rank, dbuf, hs, kNcclUint8, c->comm, (cudaStream_t)0);
+  if (rc == 0 && cudaStreamSynchronize(0) != cudaSuccess) rc = -1;
+  std::vector<cudaIpcMemHandle_t> all(c->nranks);
+  if (rc == 0) cudaMemcpy(all.data(), dbuf, hs * c->nranks, cudaMemcpyDeviceToHost);
+  cudaFree(dbuf);
+  if (rc != 0) { cudaFree(local); return failf(KB2_ERR_CUDA, "IPC handle exchange failed"); }
+  for (int r = 0; r < c->nranks; ++r) {
+    if (r == c->rank) { ptrs_out_host[r] = local; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      return failf(KB2_ERR_CUDA, "cudaIpcOpenMemHandle failed for rank %d (no peer access between the devices?)", r);
+    }
+    ptrs_out_host[r] = p;
+  }
+  return KB2_OK;
+}
+
+KB2_API int kb2_comm_peer_free(kb2_comm* c, void** ptrs_host) {
+  if (!c || !ptrs_host) return failf(KB2_ERR_VALUE, "null argument");
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->nranks; ++r) {
+    if (!ptrs_host[r]) continue;
+    if (r == c->rank) cudaFree(ptrs_host[r]);
+    else cudaIpcCloseMemHandle(ptrs_host[r]);
+    ptrs_host[r] = nullptr;
+  }
   return KB2_OK;
 }
 

@@ -98,4 +98,11 @@ struct GemmParams {
   long long* trace;           // optional (tuning only, KB2_GEMM_TRACE=<device pointer>): clock64 stamps of CTA 0, [item < 16][16]
 };
 
+// combine_kernel output redirection for the fused reduce-scatter of expert parallelism (n_ranks == 0: plain local output)
+constexpr int kMaxPeers = 8;
+struct CombineScatter {
+  __nv_bfloat16* peer_out[kMaxPeers] = {};   // receive buffer of every rank ([rows_per_rank][n_ranks][H] bf16), peer-mapped
+  int rows_per_rank = 0, src_rank = 0, n_ranks = 0;
+};
+
 }  // namespace kb2

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const __nv_bfloat16* __res
                                                       const int* __restrict__ slot_of, int M, int H, int top_k,
                                                       float rsf, int apply_rsf,
                                                       const __nv_bfloat16* __restrict__ shared,
-                                                      __nv_bfloat16* __restrict__ out) {
+                                                      __nv_bfloat16* __restrict__ out, CombineScatter sc) {
   const int vec_per_row = H >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M * vec_per_row) return;
@@ -309,6 +309,15 @@ __global__ void __launch_bounds__(256) combine_kernel(const __nv_bfloat16* __res
     if (apply_rsf) r = bf16_round_rn(rsf * r);
     if (shared) r = bf16_round_rn(r + __bfloat162float(ps[i]));
     po[i] = __ushort_as_bfloat16((unsigned short)(__float_as_uint(r) >> 16));
+  }
+  if (sc.n_ranks > 0) {
+    // fused reduce-scatter, producer side: the row goes straight into its OWNER rank's receive buffer over NVLink (peer-mapped
+    // memory), slot `src_rank` of token (m - owner * rows_per_rank); the owner sums its n_ranks slots with this same kernel
+    // (slot_of == nullptr, top_k == n_ranks) once every rank has passed the barrier that follows
+    const int owner = m / sc.rows_per_rank, ml = m - owner * sc.rows_per_rank;
+    __nv_bfloat16* dst = sc.peer_out[owner] + ((long long)ml * sc.n_ranks + sc.src_rank) * H + v * 8;
+    *reinterpret_cast<uint4*>(dst) = o;
+    return;
   }
   *reinterpret_cast<uint4*>(out + (long long)m * H + v * 8) = o;
 }
@@ -611,15 +620,19 @@ cudaError_t launch_binning_index(const int* ids, const float* wts, int M, int to
   return cudaGetLastError();
 }
 
-cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
-                           const void* shared, void* out, cudaStream_t s) {
+cudaError_t launch_combine_scatter(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
+                                   const void* shared, void* out, const CombineScatter& sc, cudaStream_t s) {
   KernelSpan ks(K_COMBINE, s);
   const long long total = (long long)M * (H / 8);
   if (total == 0) return cudaSuccess;
   combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)c3, slot_of, M, H, top_k, rsf,
                                                                 apply_rsf, (const __nv_bfloat16*)shared,
-                                                                (__nv_bfloat16*)out);
+                                                                (__nv_bfloat16*)out, sc);
   return cudaGetLastError();
+}
+cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf,
+                           const void* shared, void* out, cudaStream_t s) {
+  return launch_combine_scatter(c3, slot_of, M, H, top_k, rsf, apply_rsf, shared, out, CombineScatter{}, s);
 }
 
 cudaError_t launch_repack(int fmt, const void* src_q, const void* src_s, void* dst_q, void* dst_s, int E, int N, int K,

@@ -391,6 +391,28 @@ class KrasisEngine:
                                              _stream_ptr(hidden_states.device)))
         return out
 
+    def moe_forward_scatter(self, moe_layer_idx, hidden_states, topk_ids, topk_weights, peer_ptrs, src_rank: int) -> None:
+        """Local expert slice over ALL tokens with the expert-parallel reduce-scatter fused into the combine kernel: the partial rows
+        go straight into the token owners' receive buffers (peer_ptrs from Communicator.peer_alloc, [rows][world][H] bf16 each)."""
+        self._check_act(hidden_states, "hidden_states")
+        M, k, R = hidden_states.shape[0], self._cfg.num_experts_per_tok, len(peer_ptrs)
+        if tuple(topk_ids.shape) != (M, k) or topk_ids.dtype != torch.int32 or not topk_ids.is_contiguous():
+            raise ValueError(f"topk_ids: expected contiguous int32 [{M}, {k}]")
+        if tuple(topk_weights.shape) != (M, k) or topk_weights.dtype != torch.float32 or not topk_weights.is_contiguous():
+            raise ValueError(f"topk_weights: expected contiguous float32 [{M}, {k}]")
+        arr = (C.c_void_p * R)(*peer_ptrs)
+        capi.check(self._lib.kb2_moe_forward_scatter(self._h, moe_layer_idx, hidden_states.data_ptr(), topk_ids.data_ptr(),
+                                                     topk_weights.data_ptr(), arr, R, src_rank, M, _stream_ptr(hidden_states.device)))
+
+    def finish_slots(self, slots_ptr: int, world: int, rows: int, shared: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
+        """bf16(rsf * bf16(sum over the `world` partial rows of every token)) + shared, from this rank's receive buffer."""
+        out = torch.empty((rows, self._cfg.hidden_size), dtype=torch.bfloat16, device=like.device)
+        if shared is not None:
+            self._check_act(shared, "shared")
+        capi.check(self._lib.kb2_finish_routed_slots(self._h, slots_ptr, world, shared.data_ptr() if shared is not None else None,
+                                                     out.data_ptr(), rows, _stream_ptr(like.device)))
+        return out
+
     def finish(self, routed: torch.Tensor, shared: Optional[torch.Tensor] = None) -> torch.Tensor:
         """bf16(rsf * routed) + shared, in place on `routed` (the tail of gpu_prefill.py:4467-4482 after an EP reduction)."""
         self._check_act(routed, "routed")

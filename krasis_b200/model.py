@@ -550,6 +550,9 @@ class KrasisModel:
         # hold SMs that the persistent one-CTA-per-SM GEMM / scan kernels are sized for (Gated DeltaNet 24.8 -> 32.0 ms), which costs
         # more than the 2 x 1 ms of hidden communication.  KB2_PIPELINE_ATTENTION=1 enables it.
         self.pipeline_attention = os.environ.get("KB2_PIPELINE_ATTENTION", "0") == "1"
+        # expert-parallel reduce-scatter fused into the combine kernel over peer memory (KB2_FUSED_EP=0: NCCL reduce-scatter)
+        self.fused_ep = os.environ.get("KB2_FUSED_EP", "1") != "0"
+        self._ep_recv, self._ep_recv_rows = None, 0
 
     # ------------------------------------------------------------------------------------------- real checkpoints
     @classmethod
@@ -630,6 +633,21 @@ class KrasisModel:
             main.wait_stream(side)                                          # gathered rows / ids / weights are in place
             for t in (h_all, ids_all, w_all):
                 t.record_stream(main)
+        if self.fused_ep:
+            # reduce-scatter fused into the combine kernel: every rank's partial rows go straight into the owner's receive buffer over
+            # NVLink; two buffers alternate by layer so that a fast rank cannot overwrite slots a slow rank is still summing
+            rows = h.shape[0]
+            if self._ep_recv is None or self._ep_recv_rows != rows:
+                nbytes = rows * R * self.cfg.hidden_size * 2
+                self._ep_recv = [self.comm.peer_alloc(nbytes), self.comm.peer_alloc(nbytes)]
+                self._ep_recv_rows = rows
+            ptrs = self._ep_recv[m & 1]
+            with tm("routed_experts"):
+                self.engine.moe_forward_scatter(m, h_all, ids_all, w_all, ptrs, self.rank)
+            with tm("ep_reduce_scatter"):
+                self.comm.barrier()
+            with tm("routed_experts"):
+                return self.engine.finish_slots(ptrs[self.rank], R, rows, shared, h)
         with tm("routed_experts"):
             part = self.engine.moe_forward(m, h_all, ids_all, w_all, routed_only=True)       # local expert slice, all tokens
         with tm("ep_reduce_scatter"):

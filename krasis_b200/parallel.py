@@ -73,6 +73,7 @@ class Communicator:
     def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
         self._lib = capi.load()
         self.rank, self.world, self.device = rank, world, torch.device("cuda", device)
+        self._peer_allocs = []
         self._h = C.c_void_p()
         buf = C.create_string_buffer(bytes(unique_id), 128)
         capi.check(self._lib.kb2_comm_init(buf, rank, world, device, C.byref(self._h)))
@@ -122,6 +123,20 @@ class Communicator:
     def all_reduce(self, x: torch.Tensor) -> torch.Tensor:
         capi.check(self._lib.kb2_comm_all_reduce_bf16(self._h, x.data_ptr(), x.data_ptr(), x.numel(), self._stream()))
         return x
+
+    def peer_alloc(self, nbytes: int):
+        """Collective: `nbytes` of zero-filled device memory on every rank, mapped into every process through CUDA IPC.  Returns the
+        list of device pointers [world] through which THIS rank addresses each rank's buffer (entry `rank` is the local one)."""
+        arr = (C.c_void_p * self.world)()
+        capi.check(self._lib.kb2_comm_peer_alloc(self._h, nbytes, arr))
+        ptrs = [int(arr[r]) for r in range(self.world)]
+        self._peer_allocs.append(arr)
+        return ptrs
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier (4-byte all-reduce): peers' kernels enqueued before it — and their peer-memory stores —
+        are complete when it returns on this rank's stream."""
+        capi.check(self._lib.kb2_comm_barrier(self._h, self._stream()))
 
     def reduce_rows(self, x: torch.Tensor, root: int, out: torch.Tensor = None) -> torch.Tensor:
         """BF16 sum over ranks of `x`, delivered to `root` (returns `out` there, None elsewhere)."""
