@@ -347,6 +347,16 @@ KB2_API int kb2_mla_forward(kb2_mla* h, int layer, const void* hidden_dev, const
                             void* ckv_cache_layer_dev, void* kpe_cache_layer_dev, const int32_t* kv_indices_dev,
                             int32_t kv_len_after, void* out_dev, int32_t num_tokens, void* stream);
 
+/* GEMM -> reduce-scatter fused (head-parallel attention under token sharding): after kb2_{gdn,gqa,mla}_set_output_scatter the
+ * block's out_proj GEMM stores every output row straight into the receive buffer of the rank that owns the token
+ * (peer_recv_host[r] from kb2_comm_peer_alloc, layout [M / num_ranks][num_ranks][hidden] bf16, slot = src_rank) instead of out_dev
+ * (ignored).  num_ranks = 0 restores the local output.  Consumer: kb2_comm_barrier, then kb2_sum_slots_bf16 on the own buffer. */
+KB2_API int kb2_gdn_set_output_scatter(kb2_gdn* h, void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank);
+KB2_API int kb2_gqa_set_output_scatter(kb2_gqa* h, void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank);
+KB2_API int kb2_mla_set_output_scatter(kb2_mla* h, void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank);
+KB2_API int kb2_sum_slots_bf16(const void* slots_dev, int32_t num_ranks, void* out_dev, int32_t rows, int32_t H, int32_t device, void* stream);
+
+
 /* ================================================================================================
  * Multi-GPU: the expert-parallel communicator.  One process per GPU; replaces the reference's replicated-token EP loop
  * with a pinned-host bounce and a GPU0 reduction (python/krasis/model.py:3086-3211, KrasisEngine.reduce_sum_bf16

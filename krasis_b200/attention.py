@@ -87,6 +87,14 @@ class GatedDeltaNetAttention:
     def reset_state(self):
         capi.check(self._lib.kb2_gdn_reset_state(self._h, self._slot, _stream(self.device)))
 
+    def set_output_scatter(self, peer_ptrs=None, src_rank: int = 0) -> None:
+        """Head-parallel attention under token sharding: send the out_proj rows straight to the token owners' receive buffers
+        (Communicator.peer_alloc pointers, [rows][world][hidden] bf16) instead of returning them; None restores the local output.
+        The setting lives in the handle shared by all layers of the model, so the caller sets it before every forward."""
+        n = len(peer_ptrs) if peer_ptrs else 0
+        arr = (C.c_void_p * max(n, 1))(*(peer_ptrs or [None]))
+        capi.check(self._lib.kb2_gdn_set_output_scatter(self._h, arr, n, src_rank))
+
     def forward(self, hidden: torch.Tensor, is_decode: bool = False) -> torch.Tensor:
         if is_decode:
             raise NotImplementedError("M=1 recurrent decode is out of scope (SURVEY.md §8: prefill path only)")
@@ -250,6 +258,14 @@ class GQAAttention:
         except Exception:
             pass
 
+    def set_output_scatter(self, peer_ptrs=None, src_rank: int = 0) -> None:
+        """Head-parallel attention under token sharding: send the out_proj rows straight to the token owners' receive buffers
+        (Communicator.peer_alloc pointers, [rows][world][hidden] bf16) instead of returning them; None restores the local output.
+        The setting lives in the handle shared by all layers of the model, so the caller sets it before every forward."""
+        n = len(peer_ptrs) if peer_ptrs else 0
+        arr = (C.c_void_p * max(n, 1))(*(peer_ptrs or [None]))
+        capi.check(self._lib.kb2_gqa_set_output_scatter(self._h, arr, n, src_rank))
+
     def forward(self, hidden: torch.Tensor, positions: torch.Tensor, kv_cache: PagedKVCache, seq_state: SequenceKVState,
                 layer_offset: int, num_new_tokens: int = 0) -> torch.Tensor:
         if not hidden.is_cuda or hidden.dtype != torch.bfloat16 or hidden.dim() != 2 or not hidden.is_contiguous() \
@@ -372,6 +388,14 @@ class MLAAttention:
                 self._h = C.c_void_p()
         except Exception:
             pass
+
+    def set_output_scatter(self, peer_ptrs=None, src_rank: int = 0) -> None:
+        """Head-parallel attention under token sharding: send the out_proj rows straight to the token owners' receive buffers
+        (Communicator.peer_alloc pointers, [rows][world][hidden] bf16) instead of returning them; None restores the local output.
+        The setting lives in the handle shared by all layers of the model, so the caller sets it before every forward."""
+        n = len(peer_ptrs) if peer_ptrs else 0
+        arr = (C.c_void_p * max(n, 1))(*(peer_ptrs or [None]))
+        capi.check(self._lib.kb2_mla_set_output_scatter(self._h, arr, n, src_rank))
 
     def forward(self, hidden: torch.Tensor, positions: torch.Tensor, kv_cache: MLAPagedKVCache, seq_state: SequenceKVState,
                 layer_offset: int, num_new_tokens: int = 0) -> torch.Tensor:

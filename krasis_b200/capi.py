@@ -115,6 +115,10 @@ SIGNATURES = {
     "kb2_comm_reduce_scatter_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kb2_comm_all_reduce_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kb2_comm_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
+    "kb2_gdn_set_output_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "kb2_gqa_set_output_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "kb2_mla_set_output_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "kb2_sum_slots_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "kb2_comm_peer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "kb2_comm_peer_free": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "kb2_comm_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),

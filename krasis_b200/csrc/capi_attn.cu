@@ -20,6 +20,10 @@ cudaError_t launch_gdn_core(const GdnDims& d, const void* qkvz, const void* ba, 
                             const float* A_log, const float* dt_bias, const float* norm_w, float* rec_state,
                             void* qn, void* kn, void* vc, float* beta, float* g, float* vcorr, float* kcd, float* intra,
                             float* gcum, float* core, void* normed_out, int M, cudaStream_t s);
+cudaError_t launch_dense_gemm_scatter(const void* x, const void* w, void* out, const float* bias, int M, int N, int K, long long ldo,
+                                      bool out_f32, int num_sms, cudaStream_t s, const CombineScatter& sc);
+cudaError_t launch_combine(const void* c3, const int* slot_of, int M, int H, int top_k, float rsf, int apply_rsf, const void* shared,
+                           void* out, cudaStream_t s);
 cudaError_t launch_dense_gemm_i8(const void* xq, const float* x_scale, const void* wq, const void* w_scale, void* out,
                                  int M, int N, int K, long long ldo, int num_sms, cudaStream_t s);
 cudaError_t launch_rmsnorm(void* x, void* residual, const float* w, void* out, int M, int H, float eps, cudaStream_t s);
@@ -83,12 +87,32 @@ struct GdnLayer {
   bool loaded = false;
 };
 
+// the handle's output scatter resolved for a call over M tokens (rows_per_rank = M / n_ranks); disabled: all zero
+static CombineScatter scatter_for(const CombineScatter& sc, int M) {
+  CombineScatter r = sc;
+  if (r.n_ranks > 0) r.rows_per_rank = M / r.n_ranks;
+  return r;
+}
+static int set_scatter(CombineScatter& sc, void* const* peer_recv_host, int num_ranks, int src_rank) {
+  sc = CombineScatter{};
+  if (num_ranks == 0) return KB2_OK;                                      // back to the plain local output
+  if (!peer_recv_host || num_ranks < 1 || num_ranks > kMaxPeers || src_rank < 0 || src_rank >= num_ranks)
+    return failf(KB2_ERR_VALUE, "output scatter: need 1 <= num_ranks <= %d and 0 <= src_rank < num_ranks", kMaxPeers);
+  for (int r = 0; r < num_ranks; ++r) {
+    if (!peer_recv_host[r]) return failf(KB2_ERR_VALUE, "output scatter: null receive buffer for rank %d", r);
+    sc.peer_out[r] = (__nv_bfloat16*)peer_recv_host[r];
+  }
+  sc.n_ranks = num_ranks; sc.src_rank = src_rank;
+  return KB2_OK;
+}
+
 struct kb2_gdn {
   kb2_gdn_config cfg{};
   GdnDims d{};
   std::vector<GdnLayer> layers;
   void *qkvz = nullptr, *ba = nullptr, *qn = nullptr, *kn = nullptr, *vc = nullptr, *normed = nullptr;
   float *beta = nullptr, *g = nullptr, *vcorr = nullptr, *kcd = nullptr, *intra = nullptr, *gcum = nullptr, *core = nullptr;
+  CombineScatter out_scatter{};      // kb2_attn_set_output_scatter: out_proj rows go to the token owners' receive buffers
 };
 
 static std::vector<float> bf16_to_f32_host(const void* p, size_t n) {
@@ -208,6 +232,16 @@ KB2_API int kb2_add_bf16(const void* a_dev, const void* b_dev, void* out_dev, in
   return KB2_OK;
 }
 
+// out[m] = bf16(sum_r f32(slots[m][r])): the consumer side of a reduce-scatter fused into a producer kernel (slots = this rank's
+// receive buffer [rows][num_ranks][H] bf16, filled by every rank's out_proj GEMM / combine kernel; call after kb2_comm_barrier)
+KB2_API int kb2_sum_slots_bf16(const void* slots_dev, int32_t num_ranks, void* out_dev, int32_t rows, int32_t H, int32_t device, void* stream) {
+  if (!slots_dev || !out_dev) return failf(KB2_ERR_VALUE, "null argument");
+  if (rows <= 0 || H <= 0 || H % 8 || num_ranks < 1 || num_ranks > kMaxPeers) return failf(KB2_ERR_VALUE, "sum_slots: bad rows / H / num_ranks");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(launch_combine(slots_dev, nullptr, rows, H, num_ranks, 1.0f, 0, nullptr, out_dev, (cudaStream_t)stream));
+  return KB2_OK;
+}
+
 KB2_API int kb2_gdn_create(const kb2_gdn_config* c, kb2_gdn** out) {
   if (!c || !out) return failf(KB2_ERR_VALUE, "null argument");
   if (c->num_k_heads < 1 || c->num_v_heads % c->num_k_heads) return failf(KB2_ERR_VALUE, "num_v_heads must be a multiple of num_k_heads");
@@ -246,6 +280,11 @@ KB2_API int kb2_gdn_create(const kb2_gdn_config* c, kb2_gdn** out) {
 #undef ALLOC
   *out = h;
   return KB2_OK;
+}
+
+KB2_API int kb2_gdn_set_output_scatter(kb2_gdn* h, void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  return set_scatter(h->out_scatter, peer_recv_host, num_ranks, src_rank);
 }
 
 KB2_API void kb2_gdn_destroy(kb2_gdn* h) {
@@ -339,7 +378,7 @@ KB2_API int kb2_gdn_forward(kb2_gdn* h, int layer, const void* hidden_dev, void*
   CUDA_TRY(launch_dense_gemm(hidden_dev, L.w_ba, h->ba, nullptr, M, h->d.ba_ld, H, h->d.ba_ld, false, sms, s));
   CUDA_TRY(launch_gdn_core(h->d, h->qkvz, h->ba, L.conv_w, L.conv_state, L.A_log, L.dt_bias, L.norm_w, L.rec_state,
                            h->qn, h->kn, h->vc, h->beta, h->g, h->vcorr, h->kcd, h->intra, h->gcum, h->core, h->normed, M, s));
-  CUDA_TRY(launch_dense_gemm(h->normed, L.w_out, out_dev, nullptr, M, H, vd, H, false, sms, s));
+  CUDA_TRY(launch_dense_gemm_scatter(h->normed, L.w_out, out_dev, nullptr, M, H, vd, H, false, sms, s, scatter_for(h->out_scatter, M)));
   return KB2_OK;
 }
 
@@ -356,6 +395,7 @@ struct kb2_gqa {
   void *q_raw = nullptr, *k_raw = nullptr, *v_raw = nullptr, *q_rot = nullptr, *attn = nullptr;
   void *k_bf = nullptr, *v_bf = nullptr;     // dense BF16 upcast of the sequence's FP8 pages, [kv_cap][nkv*d] each
   long long kv_cap = 0;
+  CombineScatter out_scatter{};
 };
 
 KB2_API int kb2_gqa_create(const kb2_gqa_config* c, kb2_gqa** out) {
@@ -383,6 +423,11 @@ KB2_API int kb2_gqa_create(const kb2_gqa_config* c, kb2_gqa** out) {
   CUDA_TRY(cudaMalloc(&h->attn, M * qd * 2));
   *out = h;
   return KB2_OK;
+}
+
+KB2_API int kb2_gqa_set_output_scatter(kb2_gqa* h, void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  return set_scatter(h->out_scatter, peer_recv_host, num_ranks, src_rank);
 }
 
 KB2_API void kb2_gqa_destroy(kb2_gqa* h) {
@@ -447,7 +492,7 @@ KB2_API int kb2_gqa_forward(kb2_gqa* h, int layer, const void* hidden_dev, const
   }
   CUDA_TRY(launch_gqa_core(h->g, h->q_raw, h->k_raw, h->v_raw, L.q_norm, L.k_norm, positions_dev, kv_indices_dev, h->q_rot,
                            k_cache_layer_dev, v_cache_layer_dev, h->k_bf, h->v_bf, h->attn, M, first_position, kv_len_after, s));
-  CUDA_TRY(launch_dense_gemm(h->attn, L.wo, out_dev, nullptr, M, H, qd, H, false, sms, s));
+  CUDA_TRY(launch_dense_gemm_scatter(h->attn, L.wo, out_dev, nullptr, M, H, qd, H, false, sms, s, scatter_for(h->out_scatter, M)));
   return KB2_OK;
 }
 
@@ -463,6 +508,7 @@ struct kb2_mla {
   MlaDims m{};
   std::vector<MlaLayer> layers;
   void *q_full = nullptr, *q_a = nullptr, *kv_a = nullptr, *ckv_bf16 = nullptr, *kpe_bf16 = nullptr, *kv_up = nullptr, *attn = nullptr;
+  CombineScatter out_scatter{};
 };
 
 KB2_API int kb2_mla_create(const kb2_mla_config* c, kb2_mla** out) {
@@ -494,6 +540,11 @@ KB2_API int kb2_mla_create(const kb2_mla_config* c, kb2_mla** out) {
   CUDA_TRY(cudaMalloc(&h->attn, M * nh * 128 * 2));
   *out = h;
   return KB2_OK;
+}
+
+KB2_API int kb2_mla_set_output_scatter(kb2_mla* h, void* const* peer_recv_host, int32_t num_ranks, int32_t src_rank) {
+  if (!h) return failf(KB2_ERR_VALUE, "null handle");
+  return set_scatter(h->out_scatter, peer_recv_host, num_ranks, src_rank);
 }
 
 KB2_API void kb2_mla_destroy(kb2_mla* h) {
@@ -573,7 +624,7 @@ KB2_API int kb2_mla_forward(kb2_mla* h, int layer, const void* hidden_dev, const
   CUDA_TRY(launch_mla_core(h->m, h->q_full, h->kv_a, L.kv_norm, L.inv_freq, L.wkv, positions_dev, kv_indices_dev,
                            ckv_cache_layer_dev, kpe_cache_layer_dev, h->ckv_bf16, h->kpe_bf16, h->kv_up, h->attn, M,
                            first_position, kv_len_after, c.sm_scale, sms, s));
-  CUDA_TRY(launch_dense_gemm(h->attn, L.wo, out_dev, nullptr, M, H, nh * 128, H, false, sms, s));
+  CUDA_TRY(launch_dense_gemm_scatter(h->attn, L.wo, out_dev, nullptr, M, H, nh * 128, H, false, sms, s, scatter_for(h->out_scatter, M)));
   return KB2_OK;
 }
 

@@ -29,7 +29,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kDThreads, 1)
     dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       void* __restrict__ out, const float* __restrict__ bias, int M, int N, int K, long long ldo,
-                      const float* __restrict__ row_scale, const __nv_bfloat16* __restrict__ col_scale) {
+                      const float* __restrict__ row_scale, const __nv_bfloat16* __restrict__ col_scale, CombineScatter sc) {
   constexpr bool kOutF32 = MODE == 1;
   constexpr int kElemsPerBlock = MODE == 2 ? 128 : 64;     // 128 B of K per smem row
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -164,7 +164,14 @@ __global__ void __launch_bounds__(kDThreads, 1)
               __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
               pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ldo + n);
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(out) + (long long)m * ldo;
+            if (sc.n_ranks > 0) {
+              // GEMM -> reduce-scatter fused: this rank's partial output row goes straight into the receive buffer of the rank
+              // that owns token m (peer-mapped memory, [rows_per_rank][n_ranks][ldo], slot = source rank); see CombineScatter
+              const int owner = m / sc.rows_per_rank, ml = m - owner * sc.rows_per_rank;
+              orow = sc.peer_out[owner] + ((long long)ml * sc.n_ranks + sc.src_rank) * ldo;
+            }
+            uint4* o = reinterpret_cast<uint4*>(orow + n);
             o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
@@ -197,8 +204,16 @@ static cudaError_t dense_configure() {
 }
 
 // X [M][K] bf16 row-major, W [N][K] bf16 row-major, out [M][ldo] (bf16 or f32).  K % 64 == 0, N % 16 == 0.
+cudaError_t launch_dense_gemm_scatter(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
+                                      long long ldo, bool out_f32, int num_sms, cudaStream_t s, const CombineScatter& sc);
 cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
                               long long ldo, bool out_f32, int num_sms, cudaStream_t s) {
+  return launch_dense_gemm_scatter(x, w, out, bias, M, N, K, ldo, out_f32, num_sms, s, CombineScatter{});
+}
+// sc.n_ranks > 0 (BF16 output only): rows are stored into the token owners' receive buffers instead of `out`
+cudaError_t launch_dense_gemm_scatter(const void* x, const void* w, void* out, const float* bias, int M, int N, int K,
+                                      long long ldo, bool out_f32, int num_sms, cudaStream_t s, const CombineScatter& sc) {
+  if (sc.n_ranks > 0 && (out_f32 || M % sc.n_ranks || sc.rows_per_rank * sc.n_ranks != M)) return cudaErrorInvalidValue;
   KernelSpan ks(K_DENSE_BF16, s);
   if (K % kBlockK || N % 16 || M <= 0) return cudaErrorInvalidValue;
   alignas(64) CUtensorMap tx, tw;
@@ -211,9 +226,9 @@ cudaError_t launch_dense_gemm(const void* x, const void* w, void* out, const flo
   const int total = ((M + kDTileM - 1) / kDTileM) * ((N + kDTileN - 1) / kDTileN);
   const int grid = total < num_sms ? total : num_sms;
   if (out_f32)
-    dense_gemm_kernel<1><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo, nullptr, nullptr);
+    dense_gemm_kernel<1><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo, nullptr, nullptr, CombineScatter{});
   else
-    dense_gemm_kernel<0><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo, nullptr, nullptr);
+    dense_gemm_kernel<0><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, bias, M, N, K, ldo, nullptr, nullptr, sc);
   return cudaGetLastError();
 }
 
@@ -232,7 +247,7 @@ cudaError_t launch_dense_gemm_i8(const void* xq, const float* x_scale, const voi
   const int total = ((M + kDTileM - 1) / kDTileM) * ((N + kDTileN - 1) / kDTileN);
   const int grid = total < num_sms ? total : num_sms;
   dense_gemm_kernel<2><<<grid, kDThreads, kDSmem, s>>>(tx, tw, out, nullptr, M, N, K, ldo, x_scale,
-                                                      (const __nv_bfloat16*)w_scale);
+                                                      (const __nv_bfloat16*)w_scale, CombineScatter{});
   return cudaGetLastError();
 }
 

@@ -34,6 +34,17 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
+// clamp(round_half_even(x / scale)) of the reference's `(x / scale).round().clamp(-128, 127)` (weight_loader.py:25-43, 46-99), exactly,
+// without an IEEE division per element: y = x * rn(1 / scale) is within ~1e-5 of the correctly rounded quotient for |x / scale| <= 128,
+// so rint(y) can only differ from rint(x / scale) when y sits within that distance of a half-integer — those (rare) elements take the
+// true division.
+__device__ __forceinline__ int quant_code_rhe(float x, float scale, float rscale) {
+  const float y = x * rscale;
+  float r = rintf(y);
+  if (fabsf(fabsf(y - r) - 0.5f) < 1e-3f) r = rintf(x / scale);
+  return (int)fminf(fmaxf(r, -128.f), 127.f);
+}
+
 // one WARP per row, row kept in registers (H == 256 * VPL): no shared memory, no block barriers
 // kQuant: additionally emits the row-quantised INT8 copy of the OUTPUT row (the activation quantisation of int8_linear,
 // weight_loader.py:46-99: scale = max(|y|, 1e-10) / 127, q = clamp(round_half_even(y / scale))) — the row is already in registers,
@@ -97,14 +108,14 @@ __global__ void __launch_bounds__(256) rmsnorm_warp_kernel(__nv_bfloat16* __rest
 #pragma unroll
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const float scale = fmaxf(mx, 1e-10f) / 127.0f;
+    const float rscale = 1.0f / scale;
     if (lane == 0) q_scale[row] = scale;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       uint32_t o[2] = {0u, 0u};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float r = rintf(f[j][i] / scale);
-        const int qi = (int)fminf(fmaxf(r, -128.f), 127.f);
+        const int qi = quant_code_rhe(f[j][i], scale, rscale);
         o[i >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (i & 3));
       }
       *reinterpret_cast<uint2*>(q_out + row * H + (lane + 32 * j) * 8) = make_uint2(o[0], o[1]);
@@ -175,6 +186,7 @@ __global__ void __launch_bounds__(256) quant_rows_int8_kernel(const __nv_bfloat1
 #pragma unroll
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   const float scale = fmaxf(mx, 1e-10f) / 127.0f;
+  const float rscale = 1.0f / scale;
   if (lane == 0) {
     if (scale_f32) scale_f32[row] = scale;
     if (scale_bf16) scale_bf16[row] = __float2bfloat16_rn(scale);
@@ -185,8 +197,7 @@ __global__ void __launch_bounds__(256) quant_rows_int8_kernel(const __nv_bfloat1
     uint32_t o[2] = {0u, 0u};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float r = rintf(__bfloat162float(pa[i]) / scale);               // torch.round: half to even
-      const int qi = (int)fminf(fmaxf(r, -128.f), 127.f);
+      const int qi = quant_code_rhe(__bfloat162float(pa[i]), scale, rscale);   // torch.round: half to even
       o[i >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (i & 3));
     }
     *reinterpret_cast<uint2*>(q + row * K + v * 8) = make_uint2(o[0], o[1]);
@@ -241,14 +252,14 @@ __global__ void __launch_bounds__(256) silu_mul_quant_kernel(const __nv_bfloat16
 #pragma unroll
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   const float scale = fmaxf(mx, 1e-10f) / 127.0f;
+  const float rscale = 1.0f / scale;
   if (lane == 0) scale_f32[row] = scale;
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     uint32_t o[2] = {0u, 0u};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float r = rintf(f[j][i] / scale);
-      const int qi = (int)fminf(fmaxf(r, -128.f), 127.f);
+      const int qi = quant_code_rhe(f[j][i], scale, rscale);
       o[i >> 2] |= (uint32_t)(qi & 0xFF) << (8 * (i & 3));
     }
     *reinterpret_cast<uint2*>(q + row * N + (lane + 32 * j) * 8) = make_uint2(o[0], o[1]);

@@ -50,6 +50,14 @@ def fused_add_rmsnorm_q8(x: torch.Tensor, residual: torch.Tensor, weight_f32: to
     return q, qs
 
 
+def sum_slots(slots_ptr: int, world: int, rows: int, hidden: int, device: torch.device) -> torch.Tensor:
+    """bf16(sum over the `world` partial rows of every token) from a peer-filled receive buffer [rows][world][hidden] bf16."""
+    out = torch.empty((rows, hidden), dtype=torch.bfloat16, device=device)
+    capi.check(capi.load().kb2_sum_slots_bf16(slots_ptr, world, out.data_ptr(), rows, hidden, device.index or 0,
+                                              torch.cuda.current_stream(device).cuda_stream))
+    return out
+
+
 def quantize_to_int8(weight_bf16: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """weight_loader.py:25-43: per-row symmetric INT8; returns (int8 [N,K], scale bf16 [N])."""
     _chk_bf16(weight_bf16, "weight")

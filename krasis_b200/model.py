@@ -553,6 +553,9 @@ class KrasisModel:
         # expert-parallel reduce-scatter fused into the combine kernel over peer memory (KB2_FUSED_EP=0: NCCL reduce-scatter)
         self.fused_ep = os.environ.get("KB2_FUSED_EP", "1") != "0"
         self._ep_recv, self._ep_recv_rows = None, 0
+        # attention out_proj GEMM -> reduce-scatter fused the same way (KB2_FUSED_ATTN_RS=0: NCCL reduce-scatter)
+        self.fused_attn_rs = os.environ.get("KB2_FUSED_ATTN_RS", "1") != "0"
+        self._attn_recv, self._attn_recv_rows = None, 0
 
     # ------------------------------------------------------------------------------------------- real checkpoints
     @classmethod
@@ -726,13 +729,28 @@ class KrasisModel:
                 if R > 1:
                     with tm("attention_all_gather"):
                         hidden = self.comm.all_gather_rows(hidden)             # head-parallel attention sees every token
+                fused_rs = R > 1 and self.fused_attn_rs
+                if fused_rs:
+                    # GEMM -> reduce-scatter fused: the out_proj epilogue stores its rows into the token owners' receive buffers
+                    rows = M // R
+                    if self._attn_recv is None or self._attn_recv_rows != rows:
+                        nbytes = rows * R * cfg.hidden_size * 2
+                        self._attn_recv = [self.comm.peer_alloc(nbytes), self.comm.peer_alloc(nbytes)]
+                        self._attn_recv_rows = rows
+                    ptrs = self._attn_recv[i & 1]
+                    lay.attention.set_output_scatter(ptrs, self.rank)
                 if lay.layer_type == "linear_attention":
                     with tm("gdn_attention"):
                         attn = lay.attention.forward(hidden, is_decode=False)
                 else:
                     with tm("mla_attention" if lay.layer_type == "mla" else "gqa_attention"):
                         attn = lay.attention.forward(hidden, positions, self.kv_cache, st, self._kv_layer_offsets[i], num_new_tokens=M)
-                if R > 1:
+                if fused_rs:
+                    lay.attention.set_output_scatter(None)
+                    with tm("attention_reduce_scatter"):
+                        self.comm.barrier()
+                        attn = L.sum_slots(ptrs[self.rank], R, rows, cfg.hidden_size, self.device)
+                elif R > 1:
                     with tm("attention_reduce_scatter"):
                         attn = self.comm.reduce_scatter_rows(attn)             # sum of the partial o_proj outputs, this rank's rows
             h_q8 = None
