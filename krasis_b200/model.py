@@ -553,8 +553,11 @@ class KrasisModel:
         # expert-parallel reduce-scatter fused into the combine kernel over peer memory (KB2_FUSED_EP=0: NCCL reduce-scatter)
         self.fused_ep = os.environ.get("KB2_FUSED_EP", "1") != "0"
         self._ep_recv, self._ep_recv_rows = None, 0
-        # attention out_proj GEMM -> reduce-scatter fused the same way (KB2_FUSED_ATTN_RS=0: NCCL reduce-scatter)
-        self.fused_attn_rs = os.environ.get("KB2_FUSED_ATTN_RS", "1") != "0"
+        # attention out_proj GEMM -> reduce-scatter fused the same way: OFF by default.  Measured on 2 GPUs (profiles/r02s_*): the
+        # reduce-scatter itself drops from 3.1 to 2.2 ms per step, but the GEMM epilogue holds its TMEM accumulator while half of its
+        # rows cross NVLink (Gated DeltaNet 24.6 -> 28.0 ms, GQA 7.0 -> 8.2 ms): 67.0 ms per step against 63.7.  The combine kernel
+        # of the experts is HBM-bound elementwise work and hides the remote stores; a tensor-core epilogue does not.
+        self.fused_attn_rs = os.environ.get("KB2_FUSED_ATTN_RS", "0") == "1"
         self._attn_recv, self._attn_recv_rows = None, 0
 
     # ------------------------------------------------------------------------------------------- real checkpoints
