@@ -1097,6 +1097,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
       //   level 2  T[2:4][0:2] = T_hi (A_lo T_lo)                                           (32x32x32 products)
       for (int idx = tid; idx < 64 * (kPLdAT / 4); idx += 256) reinterpret_cast<float4*>(sT)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
       named_bar_sync(2, 256);
+      if (tid == 0) stamp(it, 11);
       if (tid < 64) {
         const int b = tid >> 4, cc = tid & 15;
         const float* Ab = sA + (16 * b) * kPLdAT + 16 * b;
@@ -1114,6 +1115,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         }
       }
       named_bar_sync(2, 256);
+      if (tid == 0) stamp(it, 12);
       {                                       // level 1, stage 1: P_p = A[2p+1][2p] D_2p ; stage 2: T[2p+1][2p] = D_2p+1 P_p
         const int pp = tid >> 7, r = (tid & 127) >> 3, c0 = (tid & 7) * 2;
         const float* Ar = sA + (32 * pp + 16 + r) * kPLdAT + 32 * pp;
@@ -1139,6 +1141,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         *reinterpret_cast<float2*>(sT + (32 * pp + 16 + r) * kPLdAT + 32 * pp + c0) = make_float2(out[0], out[1]);
       }
       named_bar_sync(2, 256);
+      if (tid == 0) stamp(it, 13);
       {                                       // level 2: P = A[32:64][0:32] T[0:32][0:32] ; T[32:64][0:32] = T[32:64][32:64] P
         const int r = tid >> 3, c0 = (tid & 7) * 4;
         const float* Ar = sA + (32 + r) * kPLdAT;

@@ -49,7 +49,7 @@ print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
 
 # ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,
 # 3 MMA-B/C issued; core thread 0: 4 gates scanned, 5 k.k^T seen, 6 A^T built, 7 T solved, 8 images written, 9 vcorr/kcd products seen,
-# 10 outputs stored)
+# 10 outputs stored; version 2 only: 11 T zeroed, 12 diagonal 16x16 blocks inverted, 13 level 1 done)
 for mode, version in (("1", "1"), ("0", "1"), ("0", "2")):
     os.environ["KB2_GDN_PREPARE_MMA_SYNC"] = mode
     os.environ["KB2_GDN_PREPARE_VERSION"] = version
@@ -71,7 +71,7 @@ for mode, version in (("1", "1"), ("0", "1"), ("0", "2")):
     lay.forward(x)
     torch.cuda.synchronize()
     del os.environ["KB2_GDN_PREPARE_TRACE"]
-    t = trace.cpu().view(8, 16)[:, :11]
+    t = trace.cpu().view(8, 16)[:, :14]
     print("  prepare timeline (cycles since inputs landed), loop iterations 2..9:")
     for r in (t - t[:, 0:1]).tolist()[:4]:
         print("   ", r)
