@@ -25,6 +25,7 @@
 
 #include <cstdlib>
 
+#include "mma_sync.cuh"
 #include "moe_common.cuh"
 #include "ptx.cuh"
 
@@ -1116,54 +1117,45 @@ __global__ void __launch_bounds__(kT3Threads, 1)
       }
       named_bar_sync(2, 256);
       if (tid == 0) stamp(it, 12);
-      {                                       // level 1, stage 1: P_p = A[2p+1][2p] D_2p ; stage 2: T[2p+1][2p] = D_2p+1 P_p
-        const int pp = tid >> 7, r = (tid & 127) >> 3, c0 = (tid & 7) * 2;
-        const float* Ar = sA + (32 * pp + 16 + r) * kPLdAT + 32 * pp;
-        const float* Dl = sT + (32 * pp) * kPLdAT + 32 * pp + c0;
-        float acc[2] = {0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float av = Ar[k];
-          const float2 dv = *reinterpret_cast<const float2*>(Dl + k * kPLdAT);
-          acc[0] = fmaf(av, dv.x, acc[0]); acc[1] = fmaf(av, dv.y, acc[1]);
+      // levels 1 and 2 are small dense products: 16x8 output tiles on mma.sync m16n8k8 with 3xTF32 operands (fp32-grade; the CUDA-core
+      // dot products they replace took 770 + 2700 of the unit's 10.7 K cycles, profiles/r02t_gdn_prepare_inverse_phases.txt)
+      const int fg = lane >> 2, ft = lane & 3;                              // accumulator fragment: rows fg, fg + 8; columns 2 ft, 2 ft + 1
+      {                                       // level 1, stage 1: P_p = A[2p+1][2p] D_2p ; stage 2: T[2p+1][2p] = D_2p+1 P_p   (16x16x16)
+        const int pp = warp >> 1, ct = warp & 1;                            // warps 0-3: pair pp, 8-column tile ct
+        float c1[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+        if (warp < 4) {
+          warp_mma_tiles<1, true, true>(c1, sA + (32 * pp + 16) * kPLdAT + 32 * pp, kPLdAT, 1, sT + (32 * pp) * kPLdAT + 32 * pp + 8 * ct, kPLdAT, 1,
+                                        0, 16);
+          float* pd = sP + (16 * pp) * kPLdP + 8 * ct + 2 * ft;
+          *reinterpret_cast<float2*>(pd + fg * kPLdP) = make_float2(c1[0][0], c1[0][1]);
+          *reinterpret_cast<float2*>(pd + (fg + 8) * kPLdP) = make_float2(c1[0][2], c1[0][3]);
         }
-        *reinterpret_cast<float2*>(sP + (16 * pp + r) * kPLdP + c0) = make_float2(acc[0], acc[1]);
         named_bar_sync(2, 256);
-        const float* Dr = sT + (32 * pp + 16 + r) * kPLdAT + 32 * pp + 16;
-        float out[2] = {0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float dv = Dr[k];
-          const float2 pv = *reinterpret_cast<const float2*>(sP + (16 * pp + k) * kPLdP + c0);
-          out[0] = fmaf(dv, pv.x, out[0]); out[1] = fmaf(dv, pv.y, out[1]);
+        float c2[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+        if (warp < 4)
+          warp_mma_tiles<1, true, true>(c2, sT + (32 * pp + 16) * kPLdAT + 32 * pp + 16, kPLdAT, 1, sP + (16 * pp) * kPLdP + 8 * ct, kPLdP, 1, 0, 16);
+        named_bar_sync(2, 256);               // every warp has read D / P before T[2p+1][2p] is written next to D
+        if (warp < 4) {
+          float* td = sT + (32 * pp + 16) * kPLdAT + 32 * pp + 8 * ct + 2 * ft;
+          *reinterpret_cast<float2*>(td + fg * kPLdAT) = make_float2(c2[0][0], c2[0][1]);
+          *reinterpret_cast<float2*>(td + (fg + 8) * kPLdAT) = make_float2(c2[0][2], c2[0][3]);
         }
-        named_bar_sync(2, 256);               // every thread has read D / P before T[2p+1][2p] is written next to D
-        *reinterpret_cast<float2*>(sT + (32 * pp + 16 + r) * kPLdAT + 32 * pp + c0) = make_float2(out[0], out[1]);
       }
       named_bar_sync(2, 256);
       if (tid == 0) stamp(it, 13);
-      {                                       // level 2: P = A[32:64][0:32] T[0:32][0:32] ; T[32:64][0:32] = T[32:64][32:64] P
-        const int r = tid >> 3, c0 = (tid & 7) * 4;
-        const float* Ar = sA + (32 + r) * kPLdAT;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-          const float av = Ar[k];
-          const float4 t0 = *reinterpret_cast<const float4*>(sT + k * kPLdAT + c0);
-          acc[0] = fmaf(av, t0.x, acc[0]); acc[1] = fmaf(av, t0.y, acc[1]); acc[2] = fmaf(av, t0.z, acc[2]); acc[3] = fmaf(av, t0.w, acc[3]);
-        }
-        *reinterpret_cast<float4*>(sP + r * kPLdP + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      {                                       // level 2: P = A[32:64][0:32] T[0:32][0:32] ; T[32:64][0:32] = T[32:64][32:64] P   (32x32x32)
+        const int rt = warp >> 2, ct = warp & 3;                            // 8 warps = 2 x 4 output tiles of 16 x 8
+        float c1[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+        warp_mma_tiles<1, true, true>(c1, sA + (32 + 16 * rt) * kPLdAT, kPLdAT, 1, sT + 8 * ct, kPLdAT, 1, 0, 32);
+        float* pd = sP + (16 * rt) * kPLdP + 8 * ct + 2 * ft;
+        *reinterpret_cast<float2*>(pd + fg * kPLdP) = make_float2(c1[0][0], c1[0][1]);
+        *reinterpret_cast<float2*>(pd + (fg + 8) * kPLdP) = make_float2(c1[0][2], c1[0][3]);
         named_bar_sync(2, 256);
-        const float* Tr = sT + (32 + r) * kPLdAT + 32;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-          const float tv = Tr[k];
-          const float4 p0 = *reinterpret_cast<const float4*>(sP + k * kPLdP + c0);
-          acc[0] = fmaf(tv, p0.x, acc[0]); acc[1] = fmaf(tv, p0.y, acc[1]); acc[2] = fmaf(tv, p0.z, acc[2]); acc[3] = fmaf(tv, p0.w, acc[3]);
-        }
-        *reinterpret_cast<float4*>(sT + (32 + r) * kPLdAT + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        float c2[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+        warp_mma_tiles<1, true, true>(c2, sT + (32 + 16 * rt) * kPLdAT + 32, kPLdAT, 1, sP + 8 * ct, kPLdP, 1, 0, 32);
+        float* td = sT + (32 + 16 * rt) * kPLdAT + 8 * ct + 2 * ft;
+        *reinterpret_cast<float2*>(td + fg * kPLdAT) = make_float2(c2[0][0], c2[0][1]);
+        *reinterpret_cast<float2*>(td + (fg + 8) * kPLdAT) = make_float2(c2[0][2], c2[0][3]);
       }
       named_bar_sync(2, 256);
       if (tid == 0) stamp(it, 7);
