@@ -340,7 +340,14 @@ def run_full_model(args):
     tok = tok_host.to(dev)
     logits_host = torch.empty((1, cfg.vocab_size), dtype=torch.float32).pin_memory()
 
+    use_graph = not args.no_graph
+
     def step():
+        if use_graph:
+            return model.forward_graphed(tok, pos)        # captured on the first warm-up step; eager fallback inside
+        return model.forward(tok, pos, model.new_sequence())
+
+    def eager_step():
         return model.forward(tok, pos, model.new_sequence())
 
     def barrier():
@@ -362,6 +369,7 @@ def run_full_model(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    graphed = use_graph and model._graphs.get(M) not in (None, False)
     l0 = capi.total_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -371,7 +379,7 @@ def run_full_model(args):
     ev1.record()
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = capi.total_launches() - l0
+    launches = capi.total_launches() - l0          # 0 when the steps were graph replays: counted from the eager profiled pass below
     clocks = sampler.stop() if sampler else None
     ms_per_step = ms / args.steps
     value = M / (ms_per_step * 1e-3)
@@ -379,7 +387,7 @@ def run_full_model(args):
     # ---- end to end: pinned host token ids -> device, forward, last-token logits -> pinned host, every step
     def e2e_step():
         tk = tok_host.to(dev, non_blocking=True)
-        lg = model.forward(tk, pos, model.new_sequence())
+        lg = model.forward_graphed(tk, pos) if use_graph else model.forward(tk, pos, model.new_sequence())
         logits_host.copy_(lg, non_blocking=True)
         torch.cuda.synchronize()
     for _ in range(2):
@@ -391,15 +399,20 @@ def run_full_model(args):
     barrier()
     dt = max_over_ranks((time.perf_counter() - t0) / args.steps)
     e2e = {"value": M / dt, "unit": "tokens/s", "h2d_bytes_per_step": M * 4, "d2h_bytes_per_step": cfg.vocab_size * 4,
-           "ms_per_step": dt * 1e3, "entry": "KrasisModel.forward(token_ids, positions, seq_states): pinned host token ids in, last-token logits out"}
+           "ms_per_step": dt * 1e3,
+           "entry": ("KrasisModel.forward_graphed(token_ids, positions): pinned host token ids in, CUDA-graph replay of the prefill step, last-token logits out"
+                     if graphed else "KrasisModel.forward(token_ids, positions, seq_states): pinned host token ids in, last-token logits out")}
 
     # ---- separate profiled pass (not part of `value`): CUDA events around every kernel launch + per-component spans
     prof_steps = max(1, min(2, args.steps))
     capi.kernel_profile(True)
     model.timing_start()
     barrier()
+    l1 = capi.total_launches()
     for _ in range(prof_steps):
-        step()
+        eager_step()
+    if graphed:
+        launches = (capi.total_launches() - l1) // prof_steps * args.steps      # a replay launches exactly what the captured eager step did
     kprof = {n: (t / prof_steps, c // prof_steps) for n, (t, c) in capi.kernel_profile_collect().items()}
     comp = {kk: v / prof_steps for kk, v in model.timing_collect().items()}
     capi.kernel_profile(False)
@@ -451,7 +464,7 @@ def run_full_model(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int4 experts x bf16 activations (fp32 acc), bf16 attention, fp8 KV, int8 shared expert / lm_head",
             "data": "synthetic", "config": workload_config(args, cfg, world), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_b}
+            "gpu_launches": int(launches), "cuda_graph": bool(graphed), "roofline": roofline, "cpu_baseline": cpu_b}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -469,6 +482,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying the captured step")
     ap.add_argument("--cpu-format", default="int4", choices=["int4", "gguf"],
                     help="CPU arm: int4 = moe_forward_unified on INT4 g128 (default); gguf = moe_forward_gguf on native Q4_K/Q8_0 blocks "
                          "(BASELINE configs[0]: --config v2lite --impl reference --cpu-format gguf --tokens 2048)")

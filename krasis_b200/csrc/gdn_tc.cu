@@ -103,6 +103,13 @@ __device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned
   lo = (unsigned short)l;
 }
 
+// two values that are K-neighbours in an operand image: hi / lo words {low half = element 0, high half = element 1} with one packed
+// conversion each (6 instructions per pair instead of 2 x 4 + 2 packs)
+__device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = bf16x2_bits_rn(x1, x0);
+  lo2 = bf16x2_bits_rn(x1 - __uint_as_float(hi2 & 0xFFFF0000u), x0 - __uint_as_float(hi2 << 16));
+}
+
 struct GdnTcParams {
   const uint8_t* kcd_img;    // [nv][n_chunks][hi c0 | hi c1 | lo c0 | lo c1] 8 KB each
   const uint8_t* intra_img;  // [nv][n_chunks][hi | lo] 8 KB each
@@ -1071,11 +1078,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
             const float d0 = exp_fast_nobranch(g_i - sg[j]), d1 = exp_fast_nobranch(g_i - sg[j + 1]);
             const float v0 = j <= i ? __uint_as_float(a[q8 * 8 + 2 * e]) * d0 : 0.f;
             const float v1 = j + 1 <= i ? __uint_as_float(a[q8 * 8 + 2 * e + 1]) * d1 : 0.f;
-            unsigned short h0, l0, h1, l1;
-            split_bf16(v0, h0, l0);
-            split_bf16(v1, h1, l1);
-            hw[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            lw[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            split_bf16_pair(v0, v1, hw[e], lw[e]);
           }
           const int chunk = ((part * 4 + q8) ^ (i & 7)) << 4;
           *reinterpret_cast<uint4*>(img + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -1173,15 +1176,8 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = qr * 16 + q8 * 8 + 2 * e;
-            unsigned short a0, b0, a1, b1;
-            split_bf16(tx[2 * e] * sbeta[j], a0, b0);
-            split_bf16(tx[2 * e + 1] * sbeta[j + 1], a1, b1);
-            h1[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
-            l1[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
-            split_bf16(tx[2 * e] * secol[j], a0, b0);
-            split_bf16(tx[2 * e + 1] * secol[j + 1], a1, b1);
-            h2[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
-            l2[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
+            split_bf16_pair(tx[2 * e] * sbeta[j], tx[2 * e + 1] * sbeta[j + 1], h1[e], l1[e]);
+            split_bf16_pair(tx[2 * e] * secol[j], tx[2 * e + 1] * secol[j + 1], h2[e], l2[e]);
           }
           const int chunk = ((qr * 2 + q8) ^ (c & 7)) << 4;
           *reinterpret_cast<uint4*>(ih + chunk) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
@@ -1232,11 +1228,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int jj = q8 * 8 + 2 * e;
-              unsigned short h0, l0, h1, l1;
-              split_bf16(__uint_as_float(a[jj]), h0, l0);
-              split_bf16(__uint_as_float(a[jj + 1]), h1, l1);
-              hw[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              lw[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+              split_bf16_pair(__uint_as_float(a[jj]), __uint_as_float(a[jj + 1]), hw[e], lw[e]);
             }
             const int k8 = q * 4 + q8;          // 8-element group along dk: chunk c = k8 / 8, 16-byte slot k8 % 8
             const int off = (k8 >> 3) * 8192 + (((k8 & 7) ^ (i & 7)) << 4);

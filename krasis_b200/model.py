@@ -553,6 +553,7 @@ class KrasisModel:
         # expert-parallel reduce-scatter fused into the combine kernel over peer memory (KB2_FUSED_EP=0: NCCL reduce-scatter)
         self.fused_ep = os.environ.get("KB2_FUSED_EP", "1") != "0"
         self._ep_recv, self._ep_recv_rows = None, 0
+        self._graphs = {}
         # attention out_proj GEMM -> reduce-scatter fused the same way: OFF by default.  Measured on 2 GPUs (profiles/r02s_*): the
         # reduce-scatter itself drops from 3.1 to 2.2 ms per step, but the GEMM epilogue holds its TMEM accumulator while half of its
         # rows cross NVLink (Gated DeltaNet 24.6 -> 28.0 ms, GQA 7.0 -> 8.2 ms): 67.0 ms per step against 63.7.  The combine kernel
@@ -781,6 +782,62 @@ class KrasisModel:
             if R > 1:
                 self.comm.broadcast(out, root=R - 1)
         return out
+
+    # ---- fixed-shape prefill replayed from a CUDA graph
+    def forward_graphed(self, token_ids: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        """One prefill of a FRESH sequence of token_ids.shape[0] tokens, replayed from a CUDA graph (captured on first use per length;
+        token ids and positions are copied into static buffers).  A whole-model step is ~110 kernel launches per layer: at one GPU the
+        device is the bottleneck, but with token sharding over N GPUs every kernel shrinks and the Python / ctypes launch path becomes
+        it.  Everything the step launches — our kernels through the C ABI, the NCCL collectives, the row gather of the embedding — is
+        stream-ordered on torch's current stream, so the step captures as is.  Falls back to the eager path if capture fails."""
+        M = token_ids.shape[0]
+        ent = self._graphs.get(M)
+        if ent is None:
+            ent = self._capture_graph(token_ids, positions)
+            self._graphs[M] = ent
+        if ent is False:
+            return self.forward(token_ids, positions, self.new_sequence())
+        graph, st_tok, st_pos, out, seq = ent
+        st_tok.copy_(token_ids, non_blocking=True)
+        st_pos.copy_(positions, non_blocking=True)
+        graph.replay()
+        seq[0].seq_len = M                       # host-side bookkeeping of what the replay did on the device
+        return out
+
+    def _capture_graph(self, token_ids, positions):
+        M = token_ids.shape[0]
+        try:
+            st_tok, st_pos = token_ids.clone(), positions.clone()
+            seq = self.new_sequence()
+            seq[0].ensure_capacity(M)
+            seq[0].kv_indices(self.device)       # page table on the device before capture (host -> device copies cannot be captured)
+
+            def fresh_step():
+                seq[0].seq_len = 0
+                for lay in self.layers:
+                    if lay.layer_type == "linear_attention":
+                        lay.attention.reset_state()
+                return self.forward(st_tok, st_pos, seq)
+
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):        # warm-up off the default stream: lazy allocations (peer buffers, scratch) happen here
+                for _ in range(2):
+                    fresh_step()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fresh_step()
+            return (graph, st_tok, st_pos, out, seq)
+        except Exception as exc:                 # noqa: BLE001 — any capture problem means "use the eager path", never a wrong result
+            import warnings
+            warnings.warn(f"CUDA graph capture of the prefill step failed ({exc}); using eager launches")
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception:                    # noqa: BLE001
+                pass
+            return False
 
     # ---- optional per-component device timing (the reference's KRASIS_LAYER_TIMING, model.py:2832,3355-3373)
     class _Span:

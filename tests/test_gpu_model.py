@@ -80,3 +80,24 @@ def test_small_hybrid_model_prefill_matches_oracle():
     top_ok = want.gather(1, all_logits.argmax(1)[:, None]).squeeze(1) >= want.max(1).values - 4 * 2 ** -8 * want.abs().max(1).values
     assert (cos_all >= 0.995).float().mean().item() > 0.9 and top_ok.float().mean().item() > 0.9
     assert cos_all.median().item() >= 0.999
+
+
+def test_graph_replayed_prefill_is_bit_identical_to_eager_launches():
+    """KrasisModel.forward_graphed replays the whole prefill step from a CUDA graph (same kernels, same order, static input
+    buffers): logits must equal the eager path bit for bit, for the captured inputs and for different token ids replayed later."""
+    from krasis_b200.model import HybridMoEConfig, KrasisModel
+    cfg = HybridMoEConfig(hidden_size=256, num_hidden_layers=4, full_attention_interval=4, vocab_size=512,
+                          n_routed_experts=8, num_experts_per_tok=2, moe_intermediate_size=128,
+                          shared_expert_intermediate_size=128, num_attention_heads=4, num_key_value_heads=2,
+                          gqa_head_dim=128, partial_rotary_factor=0.5, rope_theta=10000.0,
+                          linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=32, linear_value_head_dim=32)
+    M = 192
+    model = KrasisModel(cfg, device=0, max_tokens=M)
+    g = torch.Generator().manual_seed(3)
+    pos = torch.arange(M).cuda()
+    for trial in range(3):
+        tok = torch.randint(0, cfg.vocab_size, (M,), generator=g).cuda()
+        eager = model.forward(tok, pos, model.new_sequence()).clone()
+        replay = model.forward_graphed(tok, pos).clone()
+        assert model._graphs.get(M) not in (None, False), "capture fell back to eager launches"
+        assert torch.equal(eager, replay), f"trial {trial}"
