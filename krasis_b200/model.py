@@ -586,7 +586,8 @@ class KrasisModel:
     # ------------------------------------------------------------------------------------------- sequences / KV cache
     def _make_kv_cache(self):
         n_full = sum(t != "linear_attention" for t in self.layer_types)
-        pages = (self.max_tokens + 15) // 16 + 1
+        # two sequences' worth of pages: the live request plus the sequence a captured CUDA graph keeps for its replays (forward_graphed)
+        pages = 2 * ((self.max_tokens + 15) // 16 + 1)
         if self.cfg.is_mla:
             self.kv_cache = MLAPagedKVCache(max(n_full, 1), self.cfg.kv_lora_rank, self.cfg.qk_rope_head_dim, self.device, max_pages=pages)
         else:
@@ -808,7 +809,10 @@ class KrasisModel:
         M = token_ids.shape[0]
         try:
             st_tok, st_pos = token_ids.clone(), positions.clone()
-            seq = self.new_sequence()
+            if not hasattr(self, "kv_cache"):
+                self._make_kv_cache()
+            # the graph owns this sequence: its page table is baked into the captured launches, so it is never recycled by new_sequence()
+            seq = [SequenceKVState(self.kv_cache)]
             seq[0].ensure_capacity(M)
             seq[0].kv_indices(self.device)       # page table on the device before capture (host -> device copies cannot be captured)
 
