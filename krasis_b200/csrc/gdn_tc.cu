@@ -36,8 +36,6 @@ cudaError_t make_tmap_bf16_rows(void* out_tmap, const void* base, long long rows
 constexpr int kTC = 64;            // chunk length (linear_attention.py:702)
 constexpr int kTSV = 32;           // dv slice per CTA
 constexpr int kTD = 128;           // dk == dv
-constexpr int kTThreads = 192;
-constexpr int kDefaultPrepareVersion = 2;
 constexpr int kVcLd = 36;          // padded row of the vcorr slice (floats): conflict-free float4 rows
 
 // per-stage byte offsets
@@ -497,399 +495,14 @@ struct GdnPrepParams {
   int M, n_chunks, nv, nk;
 };
 
-__global__ void __launch_bounds__(kTThreads, 1)
-    gdn_prepare_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                          const __grid_constant__ CUtensorMap tmap_v, GdnPrepParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPOffBar);
-  uint64_t* full = bars;           // [2]
-  uint64_t* empty = bars + 2;      // [2]
-  uint64_t* a_done = bars + 4;
-  uint64_t* img_ready = bars + 5;
-  uint64_t* bc_done = bars + 6;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
-  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role branches
-  const int n_units = p.nv * p.n_chunks, r = p.nv / p.nk;
-  if (tid == 0) {
-    if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
-    mbar_init(a_done, 1);
-    mbar_init(img_ready, 128);
-    mbar_init(bc_done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 4) tmem_alloc(tmem_ptr_smem, 512);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColA = 0, kColB = 128, kColC = 256;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
-  auto stamp = [&](int it, int slot) {
-    if (tracing && it >= 2 && it < 10 && (tid & 31) == 0) p.trace[(it - 2) * 16 + slot] = clock64();
-  };
-
-  if (warp == 4) {
-    {
-      if (elect_one()) { prefetch_tmap(&tmap_q); prefetch_tmap(&tmap_k); prefetch_tmap(&tmap_v); }
-      int it = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-        const int h = u / p.n_chunks, ch = u % p.n_chunks, kh = h / r;
-        uint8_t* sb = smem + st * kPStage;
-        mbar_wait(&empty[st], ph ^ 1u);
-        if (elect_one()) {
-        mbar_arrive_expect_tx(&full[st], kPStage);
-        tma_load_2d(sb, &tmap_k, kh * kTD, ch * kTC, &full[st]);
-        tma_load_2d(sb + 8192, &tmap_q, kh * kTD, ch * kTC, &full[st]);
-        tma_load_2d(sb + 16384, &tmap_k, kh * kTD + 64, ch * kTC, &full[st]);
-        tma_load_2d(sb + 24576, &tmap_q, kh * kTD + 64, ch * kTC, &full[st]);
-        tma_load_2d(sb + kPOffV, &tmap_v, h * kTD, ch * kTC, &full[st]);
-        tma_load_2d(sb + kPOffV + 8192, &tmap_v, h * kTD + 64, ch * kTC, &full[st]);
-        }
-        __syncwarp();
-      }
-    }
-    __syncwarp();
-  } else if (warp == 5) {
-    {
-      const uint32_t id_a = umma_idesc_bf16_m128(64);                       // A, B K-major, N = 64
-      const uint32_t id_bc = umma_idesc_bf16_m128(128) | (1u << 16);        // B MN-major, N = 128
-      const uint32_t img1 = smem_u32(smem + kPOffImg1), img2 = smem_u32(smem + kPOffImg2);
-      int it = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (uint32_t)(it >> 1) & 1u, up = (uint32_t)it & 1u;
-        const uint32_t sb = smem_u32(smem + st * kPStage);
-        mbar_wait(&full[st], ph);
-        tc_fence_after_sync();
-        stamp(it, 0);
-        if (elect_one()) {
-#pragma unroll
-        for (int chn = 0; chn < 2; ++chn) {
-          const uint64_t ad = umma_desc_k_sw128(sb + chn * 16384);          // rows 0-63 k, rows 64-127 q
-          const uint64_t bd = umma_desc_k_sw128(sb + chn * 16384);          // N = 64: the k rows only
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_bf16(tmem_base + kColA, ad + 2 * ks, bd + 2 * ks, id_a, (chn > 0 || ks > 0) ? 1u : 0u);
-        }
-        umma_commit(a_done);
-        }
-        __syncwarp();
-        stamp(it, 1);
-        mbar_wait(img_ready, up);
-        tc_fence_after_sync();
-        stamp(it, 2);
-        if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t a1 = umma_desc_k_sw128(img1) + 2 * ks, a2 = umma_desc_k_sw128(img2) + 2 * ks;
-          umma_bf16(tmem_base + kColB, a1, tc_desc_mn_sw128(sb + kPOffV + ks * 2048, 8192, 1024), id_bc, ks > 0 ? 1u : 0u);
-          umma_bf16(tmem_base + kColC, a2, tc_desc_mn_sw128(sb + ks * 2048, 16384, 1024), id_bc, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(bc_done);
-        umma_commit(&empty[st]);
-        }
-        __syncwarp();
-        stamp(it, 3);
-      }
-    }
-    __syncwarp();
-  } else {
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int i = tid & 63, lane = tid & 31;
-    float* sA = reinterpret_cast<float*>(smem + kPOffA);
-    float* sT = reinterpret_cast<float*>(smem + kPOffT);
-    float* sP = reinterpret_cast<float*>(smem + kPOffP);
-    float* sXB = reinterpret_cast<float*>(smem + kPOffXB);
-    float* sXC = reinterpret_cast<float*>(smem + kPOffXC);
-    float* sg = reinterpret_cast<float*>(smem + kPOffSc);
-    float* sbeta = sg + 64;
-    float* secol = sg + 128;
-    float* sscan = sg + 192;
-    auto load_gate = [&](int u, float& b, float& gg) {
-      b = 0.f; gg = 0.f;
-      if (u < n_units && tid < 64) {
-        const int h = u / p.n_chunks, t = (u % p.n_chunks) * kTC + i;
-        if (t < p.M) { b = p.beta[(long long)t * p.nv + h]; gg = p.g[(long long)t * p.nv + h]; }
-      }
-    };
-    float b_nxt, g_nxt;
-    load_gate(blockIdx.x, b_nxt, g_nxt);
-    int it = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
-      const int st = it & 1;
-      const uint32_t up = (uint32_t)it & 1u;
-      const int h = u / p.n_chunks, ch = u % p.n_chunks;
-      const long long hc = (long long)h * p.n_chunks + ch;
-      const float b_i = b_nxt, g_in = g_nxt;
-      load_gate(u + gridDim.x, b_nxt, g_nxt);                      // next unit's gates are in flight during this one
-      // inclusive scan of g over the 64 tokens (warps 0, 1)
-      float gc = g_in;
-      if (tid < 64) {
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const float v = __shfl_up_sync(0xffffffffu, gc, o);
-          if (lane >= o) gc += v;
-        }
-        if (tid == 31) sscan[0] = gc;
-      }
-      named_bar_sync(2, 128);
-      if (tid >= 32 && tid < 64) gc += sscan[0];
-      if (tid < 64) {
-        sg[i] = gc;
-        sbeta[i] = b_i;
-        secol[i] = b_i * expf(gc);
-      }
-      named_bar_sync(2, 128);
-      if (tid == 0) stamp(it, 4);
-      mbar_wait(a_done, up);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(it, 5);
-      const float g_i = sg[i];
-      if (tid < 64) {                         // k k^T row i  ->  A^T
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t a[32];
-          tmem_ld32(lane_addr + kColA + half * 32, a);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = half * 32 + 4 * j4 + e;
-              v[e] = j < i ? -(__uint_as_float(a[4 * j4 + e]) * b_i) * __expf(g_i - sg[j]) : 0.f;
-            }
-            *reinterpret_cast<float4*>(sA + i * kPLdAT + half * 32 + 4 * j4) = make_float4(v[0], v[1], v[2], v[3]);
-          }
-        }
-      } else {                                // q k^T row i  ->  intra hi/lo images (global)
-        uint8_t* img = p.intra_img + hc * 16384 + i * 128;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t a[32];
-          tmem_ld32(lane_addr + kColA + half * 32, a);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = half * 32 + q8 * 8 + 2 * e;
-              const float v0 = j <= i ? __uint_as_float(a[q8 * 8 + 2 * e]) * __expf(g_i - sg[j]) : 0.f;
-              const float v1 = j + 1 <= i ? __uint_as_float(a[q8 * 8 + 2 * e + 1]) * __expf(g_i - sg[j + 1]) : 0.f;
-              unsigned short h0, l0, h1, l1;
-              split_bf16(v0, h0, l0);
-              split_bf16(v1, h1, l1);
-              hw[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              lw[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-            }
-            const int chunk = ((half * 4 + q8) ^ (i & 7)) << 4;
-            *reinterpret_cast<uint4*>(img + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(img + 8192 + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        }
-      }
-      tc_fence_before_sync();
-      named_bar_sync(2, 128);                 // A^T complete; D_A fully read
-      if (tid == 0) stamp(it, 6);
-      // ---- T = (I - A)^-1 for the unit-lower-triangular 64x64 system, blocked 16 -> 32 -> 64, all 128 threads, fp32:
-      //   level 0  the four diagonal blocks D_b = (I - A_bb)^-1 by forward substitution (thread = one column of one block)
-      //   level 1  T[1][0] = D_1 (A_10 D_0),  T[3][2] = D_3 (A_32 D_2)                      (16x16x16 products)
-      //   level 2  T[2:4][0:2] = T_hi (A_lo T_lo)                                           (32x32x32 products)
-      for (int idx = tid; idx < 64 * (kPLdAT / 4); idx += 128) reinterpret_cast<float4*>(sT)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-      named_bar_sync(2, 128);
-      if (tid < 64) {
-        const int b = tid >> 4, cc = tid & 15;
-        const float* Ab = sA + (16 * b) * kPLdAT + 16 * b;
-        float x[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          float a0 = (r == cc) ? 1.f : 0.f, a1 = 0.f;
-#pragma unroll
-          for (int j = 0; j < r; ++j) {
-            if (j & 1) a1 = fmaf(Ab[r * kPLdAT + j], x[j], a1);
-            else a0 = fmaf(Ab[r * kPLdAT + j], x[j], a0);
-          }
-          x[r] = a0 + a1;
-          sT[(16 * b + r) * kPLdAT + 16 * b + cc] = x[r];
-        }
-      }
-      named_bar_sync(2, 128);
-      {                                       // level 1, stage 1: P_p = A[2p+1][2p] D_2p ; stage 2: T[2p+1][2p] = D_2p+1 P_p
-        const int pp = tid >> 6, r = (tid & 63) >> 2, c0 = (tid & 3) * 4;
-        const float* Ar = sA + (32 * pp + 16 + r) * kPLdAT + 32 * pp;
-        const float* Dl = sT + (32 * pp) * kPLdAT + 32 * pp + c0;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float av = Ar[k];
-          const float4 dv = *reinterpret_cast<const float4*>(Dl + k * kPLdAT);
-          acc[0] = fmaf(av, dv.x, acc[0]); acc[1] = fmaf(av, dv.y, acc[1]); acc[2] = fmaf(av, dv.z, acc[2]); acc[3] = fmaf(av, dv.w, acc[3]);
-        }
-        *reinterpret_cast<float4*>(sP + (16 * pp + r) * kPLdP + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        named_bar_sync(2, 128);
-        const float* Dr = sT + (32 * pp + 16 + r) * kPLdAT + 32 * pp + 16;
-        float out[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float dv = Dr[k];
-          const float4 pv = *reinterpret_cast<const float4*>(sP + (16 * pp + k) * kPLdP + c0);
-          out[0] = fmaf(dv, pv.x, out[0]); out[1] = fmaf(dv, pv.y, out[1]); out[2] = fmaf(dv, pv.z, out[2]); out[3] = fmaf(dv, pv.w, out[3]);
-        }
-        named_bar_sync(2, 128);               // every thread has read D / P before T[2p+1][2p] is written next to D
-        *reinterpret_cast<float4*>(sT + (32 * pp + 16 + r) * kPLdAT + 32 * pp + c0) = make_float4(out[0], out[1], out[2], out[3]);
-      }
-      named_bar_sync(2, 128);
-      {                                       // level 2: P = A[32:64][0:32] T[0:32][0:32] ; T[32:64][0:32] = T[32:64][32:64] P
-        const int r = tid >> 2, c0 = (tid & 3) * 8;
-        const float* Ar = sA + (32 + r) * kPLdAT;
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-          const float av = Ar[k];
-          const float4 t0 = *reinterpret_cast<const float4*>(sT + k * kPLdAT + c0), t1 = *reinterpret_cast<const float4*>(sT + k * kPLdAT + c0 + 4);
-          acc[0] = fmaf(av, t0.x, acc[0]); acc[1] = fmaf(av, t0.y, acc[1]); acc[2] = fmaf(av, t0.z, acc[2]); acc[3] = fmaf(av, t0.w, acc[3]);
-          acc[4] = fmaf(av, t1.x, acc[4]); acc[5] = fmaf(av, t1.y, acc[5]); acc[6] = fmaf(av, t1.z, acc[6]); acc[7] = fmaf(av, t1.w, acc[7]);
-        }
-        *reinterpret_cast<float4*>(sP + r * kPLdP + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(sP + r * kPLdP + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        named_bar_sync(2, 128);
-        const float* Tr = sT + (32 + r) * kPLdAT + 32;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-          const float tv = Tr[k];
-          const float4 p0 = *reinterpret_cast<const float4*>(sP + k * kPLdP + c0), p1 = *reinterpret_cast<const float4*>(sP + k * kPLdP + c0 + 4);
-          acc[0] = fmaf(tv, p0.x, acc[0]); acc[1] = fmaf(tv, p0.y, acc[1]); acc[2] = fmaf(tv, p0.z, acc[2]); acc[3] = fmaf(tv, p0.w, acc[3]);
-          acc[4] = fmaf(tv, p1.x, acc[4]); acc[5] = fmaf(tv, p1.y, acc[5]); acc[6] = fmaf(tv, p1.z, acc[6]); acc[7] = fmaf(tv, p1.w, acc[7]);
-        }
-        *reinterpret_cast<float4*>(sT + (32 + r) * kPLdAT + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(sT + (32 + r) * kPLdAT + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-      }
-      named_bar_sync(2, 128);
-      if (tid == 0) stamp(it, 7);
-      {
-        // T' = T diag(beta), T'' = T diag(beta e^gcum) as hi/lo K-major SW128 rows: thread (row c = tid & 63, column half tid >> 6)
-        const int c = tid & 63, hf = tid >> 6;
-        const float* trow = sT + c * kPLdAT + hf * 32;
-        uint8_t* i1 = smem + kPOffImg1 + c * 128;
-        uint8_t* i2 = smem + kPOffImg2 + c * 128;
-#pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-          const float4 ta = *reinterpret_cast<const float4*>(trow + q8 * 8), tb = *reinterpret_cast<const float4*>(trow + q8 * 8 + 4);
-          const float tx[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-          uint32_t h1[4], l1[4], h2[4], l2[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = hf * 32 + q8 * 8 + 2 * e;
-            unsigned short a0, b0, a1, b1;
-            split_bf16(tx[2 * e] * sbeta[j], a0, b0);
-            split_bf16(tx[2 * e + 1] * sbeta[j + 1], a1, b1);
-            h1[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
-            l1[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
-            split_bf16(tx[2 * e] * secol[j], a0, b0);
-            split_bf16(tx[2 * e + 1] * secol[j + 1], a1, b1);
-            h2[e] = (uint32_t)a0 | ((uint32_t)a1 << 16);
-            l2[e] = (uint32_t)b0 | ((uint32_t)b1 << 16);
-          }
-          const int chunk = ((hf * 4 + q8) ^ (c & 7)) << 4;
-          *reinterpret_cast<uint4*>(i1 + chunk) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
-          *reinterpret_cast<uint4*>(i1 + 8192 + chunk) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
-          *reinterpret_cast<uint4*>(i2 + chunk) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
-          *reinterpret_cast<uint4*>(i2 + 8192 + chunk) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(img_ready);
-        if (tid < 64) p.gcum[hc * kTC + i] = g_i;
-        if (tid == 0) stamp(it, 8);
-      }
-      mbar_wait(bc_done, up);
-      tc_fence_after_sync();
-      if (tid == 0) stamp(it, 9);
-      // hand the partner its missing part: lanes 0-63 hold the hi parts, lanes 64-127 the lo parts
-      {
-        float* xdst = (tid < 64 ? sXC : sXB) + i * kPLdX;
-        const uint32_t col = tid < 64 ? kColC : kColB;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t a[32];
-          tmem_ld32(lane_addr + col + q * 32, a);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            *reinterpret_cast<float4*>(xdst + q * 32 + 4 * j4) =
-                make_float4(__uint_as_float(a[4 * j4]), __uint_as_float(a[4 * j4 + 1]), __uint_as_float(a[4 * j4 + 2]), __uint_as_float(a[4 * j4 + 3]));
-        }
-      }
-      named_bar_sync(2, 128);
-      if (tid < 64) {                         // vcorr row i = hi part (own lane) + lo part (partner) -> [slice][i][36]
-        const float* xsrc = sXB + i * kPLdX;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t a[32];
-          tmem_ld32(lane_addr + kColB + q * 32, a);
-          tmem_ld_wait();
-          float* dst = p.vcorr + ((hc * (kTD / kTSV) + q) * kTC + i) * kVcLd;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 o = *reinterpret_cast<const float4*>(xsrc + q * 32 + 4 * j4);
-            *reinterpret_cast<float4*>(dst + 4 * j4) =
-                make_float4(__uint_as_float(a[4 * j4]) + o.x, __uint_as_float(a[4 * j4 + 1]) + o.y, __uint_as_float(a[4 * j4 + 2]) + o.z,
-                            __uint_as_float(a[4 * j4 + 3]) + o.w);
-          }
-        }
-      } else {                                // kcd row i = hi part (partner) + lo part (own lane) -> hi/lo images
-        const float* xsrc = sXC + i * kPLdX;
-        uint8_t* img = p.kcd_img + hc * 32768 + i * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t a[32];
-          tmem_ld32(lane_addr + kColC + q * 32, a);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int jj = q8 * 8 + 2 * e;
-              const float v0 = __uint_as_float(a[jj]) + xsrc[q * 32 + jj], v1 = __uint_as_float(a[jj + 1]) + xsrc[q * 32 + jj + 1];
-              unsigned short h0, l0, h1, l1;
-              split_bf16(v0, h0, l0);
-              split_bf16(v1, h1, l1);
-              hw[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              lw[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-            }
-            const int k8 = q * 4 + q8;          // 8-element group along dk: chunk c = k8 / 8, 16-byte slot k8 % 8
-            const int off = (k8 >> 3) * 8192 + (((k8 & 7) ^ (i & 7)) << 4);
-            *reinterpret_cast<uint4*>(img + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(img + 16384 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        }
-      }
-      tc_fence_before_sync();
-      if (tid == 0) stamp(it, 10);
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
-}
-
 // --------------------------------------------------------------------------------------------------------------------
-// Chunk prepare, second version: EIGHT CUDA-core warps on one unit (thread = TMEM lane x column half, two warps per scheduler:
-// with four warps every phase ran at IPC ~0.2, profiles/r02f_*), and MMA-B/C restacked so that no partial sums have to be
-// exchanged:  D_B = [T'_hi ; T''_hi] v + [T'_lo ; T''_lo] v  (lanes 0-63 = T' v = vcorr),  D_C = the same A operands against k
+// The kernel: EIGHT CUDA-core warps on one unit (thread = TMEM lane x column half, two warps per scheduler: the first version had
+// four and every phase ran at IPC ~0.2, profiles/r02f_*), and MMA-B/C stacked so that no partial sums have to be exchanged:  D_B = [T'_hi ; T''_hi] v + [T'_lo ; T''_lo] v  (lanes 0-63 = T' v = vcorr),  D_C = the same A operands against k
 // (lanes 64-127 = T'' k = kcd).  Twice the MMAs (16 of N = 128 per unit, still a few hundred cycles), no shared-memory round trip.
 // Warp 8 = TMA producer, warp 9 = MMA issuer.
 // --------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kT3Threads, 1)
-    gdn_prepare_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+    gdn_prepare_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                           const __grid_constant__ CUtensorMap tmap_v, GdnPrepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kP2OffBar);
@@ -999,8 +612,6 @@ __global__ void __launch_bounds__(kT3Threads, 1)
     float* sA = reinterpret_cast<float*>(smem + kPOffA);
     float* sT = reinterpret_cast<float*>(smem + kPOffT);
     float* sP = reinterpret_cast<float*>(smem + kPOffP);
-    float* sXB = reinterpret_cast<float*>(smem + kPOffXB);
-    float* sXC = reinterpret_cast<float*>(smem + kPOffXC);
     float* sg = reinterpret_cast<float*>(smem + kP2OffSc);
     float* sbeta = sg + 64;
     float* secol = sg + 128;
@@ -1259,8 +870,7 @@ cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc
                                   int num_sms, cudaStream_t s) {
   static PerDeviceOnce once;
   if (const int dev = once.pending(); dev >= 0) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_prepare_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gdn_prepare_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Smem);
+    cudaError_t e = cudaFuncSetAttribute(gdn_prepare_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Smem);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
@@ -1275,10 +885,7 @@ cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc
   long long* trace = trv ? reinterpret_cast<long long*>(strtoull(trv, nullptr, 0)) : nullptr;
   GdnPrepParams p{trace, beta, g, (uint8_t*)kcd_img, (uint8_t*)intra_img, vcorr, gcum, M, n_chunks, nv, nk};
   const int n_units = nv * n_chunks;
-  const char* pv = getenv("KB2_GDN_PREPARE_VERSION");        // 1 = four core warps + exchange, 2 = eight core warps (default)
-  const int version = pv ? atoi(pv) : kDefaultPrepareVersion;
-  if (version == 1) gdn_prepare_tc_kernel<<<n_units < num_sms ? n_units : num_sms, kTThreads, kPSmem, s>>>(tq, tk, tv, p);
-  else gdn_prepare_tc2_kernel<<<n_units < num_sms ? n_units : num_sms, kT3Threads, kP2Smem, s>>>(tq, tk, tv, p);
+  gdn_prepare_tc_kernel<<<n_units < num_sms ? n_units : num_sms, kT3Threads, kP2Smem, s>>>(tq, tk, tv, p);
   return cudaGetLastError();
 }
 

@@ -50,9 +50,8 @@ print("  chunk period (cycles):", (t[1:, 0] - t[:-1, 0]).tolist())
 # ---- tcgen05 chunk-prepare: time + per-phase timeline of CTA 0 (slots: MMA thread 0 inputs landed, 1 MMA-A issued, 2 images seen,
 # 3 MMA-B/C issued; core thread 0: 4 gates scanned, 5 k.k^T seen, 6 A^T built, 7 T solved, 8 images written, 9 vcorr/kcd products seen,
 # 10 outputs stored; version 2 only: 11 T zeroed, 12 diagonal 16x16 blocks inverted, 13 level 1 done)
-for mode, version in (("1", "1"), ("0", "1"), ("0", "2")):
+for mode in ("1", "0"):
     os.environ["KB2_GDN_PREPARE_MMA_SYNC"] = mode
-    os.environ["KB2_GDN_PREPARE_VERSION"] = version
     for _ in range(2):
         lay.reset_state()
         lay.forward(x)
@@ -62,7 +61,7 @@ for mode, version in (("1", "1"), ("0", "1"), ("0", "2")):
         lay.forward(x)
     prof = capi.kernel_profile_collect()
     capi.kernel_profile(False)
-    print(("mma.sync" if mode == "1" else f"tcgen05 v{version}") + " prepare: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in prof.items() if "prepare" in n))
+    print(("mma.sync" if mode == "1" else "tcgen05") + " prepare: " + ", ".join(f"{n} {t / c * 1e3:.1f}us" for n, (t, c) in prof.items() if "prepare" in n))
     if mode == "1":
         continue
     trace = torch.zeros(8 * 16, dtype=torch.int64, device="cuda")

@@ -14,7 +14,7 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 if [ "${KB2_VALIDATE_NCU:-0}" = "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_8layers.csv \
     python bench.py --layers 8 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_l8.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dense_gemm_kernel|grouped_gemm_kernel|gdn_scan_tc_kernel|gdn_prepare_tc2_kernel|gqa_fmha_kernel" -s 40 -c 14 -f -o gpurun_out/top_kernels \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dense_gemm_kernel|grouped_gemm_kernel|gdn_scan_tc_kernel|gdn_prepare_tc_kernel|gqa_fmha_kernel" -s 40 -c 14 -f -o gpurun_out/top_kernels \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ncu -i gpurun_out/top_kernels.ncu-rep --page raw --csv > gpurun_out/top_kernels_raw.csv 2>/dev/null
 fi

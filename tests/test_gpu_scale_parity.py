@@ -251,9 +251,8 @@ def test_gdn_tcgen05_scan_matches_the_mma_sync_scan(M, monkeypatch):
     assert np.abs(res["0"][2] - res["1"][2]).max() <= 1e-4 * np.abs(res["1"][2]).max()
 
 
-@pytest.mark.parametrize("version", ["1", "2"])
-@pytest.mark.parametrize("M", [200, 1500])
-def test_gdn_tcgen05_prepare_matches_the_mma_sync_prepare(M, version, monkeypatch):
+@pytest.mark.parametrize("M", [200, 1500, 4100])
+def test_gdn_tcgen05_prepare_matches_the_mma_sync_prepare(M, monkeypatch):
     """tcgen05 chunk-prepare (explicit T = (I - A)^-1, BF16 hi/lo pairs of T times exact BF16 v / k) against the mma.sync
     prepare (blocked forward substitution on the right-hand sides), both feeding the same tcgen05 scan: fp32-grade both,
     so the carried state agrees to 1e-4 relative and the BF16 outputs to one ulp of the maximum."""
@@ -270,7 +269,6 @@ def test_gdn_tcgen05_prepare_matches_the_mma_sync_prepare(M, version, monkeypatc
                                 linear_value_head_dim=dv, linear_conv_kernel_dim=K, rms_norm_eps=1e-6)
     x1, x2 = torch.randn(M, H).to(bf).cuda(), torch.randn(M // 2 + 3, H).to(bf).cuda()
     res = {}
-    monkeypatch.setenv("KB2_GDN_PREPARE_VERSION", version)      # 1 = four core warps + exchange, 2 = eight core warps (gdn_tc.cu)
     for mode in ("1", "0"):
         monkeypatch.setenv("KB2_GDN_PREPARE_MMA_SYNC", mode)
         lay = GatedDeltaNetAttention(cfg, 0, w, "cuda:0", max_tokens=M)
