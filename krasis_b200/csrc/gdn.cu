@@ -836,9 +836,10 @@ static bool gdn_use_tc(const GdnDims& d) { return !gdn_legacy_env() && d.dk == 1
 cudaError_t launch_gdn_prepare_tc(const void* qn, const void* kn, const void* vc, const float* beta, const float* g,
                                   void* kcd_img, void* intra_img, float* vcorr, float* gcum, int M, int n_chunks, int nk, int nv,
                                   int num_sms, cudaStream_t s);
-// Which chunk-prepare feeds the tcgen05 scan.  Measured r02c (QCN layer, 8192 tokens): mma.sync 310 us, tcgen05 460 us — the
-// tcgen05 kernel is latency-bound on its per-unit phases; it stays selectable while it is being tuned:
-// KB2_GDN_PREPARE_MMA_SYNC=0 picks tcgen05, =1 mma.sync; unset -> kDefaultPrepareTc.
+// Which chunk-prepare feeds the tcgen05 scan (dk == dv == 128).  QCN layer, 8192 tokens: the mma.sync prepare of round 1 takes 332 us,
+// the tcgen05 prepare (gdn_tc.cu) 148 us after this round's work (460 us in its first version: profiles/r02c ... r02u).  The
+// mma.sync kernel stays for other head sizes and as the A/B reference of tests/test_gpu_scale_parity.py:
+// KB2_GDN_PREPARE_MMA_SYNC=1 picks it, =0 the tcgen05 kernel; unset -> kDefaultPrepareTc.
 constexpr bool kDefaultPrepareTc = true;
 static bool gdn_prepare_mma_sync_env() {
   const char* e = getenv("KB2_GDN_PREPARE_MMA_SYNC");
