@@ -171,3 +171,28 @@ def test_token_sharded_schedule_gloo(world):
     ret = mgr.dict()
     mp.spawn(_sharded_schedule_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world and max(ret.values()) < 1e-5
+
+
+def test_chunk_kv_state_view_offsets_the_live_sequence():
+    """The view a layer gets while it processes a later token chunk of the same prefill call (pipelined attention collectives):
+    seq_len is shifted, capacity requests cover the shifted range, the page table is the live sequence's."""
+    from krasis_b200.model import _ChunkKVState
+
+    class _Seq:
+        def __init__(self):
+            self.seq_len, self.asked = 48, []
+
+        def ensure_capacity(self, n):
+            self.asked.append(n)
+
+        def kv_indices(self, device):
+            return ("pages", device)
+
+    st = _Seq()
+    v = _ChunkKVState(st, 2048)
+    assert v.seq_len == 48 + 2048
+    v.ensure_capacity(1024)
+    assert st.asked == [2048 + 1024]
+    assert v.kv_indices("cuda:0") == ("pages", "cuda:0")
+    st.seq_len = 100                     # the view follows the live state
+    assert v.seq_len == 2148
