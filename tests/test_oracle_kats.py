@@ -269,3 +269,31 @@ def test_int8_linear_oracle_matches_reference_execution():
     assert np.array_equal(wq.numpy(), Gd["wq"]) and np.array_equal(ws.view(torch.int16).numpy().view(np.uint16), Gd["ws"])
     y = D.int8_linear(x, wq, ws)
     assert np.array_equal(y.view(torch.int16).numpy().view(np.uint16), Gd["y"])
+
+
+def test_division_free_row_quantisation_rule_is_exact():
+    """elementwise.cu:quant_code_rhe replaces `round_half_even(x / scale)` (weight_loader.py:25-43, 46-99) by `rint(x * (1 / scale))` and
+    takes the true division only when the product lands within 1e-3 of a half-integer.  Every step is a correctly rounded fp32
+    operation, so the rule can be checked on the CPU: it must agree with the division for every input, including values constructed to sit
+    on rounding boundaries."""
+    rng = np.random.default_rng(5)
+    f32 = np.float32
+    scales = np.concatenate([(rng.random(4000).astype(f32) * f32(3.0) + f32(1e-3)) / f32(127.0),
+                             (np.arange(1, 2049, dtype=np.float32) / f32(64.0)) / f32(127.0)]).astype(f32)   # row maxima on the bf16 grid too
+    worst = 0.0
+    for s in scales:
+        mx = s * f32(127.0)
+        x = (rng.standard_normal(512).astype(f32) * mx / f32(2.5)).astype(f32)
+        x = np.clip(x, -mx, mx)
+        bits = x.view(np.uint32)
+        x = ((bits + np.uint32(0x7FFF) + ((bits >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)).view(f32)   # bf16-valued inputs
+        k = rng.integers(-127, 127, 64).astype(f32) + f32(0.5)                                                    # half-integer targets
+        x = np.concatenate([x, (k * s).astype(f32), np.nextafter((k * s).astype(f32), f32(np.inf)), np.nextafter((k * s).astype(f32), f32(-np.inf))])
+        want = np.rint((x / s).astype(f32))
+        y = (x * (f32(1.0) / s)).astype(f32)
+        r = np.rint(y)
+        near = np.abs(np.abs(y - r) - f32(0.5)) < f32(1e-3)
+        got = np.where(near, want, r)
+        assert np.array_equal(got, want), (s, x[got != want][:4])
+        worst = max(worst, float(np.abs(y - (x / s).astype(f32)).max()))
+    assert worst < 1e-4          # the margin the 1e-3 window relies on
