@@ -119,6 +119,37 @@ def gdn_chunked(q, k, v, beta, g, state=None, chunk=64, dtype=torch.float32):
     return out, S
 
 
+def gdn_segment_affine(k, v, beta, g, chunk=64, dtype=torch.float64):
+    """The state update of gdn_chunked over a whole token segment as ONE affine map  S_end = P S_start + Q  per head
+    (P [nv, dk, dk], Q [nv, dk, dv]).  Per chunk  S' = e^{g_last} S + Kd^T (vcorr - kcd S)  with Kd = k e^{g_last - gcum}, so
+    P_c = e^{g_last} I - Kd^T kcd and Q_c = Kd^T vcorr; chunks compose as (P_b, Q_b) o (P_a, Q_a) = (P_b P_a, P_b Q_a + Q_b).
+    Groundwork for a sequence-parallel scan across ranks: each rank reduces its own token segment to (P, Q)
+    without knowing the incoming state.  The segment length must be a multiple of `chunk` (segments are cut at chunk boundaries)."""
+    M, nv, dk = k.shape
+    dv = v.shape[-1]
+    assert M % chunk == 0
+    n = M // chunk
+    kc = k.to(dtype).transpose(0, 1).reshape(nv, n, chunk, dk)
+    vc = v.to(dtype).transpose(0, 1).reshape(nv, n, chunk, dv)
+    bc, gc = beta.to(dtype).t().reshape(nv, n, chunk), g.to(dtype).t().reshape(nv, n, chunk)
+    vb, kb = vc * bc[..., None], kc * bc[..., None]
+    gcum = gc.cumsum(dim=-1)
+    decay = (gcum[..., :, None] - gcum[..., None, :]).tril().exp().tril()
+    A = -(kb @ kc.transpose(-1, -2)) * decay
+    A = A.masked_fill(torch.triu(torch.ones(chunk, chunk, dtype=torch.bool), 0), 0)
+    vcorr = torch.linalg.solve_triangular(-A, vb, upper=False, unitriangular=True)
+    kcd = torch.linalg.solve_triangular(-A, kb * gcum.exp()[..., None], upper=False, unitriangular=True)
+    P = torch.eye(dk, dtype=dtype).expand(nv, dk, dk).clone()
+    Q = torch.zeros(nv, dk, dv, dtype=dtype)
+    for i in range(n):
+        gl = gcum[:, i, -1]
+        kd_t = (kc[:, i] * (gl[:, None] - gcum[:, i]).exp()[..., None]).transpose(-1, -2)          # [nv, dk, chunk]
+        Pc = torch.eye(dk, dtype=dtype)[None] * gl.exp()[:, None, None] - kd_t @ kcd[:, i]
+        Qc = kd_t @ vcorr[:, i]
+        P, Q = Pc @ P, Pc @ Q + Qc
+    return P, Q
+
+
 def gated_rmsnorm(x, gate, weight, eps):
     """linear_attention.py:987-1004 (norm in fp32 -> input dtype; gate silu in fp32 -> input dtype; product)."""
     dt = x.dtype

@@ -147,3 +147,26 @@ def test_gqa_rope_matches_reference_execution(tag):
     for name in ("q", "k"):
         x = torch.from_numpy(MLA_G[f"{tag}_{name}_in"]).to(torch.bfloat16)
         assert np.array_equal(A.apply_rope(x, cos[pos], sin[pos]).float().numpy(), MLA_G[f"{tag}_{name}_out"])
+
+
+def test_gdn_segment_state_update_is_affine_and_composes():
+    """oracle.attention.gdn_segment_affine: a token segment's effect on the recurrent state is S_end = P S_start + Q, and two
+    segments compose as (P2 P1, P2 Q1 + Q2) — checked against the sequential chunked pass with a non-zero incoming state.  This is
+    the identity a sequence-parallel scan across ranks rests on."""
+    torch.manual_seed(13)
+    M, nv, dk, dv = 256, 3, 16, 8
+    q = A.l2norm(torch.randn(M, nv, dk))
+    k = A.l2norm(torch.randn(M, nv, dk))
+    v = torch.randn(M, nv, dv)
+    beta = torch.sigmoid(torch.randn(M, nv))
+    g = -torch.rand(M, nv) * 0.3
+    S0 = torch.randn(nv, dk, dv, dtype=torch.float64) * 0.5
+    _, S_seq = A.gdn_chunked(q, k, v, beta, g, state=S0, chunk=64, dtype=torch.float64)
+    P, Q = A.gdn_segment_affine(k, v, beta, g, chunk=64)
+    assert torch.allclose(P @ S0 + Q, S_seq, rtol=1e-9, atol=1e-11)
+    h = M // 2                                                       # two "ranks", each reducing its own half without the incoming state
+    P1, Q1 = A.gdn_segment_affine(k[:h], v[:h], beta[:h], g[:h], chunk=64)
+    P2, Q2 = A.gdn_segment_affine(k[h:], v[h:], beta[h:], g[h:], chunk=64)
+    assert torch.allclose(P2 @ P1, P, rtol=1e-9, atol=1e-11) and torch.allclose(P2 @ Q1 + Q2, Q, rtol=1e-9, atol=1e-11)
+    _, S_def = A.gdn_recurrent(q, k, v, beta, g, state=S0)           # and the definitional recurrence agrees
+    assert torch.allclose(P @ S0 + Q, S_def, rtol=1e-8, atol=1e-10)
